@@ -1,0 +1,165 @@
+/* slnlp_b200.h - C ABI of the B200-native hot path of sign-language-nlp.
+ *
+ * The reference (amorim-cleison/sign-language-nlp) has no FFI of its own: its hot
+ * path is a stack of torch.nn modules called by skorch.  This
+ * header is the boundary a maintainer binds instead: every entry point names the
+ * reference call site it replaces ("bkp" = model/base/encoder_decoder_attn_bkp.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless it says
+ *     "host"; the library never allocates or frees device memory;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it
+ *     and capturable into a CUDA graph (no synchronisation, no allocation);
+ *   - return value 0 = ok, non-zero = error; slnlp_last_error_string() describes the
+ *     last error of the calling thread.  There is no CPU fallback anywhere;
+ *   - activations are fp32, row-major; "time-major" means row index t*B + b;
+ *   - RNN gate order is torch's: LSTM i,f,g,o (G=4); GRU r,z,n (G=3);
+ *   - per-layer RNN weights of the two directions are adjacent in memory:
+ *     w_ih [ndir*G*H, D], w_hh [ndir, G*H, H], b_ih / b_hh [ndir*G*H].
+ */
+#ifndef SLNLP_B200_H
+#define SLNLP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLNLP_ABI_VERSION 1
+#define SLNLP_MODE_LSTM 0
+#define SLNLP_MODE_GRU 1
+#define SLNLP_MAX_FIELDS 8
+
+typedef void* slnlp_stream_t;
+
+int slnlp_abi_version(void);
+const char* slnlp_last_error_string(void);
+/* number of SMs of the current device (grid sizing), or -1 */
+int slnlp_device_sm_count(void);
+
+/* ---- K1: phonological embedding (nn.Embedding, bkp:49,60,374-379; Transformer
+ * model/transformer.py:32-37,106-109).  One fused gather(+concat)(+scale)(+PE).
+ * idx [B,T,F] int64; field f reads table + field_off[f] (row width field_w[f]);
+ * out row (t*B+b if time_major else b*T+t) is the concat of the F rows, times
+ * `scale`, plus pe[t, :] when pe != NULL (pe is [T, sum(field_w)]).
+ * field_off / field_w / field_rows (rows of each table) are HOST arrays of length F
+ * (F <= SLNLP_MAX_FIELDS).  An index outside [0, field_rows[f]) yields a NaN row
+ * (loud, but no fault); the reference would raise an IndexError. */
+int slnlp_embed_gather_fwd(const float* table, const int64_t* idx, float* out,
+                           int B, int T, int F, const int64_t* field_off, const int* field_w,
+                           const int64_t* field_rows, int time_major, float scale,
+                           const float* pe, slnlp_stream_t stream);
+/* dtable[row] += scale * dout[...]; rows whose index == padding_idx get no gradient
+ * (nn.Embedding(padding_idx=...)); pass padding_idx = -1 for none. */
+int slnlp_embed_gather_bwd(float* dtable, const int64_t* idx, const float* dout,
+                           int B, int T, int F, const int64_t* field_off, const int* field_w,
+                           const int64_t* field_rows, int time_major, float scale,
+                           int64_t padding_idx, slnlp_stream_t stream);
+
+/* ---- K3/K6/K10 and every other dense contraction (nn.Linear call sites bkp:73-76,
+ * 193-194,246,297-299; the x*W_ih^T hoisted out of nn.LSTM/GRU, bkp:114,216).
+ * Row-major C[M,N] = op(A) op(B) + bias[N] + beta*C with fp32 FMA accumulation.
+ * op(A) is A[M,K] (transA=0) or A[K,M]^T (transA=1); likewise B[K,N] / B[N,K]^T. */
+int slnlp_gemm_f32(int transA, int transB, int M, int N, int K,
+                   const float* A, int lda, const float* B, int ldb,
+                   float* C, int ldc, const float* bias, float beta, slnlp_stream_t stream);
+/* out[c] = beta*out[c] + sum_r A[r*lda + c]   (bias gradients) */
+int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
+                     slnlp_stream_t stream);
+
+/* ---- K4/K8: one (bi)directional recurrent layer over all timesteps (nn.LSTM / nn.GRU
+ * on a packed sequence, bkp:95-100,110-123; decoder step bkp:215-216 with T=1).
+ * gates [T,B,ndir,G,H]: in = x W_ih^T + b_ih; out = activated gates (stash for bwd).
+ * State is frozen and out = 0 for t >= lengths[b]; direction 1 walks t = len-1..0.
+ * lengths may be NULL (all T).  h0/c0 [ndir,B,H] may be NULL (zeros).
+ * out [T,B,ndir*H]; stash [T,B,ndir,H] (LSTM: c_t; GRU: W_hn h + b_hn);
+ * h_final [ndir,B,H] (may be NULL).  precision: 0 = fp32 FMA, 1 = bf16 tcgen05. */
+int slnlp_rnn_layer_fwd(int mode, int precision, int T, int B, int H, int ndir,
+                        float* gates, const float* w_hh, const float* b_hh,
+                        const int64_t* lengths, const float* h0, const float* c0,
+                        float* out, float* stash, float* h_final, slnlp_stream_t stream);
+/* BPTT of the same layer.  gates: in = activated gates, out = d(x-side pre-activations)
+ * (zeros at frozen steps) ready for the hoisted dW_ih / dx GEMMs.  stash: GRU only,
+ * out = d(W_hn h + b_hn).  dout [T,B,ndir*H] / dh_final / dc_final may be NULL.
+ * dh0 / dc0 [ndir,B,H] may be NULL.  carry: workspace of 2*ndir*B*H floats. */
+int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H, int ndir,
+                        float* gates, float* stash, const float* out,
+                        const float* w_hh, const int64_t* lengths,
+                        const float* h0, const float* c0,
+                        const float* dout, const float* dh_final, const float* dc_final,
+                        float* dh0, float* dc0, float* carry, slnlp_stream_t stream);
+/* pad_packed_sequence(padding_value) on the top layer (bkp:120-123): rows t >= len
+ * of x [T,B,W] are set to `value` (1.0 going forward, 0.0 before BPTT). */
+int slnlp_pad_fill(float* x, const int64_t* lengths, int T, int B, int W, float value,
+                   slnlp_stream_t stream);
+/* concatenate_directions (bkp:155-159): [ndir,B,H] -> [B, ndir*H], and its inverse */
+int slnlp_concat_dirs(const float* h_final, float* enc_final, int B, int H, int ndir,
+                      int inverse, slnlp_stream_t stream);
+
+/* ---- elementwise pieces: tanh of the bridge (bkp:276), inter-layer dropout
+ * (nn.LSTM dropout=p, bkp:100,190), decoder input [emb_bos || ctx] (bkp:215). */
+int slnlp_tanh_fwd(float* x, int64_t n, slnlp_stream_t stream);
+/* dx = dy * (1 - y*y) in place on dy */
+int slnlp_tanh_bwd(float* dy, const float* y, int64_t n, slnlp_stream_t stream);
+/* y = x * keep/(1-p), keep ~ Philox(rng[0] seed, rng[1] step, site, i); rng is a
+ * device array of two uint64.  In-place (y == x) allowed; bwd is the same call. */
+int slnlp_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* rng,
+                  uint32_t site, slnlp_stream_t stream);
+int slnlp_rng_advance(uint64_t* rng, slnlp_stream_t stream);
+/* dst[b, 0:E] = row[E]; dst[b, E:E+W] = src[b, 0:W]  (B rows) */
+int slnlp_dec_input_fwd(const float* row, const float* src, float* dst, int B, int E, int W,
+                        slnlp_stream_t stream);
+/* drow[E] += sum_b ddst[b,0:E]; dsrc[b,:] = ddst[b,E:E+W] */
+int slnlp_dec_input_bwd(const float* ddst, float* drow, float* dsrc, int B, int E, int W,
+                        slnlp_stream_t stream);
+int slnlp_axpy(float* y, const float* x, float a, int64_t n, slnlp_stream_t stream);
+
+/* ---- K7: Bahdanau attention, one fused decode step (bkp:304-327).
+ * q [B,H] (= query_layer(h)), pk [T,B,H] (= key_layer(enc_out)), v [H] energy weights,
+ * val [T,B,W] (enc_out, W = 2H), X [B,T] int64 tokens (mask = X != pad_idx).
+ * alpha [B,T], ctx [B,W]. */
+int slnlp_attn_step_fwd(const float* q, const float* pk, const float* v, const float* val,
+                        const int64_t* X, int64_t pad_idx, int T, int B, int H, int W,
+                        float* alpha, float* ctx, slnlp_stream_t stream);
+/* dval [T,B,W] (written), dpk [T,B,H] (written), dq [B,H] (written),
+ * dv_part [B,H] per-sequence partials of d(energy weight) (reduce with colsum). */
+int slnlp_attn_step_bwd(const float* dctx, const float* q, const float* pk, const float* v,
+                        const float* val, const float* alpha, int T, int B, int H, int W,
+                        float* dval, float* dpk, float* dq, float* dv_part,
+                        slnlp_stream_t stream);
+
+/* ---- K10: generator log_softmax (bkp:75-76) + skorch CrossEntropyLoss(ignore_index)
+ * applied on the log-probs (config/*.yaml:36, helper.py:67-70).
+ * logits [B,V] -> logp [B,V]. */
+int slnlp_log_softmax_fwd(const float* logits, float* logp, int B, int V, slnlp_stream_t stream);
+/* dlogits = dlogp - exp(logp) * rowsum(dlogp) */
+int slnlp_log_softmax_bwd(const float* dlogp, const float* logp, float* dlogits, int B, int V,
+                          slnlp_stream_t stream);
+/* loss_out[0] = mean over y != ignore of -log_softmax(logp)[y]; loss_out[1] = count.
+ * dlogits (may be NULL) = d loss / d logits through both log-softmaxes. */
+int slnlp_ce_on_logp(const float* logp, const int64_t* y, int64_t ignore_index, int B, int V,
+                     float* loss_out, float* dlogits, float* row_ws, slnlp_stream_t stream);
+
+/* ---- K11/K12: GradientNormClipping -> clip_grad_norm_(max_norm, 2) (helper.py:227-229)
+ * and torch.optim.SGD(momentum, nesterov=False) (config/*.yaml:39-42), over flat buffers.
+ * partials: workspace of slnlp_sumsq_partials() floats; norm_out[0] = ||g||_2. */
+int slnlp_sumsq_partials(void);
+int slnlp_gradnorm(const float* g, int64_t n, float* partials, float* norm_out,
+                   slnlp_stream_t stream);
+/* hyper (device) = {lr, momentum, max_norm (<=0: no clipping), first_step flag}.
+ * coef = min(1, max_norm/(norm+1e-6)); buf = first ? g*coef : momentum*buf + g*coef;
+ * p -= lr*buf.  grad_scale multiplies g first (1/world_size after an all-reduce). */
+int slnlp_sgd_momentum_clip(float* p, const float* g, float* buf, int64_t n,
+                            const float* hyper, const float* norm, float grad_scale,
+                            slnlp_stream_t stream);
+
+int slnlp_relu_fwd(float* x, int64_t n, slnlp_stream_t stream);
+/* dx = dy * (y > 0) in place on dy */
+int slnlp_relu_bwd(float* dy, const float* y, int64_t n, slnlp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLNLP_B200_H */

@@ -1,0 +1,131 @@
+// K7: Bahdanau (additive) attention for the single decode step of the reference
+// (BahdanauAttention.forward, bkp:304-327): score, masked softmax and context fused
+// in one kernel per direction of autograd; warp-shuffle reductions, one CTA per
+// sequence.  HBM-bound: reads proj_key [T,B,H] and enc_out [T,B,W] exactly once.
+#include "common.cuh"
+
+namespace slnlp {
+
+// grid = B, block = 256.  Dynamic smem: T floats (scores -> alphas).
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ q,
+                                                       const float* __restrict__ pk,
+                                                       const float* __restrict__ v,
+                                                       const float* __restrict__ val,
+                                                       const int64_t* __restrict__ X, int64_t pad_idx,
+                                                       int T, int B, int H, int W,
+                                                       float* __restrict__ alpha, float* __restrict__ ctx) {
+  extern __shared__ float sc[];
+  __shared__ float red[33];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* qb = q + (int64_t)b * H;
+  // e_t = sum_h v_h tanh(q_h + pk[t,b,h]); one warp per t
+  for (int t = w; t < T; t += nw) {
+    const float* k = pk + ((int64_t)t * B + b) * H;
+    float s = 0.f;
+    for (int h = lane; h < H; h += 32) s += v[h] * tanhf(qb[h] + k[h]);
+    s = warp_sum(s);
+    if (lane == 0) sc[t] = X[(int64_t)b * T + t] == pad_idx ? -INFINITY : s;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) m = fmaxf(m, sc[t]);
+  m = block_max(m, red);
+  float sum = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float e = expf(sc[t] - m);  // every position masked: -inf - -inf = NaN, as torch
+    sc[t] = e;
+    sum += e;
+  }
+  sum = block_sum(sum, red);
+  const float inv = 1.f / sum;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float a = sc[t] * inv;
+    sc[t] = a;
+    alpha[(int64_t)b * T + t] = a;
+  }
+  __syncthreads();
+  // ctx[b,:] = sum_t alpha_t val[t,b,:]
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s = fmaf(sc[t], val[((int64_t)t * B + b) * W + c], s);
+    ctx[(int64_t)b * W + c] = s;
+  }
+}
+
+// grid = B, block = 256.  Dynamic smem: T floats (dscore).
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__ dctx,
+                                                       const float* __restrict__ q,
+                                                       const float* __restrict__ pk,
+                                                       const float* __restrict__ v,
+                                                       const float* __restrict__ val,
+                                                       const float* __restrict__ alpha, int T, int B,
+                                                       int H, int W, float* __restrict__ dval,
+                                                       float* __restrict__ dpk, float* __restrict__ dq,
+                                                       float* __restrict__ dv_part) {
+  extern __shared__ float ds[];
+  __shared__ float red[33];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* dc = dctx + (int64_t)b * W;
+  const float* al = alpha + (int64_t)b * T;
+  // dalpha_t = <dctx, val_t>;  dval_t = alpha_t * dctx
+  for (int t = w; t < T; t += nw) {
+    const int64_t o = ((int64_t)t * B + b) * W;
+    const float a = al[t];
+    float s = 0.f;
+    for (int c = lane; c < W; c += 32) {
+      const float g = dc[c];
+      s = fmaf(g, val[o + c], s);
+      dval[o + c] = a * g;
+    }
+    s = warp_sum(s);
+    if (lane == 0) ds[t] = s;
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) dot += al[t] * ds[t];
+  dot = block_sum(dot, red);
+  for (int t = threadIdx.x; t < T; t += blockDim.x) ds[t] = al[t] * (ds[t] - dot);  // dscore
+  __syncthreads();
+  // u = tanh(q + pk); dpre = dscore * v * (1-u^2); dpk = dpre; dq = sum_t dpre; dv = sum_t dscore*u
+  const float* qb = q + (int64_t)b * H;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const float qh = qb[h], vh = v[h];
+    float sq = 0.f, sv = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int64_t o = ((int64_t)t * B + b) * H + h;
+      const float u = tanhf(qh + pk[o]);
+      const float dsc = ds[t];
+      const float dp = dsc * vh * (1.f - u * u);
+      dpk[o] = dp;
+      sq += dp;
+      sv = fmaf(dsc, u, sv);
+    }
+    dq[(int64_t)b * H + h] = sq;
+    dv_part[(int64_t)b * H + h] = sv;
+  }
+}
+
+}  // namespace slnlp
+
+using namespace slnlp;
+
+extern "C" int slnlp_attn_step_fwd(const float* q, const float* pk, const float* v, const float* val,
+                                   const int64_t* X, int64_t pad_idx, int T, int B, int H, int W,
+                                   float* alpha, float* ctx, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(q && pk && v && val && X && alpha && ctx, "attn_step_fwd: null pointer");
+  SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && W > 0 && T <= 12000, "attn_step_fwd: bad shape");
+  attn_fwd_kernel<<<B, 256, T * sizeof(float), as_stream(stream)>>>(q, pk, v, val, X, pad_idx, T, B, H, W, alpha, ctx);
+  SLNLP_LAUNCH_OK("attn_step_fwd");
+  return 0;
+}
+
+extern "C" int slnlp_attn_step_bwd(const float* dctx, const float* q, const float* pk, const float* v,
+                                   const float* val, const float* alpha, int T, int B, int H, int W,
+                                   float* dval, float* dpk, float* dq, float* dv_part,
+                                   slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(dctx && q && pk && v && val && alpha && dval && dpk && dq && dv_part, "attn_step_bwd: null pointer");
+  SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && W > 0 && T <= 12000, "attn_step_bwd: bad shape");
+  attn_bwd_kernel<<<B, 256, T * sizeof(float), as_stream(stream)>>>(dctx, q, pk, v, val, alpha, T, B, H, W, dval, dpk, dq, dv_part);
+  SLNLP_LAUNCH_OK("attn_step_bwd");
+  return 0;
+}

@@ -1,0 +1,78 @@
+// Shared device/host helpers for the slnlp_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/slnlp_b200.h"
+
+namespace slnlp {
+
+// thread-local error string returned by slnlp_last_error_string()
+char* err_buf();
+int fail(const char* fmt, ...);
+
+#define SLNLP_CHECK_ARG(cond, ...)                      \
+  do {                                                  \
+    if (!(cond)) return ::slnlp::fail(__VA_ARGS__);     \
+  } while (0)
+
+// launch check: cudaGetLastError after a launch (valid during graph capture too)
+#define SLNLP_LAUNCH_OK(name)                                                         \
+  do {                                                                                \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess)                                                           \
+      return ::slnlp::fail("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+  } while (0)
+
+static inline cudaStream_t as_stream(slnlp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+int sm_count();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide reductions; `red` is >= 33 floats of shared memory; result broadcast to all threads
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+// full-precision gate nonlinearities of the fp32 path (expf/tanhf, no fast-math)
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+#endif
+
+}  // namespace slnlp

@@ -1,0 +1,576 @@
+// Error plumbing + the HBM-bound kernels of the hot path:
+//   K1 embedding gather/scatter, K10 log-softmax + CE-on-logp, K11/K12 grad-norm +
+//   clip + SGD-momentum, dropout (own Philox), pad fill, small elementwise glue.
+// Reference call sites are cited in include/slnlp_b200.h next to each entry point.
+#include "common.cuh"
+
+namespace slnlp {
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return 1;
+}
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+    cached = p.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// ------------------------------------------------------------------ embedding
+struct FieldSpec {
+  int nf;
+  int etot;
+  int64_t off[SLNLP_MAX_FIELDS];
+  int w[SLNLP_MAX_FIELDS];
+  int col[SLNLP_MAX_FIELDS];
+  int64_t rows[SLNLP_MAX_FIELDS];
+};
+
+// one warp per output row; float4 path when every field width is a multiple of 4
+template <bool VEC4>
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ table,
+                                                        const int64_t* __restrict__ idx,
+                                                        float* __restrict__ out, int B, int T,
+                                                        FieldSpec fs, int time_major, float scale,
+                                                        const float* __restrict__ pe) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (int64_t)B * T) return;
+  const int b = (int)(row / T), t = (int)(row % T);
+  const int64_t orow = time_major ? (int64_t)t * B + b : row;
+  float* o = out + orow * fs.etot;
+  const float* per = pe ? pe + (int64_t)t * fs.etot : nullptr;
+  for (int f = 0; f < fs.nf; ++f) {
+    const int64_t id = idx[row * fs.nf + f];
+    const bool ok = id >= 0 && id < fs.rows[f];
+    const float* src = table + fs.off[f] + (ok ? id : 0) * fs.w[f];
+    const int c0 = fs.col[f];
+    if (VEC4) {
+      for (int e = lane * 4; e < fs.w[f]; e += 128) {
+        float4 v = ok ? __ldg(reinterpret_cast<const float4*>(src + e))
+                      : make_float4(NAN, NAN, NAN, NAN);
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        if (per) {
+          const float4 p = __ldg(reinterpret_cast<const float4*>(per + c0 + e));
+          v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+        *reinterpret_cast<float4*>(o + c0 + e) = v;
+      }
+    } else {
+      for (int e = lane; e < fs.w[f]; e += 32) {
+        float v = ok ? __ldg(src + e) * scale : NAN;
+        if (per) v += __ldg(per + c0 + e);
+        o[c0 + e] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) embed_bwd_kernel(float* __restrict__ dtable,
+                                                        const int64_t* __restrict__ idx,
+                                                        const float* __restrict__ dout, int B, int T,
+                                                        FieldSpec fs, int time_major, float scale,
+                                                        int64_t padding_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (int64_t)B * T) return;
+  const int b = (int)(row / T), t = (int)(row % T);
+  const int64_t orow = time_major ? (int64_t)t * B + b : row;
+  const float* g = dout + orow * fs.etot;
+  for (int f = 0; f < fs.nf; ++f) {
+    const int64_t id = idx[row * fs.nf + f];
+    if (id == padding_idx || id < 0 || id >= fs.rows[f]) continue;
+    float* dst = dtable + fs.off[f] + id * fs.w[f];
+    for (int e = lane; e < fs.w[f]; e += 32) atomicAdd(dst + e, scale * g[fs.col[f] + e]);
+  }
+}
+
+static int make_fields(FieldSpec& fs, int F, const int64_t* off, const int* w, const int64_t* rows) {
+  SLNLP_CHECK_ARG(F >= 1 && F <= SLNLP_MAX_FIELDS, "embed: F=%d out of range", F);
+  fs.nf = F;
+  fs.etot = 0;
+  for (int f = 0; f < F; ++f) {
+    SLNLP_CHECK_ARG(w[f] > 0 && rows[f] > 0, "embed: bad field %d", f);
+    fs.off[f] = off[f];
+    fs.w[f] = w[f];
+    fs.rows[f] = rows[f];
+    fs.col[f] = fs.etot;
+    fs.etot += w[f];
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ log-softmax / CE
+__global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* __restrict__ x,
+                                                              float* __restrict__ y, int V) {
+  __shared__ float red[33];
+  const float* xr = x + (int64_t)blockIdx.x * V;
+  float* yr = y + (int64_t)blockIdx.x * V;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, xr[v]);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(xr[v] - m);
+  s = block_sum(s, red);
+  const float lse = m + logf(s);
+  for (int v = threadIdx.x; v < V; v += blockDim.x) yr[v] = xr[v] - lse;
+}
+
+__global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __restrict__ dy,
+                                                              const float* __restrict__ y,
+                                                              float* __restrict__ dx, int V) {
+  __shared__ float red[33];
+  const int64_t o = (int64_t)blockIdx.x * V;
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) s += dy[o + v];
+  s = block_sum(s, red);
+  for (int v = threadIdx.x; v < V; v += blockDim.x) dx[o + v] = dy[o + v] - expf(y[o + v]) * s;
+}
+
+// row_ws: [0,B) row loss, [B,2B) valid flag, [2B,3B) second logsumexp
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ logp,
+                                                      const int64_t* __restrict__ y,
+                                                      int64_t ignore, int B, int V,
+                                                      float* __restrict__ row_ws) {
+  __shared__ float red[33];
+  const int b = blockIdx.x;
+  const float* r = logp + (int64_t)b * V;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, r[v]);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(r[v] - m);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float lse = m + logf(s);
+    const int64_t yb = y[b];
+    const bool valid = yb != ignore && yb >= 0 && yb < V;
+    row_ws[b] = valid ? -(r[yb] - lse) : 0.f;
+    row_ws[B + b] = valid ? 1.f : 0.f;
+    row_ws[2 * B + b] = lse;
+  }
+}
+__global__ void __launch_bounds__(256) ce_reduce_kernel(const float* __restrict__ row_ws, int B,
+                                                        float* __restrict__ loss_out) {
+  __shared__ float red[33];
+  float s = 0.f, c = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    s += row_ws[b];
+    c += row_ws[B + b];
+  }
+  s = block_sum(s, red);
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) {
+    loss_out[0] = s / c;  // 0/0 = NaN when every target is ignored, as torch
+    loss_out[1] = c;
+  }
+}
+__global__ void __launch_bounds__(256) ce_grad_kernel(const float* __restrict__ logp,
+                                                      const int64_t* __restrict__ y, int B, int V,
+                                                      const float* __restrict__ row_ws,
+                                                      const float* __restrict__ loss_out,
+                                                      float* __restrict__ dlogits) {
+  const int b = blockIdx.x;
+  const float valid = row_ws[B + b], lse = row_ws[2 * B + b];
+  const float inv = valid / loss_out[1];
+  const int64_t yb = y[b];
+  const int64_t o = (int64_t)b * V;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    // d/dlogp = softmax(logp) - onehot; through log_softmax(logits) the rowsum term is
+    // (1 - 1) = 0, so the same expression is d/dlogits.
+    float g = expf(logp[o + v] - lse) - (v == yb ? 1.f : 0.f);
+    dlogits[o + v] = valid != 0.f ? g * inv : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ grad norm + clip + SGD
+constexpr int kSumsqBlocks = 1024;
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, int64_t n,
+                                                            float* __restrict__ partials) {
+  __shared__ float red[33];
+  float s = 0.f;
+  const int64_t n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(g4 + i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s += g[i] * g[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partials, int np,
+                                                          float* __restrict__ norm_out) {
+  __shared__ double redd[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s += (double)partials[i];
+  redd[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) redd[threadIdx.x] += redd[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) norm_out[0] = (float)sqrt(redd[0]);
+}
+
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                  float* __restrict__ buf, int64_t n,
+                                                  const float* __restrict__ hyper,
+                                                  const float* __restrict__ norm, float grad_scale) {
+  const float lr = hyper[0], mom = hyper[1], max_norm = hyper[2];
+  const bool first = hyper[3] != 0.f;
+  float coef = grad_scale;
+  if (max_norm > 0.f && norm) coef *= fminf(1.f, max_norm / (norm[0] * grad_scale + 1e-6f));
+  const int64_t n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* b4 = reinterpret_cast<float4*>(buf);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 gv = __ldg(g4 + i);
+    float4 bv = b4[i], pv = p4[i];
+    bv.x = first ? gv.x * coef : mom * bv.x + gv.x * coef;
+    bv.y = first ? gv.y * coef : mom * bv.y + gv.y * coef;
+    bv.z = first ? gv.z * coef : mom * bv.z + gv.z * coef;
+    bv.w = first ? gv.w * coef : mom * bv.w + gv.w * coef;
+    pv.x -= lr * bv.x; pv.y -= lr * bv.y; pv.z -= lr * bv.z; pv.w -= lr * bv.w;
+    b4[i] = bv;
+    p4[i] = pv;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      const float gv = g[i] * coef;
+      const float bv = first ? gv : mom * buf[i] + gv;
+      buf[i] = bv;
+      p[i] -= lr * bv;
+    }
+}
+
+// ------------------------------------------------------------------ dropout (Philox4x32-10)
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x,
+                                                      float* __restrict__ y, int64_t n, float p,
+                                                      const uint64_t* __restrict__ rng, uint32_t site) {
+  const uint64_t seed = rng[0], step = rng[1];
+  const float keep = 1.f - p, inv = 1.f / (1.f - p);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32) ^ (site * 0x9E3779B9u), (uint32_t)step,
+                     (uint32_t)(step >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = q * 4 + j;
+      if (i < n) {
+        const float u = (float)(c[j] >> 8) * (1.0f / 16777216.0f);
+        y[i] = u < keep ? x[i] * inv : 0.f;
+      }
+    }
+  }
+}
+__global__ void rng_advance_kernel(uint64_t* rng) { rng[1] += 1; }
+
+// ------------------------------------------------------------------ small glue
+__global__ void __launch_bounds__(256) pad_fill_kernel(float* __restrict__ x,
+                                                       const int64_t* __restrict__ lengths, int T,
+                                                       int B, int W, float value) {
+  const int row = blockIdx.x;  // t*B + b
+  const int t = row / B, b = row % B;
+  if (t < lengths[b]) return;
+  float* r = x + (int64_t)row * W;
+  for (int e = threadIdx.x; e < W; e += blockDim.x) r[e] = value;
+}
+__global__ void __launch_bounds__(256) concat_dirs_kernel(const float* __restrict__ src,
+                                                          float* __restrict__ dst, int B, int H,
+                                                          int ndir, int inverse) {
+  const int64_t n = (int64_t)ndir * B * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % H);
+    const int b = (int)((i / H) % B);
+    const int d = (int)(i / ((int64_t)H * B));
+    const int64_t j = ((int64_t)b * ndir + d) * H + k;  // [B, ndir*H]
+    if (inverse) dst[i] = src[j]; else dst[j] = src[i];
+  }
+}
+__global__ void __launch_bounds__(256) tanh_fwd_kernel(float* x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = tanhf(x[i]);
+}
+__global__ void __launch_bounds__(256) tanh_bwd_kernel(float* dy, const float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dy[i] *= 1.f - y[i] * y[i];
+}
+__global__ void __launch_bounds__(256) relu_fwd_kernel(float* x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = fmaxf(x[i], 0.f);
+}
+__global__ void __launch_bounds__(256) relu_bwd_kernel(float* dy, const float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dy[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+__global__ void __launch_bounds__(256) axpy_kernel(float* y, const float* __restrict__ x, float a, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+__global__ void __launch_bounds__(256) dec_input_fwd_kernel(const float* __restrict__ row,
+                                                            const float* __restrict__ src,
+                                                            float* __restrict__ dst, int B, int E, int W) {
+  const int b = blockIdx.x;
+  for (int e = threadIdx.x; e < E + W; e += blockDim.x)
+    dst[(int64_t)b * (E + W) + e] = e < E ? row[e] : src[(int64_t)b * W + e - E];
+}
+// grid = ceil((E+W)/256) blocks; column sums over b for the first E columns (deterministic)
+__global__ void __launch_bounds__(256) dec_input_bwd_kernel(const float* __restrict__ ddst,
+                                                            float* __restrict__ drow,
+                                                            float* __restrict__ dsrc, int B, int E, int W) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E + W) return;
+  if (e < E) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += ddst[(int64_t)b * (E + W) + e];
+    drow[e] += s;
+  } else {
+    for (int b = 0; b < B; ++b) dsrc[(int64_t)b * W + e - E] = ddst[(int64_t)b * (E + W) + e];
+  }
+}
+// out[c] = beta*out[c] + sum_r A[r,c]; one thread column per 32-row slab, deterministic
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int rows, int cols,
+                                                     int lda, float* __restrict__ out, float beta) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = w; r < rows; r += 8) s += A[(int64_t)r * lda + c];
+  sm[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    out[c] = (beta == 0.f ? 0.f : beta * out[c]) + t;
+  }
+}
+
+static inline int ew_grid(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace slnlp
+
+using namespace slnlp;
+
+extern "C" {
+
+int slnlp_abi_version(void) { return SLNLP_ABI_VERSION; }
+const char* slnlp_last_error_string(void) { return err_buf(); }
+int slnlp_device_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return n;
+}
+
+int slnlp_embed_gather_fwd(const float* table, const int64_t* idx, float* out, int B, int T, int F,
+                           const int64_t* field_off, const int* field_w, const int64_t* field_rows,
+                           int time_major, float scale, const float* pe, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(table && idx && out && B > 0 && T > 0, "embed_gather_fwd: bad arguments");
+  FieldSpec fs;
+  if (make_fields(fs, F, field_off, field_w, field_rows)) return 1;
+  bool vec = (fs.etot % 4 == 0) && ((uintptr_t)table % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+             (!pe || (uintptr_t)pe % 16 == 0);
+  for (int f = 0; f < F; ++f) vec = vec && fs.w[f] % 4 == 0 && fs.off[f] % 4 == 0;
+  const int grid = ceil_div((int64_t)B * T, 8);
+  if (vec)
+    embed_fwd_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(table, idx, out, B, T, fs, time_major, scale, pe);
+  else
+    embed_fwd_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(table, idx, out, B, T, fs, time_major, scale, pe);
+  SLNLP_LAUNCH_OK("embed_gather_fwd");
+  return 0;
+}
+
+int slnlp_embed_gather_bwd(float* dtable, const int64_t* idx, const float* dout, int B, int T, int F,
+                           const int64_t* field_off, const int* field_w, const int64_t* field_rows,
+                           int time_major, float scale, int64_t padding_idx, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(dtable && idx && dout && B > 0 && T > 0, "embed_gather_bwd: bad arguments");
+  FieldSpec fs;
+  if (make_fields(fs, F, field_off, field_w, field_rows)) return 1;
+  embed_bwd_kernel<<<ceil_div((int64_t)B * T, 8), 256, 0, as_stream(stream)>>>(
+      dtable, idx, dout, B, T, fs, time_major, scale, padding_idx);
+  SLNLP_LAUNCH_OK("embed_gather_bwd");
+  return 0;
+}
+
+int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
+                     slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(A && out && rows >= 0 && cols > 0 && lda >= cols, "colsum: bad arguments");
+  colsum_kernel<<<ceil_div(cols, 32), 256, 0, as_stream(stream)>>>(A, rows, cols, lda, out, beta);
+  SLNLP_LAUNCH_OK("colsum");
+  return 0;
+}
+
+int slnlp_pad_fill(float* x, const int64_t* lengths, int T, int B, int W, float value,
+                   slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(x && lengths && T > 0 && B > 0 && W > 0, "pad_fill: bad arguments");
+  pad_fill_kernel<<<T * B, 128, 0, as_stream(stream)>>>(x, lengths, T, B, W, value);
+  SLNLP_LAUNCH_OK("pad_fill");
+  return 0;
+}
+
+int slnlp_concat_dirs(const float* src, float* dst, int B, int H, int ndir, int inverse,
+                      slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(src && dst && B > 0 && H > 0 && ndir > 0, "concat_dirs: bad arguments");
+  concat_dirs_kernel<<<ew_grid((int64_t)ndir * B * H), 256, 0, as_stream(stream)>>>(src, dst, B, H, ndir, inverse);
+  SLNLP_LAUNCH_OK("concat_dirs");
+  return 0;
+}
+
+int slnlp_tanh_fwd(float* x, int64_t n, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(x && n >= 0, "tanh_fwd: bad arguments");
+  if (n == 0) return 0;
+  tanh_fwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, n);
+  SLNLP_LAUNCH_OK("tanh_fwd");
+  return 0;
+}
+int slnlp_tanh_bwd(float* dy, const float* y, int64_t n, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(dy && y && n >= 0, "tanh_bwd: bad arguments");
+  if (n == 0) return 0;
+  tanh_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(dy, y, n);
+  SLNLP_LAUNCH_OK("tanh_bwd");
+  return 0;
+}
+int slnlp_relu_fwd(float* x, int64_t n, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(x && n >= 0, "relu_fwd: bad arguments");
+  if (n == 0) return 0;
+  relu_fwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, n);
+  SLNLP_LAUNCH_OK("relu_fwd");
+  return 0;
+}
+int slnlp_relu_bwd(float* dy, const float* y, int64_t n, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(dy && y && n >= 0, "relu_bwd: bad arguments");
+  if (n == 0) return 0;
+  relu_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(dy, y, n);
+  SLNLP_LAUNCH_OK("relu_bwd");
+  return 0;
+}
+int slnlp_axpy(float* y, const float* x, float a, int64_t n, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(y && x && n >= 0, "axpy: bad arguments");
+  if (n == 0) return 0;
+  axpy_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(y, x, a, n);
+  SLNLP_LAUNCH_OK("axpy");
+  return 0;
+}
+int slnlp_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* rng, uint32_t site,
+                  slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(x && y && rng && n >= 0 && p >= 0.f && p < 1.f, "dropout: bad arguments");
+  if (n == 0) return 0;
+  dropout_kernel<<<ew_grid((n + 3) / 4), 256, 0, as_stream(stream)>>>(x, y, n, p, rng, site);
+  SLNLP_LAUNCH_OK("dropout");
+  return 0;
+}
+int slnlp_rng_advance(uint64_t* rng, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(rng, "rng_advance: null");
+  rng_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(rng);
+  SLNLP_LAUNCH_OK("rng_advance");
+  return 0;
+}
+int slnlp_dec_input_fwd(const float* row, const float* src, float* dst, int B, int E, int W,
+                        slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(row && src && dst && B > 0 && E > 0 && W > 0, "dec_input_fwd: bad arguments");
+  dec_input_fwd_kernel<<<B, 256, 0, as_stream(stream)>>>(row, src, dst, B, E, W);
+  SLNLP_LAUNCH_OK("dec_input_fwd");
+  return 0;
+}
+int slnlp_dec_input_bwd(const float* ddst, float* drow, float* dsrc, int B, int E, int W,
+                        slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(ddst && drow && dsrc && B > 0 && E > 0 && W > 0, "dec_input_bwd: bad arguments");
+  dec_input_bwd_kernel<<<ceil_div(E + W, 256), 256, 0, as_stream(stream)>>>(ddst, drow, dsrc, B, E, W);
+  SLNLP_LAUNCH_OK("dec_input_bwd");
+  return 0;
+}
+
+int slnlp_log_softmax_fwd(const float* logits, float* logp, int B, int V, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(logits && logp && B > 0 && V > 0, "log_softmax_fwd: bad arguments");
+  log_softmax_fwd_kernel<<<B, 256, 0, as_stream(stream)>>>(logits, logp, V);
+  SLNLP_LAUNCH_OK("log_softmax_fwd");
+  return 0;
+}
+int slnlp_log_softmax_bwd(const float* dlogp, const float* logp, float* dlogits, int B, int V,
+                          slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(dlogp && logp && dlogits && B > 0 && V > 0, "log_softmax_bwd: bad arguments");
+  log_softmax_bwd_kernel<<<B, 256, 0, as_stream(stream)>>>(dlogp, logp, dlogits, V);
+  SLNLP_LAUNCH_OK("log_softmax_bwd");
+  return 0;
+}
+int slnlp_ce_on_logp(const float* logp, const int64_t* y, int64_t ignore_index, int B, int V,
+                     float* loss_out, float* dlogits, float* row_ws, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(logp && y && loss_out && row_ws && B > 0 && V > 0, "ce_on_logp: bad arguments");
+  ce_rows_kernel<<<B, 256, 0, as_stream(stream)>>>(logp, y, ignore_index, B, V, row_ws);
+  ce_reduce_kernel<<<1, 256, 0, as_stream(stream)>>>(row_ws, B, loss_out);
+  if (dlogits) ce_grad_kernel<<<B, 256, 0, as_stream(stream)>>>(logp, y, B, V, row_ws, loss_out, dlogits);
+  SLNLP_LAUNCH_OK("ce_on_logp");
+  return 0;
+}
+
+int slnlp_sumsq_partials(void) { return kSumsqBlocks; }
+int slnlp_gradnorm(const float* g, int64_t n, float* partials, float* norm_out, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(g && partials && norm_out && n > 0, "gradnorm: bad arguments");
+  SLNLP_CHECK_ARG((uintptr_t)g % 16 == 0, "gradnorm: g must be 16-byte aligned");
+  int64_t want = (n / 4 + 255) / 256;
+  int grid = (int)(want < 1 ? 1 : (want > kSumsqBlocks ? kSumsqBlocks : want));
+  sumsq_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, n, partials);
+  sumsq_final_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, grid, norm_out);
+  SLNLP_LAUNCH_OK("gradnorm");
+  return 0;
+}
+int slnlp_sgd_momentum_clip(float* p, const float* g, float* buf, int64_t n, const float* hyper,
+                            const float* norm, float grad_scale, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(p && g && buf && hyper && n > 0, "sgd_momentum_clip: bad arguments");
+  SLNLP_CHECK_ARG(((uintptr_t)p | (uintptr_t)g | (uintptr_t)buf) % 16 == 0,
+                  "sgd_momentum_clip: buffers must be 16-byte aligned");
+  int64_t want = (n / 4 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  sgd_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, g, buf, n, hyper, norm, grad_scale);
+  SLNLP_LAUNCH_OK("sgd_momentum_clip");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,626 @@
+"""B200 host side of the RNN encoder-decoder-attention classifiers.
+
+Mirrors ``EncoderDecoderAttnBaseBkp`` of the reference
+(model/base/encoder_decoder_attn_bkp.py:330-413, "bkp" below): same constructor
+keywords, ``.to(device)``, ``forward(X, y, lengths) -> [B, V_tgt]`` log-probs, same
+``state_dict`` names and shapes, same default initialisation stream (so the same
+``torch.manual_seed`` gives the same initial weights).  All model math runs in the
+hand-written sm_100a kernels behind the C ABI (include/slnlp_b200.h); PyTorch only
+owns memory, streams and autograd bookkeeping.  CPU tensors raise - no fallback.
+
+Two ways in:
+  * ``module(X=..., y=..., lengths=...)``: an autograd.Function, so stock skorch /
+    ``loss.backward()`` / ``clip_grad_norm_`` / ``torch.optim.SGD`` work unchanged;
+  * ``FusedTrainStep``: the whole skorch train step (forward, CE on the log-probs,
+    backward, global-norm clip 0.5, SGD-momentum) as one CUDA graph replay.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, lib
+
+PAD_WORD, BOS_WORD = "<pad>", "<bos>"  # dataset/constant/tokens.py:1,4
+MODE = {"lstm": 0, "gru": 1}
+GATES = {"lstm": 4, "gru": 3}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _align4(n):
+    return (n + 3) & ~3
+
+
+class _Box(nn.Module):
+    """Plain container so parameters get the reference's dotted names."""
+
+
+class RnnEncDecB200(nn.Module):
+    MAX_OUTPUT_LEN = 1  # bkp:332
+
+    def __init__(self, src_vocab, tgt_vocab, batch_first, rnn_type, embedding_size=256,
+                 hidden_size=512, num_layers=1, dropout=0.1, precision="fp32", **kwargs):
+        super().__init__()
+        assert rnn_type in MODE, "Invalid `rnn_type`."          # bkp:347
+        assert precision in ("fp32", "bf16")
+        self.batch_first = batch_first
+        self.src_vocab, self.tgt_vocab = src_vocab, tgt_vocab
+        self.rnn_type, self.precision = rnn_type, precision
+        self.E, self.H, self.L = int(embedding_size), int(hidden_size), int(num_layers)
+        self.G = GATES[rnn_type]
+        self.p_drop = float(dropout)
+        self.p_rnn = float(dropout) if self.L > 1 else 0.0       # bkp:100,190
+        self.src_pad = src_vocab.stoi[PAD_WORD]                  # model/util/util.py:5-6
+        self.tgt_pad = tgt_vocab.stoi[PAD_WORD]
+        self.bos_idx = tgt_vocab.stoi[BOS_WORD]                  # util.py:8-9 (-> unk = 0)
+        self.V_src, self.V_tgt = len(src_vocab), len(tgt_vocab)
+        self.device = kwargs.get("device", None)
+        self.validate_inputs = True
+        self._build_parameters()
+        self._ws_cache: Dict = {}
+        self._rng = None
+        self.seed = int(kwargs.get("seed", torch.initial_seed() & 0x7FFFFFFF))
+
+    # ------------------------------------------------------------------ parameters
+    def _build_parameters(self):
+        E, H, L, G = self.E, self.H, self.L, self.G
+        rnn_cls = nn.LSTM if self.rnn_type == "lstm" else nn.GRU
+        # default initialisers drawn in the reference's construction order (bkp:362-381):
+        # Encoder.rnn, attention (key, query, energy), Decoder.rnn, bridge, pre_output,
+        # src Embedding, trg Embedding, Generator.  torch.nn is used for init only.
+        t_enc = rnn_cls(E, H, L, batch_first=True, bidirectional=True)
+        t_key = nn.Linear(2 * H, H, bias=False)
+        t_query = nn.Linear(H, H, bias=False)
+        t_energy = nn.Linear(H, 1, bias=False)
+        t_dec = rnn_cls(E + 2 * H, H, L, batch_first=True)
+        t_bridge = nn.Linear(2 * H, H, bias=True)
+        t_pre = nn.Linear(3 * H + E, H, bias=False)
+        t_src = nn.Embedding(self.V_src, E, padding_idx=self.src_pad)
+        t_trg = nn.Embedding(self.V_tgt, E, padding_idx=self.tgt_pad)
+        t_gen = nn.Linear(H, self.V_tgt, bias=False)
+
+        # flat layout: per layer the two directions of each tensor are adjacent
+        segs: List = []  # (name, init tensor)
+        for l in range(L):
+            for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                for suf in ("", "_reverse"):
+                    segs.append((f"model.encoder.rnn.{kind}_l{l}{suf}", getattr(t_enc, f"{kind}_l{l}{suf}")))
+        segs += [("model.decoder.attention.key_layer.weight", t_key.weight),
+                 ("model.decoder.attention.query_layer.weight", t_query.weight),
+                 ("model.decoder.attention.energy_layer.weight", t_energy.weight)]
+        for l in range(L):
+            for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                segs.append((f"model.decoder.rnn.{kind}_l{l}", getattr(t_dec, f"{kind}_l{l}")))
+        segs += [("model.decoder.bridge.weight", t_bridge.weight),
+                 ("model.decoder.bridge.bias", t_bridge.bias),
+                 ("model.decoder.pre_output_layer.weight", t_pre.weight),
+                 ("model.src_embed.weight", t_src.weight),
+                 ("model.trg_embed.weight", t_trg.weight),
+                 ("model.generator.proj.weight", t_gen.weight)]
+        self._names = [n for n, _ in segs]
+        self._shapes = {n: tuple(t.shape) for n, t in segs}
+        self._off: Dict[str, int] = {}
+        off = 0
+        for i, (n, t) in enumerate(segs):
+            # keep fwd/_reverse pairs contiguous; align everything else to 16 bytes
+            if not n.endswith("_reverse"):
+                off = _align4(off)
+            self._off[n] = off
+            off += t.numel()
+        self._numel = _align4(off)
+        flat = torch.zeros(self._numel)
+        for n, t in segs:
+            flat[self._off[n]:self._off[n] + t.numel()] = t.detach().reshape(-1)
+        self._flat = flat
+        self._gflat = None
+        # module tree with the reference's names (state_dict / Checkpoint compatibility)
+        self.model = _Box()
+        self._params: Dict[str, nn.Parameter] = {}
+        # registration order = the reference's named_parameters() order
+        order = []
+        for l in range(L):
+            for suf in ("", "_reverse"):
+                for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                    order.append(f"model.encoder.rnn.{kind}_l{l}{suf}")
+        order += [n for n in self._names if n.startswith("model.decoder.attention")]
+        order += [n for n in self._names if n.startswith("model.decoder.rnn")]
+        order += ["model.decoder.bridge.weight", "model.decoder.bridge.bias",
+                  "model.decoder.pre_output_layer.weight", "model.src_embed.weight",
+                  "model.trg_embed.weight", "model.generator.proj.weight"]
+        for n in order:
+            parts = n.split(".")
+            box = self
+            for p in parts[:-1]:
+                if not hasattr(box, p):
+                    setattr(box, p, _Box())
+                box = getattr(box, p)
+            prm = nn.Parameter(self._view(self._flat, n))
+            box.register_parameter(parts[-1], prm)
+            self._params[n] = prm
+
+    def _view(self, flat, name):
+        shape = self._shapes[name]
+        n = math.prod(shape)
+        return flat[self._off[name]:self._off[name] + n].view(shape)
+
+    def _apply(self, fn, recurse=True):
+        # keep every parameter a view of ONE flat buffer across .to()/.cuda()/.float()
+        self._flat = fn(self._flat)
+        for n, prm in self._params.items():
+            prm.data = self._view(self._flat, n)
+            prm.grad = None
+        self._gflat = None
+        self._ws_cache = {}
+        self._rng = None
+        return self
+
+    def to(self, device=None, *args, **kwargs):                  # bkp:383-386
+        out = super().to(device, *args, **kwargs)
+        if device is not None:
+            self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        return out
+
+    def _ensure_flat(self):
+        """Re-flatten if some outside code replaced parameter storage."""
+        base = self._flat.data_ptr()
+        ok = all(p.data_ptr() == base + 4 * self._off[n] and p.device == self._flat.device
+                 for n, p in self._params.items())
+        if not ok:
+            dev = next(iter(self._params.values())).device
+            flat = torch.zeros(self._numel, device=dev)
+            for n, p in self._params.items():
+                flat[self._off[n]:self._off[n] + p.numel()] = p.data.reshape(-1).to(dev)
+            self._flat = flat
+            for n, p in self._params.items():
+                p.data = self._view(flat, n)
+            self._gflat = None
+        if not self._flat.is_cuda:
+            raise RuntimeError("slnlp_b200 modules compute on CUDA only (no CPU fallback): "
+                               "call .to('cuda') first")
+
+    def flat_parameters(self):
+        self._ensure_flat()
+        return self._flat
+
+    def flat_grads(self):
+        """Flat gradient buffer; ``p.grad`` of every live parameter is a view of it."""
+        self._ensure_flat()
+        if self._gflat is None or self._gflat.device != self._flat.device:
+            self._gflat = torch.zeros_like(self._flat)
+        for n, p in self._params.items():
+            if n == "model.decoder.pre_output_layer.weight":
+                continue  # dead branch: grad stays None as in the reference
+            want = self._view(self._gflat, n)
+            if p.grad is None or p.grad.data_ptr() != want.data_ptr():
+                p.grad = want
+        return self._gflat
+
+    def _ptr(self, name, flat=None):
+        flat = self._flat if flat is None else flat
+        return flat.data_ptr() + 4 * self._off[name]
+
+    def _rng_state(self):
+        if self._rng is None or self._rng.device != self._flat.device:
+            self._rng = torch.tensor([self.seed, 0], dtype=torch.int64, device=self._flat.device)
+        return self._rng
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, B, T, train, fresh=False, bwd=None):
+        bwd = train if bwd is None else bwd
+        key = (B, T, train, bwd)
+        if not fresh and key in self._ws_cache:
+            return self._ws_cache[key]
+        ws = _Workspace(self, B, T, train, bwd)
+        if not fresh:
+            self._ws_cache[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ kernels
+    def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0, big=False):
+        fn = lib.slnlp_gemm_bf16 if (self.precision == "bf16" and big) else lib.slnlp_gemm_f32
+        check(fn(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, _stream()), "gemm")
+
+    def _run_forward(self, ws, X, lengths):
+        """X [B,T] int64 cuda, lengths [B] int64 cuda.  Fills ws; returns ws.logp."""
+        E, H, L, G = self.E, self.H, self.L, self.G
+        B, T = ws.B, ws.T
+        s = _stream()
+        mode, prec = MODE[self.rnn_type], (1 if self.precision == "bf16" else 0)
+        Xp, lp = X.data_ptr(), lengths.data_ptr()
+        check(lib.slnlp_embed_gather_fwd(self._ptr("model.src_embed.weight"), Xp, ws.emb.data_ptr(), B, T, 1,
+                                         ws.f_off, ws.f_w_src, ws.f_rows_src, 1, 1.0, None, s), "embed")
+        drop = ws.train and self.p_rnn > 0.0
+        rng = self._rng_state().data_ptr() if drop else None
+        for l in range(L):
+            D = E if l == 0 else 2 * H
+            xin = ws.emb if l == 0 else ws.enc_xin[l]
+            pre = f"model.encoder.rnn."
+            self._gemm(0, 1, T * B, 2 * G * H, D, xin.data_ptr(), D, self._ptr(f"{pre}weight_ih_l{l}"), D,
+                       ws.enc_gates[l].data_ptr(), 2 * G * H, self._ptr(f"{pre}bias_ih_l{l}"), 0.0, big=True)
+            check(lib.slnlp_rnn_layer_fwd(mode, prec, T, B, H, 2, ws.enc_gates[l].data_ptr(),
+                                          self._ptr(f"{pre}weight_hh_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
+                                          lp, None, None, ws.enc_out[l].data_ptr(), ws.enc_stash[l].data_ptr(),
+                                          ws.enc_hfin[l].data_ptr(), s), "rnn_layer_fwd")
+            if l < L - 1 and drop:
+                check(lib.slnlp_dropout(ws.enc_out[l].data_ptr(), ws.enc_xin[l + 1].data_ptr(),
+                                        ws.enc_out[l].numel(), self.p_rnn, rng, l, s), "dropout")
+            check(lib.slnlp_concat_dirs(ws.enc_hfin[l].data_ptr(), ws.enc_final[l].data_ptr(), B, H, 2, 0, s),
+                  "concat_dirs")
+        enc_out = ws.enc_out[L - 1]
+        check(lib.slnlp_pad_fill(enc_out.data_ptr(), lp, T, B, 2 * H, float(self.src_pad), s), "pad_fill")
+        # bridge (bkp:268-280)
+        self._gemm(0, 1, L * B, H, 2 * H, ws.enc_final.data_ptr(), 2 * H, self._ptr("model.decoder.bridge.weight"),
+                   2 * H, ws.hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.bias"))
+        check(lib.slnlp_tanh_fwd(ws.hidden0.data_ptr(), ws.hidden0.numel(), s), "tanh")
+        # attention (bkp:246,304-327)
+        self._gemm(0, 1, T * B, H, 2 * H, enc_out.data_ptr(), 2 * H,
+                   self._ptr("model.decoder.attention.key_layer.weight"), 2 * H, ws.pk.data_ptr(), H, big=True)
+        self._gemm(0, 1, B, H, H, ws.hidden0[L - 1].data_ptr(), H,
+                   self._ptr("model.decoder.attention.query_layer.weight"), H, ws.q.data_ptr(), H)
+        check(lib.slnlp_attn_step_fwd(ws.q.data_ptr(), ws.pk.data_ptr(),
+                                      self._ptr("model.decoder.attention.energy_layer.weight"),
+                                      enc_out.data_ptr(), Xp, self.src_pad, T, B, H, 2 * H,
+                                      ws.alpha.data_ptr(), ws.ctx.data_ptr(), s), "attn_fwd")
+        # one decoder step (bkp:215-216)
+        check(lib.slnlp_dec_input_fwd(self._ptr("model.trg_embed.weight") + 4 * self.bos_idx * E,
+                                      ws.ctx.data_ptr(), ws.dec_xin[0].data_ptr(), B, E, 2 * H, s), "dec_input")
+        for l in range(L):
+            D = E + 2 * H if l == 0 else H
+            pre = "model.decoder.rnn."
+            self._gemm(0, 1, B, G * H, D, ws.dec_xin[l].data_ptr(), D, self._ptr(f"{pre}weight_ih_l{l}"), D,
+                       ws.dec_gates[l].data_ptr(), G * H, self._ptr(f"{pre}bias_ih_l{l}"))
+            h0 = ws.hidden0[l].data_ptr()
+            check(lib.slnlp_rnn_layer_fwd(mode, 0, 1, B, H, 1, ws.dec_gates[l].data_ptr(),
+                                          self._ptr(f"{pre}weight_hh_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
+                                          None, h0, h0 if mode == 0 else None, ws.dec_h[l].data_ptr(),
+                                          ws.dec_stash[l].data_ptr(), None, s), "rnn_layer_fwd(dec)")
+            if l < L - 1 and drop:
+                check(lib.slnlp_dropout(ws.dec_h[l].data_ptr(), ws.dec_xin[l + 1].data_ptr(), B * H,
+                                        self.p_rnn, rng, 100 + l, s), "dropout")
+        # generator (bkp:73-76) on decoder_states, not pre_output (bkp:40-46)
+        self._gemm(0, 1, B, self.V_tgt, H, ws.dec_h[L - 1].data_ptr(), H,
+                   self._ptr("model.generator.proj.weight"), H, ws.logits.data_ptr(), self.V_tgt)
+        check(lib.slnlp_log_softmax_fwd(ws.logits.data_ptr(), ws.logp.data_ptr(), B, self.V_tgt, s), "log_softmax")
+        return ws.logp
+
+    def _run_backward(self, ws, X, lengths, gflat):
+        """Consumes ws.dlogits; accumulates parameter gradients into ``gflat``."""
+        E, H, L, G = self.E, self.H, self.L, self.G
+        B, T, V = ws.B, ws.T, self.V_tgt
+        s = _stream()
+        mode = MODE[self.rnn_type]
+        Xp, lp = X.data_ptr(), lengths.data_ptr()
+        gp = lambda n: self._ptr(n, gflat)
+        drop = ws.train and self.p_rnn > 0.0
+        rng = self._rng_state().data_ptr() if drop else None
+        GH = G * H
+        # generator
+        self._gemm(1, 0, V, H, B, ws.dlogits.data_ptr(), V, ws.dec_h[L - 1].data_ptr(), H,
+                   gp("model.generator.proj.weight"), H, None, 1.0)
+        self._gemm(0, 0, B, H, V, ws.dlogits.data_ptr(), V, self._ptr("model.generator.proj.weight"), H,
+                   ws.d_h.data_ptr(), H)
+        # decoder cells, top down
+        pre = "model.decoder.rnn."
+        for l in range(L - 1, -1, -1):
+            D = E + 2 * H if l == 0 else H
+            h0 = ws.hidden0[l].data_ptr()
+            dg, dst = ws.dec_gates[l].data_ptr(), ws.dec_stash[l].data_ptr()
+            check(lib.slnlp_rnn_layer_bwd(mode, 0, 1, B, H, 1, dg, dst, ws.dec_h[l].data_ptr(),
+                                          self._ptr(f"{pre}weight_hh_l{l}"), None, h0, h0 if mode == 0 else None,
+                                          ws.d_h.data_ptr(), None, None, ws.d_hidden0[l].data_ptr(),
+                                          ws.d_c0.data_ptr() if mode == 0 else None, ws.carry.data_ptr(), s),
+                  "rnn_layer_bwd(dec)")
+            if mode == 0:  # LSTM: c0 = h0 = hidden0 (bkp:278-279)
+                check(lib.slnlp_axpy(ws.d_hidden0[l].data_ptr(), ws.d_c0.data_ptr(), 1.0, B * H, s), "axpy")
+            xin = ws.dec_xin[l].data_ptr()
+            self._gemm(1, 0, GH, D, B, dg, GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0)
+            check(lib.slnlp_colsum_f32(dg, B, GH, GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
+            if mode == 0:
+                self._gemm(1, 0, GH, H, B, dg, GH, h0, H, gp(f"{pre}weight_hh_l{l}"), H, None, 1.0)
+                check(lib.slnlp_colsum_f32(dg, B, GH, GH, gp(f"{pre}bias_hh_l{l}"), 1.0, s), "colsum")
+            else:
+                self._gemm(1, 0, 2 * H, H, B, dg, GH, h0, H, gp(f"{pre}weight_hh_l{l}"), H, None, 1.0)
+                self._gemm(1, 0, H, H, B, dst, H, h0, H, gp(f"{pre}weight_hh_l{l}") + 4 * 2 * H * H, H, None, 1.0)
+                check(lib.slnlp_colsum_f32(dg, B, 2 * H, GH, gp(f"{pre}bias_hh_l{l}"), 1.0, s), "colsum")
+                check(lib.slnlp_colsum_f32(dst, B, H, H, gp(f"{pre}bias_hh_l{l}") + 4 * 2 * H, 1.0, s), "colsum")
+            dx = ws.d_decx if l == 0 else ws.d_h
+            self._gemm(0, 0, B, D, GH, dg, GH, self._ptr(f"{pre}weight_ih_l{l}"), D, dx.data_ptr(), D)
+            if l > 0 and drop:
+                check(lib.slnlp_dropout(dx.data_ptr(), dx.data_ptr(), B * H, self.p_rnn, rng, 100 + l - 1, s),
+                      "dropout")
+        # decoder input = [trg_embed[bos] || ctx]
+        if self.bos_idx != self.tgt_pad:
+            drow = gp("model.trg_embed.weight") + 4 * self.bos_idx * E
+        else:
+            drow = ws.scratch_row.data_ptr()  # padding_idx row gets no gradient
+        check(lib.slnlp_dec_input_bwd(ws.d_decx.data_ptr(), drow, ws.d_ctx.data_ptr(), B, E, 2 * H, s), "dec_input_bwd")
+        # attention
+        enc_out = ws.enc_out[L - 1]
+        att = "model.decoder.attention."
+        check(lib.slnlp_attn_step_bwd(ws.d_ctx.data_ptr(), ws.q.data_ptr(), ws.pk.data_ptr(),
+                                      self._ptr(att + "energy_layer.weight"), enc_out.data_ptr(),
+                                      ws.alpha.data_ptr(), T, B, H, 2 * H, ws.d_seq.data_ptr(), ws.d_pk.data_ptr(),
+                                      ws.d_q.data_ptr(), ws.dv_part.data_ptr(), s), "attn_bwd")
+        check(lib.slnlp_colsum_f32(ws.dv_part.data_ptr(), B, H, H, gp(att + "energy_layer.weight"), 1.0, s), "colsum")
+        self._gemm(1, 0, H, H, B, ws.d_q.data_ptr(), H, ws.hidden0[L - 1].data_ptr(), H,
+                   gp(att + "query_layer.weight"), H, None, 1.0)
+        self._gemm(0, 0, B, H, H, ws.d_q.data_ptr(), H, self._ptr(att + "query_layer.weight"), H,
+                   ws.d_hidden0[L - 1].data_ptr(), H, None, 1.0)
+        self._gemm(1, 0, H, 2 * H, T * B, ws.d_pk.data_ptr(), H, enc_out.data_ptr(), 2 * H,
+                   gp(att + "key_layer.weight"), 2 * H, None, 1.0, big=True)
+        self._gemm(0, 0, T * B, 2 * H, H, ws.d_pk.data_ptr(), H, self._ptr(att + "key_layer.weight"), 2 * H,
+                   ws.d_seq.data_ptr(), 2 * H, None, 1.0, big=True)
+        # bridge
+        check(lib.slnlp_tanh_bwd(ws.d_hidden0.data_ptr(), ws.hidden0.data_ptr(), L * B * H, s), "tanh_bwd")
+        self._gemm(1, 0, H, 2 * H, L * B, ws.d_hidden0.data_ptr(), H, ws.enc_final.data_ptr(), 2 * H,
+                   gp("model.decoder.bridge.weight"), 2 * H, None, 1.0)
+        check(lib.slnlp_colsum_f32(ws.d_hidden0.data_ptr(), L * B, H, H, gp("model.decoder.bridge.bias"), 1.0, s),
+              "colsum")
+        self._gemm(0, 0, L * B, 2 * H, H, ws.d_hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.weight"),
+                   2 * H, ws.d_enc_final.data_ptr(), 2 * H)
+        # encoder BPTT, top down.  Padded rows of enc_out go back to 0 first (the 1.0
+        # fill of pad_packed_sequence is a constant and must not enter dW_hh).
+        check(lib.slnlp_pad_fill(enc_out.data_ptr(), lp, T, B, 2 * H, 0.0, s), "pad_unfill")
+        pre = "model.encoder.rnn."
+        for l in range(L - 1, -1, -1):
+            D = E if l == 0 else 2 * H
+            check(lib.slnlp_concat_dirs(ws.d_enc_final[l].data_ptr(), ws.d_hfin.data_ptr(), B, H, 2, 1, s),
+                  "concat_dirs_inv")
+            dg, st, out = ws.enc_gates[l].data_ptr(), ws.enc_stash[l].data_ptr(), ws.enc_out[l].data_ptr()
+            check(lib.slnlp_rnn_layer_bwd(mode, 0, T, B, H, 2, dg, st, out, self._ptr(f"{pre}weight_hh_l{l}"),
+                                          lp, None, None, ws.d_seq.data_ptr(), ws.d_hfin.data_ptr(), None,
+                                          None, None, ws.carry.data_ptr(), s), "rnn_layer_bwd")
+            xin = (ws.emb if l == 0 else ws.enc_xin[l]).data_ptr()
+            self._gemm(1, 0, 2 * GH, D, T * B, dg, 2 * GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0, big=True)
+            check(lib.slnlp_colsum_f32(dg, T * B, 2 * GH, 2 * GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
+            K = (T - 1) * B
+            for d in range(2):
+                # dW_hh[d] = sum_t dG_t^T h_{prev(t)}: a GEMM over rows shifted by one timestep
+                a_row = B if d == 0 else 0
+                b_row = 0 if d == 0 else B
+                gw = gp(f"{pre}weight_hh_l{l}") + 4 * d * GH * H
+                gb = gp(f"{pre}bias_hh_l{l}") + 4 * d * GH
+                hb = out + 4 * (b_row * 2 * H + d * H)
+                if mode == 0:
+                    if K > 0:
+                        self._gemm(1, 0, GH, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,
+                                   gw, H, None, 1.0, big=True)
+                    check(lib.slnlp_colsum_f32(dg + 4 * d * GH, T * B, GH, 2 * GH, gb, 1.0, s), "colsum")
+                else:
+                    if K > 0:
+                        self._gemm(1, 0, 2 * H, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,
+                                   gw, H, None, 1.0, big=True)
+                        self._gemm(1, 0, H, H, K, st + 4 * (a_row * 2 * H + d * H), 2 * H, hb, 2 * H,
+                                   gw + 4 * 2 * H * H, H, None, 1.0, big=True)
+                    check(lib.slnlp_colsum_f32(dg + 4 * d * GH, T * B, 2 * H, 2 * GH, gb, 1.0, s), "colsum")
+                    check(lib.slnlp_colsum_f32(st + 4 * d * H, T * B, H, 2 * H, gb + 4 * 2 * H, 1.0, s), "colsum")
+            if l > 0:
+                self._gemm(0, 0, T * B, D, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), D,
+                           ws.d_seq.data_ptr(), D, big=True)
+                if drop:
+                    check(lib.slnlp_dropout(ws.d_seq.data_ptr(), ws.d_seq.data_ptr(), T * B * D, self.p_rnn,
+                                            rng, l - 1, s), "dropout")
+            else:
+                self._gemm(0, 0, T * B, E, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), E,
+                           ws.d_emb.data_ptr(), E, big=True)
+                check(lib.slnlp_embed_gather_bwd(gp("model.src_embed.weight"), Xp, ws.d_emb.data_ptr(), B, T, 1,
+                                                 ws.f_off, ws.f_w_src, ws.f_rows_src, 1, 1.0, self.src_pad, s),
+                      "embed_bwd")
+
+    # ------------------------------------------------------------------ public forward
+    def _check_inputs(self, X, lengths):
+        if not (X.is_cuda and lengths.is_cuda):
+            raise RuntimeError("slnlp_b200: inputs must be CUDA tensors (no CPU fallback)")
+        if X.dim() != 2 or lengths.dim() != 1 or lengths.numel() != X.shape[0]:
+            raise ValueError("expected X [B,T] and lengths [B]")
+        if self.validate_inputs:
+            T = X.shape[1]
+            bad = ((lengths < 1) | (lengths > T)).any() | (X < 0).any() | (X >= self.V_src).any()
+            if bool(bad):
+                raise ValueError("lengths must be in [1, T] (pack_padded_sequence) and tokens in [0, V_src)")
+
+    def forward(self, X, y=None, lengths=None, **kwargs):        # bkp:388-402
+        """Returns log-probabilities [B, V_tgt].  ``y`` is accepted for interface parity;
+        its values never reach the output of the RNN models."""
+        if not self.batch_first:
+            X = X.t()
+        self._ensure_flat()
+        dev = self._flat.device
+        X = X.to(dev, torch.int64).contiguous()
+        if lengths is None:                                       # util.resolve_lengths
+            lengths = (X != self.src_pad).sum(1)
+        lengths = lengths.to(dev, torch.int64).contiguous()
+        self._check_inputs(X, lengths)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self._params.values()):
+            names = [n for n in self._params]
+            return _RnnFn.apply(self, X, lengths, *[self._params[n] for n in names])
+        ws = self._workspace(X.shape[0], X.shape[1], self.training)
+        if ws.train and self.p_rnn > 0:
+            check(lib.slnlp_rng_advance(self._rng_state().data_ptr(), _stream()), "rng")
+        return self._run_forward(ws, X, lengths).clone()
+
+    @torch.no_grad()
+    def predict_logp(self, X, lengths):
+        """Inference forward without autograd or input validation."""
+        self._ensure_flat()
+        was = self.training
+        self.training = False
+        try:
+            ws = self._workspace(X.shape[0], X.shape[1], False)
+            return self._run_forward(ws, X, lengths)
+        finally:
+            self.training = was
+
+
+class _Workspace:
+    """Activation + gradient scratch for one (B, T, train) shape; torch owns the memory."""
+
+    def __init__(self, m: RnnEncDecB200, B, T, train, bwd=None):
+        import ctypes
+        bwd = train if bwd is None else bwd
+        E, H, L, G, V = m.E, m.H, m.L, m.G, m.V_tgt
+        dev = m._flat.device
+        f = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+        self.B, self.T, self.train = B, T, train
+        self.f_off = (ctypes.c_int64 * 1)(0)
+        self.f_w_src = (ctypes.c_int * 1)(E)
+        self.f_rows_src = (ctypes.c_int64 * 1)(m.V_src)
+        drop = train and m.p_rnn > 0
+        self.emb = f(T, B, E)
+        self.enc_gates = [f(T, B, 2, G, H) for _ in range(L)]
+        self.enc_stash = [f(T, B, 2, H) for _ in range(L)]
+        self.enc_out = [f(T, B, 2 * H) for _ in range(L)]
+        self.enc_xin = [None] + [f(T, B, 2 * H) if drop else self.enc_out[l - 1] for l in range(1, L)]
+        self.enc_hfin = [f(2, B, H) for _ in range(L)]
+        self.enc_final = f(L, B, 2 * H)
+        self.hidden0 = f(L, B, H)
+        self.pk, self.q = f(T, B, H), f(B, H)
+        self.alpha, self.ctx = f(B, T), f(B, 2 * H)
+        self.dec_gates = [f(1, B, 1, G, H) for _ in range(L)]
+        self.dec_stash = [f(1, B, 1, H) for _ in range(L)]
+        self.dec_h = [f(1, B, H) for _ in range(L)]
+        self.dec_xin = [f(B, E + 2 * H)] + [f(B, H) if drop else self.dec_h[l - 1] for l in range(1, L)]
+        self.logits, self.logp = f(B, V), f(B, V)
+        if bwd:
+            self.dlogits = f(B, V)
+            self.d_h, self.d_c0 = f(B, H), f(B, H)
+            self.d_decx, self.d_ctx = f(B, E + 2 * H), f(B, 2 * H)
+            self.d_seq = f(T, B, 2 * H)       # d enc_out / d layer outputs (reused down the stack)
+            self.d_pk, self.d_q, self.dv_part = f(T, B, H), f(B, H), f(B, H)
+            self.d_hidden0, self.d_enc_final = f(L, B, H), f(L, B, 2 * H)
+            self.d_hfin = f(2, B, H)
+            self.d_emb = f(T, B, E)
+            self.carry = f(4, B, H)
+            self.scratch_row = torch.zeros(E, device=dev)
+            self.loss = torch.zeros(2, device=dev)
+            self.row_ws = f(3 * B)
+
+
+class _RnnFn(torch.autograd.Function):
+    """Autograd bridge for the drop-in path: forward/backward launch the C-ABI kernels."""
+
+    @staticmethod
+    def forward(ctx, module: RnnEncDecB200, X, lengths, *params):
+        ws = module._workspace(X.shape[0], X.shape[1], module.training, fresh=True, bwd=True)
+        if ws.train and module.p_rnn > 0:
+            check(lib.slnlp_rng_advance(module._rng_state().data_ptr(), _stream()), "rng")
+            ctx.rng_step = module._rng_state().clone()
+        ctx.module, ctx.ws, ctx.X, ctx.lengths = module, ws, X, lengths
+        logp = module._run_forward(ws, X, lengths)
+        return logp.clone()
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        m, ws = ctx.module, ctx.ws
+        if not dlogp.is_cuda:
+            raise RuntimeError("slnlp_b200: gradient must be a CUDA tensor")
+        dlogp = dlogp.contiguous().float()
+        check(lib.slnlp_log_softmax_bwd(dlogp.data_ptr(), ws.logp.data_ptr(), ws.dlogits.data_ptr(),
+                                        ws.B, m.V_tgt, _stream()), "log_softmax_bwd")
+        g = torch.zeros_like(m._flat)
+        if ws.train and m.p_rnn > 0:  # replay the dropout masks of this forward
+            saved = m._rng_state().clone()
+            m._rng_state().copy_(ctx.rng_step)
+        m._run_backward(ws, ctx.X, ctx.lengths, g)
+        if ws.train and m.p_rnn > 0:
+            m._rng_state().copy_(saved)
+        grads = []
+        for n in m._params:
+            grads.append(None if n == "model.decoder.pre_output_layer.weight" else m._view(g, n))
+        return (None, None, None, *grads)
+
+
+class FusedTrainStep:
+    """The skorch train step of SURVEY.md 3.2 as ONE CUDA-graph replay:
+
+    zero grads -> forward -> CrossEntropyLoss(ignore_index=pad) on the log-probs ->
+    backward -> global L2 norm clip (GradientNormClipping, helper.py:227-229) ->
+    SGD(momentum, nesterov=False) (config/*.yaml:39-42).
+    """
+
+    def __init__(self, module: RnnEncDecB200, batch_size: int, seq_len: int, lr: float,
+                 momentum: float = 0.9, max_norm: float = 0.5, use_graph: bool = True,
+                 grad_sync=None):
+        module._ensure_flat()
+        self.m, self.B, self.T = module, batch_size, seq_len
+        dev = module._flat.device
+        self.ws = _Workspace(module, batch_size, seq_len, True, True)
+        self.X = torch.full((batch_size, seq_len), module.src_pad, dtype=torch.int64, device=dev)
+        self.lengths = torch.ones(batch_size, dtype=torch.int64, device=dev)
+        self.y = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        self.hyper = torch.tensor([lr, momentum, max_norm if max_norm else 0.0, 0.0], device=dev)
+        self.buf = torch.zeros_like(module._flat)     # zero buffer == "first step" of torch SGD
+        self.partials = torch.zeros(lib.slnlp_sumsq_partials(), device=dev)
+        self.norm = torch.zeros(1, device=dev)
+        self.gflat = module.flat_grads()
+        self.grad_sync = grad_sync                   # callable(gflat, loss) for data parallel
+        self.grad_scale = 1.0
+        self.graph = None
+        self.use_graph = use_graph and grad_sync is None
+        self._lr = lr
+
+    def set_lr(self, lr):
+        if lr != self._lr:
+            self.hyper[0] = lr
+            self._lr = lr
+
+    def _step(self):
+        m, ws = self.m, self.ws
+        s = _stream()
+        self.gflat.zero_()
+        if m.p_rnn > 0:
+            check(lib.slnlp_rng_advance(m._rng_state().data_ptr(), s), "rng")
+        m._run_forward(ws, self.X, self.lengths)
+        check(lib.slnlp_ce_on_logp(ws.logp.data_ptr(), self.y.data_ptr(), m.tgt_pad, self.B, m.V_tgt,
+                                   ws.loss.data_ptr(), ws.dlogits.data_ptr(), ws.row_ws.data_ptr(), s), "ce")
+        m._run_backward(ws, self.X, self.lengths, self.gflat)
+        if self.grad_sync is not None:
+            self.grad_sync(self.gflat, ws.loss)
+            s = _stream()
+        n = m._numel
+        check(lib.slnlp_gradnorm(self.gflat.data_ptr(), n, self.partials.data_ptr(), self.norm.data_ptr(), s), "gradnorm")
+        check(lib.slnlp_sgd_momentum_clip(m._flat.data_ptr(), self.gflat.data_ptr(), self.buf.data_ptr(), n,
+                                          self.hyper.data_ptr(), self.norm.data_ptr(), self.grad_scale, s), "sgd")
+
+    def load_batch(self, X, y, lengths):
+        """Stage one batch into the graph's static input buffers (device or pinned host)."""
+        self.X.copy_(X, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        self.lengths.copy_(lengths, non_blocking=True)
+
+    def run(self):
+        """One training step on the staged batch.  Returns the device tensor [loss, n_valid]."""
+        if not self.use_graph:
+            self._step()
+            return self.ws.loss
+        if self.graph is None:
+            # warm-up outside capture (lazy module/func attribute init), on a side stream
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            saved = (self.m._flat.clone(), self.buf.clone(), self.m._rng_state().clone())
+            with torch.cuda.stream(side):
+                self._step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.m._flat.copy_(saved[0]); self.buf.copy_(saved[1]); self.m._rng_state().copy_(saved[2])
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step()
+            self.m._flat.copy_(saved[0]); self.buf.copy_(saved[1]); self.m._rng_state().copy_(saved[2])
+        self.graph.replay()
+        return self.ws.loss
+
+    def step(self, X, y, lengths):
+        self.load_batch(X, y, lengths)
+        return self.run()
+
+    @property
+    def grad_norm(self):
+        return self.norm

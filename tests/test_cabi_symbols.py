@@ -1,0 +1,60 @@
+"""CPU: the C-ABI library loads and exports every symbol include/slnlp_b200.h declares
+(no compute calls - there is no GPU here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "slnlp_b200.h")
+
+
+def declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"(?:int|const char\*)\s+(slnlp_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        out[m.group(1)] = n
+    return out
+
+
+def test_header_declares_the_hot_path():
+    d = declared()
+    for name in ("slnlp_embed_gather_fwd", "slnlp_gemm_f32", "slnlp_rnn_layer_fwd", "slnlp_rnn_layer_bwd",
+                 "slnlp_attn_step_fwd", "slnlp_attn_step_bwd", "slnlp_ce_on_logp", "slnlp_gradnorm",
+                 "slnlp_sgd_momentum_clip", "slnlp_last_error_string"):
+        assert name in d
+
+
+def test_library_exports_every_declared_symbol():
+    from slnlp_b200 import _lib
+    d = declared()
+    assert len(d) >= 25
+    for name, nargs in d.items():
+        fn = getattr(_lib.lib, name)            # AttributeError = missing export
+        assert name in _lib.SIGNATURES, name
+        assert len(_lib.SIGNATURES[name]) == nargs, (name, nargs, len(_lib.SIGNATURES[name]))
+        assert fn is not None
+    assert _lib.lib.slnlp_abi_version() == 1
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from slnlp_b200 import _lib
+    rc = _lib.lib.slnlp_gemm_f32(0, 0, 4, 4, 4, None, 4, None, 4, None, 4, None, 0.0, None)
+    assert rc != 0 and "null" in _lib.last_error()
+    rc = _lib.lib.slnlp_rnn_layer_fwd(7, 0, 1, 1, 1, 1, None, None, None, None, None, None, None, None, None, None)
+    assert rc != 0 and "mode" in _lib.last_error()
+
+
+def test_library_is_cuda_only_sm100a():
+    """The .so carries sm_100a SASS (and nothing for another arch)."""
+    import subprocess
+    from slnlp_b200 import _lib
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        import pytest
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs

