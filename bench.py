@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Headline benchmark: training sequences/s of one fit of the reference's
+EncoderDecoderLSTMAttn on one B200, next to the reference's CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1|cfg2|cfg4]
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port)
+
+A "step" is one skorch-equivalent training step (forward, CrossEntropyLoss on the
+log-probs, backward, global-norm clip 0.5, SGD momentum 0.9) on one batch of synthetic
+6-field phonology sequences.  At N > 1 every rank runs its own
+independent fit (the reference's only parallelism is farming grid-search fits, one per
+GPU, with no collective: SURVEY.md section 8e) - weak scaling; ``--dp`` instead splits
+one global batch across ranks with an NCCL gradient all-reduce.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "sign-language-nlp_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # BASELINE.json configs[0]: the configuration the metric is quoted on ("LSTM-attn, 1 B200")
+    "cfg1": dict(kind="lstm", E=128, H=128, L=2, p=0.1, B=50, T=64, Vs=4098, Vt=1026,
+                 name="EncoderDecoderLSTMAttn emb128 hidden128 layers2 dropout0.1 batch50 len64"),
+    "cfg2": dict(kind="gru", E=512, H=256, L=4, p=0.1, B=50, T=64, Vs=4098, Vt=1026,
+                 name="EncoderDecoderGRUAttn emb512 hidden256 layers4 batch50 len64"),
+    "cfg4": dict(kind="lstm", E=1024, H=512, L=6, p=0.5, B=4096, T=64, Vs=4098, Vt=1026,
+                 name="EncoderDecoderLSTMAttn emb1024 hidden512 layers6 dropout0.5 batch4096 len64"),
+}
+METRIC, UNIT = "train_seq_per_s", "sequences/s"
+
+
+def train_flops_per_seq(w):
+    """3 x forward GEMM FLOPs of the live graph."""
+    G = 4 if w["kind"] == "lstm" else 3
+    E, H, L, T, V = w["E"], w["H"], w["L"], w["T"], w["Vt"]
+    enc = sum(2 * T * (2 * G * H * (E if l == 0 else 2 * H) + 2 * G * H * H) for l in range(L))
+    key, bridge = T * 2 * 2 * H * H, L * 2 * 2 * H * H
+    att = 2 * H * H + 2 * T * H + 4 * T * H
+    dec = sum(2 * G * H * ((E + 2 * H) if l == 0 else H) + 2 * G * H * H for l in range(L))
+    return 3 * (enc + key + bridge + att + dec + 2 * H * V)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_reference_port(w):
+    import torch
+    from oracle import port
+    torch.manual_seed(1)
+    return port.build_port(w["kind"], w["Vs"], w["Vt"], w["E"], w["H"], w["L"], dropout=w["p"])
+
+
+def time_cpu_port(w, data, steps, warmup, batch=None):
+    """The reference's CPU path (torch.nn port of its modules, oracle/port.py) on the host cores."""
+    import torch
+    from oracle import port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = batch or min(w["B"], 50)
+    ref = build_reference_port(w)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9, nesterov=False)
+    X, y, lengths = data["X"], data["y"], data["lengths"]
+    nb = X.shape[0] // B
+    times = []
+    for i in range(warmup + steps):
+        j = (i % nb) * B
+        t0 = time.perf_counter()
+        port.reference_train_step(ref, opt, X[j:j + B], y[j:j + B], lengths[j:j + B])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return B / sec, sec, cores, B
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from slnlp_b200.data import synthetic_dataset
+    data = synthetic_dataset(n_seq=max(500, 50 * 10), T=w["T"], v_src=w["Vs"], v_tgt=w["Vt"], seed=1)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    if w["B"] > 50:  # cfg4 on CPU: batch 50 sample, reported per sequence
+        steps, warmup = min(steps, 3), 1
+    val, sec, cores, B = time_cpu_port(w, data, steps, warmup)
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "batch": B, "seq_len": w["T"], "v_src": w["Vs"], "v_tgt": w["Vt"]},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),
+                             "sample": f"{steps} training steps of batch {B} (median), torch {__import__('torch').__version__} CPU, "
+                                       "oracle/port.py = the reference modules on stock torch.nn"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg1", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("SLNLP_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--dp", action="store_true", help="data-parallel one global batch (NCCL all-reduce)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["B"] = args.batch
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    import torch
+    import torch.distributed as dist
+    import model as dropin
+    from slnlp_b200 import _lib
+    from slnlp_b200.data import synthetic_dataset
+    from slnlp_b200.rnn import FusedTrainStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = args.steps
+    B = w["B"] // world if args.dp else w["B"]
+
+    n_seq = max(5000 if w["B"] <= 50 else 8 * w["B"], B * 4)
+    data = synthetic_dataset(n_seq=n_seq, T=w["T"], v_src=w["Vs"], v_tgt=w["Vt"], seed=1 + (0 if args.dp else rank))
+    torch.manual_seed(1)
+    cls = dropin.EncoderDecoderLSTMAttn if w["kind"] == "lstm" else dropin.EncoderDecoderGRUAttn
+    m = cls(src_vocab=data["src_vocab"], tgt_vocab=data["tgt_vocab"], batch_first=True, embedding_size=w["E"],
+            hidden_size=w["H"], num_layers=w["L"], dropout=w["p"], device=dev, precision=args.precision).to(dev).train()
+
+    grad_sync = None
+    if args.dp and world > 1:
+        def grad_sync(gflat, loss):
+            dist.all_reduce(gflat)
+    ts = FusedTrainStep(m, B, w["T"], lr=0.01, momentum=0.9, max_norm=0.5, grad_sync=grad_sync)
+    if args.dp and world > 1:
+        ts.grad_scale = 1.0 / world
+
+    # ---------------- device-resident leg: whole dataset in HBM, batches sliced on device
+    Xd, yd, ld = data["X"].to(dev), data["y"].to(dev), data["lengths"].to(dev)
+    if args.dp and world > 1:  # each rank takes its slice of every global batch
+        Xd, yd, ld = Xd[rank::world].contiguous(), yd[rank::world].contiguous(), ld[rank::world].contiguous()
+    nb = Xd.shape[0] // B
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def batch(i):
+        j = (i % nb) * B
+        return Xd[j:j + B], yd[j:j + B], ld[j:j + B]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        ts.step(*batch(i))
+    barrier()
+    l0 = _lib.lib.slnlp_launch_count()
+    if not ts.use_graph:
+        ts.step(*batch(0))
+    launches_per_step = None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    losses = []
+    barrier()
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            if flush is not None:
+                flush.zero_()                       # evict L2 between timed steps (not timed)
+            ts.load_batch(*batch(W + i))
+            ev[i][0].record()
+            ts.run()
+            ev[i][1].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_s = sum(step_ms) / 1e3
+    tt = torch.tensor([dev_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_s = float(tt)
+    total_seqs = K * B * world
+    value = total_seqs / dev_s
+    final_loss = float(ts.ws.loss[0])
+
+    # kernels per step: count one un-captured step through the C ABI
+    c0 = _lib.lib.slnlp_launch_count()
+    ts._step()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.lib.slnlp_launch_count() - c0
+
+    # ---------------- e2e leg: host (pinned) batches through the public step API, loss read back
+    Xh, yh, lh = data["X"].pin_memory(), data["y"].pin_memory(), data["lengths"].pin_memory()
+    if args.dp and world > 1:
+        Xh, yh, lh = Xh[rank::world].contiguous().pin_memory(), yh[rank::world].contiguous().pin_memory(), lh[rank::world].contiguous().pin_memory()
+    Ke = K
+    for i in range(3):
+        j = (i % nb) * B
+        float(ts.step(Xh[j:j + B], yh[j:j + B], lh[j:j + B])[0])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_loss = torch.empty(2, pin_memory=True)
+    e0.record()
+    for i in range(Ke):
+        j = ((W + i) % nb) * B
+        loss = ts.step(Xh[j:j + B], yh[j:j + B], lh[j:j + B])   # H2D of the batch inside the timed region
+        host_loss.copy_(loss, non_blocking=False)                # D2H of the step's loss, every step
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = Ke * B * world / float(te)
+    h2d = B * w["T"] * 8 + B * 8 + B * 8
+    d2h = 8
+
+    # ---------------- dominant kernel, timed alone: the encoder layer-0 recurrence (T launches)
+    roof = dominant_kernel_roofline(m, ts, w, B, dev)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        flops_seq = train_flops_per_seq(w)
+        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_s / K * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.dp else "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": w["name"], "batch_per_gpu": B, "global_batch": B * world, "seq_len": w["T"],
+                       "v_src": w["Vs"], "v_tgt": w["Vt"], "params": m._numel,
+                       "parallelism": ("dp%d (NCCL all-reduce)" % world) if args.dp else
+                                      ("%d independent fits (grid-search farm, no collective)" % world),
+                       "l2": "none (--no-flush)" if flush is None else "256 MiB zero-fill between timed steps (outside the timed events)",
+                       "cuda_graph": bool(ts.use_graph), "optimizer": "SGD momentum 0.9, global-norm clip 0.5, lr 0.01"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "FusedTrainStep.step(pinned host X,y,lengths) + loss read-back every step"},
+            "gpu_launches": int(launches_per_step * K),
+            "launches_per_step": int(launches_per_step),
+            "clocks": clocks.summary(),
+            "wall_ms_per_step_incl_flush": t_wall / K * 1e3,
+            "final_loss": final_loss,
+            "model_tflops": value * flops_seq / 1e12,
+            "model_frac_of_tensor_peak": value * flops_seq / 1e12 / tf_peak,
+            "train_mflop_per_seq": flops_seq / 1e6,
+            "roofline": roof,
+        }
+        if roof is not None:
+            roof["peak"] = peaks.get("bf16_tflops", 1590.0)
+            roof["peak_source"] = "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"
+            roof["frac"] = roof["achieved"] / roof["peak"]
+        if not args.no_cpu_baseline:
+            cdata = {k: (v[:1000] if hasattr(v, "shape") else v) for k, v in data.items()}
+            cval, csec, cores, cB = time_cpu_port(w, cdata, steps=12 if w["B"] <= 50 and w["H"] <= 128 else 3, warmup=2)
+            line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),
+                                    "sample": f"median of {12 if w['B'] <= 50 and w['H'] <= 128 else 3} training steps of batch {cB} "
+                                              f"({csec * 1e3:.0f} ms/step) on the box's host cores; oracle/port.py = the reference "
+                                              "modules on stock torch.nn (the Python reference cannot travel to the box)"}
+            line["speedup_e2e_vs_cpu"] = e2e / cval
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(m, ts, w, B, dev):
+    """Time the dominant kernel (the recurrent step of encoder layer 0: T launches per layer
+    call, both directions per launch) alone with CUDA events on its launching stream."""
+    import torch
+    from slnlp_b200 import _lib
+    lib = _lib.lib
+    T, H, G = w["T"], w["H"], (4 if w["kind"] == "lstm" else 3)
+    ws = ts.ws
+    mode = 0 if w["kind"] == "lstm" else 1
+    prec = 1 if m.precision == "bf16" else 0
+
+    def call():
+        _lib.check(lib.slnlp_rnn_layer_fwd(mode, prec, T, B, H, 2, ws.enc_gates[0].data_ptr(),
+                                           m._ptr("model.encoder.rnn.weight_hh_l0"), m._ptr("model.encoder.rnn.bias_hh_l0"),
+                                           ts.lengths.data_ptr(), None, None, ws.enc_out[0].data_ptr(),
+                                           ws.enc_stash[0].data_ptr(), ws.enc_hfin[0].data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+    ws.enc_gates[0].normal_(0, 0.5)
+    for _ in range(3):
+        call()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        call()
+    reps = 20
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    per_launch_s = a.elapsed_time(b) / 1e3 / (reps * T)
+    flops = 2.0 * B * (G * H) * H * 2            # h_{t-1} W_hh^T, both directions, per launch
+    return {"kernel": "rnn_step_fwd_kernel (h W_hh^T + gates + cell, both directions)" if prec == 0 else "rnn persistent tcgen05",
+            "bound": "tensor", "achieved": flops / per_launch_s / 1e12, "unit": "TFLOP/s",
+            "us_per_launch": per_launch_s * 1e6, "flops_per_launch": flops, "traffic": None,
+            "note": "at batch 50 the 2*L*T dependent recurrence steps, not FLOPs or bytes, bound the step "
+                    "(SURVEY.md 8d); timed as a CUDA-graph replay of one layer call (T launches)"}
+
+
+if __name__ == "__main__":
+    main()

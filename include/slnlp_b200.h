@@ -36,6 +36,8 @@ typedef void* slnlp_stream_t;
 
 int slnlp_abi_version(void);
 const char* slnlp_last_error_string(void);
+/* kernels launched through this ABI by the process so far (bench.py's gpu_launches) */
+int64_t slnlp_launch_count(void);
 /* number of SMs of the current device (grid sizing), or -1 */
 int slnlp_device_sm_count(void);
 
@@ -61,10 +63,14 @@ int slnlp_embed_gather_bwd(float* dtable, const int64_t* idx, const float* dout,
 /* ---- K3/K6/K10 and every other dense contraction (nn.Linear call sites bkp:73-76,
  * 193-194,246,297-299; the x*W_ih^T hoisted out of nn.LSTM/GRU, bkp:114,216).
  * Row-major C[M,N] = op(A) op(B) + bias[N] + beta*C with fp32 FMA accumulation.
- * op(A) is A[M,K] (transA=0) or A[K,M]^T (transA=1); likewise B[K,N] / B[N,K]^T. */
+ * op(A) is A[M,K] (transA=0) or A[K,M]^T (transA=1); likewise B[K,N] / B[N,K]^T.
+ * workspace (may be NULL): scratch for deterministic split-K when M*N is small and K
+ * long (the dW GEMMs over K = B*T); slnlp_gemm_workspace_floats() is always enough. */
+int64_t slnlp_gemm_workspace_floats(void);
 int slnlp_gemm_f32(int transA, int transB, int M, int N, int K,
                    const float* A, int lda, const float* B, int ldb,
-                   float* C, int ldc, const float* bias, float beta, slnlp_stream_t stream);
+                   float* C, int ldc, const float* bias, float beta,
+                   float* workspace, int64_t workspace_floats, slnlp_stream_t stream);
 /* out[c] = beta*out[c] + sum_r A[r*lda + c]   (bias gradients) */
 int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
                      slnlp_stream_t stream);

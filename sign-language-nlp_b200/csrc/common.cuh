@@ -24,12 +24,15 @@ int fail(const char* fmt, ...);
     cudaError_t e__ = cudaGetLastError();                                             \
     if (e__ != cudaSuccess)                                                           \
       return ::slnlp::fail("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+    ::slnlp::note_launches(1);                                                        \
   } while (0)
 
 static inline cudaStream_t as_stream(slnlp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 int sm_count();
+// kernels launched by this process through the C ABI (bench.py's gpu_launches claim)
+void note_launches(int64_t n);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float warp_sum(float v) {

@@ -3,8 +3,10 @@
 //   clip + SGD-momentum, dropout (own Philox), pad fill, small elementwise glue.
 // Reference call sites are cited in include/slnlp_b200.h next to each entry point.
 #include "common.cuh"
+#include <atomic>
 
 namespace slnlp {
+int64_t launches();
 
 char* err_buf() {
   static thread_local char buf[512] = {0};
@@ -17,6 +19,9 @@ int fail(const char* fmt, ...) {
   va_end(ap);
   return 1;
 }
+static std::atomic<int64_t> g_launches{0};
+void note_launches(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -401,6 +406,7 @@ extern "C" {
 
 int slnlp_abi_version(void) { return SLNLP_ABI_VERSION; }
 const char* slnlp_last_error_string(void) { return err_buf(); }
+int64_t slnlp_launch_count(void) { return slnlp::launches(); }
 int slnlp_device_sm_count(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -545,6 +551,7 @@ int slnlp_ce_on_logp(const float* logp, const int64_t* y, int64_t ignore_index, 
   ce_rows_kernel<<<B, 256, 0, as_stream(stream)>>>(logp, y, ignore_index, B, V, row_ws);
   ce_reduce_kernel<<<1, 256, 0, as_stream(stream)>>>(row_ws, B, loss_out);
   if (dlogits) ce_grad_kernel<<<B, 256, 0, as_stream(stream)>>>(logp, y, B, V, row_ws, loss_out, dlogits);
+  note_launches(dlogits ? 2 : 1);
   SLNLP_LAUNCH_OK("ce_on_logp");
   return 0;
 }
@@ -557,6 +564,7 @@ int slnlp_gradnorm(const float* g, int64_t n, float* partials, float* norm_out, 
   int grid = (int)(want < 1 ? 1 : (want > kSumsqBlocks ? kSumsqBlocks : want));
   sumsq_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, n, partials);
   sumsq_final_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, grid, norm_out);
+  note_launches(1);
   SLNLP_LAUNCH_OK("gradnorm");
   return 0;
 }

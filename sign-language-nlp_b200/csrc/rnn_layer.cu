@@ -58,17 +58,46 @@ __global__ void __launch_bounds__(FJ * FTB) rnn_step_fwd_kernel(StepFwd p) {
     for (int r = 0; r < RB; ++r) acc[g][r] = 0.f;
 
   if (hprev) {  // first step with zero state: the recurrent product is exactly 0
+    const bool vec = (H % 4 == 0) && ((((uintptr_t)W | (uintptr_t)hprev) & 15) == 0);
     for (int k0 = 0; k0 < H; k0 += FKC) {
       const int kc = min(FKC, H - k0);
       if (k0) __syncthreads();
-      for (int e = tid; e < G * FJ * FKC; e += FJ * FTB) {
-        const int kk = e % FKC, row = e / FKC, g = row / FJ, jj = row % FJ;
-        const int j = j0 + jj;
-        Ws[row * LDS_ + kk] = (kk < kc && j < H) ? __ldg(W + ((int64_t)g * H + j) * H + k0 + kk) : 0.f;
-      }
-      for (int e = tid; e < BB * FKC; e += FJ * FTB) {
-        const int kk = e % FKC, bb = e / FKC, b = b0 + bb;
-        Hs[bb * LDS_ + kk] = (kk < kc && b < B) ? hprev[(int64_t)b * hprev_ld + k0 + kk] : 0.f;
+      if (vec) {
+        // all global loads of the tile are issued before the first shared store (one L2 round trip)
+        constexpr int NW = G * FJ * (FKC / 4) / (FJ * FTB), NH = BB * (FKC / 4) / (FJ * FTB);
+        float4 wv[NW], hv[NH];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          const int e = tid + i * (FJ * FTB), k4 = e % (FKC / 4), row = e / (FKC / 4), g = row / FJ, j = j0 + row % FJ;
+          wv[i] = (k4 * 4 < kc && j < H) ? __ldg(reinterpret_cast<const float4*>(W + ((int64_t)g * H + j) * H + k0) + k4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < NH; ++i) {
+          const int e = tid + i * (FJ * FTB), k4 = e % (FKC / 4), bb = e / (FKC / 4), b = b0 + bb;
+          hv[i] = (k4 * 4 < kc && b < B) ? *(reinterpret_cast<const float4*>(hprev + (int64_t)b * hprev_ld + k0) + k4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          const int e = tid + i * (FJ * FTB), k4 = e % (FKC / 4), row = e / (FKC / 4);
+          *reinterpret_cast<float4*>(&Ws[row * LDS_ + k4 * 4]) = wv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NH; ++i) {
+          const int e = tid + i * (FJ * FTB), k4 = e % (FKC / 4), bb = e / (FKC / 4);
+          *reinterpret_cast<float4*>(&Hs[bb * LDS_ + k4 * 4]) = hv[i];
+        }
+      } else {
+        for (int e = tid; e < G * FJ * FKC; e += FJ * FTB) {
+          const int kk = e % FKC, row = e / FKC, g = row / FJ, jj = row % FJ;
+          const int j = j0 + jj;
+          Ws[row * LDS_ + kk] = (kk < kc && j < H) ? __ldg(W + ((int64_t)g * H + j) * H + k0 + kk) : 0.f;
+        }
+        for (int e = tid; e < BB * FKC; e += FJ * FTB) {
+          const int kk = e % FKC, bb = e / FKC, b = b0 + bb;
+          Hs[bb * LDS_ + kk] = (kk < kc && b < B) ? hprev[(int64_t)b * hprev_ld + k0 + kk] : 0.f;
+        }
       }
       __syncthreads();
       const int kc4 = (kc + 3) & ~3;
@@ -185,22 +214,59 @@ __global__ void __launch_bounds__(BJS * 32) rnn_step_bwd_kernel(StepBwd p) {
     for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
 
   if (has_next) {
+    const bool vec = (H % 4 == 0) &&
+                     ((((uintptr_t)W | (uintptr_t)p.gates | (uintptr_t)p.stash) & 15) == 0);
     for (int jbase = 0; jbase < GH; jbase += jc_max) {
       const int jc = min(jc_max, GH - jbase);
       if (jbase) __syncthreads();
-      for (int e = tid; e < jc_max * BKT; e += BJS * 32) {
-        const int kk = e % BKT, jj = e / BKT;
-        Ws[jj * WLD + kk] = (jj < jc && k0 + kk < H) ? __ldg(W + (int64_t)(jbase + jj) * H + k0 + kk) : 0.f;
-      }
-      for (int e = tid; e < BB * jc_max; e += BJS * 32) {
-        const int jj = e % jc_max, bb = e / jc_max, b = b0 + bb, j = jbase + jj;
-        float v = 0.f;
-        if (jj < jc && b < B) {
-          const int64_t row = ((int64_t)tn * B + b) * p.ndir + d;
-          if (G == 4 || j < 2 * H) v = p.gates[row * GH + j];
-          else v = p.stash[row * H + (j - 2 * H)];
+      if (vec) {
+        constexpr int NV = BJC * (BKT / 4) / (BJS * 32);       // float4 per thread for a full chunk
+        constexpr int ND = 8 * RB * (BJC / 4) / (BJS * 32);
+        float4 wv[NV], dv[ND];
+        const int nw4 = jc_max * (BKT / 4), jq = jc_max / 4, nd4 = BB * jq;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int e = tid + i * (BJS * 32), k4 = e % (BKT / 4), jj = e / (BKT / 4);
+          wv[i] = (e < nw4 && jj < jc && k0 + k4 * 4 < H)
+                      ? __ldg(reinterpret_cast<const float4*>(W + (int64_t)(jbase + jj) * H + k0) + k4)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        Ds[bb * DLD + jj] = v;
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+          const int e = tid + i * (BJS * 32), j4 = e % jq, bb = e / jq, b = b0 + bb, j = jbase + j4 * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e < nd4 && j4 * 4 < jc && b < B) {
+            const int64_t row = ((int64_t)tn * B + b) * p.ndir + d;
+            v = (G == 4 || j < 2 * H) ? *reinterpret_cast<const float4*>(p.gates + row * GH + j)
+                                      : *reinterpret_cast<const float4*>(p.stash + row * H + (j - 2 * H));
+          }
+          dv[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int e = tid + i * (BJS * 32), k4 = e % (BKT / 4), jj = e / (BKT / 4);
+          if (e < nw4) *reinterpret_cast<float4*>(&Ws[jj * WLD + k4 * 4]) = wv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+          const int e = tid + i * (BJS * 32), j4 = e % jq, bb = e / jq;
+          if (e < nd4) *reinterpret_cast<float4*>(&Ds[bb * DLD + j4 * 4]) = dv[i];
+        }
+      } else {
+        for (int e = tid; e < jc_max * BKT; e += BJS * 32) {
+          const int kk = e % BKT, jj = e / BKT;
+          Ws[jj * WLD + kk] = (jj < jc && k0 + kk < H) ? __ldg(W + (int64_t)(jbase + jj) * H + k0 + kk) : 0.f;
+        }
+        for (int e = tid; e < BB * jc_max; e += BJS * 32) {
+          const int jj = e % jc_max, bb = e / jc_max, b = b0 + bb, j = jbase + jj;
+          float v = 0.f;
+          if (jj < jc && b < B) {
+            const int64_t row = ((int64_t)tn * B + b) * p.ndir + d;
+            if (G == 4 || j < 2 * H) v = p.gates[row * GH + j];
+            else v = p.stash[row * H + (j - 2 * H)];
+          }
+          Ds[bb * DLD + jj] = v;
+        }
       }
       __syncthreads();
       const int per = ((jc + BJS * 4 - 1) / (BJS * 4)) * 4;  // j' per split, multiple of 4
@@ -332,6 +398,10 @@ static int launch_bwd(const StepBwd& p, cudaStream_t s) {
 int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh,
                      const float* b_hh, const int64_t* lengths, const float* h0, const float* c0,
                      float* out, float* stash, float* h_final, cudaStream_t s);
+int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, float* stash, const float* out,
+                     const float* w_hh, const int64_t* lengths, const float* h0, const float* c0,
+                     const float* dout, const float* dh_final, const float* dc_final, float* dh0, float* dc0,
+                     cudaStream_t s);
 
 }  // namespace slnlp
 
@@ -357,6 +427,7 @@ extern "C" int slnlp_rnn_layer_fwd(int mode, int precision, int T, int B, int H,
     if (mode == SLNLP_MODE_LSTM) { if (big) launch_fwd<4, 4>(p, s); else launch_fwd<4, 2>(p, s); }
     else { if (big) launch_fwd<3, 4>(p, s); else launch_fwd<3, 2>(p, s); }
   }
+  note_launches(T - 1);
   SLNLP_LAUNCH_OK("rnn_layer_fwd");
   return 0;
 }
@@ -366,12 +437,16 @@ extern "C" int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H,
                                    const int64_t* lengths, const float* h0, const float* c0,
                                    const float* dout, const float* dh_final, const float* dc_final,
                                    float* dh0, float* dc0, float* carry, slnlp_stream_t stream) {
-  (void)precision;
   SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM || mode == SLNLP_MODE_GRU, "rnn_layer_bwd: bad mode %d", mode);
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_bwd: bad shape");
   SLNLP_CHECK_ARG(gates && stash && out && w_hh && carry, "rnn_layer_bwd: null pointer");
   SLNLP_CHECK_ARG(!(dh0 || dc0) || !lengths, "rnn_layer_bwd: dh0/dc0 need lengths == NULL");
   cudaStream_t s = as_stream(stream);
+  if (precision == 1) {
+    const int rc = rnn_layer_bwd_tc(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
+                                    dc_final, dh0, dc0, s);
+    if (rc >= 0) return rc;
+  }
   StepBwd p{T, B, H, ndir, 0, 0, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0, carry};
   const bool big = B > 256;
   auto go = [&]() {
@@ -386,6 +461,7 @@ extern "C" int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H,
     p.final_only = 1;
     go();
   }
+  note_launches(T - 1 + ((dh0 || dc0) ? 1 : 0));
   SLNLP_LAUNCH_OK("rnn_layer_bwd");
   return 0;
 }

@@ -25,9 +25,11 @@ SIGNATURES = {
     "slnlp_abi_version": [],
     "slnlp_last_error_string": [],
     "slnlp_device_sm_count": [],
+    "slnlp_launch_count": [],
     "slnlp_embed_gather_fwd": [P, P, P, I, I, I, P, P, P, I, F, P, P],
     "slnlp_embed_gather_bwd": [P, P, P, I, I, I, P, P, P, I, F, L, P],
-    "slnlp_gemm_f32": [I, I, I, I, I, P, I, P, I, P, I, P, F, P],
+    "slnlp_gemm_f32": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],
+    "slnlp_gemm_workspace_floats": [],
     "slnlp_gemm_bf16": [I, I, I, I, I, P, I, P, I, P, I, P, F, P],
     "slnlp_colsum_f32": [P, I, I, I, P, F, P],
     "slnlp_rnn_layer_fwd": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
@@ -57,7 +59,8 @@ SIGNATURES = {
     "slnlp_ln_bwd_blocks": [I],
     "slnlp_layernorm_bwd": [P, P, P, P, P, P, P, I, I, P],
 }
-_RESTYPES = {"slnlp_last_error_string": c_char_p}
+_RESTYPES = {"slnlp_last_error_string": c_char_p, "slnlp_launch_count": c_int64,
+             "slnlp_gemm_workspace_floats": c_int64}
 
 for _name, _args in SIGNATURES.items():
     try:

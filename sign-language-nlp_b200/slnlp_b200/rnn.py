@@ -30,6 +30,9 @@ MODE = {"lstm": 0, "gru": 1}
 GATES = {"lstm": 4, "gru": 3}
 
 
+_HAS_GEMM_BF16 = hasattr(lib, "slnlp_gemm_bf16")
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -224,8 +227,16 @@ class RnnEncDecB200(nn.Module):
 
     # ------------------------------------------------------------------ kernels
     def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0, big=False):
-        fn = lib.slnlp_gemm_bf16 if (self.precision == "bf16" and big) else lib.slnlp_gemm_f32
-        check(fn(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, _stream()), "gemm")
+        fn = lib.slnlp_gemm_bf16 if (self.precision == "bf16" and big and _HAS_GEMM_BF16) else lib.slnlp_gemm_f32
+        ws = self._gemm_ws()
+        check(fn(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, ws.data_ptr(), ws.numel(), _stream()), "gemm")
+
+    def _gemm_ws(self):
+        """Split-K scratch shared by every GEMM of this module (one stream per module)."""
+        ws = getattr(self, "_gemm_scratch", None)
+        if ws is None or ws.device != self._flat.device:
+            ws = self._gemm_scratch = torch.empty(lib.slnlp_gemm_workspace_floats(), device=self._flat.device)
+        return ws
 
     def _run_forward(self, ws, X, lengths):
         """X [B,T] int64 cuda, lengths [B] int64 cuda.  Fills ws; returns ws.logp."""
@@ -295,7 +306,7 @@ class RnnEncDecB200(nn.Module):
         E, H, L, G = self.E, self.H, self.L, self.G
         B, T, V = ws.B, ws.T, self.V_tgt
         s = _stream()
-        mode = MODE[self.rnn_type]
+        mode, prec = MODE[self.rnn_type], (1 if self.precision == "bf16" else 0)
         Xp, lp = X.data_ptr(), lengths.data_ptr()
         gp = lambda n: self._ptr(n, gflat)
         drop = ws.train and self.p_rnn > 0.0
@@ -374,7 +385,7 @@ class RnnEncDecB200(nn.Module):
             check(lib.slnlp_concat_dirs(ws.d_enc_final[l].data_ptr(), ws.d_hfin.data_ptr(), B, H, 2, 1, s),
                   "concat_dirs_inv")
             dg, st, out = ws.enc_gates[l].data_ptr(), ws.enc_stash[l].data_ptr(), ws.enc_out[l].data_ptr()
-            check(lib.slnlp_rnn_layer_bwd(mode, 0, T, B, H, 2, dg, st, out, self._ptr(f"{pre}weight_hh_l{l}"),
+            check(lib.slnlp_rnn_layer_bwd(mode, prec, T, B, H, 2, dg, st, out, self._ptr(f"{pre}weight_hh_l{l}"),
                                           lp, None, None, ws.d_seq.data_ptr(), ws.d_hfin.data_ptr(), None,
                                           None, None, ws.carry.data_ptr(), s), "rnn_layer_bwd")
             xin = (ws.emb if l == 0 else ws.enc_xin[l]).data_ptr()

@@ -12,7 +12,7 @@ def declared():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"(?:int|const char\*)\s+(slnlp_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"(?:int64_t|int|const char\*)\s+(slnlp_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
         out[m.group(1)] = n
@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_argument_errors_are_reported_without_a_gpu():
     from slnlp_b200 import _lib
-    rc = _lib.lib.slnlp_gemm_f32(0, 0, 4, 4, 4, None, 4, None, 4, None, 4, None, 0.0, None)
+    rc = _lib.lib.slnlp_gemm_f32(0, 0, 4, 4, 4, None, 4, None, 4, None, 4, None, 0.0, None, 0, None)
     assert rc != 0 and "null" in _lib.last_error()
     rc = _lib.lib.slnlp_rnn_layer_fwd(7, 0, 1, 1, 1, 1, None, None, None, None, None, None, None, None, None, None)
     assert rc != 0 and "mode" in _lib.last_error()

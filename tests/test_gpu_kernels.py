@@ -34,17 +34,34 @@ def test_gemm_f32(tA, tB, M, N, K):
     C0 = cuda(M, N, seed=4)
     C = C0.clone()
     L.check(L.lib.slnlp_gemm_f32(tA, tB, M, N, K, A.data_ptr(), A.shape[1], B.data_ptr(), B.shape[1],
-                                 C.data_ptr(), N, bias.data_ptr(), 0.5, S()))
+                                 C.data_ptr(), N, bias.data_ptr(), 0.5, None, 0, S()))
     ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double() + bias.double() + 0.5 * C0.double()
     assert rel_err(C, ref) < 1e-5
     # strided views (lda > K, ldc > N), no bias, beta = 0
     if not tA and tB and K > 4:
         C2 = torch.zeros(M, N + 3, device="cuda")
         L.check(L.lib.slnlp_gemm_f32(0, 1, M, N, K - 2, A.data_ptr() + 4, K, B.data_ptr() + 8, K,
-                                     C2.data_ptr() + 4, N + 3, None, 0.0, S()))
+                                     C2.data_ptr() + 4, N + 3, None, 0.0, None, 0, S()))
         ref2 = A[:, 1:K - 1].double() @ B[:, 2:K].double().t()
         assert rel_err(C2[:, 1:N + 1], ref2) < 1e-5
         assert float(C2[:, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 128, 3150), (1024, 256, 3200), (128, 64, 700)])
+def test_gemm_f32_split_k_is_deterministic_and_exact(M, N, K):
+    """The dW GEMMs (small M*N, K = B*T): split-K through the caller's workspace."""
+    L = _lib()
+    A, B = cuda(K, M, seed=21), cuda(K, N, seed=22)
+    C0 = cuda(M, N, seed=23)
+    ws = torch.empty(L.lib.slnlp_gemm_workspace_floats(), device="cuda")
+    outs = []
+    for _ in range(2):
+        C = C0.clone()
+        L.check(L.lib.slnlp_gemm_f32(1, 0, M, N, K, A.data_ptr(), M, B.data_ptr(), N, C.data_ptr(), N, None, 1.0,
+                                     ws.data_ptr(), ws.numel(), S()))
+        outs.append(C)
+    assert torch.equal(outs[0], outs[1])                       # fixed summation order
+    assert rel_err(outs[0], A.double().t() @ B.double() + C0.double()) < 1e-5
 
 
 def test_colsum():
@@ -231,7 +248,7 @@ def test_rnn_layer_fwd_bwd_against_oracle(mode, T, B, H, D):
     x_tm = c(x.transpose(0, 1))                                     # [T,B,D]
     gates = torch.empty(T, B, 2, G, H, device="cuda")
     L.check(L.lib.slnlp_gemm_f32(0, 1, T * B, 2 * G * H, D, x_tm.data_ptr(), D, w_ih.data_ptr(), D,
-                                 gates.data_ptr(), 2 * G * H, b_ih.data_ptr(), 0.0, S()))
+                                 gates.data_ptr(), 2 * G * H, b_ih.data_ptr(), 0.0, None, 0, S()))
     out, stash, hfin = torch.empty(T, B, 2 * H, device="cuda"), torch.empty(T, B, 2, H, device="cuda"), torch.empty(2, B, H, device="cuda")
     len_d = lengths.cuda()
     L.check(L.lib.slnlp_rnn_layer_fwd(0 if mode == "lstm" else 1, 0, T, B, H, 2, gates.data_ptr(), w_hh.data_ptr(),
@@ -249,7 +266,7 @@ def test_rnn_layer_fwd_bwd_against_oracle(mode, T, B, H, D):
     dG = gates.view(T * B, 2 * GH)
     # dx and dW_ih / db_ih through the hoisted GEMMs
     dx = torch.empty(T, B, D, device="cuda")
-    L.check(L.lib.slnlp_gemm_f32(0, 0, T * B, D, 2 * GH, dG.data_ptr(), 2 * GH, w_ih.data_ptr(), D, dx.data_ptr(), D, None, 0.0, S()))
+    L.check(L.lib.slnlp_gemm_f32(0, 0, T * B, D, 2 * GH, dG.data_ptr(), 2 * GH, w_ih.data_ptr(), D, dx.data_ptr(), D, None, 0.0, None, 0, S()))
     scale = max(float(t.grad.abs().max()) for v in leaves.values() for t in v)
     assert rel_err(dx.transpose(0, 1), xr.grad) < 2e-5
     dW_ih = (dG.double().t() @ x_tm.view(T * B, D).double())
@@ -371,3 +388,98 @@ def test_pad_fill_concat_dirs_dec_input():
     drow, dsrc = torch.ones(7, device="cuda"), torch.empty(B, 10, device="cuda")
     L.check(L.lib.slnlp_dec_input_bwd(dst.data_ptr(), drow.data_ptr(), dsrc.data_ptr(), B, 7, 10, S()))
     assert rel_err(drow, 1.0 + dst[:, :7].sum(0)) < 1e-6 and torch.equal(dsrc, src)
+
+
+@pytest.mark.parametrize("mode", ["lstm", "gru"])
+@pytest.mark.parametrize("T,B,ragged", [(64, 50, False), (17, 50, True), (5, 3, True), (9, 16, True), (1, 20, False)])
+def test_rnn_layer_tcgen05_path(mode, T, B, ragged):
+    """precision=1: the persistent W_hh-resident tcgen05 kernel (H = 128), bf16 operands with
+    fp32 accumulation.  north_star tolerance for this path: 2e-2 relative; also checked
+    against the fp32 step kernels run on the same inputs."""
+    from oracle import restatement as R
+    from helpers import BF16_RTOL
+    L = _lib()
+    H, D = 128, 64
+    G = 4 if mode == "lstm" else 3
+    md = 0 if mode == "lstm" else 1
+    w, x, lengths = _rnn_inputs(mode, T, B, H, D, seed=900 + T, ragged=ragged)
+    leaves = {k: [t.clone().requires_grad_(True) for t in v] for k, v in w.items()}
+    xr = x.clone().requires_grad_(True)
+    outs, fins = [], []
+    for d in range(2):
+        o, hf = R._run_direction(xr, lengths, leaves["w_ih"][d], leaves["w_hh"][d], leaves["b_ih"][d],
+                                 leaves["b_hh"][d], mode, reverse=(d == 1))
+        outs.append(o)
+        fins.append(hf)
+    out_ref = torch.cat(outs, 2)
+    gq = torch.Generator().manual_seed(5)
+    dout, dfin = torch.randn(B, T, 2 * H, generator=gq), torch.randn(2, B, H, generator=gq)
+    (out_ref * dout).sum().add((torch.stack(fins) * dfin).sum()).backward()
+    c = lambda t: t.cuda().contiguous()
+    w_ih, w_hh = c(torch.cat(w["w_ih"])), c(torch.stack(w["w_hh"]))
+    b_ih, b_hh = c(torch.cat(w["b_ih"])), c(torch.cat(w["b_hh"]))
+    x_tm, len_d = c(x.transpose(0, 1)), lengths.cuda()
+    res = {}
+    for prec in (0, 1):
+        gates = torch.empty(T, B, 2, G, H, device="cuda")
+        L.check(L.lib.slnlp_gemm_f32(0, 1, T * B, 2 * G * H, D, x_tm.data_ptr(), D, w_ih.data_ptr(), D,
+                                     gates.data_ptr(), 2 * G * H, b_ih.data_ptr(), 0.0, None, 0, S()))
+        out, stash, hfin = (torch.empty(T, B, 2 * H, device="cuda"), torch.empty(T, B, 2, H, device="cuda"),
+                            torch.empty(2, B, H, device="cuda"))
+        L.check(L.lib.slnlp_rnn_layer_fwd(md, prec, T, B, H, 2, gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(),
+                                          len_d.data_ptr(), None, None, out.data_ptr(), stash.data_ptr(),
+                                          hfin.data_ptr(), S()))
+        fwd = (out.clone(), hfin.clone())
+        carry = torch.zeros(4, B, H, device="cuda")
+        dout_tm, dfin_d = c(dout.transpose(0, 1)), c(dfin)
+        L.check(L.lib.slnlp_rnn_layer_bwd(md, prec, T, B, H, 2, gates.data_ptr(), stash.data_ptr(), out.data_ptr(),
+                                          w_hh.data_ptr(), len_d.data_ptr(), None, None, dout_tm.data_ptr(),
+                                          dfin_d.data_ptr(), None, None, None, carry.data_ptr(), S()))
+        dx = torch.empty(T, B, D, device="cuda")
+        L.check(L.lib.slnlp_gemm_f32(0, 0, T * B, D, 2 * G * H, gates.data_ptr(), 2 * G * H, w_ih.data_ptr(), D,
+                                     dx.data_ptr(), D, None, 0.0, None, 0, S()))
+        res[prec] = fwd + (dx, gates.clone())
+    torch.cuda.synchronize()
+    for prec, tol in ((0, 1e-5), (1, BF16_RTOL)):
+        out, hfin, dx, dG = res[prec]
+        assert rel_err(out.transpose(0, 1), out_ref) < tol, (prec, "out")
+        assert rel_err(hfin, torch.stack(fins)) < tol, (prec, "h_final")
+        assert rel_err(dx.transpose(0, 1), xr.grad) < 2 * tol, (prec, "dx")
+        dW_ih = dG.view(T * B, -1).double().t() @ x_tm.view(T * B, D).double()
+        assert rel_err(dW_ih, torch.cat([t.grad for t in leaves["w_ih"]]).double()) < 2 * tol, (prec, "dW_ih")
+    # the two CUDA paths agree with each other at bf16 level, and padded positions are exact zeros in both
+    assert rel_err(res[1][0], res[0][0]) < BF16_RTOL
+    pad = (torch.arange(T).view(T, 1) >= lengths.view(1, B)).cuda()
+    assert float(res[1][0][pad].abs().max() if pad.any() else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("mode", ["lstm", "gru"])
+def test_rnn_tcgen05_single_step_initial_state(mode):
+    """tcgen05 path with h0/c0 and gradients to the initial state (T = 1)."""
+    from helpers import BF16_RTOL
+    L = _lib()
+    B, H = 50, 128
+    G = 4 if mode == "lstm" else 3
+    md = 0 if mode == "lstm" else 1
+    g = torch.Generator().manual_seed(321)
+    gates0 = torch.randn(1, B, 1, G, H, generator=g).cuda()
+    w_hh = ((torch.rand(G * H, H, generator=g) * 2 - 1) / H ** 0.5).cuda()
+    b_hh = ((torch.rand(G * H, generator=g) * 2 - 1) / H ** 0.5).cuda()
+    h0 = torch.tanh(torch.randn(B, H, generator=g)).cuda()
+    dh = torch.randn(B, H, generator=g).cuda()
+    res = {}
+    for prec in (0, 1):
+        gates = gates0.clone()
+        out, stash = torch.empty(1, B, H, device="cuda"), torch.empty(1, B, 1, H, device="cuda")
+        L.check(L.lib.slnlp_rnn_layer_fwd(md, prec, 1, B, H, 1, gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), None,
+                                          h0.data_ptr(), h0.data_ptr() if md == 0 else None, out.data_ptr(),
+                                          stash.data_ptr(), None, S()))
+        dh0, dc0, carry = torch.zeros(B, H, device="cuda"), torch.zeros(B, H, device="cuda"), torch.zeros(4, B, H, device="cuda")
+        o = out.clone()
+        L.check(L.lib.slnlp_rnn_layer_bwd(md, prec, 1, B, H, 1, gates.data_ptr(), stash.data_ptr(), out.data_ptr(),
+                                          w_hh.data_ptr(), None, h0.data_ptr(), h0.data_ptr() if md == 0 else None,
+                                          dh.data_ptr(), None, None, dh0.data_ptr(), dc0.data_ptr() if md == 0 else None,
+                                          carry.data_ptr(), S()))
+        res[prec] = (o, dh0 + dc0, gates.clone())
+    for a, b in zip(res[1], res[0]):
+        assert rel_err(a, b) < BF16_RTOL
