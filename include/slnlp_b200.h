@@ -71,6 +71,14 @@ int slnlp_gemm_f32(int transA, int transB, int M, int N, int K,
                    const float* A, int lda, const float* B, int ldb,
                    float* C, int ldc, const float* bias, float beta,
                    float* workspace, int64_t workspace_floats, slnlp_stream_t stream);
+/* Same contraction on the 5th-gen tensor cores: A, B are read as fp32, rounded to bf16 on
+ * the way into shared memory, multiplied by tcgen05.mma kind::f16 with fp32 accumulators
+ * in TMEM.  The 2e-2 path of north_star.  Shapes the tile kernel does not cover (unaligned
+ * k-contiguous operands, M < 64, N < 32, K < 32) are computed by slnlp_gemm_f32. */
+int slnlp_gemm_bf16(int transA, int transB, int M, int N, int K,
+                    const float* A, int lda, const float* B, int ldb,
+                    float* C, int ldc, const float* bias, float beta,
+                    float* workspace, int64_t workspace_floats, slnlp_stream_t stream);
 /* out[c] = beta*out[c] + sum_r A[r*lda + c]   (bias gradients) */
 int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
                      slnlp_stream_t stream);

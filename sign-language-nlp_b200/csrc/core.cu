@@ -373,21 +373,30 @@ __global__ void __launch_bounds__(256) dec_input_bwd_kernel(const float* __restr
     for (int b = 0; b < B; ++b) dsrc[(int64_t)b * W + e - E] = ddst[(int64_t)b * (E + W) + e];
   }
 }
-// out[c] = beta*out[c] + sum_r A[r,c]; one thread column per 32-row slab, deterministic
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int rows, int cols,
-                                                     int lda, float* __restrict__ out, float beta) {
-  __shared__ float sm[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int w = threadIdx.x >> 5;
-  float s = 0.f;
-  if (c < cols)
-    for (int r = w; r < rows; r += 8) s += A[(int64_t)r * lda + c];
-  sm[w][threadIdx.x & 31] = s;
+// out[c] = beta*out[c] + sum_r A[r,c]; 32 columns per CTA, 32 warps stride the rows, fixed
+// combination order (deterministic)
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ A, int rows, int cols,
+                                                      int lda, float* __restrict__ out, float beta) {
+  __shared__ float sm[32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < cols) {
+    int r = w;
+    for (; r + 96 < rows; r += 128) {
+      s0 += A[(int64_t)r * lda + c];
+      s1 += A[(int64_t)(r + 32) * lda + c];
+      s2 += A[(int64_t)(r + 64) * lda + c];
+      s3 += A[(int64_t)(r + 96) * lda + c];
+    }
+    for (; r < rows; r += 32) s0 += A[(int64_t)r * lda + c];
+  }
+  sm[w][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (w == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    for (int i = 0; i < 32; ++i) t += sm[i][lane];
     out[c] = (beta == 0.f ? 0.f : beta * out[c]) + t;
   }
 }
@@ -447,7 +456,7 @@ int slnlp_embed_gather_bwd(float* dtable, const int64_t* idx, const float* dout,
 int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
                      slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(A && out && rows >= 0 && cols > 0 && lda >= cols, "colsum: bad arguments");
-  colsum_kernel<<<ceil_div(cols, 32), 256, 0, as_stream(stream)>>>(A, rows, cols, lda, out, beta);
+  colsum_kernel<<<ceil_div(cols, 32), 1024, 0, as_stream(stream)>>>(A, rows, cols, lda, out, beta);
   SLNLP_LAUNCH_OK("colsum");
   return 0;
 }

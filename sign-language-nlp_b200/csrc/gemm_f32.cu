@@ -234,6 +234,16 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
+// host-side launcher shared with gemm_bf16.cu
+void launch_splitk_reduce(const float* partial, int splits, int M, int N, float* C, int ldc, const float* bias,
+                          float beta, cudaStream_t s) {
+  const int64_t total = (int64_t)M * N;
+  int rg = (int)((total + 255) / 256);
+  if (rg > sm_count() * 4) rg = sm_count() * 4;
+  splitk_reduce_kernel<<<rg, 256, 0, s>>>(partial, splits, M, N, C, ldc, bias, beta);
+  note_launches(1);
+}
+
 }  // namespace slnlp
 
 using namespace slnlp;
@@ -279,13 +289,7 @@ extern "C" int slnlp_gemm_f32(int transA, int transB, int M, int N, int K, const
     else if (!transA && transB) gemm_f32_vec_kernel<true, false><<<vgrid, 256, 0, s>>>(M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
     else if (transA && !transB) gemm_f32_vec_kernel<false, true><<<vgrid, 256, 0, s>>>(M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
     else gemm_f32_vec_kernel<false, false><<<vgrid, 256, 0, s>>>(M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
-    if (partial) {
-      const int64_t total = (int64_t)M * N;
-      int rg = (int)((total + 255) / 256);
-      if (rg > sm_count() * 4) rg = sm_count() * 4;
-      splitk_reduce_kernel<<<rg, 256, 0, s>>>(partial, splits, M, N, C, ldc, bias, beta);
-      note_launches(1);
-    }
+    if (partial) launch_splitk_reduce(partial, splits, M, N, C, ldc, bias, beta, s);
     SLNLP_LAUNCH_OK("gemm_f32");
     return 0;
   }

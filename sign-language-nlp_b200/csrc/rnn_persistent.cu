@@ -15,89 +15,14 @@
 //
 // Numerics: the recurrent product rounds h and W_hh (dG in BPTT) to bf16 with fp32
 // accumulation - the 2e-2 path of north_star.  Everything else is fp32.
-#include <cuda_bf16.h>
-#include "common.cuh"
+#include "tc05.cuh"
 
 namespace slnlp {
 
 constexpr int PH = 128;   // hidden size handled by this kernel
 constexpr int PN = 16;    // sequences per CTA (MMA N)
-constexpr int PTHREADS = 128;
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor):
-// [0,14) start>>4, [16,30) leading (K-direction core-matrix) byte offset>>4,
-// [32,46) stride (M/N-direction core-matrix) byte offset>>4, [46,48) version = 1.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (bit 4), a=b=bf16 (bits 7, 10),
-// both operands K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// canonical K-major no-swizzle placement of element (row, k) of an operand with R rows:
-// 8x8 core matrices (8 rows x 16 bytes), row-groups contiguous (SBO = 128 B), K-groups
-// R/8*128 B apart (LBO).
-__device__ __forceinline__ uint32_t canon_off(int row, int k, int R) {
-  return (uint32_t)((k >> 3) * (R * 16) + (row >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2);
-}
+constexpr int PTHREADS = 512;  // 16 warps: TMEM lane quadrant = warp % 4, column group = warp / 4
+constexpr int PC = PN / 4;     // batch columns per thread
 
 struct PersistFwd {
   int T, B, ndir;
@@ -124,7 +49,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
   const int tid = threadIdx.x, warp = tid >> 5;
   const int d = blockIdx.y, b0 = blockIdx.x * PN;
   const int T = p.T, B = p.B;
-  const int j = tid;  // hidden unit = TMEM lane
+  const int j = tid & (H - 1);   // hidden unit = TMEM lane
+  const int cg = tid >> 7;       // column group: batch columns cg*PC .. cg*PC+PC-1
 
   // ---- one-time setup: W_hh -> bf16 canonical tiles; h tile = h0 or 0
   const float* W = p.w_hh + (int64_t)d * G * H * H;
@@ -140,13 +66,15 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
     const int g = r / H, rr = r % H;
     *reinterpret_cast<uint4*>(sW + g * (H * H * 2) + canon_off(rr, k8 * 8, H)) = pk;
   }
-  float hreg[PN], creg[PN];
+  float hreg[PC], creg[PC];
+  int len[PC];
 #pragma unroll
-  for (int n = 0; n < PN; ++n) {
-    const int b = b0 + n;
-    hreg[n] = (p.h0 && b < B) ? p.h0[((int64_t)d * B + b) * H + j] : 0.f;
-    creg[n] = (p.c0 && b < B) ? p.c0[((int64_t)d * B + b) * H + j] : 0.f;
-    *reinterpret_cast<__nv_bfloat16*>(sH + canon_off(n, j, PN)) = __float2bfloat16(hreg[n]);
+  for (int c = 0; c < PC; ++c) {
+    const int n = cg * PC + c, b = b0 + n;
+    hreg[c] = (p.h0 && b < B) ? p.h0[((int64_t)d * B + b) * H + j] : 0.f;
+    creg[c] = (p.c0 && b < B) ? p.c0[((int64_t)d * B + b) * H + j] : 0.f;
+    len[c] = b < B ? (p.lengths ? (int)p.lengths[b] : T) : 0;
+    *reinterpret_cast<__nv_bfloat16*>(sH + canon_off(n, j, PN)) = __float2bfloat16(hreg[c]);
   }
   if (tid == 0) mbar_init(bar, 1);
   if (warp == 0) tmem_alloc(tmem_slot, 64);
@@ -155,21 +83,28 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_mine = tmem + ((uint32_t)((warp & 3) * 32) << 16) + cg * PC;
   constexpr uint32_t idesc = make_idesc(128, PN);
-  const uint32_t sW_addr = smem_u32(sW), sH_addr = smem_u32(sH);
+  const uint64_t descA0 = make_desc(smem_u32(sW), H * 16, 128), descB0 = make_desc(smem_u32(sH), PN * 16, 128);
   const bool have_state0 = p.h0 != nullptr;
-
-  int len[PN];
-#pragma unroll
-  for (int n = 0; n < PN; ++n) {
-    const int b = b0 + n;
-    len[n] = b < B ? (p.lengths ? (int)p.lengths[b] : T) : 0;
-  }
   const float* bh = p.b_hh + (int64_t)d * G * H;
   float bias[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) bias[g] = bh[g * H + j];
+
+  // hoisted input projection of step 0
+  float xg[G][PC];
+  auto load_x = [&](int t) {
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+      const int b = b0 + cg * PC + c;
+      const bool act = t < len[c];
+      const float* gt = p.gates + ((((int64_t)t * B + (act ? b : 0)) * p.ndir + d) * G) * H + j;
+#pragma unroll
+      for (int g = 0; g < G; ++g) xg[g][c] = act ? gt[g * H] : 0.f;
+    }
+  };
+  load_x(d == 0 ? 0 : T - 1);
 
   uint32_t phase = 0;
   for (int step = 0; step < T; ++step) {
@@ -177,77 +112,74 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
     const bool do_mma = step > 0 || have_state0;
     if (do_mma && tid == 0) {
       // G gate tiles x (H/16) k-steps; A K-step = 2 K-groups of H*16 bytes, B K-step = 2 K-groups of PN*16 bytes
+      // descriptors differ only in the start-address field: base + (byte offset >> 4)
 #pragma unroll
       for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int kk = 0; kk < H / 16; ++kk) {
-          const uint64_t da = make_desc(sW_addr + g * (H * H * 2) + kk * 2 * (H * 16), H * 16, 128);
-          const uint64_t db = make_desc(sH_addr + kk * 2 * (PN * 16), PN * 16, 128);
-          umma_bf16(tmem + g * PN, da, db, idesc, kk > 0 ? 1u : 0u);
-        }
+        for (int kk = 0; kk < H / 16; ++kk)
+          umma_bf16(tmem + g * PN, descA0 + (uint64_t)((g * (H * H * 2) + kk * 2 * (H * 16)) >> 4),
+                    descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk > 0 ? 1u : 0u);
       umma_commit(bar);
     }
     __syncwarp();
-    // hoisted input projection for this step (overlaps the MMAs): xp[t, b, d, g, j]
-    float xg[G][PN];
-#pragma unroll
-    for (int n = 0; n < PN; ++n) {
-      const int b = b0 + n;
-      const bool act = t < len[n];
-      const float* gt = p.gates + ((((int64_t)t * B + (act ? b : 0)) * p.ndir + d) * G) * H + j;
-#pragma unroll
-      for (int g = 0; g < G; ++g) xg[g][n] = act ? gt[g * H] : 0.f;
-    }
-    float acc[G][PN];
+    float acc[G][PC];
     if (do_mma) {
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
 #pragma unroll
-      for (int g = 0; g < G; ++g) tmem_ld16(tmem_lane + g * PN, acc[g]);
+      for (int g = 0; g < G; ++g) tmem_ld4(tmem_mine + g * PN, acc[g]);
     } else {
 #pragma unroll
       for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int n = 0; n < PN; ++n) acc[g][n] = 0.f;
+        for (int c = 0; c < PC; ++c) acc[g][c] = 0.f;
     }
+    float gout[G][PC], hv[PC], sv[PC];
 #pragma unroll
-    for (int n = 0; n < PN; ++n) {
-      const int b = b0 + n;
+    for (int c = 0; c < PC; ++c) {
+      if (G == 4) {
+        const float gi = sigmoid_fast(xg[0][c] + acc[0][c] + bias[0]);
+        const float gf = sigmoid_fast(xg[1][c] + acc[1][c] + bias[1]);
+        const float gg = tanh_fast(xg[2][c] + acc[2][c] + bias[2]);
+        const float go = sigmoid_fast(xg[G - 1][c] + acc[G - 1][c] + bias[G - 1]);
+        const float cn = gf * creg[c] + gi * gg;
+        hv[c] = go * tanh_fast(cn);
+        sv[c] = cn;
+        gout[0][c] = gi; gout[1][c] = gf; gout[2][c] = gg; gout[G - 1][c] = go;
+      } else {
+        const float hn = acc[2][c] + bias[2];
+        const float gr = sigmoid_fast(xg[0][c] + acc[0][c] + bias[0]);
+        const float gz = sigmoid_fast(xg[1][c] + acc[1][c] + bias[1]);
+        const float gn = tanh_fast(xg[2][c] + gr * hn);
+        hv[c] = (1.f - gz) * gn + gz * hreg[c];
+        sv[c] = hn;
+        gout[0][c] = gr; gout[1][c] = gz; gout[2][c] = gn;
+      }
+    }
+    // next step's input projection: issue the loads before this step's stores
+    if (step + 1 < T) load_x(d == 0 ? step + 1 : T - 2 - step);
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+      const int n = cg * PC + c, b = b0 + n;
       if (b >= B) continue;
       const int64_t row = (int64_t)t * B + b;
       float* o = p.out + row * p.ndir * H + (int64_t)d * H + j;
       float* st = p.stash + (row * p.ndir + d) * H + j;
-      if (t >= len[n]) {
+      if (t >= len[c]) {
         *o = 0.f;
         *st = 0.f;
         continue;
       }
       float* gt = p.gates + ((row * p.ndir + d) * G) * H + j;
-      float h;
-      if (G == 4) {
-        const float gi = sigmoidf_(xg[0][n] + acc[0][n] + bias[0]);
-        const float gf = sigmoidf_(xg[1][n] + acc[1][n] + bias[1]);
-        const float gg = tanhf(xg[2][n] + acc[2][n] + bias[2]);
-        const float go = sigmoidf_(xg[G - 1][n] + acc[G - 1][n] + bias[G - 1]);
-        const float c = gf * creg[n] + gi * gg;
-        h = go * tanhf(c);
-        creg[n] = c;
-        gt[0] = gi; gt[H] = gf; gt[2 * H] = gg; gt[3 * H] = go;
-        *st = c;
-      } else {
-        const float hn = acc[2][n] + bias[2];
-        const float gr = sigmoidf_(xg[0][n] + acc[0][n] + bias[0]);
-        const float gz = sigmoidf_(xg[1][n] + acc[1][n] + bias[1]);
-        const float gn = tanhf(xg[2][n] + gr * hn);
-        h = (1.f - gz) * gn + gz * hreg[n];
-        gt[0] = gr; gt[H] = gz; gt[2 * H] = gn;
-        *st = hn;
-      }
-      hreg[n] = h;
-      *o = h;
-      *reinterpret_cast<__nv_bfloat16*>(sH + canon_off(n, j, PN)) = __float2bfloat16(h);
-      if (p.h_final && (d == 0 ? t == len[n] - 1 : t == 0)) p.h_final[((int64_t)d * B + b) * H + j] = h;
+#pragma unroll
+      for (int g = 0; g < G; ++g) gt[g * H] = gout[g][c];
+      *st = sv[c];
+      if (G == 4) creg[c] = sv[c];
+      hreg[c] = hv[c];
+      *o = hv[c];
+      *reinterpret_cast<__nv_bfloat16*>(sH + canon_off(n, j, PN)) = __float2bfloat16(hv[c]);
+      if (p.h_final && (d == 0 ? t == len[c] - 1 : t == 0)) p.h_final[((int64_t)d * B + b) * H + j] = hv[c];
     }
     // h tile (generic-proxy stores) -> visible to the tensor core; accumulators free to overwrite
     fence_async_smem();
@@ -287,13 +219,13 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
   const int tid = threadIdx.x, warp = tid >> 5;
   const int d = blockIdx.y, b0 = blockIdx.x * PN;
   const int T = p.T, B = p.B;
-  const int k = tid;  // hidden unit = TMEM lane = output row of W_hh^T
+  const int k = tid & (H - 1);  // hidden unit = TMEM lane = output row of W_hh^T
+  const int cg = tid >> 7;
 
   const float* W = p.w_hh + (int64_t)d * GH * H;
-  // A'(m = kcol, kk = jrow) = W_hh[jrow][kcol]: thread = column kcol, 8 consecutive rows -> one 16-byte store
-  // (global reads coalesced across the warp, shared stores 16 bytes apart: conflict-free)
-#pragma unroll 2
-  for (int jg = 0; jg < GH / 8; ++jg) {
+  // A'(m = kcol, kk = jrow) = W_hh[jrow][kcol]: thread = column kcol, 8 consecutive rows -> one 16-byte
+  // store (global reads coalesced across the warp, shared stores 16 bytes apart: conflict-free)
+  for (int jg = cg; jg < GH / 8; jg += PTHREADS / H) {
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = __ldg(W + (int64_t)(jg * 8 + u) * H + k);
@@ -312,18 +244,44 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_mine = tmem + ((uint32_t)((warp & 3) * 32) << 16) + cg * PC;
   constexpr uint32_t idesc = make_idesc(128, PN);
-  const uint32_t sW_addr = smem_u32(sW), sD_addr = smem_u32(sD);
+  const uint64_t descA0 = make_desc(smem_u32(sW), H * 16, 128), descB0 = make_desc(smem_u32(sD), PN * 16, 128);
 
-  int len[PN];
-  float carry[PN];  // LSTM: dc carry; GRU: direct dh carry (dh * z)
+  int len[PC];
+  float carry[PC];  // LSTM: dc carry; GRU: direct dh carry (dh * z)
 #pragma unroll
-  for (int n = 0; n < PN; ++n) {
-    const int b = b0 + n;
-    len[n] = b < B ? (p.lengths ? (int)p.lengths[b] : T) : 0;
-    carry[n] = 0.f;
+  for (int c = 0; c < PC; ++c) {
+    const int b = b0 + cg * PC + c;
+    len[c] = b < B ? (p.lengths ? (int)p.lengths[b] : T) : 0;
+    carry[c] = 0.f;
   }
+
+  // per-step operands, loaded one step ahead: activated gates, stash, predecessor state, dout
+  float gin[G][PC], sin_[PC], pin[PC], din[PC];
+  auto load_step = [&](int t) {
+    const int tp = d == 0 ? t - 1 : t + 1;
+    const bool has_prev = tp >= 0 && tp < T;
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+      const int b = b0 + cg * PC + c;
+      const bool act = t < len[c];
+      const int bb = act ? b : 0;
+      const int64_t row = ((int64_t)t * B + bb) * p.ndir + d;
+      const int64_t cidx = ((int64_t)d * B + bb) * H + k;
+#pragma unroll
+      for (int g = 0; g < G; ++g) gin[g][c] = act ? p.gates[row * GH + g * H + k] : 0.f;
+      sin_[c] = act ? p.stash[row * H + k] : 0.f;
+      din[c] = (act && p.dout) ? p.dout[((int64_t)t * B + bb) * p.ndir * H + (int64_t)d * H + k] : 0.f;
+      float pv = 0.f;
+      if (act) {
+        if (G == 4) pv = has_prev ? p.stash[(((int64_t)tp * B + bb) * p.ndir + d) * H + k] : (p.c0 ? p.c0[cidx] : 0.f);
+        else pv = has_prev ? p.out[((int64_t)tp * B + bb) * p.ndir * H + (int64_t)d * H + k] : (p.h0 ? p.h0[cidx] : 0.f);
+      }
+      pin[c] = pv;
+    }
+  };
+  load_step(d == 0 ? T - 1 : 0);
 
   uint32_t phase = 0;
   const int nsteps = T + ((p.dh0 || p.dc0) ? 1 : 0);
@@ -332,94 +290,95 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     const int t = final_only ? (d == 0 ? -1 : T) : (d == 0 ? T - 1 - step : step);
     const bool do_mma = step > 0;
     if (do_mma && tid == 0) {
-#pragma unroll 4
-      for (int kk = 0; kk < GH / 16; ++kk) {
-        const uint64_t da = make_desc(sW_addr + kk * 2 * (H * 16), H * 16, 128);
-        const uint64_t db = make_desc(sD_addr + kk * 2 * (PN * 16), PN * 16, 128);
-        umma_bf16(tmem, da, db, idesc, kk > 0 ? 1u : 0u);
-      }
+#pragma unroll
+      for (int kk = 0; kk < GH / 16; ++kk)
+        umma_bf16(tmem, descA0 + (uint64_t)((kk * 2 * (H * 16)) >> 4), descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4),
+                  idesc, kk > 0 ? 1u : 0u);
       umma_commit(bar);
     }
     __syncwarp();
-    float m[PN];
+    float m[PC];
     if (do_mma) {
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
-      tmem_ld16(tmem_lane, m);
+      tmem_ld4(tmem_mine, m);
     } else {
 #pragma unroll
-      for (int n = 0; n < PN; ++n) m[n] = 0.f;
+      for (int c = 0; c < PC; ++c) m[c] = 0.f;
     }
+    if (final_only) {
 #pragma unroll
-    for (int n = 0; n < PN; ++n) {
-      const int b = b0 + n;
-      if (b >= B) continue;
-      const int64_t cidx = ((int64_t)d * B + b) * H + k;
-      if (final_only) {
+      for (int c = 0; c < PC; ++c) {
+        const int b = b0 + cg * PC + c;
+        if (b >= B) continue;
+        const int64_t cidx = ((int64_t)d * B + b) * H + k;
         if (G == 4) {
-          if (p.dh0) p.dh0[cidx] = m[n];
-          if (p.dc0) p.dc0[cidx] = carry[n];
+          if (p.dh0) p.dh0[cidx] = m[c];
+          if (p.dc0) p.dc0[cidx] = carry[c];
         } else if (p.dh0) {
-          p.dh0[cidx] = m[n] + carry[n];
+          p.dh0[cidx] = m[c] + carry[c];
         }
+      }
+      break;
+    }
+    float dg[G][PC], dst[PC];
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+      const int b = b0 + cg * PC + c;
+      const int64_t cidx = ((int64_t)d * B + (b < B ? b : 0)) * H + k;
+      dst[c] = 0.f;
+      if (t >= len[c]) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) dg[g][c] = 0.f;
         continue;
       }
+      const bool inject = d == 0 ? t == len[c] - 1 : t == 0;
+      float dh = din[c];
+      if (G == 4) {
+        float dc_in;
+        if (inject) {
+          dh += p.dh_final ? p.dh_final[cidx] : 0.f;
+          dc_in = p.dc_final ? p.dc_final[cidx] : 0.f;
+        } else {
+          dh += m[c];
+          dc_in = carry[c];
+        }
+        const float gi = gin[0][c], gf = gin[1][c], gg = gin[2][c], go = gin[G - 1][c];
+        const float tc = tanh_fast(sin_[c]);
+        const float dc = dh * go * (1.f - tc * tc) + dc_in;
+        dg[0][c] = dc * gg * gi * (1.f - gi);
+        dg[1][c] = dc * pin[c] * gf * (1.f - gf);
+        dg[2][c] = dc * gi * (1.f - gg * gg);
+        dg[G - 1][c] = dh * tc * go * (1.f - go);
+        carry[c] = dc * gf;
+      } else {
+        if (inject) dh += p.dh_final ? p.dh_final[cidx] : 0.f;
+        else dh += m[c] + carry[c];
+        const float gr = gin[0][c], gz = gin[1][c], gn = gin[2][c];
+        const float da_n = dh * (1.f - gz) * (1.f - gn * gn);
+        dg[0][c] = da_n * sin_[c] * gr * (1.f - gr);
+        dg[1][c] = dh * (pin[c] - gn) * gz * (1.f - gz);
+        dg[2][c] = da_n;
+        dst[c] = da_n * gr;
+        carry[c] = dh * gz;
+      }
+    }
+    // operands of the next step: issue the loads before this step's stores
+    if (step + 1 < T) load_step(d == 0 ? T - 2 - step : step + 1);
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+      const int n = cg * PC + c, b = b0 + n;
+      if (b >= B) continue;
       const int64_t row = ((int64_t)t * B + b) * p.ndir + d;
       float* gt = p.gates + row * GH + k;
-      float* st = p.stash + row * H + k;
-      float dg[G];
-      float dstash = 0.f;
-      if (t >= len[n]) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) dg[g] = 0.f;
-      } else {
-        const bool inject = d == 0 ? t == len[n] - 1 : t == 0;
-        float dh = p.dout ? p.dout[((int64_t)t * B + b) * p.ndir * H + (int64_t)d * H + k] : 0.f;
-        const int tp = d == 0 ? t - 1 : t + 1;
-        const bool has_prev = tp >= 0 && tp < T;
-        if (G == 4) {
-          float dc_in;
-          if (inject) {
-            dh += p.dh_final ? p.dh_final[cidx] : 0.f;
-            dc_in = p.dc_final ? p.dc_final[cidx] : 0.f;
-          } else {
-            dh += m[n];
-            dc_in = carry[n];
-          }
-          const float gi = gt[0], gf = gt[H], gg = gt[2 * H], go = gt[3 * H];
-          const float c = *st;
-          const float cp = has_prev ? p.stash[(((int64_t)tp * B + b) * p.ndir + d) * H + k]
-                                    : (p.c0 ? p.c0[cidx] : 0.f);
-          const float tc = tanhf(c);
-          const float dc = dh * go * (1.f - tc * tc) + dc_in;
-          dg[0] = dc * gg * gi * (1.f - gi);
-          dg[1] = dc * cp * gf * (1.f - gf);
-          dg[2] = dc * gi * (1.f - gg * gg);
-          dg[G - 1] = dh * tc * go * (1.f - go);
-          carry[n] = dc * gf;
-        } else {
-          if (inject) dh += p.dh_final ? p.dh_final[cidx] : 0.f;
-          else dh += m[n] + carry[n];
-          const float gr = gt[0], gz = gt[H], gn = gt[2 * H];
-          const float hn = *st;
-          const float hp = has_prev ? p.out[((int64_t)tp * B + b) * p.ndir * H + (int64_t)d * H + k]
-                                    : (p.h0 ? p.h0[cidx] : 0.f);
-          const float da_n = dh * (1.f - gz) * (1.f - gn * gn);
-          dg[0] = da_n * hn * gr * (1.f - gr);
-          dg[1] = dh * (hp - gn) * gz * (1.f - gz);
-          dg[2] = da_n;
-          dstash = da_n * gr;
-          carry[n] = dh * gz;
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g) gt[g * H] = dg[g];
-      if (G == 3) *st = dstash;
+      for (int g = 0; g < G; ++g) gt[g * H] = dg[g][c];
+      if (G == 3) p.stash[row * H + k] = dst[c];
       // h-side gradients of this step = next step's B operand: dG[n][g*H + k]
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const float hv = (G == 3 && g == 2) ? dstash : dg[g];
+        const float hv = (G == 3 && g == 2) ? dst[c] : dg[g][c];
         *reinterpret_cast<__nv_bfloat16*>(sD + canon_off(n, g * H + k, PN)) = __float2bfloat16(hv);
       }
     }
@@ -428,6 +387,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     __syncthreads();
     tc_fence_after();
   }
+  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 32);
 }
 

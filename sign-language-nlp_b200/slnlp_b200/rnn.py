@@ -335,7 +335,8 @@ class RnnEncDecB200(nn.Module):
             check(lib.slnlp_colsum_f32(dg, B, GH, GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
             if mode == 0:
                 self._gemm(1, 0, GH, H, B, dg, GH, h0, H, gp(f"{pre}weight_hh_l{l}"), H, None, 1.0)
-                check(lib.slnlp_colsum_f32(dg, B, GH, GH, gp(f"{pre}bias_hh_l{l}"), 1.0, s), "colsum")
+                # LSTM: d b_hh == d b_ih (both add to the same pre-activation)
+                check(lib.slnlp_axpy(gp(f"{pre}bias_hh_l{l}"), gp(f"{pre}bias_ih_l{l}"), 1.0, GH, s), "axpy")
             else:
                 self._gemm(1, 0, 2 * H, H, B, dg, GH, h0, H, gp(f"{pre}weight_hh_l{l}"), H, None, 1.0)
                 self._gemm(1, 0, H, H, B, dst, H, h0, H, gp(f"{pre}weight_hh_l{l}") + 4 * 2 * H * H, H, None, 1.0)
@@ -403,7 +404,8 @@ class RnnEncDecB200(nn.Module):
                     if K > 0:
                         self._gemm(1, 0, GH, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,
                                    gw, H, None, 1.0, big=True)
-                    check(lib.slnlp_colsum_f32(dg + 4 * d * GH, T * B, GH, 2 * GH, gb, 1.0, s), "colsum")
+                    if d == 0:  # LSTM: d b_hh == d b_ih for both directions at once
+                        check(lib.slnlp_axpy(gb, gp(f"{pre}bias_ih_l{l}"), 1.0, 2 * GH, s), "axpy")
                 else:
                     if K > 0:
                         self._gemm(1, 0, 2 * H, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,

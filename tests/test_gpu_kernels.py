@@ -483,3 +483,28 @@ def test_rnn_tcgen05_single_step_initial_state(mode):
         res[prec] = (o, dh0 + dc0, gates.clone())
     for a, b in zip(res[1], res[0]):
         assert rel_err(a, b) < BF16_RTOL
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (3200, 1024, 128), (3200, 256, 1024), (1024, 256, 3200),
+                                   (512, 128, 3150), (200, 72, 136), (100, 128, 256)])
+def test_gemm_bf16_tcgen05(tA, tB, M, N, K):
+    """tcgen05 GEMM (bf16 operands, fp32 TMEM accumulate) vs fp64 on bf16-rounded inputs (tight) and vs
+    the exact product (the 2e-2 budget of the bf16 path)."""
+    from helpers import BF16_RTOL
+    L = _lib()
+    A = cuda(*((K, M) if tA else (M, K)), seed=51)
+    B = cuda(*((N, K) if tB else (K, N)), seed=52)
+    bias, C0 = cuda(N, seed=53), cuda(M, N, seed=54)
+    ws = torch.empty(L.lib.slnlp_gemm_workspace_floats(), device="cuda")
+    C = C0.clone()
+    L.check(L.lib.slnlp_gemm_bf16(tA, tB, M, N, K, A.data_ptr(), A.shape[1], B.data_ptr(), B.shape[1],
+                                  C.data_ptr(), N, bias.data_ptr(), 0.5, ws.data_ptr(), ws.numel(), S()))
+    opA, opB = (A.t() if tA else A), (B.t() if tB else B)
+    rounded = opA.bfloat16().double() @ opB.bfloat16().double() + bias.double() + 0.5 * C0.double()
+    exact = opA.double() @ opB.double() + bias.double() + 0.5 * C0.double()
+    # shapes outside the tile kernel's alignment rules (k-contiguous operand with K % 8 != 0) are
+    # computed by the fp32 kernel: those match the exact product instead of the bf16-rounded one
+    tile_path = (tA or K % 8 == 0) and (not tB or K % 8 == 0)
+    assert rel_err(C, rounded if tile_path else exact) < 1e-5   # exact up to fp32 accumulation order
+    assert rel_err(C, exact) < BF16_RTOL
