@@ -15,7 +15,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libslnlp_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+EXTRA = os.environ.get("SLNLP_NVCC_FLAGS", "").split()
+FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas=-v"]
 
 

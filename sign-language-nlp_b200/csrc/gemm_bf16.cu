@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(GT) gemm_bf16_kernel(int M, int N, int Kfull, 
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * B_BYTES);  // free[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, warp_u = warp_uniform();
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int kbeg = blockIdx.z * kchunk;
   const int K = min(Kfull, kbeg + kchunk);
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(GT) gemm_bf16_kernel(int M, int N, int Kfull, 
     if (i + 1 < nk) load_regs(kbeg + (i + 1) * TK);  // next tile's loads fly while this tile's MMAs run
     fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < TK / 16; ++kk)

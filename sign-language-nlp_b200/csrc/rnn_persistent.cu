@@ -23,6 +23,15 @@ constexpr int PH = 128;   // hidden size handled by this kernel
 constexpr int PN = 16;    // sequences per CTA (MMA N)
 constexpr int PTHREADS = 512;  // 16 warps: TMEM lane quadrant = warp % 4, column group = warp / 4
 constexpr int PC = PN / 4;     // batch columns per thread
+constexpr int NACC = 4;        // BPTT: partial accumulators (independent MMA chains)
+
+#ifdef SLNLP_PERSIST_TIMING
+// debug build only: per-phase cycle counters of CTA (0,0), read back by slnlp_debug_persist_clocks
+__device__ unsigned long long g_clk[8];
+#define CLK(i, expr) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 200)) { expr; } } while (0)
+#else
+#define CLK(i, expr) do { } while (0)
+#endif
 
 struct PersistFwd {
   int T, B, ndir;
@@ -46,7 +55,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
   uint64_t* bar = reinterpret_cast<uint64_t*>(sH + PN * H * 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, warp_u = warp_uniform();
   const int d = blockIdx.y, b0 = blockIdx.x * PN;
   const int T = p.T, B = p.B;
   const int j = tid & (H - 1);   // hidden unit = TMEM lane
@@ -92,16 +101,34 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
 #pragma unroll
   for (int g = 0; g < G; ++g) bias[g] = bh[g * H + j];
 
-  // hoisted input projection of step 0
+  // per-column base pointers; a timestep only adds t * (row stride) to them
+  const int64_t gstride = (int64_t)B * p.ndir * G * H, ostride = (int64_t)B * p.ndir * H;
+  float* gbase[PC];
+  float* obase[PC];
+  float* sbase[PC];
+  float* fin[PC];
+  uint32_t hoff[PC];
+  bool valid[PC];
+#pragma unroll
+  for (int c = 0; c < PC; ++c) {
+    const int n = cg * PC + c;
+    valid[c] = b0 + n < B;
+    const int b = valid[c] ? b0 + n : 0;
+    gbase[c] = p.gates + ((int64_t)b * p.ndir + d) * G * H + j;
+    obase[c] = p.out + (int64_t)b * p.ndir * H + (int64_t)d * H + j;
+    sbase[c] = p.stash + ((int64_t)b * p.ndir + d) * H + j;
+    fin[c] = p.h_final ? p.h_final + ((int64_t)d * B + b) * H + j : nullptr;
+    hoff[c] = canon_off(n, j, PN);
+  }
+  // hoisted input projection, loaded one step ahead
   float xg[G][PC];
   auto load_x = [&](int t) {
+    const int64_t off = (int64_t)t * gstride;
 #pragma unroll
     for (int c = 0; c < PC; ++c) {
-      const int b = b0 + cg * PC + c;
       const bool act = t < len[c];
-      const float* gt = p.gates + ((((int64_t)t * B + (act ? b : 0)) * p.ndir + d) * G) * H + j;
 #pragma unroll
-      for (int g = 0; g < G; ++g) xg[g][c] = act ? gt[g * H] : 0.f;
+      for (int g = 0; g < G; ++g) xg[g][c] = act ? gbase[c][off + g * H] : 0.f;
     }
   };
   load_x(d == 0 ? 0 : T - 1);
@@ -110,31 +137,49 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
   for (int step = 0; step < T; ++step) {
     const int t = d == 0 ? step : T - 1 - step;
     const bool do_mma = step > 0 || have_state0;
-    if (do_mma && tid == 0) {
-      // G gate tiles x (H/16) k-steps; A K-step = 2 K-groups of H*16 bytes, B K-step = 2 K-groups of PN*16 bytes
-      // descriptors differ only in the start-address field: base + (byte offset >> 4)
+#ifdef SLNLP_PERSIST_TIMING
+    long long c0 = clock64(), c1 = c0, c2 = c0, c3 = c0, c4 = c0, c5 = c0;
+#endif
+    if (do_mma && warp_u == 0 && elect_one()) {
+      // G gate tiles x (H/16) k-steps; descriptors differ only in the start-address field
+      // issued k-major so that consecutive MMAs accumulate into different gate tiles
 #pragma unroll
-      for (int g = 0; g < G; ++g)
+      for (int kk = 0; kk < H / 16; ++kk)
 #pragma unroll
-        for (int kk = 0; kk < H / 16; ++kk)
+        for (int g = 0; g < G; ++g)
           umma_bf16(tmem + g * PN, descA0 + (uint64_t)((g * (H * H * 2) + kk * 2 * (H * 16)) >> 4),
                     descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk > 0 ? 1u : 0u);
       umma_commit(bar);
     }
     __syncwarp();
+#ifdef SLNLP_PERSIST_TIMING
+    c1 = clock64();
+#endif
     float acc[G][PC];
     if (do_mma) {
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
+#ifdef SLNLP_PERSIST_TIMING
+      c2 = clock64();
+#endif
+      uint32_t raw[G][4];
 #pragma unroll
-      for (int g = 0; g < G; ++g) tmem_ld4(tmem_mine + g * PN, acc[g]);
+      for (int g = 0; g < G; ++g) tmem_ld4_nowait(tmem_mine + g * PN, raw[g]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int c = 0; c < PC; ++c) acc[g][c] = __uint_as_float(raw[g][c]);
     } else {
 #pragma unroll
       for (int g = 0; g < G; ++g)
 #pragma unroll
         for (int c = 0; c < PC; ++c) acc[g][c] = 0.f;
     }
+#ifdef SLNLP_PERSIST_TIMING
+    c3 = clock64();
+#endif
     float gout[G][PC], hv[PC], sv[PC];
 #pragma unroll
     for (int c = 0; c < PC; ++c) {
@@ -159,33 +204,46 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
     }
     // next step's input projection: issue the loads before this step's stores
     if (step + 1 < T) load_x(d == 0 ? step + 1 : T - 2 - step);
+    const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride;
 #pragma unroll
     for (int c = 0; c < PC; ++c) {
-      const int n = cg * PC + c, b = b0 + n;
-      if (b >= B) continue;
-      const int64_t row = (int64_t)t * B + b;
-      float* o = p.out + row * p.ndir * H + (int64_t)d * H + j;
-      float* st = p.stash + (row * p.ndir + d) * H + j;
+      if (!valid[c]) continue;
       if (t >= len[c]) {
-        *o = 0.f;
-        *st = 0.f;
+        obase[c][ooff] = 0.f;
+        sbase[c][ooff] = 0.f;
         continue;
       }
-      float* gt = p.gates + ((row * p.ndir + d) * G) * H + j;
 #pragma unroll
-      for (int g = 0; g < G; ++g) gt[g * H] = gout[g][c];
-      *st = sv[c];
+      for (int g = 0; g < G; ++g) gbase[c][goff + g * H] = gout[g][c];
+      sbase[c][ooff] = sv[c];
       if (G == 4) creg[c] = sv[c];
       hreg[c] = hv[c];
-      *o = hv[c];
-      *reinterpret_cast<__nv_bfloat16*>(sH + canon_off(n, j, PN)) = __float2bfloat16(hv[c]);
-      if (p.h_final && (d == 0 ? t == len[c] - 1 : t == 0)) p.h_final[((int64_t)d * B + b) * H + j] = hv[c];
+      obase[c][ooff] = hv[c];
+      *reinterpret_cast<__nv_bfloat16*>(sH + hoff[c]) = __float2bfloat16(hv[c]);
+      if (fin[c] && (d == 0 ? t == len[c] - 1 : t == 0)) *fin[c] = hv[c];
     }
     // h tile (generic-proxy stores) -> visible to the tensor core; accumulators free to overwrite
+#ifdef SLNLP_PERSIST_TIMING
+    c4 = clock64();
+#endif
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+#ifdef SLNLP_PERSIST_TIMING
+    c5 = clock64();
+    if (blockIdx.x == 0 && blockIdx.y == 0 && step > 0) {
+      if (tid < 32 && c1 - c0 > 200) { atomicAdd(&g_clk[0], (unsigned long long)(c1 - c0)); }     // MMA issue (elected lane)
+      if (tid == 200) {
+        atomicAdd(&g_clk[1], (unsigned long long)(c2 - c1));   // wait for MMA completion
+        atomicAdd(&g_clk[2], (unsigned long long)(c3 - c2));   // tmem ld
+        atomicAdd(&g_clk[3], (unsigned long long)(c4 - c3));   // compute + prefetch issue + stores
+        atomicAdd(&g_clk[4], (unsigned long long)(c5 - c4));   // fences + syncthreads
+        atomicAdd(&g_clk[5], (unsigned long long)(c5 - c0));   // whole step
+        atomicAdd(&g_clk[6], 1ull);
+      }
+    }
+#endif
   }
   if (warp == 0) tmem_dealloc(tmem, 64);
 }
@@ -216,7 +274,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
   uint64_t* bar = reinterpret_cast<uint64_t*>(sD + PN * GH * 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, warp_u = warp_uniform();
   const int d = blockIdx.y, b0 = blockIdx.x * PN;
   const int T = p.T, B = p.B;
   const int k = tid & (H - 1);  // hidden unit = TMEM lane = output row of W_hh^T
@@ -238,7 +296,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
   }
   for (int e = tid; e < PN * GH / 8; e += PTHREADS) reinterpret_cast<uint4*>(sD)[e] = make_uint4(0, 0, 0, 0);
   if (tid == 0) mbar_init(bar, 1);
-  if (warp == 0) tmem_alloc(tmem_slot, 32);
+  if (warp == 0) tmem_alloc(tmem_slot, 64);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -257,26 +315,44 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     carry[c] = 0.f;
   }
 
+  // per-column base pointers; a timestep only adds t * (row stride) to them
+  const int64_t gstride = (int64_t)B * p.ndir * GH, ostride = (int64_t)B * p.ndir * H;
+  float* gbase[PC];
+  float* sbase[PC];
+  const float* obase[PC];
+  const float* dbase[PC];
+  int64_t cidx[PC];
+  uint32_t doff[PC];
+  bool valid[PC];
+#pragma unroll
+  for (int c = 0; c < PC; ++c) {
+    const int n = cg * PC + c;
+    valid[c] = b0 + n < B;
+    const int b = valid[c] ? b0 + n : 0;
+    gbase[c] = p.gates + ((int64_t)b * p.ndir + d) * GH + k;
+    sbase[c] = p.stash + ((int64_t)b * p.ndir + d) * H + k;
+    obase[c] = p.out + (int64_t)b * p.ndir * H + (int64_t)d * H + k;
+    dbase[c] = p.dout ? p.dout + (int64_t)b * p.ndir * H + (int64_t)d * H + k : nullptr;
+    cidx[c] = ((int64_t)d * B + b) * H + k;
+    doff[c] = canon_off(n, k, PN);
+  }
   // per-step operands, loaded one step ahead: activated gates, stash, predecessor state, dout
   float gin[G][PC], sin_[PC], pin[PC], din[PC];
   auto load_step = [&](int t) {
     const int tp = d == 0 ? t - 1 : t + 1;
     const bool has_prev = tp >= 0 && tp < T;
+    const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride, poff = (int64_t)tp * ostride;
 #pragma unroll
     for (int c = 0; c < PC; ++c) {
-      const int b = b0 + cg * PC + c;
       const bool act = t < len[c];
-      const int bb = act ? b : 0;
-      const int64_t row = ((int64_t)t * B + bb) * p.ndir + d;
-      const int64_t cidx = ((int64_t)d * B + bb) * H + k;
 #pragma unroll
-      for (int g = 0; g < G; ++g) gin[g][c] = act ? p.gates[row * GH + g * H + k] : 0.f;
-      sin_[c] = act ? p.stash[row * H + k] : 0.f;
-      din[c] = (act && p.dout) ? p.dout[((int64_t)t * B + bb) * p.ndir * H + (int64_t)d * H + k] : 0.f;
+      for (int g = 0; g < G; ++g) gin[g][c] = act ? gbase[c][goff + g * H] : 0.f;
+      sin_[c] = act ? sbase[c][ooff] : 0.f;
+      din[c] = (act && dbase[c]) ? dbase[c][ooff] : 0.f;
       float pv = 0.f;
       if (act) {
-        if (G == 4) pv = has_prev ? p.stash[(((int64_t)tp * B + bb) * p.ndir + d) * H + k] : (p.c0 ? p.c0[cidx] : 0.f);
-        else pv = has_prev ? p.out[((int64_t)tp * B + bb) * p.ndir * H + (int64_t)d * H + k] : (p.h0 ? p.h0[cidx] : 0.f);
+        if (G == 4) pv = has_prev ? sbase[c][poff] : (p.c0 ? p.c0[cidx[c]] : 0.f);
+        else pv = has_prev ? obase[c][poff] : (p.h0 ? p.h0[cidx[c]] : 0.f);
       }
       pin[c] = pv;
     }
@@ -289,11 +365,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     const bool final_only = step == T;
     const int t = final_only ? (d == 0 ? -1 : T) : (d == 0 ? T - 1 - step : step);
     const bool do_mma = step > 0;
-    if (do_mma && tid == 0) {
+    if (do_mma && warp_u == 0 && elect_one()) {
+      // NACC partial accumulators: consecutive MMAs are independent, the epilogue adds them
 #pragma unroll
       for (int kk = 0; kk < GH / 16; ++kk)
-        umma_bf16(tmem, descA0 + (uint64_t)((kk * 2 * (H * 16)) >> 4), descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4),
-                  idesc, kk > 0 ? 1u : 0u);
+        umma_bf16(tmem + (kk % NACC) * PN, descA0 + (uint64_t)((kk * 2 * (H * 16)) >> 4),
+                  descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk >= NACC ? 1u : 0u);
       umma_commit(bar);
     }
     __syncwarp();
@@ -302,7 +379,17 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
-      tmem_ld4(tmem_mine, m);
+      uint32_t raw[NACC][4];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) tmem_ld4_nowait(tmem_mine + a * PN, raw[a]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < PC; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc += __uint_as_float(raw[a][c]);
+        m[c] = acc;
+      }
     } else {
 #pragma unroll
       for (int c = 0; c < PC; ++c) m[c] = 0.f;
@@ -310,14 +397,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     if (final_only) {
 #pragma unroll
       for (int c = 0; c < PC; ++c) {
-        const int b = b0 + cg * PC + c;
-        if (b >= B) continue;
-        const int64_t cidx = ((int64_t)d * B + b) * H + k;
+        if (!valid[c]) continue;
         if (G == 4) {
-          if (p.dh0) p.dh0[cidx] = m[c];
-          if (p.dc0) p.dc0[cidx] = carry[c];
+          if (p.dh0) p.dh0[cidx[c]] = m[c];
+          if (p.dc0) p.dc0[cidx[c]] = carry[c];
         } else if (p.dh0) {
-          p.dh0[cidx] = m[c] + carry[c];
+          p.dh0[cidx[c]] = m[c] + carry[c];
         }
       }
       break;
@@ -325,8 +410,6 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     float dg[G][PC], dst[PC];
 #pragma unroll
     for (int c = 0; c < PC; ++c) {
-      const int b = b0 + cg * PC + c;
-      const int64_t cidx = ((int64_t)d * B + (b < B ? b : 0)) * H + k;
       dst[c] = 0.f;
       if (t >= len[c]) {
 #pragma unroll
@@ -338,8 +421,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
       if (G == 4) {
         float dc_in;
         if (inject) {
-          dh += p.dh_final ? p.dh_final[cidx] : 0.f;
-          dc_in = p.dc_final ? p.dc_final[cidx] : 0.f;
+          dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
+          dc_in = p.dc_final ? p.dc_final[cidx[c]] : 0.f;
         } else {
           dh += m[c];
           dc_in = carry[c];
@@ -353,7 +436,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
         dg[G - 1][c] = dh * tc * go * (1.f - go);
         carry[c] = dc * gf;
       } else {
-        if (inject) dh += p.dh_final ? p.dh_final[cidx] : 0.f;
+        if (inject) dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
         else dh += m[c] + carry[c];
         const float gr = gin[0][c], gz = gin[1][c], gn = gin[2][c];
         const float da_n = dh * (1.f - gz) * (1.f - gn * gn);
@@ -366,20 +449,19 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     }
     // operands of the next step: issue the loads before this step's stores
     if (step + 1 < T) load_step(d == 0 ? T - 2 - step : step + 1);
+    const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride;
 #pragma unroll
     for (int c = 0; c < PC; ++c) {
-      const int n = cg * PC + c, b = b0 + n;
-      if (b >= B) continue;
-      const int64_t row = ((int64_t)t * B + b) * p.ndir + d;
-      float* gt = p.gates + row * GH + k;
+      if (!valid[c]) continue;
 #pragma unroll
-      for (int g = 0; g < G; ++g) gt[g * H] = dg[g][c];
-      if (G == 3) p.stash[row * H + k] = dst[c];
-      // h-side gradients of this step = next step's B operand: dG[n][g*H + k]
+      for (int g = 0; g < G; ++g) gbase[c][goff + g * H] = dg[g][c];
+      if (G == 3) sbase[c][ooff] = dst[c];
+      // h-side gradients of this step = next step's B operand: dG[n][g*H + k]; consecutive
+      // gates are H/8 K-groups apart in the canonical tile
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const float hv = (G == 3 && g == 2) ? dst[c] : dg[g][c];
-        *reinterpret_cast<__nv_bfloat16*>(sD + canon_off(n, g * H + k, PN)) = __float2bfloat16(hv);
+        *reinterpret_cast<__nv_bfloat16*>(sD + doff[c] + g * (H / 8) * (PN * 16)) = __float2bfloat16(hv);
       }
     }
     fence_async_smem();
@@ -388,7 +470,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     tc_fence_after();
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 32);
+  if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
 static size_t persist_fwd_smem(int G) { return (size_t)G * PH * PH * 2 + PN * PH * 2 + 64; }
@@ -436,3 +518,12 @@ int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, floa
 }
 
 }  // namespace slnlp
+
+#ifdef SLNLP_PERSIST_TIMING
+extern "C" int slnlp_debug_persist_clocks(unsigned long long* out8, int reset) {
+  unsigned long long z[8] = {0};
+  if (cudaMemcpyFromSymbol(out8, slnlp::g_clk, sizeof(z)) != cudaSuccess) return 1;
+  if (reset && cudaMemcpyToSymbol(slnlp::g_clk, z, sizeof(z)) != cudaSuccess) return 1;
+  return 0;
+}
+#endif
