@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg1", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("SLNLP_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("SLNLP_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--dp", action="store_true", help="data-parallel one global batch (NCCL all-reduce)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
