@@ -169,6 +169,42 @@ int slnlp_sgd_momentum_clip(float* p, const float* g, float* buf, int64_t n,
                             const float* hyper, const float* norm, float grad_scale,
                             slnlp_stream_t stream);
 
+/* ---- K13: nn.Transformer pieces (model/transformer.py:40-45,82-87; post-norm, ReLU, LayerNorm
+ * eps 1e-5).  The projections are slnlp_gemm_*; the FFN activation is slnlp_relu_*.
+ *
+ * Scaled-dot-product attention of nn.MultiheadAttention, FlashAttention-style (no S x S matrix
+ * in HBM).  Row (b*Sq + i) of q / o and row (b*Sk + j) of k / v hold all heads; head h is
+ * columns [h*dh, (h+1)*dh); ldq/ldk/ldv/ldo are row strides in floats, so q, k, v may point
+ * into one packed in-projection buffer.  dh a multiple of 4, <= 256.
+ * causal != 0: key j > query i is masked (the reference applies this to the ENCODER self-
+ * attention, model/transformer.py:68,84).  key_tokens [B,Sk] int64 (may be NULL): key j of
+ * sequence b is masked when key_tokens[b,j] == pad_idx (src_key_padding_mask, util.py:45-61).
+ * A row whose keys are all masked yields NaN, as torch.  lse [B,nhead,Sq] is saved for backward.
+ * p_drop > 0: dropout on the attention weights with Philox(rng, site, element). */
+int slnlp_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                  float* o, int ldo, float* lse, int B, int Sq, int Sk, int nhead, int dh,
+                  int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                  const uint64_t* rng, uint32_t site, slnlp_stream_t stream);
+/* o = forward output, dout = d o; dvec: workspace [B,nhead,Sq].  dq / dk / dv are written (not
+ * accumulated) with the leading dimensions of q / k / v.  Deterministic (no atomics). */
+int slnlp_mha_bwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                  const float* o, const float* dout, int ldo, const float* lse, float* dvec,
+                  float* dq, float* dk, float* dv, int B, int Sq, int Sk, int nhead, int dh,
+                  int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                  const uint64_t* rng, uint32_t site, slnlp_stream_t stream);
+/* y = LayerNorm(x + res) * gamma + beta over rows of E floats (res may be NULL;
+ * E <= 1024).  mean / rstd [rows] (may be NULL at inference) are saved for backward. */
+int slnlp_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
+                            float* y, float* mean, float* rstd, int rows, int E, float eps,
+                            slnlp_stream_t stream);
+/* dx (= d x = d res) from dy; accumulate != 0 adds into dx.  partials: workspace of
+ * slnlp_ln_bwd_blocks(rows) * 2 * E floats; row-block sums of d gamma (first E) and d beta
+ * (next E) - reduce them with slnlp_colsum_f32(partials, blocks, 2E, 2E, ...). */
+int slnlp_ln_bwd_blocks(int rows);
+int slnlp_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma,
+                        const float* mean, const float* rstd, float* dx, float* partials,
+                        int rows, int E, int accumulate, slnlp_stream_t stream);
+
 int slnlp_relu_fwd(float* x, int64_t n, slnlp_stream_t stream);
 /* dx = dy * (y > 0) in place on dy */
 int slnlp_relu_bwd(float* dy, const float* y, int64_t n, slnlp_stream_t stream);

@@ -74,6 +74,28 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   __syncthreads();
   return red[32];
 }
+// Philox4x32-10 counter RNG shared by every dropout site (own stream: torch's cannot be matched)
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// one uniform in [0,1) per (element index, site) under the module's (seed, step) state
+__device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t step, uint32_t site, uint64_t q, float (&u)[4]) {
+  uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32) ^ (site * 0x9E3779B9u), (uint32_t)step, (uint32_t)(step >> 32)};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) u[j] = (float)(c[j] >> 8) * (1.0f / 16777216.0f);
+}
 // full-precision gate nonlinearities of the fp32 path (expf/tanhf, no fast-math)
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 #endif

@@ -268,20 +268,6 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
 }
 
 // ------------------------------------------------------------------ dropout (Philox4x32-10)
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-}
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-}
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x,
                                                       float* __restrict__ y, int64_t n, float p,
                                                       const uint64_t* __restrict__ rng, uint32_t site) {

@@ -1,0 +1,578 @@
+// K13: Transformer attention + LayerNorm kernels (nn.Transformer as used by
+// model/transformer.py:40-45,82-87: post-norm, ReLU, LayerNorm eps 1e-5).
+//
+//   slnlp_mha_fwd / slnlp_mha_bwd   scaled-dot-product attention of nn.MultiheadAttention,
+//       FlashAttention-style: scores, mask (causal and/or key padding), softmax, attention
+//       dropout and P.V per (sequence, head, 64-query tile) with an online softmax over
+//       64-key tiles; the S x S matrix never reaches HBM.  Backward recomputes P from the
+//       saved row log-sum-exp: one pass per query tile for dQ, one per key tile for dK/dV,
+//       so there are no atomics and the result is deterministic.
+//   slnlp_add_layernorm_fwd / slnlp_layernorm_bwd   y = LN(x + res): the residual add is
+//       fused into the normalisation, one warp per row, warp-shuffle reductions.
+//
+// fp32 FMA arithmetic: at the reference's shapes (S = tens of frames, head dim <= 256) the
+// attention is a few MFLOP per (sequence, head) and bound by reading Q/K/V once; the
+// projections around it are the GEMMs (gemm_bf16.cu / gemm_f32.cu).
+#include "common.cuh"
+
+namespace slnlp {
+
+struct MhaArgs {
+  const float *q, *k, *v;
+  int ldq, ldk, ldv;
+  float* o;            // fwd: out; bwd: forward output (for D = rowsum(dO * O))
+  const float* dout;   // bwd
+  int ldo;
+  float* lse;          // [B, nhead, Sq] row log-sum-exp (fwd: written, bwd: read)
+  float* dvec;         // [B, nhead, Sq] D (bwd: written by the dQ pass, read by the dK/dV pass)
+  float *dq, *dk, *dv; // bwd, same leading dimensions as q / k / v
+  int B, Sq, Sk, nhead, dh, causal;
+  const int64_t* key_tokens;  // [B, Sk] or NULL: key j of sequence b is masked when == pad_idx
+  int64_t pad_idx;
+  float scale, p_drop;
+  const uint64_t* rng;
+  uint32_t site;
+};
+
+// thread layout of every tile product: 256 threads = 16 x 16, thread (ty, tx) owns rows
+// ty*RPT + r and columns tx + 16*c (strided columns keep shared-memory reads conflict-free)
+template <int RPT>
+struct Tile {
+  static constexpr int N = 16 * RPT;   // tile edge (queries and keys)
+};
+
+__device__ __forceinline__ float half_warp_max(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// rows [r0, r0+N) of a [rows, ld] matrix (head columns [0, dh)) -> smem tile [N][dh+1], zero-filled
+template <int N>
+__device__ __forceinline__ void load_tile(float* s, const float* g, int ld, int r0, int rows, int dh, float mul) {
+  const int st = dh + 1;
+  for (int e = threadIdx.x; e < N * (dh >> 2); e += blockDim.x) {
+    const int r = e / (dh >> 2), c4 = (e % (dh >> 2)) << 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + r < rows) v = *reinterpret_cast<const float4*>(g + (int64_t)(r0 + r) * ld + c4);
+    float* d = s + r * st + c4;
+    d[0] = v.x * mul; d[1] = v.y * mul; d[2] = v.z * mul; d[3] = v.w * mul;
+  }
+}
+
+// s[r][c] = <A[ty*RPT+r, :], Bm[tx+16c, :]>
+template <int RPT>
+__device__ __forceinline__ void tile_dot(const float* sA, const float* sB, int dh, int ty, int tx, float (&s)[RPT][RPT]) {
+  const int st = dh + 1;
+#pragma unroll
+  for (int r = 0; r < RPT; ++r)
+#pragma unroll
+    for (int c = 0; c < RPT; ++c) s[r][c] = 0.f;
+  const float* a = sA + ty * RPT * st;
+  const float* b = sB + tx * st;
+#pragma unroll 4
+  for (int d = 0; d < dh; ++d) {
+    float av[RPT], bv[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) av[r] = a[r * st + d];
+#pragma unroll
+    for (int c = 0; c < RPT; ++c) bv[c] = b[c * 16 * st + d];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+      for (int c = 0; c < RPT; ++c) s[r][c] = fmaf(av[r], bv[c], s[r][c]);
+  }
+}
+
+__device__ __forceinline__ bool masked(const MhaArgs& p, const int64_t* ktok, int i, int j) {
+  if (j >= p.Sk) return true;
+  if (p.causal && j > i) return true;
+  return ktok != nullptr && ktok[j] == p.pad_idx;
+}
+
+// dropout keep-factor (0 or 1/(1-p)) of attention weight (b, h, i, j)
+__device__ __forceinline__ float drop_factor(const MhaArgs& p, uint64_t seed, uint64_t step, int bh, int i, int j) {
+  const uint64_t e = ((uint64_t)bh * p.Sq + i) * p.Sk + j;
+  float u[4];
+  philox_uniform4(seed, step, p.site, e >> 2, u);
+  return u[e & 3] < 1.f - p.p_drop ? 1.f / (1.f - p.p_drop) : 0.f;
+}
+
+// grid (ceil(Sq/N), nhead, B), block 256.  smem: Q, K, V tiles [N][dh+1] + P [N][N+1].
+template <int RPT, int NDC>
+__global__ void __launch_bounds__(256) mha_fwd_kernel(MhaArgs p) {
+  constexpr int N = Tile<RPT>::N;
+  extern __shared__ float sm[];
+  const int dh = p.dh, st = dh + 1;
+  float* sQ = sm;
+  float* sK = sQ + N * st;
+  float* sV = sK + N * st;
+  float* sP = sV + N * st;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i0 = blockIdx.x * N, h = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.nhead + h;
+  const float* q = p.q + (int64_t)b * p.Sq * p.ldq + h * dh;
+  const float* k = p.k + (int64_t)b * p.Sk * p.ldk + h * dh;
+  const float* v = p.v + (int64_t)b * p.Sk * p.ldv + h * dh;
+  const int64_t* ktok = p.key_tokens ? p.key_tokens + (int64_t)b * p.Sk : nullptr;
+  const bool drop = p.p_drop > 0.f;
+  const uint64_t seed = drop ? p.rng[0] : 0, step = drop ? p.rng[1] : 0;
+
+  load_tile<N>(sQ, q, p.ldq, i0, p.Sq, dh, p.scale);
+  float m[RPT], l[RPT], acc[RPT][NDC];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    m[r] = -INFINITY;
+    l[r] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NDC; ++n) acc[r][n] = 0.f;
+  }
+  for (int k0 = 0; k0 < p.Sk; k0 += N) {
+    if (p.causal && k0 > i0 + N - 1) break;
+    __syncthreads();
+    load_tile<N>(sK, k, p.ldk, k0, p.Sk, dh, 1.f);
+    load_tile<N>(sV, v, p.ldv, k0, p.Sk, dh, 1.f);
+    __syncthreads();
+    float s[RPT][RPT];
+    tile_dot<RPT>(sQ, sK, dh, ty, tx, s);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int i = i0 + ty * RPT + r;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < RPT; ++c) {
+        if (masked(p, ktok, i, k0 + tx + 16 * c)) s[r][c] = -INFINITY;
+        mx = fmaxf(mx, s[r][c]);
+      }
+      mx = half_warp_max(mx);
+      const float mn = fmaxf(m[r], mx);
+      const float corr = mn == -INFINITY ? 1.f : expf(m[r] - mn);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < RPT; ++c) {
+        float e = mn == -INFINITY ? 0.f : expf(s[r][c] - mn);
+        sum += e;
+        if (drop && e != 0.f) e *= drop_factor(p, seed, step, bh, i, k0 + tx + 16 * c);
+        sP[(ty * RPT + r) * (N + 1) + tx + 16 * c] = e;
+      }
+      sum = half_warp_sum(sum);
+      l[r] = l[r] * corr + sum;
+      m[r] = mn;
+#pragma unroll
+      for (int n = 0; n < NDC; ++n) acc[r][n] *= corr;
+    }
+    __syncthreads();
+    // acc[r][n] += sum_j P[row r][j] V[j][tx + 16 n]
+#pragma unroll 2
+    for (int j = 0; j < N; ++j) {
+      float pv[RPT], vv[NDC];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) pv[r] = sP[(ty * RPT + r) * (N + 1) + j];
+#pragma unroll
+      for (int n = 0; n < NDC; ++n) vv[n] = tx + 16 * n < dh ? sV[j * st + tx + 16 * n] : 0.f;
+#pragma unroll
+      for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int n = 0; n < NDC; ++n) acc[r][n] = fmaf(pv[r], vv[n], acc[r][n]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int i = i0 + ty * RPT + r;
+    if (i >= p.Sq) continue;
+    const float inv = 1.f / l[r];   // every key masked: 0/0 = NaN, as torch's softmax of all -inf
+    float* o = p.o + ((int64_t)b * p.Sq + i) * p.ldo + h * dh;
+#pragma unroll
+    for (int n = 0; n < NDC; ++n)
+      if (tx + 16 * n < dh) o[tx + 16 * n] = acc[r][n] * inv;
+    if (tx == 0) p.lse[(int64_t)bh * p.Sq + i] = m[r] + logf(l[r]);
+  }
+}
+
+// One (query tile, key tile) step of the backward pass: fills sP (dropped probabilities)
+// and sDS (d scores) for the tile; both are [N][N+1], indexed [query][key].
+template <int RPT>
+__device__ __forceinline__ void bwd_tile(const MhaArgs& p, const float* sQ, const float* sK, const float* sV,
+                                         const float* sDO, float* sP, float* sDS, const float* lse, const float* dvec,
+                                         const int64_t* ktok, int bh, int i0, int k0, uint64_t seed, uint64_t step) {
+  constexpr int N = Tile<RPT>::N;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool drop = p.p_drop > 0.f;
+  float s[RPT][RPT], dp[RPT][RPT];
+  tile_dot<RPT>(sQ, sK, p.dh, ty, tx, s);     // Q already carries the 1/sqrt(dh) scale
+  tile_dot<RPT>(sDO, sV, p.dh, ty, tx, dp);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int i = i0 + ty * RPT + r;
+    const bool row_ok = i < p.Sq;
+    const float L = row_ok ? lse[i] : 0.f, D = row_ok ? dvec[i] : 0.f;
+#pragma unroll
+    for (int c = 0; c < RPT; ++c) {
+      const int j = k0 + tx + 16 * c;
+      float pr = 0.f, dsc = 0.f;
+      if (row_ok && !masked(p, ktok, i, j)) {
+        pr = expf(s[r][c] - L);
+        float f = 1.f;
+        if (drop) f = drop_factor(p, seed, step, bh, i, j);
+        dsc = pr * (dp[r][c] * f - D);
+        pr *= f;
+      }
+      sP[(ty * RPT + r) * (N + 1) + tx + 16 * c] = pr;
+      sDS[(ty * RPT + r) * (N + 1) + tx + 16 * c] = dsc;
+    }
+  }
+}
+
+// DKV = false: grid (ceil(Sq/N), nhead, B), writes D and dQ.  DKV = true: grid (ceil(Sk/N), nhead, B),
+// writes dK and dV.  smem: four [N][dh+1] tiles + two [N][N+1] tiles.
+template <int RPT, int NDC, bool DKV>
+__global__ void __launch_bounds__(256) mha_bwd_kernel(MhaArgs p) {
+  constexpr int N = Tile<RPT>::N;
+  extern __shared__ float sm[];
+  const int dh = p.dh, st = dh + 1;
+  float* sQ = sm;
+  float* sK = sQ + N * st;
+  float* sV = sK + N * st;
+  float* sDO = sV + N * st;
+  float* sP = sDO + N * st;
+  float* sDS = sP + N * (N + 1);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int h = blockIdx.y, b = blockIdx.z, bh = b * p.nhead + h;
+  const float* q = p.q + (int64_t)b * p.Sq * p.ldq + h * dh;
+  const float* k = p.k + (int64_t)b * p.Sk * p.ldk + h * dh;
+  const float* v = p.v + (int64_t)b * p.Sk * p.ldv + h * dh;
+  const float* dO = p.dout + (int64_t)b * p.Sq * p.ldo + h * dh;
+  const float* lse = p.lse + (int64_t)bh * p.Sq;
+  float* dvec = p.dvec + (int64_t)bh * p.Sq;
+  const int64_t* ktok = p.key_tokens ? p.key_tokens + (int64_t)b * p.Sk : nullptr;
+  const bool drop = p.p_drop > 0.f;
+  const uint64_t seed = drop ? p.rng[0] : 0, step = drop ? p.rng[1] : 0;
+  float acc[RPT][NDC], acc2[RPT][NDC];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r)
+#pragma unroll
+    for (int n = 0; n < NDC; ++n) acc[r][n] = acc2[r][n] = 0.f;
+
+  if (!DKV) {
+    const int i0 = blockIdx.x * N;
+    load_tile<N>(sQ, q, p.ldq, i0, p.Sq, dh, p.scale);
+    load_tile<N>(sDO, dO, p.ldo, i0, p.Sq, dh, 1.f);
+    // D_i = <dO_i, O_i>, one half-warp per row
+    const float* O = p.o + (int64_t)b * p.Sq * p.ldo + h * dh;
+    for (int r = ty; r < N; r += 16) {
+      float s = 0.f;
+      if (i0 + r < p.Sq)
+        for (int d = tx; d < dh; d += 16) s = fmaf(dO[(int64_t)(i0 + r) * p.ldo + d], O[(int64_t)(i0 + r) * p.ldo + d], s);
+      s = half_warp_sum(s);
+      if (tx == 0 && i0 + r < p.Sq) dvec[i0 + r] = s;
+    }
+    __syncthreads();   // dvec rows of this tile are re-read below (same CTA wrote them)
+    for (int k0 = 0; k0 < p.Sk; k0 += N) {
+      if (p.causal && k0 > i0 + N - 1) break;
+      __syncthreads();
+      load_tile<N>(sK, k, p.ldk, k0, p.Sk, dh, 1.f);
+      load_tile<N>(sV, v, p.ldv, k0, p.Sk, dh, 1.f);
+      __syncthreads();
+      bwd_tile<RPT>(p, sQ, sK, sV, sDO, sP, sDS, lse, dvec, ktok, bh, i0, k0, seed, step);
+      __syncthreads();
+      // dQ[i][d] += sum_j dS[i][j] K[j][d]
+#pragma unroll 2
+      for (int j = 0; j < N; ++j) {
+        float a[RPT], kv[NDC];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) a[r] = sDS[(ty * RPT + r) * (N + 1) + j];
+#pragma unroll
+        for (int n = 0; n < NDC; ++n) kv[n] = tx + 16 * n < dh ? sK[j * st + tx + 16 * n] : 0.f;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r)
+#pragma unroll
+          for (int n = 0; n < NDC; ++n) acc[r][n] = fmaf(a[r], kv[n], acc[r][n]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int i = i0 + ty * RPT + r;
+      if (i >= p.Sq) continue;
+      float* g = p.dq + ((int64_t)b * p.Sq + i) * p.ldq + h * dh;
+#pragma unroll
+      for (int n = 0; n < NDC; ++n)
+        if (tx + 16 * n < dh) g[tx + 16 * n] = acc[r][n] * p.scale;
+    }
+  } else {
+    const int k0 = blockIdx.x * N;
+    load_tile<N>(sK, k, p.ldk, k0, p.Sk, dh, 1.f);
+    load_tile<N>(sV, v, p.ldv, k0, p.Sk, dh, 1.f);
+    for (int i0 = 0; i0 < p.Sq; i0 += N) {
+      if (p.causal && i0 + N - 1 < k0) continue;
+      __syncthreads();
+      load_tile<N>(sQ, q, p.ldq, i0, p.Sq, dh, p.scale);
+      load_tile<N>(sDO, dO, p.ldo, i0, p.Sq, dh, 1.f);
+      __syncthreads();
+      bwd_tile<RPT>(p, sQ, sK, sV, sDO, sP, sDS, lse, dvec, ktok, bh, i0, k0, seed, step);
+      __syncthreads();
+      // dV[j][d] += sum_i P[i][j] dO[i][d];  dK[j][d] += sum_i dS[i][j] Q[i][d]  (Q carries the scale)
+#pragma unroll 2
+      for (int i = 0; i < N; ++i) {
+        float pj[RPT], dj[RPT], ov[NDC], qv[NDC];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          pj[r] = sP[i * (N + 1) + ty * RPT + r];
+          dj[r] = sDS[i * (N + 1) + ty * RPT + r];
+        }
+#pragma unroll
+        for (int n = 0; n < NDC; ++n) {
+          const bool ok = tx + 16 * n < dh;
+          ov[n] = ok ? sDO[i * st + tx + 16 * n] : 0.f;
+          qv[n] = ok ? sQ[i * st + tx + 16 * n] : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < RPT; ++r)
+#pragma unroll
+          for (int n = 0; n < NDC; ++n) {
+            acc[r][n] = fmaf(pj[r], ov[n], acc[r][n]);
+            acc2[r][n] = fmaf(dj[r], qv[n], acc2[r][n]);
+          }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int j = k0 + ty * RPT + r;
+      if (j >= p.Sk) continue;
+      float* gv = p.dv + ((int64_t)b * p.Sk + j) * p.ldv + h * dh;
+      float* gk = p.dk + ((int64_t)b * p.Sk + j) * p.ldk + h * dh;
+#pragma unroll
+      for (int n = 0; n < NDC; ++n)
+        if (tx + 16 * n < dh) {
+          gv[tx + 16 * n] = acc[r][n];
+          gk[tx + 16 * n] = acc2[r][n];
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm
+constexpr int LN_MAX_VPL = 32;   // values per lane: E <= 1024
+constexpr int LN_WARPS = 4;
+
+// y = LN(x + res) * gamma + beta; one warp per row.  mean / rstd [rows] saved for backward.
+__global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(const float* __restrict__ x,
+                                                                        const float* __restrict__ res,
+                                                                        const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta,
+                                                                        float* __restrict__ y, float* __restrict__ mean,
+                                                                        float* __restrict__ rstd, int rows, int E, float eps) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int row = blockIdx.x * LN_WARPS + w;
+  if (row >= rows) return;
+  const int vpl = (E + 31) >> 5;
+  const float* xr = x + (int64_t)row * E;
+  const float* rr = res ? res + (int64_t)row * E : nullptr;
+  float v[LN_MAX_VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VPL; ++k)
+    if (k < vpl && lane + 32 * k < E) {
+      v[k] = xr[lane + 32 * k] + (rr ? rr[lane + 32 * k] : 0.f);
+      s += v[k];
+    }
+  const float mu = warp_sum(s) / E;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VPL; ++k)
+    if (k < vpl && lane + 32 * k < E) {
+      const float d = v[k] - mu;
+      q = fmaf(d, d, q);
+    }
+  const float rs = rsqrtf(warp_sum(q) / E + eps);
+  float* yr = y + (int64_t)row * E;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VPL; ++k)
+    if (k < vpl && lane + 32 * k < E) yr[lane + 32 * k] = (v[k] - mu) * rs * gamma[lane + 32 * k] + beta[lane + 32 * k];
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma, xhat = (x + res - mean) * rstd.
+// dx is accumulated into when `accumulate` (the residual branch already holds a gradient).
+// partials [gridDim.x, 2, E]: per-block sums of dy * xhat (d gamma) and dy (d beta).
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const float* __restrict__ dy,
+                                                                    const float* __restrict__ x,
+                                                                    const float* __restrict__ res,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd, float* __restrict__ dx,
+                                                                    float* __restrict__ partials, int rows, int E,
+                                                                    int accumulate) {
+  extern __shared__ float sred[];   // [LN_WARPS][2][E]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int vpl = (E + 31) >> 5;
+  float dg[LN_MAX_VPL], db[LN_MAX_VPL], gm[LN_MAX_VPL];
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VPL; ++k) {
+    dg[k] = db[k] = 0.f;
+    gm[k] = (k < vpl && lane + 32 * k < E) ? gamma[lane + 32 * k] : 0.f;
+  }
+  for (int row = blockIdx.x * LN_WARPS + w; row < rows; row += gridDim.x * LN_WARPS) {
+    const float* xr = x + (int64_t)row * E;
+    const float* rr = res ? res + (int64_t)row * E : nullptr;
+    const float* gr = dy + (int64_t)row * E;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[LN_MAX_VPL], g[LN_MAX_VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VPL; ++k)
+      if (k < vpl && lane + 32 * k < E) {
+        const float d = gr[lane + 32 * k];
+        xh[k] = (xr[lane + 32 * k] + (rr ? rr[lane + 32 * k] : 0.f) - mu) * rs;
+        g[k] = d * gm[k];
+        s1 += g[k];
+        s2 = fmaf(g[k], xh[k], s2);
+        dg[k] = fmaf(d, xh[k], dg[k]);
+        db[k] += d;
+      }
+    s1 = warp_sum(s1) / E;
+    s2 = warp_sum(s2) / E;
+    float* o = dx + (int64_t)row * E;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VPL; ++k)
+      if (k < vpl && lane + 32 * k < E) {
+        const float val = rs * (g[k] - s1 - xh[k] * s2);
+        o[lane + 32 * k] = accumulate ? o[lane + 32 * k] + val : val;
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VPL; ++k)
+    if (k < vpl && lane + 32 * k < E) {
+      sred[(w * 2 + 0) * E + lane + 32 * k] = dg[k];
+      sred[(w * 2 + 1) * E + lane + 32 * k] = db[k];
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * E; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < LN_WARPS; ++ww) s += sred[ww * 2 * E + c];
+    partials[(int64_t)blockIdx.x * 2 * E + c] = s;
+  }
+}
+
+static int ln_bwd_blocks(int rows) {
+  int nb = ceil_div(rows, LN_WARPS);
+  const int cap = 2 * (sm_count() > 0 ? sm_count() : 148);
+  return nb < cap ? nb : cap;
+}
+
+template <int RPT, int NDC>
+static int launch_mha_fwd(const MhaArgs& a, cudaStream_t s) {
+  constexpr int N = Tile<RPT>::N;
+  const size_t smem = (size_t)(3 * N * (a.dh + 1) + N * (N + 1)) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(mha_fwd_kernel<RPT, NDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return fail("mha_fwd: cannot raise the shared-memory limit");
+    attr = true;
+  }
+  dim3 grid(ceil_div(a.Sq, N), a.nhead, a.B);
+  mha_fwd_kernel<RPT, NDC><<<grid, 256, smem, s>>>(a);
+  SLNLP_LAUNCH_OK("mha_fwd");
+  return 0;
+}
+
+template <int RPT, int NDC>
+static int launch_mha_bwd(const MhaArgs& a, cudaStream_t s) {
+  constexpr int N = Tile<RPT>::N;
+  const size_t smem = (size_t)(4 * N * (a.dh + 1) + 2 * N * (N + 1)) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(mha_bwd_kernel<RPT, NDC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(mha_bwd_kernel<RPT, NDC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return fail("mha_bwd: cannot raise the shared-memory limit");
+    attr = true;
+  }
+  mha_bwd_kernel<RPT, NDC, false><<<dim3(ceil_div(a.Sq, N), a.nhead, a.B), 256, smem, s>>>(a);
+  SLNLP_LAUNCH_OK("mha_bwd(dq)");
+  mha_bwd_kernel<RPT, NDC, true><<<dim3(ceil_div(a.Sk, N), a.nhead, a.B), 256, smem, s>>>(a);
+  SLNLP_LAUNCH_OK("mha_bwd(dkv)");
+  return 0;
+}
+
+static int check_mha(const MhaArgs& a, const char* who) {
+  SLNLP_CHECK_ARG(a.B > 0 && a.Sq > 0 && a.Sk > 0 && a.nhead > 0, "%s: bad shape", who);
+  SLNLP_CHECK_ARG(a.dh >= 4 && a.dh <= 256 && a.dh % 4 == 0, "%s: head dimension %d must be a multiple of 4 in [4, 256]", who, a.dh);
+  SLNLP_CHECK_ARG(a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0 && a.ldo % 4 == 0, "%s: leading dimensions must be multiples of 4", who);
+  SLNLP_CHECK_ARG(a.p_drop >= 0.f && a.p_drop < 1.f && (a.p_drop == 0.f || a.rng), "%s: bad dropout arguments", who);
+  SLNLP_CHECK_ARG(a.B <= 65535 && a.nhead <= 65535, "%s: grid too large", who);
+  return 0;
+}
+
+}  // namespace slnlp
+
+using namespace slnlp;
+
+// head-dim columns per thread: the smallest of 1, 2, 4, 8 (64-row tiles) or 16 (32-row tiles) covering dh / 16
+#define MHA_DISPATCH(FN, a, s)                          \
+  if ((a).dh <= 16) return FN<4, 1>(a, s);              \
+  if ((a).dh <= 32) return FN<4, 2>(a, s);              \
+  if ((a).dh <= 64) return FN<4, 4>(a, s);              \
+  if ((a).dh <= 128) return FN<4, 8>(a, s);             \
+  return FN<2, 16>(a, s);
+
+extern "C" int slnlp_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                             float* o, int ldo, float* lse, int B, int Sq, int Sk, int nhead, int dh,
+                             int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                             const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(q && k && v && o && lse, "mha_fwd: null pointer");
+  MhaArgs a{};
+  a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.o = o; a.ldo = ldo; a.lse = lse;
+  a.B = B; a.Sq = Sq; a.Sk = Sk; a.nhead = nhead; a.dh = dh; a.causal = causal;
+  a.key_tokens = key_tokens; a.pad_idx = pad_idx; a.scale = 1.f / sqrtf((float)dh);
+  a.p_drop = p_drop; a.rng = rng; a.site = site;
+  if (int rc = check_mha(a, "mha_fwd")) return rc;
+  MHA_DISPATCH(launch_mha_fwd, a, as_stream(stream));
+}
+
+extern "C" int slnlp_mha_bwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                             const float* o, const float* dout, int ldo, const float* lse, float* dvec,
+                             float* dq, float* dk, float* dv, int B, int Sq, int Sk, int nhead, int dh,
+                             int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                             const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(q && k && v && o && dout && lse && dvec && dq && dk && dv, "mha_bwd: null pointer");
+  MhaArgs a{};
+  a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.o = const_cast<float*>(o); a.dout = dout;
+  a.ldo = ldo; a.lse = const_cast<float*>(lse); a.dvec = dvec; a.dq = dq; a.dk = dk; a.dv = dv;
+  a.B = B; a.Sq = Sq; a.Sk = Sk; a.nhead = nhead; a.dh = dh; a.causal = causal;
+  a.key_tokens = key_tokens; a.pad_idx = pad_idx; a.scale = 1.f / sqrtf((float)dh);
+  a.p_drop = p_drop; a.rng = rng; a.site = site;
+  if (int rc = check_mha(a, "mha_bwd")) return rc;
+  MHA_DISPATCH(launch_mha_bwd, a, as_stream(stream));
+}
+
+extern "C" int slnlp_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
+                                       float* y, float* mean, float* rstd, int rows, int E, float eps,
+                                       slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(x && gamma && beta && y, "add_layernorm_fwd: null pointer");
+  SLNLP_CHECK_ARG(rows > 0 && E >= 1 && E <= 32 * LN_MAX_VPL, "add_layernorm_fwd: E must be in [1, 1024]");
+  add_layernorm_fwd_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, as_stream(stream)>>>(x, res, gamma, beta, y, mean, rstd, rows, E, eps);
+  SLNLP_LAUNCH_OK("add_layernorm_fwd");
+  return 0;
+}
+
+extern "C" int slnlp_ln_bwd_blocks(int rows) { return ln_bwd_blocks(rows); }
+
+extern "C" int slnlp_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma,
+                                   const float* mean, const float* rstd, float* dx, float* partials,
+                                   int rows, int E, int accumulate, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(dy && x && gamma && mean && rstd && dx && partials, "layernorm_bwd: null pointer");
+  SLNLP_CHECK_ARG(rows > 0 && E >= 1 && E <= 32 * LN_MAX_VPL, "layernorm_bwd: E must be in [1, 1024]");
+  const int nb = ln_bwd_blocks(rows);
+  layernorm_bwd_kernel<<<nb, LN_WARPS * 32, LN_WARPS * 2 * E * sizeof(float), as_stream(stream)>>>(
+      dy, x, res, gamma, mean, rstd, dx, partials, rows, E, accumulate);
+  SLNLP_LAUNCH_OK("layernorm_bwd");
+  return 0;
+}

@@ -53,11 +53,11 @@ SIGNATURES = {
     "slnlp_sumsq_partials": [],
     "slnlp_gradnorm": [P, L, P, P, P],
     "slnlp_sgd_momentum_clip": [P, P, P, L, P, P, F, P],
-    "slnlp_mha_fwd": [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, P, L, P],
-    "slnlp_mha_bwd": [P, I, P, I, P, I, P, I, P, P, P, P, P, I, I, I, I, I, I, P, L, P],
+    "slnlp_mha_fwd": [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, P, L, F, P, U32, P],
+    "slnlp_mha_bwd": [P, I, P, I, P, I, P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, L, F, P, U32, P],
     "slnlp_add_layernorm_fwd": [P, P, P, P, P, P, P, I, I, F, P],
     "slnlp_ln_bwd_blocks": [I],
-    "slnlp_layernorm_bwd": [P, P, P, P, P, P, P, I, I, P],
+    "slnlp_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, I, P],
 }
 _RESTYPES = {"slnlp_last_error_string": c_char_p, "slnlp_launch_count": c_int64,
              "slnlp_gemm_workspace_floats": c_int64}

@@ -1,0 +1,162 @@
+"""One flat fp32 buffer behind a module's named parameters (shared by the RNN and the
+Transformer host classes): the C-ABI kernels take raw device pointers into it, the fused
+clip+SGD kernels walk it in one pass, and ``state_dict`` keeps the reference's names/shapes.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from ._lib import check, lib
+
+_HAS_GEMM_BF16 = hasattr(lib, "slnlp_gemm_bf16")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _align4(n):
+    return (n + 3) & ~3
+
+
+class _Box(nn.Module):
+    """Plain container so parameters get the reference's dotted names."""
+
+
+class FlatParamModule(nn.Module):
+    """nn.Module whose parameters are views of ONE flat buffer (and whose grads are views of
+    one flat gradient buffer).  Subclasses call ``_register_flat`` from ``__init__``."""
+
+    precision = "fp32"
+    _dead: Tuple[str, ...] = ()      # parameters that never receive a gradient (grad stays None)
+
+    def _register_flat(self, segs: Sequence[Tuple[str, torch.Tensor]], order: Sequence[str],
+                       glue_suffix: str = "\0"):
+        """segs: (name, init tensor) in MEMORY order; order: names in named_parameters() order.
+        A name ending in ``glue_suffix`` is laid out directly after its predecessor (no
+        alignment gap) so that the pair forms one contiguous kernel operand."""
+        self._names = [n for n, _ in segs]
+        self._shapes = {n: tuple(t.shape) for n, t in segs}
+        self._off: Dict[str, int] = {}
+        off = 0
+        for n, t in segs:
+            if not n.endswith(glue_suffix):
+                off = _align4(off)
+            self._off[n] = off
+            off += t.numel()
+        self._numel = _align4(off)
+        flat = torch.zeros(self._numel)
+        for n, t in segs:
+            flat[self._off[n]:self._off[n] + t.numel()] = t.detach().reshape(-1)
+        self._flat = flat
+        self._gflat = None
+        self._params: Dict[str, nn.Parameter] = {}
+        self._ws_cache: Dict = {}
+        self._rng = None
+        for n in order:
+            parts = n.split(".")
+            box = self
+            for p in parts[:-1]:
+                if not hasattr(box, p):
+                    setattr(box, p, _Box())
+                box = getattr(box, p)
+            prm = nn.Parameter(self._view(self._flat, n))
+            box.register_parameter(parts[-1], prm)
+            self._params[n] = prm
+
+    def _view(self, flat, name):
+        shape = self._shapes[name]
+        n = math.prod(shape)
+        return flat[self._off[name]:self._off[name] + n].view(shape)
+
+    def _apply(self, fn, recurse=True):
+        # keep every parameter a view of ONE flat buffer across .to()/.cuda()/.float()
+        self._flat = fn(self._flat)
+        for n, prm in self._params.items():
+            prm.data = self._view(self._flat, n)
+            prm.grad = None
+        for name, buf in list(self.named_buffers()):
+            mod, _, leaf = name.rpartition(".")
+            owner = self.get_submodule(mod) if mod else self
+            owner._buffers[leaf] = fn(buf)
+        self._gflat = None
+        self._ws_cache = {}
+        self._rng = None
+        return self
+
+    def to(self, device=None, *args, **kwargs):                  # bkp:383-386, transformer.py:50-58
+        out = super().to(device, *args, **kwargs)
+        if device is not None:
+            self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        return out
+
+    def _ensure_flat(self):
+        """Re-flatten if some outside code replaced parameter storage."""
+        base = self._flat.data_ptr()
+        ok = all(p.data_ptr() == base + 4 * self._off[n] and p.device == self._flat.device
+                 for n, p in self._params.items())
+        if not ok:
+            dev = next(iter(self._params.values())).device
+            flat = torch.zeros(self._numel, device=dev)
+            for n, p in self._params.items():
+                flat[self._off[n]:self._off[n] + p.numel()] = p.data.reshape(-1).to(dev)
+            self._flat = flat
+            for n, p in self._params.items():
+                p.data = self._view(flat, n)
+            self._gflat = None
+        if not self._flat.is_cuda:
+            raise RuntimeError("slnlp_b200 modules compute on CUDA only (no CPU fallback): "
+                               "call .to('cuda') first")
+
+    def flat_parameters(self):
+        self._ensure_flat()
+        return self._flat
+
+    def flat_grads(self):
+        """Flat gradient buffer; ``p.grad`` of every live parameter is a view of it."""
+        self._ensure_flat()
+        if self._gflat is None or self._gflat.device != self._flat.device:
+            self._gflat = torch.zeros_like(self._flat)
+        for n, p in self._params.items():
+            if n in self._dead:
+                continue  # dead branch: grad stays None as in the reference
+            want = self._view(self._gflat, n)
+            if p.grad is None or p.grad.data_ptr() != want.data_ptr():
+                p.grad = want
+        return self._gflat
+
+    def _ptr(self, name, flat=None):
+        flat = self._flat if flat is None else flat
+        return flat.data_ptr() + 4 * self._off[name]
+
+    def _rng_state(self):
+        if self._rng is None or self._rng.device != self._flat.device:
+            self._rng = torch.tensor([self.seed, 0], dtype=torch.int64, device=self._flat.device)
+        return self._rng
+
+    def _workspace(self, B, T, train, fresh=False, bwd=None):
+        bwd = train if bwd is None else bwd
+        key = (B, T, train, bwd)
+        if not fresh and key in self._ws_cache:
+            return self._ws_cache[key]
+        ws = self._make_workspace(B, T, train, bwd)
+        if not fresh:
+            self._ws_cache[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ kernels
+    def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0, big=False):
+        fn = lib.slnlp_gemm_bf16 if (self.precision == "bf16" and big and _HAS_GEMM_BF16) else lib.slnlp_gemm_f32
+        ws = self._gemm_ws()
+        check(fn(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, ws.data_ptr(), ws.numel(), _stream()), "gemm")
+
+    def _gemm_ws(self):
+        """Split-K scratch shared by every GEMM of this module (one stream per module)."""
+        ws = getattr(self, "_gemm_scratch", None)
+        if ws is None or ws.device != self._flat.device:
+            ws = self._gemm_scratch = torch.empty(lib.slnlp_gemm_workspace_floats(), device=self._flat.device)
+        return ws

@@ -30,23 +30,12 @@ MODE = {"lstm": 0, "gru": 1}
 GATES = {"lstm": 4, "gru": 3}
 
 
-_HAS_GEMM_BF16 = hasattr(lib, "slnlp_gemm_bf16")
+from .flat import FlatParamModule, _Box, _align4, _stream  # noqa: F401
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
-
-
-def _align4(n):
-    return (n + 3) & ~3
-
-
-class _Box(nn.Module):
-    """Plain container so parameters get the reference's dotted names."""
-
-
-class RnnEncDecB200(nn.Module):
+class RnnEncDecB200(FlatParamModule):
     MAX_OUTPUT_LEN = 1  # bkp:332
+    _dead = ("model.decoder.pre_output_layer.weight",)
 
     def __init__(self, src_vocab, tgt_vocab, batch_first, rnn_type, embedding_size=256,
                  hidden_size=512, num_layers=1, dropout=0.1, precision="fp32", **kwargs):
@@ -67,8 +56,6 @@ class RnnEncDecB200(nn.Module):
         self.device = kwargs.get("device", None)
         self.validate_inputs = True
         self._build_parameters()
-        self._ws_cache: Dict = {}
-        self._rng = None
         self.seed = int(kwargs.get("seed", torch.initial_seed() & 0x7FFFFFFF))
 
     # ------------------------------------------------------------------ parameters
@@ -107,138 +94,27 @@ class RnnEncDecB200(nn.Module):
                  ("model.src_embed.weight", t_src.weight),
                  ("model.trg_embed.weight", t_trg.weight),
                  ("model.generator.proj.weight", t_gen.weight)]
-        self._names = [n for n, _ in segs]
-        self._shapes = {n: tuple(t.shape) for n, t in segs}
-        self._off: Dict[str, int] = {}
-        off = 0
-        for i, (n, t) in enumerate(segs):
-            # keep fwd/_reverse pairs contiguous; align everything else to 16 bytes
-            if not n.endswith("_reverse"):
-                off = _align4(off)
-            self._off[n] = off
-            off += t.numel()
-        self._numel = _align4(off)
-        flat = torch.zeros(self._numel)
-        for n, t in segs:
-            flat[self._off[n]:self._off[n] + t.numel()] = t.detach().reshape(-1)
-        self._flat = flat
-        self._gflat = None
-        # module tree with the reference's names (state_dict / Checkpoint compatibility)
-        self.model = _Box()
-        self._params: Dict[str, nn.Parameter] = {}
         # registration order = the reference's named_parameters() order
         order = []
         for l in range(L):
             for suf in ("", "_reverse"):
                 for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
                     order.append(f"model.encoder.rnn.{kind}_l{l}{suf}")
-        order += [n for n in self._names if n.startswith("model.decoder.attention")]
-        order += [n for n in self._names if n.startswith("model.decoder.rnn")]
+        order += [n for n, _ in segs if n.startswith("model.decoder.attention")]
+        order += [n for n, _ in segs if n.startswith("model.decoder.rnn")]
         order += ["model.decoder.bridge.weight", "model.decoder.bridge.bias",
                   "model.decoder.pre_output_layer.weight", "model.src_embed.weight",
                   "model.trg_embed.weight", "model.generator.proj.weight"]
-        for n in order:
-            parts = n.split(".")
-            box = self
-            for p in parts[:-1]:
-                if not hasattr(box, p):
-                    setattr(box, p, _Box())
-                box = getattr(box, p)
-            prm = nn.Parameter(self._view(self._flat, n))
-            box.register_parameter(parts[-1], prm)
-            self._params[n] = prm
+        self._register_flat(segs, order, glue_suffix="_reverse")
 
-    def _view(self, flat, name):
-        shape = self._shapes[name]
-        n = math.prod(shape)
-        return flat[self._off[name]:self._off[name] + n].view(shape)
+    def _make_workspace(self, B, T, train, bwd):
+        return _Workspace(self, B, T, train, bwd)
 
-    def _apply(self, fn, recurse=True):
-        # keep every parameter a view of ONE flat buffer across .to()/.cuda()/.float()
-        self._flat = fn(self._flat)
-        for n, prm in self._params.items():
-            prm.data = self._view(self._flat, n)
-            prm.grad = None
-        self._gflat = None
-        self._ws_cache = {}
-        self._rng = None
-        return self
+    @property
+    def uses_rng(self):
+        return self.p_rnn > 0.0
 
-    def to(self, device=None, *args, **kwargs):                  # bkp:383-386
-        out = super().to(device, *args, **kwargs)
-        if device is not None:
-            self.device = torch.device(device) if not isinstance(device, torch.device) else device
-        return out
-
-    def _ensure_flat(self):
-        """Re-flatten if some outside code replaced parameter storage."""
-        base = self._flat.data_ptr()
-        ok = all(p.data_ptr() == base + 4 * self._off[n] and p.device == self._flat.device
-                 for n, p in self._params.items())
-        if not ok:
-            dev = next(iter(self._params.values())).device
-            flat = torch.zeros(self._numel, device=dev)
-            for n, p in self._params.items():
-                flat[self._off[n]:self._off[n] + p.numel()] = p.data.reshape(-1).to(dev)
-            self._flat = flat
-            for n, p in self._params.items():
-                p.data = self._view(flat, n)
-            self._gflat = None
-        if not self._flat.is_cuda:
-            raise RuntimeError("slnlp_b200 modules compute on CUDA only (no CPU fallback): "
-                               "call .to('cuda') first")
-
-    def flat_parameters(self):
-        self._ensure_flat()
-        return self._flat
-
-    def flat_grads(self):
-        """Flat gradient buffer; ``p.grad`` of every live parameter is a view of it."""
-        self._ensure_flat()
-        if self._gflat is None or self._gflat.device != self._flat.device:
-            self._gflat = torch.zeros_like(self._flat)
-        for n, p in self._params.items():
-            if n == "model.decoder.pre_output_layer.weight":
-                continue  # dead branch: grad stays None as in the reference (SURVEY quirk 1)
-            want = self._view(self._gflat, n)
-            if p.grad is None or p.grad.data_ptr() != want.data_ptr():
-                p.grad = want
-        return self._gflat
-
-    def _ptr(self, name, flat=None):
-        flat = self._flat if flat is None else flat
-        return flat.data_ptr() + 4 * self._off[name]
-
-    def _rng_state(self):
-        if self._rng is None or self._rng.device != self._flat.device:
-            self._rng = torch.tensor([self.seed, 0], dtype=torch.int64, device=self._flat.device)
-        return self._rng
-
-    # ------------------------------------------------------------------ workspace
-    def _workspace(self, B, T, train, fresh=False, bwd=None):
-        bwd = train if bwd is None else bwd
-        key = (B, T, train, bwd)
-        if not fresh and key in self._ws_cache:
-            return self._ws_cache[key]
-        ws = _Workspace(self, B, T, train, bwd)
-        if not fresh:
-            self._ws_cache[key] = ws
-        return ws
-
-    # ------------------------------------------------------------------ kernels
-    def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0, big=False):
-        fn = lib.slnlp_gemm_bf16 if (self.precision == "bf16" and big and _HAS_GEMM_BF16) else lib.slnlp_gemm_f32
-        ws = self._gemm_ws()
-        check(fn(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, ws.data_ptr(), ws.numel(), _stream()), "gemm")
-
-    def _gemm_ws(self):
-        """Split-K scratch shared by every GEMM of this module (one stream per module)."""
-        ws = getattr(self, "_gemm_scratch", None)
-        if ws is None or ws.device != self._flat.device:
-            ws = self._gemm_scratch = torch.empty(lib.slnlp_gemm_workspace_floats(), device=self._flat.device)
-        return ws
-
-    def _run_forward(self, ws, X, lengths):
+    def _run_forward(self, ws, X, lengths, y=None):
         """X [B,T] int64 cuda, lengths [B] int64 cuda.  Fills ws; returns ws.logp."""
         E, H, L, G = self.E, self.H, self.L, self.G
         B, T = ws.B, ws.T
@@ -301,7 +177,7 @@ class RnnEncDecB200(nn.Module):
         check(lib.slnlp_log_softmax_fwd(ws.logits.data_ptr(), ws.logp.data_ptr(), B, self.V_tgt, s), "log_softmax")
         return ws.logp
 
-    def _run_backward(self, ws, X, lengths, gflat):
+    def _run_backward(self, ws, X, lengths, gflat, y=None):
         """Consumes ws.dlogits; accumulates parameter gradients into ``gflat``."""
         E, H, L, G = self.E, self.H, self.L, self.G
         B, T, V = ws.B, ws.T, self.V_tgt
@@ -453,7 +329,7 @@ class RnnEncDecB200(nn.Module):
         self._check_inputs(X, lengths)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self._params.values()):
             names = [n for n in self._params]
-            return _RnnFn.apply(self, X, lengths, *[self._params[n] for n in names])
+            return _ModuleFn.apply(self, X, lengths, None, *[self._params[n] for n in names])
         ws = self._workspace(X.shape[0], X.shape[1], self.training)
         if ws.train and self.p_rnn > 0:
             check(lib.slnlp_rng_advance(self._rng_state().data_ptr(), _stream()), "rng")
@@ -516,17 +392,17 @@ class _Workspace:
             self.row_ws = f(3 * B)
 
 
-class _RnnFn(torch.autograd.Function):
+class _ModuleFn(torch.autograd.Function):
     """Autograd bridge for the drop-in path: forward/backward launch the C-ABI kernels."""
 
     @staticmethod
-    def forward(ctx, module: RnnEncDecB200, X, lengths, *params):
+    def forward(ctx, module, X, lengths, y, *params):
         ws = module._workspace(X.shape[0], X.shape[1], module.training, fresh=True, bwd=True)
-        if ws.train and module.p_rnn > 0:
+        if ws.train and module.uses_rng:
             check(lib.slnlp_rng_advance(module._rng_state().data_ptr(), _stream()), "rng")
             ctx.rng_step = module._rng_state().clone()
-        ctx.module, ctx.ws, ctx.X, ctx.lengths = module, ws, X, lengths
-        logp = module._run_forward(ws, X, lengths)
+        ctx.module, ctx.ws, ctx.X, ctx.lengths, ctx.y = module, ws, X, lengths, y
+        logp = module._run_forward(ws, X, lengths, y)
         return logp.clone()
 
     @staticmethod
@@ -538,16 +414,16 @@ class _RnnFn(torch.autograd.Function):
         check(lib.slnlp_log_softmax_bwd(dlogp.data_ptr(), ws.logp.data_ptr(), ws.dlogits.data_ptr(),
                                         ws.B, m.V_tgt, _stream()), "log_softmax_bwd")
         g = torch.zeros_like(m._flat)
-        if ws.train and m.p_rnn > 0:  # replay the dropout masks of this forward
+        if ws.train and m.uses_rng:  # replay the dropout masks of this forward
             saved = m._rng_state().clone()
             m._rng_state().copy_(ctx.rng_step)
-        m._run_backward(ws, ctx.X, ctx.lengths, g)
-        if ws.train and m.p_rnn > 0:
+        m._run_backward(ws, ctx.X, ctx.lengths, g, ctx.y)
+        if ws.train and m.uses_rng:
             m._rng_state().copy_(saved)
         grads = []
         for n in m._params:
-            grads.append(None if n == "model.decoder.pre_output_layer.weight" else m._view(g, n))
-        return (None, None, None, *grads)
+            grads.append(None if n in m._dead else m._view(g, n))
+        return (None, None, None, None, *grads)
 
 
 class FusedTrainStep:
@@ -558,13 +434,13 @@ class FusedTrainStep:
     SGD(momentum, nesterov=False) (config/*.yaml:39-42).
     """
 
-    def __init__(self, module: RnnEncDecB200, batch_size: int, seq_len: int, lr: float,
+    def __init__(self, module: FlatParamModule, batch_size: int, seq_len: int, lr: float,
                  momentum: float = 0.9, max_norm: float = 0.5, use_graph: bool = True,
                  grad_sync=None):
         module._ensure_flat()
         self.m, self.B, self.T = module, batch_size, seq_len
         dev = module._flat.device
-        self.ws = _Workspace(module, batch_size, seq_len, True, True)
+        self.ws = module._make_workspace(batch_size, seq_len, True, True)
         self.X = torch.full((batch_size, seq_len), module.src_pad, dtype=torch.int64, device=dev)
         self.lengths = torch.ones(batch_size, dtype=torch.int64, device=dev)
         self.y = torch.zeros(batch_size, dtype=torch.int64, device=dev)
@@ -588,12 +464,12 @@ class FusedTrainStep:
         m, ws = self.m, self.ws
         s = _stream()
         self.gflat.zero_()
-        if m.p_rnn > 0:
+        if m.uses_rng:
             check(lib.slnlp_rng_advance(m._rng_state().data_ptr(), s), "rng")
-        m._run_forward(ws, self.X, self.lengths)
+        m._run_forward(ws, self.X, self.lengths, self.y)
         check(lib.slnlp_ce_on_logp(ws.logp.data_ptr(), self.y.data_ptr(), m.tgt_pad, self.B, m.V_tgt,
                                    ws.loss.data_ptr(), ws.dlogits.data_ptr(), ws.row_ws.data_ptr(), s), "ce")
-        m._run_backward(ws, self.X, self.lengths, self.gflat)
+        m._run_backward(ws, self.X, self.lengths, self.gflat, self.y)
         if self.grad_sync is not None:
             self.grad_sync(self.gflat, ws.loss)
             s = _stream()

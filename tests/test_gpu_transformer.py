@@ -1,0 +1,293 @@
+"""GPU: Transformer kernels (flash-style attention, fused residual+LayerNorm) against a plain
+torch fp32 statement of the same op, and the drop-in ``model.Transformer`` against the
+reference's golden vectors and, at the cfg3 shape, the torch.nn port on identical weights.
+
+Tolerances: 1e-5 relative on logits / loss (fp32 path), identical argmax; 2e-5 of the tensor
+scale on gradients and post-step weights; 2e-2 on the bf16 tensor-core path."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import BF16_RTOL, FP32_RTOL, GOLDEN_CASES, TRANSFORMER_CASES, grad_rel_err, load_golden, rel_err  # noqa: E402
+
+
+def _lib():
+    from slnlp_b200 import _lib as L
+    return L
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ref_attention(q, k, v, nhead, causal, keypad):
+    """q [B,Sq,E], k/v [B,Sk,E] -> [B,Sq,E]; keypad [B,Sk] bool or None."""
+    B, Sq, E = q.shape
+    Sk, dh = k.shape[1], E // nhead
+    qh = q.view(B, Sq, nhead, dh).transpose(1, 2)
+    kh = k.view(B, Sk, nhead, dh).transpose(1, 2)
+    vh = v.view(B, Sk, nhead, dh).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) / math.sqrt(dh)
+    bias = torch.zeros(B, 1, Sq, Sk, device=q.device)
+    if causal:
+        bias = bias.masked_fill(torch.triu(torch.ones(Sq, Sk, dtype=torch.bool, device=q.device), 1), float("-inf"))
+    if keypad is not None:
+        bias = bias.masked_fill(keypad[:, None, None, :], float("-inf"))
+    a = torch.softmax(s + bias, -1)
+    return (a @ vh).transpose(1, 2).reshape(B, Sq, E)
+
+
+@pytest.mark.parametrize("B,Sq,Sk,nhead,dh,causal,pad", [
+    (3, 64, 64, 8, 64, 1, True),      # cfg3 shape: causal + key padding (the reference's encoder)
+    (2, 37, 37, 2, 16, 1, True),      # ragged tile
+    (2, 100, 100, 2, 32, 1, False),   # two key tiles, online softmax
+    (3, 1, 64, 4, 128, 0, False),     # decoder cross attention (one query)
+    (4, 1, 1, 4, 16, 0, False),       # decoder self attention on one token
+    (2, 70, 90, 1, 256, 0, True),     # head dim 256 (E 1024 / 4 heads), 32-row tiles
+])
+def test_mha_fwd_bwd_against_torch(B, Sq, Sk, nhead, dh, causal, pad):
+    L = _lib()
+    E = nhead * dh
+    g = torch.Generator(device="cuda").manual_seed(0)
+    qkv_q = torch.randn(B, Sq, E, device="cuda", generator=g)
+    # k and v packed in one buffer (leading dimension 2E), as the cross-attention projection writes them
+    kv = torch.randn(B, Sk, 2 * E, device="cuda", generator=g)
+    tokens = torch.full((B, Sk), 5, dtype=torch.int64, device="cuda")
+    if pad:
+        for b in range(B):
+            tokens[b, Sk - 1 - 3 * b:] = 1
+    keypad = (tokens == 1) if pad else None
+    o = torch.empty(B, Sq, E, device="cuda")
+    lse = torch.empty(B, nhead, Sq, device="cuda")
+    kp, vp = kv.data_ptr(), kv.data_ptr() + 4 * E
+    L.check(L.lib.slnlp_mha_fwd(qkv_q.data_ptr(), E, kp, 2 * E, vp, 2 * E, o.data_ptr(), E, lse.data_ptr(), B, Sq, Sk,
+                                nhead, dh, causal, tokens.data_ptr() if pad else None, 1, 0.0, None, 0, S()))
+    q = qkv_q.clone().requires_grad_(True)
+    k = kv[..., :E].clone().requires_grad_(True)
+    v = kv[..., E:].clone().requires_grad_(True)
+    want = _ref_attention(q, k, v, nhead, causal, keypad)
+    assert rel_err(o, want) < 5e-6
+    do = torch.randn(B, Sq, E, device="cuda", generator=g)
+    want.backward(do)
+    dq = torch.empty_like(qkv_q)
+    dkv = torch.empty_like(kv)
+    dvec = torch.empty(B, nhead, Sq, device="cuda")
+    L.check(L.lib.slnlp_mha_bwd(qkv_q.data_ptr(), E, kp, 2 * E, vp, 2 * E, o.data_ptr(), do.data_ptr(), E, lse.data_ptr(),
+                                dvec.data_ptr(), dq.data_ptr(), dkv.data_ptr(), dkv.data_ptr() + 4 * E, B, Sq, Sk, nhead,
+                                dh, causal, tokens.data_ptr() if pad else None, 1, 0.0, None, 0, S()))
+    # a single unmasked key makes dq / dk exactly 0 in torch: judge against the scale of d out
+    # (P (dP - D) cancels to rounding noise there), so measure against |dO| |V| dh
+    scale = 1e3 * float(do.abs().max()) * float(v.abs().max()) * dh
+    assert grad_rel_err(dq, q.grad, scale) < 1e-5
+    assert grad_rel_err(dkv[..., :E], k.grad, scale) < 1e-5
+    assert grad_rel_err(dkv[..., E:], v.grad, scale) < 1e-5
+
+
+def test_mha_all_keys_masked_gives_nan_like_torch():
+    L = _lib()
+    B, Sq, Sk, nhead, dh = 2, 1, 1, 2, 16
+    E = nhead * dh
+    x = torch.randn(B, 1, 3 * E, device="cuda")
+    tokens = torch.tensor([[1], [7]], dtype=torch.int64, device="cuda")
+    o, lse = torch.empty(B, 1, E, device="cuda"), torch.empty(B, nhead, 1, device="cuda")
+    p = x.data_ptr()
+    L.check(L.lib.slnlp_mha_fwd(p, 3 * E, p + 4 * E, 3 * E, p + 8 * E, 3 * E, o.data_ptr(), E, lse.data_ptr(), B, 1, 1,
+                                nhead, dh, 0, tokens.data_ptr(), 1, 0.0, None, 0, S()))
+    assert torch.isnan(o[0]).all()                      # y == <pad>: torch's softmax over all -inf
+    assert rel_err(o[1], x[1, :, 2 * E:]) < 1e-6          # one unmasked key: the value itself
+
+
+def test_mha_dropout_statistics_and_backward_replays_mask():
+    L = _lib()
+    B, Sn, nhead, dh, p = 2, 64, 2, 32, 0.25
+    E = nhead * dh
+    x = torch.randn(B, Sn, 3 * E, device="cuda")
+    x[..., 2 * E:] = 1.0                                # V = 1: each output is the kept mass / (1-p)
+    rng = torch.tensor([1234, 5], dtype=torch.int64, device="cuda")
+    o, lse = torch.empty(B, Sn, E, device="cuda"), torch.empty(B, nhead, Sn, device="cuda")
+    q = x.data_ptr()
+    args = (q, 3 * E, q + 4 * E, 3 * E, q + 8 * E, 3 * E)
+    L.check(L.lib.slnlp_mha_fwd(*args, o.data_ptr(), E, lse.data_ptr(), B, Sn, Sn, nhead, dh, 0, None, 0, p, rng.data_ptr(), 3, S()))
+    assert abs(float(o.mean()) - 1.0) < 0.02            # E[mask/(1-p)] = 1
+    assert float(o.std()) > 0.01
+    o2 = torch.empty_like(o)
+    L.check(L.lib.slnlp_mha_fwd(*args, o2.data_ptr(), E, lse.data_ptr(), B, Sn, Sn, nhead, dh, 0, None, 0, p, rng.data_ptr(), 3, S()))
+    assert torch.equal(o, o2)                           # same (seed, step, site) -> same mask
+    # backward with the same mask: d/dV of sum(o) = column sums of the dropped weights, whose total is B*nhead*Sn*E/E...
+    do = torch.ones_like(o)
+    dqkv, dvec = torch.empty_like(x), torch.empty(B, nhead, Sn, device="cuda")
+    d = dqkv.data_ptr()
+    L.check(L.lib.slnlp_mha_bwd(*args, o.data_ptr(), do.data_ptr(), E, lse.data_ptr(), dvec.data_ptr(), d, d + 4 * E, d + 8 * E,
+                                B, Sn, Sn, nhead, dh, 0, None, 0, p, rng.data_ptr(), 3, S()))
+    # sum_j dV[j, d] = sum_i sum_j Pdrop[i, j] = sum_i o[i, d] for V = 1
+    dv = dqkv[..., 2 * E:]
+    assert rel_err(dv.sum(1), o.sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("rows,E", [(7, 32), (3200, 512), (50, 1024), (333, 128), (40, 24), (9, 16)])
+def test_add_layernorm_fwd_bwd(rows, E):
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(rows, E, device="cuda", generator=g)
+    res = torch.randn(rows, E, device="cuda", generator=g)
+    gamma = torch.randn(E, device="cuda", generator=g)
+    beta = torch.randn(E, device="cuda", generator=g)
+    y, mean, rstd = torch.empty_like(x), torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    L.check(L.lib.slnlp_add_layernorm_fwd(x.data_ptr(), res.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                          mean.data_ptr(), rstd.data_ptr(), rows, E, 1e-5, S()))
+    xs = (x + res).clone().requires_grad_(True)
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    want = torch.nn.functional.layer_norm(xs, (E,), gm, bt, 1e-5)
+    assert rel_err(y, want) < 2e-6
+    dy = torch.randn(rows, E, device="cuda", generator=g)
+    want.backward(dy)
+    nb = L.lib.slnlp_ln_bwd_blocks(rows)
+    dx, part = torch.empty_like(x), torch.empty(nb, 2 * E, device="cuda")
+    L.check(L.lib.slnlp_layernorm_bwd(dy.data_ptr(), x.data_ptr(), res.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+                                      rstd.data_ptr(), dx.data_ptr(), part.data_ptr(), rows, E, 0, S()))
+    assert rel_err(dx, xs.grad) < 1e-5
+    assert rel_err(part.sum(0)[:E], gm.grad) < 1e-5
+    assert rel_err(part.sum(0)[E:], bt.grad) < 1e-5
+    # no residual + accumulate
+    L.check(L.lib.slnlp_add_layernorm_fwd(x.data_ptr(), None, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                          mean.data_ptr(), rstd.data_ptr(), rows, E, 1e-5, S()))
+    assert rel_err(y, torch.nn.functional.layer_norm(x, (E,), gamma, beta, 1e-5)) < 2e-6
+
+
+def build(name, dropout=0.0, **extra):
+    import model as dropin
+    from slnlp_b200.vocab import Vocab
+    kind, kw = GOLDEN_CASES[name]
+    g = load_golden(name)
+    m = dropin.Transformer(src_vocab=Vocab(size=g["w0"]["src_embedding.weight"].shape[0]),
+                           tgt_vocab=Vocab(size=g["w0"]["tgt_embedding.weight"].shape[0]),
+                           batch_first=True, dropout=dropout, device=torch.device("cuda"), **kw, **extra)
+    m.load_state_dict(g["w0"], strict=False)              # golden holds the parameters; pe is a computed buffer
+    return m.to(torch.device("cuda")), g
+
+
+@pytest.mark.parametrize("name", TRANSFORMER_CASES)
+def test_transformer_forward_matches_reference_golden(name):
+    m, g = build(name)
+    X, y, lengths = g["X"].cuda(), g["y"].cuda(), g["lengths"].cuda()
+    m.eval()
+    with torch.no_grad():
+        logp = m(X=X, y=y, lengths=lengths)
+    assert rel_err(logp, g["logp_eval"]) < FP32_RTOL
+    assert torch.equal(logp.argmax(1).cpu(), g["logp_eval"].argmax(1))
+    # quirk 7: the label is the decoder input, so the output depends on y
+    with torch.no_grad():
+        other = m(X=X, y=(y + 1) % 5 + 2, lengths=lengths)
+    assert not torch.equal(other, logp)
+
+
+@pytest.mark.parametrize("name", TRANSFORMER_CASES)
+def test_transformer_autograd_path_with_stock_clip_and_sgd(name):
+    m, g = build(name)
+    X, y, lengths = g["X"].cuda(), g["y"].cuda(), g["lengths"].cuda()
+    m.train()
+    opt = torch.optim.SGD(m.parameters(), lr=g["lr"], momentum=0.9, nesterov=False)
+    scale = max(float(v.abs().max()) for v in g["g0"].values())
+    for step in range(3):
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(m(X=X, y=y, lengths=lengths), y, ignore_index=1)
+        loss.backward()
+        if step == 0:
+            grads = dict(m.named_parameters())
+            for k, ref in g["g0"].items():
+                assert grad_rel_err(grads[k].grad, ref, scale) < 2e-5, k
+        gn = torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=0.5, norm_type=2)
+        assert abs(float(loss) - g["loss"][step]) < 2e-5 * abs(g["loss"][step])
+        assert abs(float(gn) - g["gnorm"][step]) < 1e-4 * g["gnorm"][step]
+        opt.step()
+    sd = m.state_dict()
+    for k, ref in g["w3"].items():
+        assert rel_err(sd[k], ref) < 2e-5, k
+
+
+@pytest.mark.parametrize("name", TRANSFORMER_CASES)
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_transformer_fused_train_step_matches_reference_golden(name, use_graph):
+    from slnlp_b200.rnn import FusedTrainStep
+    m, g = build(name)
+    m.train()
+    B, T = g["X"].shape
+    ts = FusedTrainStep(m, B, T, lr=g["lr"], momentum=0.9, max_norm=0.5, use_graph=use_graph)
+    X, y, lengths = g["X"].cuda(), g["y"].cuda(), g["lengths"].cuda()
+    for step in range(3):
+        loss = ts.step(X, y, lengths)
+        assert abs(float(loss[0]) - g["loss"][step]) < 2e-5 * abs(g["loss"][step])
+        assert abs(float(ts.grad_norm) - g["gnorm"][step]) < 1e-4 * g["gnorm"][step]
+    sd = m.state_dict()
+    for k, ref in g["w3"].items():
+        assert rel_err(sd[k], ref) < 2e-5, k
+
+
+@pytest.mark.parametrize("E,F,L,heads,precision", [(512, 256, 4, 8, "fp32"), (128, 512, 2, 4, "fp32"),
+                                                  (1024, 128, 2, 4, "fp32"), (512, 256, 4, 8, "bf16")])
+def test_transformer_cfg3_against_oracle_port(E, F, L, heads, precision):
+    """cfg3 (config-transformer.yaml grid point E512 / hidden 256 / 4 layers / 8 heads, B50, S64)
+    and two more grid points against the torch.nn port with identical weights."""
+    import model as dropin
+    from oracle import port
+    from slnlp_b200.rnn import FusedTrainStep
+    from slnlp_b200.vocab import Vocab
+    B, T, Vs, Vt = 50, 64, 4098, 1026
+    torch.manual_seed(1)
+    ref = port.build_port("transformer", Vs, Vt, E, F, L, dropout=0.0, num_heads=heads)
+    m = dropin.Transformer(src_vocab=Vocab(size=Vs), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E,
+                           hidden_size=F, num_layers=L, num_heads=heads, dropout=0.0, device=torch.device("cuda"),
+                           precision=precision)
+    m.load_state_dict(ref.state_dict())
+    m = m.to(torch.device("cuda"))
+    g = torch.Generator().manual_seed(3)
+    X = torch.randint(2, Vs, (B, T), generator=g)
+    lengths = torch.randint(5, T + 1, (B,), generator=g)
+    for b in range(B):
+        X[b, lengths[b]:] = 1
+    y = torch.randint(2, Vt, (B,), generator=g)
+    tol = FP32_RTOL if precision == "fp32" else BF16_RTOL
+    ref.eval()
+    with torch.no_grad():
+        want = ref(X=X, y=y, lengths=lengths)
+    m.eval()
+    with torch.no_grad():
+        got = m(X=X.cuda(), y=y.cuda(), lengths=lengths.cuda())
+    assert rel_err(got, want) < tol
+    if precision == "fp32":
+        assert torch.equal(got.argmax(1).cpu(), want.argmax(1))
+    m.train()
+    ref.train()
+    ts = FusedTrainStep(m, B, T, lr=0.01)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9)
+    for step in range(2):
+        want_loss = port.reference_train_step(ref, opt, X, y, lengths)
+        got_loss = ts.step(X.cuda(), y.cuda(), lengths.cuda())
+        assert abs(float(got_loss[0]) - float(want_loss)) < tol * abs(float(want_loss))
+    if precision == "fp32":
+        rsd, sd = ref.state_dict(), m.state_dict()
+        for k in rsd:
+            # zero-initialised attention biases hold only -lr * (cancellation-noise gradient) ~ 1e-6:
+            # judge every tensor against max(its own scale, 1e-3)
+            err = float((sd[k].cpu() - rsd[k]).abs().max()) / max(float(rsd[k].abs().max()), 1e-3)
+            assert err < 2e-5, k
+
+
+def test_transformer_dropout_train_and_eval():
+    m, g = build("transformer_small", dropout=0.2)
+    X, y, lengths = g["X"].cuda(), g["y"].cuda(), g["lengths"].cuda()
+    m.train()
+    a = m(X=X, y=y, lengths=lengths).detach()
+    b = m(X=X, y=y, lengths=lengths).detach()
+    assert not torch.equal(a, b) and torch.isfinite(a).all()
+    loss = torch.nn.functional.cross_entropy(m(X=X, y=y, lengths=lengths), y, ignore_index=1)
+    loss.backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    m.eval()
+    with torch.no_grad():
+        c = m(X=X, y=y, lengths=lengths)
+    assert rel_err(c, g["logp_eval"]) < FP32_RTOL

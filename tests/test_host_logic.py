@@ -3,7 +3,7 @@ initialisation stream, flat-parameter views, refusal to compute on CPU)."""
 import pytest
 import torch
 
-from helpers import GOLDEN_CASES, RNN_CASES, load_golden
+from helpers import GOLDEN_CASES, RNN_CASES, TRANSFORMER_CASES, load_golden
 from slnlp_b200.vocab import Vocab
 import model as dropin
 
@@ -61,3 +61,22 @@ def test_constructor_surface():
     m, _ = build("gru_small")
     assert m.bos_idx == 0 and m.src_pad == 1 and m.tgt_pad == 1   # <bos> -> <unk>
     assert m.to(torch.device("cpu")).device == torch.device("cpu")
+
+
+@pytest.mark.parametrize("name", TRANSFORMER_CASES)
+def test_transformer_state_dict_surface_and_init_stream(name):
+    m, g = build(name)
+    sd = m.state_dict()
+    # parameters: the reference's names, order and (same seed) initial values
+    assert [k for k in sd if not k.endswith(".pe")] == list(g["w0"].keys())
+    for k, ref in g["w0"].items():
+        assert torch.equal(sd[k], ref), k
+    # buffers sit where the reference registers them (transformer.py:32-39; positional_encoding.py:31)
+    keys = list(sd.keys())
+    assert keys[:4] == ["src_embedding.weight", "src_pos_encoding.pe", "tgt_embedding.weight", "tgt_pos_encoding.pe"]
+    assert sd["src_pos_encoding.pe"].shape == (5000, 1, m.E)
+    E = m.E
+    assert m._off["transformer.encoder.norm.bias"] == m._off["transformer.encoder.norm.weight"] + E
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(X=g["X"], y=g["y"], lengths=g["lengths"])
+    assert dropin.EncoderDecoderTransformerAttn is dropin.Transformer
