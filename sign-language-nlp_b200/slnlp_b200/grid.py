@@ -1,0 +1,242 @@
+"""Grid search over independent fits, farmed one worker process per GPU with NO collective
+(SURVEY.md section 8e): the B200-box replacement of the reference's
+``GridSearchCV(n_jobs=-1)`` under ``joblib.parallel_backend('dask')`` with one Dask worker per
+GPU (main.py:70-78; helper.py:490-526; cluster/az-start-workers.sh:11-15).
+
+``GridSearchFarm`` takes GridSearchCV's keyword arguments (helper.py:154-172) and exposes its
+result surface: ``cv_results_`` (same column names), ``best_index_``, ``best_score_``,
+``best_params_``, ``best_estimator_`` (refit on all the data).
+
+Units of work = (candidate, fold) fits.  They are ordered longest-first by a FLOP estimate and
+claimed dynamically:
+  * ``backend="spawn"``: this process spawns one worker per GPU and feeds a queue;
+  * ``backend="torchrun"``: every rank of a torchrun launch calls ``fit`` with the same
+    arguments; a fetch-and-add counter in the rendezvous store hands out work and carries the
+    results back - host TCP only, no NCCL, no GPU-GPU traffic.
+"""
+from __future__ import annotations
+
+import itertools
+import os
+import pickle
+import time
+import traceback
+from typing import Dict, List
+
+import numpy as np
+from sklearn.base import clone, is_classifier
+from sklearn.model_selection import ParameterGrid, check_cv
+
+
+def estimate_cost(params: Dict) -> float:
+    """Relative training cost of one fit (SURVEY.md section 8d FLOP formulas, G folded in)."""
+    E = params.get("module__embedding_size", 128) or 128
+    H = params.get("module__hidden_size", 128) or 128
+    L = params.get("module__num_layers", 1) or 1
+    return float(sum(H * ((E if l == 0 else 2 * H) + H) for l in range(L)))
+
+
+def _fit_and_score(estimator, params, X, y, train, test, scorer, fit_subdir=None):
+    """One (candidate, fold): clone -> set_params -> fit(train) -> scorer(test)."""
+    from sklearn.utils import _safe_indexing
+    est = clone(estimator).set_params(**params)
+    if fit_subdir is not None:      # per-fit checkpoint directory (the reference's fits clobber one dir)
+        for item in (getattr(est, "callbacks", None) or []):
+            cb = item[1] if isinstance(item, tuple) else item
+            if hasattr(cb, "dirname") and cb.dirname:
+                cb.dirname = os.path.join(cb.dirname, fit_subdir)
+    Xtr, ytr = _safe_indexing(X, train), _safe_indexing(y, train)
+    Xte, yte = _safe_indexing(X, test), _safe_indexing(y, test)
+    t0 = time.perf_counter()
+    est.fit(Xtr, ytr)
+    t1 = time.perf_counter()
+    score = float(scorer(est, Xte, yte))
+    t2 = time.perf_counter()
+    return {"score": score, "fit_time": t1 - t0, "score_time": t2 - t1,
+            "epochs": len(getattr(est, "history", [])), "n_train": len(train)}
+
+
+def _worker_main(gpu, task_q, result_q, payload_bytes):
+    try:
+        import torch
+        torch.cuda.set_device(gpu)
+        estimator, X, y, scorer = pickle.loads(payload_bytes)
+        estimator.set_params(device=f"cuda:{gpu}")
+        while True:
+            task = task_q.get()
+            if task is None:
+                break
+            tid, params, train, test, sub = task
+            try:
+                out = _fit_and_score(estimator, params, X, y, train, test, scorer, sub)
+                out["gpu"] = gpu
+                result_q.put((tid, out, None))
+            except Exception:            # error_score="raise": reported to the parent, which raises
+                result_q.put((tid, None, traceback.format_exc()))
+    except Exception:
+        result_q.put((-1, None, traceback.format_exc()))
+
+
+class GridSearchFarm:
+    def __init__(self, estimator, param_grid, *, scoring=None, n_jobs=None, refit=True, cv=None, verbose=0,
+                 pre_dispatch=None, error_score="raise", return_train_score=False, n_gpus=None, backend="auto",
+                 per_fit_checkpoint_dirs=True):
+        self.estimator, self.param_grid, self.scoring, self.n_jobs = estimator, param_grid, scoring, n_jobs
+        self.refit, self.cv, self.verbose, self.pre_dispatch = refit, cv, verbose, pre_dispatch
+        self.error_score, self.return_train_score = error_score, return_train_score
+        self.n_gpus, self.backend, self.per_fit_checkpoint_dirs = n_gpus, backend, per_fit_checkpoint_dirs
+
+    # ------------------------------------------------------------------ scheduling
+    def _tasks(self, X, y):
+        cands = list(ParameterGrid(self.param_grid))
+        cv = check_cv(self.cv, y, classifier=is_classifier(self.estimator))
+        folds = [(tr, te) for tr, te in cv.split(np.arange(len(y)), y)]
+        tasks = [(ci, fi) for ci in range(len(cands)) for fi in range(len(folds))]
+        # longest first, so no GPU is left holding a 6-layer fit at the end
+        order = sorted(range(len(tasks)), key=lambda t: -estimate_cost(cands[tasks[t][0]]) * len(folds[tasks[t][1]][0]))
+        return cands, folds, tasks, order
+
+    def _scorer(self):
+        if callable(self.scoring):
+            return self.scoring
+        from sklearn.metrics import get_scorer
+        return get_scorer(self.scoring or "accuracy")
+
+    def _resolve_backend(self):
+        if self.backend != "auto":
+            return self.backend
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            return "torchrun"
+        return "spawn"
+
+    def fit(self, X, y):
+        import torch
+        y = np.asarray(y.to_array() if hasattr(y, "to_array") else y)
+        cands, folds, tasks, order = self._tasks(X, y)
+        scorer = self._scorer()
+        backend = self._resolve_backend()
+        t0 = time.perf_counter()
+        if backend == "torchrun":
+            results = self._run_torchrun(cands, folds, tasks, order, X, y, scorer)
+        else:
+            n = self.n_gpus or (torch.cuda.device_count() if torch.cuda.is_available() else 0)
+            if n <= 1 or backend == "inline":
+                results = self._run_inline(cands, folds, tasks, order, X, y, scorer)
+            else:
+                results = self._run_spawn(n, cands, folds, tasks, order, X, y, scorer)
+        self.search_time_ = time.perf_counter() - t0
+        self.n_fits_ = len(tasks)
+        self._collect(cands, folds, tasks, results)
+        if self.refit and self._is_main():
+            t1 = time.perf_counter()
+            self.best_estimator_ = clone(self.estimator).set_params(**self.best_params_)
+            self.best_estimator_.fit(X, y)
+            self.refit_time_ = time.perf_counter() - t1
+        return self
+
+    def _is_main(self):
+        return int(os.environ.get("RANK", "0")) == 0 or self._resolve_backend() != "torchrun"
+
+    def _sub(self, ci, fi):
+        return f"cand{ci:04d}_fold{fi}" if self.per_fit_checkpoint_dirs else None
+
+    def _run_inline(self, cands, folds, tasks, order, X, y, scorer):
+        out = {}
+        for t in order:
+            ci, fi = tasks[t]
+            out[t] = _fit_and_score(self.estimator, cands[ci], X, y, folds[fi][0], folds[fi][1], scorer, self._sub(ci, fi))
+            if self.verbose:
+                print(f"[grid] {len(out)}/{len(tasks)} cand {ci} fold {fi}: score {out[t]['score']:.4f} "
+                      f"fit {out[t]['fit_time']:.2f}s", flush=True)
+        return out
+
+    def _run_spawn(self, n, cands, folds, tasks, order, X, y, scorer):
+        import torch.multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        task_q, result_q = ctx.Queue(), ctx.Queue()
+        payload = pickle.dumps((self.estimator, X, y, scorer))
+        procs = [ctx.Process(target=_worker_main, args=(g, task_q, result_q, payload), daemon=True) for g in range(n)]
+        for p in procs:
+            p.start()
+        for t in order:
+            ci, fi = tasks[t]
+            task_q.put((t, cands[ci], folds[fi][0], folds[fi][1], self._sub(ci, fi)))
+        for _ in procs:
+            task_q.put(None)
+        out = {}
+        try:
+            while len(out) < len(tasks):
+                tid, res, err = result_q.get()
+                if err is not None:
+                    raise RuntimeError(f"grid-search fit failed (error_score='raise'):\n{err}")
+                out[tid] = res
+                if self.verbose:
+                    ci, fi = tasks[tid]
+                    print(f"[grid] {len(out)}/{len(tasks)} cand {ci} fold {fi} on gpu {res['gpu']}: "
+                          f"score {res['score']:.4f} fit {res['fit_time']:.2f}s", flush=True)
+        finally:
+            for p in procs:
+                p.join(timeout=30)
+                if p.is_alive():
+                    p.terminate()
+        return out
+
+    def _run_torchrun(self, cands, folds, tasks, order, X, y, scorer):
+        """SPMD under torchrun: work is claimed with a store counter, results travel through the
+        store.  No process-group collective is issued (no NCCL on the grid path)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        store = getattr(self, "store", None)
+        if store is None:
+            store = dist.TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ["MASTER_PORT"]) + 17,
+                                  world, is_master=(rank == 0), wait_for_workers=True)
+            self.store = store
+        gen = getattr(self, "_generation", 0)
+        self._generation = gen + 1
+        key = f"grid{gen}"
+        est = clone(self.estimator)
+        if torch.cuda.is_available() and "device" in est.get_params(deep=False):
+            est.set_params(device=f"cuda:{torch.cuda.current_device()}")
+        while True:
+            k = store.add(f"{key}/next", 1) - 1
+            if k >= len(order):
+                break
+            t = order[k]
+            ci, fi = tasks[t]
+            res = _fit_and_score(est, cands[ci], X, y, folds[fi][0], folds[fi][1], scorer, self._sub(ci, fi))
+            res["gpu"] = rank
+            store.set(f"{key}/res/{t}", pickle.dumps(res))
+        out = {}
+        for t in range(len(tasks)):     # blocks until the owning rank has published it
+            out[t] = pickle.loads(store.get(f"{key}/res/{t}"))
+        return out
+
+    # ------------------------------------------------------------------ GridSearchCV result surface
+    def _collect(self, cands, folds, tasks, results):
+        nc, nf = len(cands), len(folds)
+        score = np.full((nc, nf), np.nan)
+        fit_t, score_t = np.zeros((nc, nf)), np.zeros((nc, nf))
+        for t, (ci, fi) in enumerate(tasks):
+            r = results[t]
+            score[ci, fi], fit_t[ci, fi], score_t[ci, fi] = r["score"], r["fit_time"], r["score_time"]
+        res: Dict[str, object] = {
+            "mean_fit_time": fit_t.mean(1), "std_fit_time": fit_t.std(1),
+            "mean_score_time": score_t.mean(1), "std_score_time": score_t.std(1),
+        }
+        keys = sorted({k for c in cands for k in c})
+        for k in keys:
+            res[f"param_{k}"] = np.ma.MaskedArray([c.get(k) for c in cands], mask=[k not in c for c in cands], dtype=object)
+        res["params"] = cands
+        for fi in range(nf):
+            res[f"split{fi}_test_score"] = score[:, fi]
+        res["mean_test_score"] = score.mean(1)
+        res["std_test_score"] = score.std(1)
+        from scipy.stats import rankdata
+        res["rank_test_score"] = rankdata(-res["mean_test_score"], method="min").astype(np.int32)
+        self.cv_results_ = res
+        self.best_index_ = int(np.argmin(res["rank_test_score"]))
+        self.best_score_ = float(res["mean_test_score"][self.best_index_])
+        self.best_params_ = cands[self.best_index_]
+        self.fit_results_ = results
+        self.n_splits_ = nf

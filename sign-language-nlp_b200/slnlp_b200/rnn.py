@@ -336,7 +336,7 @@ class RnnEncDecB200(FlatParamModule):
         return self._run_forward(ws, X, lengths).clone()
 
     @torch.no_grad()
-    def predict_logp(self, X, lengths):
+    def predict_logp(self, X, lengths, y=None):
         """Inference forward without autograd or input validation."""
         self._ensure_flat()
         was = self.training
@@ -426,6 +426,29 @@ class _ModuleFn(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+class OptimState:
+    """SGD-momentum + clip state of one fit: hyper = {lr, momentum, max_norm, first-step flag}
+    (device, read by the kernels so that a captured graph sees lr changes), momentum buffer,
+    gradient-norm scratch."""
+
+    def __init__(self, module: FlatParamModule, lr: float, momentum: float = 0.9, max_norm: float = 0.5):
+        module._ensure_flat()
+        dev = module._flat.device
+        self.hyper = torch.tensor([lr, momentum, max_norm if max_norm else 0.0, 0.0], device=dev)
+        self.buf = torch.zeros_like(module._flat)     # zero buffer == "first step" of torch SGD
+        self.partials = torch.zeros(lib.slnlp_sumsq_partials(), device=dev)
+        self.norm = torch.zeros(1, device=dev)
+        self._lr = lr
+
+    def set_lr(self, lr):
+        if lr != self._lr:
+            self.hyper[0] = lr
+            self._lr = lr
+
+    def state_dict(self):
+        return {"hyper": self.hyper.clone(), "momentum_buffer": self.buf.clone()}
+
+
 class FusedTrainStep:
     """The skorch train step of SURVEY.md 3.2 as ONE CUDA-graph replay:
 
@@ -434,9 +457,9 @@ class FusedTrainStep:
     SGD(momentum, nesterov=False) (config/*.yaml:39-42).
     """
 
-    def __init__(self, module: FlatParamModule, batch_size: int, seq_len: int, lr: float,
+    def __init__(self, module: FlatParamModule, batch_size: int, seq_len: int, lr: float = 0.01,
                  momentum: float = 0.9, max_norm: float = 0.5, use_graph: bool = True,
-                 grad_sync=None):
+                 grad_sync=None, state: "OptimState" = None):
         module._ensure_flat()
         self.m, self.B, self.T = module, batch_size, seq_len
         dev = module._flat.device
@@ -444,21 +467,22 @@ class FusedTrainStep:
         self.X = torch.full((batch_size, seq_len), module.src_pad, dtype=torch.int64, device=dev)
         self.lengths = torch.ones(batch_size, dtype=torch.int64, device=dev)
         self.y = torch.zeros(batch_size, dtype=torch.int64, device=dev)
-        self.hyper = torch.tensor([lr, momentum, max_norm if max_norm else 0.0, 0.0], device=dev)
-        self.buf = torch.zeros_like(module._flat)     # zero buffer == "first step" of torch SGD
-        self.partials = torch.zeros(lib.slnlp_sumsq_partials(), device=dev)
-        self.norm = torch.zeros(1, device=dev)
+        # optimizer state may be shared by several steps of different batch shape (tail batches)
+        self.state = state if state is not None else OptimState(module, lr, momentum, max_norm)
         self.gflat = module.flat_grads()
         self.grad_sync = grad_sync                   # callable(gflat, loss) for data parallel
         self.grad_scale = 1.0
         self.graph = None
         self.use_graph = use_graph and grad_sync is None
-        self._lr = lr
+
+    # optimizer state lives in self.state; these aliases keep call sites short
+    hyper = property(lambda self: self.state.hyper)
+    buf = property(lambda self: self.state.buf)
+    partials = property(lambda self: self.state.partials)
+    norm = property(lambda self: self.state.norm)
 
     def set_lr(self, lr):
-        if lr != self._lr:
-            self.hyper[0] = lr
-            self._lr = lr
+        self.state.set_lr(lr)
 
     def _step(self):
         m, ws = self.m, self.ws
