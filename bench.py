@@ -35,6 +35,9 @@ WORKLOADS = {
                  name="EncoderDecoderLSTMAttn emb128 hidden128 layers2 dropout0.1 batch50 len64"),
     "cfg2": dict(kind="gru", E=512, H=256, L=4, p=0.1, B=50, T=64, Vs=4098, Vt=1026,
                  name="EncoderDecoderGRUAttn emb512 hidden256 layers4 batch50 len64"),
+    # config-transformer.yaml grid point: model.Transformer E512, dim_feedforward 256, 4+4 layers, 8 heads
+    "cfg3": dict(kind="transformer", E=512, H=256, L=4, p=0.1, heads=8, B=50, T=64, Vs=4098, Vt=1026,
+                 name="Transformer emb512 ffn256 layers4 heads8 dropout0.1 batch50 len64"),
     "cfg4": dict(kind="lstm", E=1024, H=512, L=6, p=0.5, B=4096, T=64, Vs=4098, Vt=1026,
                  name="EncoderDecoderLSTMAttn emb1024 hidden512 layers6 dropout0.5 batch4096 len64"),
 }
@@ -43,8 +46,13 @@ METRIC, UNIT = "train_seq_per_s", "sequences/s"
 
 def train_flops_per_seq(w):
     """3 x forward GEMM FLOPs of the live graph."""
-    G = 4 if w["kind"] == "lstm" else 3
     E, H, L, T, V = w["E"], w["H"], w["L"], w["T"], w["Vt"]
+    if w["kind"] == "transformer":
+        F = H
+        enc = L * (2 * T * (3 * E * E + E * E + 2 * E * F) + 4 * T * T * E)          # qkv, out, ffn, QK^T + PV
+        dec = L * (2 * (3 * E * E + E * E) + 2 * (E * E + E * E) + 2 * T * 2 * E * E + 4 * T * E + 2 * 2 * E * F)
+        return 3 * (enc + dec + 2 * E * V)
+    G = 4 if w["kind"] == "lstm" else 3
     enc = sum(2 * T * (2 * G * H * (E if l == 0 else 2 * H) + 2 * G * H * H) for l in range(L))
     key, bridge = T * 2 * 2 * H * H, L * 2 * 2 * H * H
     att = 2 * H * H + 2 * T * H + 4 * T * H
@@ -102,7 +110,7 @@ def build_reference_port(w):
     import torch
     from oracle import port
     torch.manual_seed(1)
-    return port.build_port(w["kind"], w["Vs"], w["Vt"], w["E"], w["H"], w["L"], dropout=w["p"])
+    return port.build_port(w["kind"], w["Vs"], w["Vt"], w["E"], w["H"], w["L"], dropout=w["p"], num_heads=w.get("heads"))
 
 
 def time_cpu_port(w, data, steps, warmup, batch=None):
@@ -199,9 +207,10 @@ def main():
     n_seq = max(5000 if w["B"] <= 50 else 8 * w["B"], B * 4)
     data = synthetic_dataset(n_seq=n_seq, T=w["T"], v_src=w["Vs"], v_tgt=w["Vt"], seed=1 + (0 if args.dp else rank))
     torch.manual_seed(1)
-    cls = dropin.EncoderDecoderLSTMAttn if w["kind"] == "lstm" else dropin.EncoderDecoderGRUAttn
+    cls = {"lstm": dropin.EncoderDecoderLSTMAttn, "gru": dropin.EncoderDecoderGRUAttn, "transformer": dropin.Transformer}[w["kind"]]
+    extra = {"num_heads": w["heads"]} if w["kind"] == "transformer" else {}
     m = cls(src_vocab=data["src_vocab"], tgt_vocab=data["tgt_vocab"], batch_first=True, embedding_size=w["E"],
-            hidden_size=w["H"], num_layers=w["L"], dropout=w["p"], device=dev, precision=args.precision).to(dev).train()
+            hidden_size=w["H"], num_layers=w["L"], dropout=w["p"], device=dev, precision=args.precision, **extra).to(dev).train()
 
     grad_sync = None
     if args.dp and world > 1:
@@ -290,7 +299,7 @@ def main():
     d2h = 8
 
     # ---------------- dominant kernel, timed alone: the encoder layer-0 recurrence (T launches)
-    roof = dominant_kernel_roofline(m, ts, w, B, dev)
+    roof = dominant_kernel_roofline(m, ts, w, B, dev) if w["kind"] != "transformer" else None
 
     if rank == 0:
         peaks = {}
