@@ -79,6 +79,15 @@ int slnlp_gemm_bf16(int transA, int transB, int M, int N, int K,
                     const float* A, int lda, const float* B, int ldb,
                     float* C, int ldc, const float* bias, float beta,
                     float* workspace, int64_t workspace_floats, slnlp_stream_t stream);
+/* The TMA-fed variant (north_star: "x W_ih hoisted into one TMA-fed GEMM over all timesteps"):
+ * operands stay fp32 in HBM and are consumed as TF32 by tcgen05.mma kind::tf32 from 128-byte
+ * swizzled TMA tiles (4-stage mbarrier ring, warp-specialised producer / MMA / epilogue),
+ * transposed operands as MN-major tiles.  Same contract as slnlp_gemm_bf16; needs 16-byte
+ * aligned A, B and lda, ldb multiples of 4, else it computes with slnlp_gemm_f32. */
+int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K,
+                    const float* A, int lda, const float* B, int ldb,
+                    float* C, int ldc, const float* bias, float beta,
+                    float* workspace, int64_t workspace_floats, slnlp_stream_t stream);
 /* out[c] = beta*out[c] + sum_r A[r*lda + c]   (bias gradients) */
 int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
                      slnlp_stream_t stream);

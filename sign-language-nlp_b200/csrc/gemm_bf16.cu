@@ -120,12 +120,19 @@ __global__ void __launch_bounds__(GT) gemm_bf16_kernel(int M, int N, int Kfull, 
     }
   }
   float* P = partial ? partial + (int64_t)blockIdx.z * M * N : nullptr;
-  const int m = m0 + tid;
   if (nk > 0) {
     const int last = nk - 1;
     mbar_wait(&bars[last & 1], (uint32_t)(last >> 1) & 1u);  // the last commit covers every MMA issued
     tc_fence_after();
   }
+  // Epilogue: TMEM -> registers -> shared (the operand buffers are free now) -> coalesced rows.
+  // A thread owns a TMEM lane (= a row of C), so storing straight from the tcgen05.ld registers
+  // would touch 32 different rows per instruction; staging lets a warp write 128 contiguous
+  // bytes of ONE row per instruction instead.
+  constexpr int SLD = TN + 1;
+  float* stage = reinterpret_cast<float*>(smem_raw) + warp * 32 * SLD;
+  static_assert(4 * 32 * SLD * 4 <= 2 * A_BYTES + 2 * B_BYTES, "staging tile must fit the operand buffers");
+  const int lane = tid & 31;
 #pragma unroll 1
   for (int c0 = 0; c0 < TN; c0 += 16) {
     float v[16];
@@ -135,20 +142,33 @@ __global__ void __launch_bounds__(GT) gemm_bf16_kernel(int M, int N, int Kfull, 
 #pragma unroll
       for (int q = 0; q < 16; ++q) v[q] = 0.f;
     }
-    if (m < M) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int n = n0 + c0 + q;
-        if (n >= N) continue;
-        if (P) {
-          P[(int64_t)m * N + n] = v[q];
-        } else {
-          float o = v[q];
-          if (bias) o += bias[n];
-          float* c = C + (int64_t)m * ldc + n;
-          if (beta != 0.f) o += beta * *c;
-          *c = o;
-        }
+    for (int q = 0; q < 16; ++q) stage[lane * SLD + c0 + q] = v[q];
+  }
+  __syncwarp();
+  float bv[TN / 32];
+#pragma unroll
+  for (int j = 0; j < TN / 32; ++j) {
+    const int n = n0 + lane + 32 * j;
+    bv[j] = (bias && !P && n < N) ? bias[n] : 0.f;
+  }
+  const int mrow0 = m0 + warp * 32;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const int m = mrow0 + r;
+    if (m >= M) break;
+#pragma unroll
+    for (int j = 0; j < TN / 32; ++j) {
+      const int n = n0 + lane + 32 * j;
+      if (n >= N) continue;
+      const float acc = stage[r * SLD + lane + 32 * j];
+      if (P) {
+        P[(int64_t)m * N + n] = acc;
+      } else {
+        float* c = C + (int64_t)m * ldc + n;
+        float o = acc + bv[j];
+        if (beta != 0.f) o += beta * *c;
+        *c = o;
       }
     }
   }

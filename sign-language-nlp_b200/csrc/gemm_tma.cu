@@ -1,0 +1,323 @@
+// K3/K6 and every other large dense contraction on the 5th-gen tensor cores, TMA-fed:
+// C[M,N] = op(A) op(B) + bias + beta*C with A and B read from HBM AS THE fp32 THEY ARE.
+//
+//   producer warp : one elected thread issues cp.async.bulk.tensor (TMA, 128-byte swizzle) for
+//                   a 128 x 32 tile of A and a 64 x 32 tile of B per stage, 4 stages deep, each
+//                   stage armed on an mbarrier with its byte count;
+//   MMA warp      : one elected thread issues tcgen05.mma kind::tf32 (M128 x N64 x K8, fp32
+//                   accumulators in 64 TMEM columns) straight on the swizzled tiles, and hands a
+//                   stage back to the producer with tcgen05.commit;
+//   4 epilogue warps : tcgen05.ld the accumulator, stage it through shared memory (the operand
+//                   ring is idle by then) and write bias/beta-combined rows coalesced.
+//
+// There is no conversion pass: TF32 (10-bit mantissa) reads fp32 operands directly, which is
+// both cheaper than rounding to bf16 through registers and more accurate than the 2e-2 budget
+// of the tensor-core path needs.  Transposed operands are consumed in place as MN-major tiles
+// (the dW = dY^T X and dX = dY W GEMMs of the backward pass), so no operand is ever transposed
+// in HBM.  Long-K / small-MN problems (dW over K = B*T) use deterministic split-K into the
+// caller's workspace.
+#include <cuda.h>
+
+#include <unordered_map>
+
+#include "tc05.cuh"
+
+namespace slnlp {
+
+constexpr int BM = 128, BN = 64, BK = 32, STAGES = 4;      // BK floats = 128 bytes = one swizzle row
+constexpr int A_STAGE = BM * BK * 4, B_STAGE = BN * BK * 4;
+constexpr int TMA_THREADS = 192;                             // producer, MMA, 4 epilogue warps
+constexpr int UMMA_K = 8;                                    // tf32
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 128-byte-swizzled operand descriptor (cute::UMMA::SmemDescriptor): layout_type 2 = SWIZZLE_128B
+// (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks: the only MN-major layout of 32-bit operands)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout_type) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout_type << 61);
+}
+// c = f32, a = b = tf32, per-operand major bit (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// A_MN / B_MN: the operand is stored with its M (resp. N) index contiguous ("MN-major").
+// K-major tile : one TMA box {32 k, rows}, SWIZZLE_128B; row r at r*128 B, 8-row groups 1024 B
+//                apart (SBO); an MMA of K = 8 advances 32 B inside the swizzled row.
+// MN-major tile: rows/32 TMA boxes {32 mn, 32 k} of 4096 B, SWIZZLE_128B_ATOM_32B (32-bit MN-major
+//                operands only exist in that layout); inside a box k-row kk at kk*128 B, 4-row
+//                swizzle groups 512 B apart (SBO); LBO = 4096 B between mn blocks; an MMA of K = 8
+//                consumes two groups = 1024 B.
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                const __grid_constant__ CUtensorMap mapB, int M, int N,
+                                                                int Kfull, int kchunk, float* __restrict__ C, int ldc,
+                                                                const float* __restrict__ bias, float beta,
+                                                                float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_dyn[];
+  // the 128-byte swizzle is a function of the shared-memory address: tiles must sit on 1024 B
+  uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  uint8_t* sA = smem_raw;
+  uint8_t* sB = smem_raw + STAGES * A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = warp_uniform(), lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(Kfull, kbeg + kchunk);
+  const int nk = (kend - kbeg + BK - 1) / BK;
+
+  if (warp == 0 && elect_one()) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait(&empty[s], (uint32_t)(i / STAGES - 1) & 1u);
+        mbar_expect_tx(&full[s], A_STAGE + B_STAGE);
+        const int k0 = kbeg + i * BK;
+        if (!A_MN) {
+          tma_load_2d(sA + s * A_STAGE, &mapA, &full[s], k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sA + s * A_STAGE + j * 4096, &mapA, &full[s], m0 + 32 * j, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sB + s * B_STAGE, &mapB, &full[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(sB + s * B_STAGE + j * 4096, &mapB, &full[s], n0 + 32 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint64_t dA = A_MN ? make_desc_sw128(smem_u32(sA), 4096, 512, 1) : make_desc_sw128(smem_u32(sA), 16, 1024, 2);
+    const uint64_t dB = B_MN ? make_desc_sw128(smem_u32(sB), 4096, 512, 1) : make_desc_sw128(smem_u32(sB), 16, 1024, 2);
+    constexpr uint32_t a_step = A_MN ? 1024 : UMMA_K * 4, b_step = B_MN ? 1024 : UMMA_K * 4;   // bytes per K = 8
+    for (int i = 0; i < nk; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(&full[s], (uint32_t)(i / STAGES) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk)
+          umma_tf32(tmem, dA + (uint64_t)((s * A_STAGE + kk * a_step) >> 4), dB + (uint64_t)((s * B_STAGE + kk * b_step) >> 4),
+                    idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&empty[s]);
+        if (i == nk - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue warps 2..5 own TMEM lane quadrants 2, 3, 0, 1 (a warp may only touch lanes 32*(warp%4)..)
+    const int q = warp & 3;
+    if (nk > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    constexpr int SLD = BN + 1;
+    float* stage = reinterpret_cast<float*>(smem_raw) + q * 32 * SLD;
+    static_assert(4 * 32 * SLD * 4 <= STAGES * A_STAGE, "staging tile must fit the operand ring");
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      if (nk > 0) {
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      } else {
+#pragma unroll
+        for (int x = 0; x < 16; ++x) v[x] = 0.f;
+      }
+#pragma unroll
+      for (int x = 0; x < 16; ++x) stage[lane * SLD + c0 + x] = v[x];
+    }
+    __syncwarp();
+    float* P = partial ? partial + (int64_t)blockIdx.z * M * N : nullptr;
+    float bv[BN / 32];
+#pragma unroll
+    for (int j = 0; j < BN / 32; ++j) {
+      const int n = n0 + lane + 32 * j;
+      bv[j] = (bias && !P && n < N) ? bias[n] : 0.f;
+    }
+    const int mrow0 = m0 + q * 32;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const int m = mrow0 + r;
+      if (m >= M) break;
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) {
+        const int n = n0 + lane + 32 * j;
+        if (n >= N) continue;
+        const float acc = stage[r * SLD + lane + 32 * j];
+        if (P) {
+          P[(int64_t)m * N + n] = acc;
+        } else {
+          float* c = C + (int64_t)m * ldc + n;
+          float o = acc + bv[j];
+          if (beta != 0.f) o += beta * *c;
+          *c = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, BN);
+}
+
+void launch_splitk_reduce(const float* partial, int splits, int M, int N, float* C, int ldc, const float* bias,
+                          float beta, cudaStream_t s);   // gemm_f32.cu
+
+// ---------------------------------------------------------------- host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d0, d1, ld;
+  uint32_t b1;      // box rows; bit 31 = MN-major (32-byte swizzle atom)
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b1 == o.b1; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    for (uint64_t v : {k.d0, k.d1, k.ld, (uint64_t)k.b1}) h = h * 1000003u ^ (size_t)v;
+    return h;
+  }
+};
+
+// fp32 matrix with `d0` contiguous elements per row, `d1` rows of stride `ld` floats; box {32, b1}.
+static bool tensor_map(const float* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b1, bool mn_major, CUtensorMap* out) {
+  thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, d0, d1, ld, b1 | (mn_major ? 0x80000000u : 0u)};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {d0, d1};
+  const cuuint64_t gstr[1] = {ld * sizeof(float)};
+  const cuuint32_t box[2] = {32, b1};
+  const cuuint32_t estr[2] = {1, 1};
+  if (fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return true;
+}
+
+}  // namespace slnlp
+
+using namespace slnlp;
+
+extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda,
+                               const float* B, int ldb, float* C, int ldc, const float* bias, float beta,
+                               float* workspace, int64_t workspace_floats, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(A && B && C, "gemm_tf32: null pointer");
+  SLNLP_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "gemm_tf32: bad shape M=%d N=%d K=%d ldc=%d", M, N, K, ldc);
+  SLNLP_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N), "gemm_tf32: bad lda/ldb");
+  if (M == 0 || N == 0) return 0;
+  // TMA wants 16-byte aligned bases and row strides; tiny problems are not worth a 128 x 64 tile.
+  // Anything else goes to the fp32 kernel - still CUDA, never a CPU path.
+  const bool ok = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && lda % 4 == 0 && ldb % 4 == 0 && M >= 64 &&
+                  N >= 32 && K >= 32;
+  CUtensorMap mapA, mapB;
+  // A(m,k): transA=0 -> [M rows, K contiguous] (K-major); transA=1 -> stored [K rows, M contiguous] (MN-major)
+  // B(k,n): transB=1 -> stored [N rows, K contiguous] (K-major); transB=0 -> [K rows, N contiguous] (MN-major)
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  if (!ok || !(a_mn ? tensor_map(A, M, K, lda, 32, true, &mapA) : tensor_map(A, K, M, lda, BM, false, &mapA)) ||
+      !(b_mn ? tensor_map(B, N, K, ldb, 32, true, &mapB) : tensor_map(B, K, N, ldb, BN, false, &mapB)))
+    return slnlp_gemm_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, workspace, workspace_floats, stream);
+  cudaStream_t s = as_stream(stream);
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  SLNLP_CHECK_ARG(grid.y <= 65535, "gemm_tf32: M too large");
+  const int tiles = grid.x * grid.y;
+  int splits = 1;
+  if (workspace && tiles < sm_count() && K >= 512) {
+    splits = (2 * sm_count()) / tiles;
+    if (splits > K / 128) splits = K / 128;
+    while (splits > 1 && (int64_t)splits * M * N > workspace_floats) --splits;
+    if (splits < 1) splits = 1;
+  }
+  int kchunk = K;
+  float* partial = nullptr;
+  if (splits > 1) {
+    kchunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+    splits = (K + kchunk - 1) / kchunk;
+    grid.z = splits;
+    partial = workspace;
+  }
+  const size_t sm = STAGES * (A_STAGE + B_STAGE) + (2 * STAGES + 1) * 8 + 16 + 1024;
+#define SLNLP_GO(AMN, BMN)                                                                                         \
+  do {                                                                                                             \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      cudaFuncSetAttribute(gemm_tma_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);        \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    gemm_tma_kernel<AMN, BMN><<<grid, TMA_THREADS, sm, s>>>(mapA, mapB, M, N, K, kchunk, C, ldc, bias, beta, partial); \
+  } while (0)
+  if (!a_mn && !b_mn) SLNLP_GO(false, false);
+  else if (!a_mn && b_mn) SLNLP_GO(false, true);
+  else if (a_mn && !b_mn) SLNLP_GO(true, false);
+  else SLNLP_GO(true, true);
+#undef SLNLP_GO
+  if (partial) launch_splitk_reduce(partial, splits, M, N, C, ldc, bias, beta, s);
+  SLNLP_LAUNCH_OK("gemm_tf32");
+  return 0;
+}

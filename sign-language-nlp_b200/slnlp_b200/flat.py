@@ -12,7 +12,8 @@ import torch.nn as nn
 
 from ._lib import check, lib
 
-_HAS_GEMM_BF16 = hasattr(lib, "slnlp_gemm_bf16")
+import os as _os
+_TC_GEMM = lib.slnlp_gemm_bf16 if _os.environ.get("SLNLP_GEMM", "tf32") == "bf16" else lib.slnlp_gemm_tf32
 
 
 def _stream():
@@ -150,7 +151,8 @@ class FlatParamModule(nn.Module):
 
     # ------------------------------------------------------------------ kernels
     def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0, big=False):
-        fn = lib.slnlp_gemm_bf16 if (self.precision == "bf16" and big and _HAS_GEMM_BF16) else lib.slnlp_gemm_f32
+        # tensor-core path: the TMA-fed TF32 kernel (SLNLP_GEMM=bf16 selects the register-staged bf16 one)
+        fn = _TC_GEMM if (self.precision == "bf16" and big) else lib.slnlp_gemm_f32
         ws = self._gemm_ws()
         check(fn(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, ws.data_ptr(), ws.numel(), _stream()), "gemm")
 

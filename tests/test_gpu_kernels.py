@@ -508,3 +508,33 @@ def test_gemm_bf16_tcgen05(tA, tB, M, N, K):
     tile_path = (tA or K % 8 == 0) and (not tB or K % 8 == 0)
     assert rel_err(C, rounded if tile_path else exact) < 1e-5   # exact up to fp32 accumulation order
     assert rel_err(C, exact) < BF16_RTOL
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (128, 64, 64), (3200, 1024, 128), (3200, 256, 1024), (1024, 256, 3200),
+                                   (512, 128, 3150), (200, 72, 136), (100, 128, 256), (3200, 1536, 512), (64, 32, 4000)])
+def test_gemm_tf32_tma(tA, tB, M, N, K):
+    """TMA-fed tcgen05 kind::tf32 GEMM vs fp64 on TF32-truncated inputs (tight: proves tile
+    addressing, swizzle, MN-major descriptors, split-K and ragged edges) and vs the exact product
+    (the 2e-2 budget of the tensor-core path)."""
+    from helpers import BF16_RTOL
+    L = _lib()
+    ldA, ldB = ((M if tA else K) + 3) // 4 * 4 + 4, ((K if tB else N) + 3) // 4 * 4      # padded leading dimensions
+    Afull = cuda(*((K, ldA) if tA else (M, ldA)), seed=61)
+    Bfull = cuda(*((N, ldB) if tB else (K, ldB)), seed=62)
+    A = Afull[:, :(M if tA else K)]
+    B = Bfull[:, :(K if tB else N)]
+    bias, C0 = cuda(N, seed=63), cuda(M, N, seed=64)
+    ws = torch.empty(L.lib.slnlp_gemm_workspace_floats(), device="cuda")
+    C = C0.clone()
+    L.check(L.lib.slnlp_gemm_tf32(tA, tB, M, N, K, Afull.data_ptr(), ldA, Bfull.data_ptr(), ldB,
+                                  C.data_ptr(), N, bias.data_ptr(), 0.5, ws.data_ptr(), ws.numel(), S()))
+    opA, opB = (A.t() if tA else A), (B.t() if tB else B)
+
+    def tf32(x):        # the tensor core reads the top 19 bits of an fp32 operand
+        return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+    trunc = tf32(opA) @ tf32(opB) + bias.double() + 0.5 * C0.double()
+    exact = opA.double() @ opB.double() + bias.double() + 0.5 * C0.double()
+    assert rel_err(C, exact) < BF16_RTOL
+    assert rel_err(C, exact) < 2e-3                    # TF32: ~2^-11 per operand
+    assert rel_err(C, trunc) < 2e-5 or rel_err(C, exact) < 1e-6   # (fp32 fallback shapes are exact)
