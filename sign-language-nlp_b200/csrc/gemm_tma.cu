@@ -16,49 +16,13 @@
 // (the dW = dY^T X and dX = dY W GEMMs of the backward pass), so no operand is ever transposed
 // in HBM.  Long-K / small-MN problems (dW over K = B*T) use deterministic split-K into the
 // caller's workspace.
-#include <cuda.h>
-
-#include <unordered_map>
-
-#include "tc05.cuh"
+#include "tma.cuh"
 
 namespace slnlp {
 
 constexpr int BM = 128, BN = 64, BK = 32, STAGES = 4;      // BK floats = 128 bytes = one swizzle row
 constexpr int A_STAGE = BM * BK * 4, B_STAGE = BN * BK * 4;
 constexpr int TMA_THREADS = 192;                             // producer, MMA, 4 epilogue warps
-constexpr int UMMA_K = 8;                                    // tf32
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 128-byte-swizzled operand descriptor (cute::UMMA::SmemDescriptor): layout_type 2 = SWIZZLE_128B
-// (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks: the only MN-major layout of 32-bit operands)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout_type) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout_type << 61);
-}
-// c = f32, a = b = tf32, per-operand major bit (0 = K-major, 1 = MN-major)
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // A_MN / B_MN: the operand is stored with its M (resp. N) index contiguous ("MN-major").
 // K-major tile : one TMA box {32 k, rows}, SWIZZLE_128B; row r at r*128 B, 8-row groups 1024 B
@@ -203,64 +167,6 @@ __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_cons
 void launch_splitk_reduce(const float* partial, int splits, int M, int N, float* C, int ldc, const float* bias,
                           float beta, cudaStream_t s);   // gemm_f32.cu
 
-// ---------------------------------------------------------------- host: tensor maps
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-struct MapKey {
-  const void* ptr;
-  uint64_t d0, d1, ld;
-  uint32_t b1;      // box rows; bit 31 = MN-major (32-byte swizzle atom)
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b1 == o.b1; }
-};
-struct MapKeyHash {
-  size_t operator()(const MapKey& k) const {
-    size_t h = reinterpret_cast<size_t>(k.ptr);
-    for (uint64_t v : {k.d0, k.d1, k.ld, (uint64_t)k.b1}) h = h * 1000003u ^ (size_t)v;
-    return h;
-  }
-};
-
-// fp32 matrix with `d0` contiguous elements per row, `d1` rows of stride `ld` floats; box {32, b1}.
-static bool tensor_map(const float* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b1, bool mn_major, CUtensorMap* out) {
-  thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  const MapKey key{ptr, d0, d1, ld, b1 | (mn_major ? 0x80000000u : 0u)};
-  auto it = cache.find(key);
-  if (it != cache.end()) {
-    *out = it->second;
-    return true;
-  }
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  const cuuint64_t gdim[2] = {d0, d1};
-  const cuuint64_t gstr[1] = {ld * sizeof(float)};
-  const cuuint32_t box[2] = {32, b1};
-  const cuuint32_t estr[2] = {1, 1};
-  if (fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
-         CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return false;
-  if (cache.size() > 8192) cache.clear();
-  cache.emplace(key, *out);
-  return true;
-}
-
 }  // namespace slnlp
 
 using namespace slnlp;
@@ -274,7 +180,7 @@ extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, cons
   if (M == 0 || N == 0) return 0;
   // TMA wants 16-byte aligned bases and row strides; tiny problems are not worth a 128 x 64 tile.
   // Anything else goes to the fp32 kernel - still CUDA, never a CPU path.
-  const bool ok = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && lda % 4 == 0 && ldb % 4 == 0 && M >= 64 &&
+  const bool ok = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && lda % 4 == 0 && ldb % 4 == 0 && M >= 8 &&
                   N >= 32 && K >= 32;
   CUtensorMap mapA, mapB;
   // A(m,k): transA=0 -> [M rows, K contiguous] (K-major); transA=1 -> stored [K rows, M contiguous] (MN-major)

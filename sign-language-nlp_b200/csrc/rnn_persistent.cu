@@ -20,10 +20,14 @@
 namespace slnlp {
 
 constexpr int PH = 128;   // hidden size handled by this kernel
-constexpr int PN = 16;    // sequences per CTA (MMA N)
+constexpr int PN = 16;    // MMA N (the smallest N of an M = 128 instruction)
+constexpr int PSEQ = 8;   // sequences a CTA actually owns (columns PSEQ..PN-1 of the B tile stay zero): the
+                          // per-step gate math and stores scale with PSEQ and idle SMs are free at batch 50
 constexpr int PTHREADS = 512;  // 16 warps: TMEM lane quadrant = warp % 4, column group = warp / 4
-constexpr int PC = PN / 4;     // batch columns per thread
+constexpr int PC = PSEQ / 4;   // batch columns per thread
 constexpr int NACC = 4;        // BPTT: partial accumulators (independent MMA chains)
+constexpr int A_COL0 = 64;     // TMEM: accumulators in columns [0, 64), the resident W_hh operand from 64 on
+constexpr int TMEM_COLS = 512; // 64 + up to 256 operand columns -> the whole tensor memory of the SM
 
 #ifdef SLNLP_PERSIST_TIMING
 // debug build only: per-phase cycle counters of CTA (0,0), read back by slnlp_debug_persist_clocks
@@ -50,31 +54,18 @@ template <int G>
 __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(PersistFwd p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int H = PH;
-  uint8_t* sW = smem_raw;                       // G tiles of [128 x 128] bf16, canonical
-  uint8_t* sH = smem_raw + G * H * H * 2;       // [PN x 128] bf16, canonical (B operand)
+  uint8_t* sH = smem_raw;                       // [PN x 128] bf16, canonical (B operand)
   uint64_t* bar = reinterpret_cast<uint64_t*>(sH + PN * H * 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, warp_u = warp_uniform();
-  const int d = blockIdx.y, b0 = blockIdx.x * PN;
+  const int d = blockIdx.y, b0 = blockIdx.x * PSEQ;
   const int T = p.T, B = p.B;
   const int j = tid & (H - 1);   // hidden unit = TMEM lane
   const int cg = tid >> 7;       // column group: batch columns cg*PC .. cg*PC+PC-1
 
-  // ---- one-time setup: W_hh -> bf16 canonical tiles; h tile = h0 or 0
+  // ---- one-time setup: h tile = h0 or 0 (W_hh goes to tensor memory below)
   const float* W = p.w_hh + (int64_t)d * G * H * H;
-  for (int e = tid; e < G * H * (H / 8); e += PTHREADS) {
-    const int r = e % (G * H), k8 = e / (G * H);  // consecutive threads -> consecutive rows (conflict-free stores)
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(W + (int64_t)r * H + k8 * 8));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(W + (int64_t)r * H + k8 * 8) + 1);
-    __nv_bfloat162 q0 = __floats2bfloat162_rn(v0.x, v0.y), q1 = __floats2bfloat162_rn(v0.z, v0.w);
-    __nv_bfloat162 q2 = __floats2bfloat162_rn(v1.x, v1.y), q3 = __floats2bfloat162_rn(v1.z, v1.w);
-    uint4 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
-    pk.z = *reinterpret_cast<uint32_t*>(&q2); pk.w = *reinterpret_cast<uint32_t*>(&q3);
-    const int g = r / H, rr = r % H;
-    *reinterpret_cast<uint4*>(sW + g * (H * H * 2) + canon_off(rr, k8 * 8, H)) = pk;
-  }
   float hreg[PC], creg[PC];
   int len[PC];
 #pragma unroll
@@ -86,15 +77,37 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
     *reinterpret_cast<__nv_bfloat16*>(sH + canon_off(n, j, PN)) = __float2bfloat16(hreg[c]);
   }
   if (tid == 0) mbar_init(bar, 1);
-  if (warp == 0) tmem_alloc(tmem_slot, 64);
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_mine = tmem + ((uint32_t)((warp & 3) * 32) << 16) + cg * PC;
+  // W_hh -> tensor memory, the A operand of every step: gate tile g = [128 rows (lanes) x 128 k]
+  // bf16 = 64 packed 32-bit columns at column A_COL0 + 64 g.  Reading A from TMEM instead of
+  // shared memory takes the 128 KB-per-step operand fetch off the 128 B/clk shared-memory port
+  // (it bounded the step at ~1000 cycles).  Warp w fills lane quadrant w % 4 of gate w / 4.
+  if (cg < G) {
+    const float* wrow = W + ((int64_t)cg * H + j) * H;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wrow + i * 32) + u);
+        pk[2 * u] = pack2_bf16(v.x, v.y);
+        pk[2 * u + 1] = pack2_bf16(v.z, v.w);
+      }
+      tmem_st16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + A_COL0 + cg * 64 + i * 16, pk);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   constexpr uint32_t idesc = make_idesc(128, PN);
-  const uint64_t descA0 = make_desc(smem_u32(sW), H * 16, 128), descB0 = make_desc(smem_u32(sH), PN * 16, 128);
+  const uint64_t descB0 = make_desc(smem_u32(sH), PN * 16, 128);
   const bool have_state0 = p.h0 != nullptr;
   const float* bh = p.b_hh + (int64_t)d * G * H;
   float bias[G];
@@ -120,52 +133,73 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
     fin[c] = p.h_final ? p.h_final + ((int64_t)d * B + b) * H + j : nullptr;
     hoff[c] = canon_off(n, j, PN);
   }
-  // hoisted input projection, loaded one step ahead
-  float xg[G][PC];
-  auto load_x = [&](int t) {
+  // the h tile rows PSEQ..PN-1 are never written: zero them once
+  for (int e = tid; e < PN * H / 8; e += PTHREADS) {
+    const int n = e % PN;   // canonical tile: 16-byte core rows, row index = (e % (PN)) within a K-group
+    if (n >= PSEQ) reinterpret_cast<uint4*>(sH)[e] = make_uint4(0, 0, 0, 0);
+  }
+  fence_async_smem();
+  __syncthreads();
+  // hoisted input projection, loaded one step ahead into a second register set
+  float xg[G][PC], xn[G][PC];
+  auto load_x = [&](float (&x)[G][PC], int t) {
     const int64_t off = (int64_t)t * gstride;
 #pragma unroll
     for (int c = 0; c < PC; ++c) {
       const bool act = t < len[c];
 #pragma unroll
-      for (int g = 0; g < G; ++g) xg[g][c] = act ? gbase[c][off + g * H] : 0.f;
+      for (int g = 0; g < G; ++g) x[g][c] = act ? gbase[c][off + g * H] : 0.f;
     }
   };
-  load_x(d == 0 ? 0 : T - 1);
+  load_x(xg, d == 0 ? 0 : T - 1);
+  // results of a step are written to HBM one iteration later, while the next step's MMAs run
+  float gout[G][PC], hv[PC], sv[PC];
+  auto store_step = [&](int t) {
+    const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride;
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+      if (!valid[c]) continue;
+      if (t >= len[c]) {
+        obase[c][ooff] = 0.f;
+        sbase[c][ooff] = 0.f;
+        continue;
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) gbase[c][goff + g * H] = gout[g][c];
+      sbase[c][ooff] = sv[c];
+      obase[c][ooff] = hv[c];
+      if (fin[c] && (d == 0 ? t == len[c] - 1 : t == 0)) *fin[c] = hv[c];
+    }
+  };
 
   uint32_t phase = 0;
+  int t_prev = 0;
   for (int step = 0; step < T; ++step) {
     const int t = d == 0 ? step : T - 1 - step;
     const bool do_mma = step > 0 || have_state0;
-#ifdef SLNLP_PERSIST_TIMING
-    long long c0 = clock64(), c1 = c0, c2 = c0, c3 = c0, c4 = c0, c5 = c0;
-#endif
     if (do_mma && warp_u == 0 && elect_one()) {
-      // G gate tiles x (H/16) k-steps; descriptors differ only in the start-address field
+      // G gate tiles x (H/16) k-steps, A = W_hh from tensor memory, B = the h tile in shared memory;
       // issued k-major so that consecutive MMAs accumulate into different gate tiles
 #pragma unroll
       for (int kk = 0; kk < H / 16; ++kk)
 #pragma unroll
         for (int g = 0; g < G; ++g)
-          umma_bf16(tmem + g * PN, descA0 + (uint64_t)((g * (H * H * 2) + kk * 2 * (H * 16)) >> 4),
-                    descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk > 0 ? 1u : 0u);
+          umma_bf16_ts(tmem + g * PN, tmem + A_COL0 + g * 64 + kk * 8,
+                       descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk > 0 ? 1u : 0u);
       umma_commit(bar);
     }
     __syncwarp();
-#ifdef SLNLP_PERSIST_TIMING
-    c1 = clock64();
-#endif
+    // off the critical path (the tensor core is busy): previous step -> HBM, next step's x <- HBM
+    if (step > 0) store_step(t_prev);
+    if (step + 1 < T) load_x(xn, d == 0 ? step + 1 : T - 2 - step);
     float acc[G][PC];
     if (do_mma) {
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
-#ifdef SLNLP_PERSIST_TIMING
-      c2 = clock64();
-#endif
-      uint32_t raw[G][4];
+      uint32_t raw[G][PC];
 #pragma unroll
-      for (int g = 0; g < G; ++g) tmem_ld4_nowait(tmem_mine + g * PN, raw[g]);
+      for (int g = 0; g < G; ++g) tmem_ldn_nowait<PC>(tmem_mine + g * PN, raw[g]);
       tmem_wait_ld();
 #pragma unroll
       for (int g = 0; g < G; ++g)
@@ -177,10 +211,6 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
 #pragma unroll
         for (int c = 0; c < PC; ++c) acc[g][c] = 0.f;
     }
-#ifdef SLNLP_PERSIST_TIMING
-    c3 = clock64();
-#endif
-    float gout[G][PC], hv[PC], sv[PC];
 #pragma unroll
     for (int c = 0; c < PC; ++c) {
       if (G == 4) {
@@ -201,51 +231,26 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
         sv[c] = hn;
         gout[0][c] = gr; gout[1][c] = gz; gout[2][c] = gn;
       }
-    }
-    // next step's input projection: issue the loads before this step's stores
-    if (step + 1 < T) load_x(d == 0 ? step + 1 : T - 2 - step);
-    const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride;
-#pragma unroll
-    for (int c = 0; c < PC; ++c) {
-      if (!valid[c]) continue;
-      if (t >= len[c]) {
-        obase[c][ooff] = 0.f;
-        sbase[c][ooff] = 0.f;
-        continue;
+      // state update + next step's B tile: the only stores the next MMA waits for
+      if (valid[c] && t < len[c]) {
+        if (G == 4) creg[c] = sv[c];
+        hreg[c] = hv[c];
+        *reinterpret_cast<__nv_bfloat16*>(sH + hoff[c]) = __float2bfloat16(hv[c]);
       }
-#pragma unroll
-      for (int g = 0; g < G; ++g) gbase[c][goff + g * H] = gout[g][c];
-      sbase[c][ooff] = sv[c];
-      if (G == 4) creg[c] = sv[c];
-      hreg[c] = hv[c];
-      obase[c][ooff] = hv[c];
-      *reinterpret_cast<__nv_bfloat16*>(sH + hoff[c]) = __float2bfloat16(hv[c]);
-      if (fin[c] && (d == 0 ? t == len[c] - 1 : t == 0)) *fin[c] = hv[c];
     }
     // h tile (generic-proxy stores) -> visible to the tensor core; accumulators free to overwrite
-#ifdef SLNLP_PERSIST_TIMING
-    c4 = clock64();
-#endif
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-#ifdef SLNLP_PERSIST_TIMING
-    c5 = clock64();
-    if (blockIdx.x == 0 && blockIdx.y == 0 && step > 0) {
-      if (tid < 32 && c1 - c0 > 200) { atomicAdd(&g_clk[0], (unsigned long long)(c1 - c0)); }     // MMA issue (elected lane)
-      if (tid == 200) {
-        atomicAdd(&g_clk[1], (unsigned long long)(c2 - c1));   // wait for MMA completion
-        atomicAdd(&g_clk[2], (unsigned long long)(c3 - c2));   // tmem ld
-        atomicAdd(&g_clk[3], (unsigned long long)(c4 - c3));   // compute + prefetch issue + stores
-        atomicAdd(&g_clk[4], (unsigned long long)(c5 - c4));   // fences + syncthreads
-        atomicAdd(&g_clk[5], (unsigned long long)(c5 - c0));   // whole step
-        atomicAdd(&g_clk[6], 1ull);
-      }
-    }
-#endif
+    t_prev = t;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int c = 0; c < PC; ++c) xg[g][c] = xn[g][c];
   }
-  if (warp == 0) tmem_dealloc(tmem, 64);
+  store_step(t_prev);
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------- BPTT twin
@@ -269,42 +274,48 @@ template <int G>
 __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(PersistBwd p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int H = PH, GH = G * PH;
-  uint8_t* sW = smem_raw;                        // A' = W_hh^T: [128 (k) x GH (j)] bf16, canonical
-  uint8_t* sD = smem_raw + GH * H * 2;           // B' = dG: [PN x GH] bf16, canonical
+  uint8_t* sD = smem_raw;                        // B' = dG: [PN x GH] bf16, canonical
   uint64_t* bar = reinterpret_cast<uint64_t*>(sD + PN * GH * 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, warp_u = warp_uniform();
-  const int d = blockIdx.y, b0 = blockIdx.x * PN;
+  const int d = blockIdx.y, b0 = blockIdx.x * PSEQ;
   const int T = p.T, B = p.B;
   const int k = tid & (H - 1);  // hidden unit = TMEM lane = output row of W_hh^T
   const int cg = tid >> 7;
 
   const float* W = p.w_hh + (int64_t)d * GH * H;
-  // A'(m = kcol, kk = jrow) = W_hh[jrow][kcol]: thread = column kcol, 8 consecutive rows -> one 16-byte
-  // store (global reads coalesced across the warp, shared stores 16 bytes apart: conflict-free)
-  for (int jg = cg; jg < GH / 8; jg += PTHREADS / H) {
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(W + (int64_t)(jg * 8 + u) * H + k);
-    __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
-    __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
-    uint4 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
-    pk.z = *reinterpret_cast<uint32_t*>(&q2); pk.w = *reinterpret_cast<uint32_t*>(&q3);
-    *reinterpret_cast<uint4*>(sW + canon_off(k, jg * 8, H)) = pk;
-  }
   for (int e = tid; e < PN * GH / 8; e += PTHREADS) reinterpret_cast<uint4*>(sD)[e] = make_uint4(0, 0, 0, 0);
   if (tid == 0) mbar_init(bar, 1);
-  if (warp == 0) tmem_alloc(tmem_slot, 64);
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_mine = tmem + ((uint32_t)((warp & 3) * 32) << 16) + cg * PC;
+  // A' = W_hh^T -> tensor memory: lane = hidden unit k, K index = gate row j' (GH of them) = GH/2 packed
+  // columns from A_COL0.  Column group cg fills rows j' in [cg*GH/4, (cg+1)*GH/4): global reads are
+  // coalesced across the warp (consecutive k).
+  {
+    constexpr int JQ = GH / 4;   // 32 G gate rows -> 16 G packed columns = G stores of 16 columns
+#pragma unroll 1
+    for (int i = 0; i < G; ++i) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int jr = cg * JQ + i * 32 + 2 * u;
+        pk[u] = pack2_bf16(__ldg(W + (int64_t)jr * H + k), __ldg(W + (int64_t)(jr + 1) * H + k));
+      }
+      tmem_st16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + A_COL0 + cg * (JQ / 2) + i * 16, pk);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   constexpr uint32_t idesc = make_idesc(128, PN);
-  const uint64_t descA0 = make_desc(smem_u32(sW), H * 16, 128), descB0 = make_desc(smem_u32(sD), PN * 16, 128);
+  const uint64_t descB0 = make_desc(smem_u32(sD), PN * 16, 128);
 
   int len[PC];
   float carry[PC];  // LSTM: dc carry; GRU: direct dh carry (dh * z)
@@ -336,9 +347,13 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     cidx[c] = ((int64_t)d * B + b) * H + k;
     doff[c] = canon_off(n, k, PN);
   }
-  // per-step operands, loaded one step ahead: activated gates, stash, predecessor state, dout
-  float gin[G][PC], sin_[PC], pin[PC], din[PC];
-  auto load_step = [&](int t) {
+  // per-step operands, loaded one step ahead into a second register set: activated gates, stash,
+  // predecessor state, dout
+  struct StepIn {
+    float g[G][PC], s[PC], pv[PC], d[PC];
+  };
+  StepIn cur, nxt;
+  auto load_step = [&](StepIn& in, int t) {
     const int tp = d == 0 ? t - 1 : t + 1;
     const bool has_prev = tp >= 0 && tp < T;
     const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride, poff = (int64_t)tp * ostride;
@@ -346,42 +361,63 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     for (int c = 0; c < PC; ++c) {
       const bool act = t < len[c];
 #pragma unroll
-      for (int g = 0; g < G; ++g) gin[g][c] = act ? gbase[c][goff + g * H] : 0.f;
-      sin_[c] = act ? sbase[c][ooff] : 0.f;
-      din[c] = (act && dbase[c]) ? dbase[c][ooff] : 0.f;
+      for (int g = 0; g < G; ++g) in.g[g][c] = act ? gbase[c][goff + g * H] : 0.f;
+      in.s[c] = act ? sbase[c][ooff] : 0.f;
+      in.d[c] = (act && dbase[c]) ? dbase[c][ooff] : 0.f;
       float pv = 0.f;
       if (act) {
         if (G == 4) pv = has_prev ? sbase[c][poff] : (p.c0 ? p.c0[cidx[c]] : 0.f);
         else pv = has_prev ? obase[c][poff] : (p.h0 ? p.h0[cidx[c]] : 0.f);
       }
-      pin[c] = pv;
+      in.pv[c] = pv;
     }
   };
-  load_step(d == 0 ? T - 1 : 0);
+  load_step(cur, d == 0 ? T - 1 : 0);
+  // d(pre-activations) of a step go to HBM one iteration later, while the next step's MMAs run
+  float dg[G][PC], dst[PC];
+  auto store_step = [&](int t) {
+    const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride;
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+      if (!valid[c]) continue;
+#pragma unroll
+      for (int g = 0; g < G; ++g) gbase[c][goff + g * H] = dg[g][c];
+      if (G == 3) sbase[c][ooff] = dst[c];
+    }
+  };
 
   uint32_t phase = 0;
   const int nsteps = T + ((p.dh0 || p.dc0) ? 1 : 0);
+  int t_prev = 0;
+  bool pending = false;
   for (int step = 0; step < nsteps; ++step) {
     const bool final_only = step == T;
     const int t = final_only ? (d == 0 ? -1 : T) : (d == 0 ? T - 1 - step : step);
     const bool do_mma = step > 0;
     if (do_mma && warp_u == 0 && elect_one()) {
-      // NACC partial accumulators: consecutive MMAs are independent, the epilogue adds them
+      // A' = W_hh^T from tensor memory, B' = the dG tile; NACC partial accumulators: consecutive
+      // MMAs are independent, the epilogue adds them
 #pragma unroll
       for (int kk = 0; kk < GH / 16; ++kk)
-        umma_bf16(tmem + (kk % NACC) * PN, descA0 + (uint64_t)((kk * 2 * (H * 16)) >> 4),
-                  descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk >= NACC ? 1u : 0u);
+        umma_bf16_ts(tmem + (kk % NACC) * PN, tmem + A_COL0 + kk * 8,
+                     descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk >= NACC ? 1u : 0u);
       umma_commit(bar);
     }
     __syncwarp();
+    // off the critical path: previous step's gradients -> HBM, next step's operands <- HBM
+    if (pending) {
+      store_step(t_prev);
+      pending = false;
+    }
+    if (step + 1 < T) load_step(nxt, d == 0 ? T - 2 - step : step + 1);
     float m[PC];
     if (do_mma) {
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
-      uint32_t raw[NACC][4];
+      uint32_t raw[NACC][PC];
 #pragma unroll
-      for (int a = 0; a < NACC; ++a) tmem_ld4_nowait(tmem_mine + a * PN, raw[a]);
+      for (int a = 0; a < NACC; ++a) tmem_ldn_nowait<PC>(tmem_mine + a * PN, raw[a]);
       tmem_wait_ld();
 #pragma unroll
       for (int c = 0; c < PC; ++c) {
@@ -407,74 +443,69 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
       }
       break;
     }
-    float dg[G][PC], dst[PC];
 #pragma unroll
     for (int c = 0; c < PC; ++c) {
       dst[c] = 0.f;
       if (t >= len[c]) {
 #pragma unroll
         for (int g = 0; g < G; ++g) dg[g][c] = 0.f;
-        continue;
-      }
-      const bool inject = d == 0 ? t == len[c] - 1 : t == 0;
-      float dh = din[c];
-      if (G == 4) {
-        float dc_in;
-        if (inject) {
-          dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
-          dc_in = p.dc_final ? p.dc_final[cidx[c]] : 0.f;
-        } else {
-          dh += m[c];
-          dc_in = carry[c];
-        }
-        const float gi = gin[0][c], gf = gin[1][c], gg = gin[2][c], go = gin[G - 1][c];
-        const float tc = tanh_fast(sin_[c]);
-        const float dc = dh * go * (1.f - tc * tc) + dc_in;
-        dg[0][c] = dc * gg * gi * (1.f - gi);
-        dg[1][c] = dc * pin[c] * gf * (1.f - gf);
-        dg[2][c] = dc * gi * (1.f - gg * gg);
-        dg[G - 1][c] = dh * tc * go * (1.f - go);
-        carry[c] = dc * gf;
       } else {
-        if (inject) dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
-        else dh += m[c] + carry[c];
-        const float gr = gin[0][c], gz = gin[1][c], gn = gin[2][c];
-        const float da_n = dh * (1.f - gz) * (1.f - gn * gn);
-        dg[0][c] = da_n * sin_[c] * gr * (1.f - gr);
-        dg[1][c] = dh * (pin[c] - gn) * gz * (1.f - gz);
-        dg[2][c] = da_n;
-        dst[c] = da_n * gr;
-        carry[c] = dh * gz;
+        const bool inject = d == 0 ? t == len[c] - 1 : t == 0;
+        float dh = cur.d[c];
+        if (G == 4) {
+          float dc_in;
+          if (inject) {
+            dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
+            dc_in = p.dc_final ? p.dc_final[cidx[c]] : 0.f;
+          } else {
+            dh += m[c];
+            dc_in = carry[c];
+          }
+          const float gi = cur.g[0][c], gf = cur.g[1][c], gg = cur.g[2][c], go = cur.g[G - 1][c];
+          const float tc = tanh_fast(cur.s[c]);
+          const float dc = dh * go * (1.f - tc * tc) + dc_in;
+          dg[0][c] = dc * gg * gi * (1.f - gi);
+          dg[1][c] = dc * cur.pv[c] * gf * (1.f - gf);
+          dg[2][c] = dc * gi * (1.f - gg * gg);
+          dg[G - 1][c] = dh * tc * go * (1.f - go);
+          carry[c] = dc * gf;
+        } else {
+          if (inject) dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
+          else dh += m[c] + carry[c];
+          const float gr = cur.g[0][c], gz = cur.g[1][c], gn = cur.g[2][c];
+          const float da_n = dh * (1.f - gz) * (1.f - gn * gn);
+          dg[0][c] = da_n * cur.s[c] * gr * (1.f - gr);
+          dg[1][c] = dh * (cur.pv[c] - gn) * gz * (1.f - gz);
+          dg[2][c] = da_n;
+          dst[c] = da_n * gr;
+          carry[c] = dh * gz;
+        }
       }
-    }
-    // operands of the next step: issue the loads before this step's stores
-    if (step + 1 < T) load_step(d == 0 ? T - 2 - step : step + 1);
-    const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride;
+      // h-side gradients of this step = next step's B operand: dG[n][g*H + k]; consecutive gates are
+      // H/8 K-groups apart in the canonical tile.  The only stores the next MMA waits for.
+      if (valid[c]) {
 #pragma unroll
-    for (int c = 0; c < PC; ++c) {
-      if (!valid[c]) continue;
-#pragma unroll
-      for (int g = 0; g < G; ++g) gbase[c][goff + g * H] = dg[g][c];
-      if (G == 3) sbase[c][ooff] = dst[c];
-      // h-side gradients of this step = next step's B operand: dG[n][g*H + k]; consecutive
-      // gates are H/8 K-groups apart in the canonical tile
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float hv = (G == 3 && g == 2) ? dst[c] : dg[g][c];
-        *reinterpret_cast<__nv_bfloat16*>(sD + doff[c] + g * (H / 8) * (PN * 16)) = __float2bfloat16(hv);
+        for (int g = 0; g < G; ++g) {
+          const float hv = (G == 3 && g == 2) ? dst[c] : dg[g][c];
+          *reinterpret_cast<__nv_bfloat16*>(sD + doff[c] + g * (H / 8) * (PN * 16)) = __float2bfloat16(hv);
+        }
       }
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    t_prev = t;
+    pending = true;
+    cur = nxt;
   }
+  if (pending) store_step(t_prev);
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 64);
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-static size_t persist_fwd_smem(int G) { return (size_t)G * PH * PH * 2 + PN * PH * 2 + 64; }
-static size_t persist_bwd_smem(int G) { return (size_t)G * PH * PH * 2 + (size_t)PN * G * PH * 2 + 64; }
+static size_t persist_fwd_smem(int G) { return (size_t)PN * PH * 2 + 64; }
+static size_t persist_bwd_smem(int G) { return (size_t)PN * G * PH * 2 + 64; }
 
 static bool tc_shape_ok(int H, const float* w_hh) { return H == PH && ((uintptr_t)w_hh & 15) == 0; }
 
@@ -483,7 +514,7 @@ int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, cons
                      float* out, float* stash, float* h_final, cudaStream_t s) {
   if (!tc_shape_ok(H, w_hh)) return -1;
   PersistFwd p{T, B, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final};
-  dim3 grid(ceil_div(B, PN), ndir);
+  dim3 grid(ceil_div(B, PSEQ), ndir);
   if (mode == SLNLP_MODE_LSTM) {
     const size_t sm = persist_fwd_smem(4);
     cudaFuncSetAttribute(rnn_persistent_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -503,7 +534,7 @@ int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, floa
                      cudaStream_t s) {
   if (!tc_shape_ok(H, w_hh)) return -1;
   PersistBwd p{T, B, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0};
-  dim3 grid(ceil_div(B, PN), ndir);
+  dim3 grid(ceil_div(B, PSEQ), ndir);
   if (mode == SLNLP_MODE_LSTM) {
     const size_t sm = persist_bwd_smem(4);
     cudaFuncSetAttribute(rnn_persistent_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

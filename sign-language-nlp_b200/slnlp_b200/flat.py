@@ -152,7 +152,9 @@ class FlatParamModule(nn.Module):
     # ------------------------------------------------------------------ kernels
     def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0, big=False):
         # tensor-core path: the TMA-fed TF32 kernel (SLNLP_GEMM=bf16 selects the register-staged bf16 one)
-        fn = _TC_GEMM if (self.precision == "bf16" and big) else lib.slnlp_gemm_f32
+        # (`big` marks the [B*T]-row GEMMs; the tensor-core path takes the skinny ones too - the
+        # library falls back to the fp32 kernel by itself for shapes a 128-row tile cannot cover)
+        fn = _TC_GEMM if self.precision == "bf16" else lib.slnlp_gemm_f32
         ws = self._gemm_ws()
         check(fn(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, ws.data_ptr(), ws.numel(), _stream()), "gemm")
 
