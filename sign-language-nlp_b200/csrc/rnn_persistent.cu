@@ -1,17 +1,20 @@
 // K4 on the 5th-gen tensor cores: persistent recurrent layer for H = 128.
 //
-// One CTA owns one direction and one slice of 16 sequences for ALL timesteps (the
-// recurrence is independent across the batch, so no CTA ever waits for another):
-//   * W_hh (bf16) is loaded ONCE into shared memory in the canonical K-major
-//     no-swizzle UMMA layout and stays resident for the whole layer;
-//   * each step is D[gate rows (M=128 per gate tile), batch (N=16)] = W_hh_g . h^T
-//     issued by one thread as tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM);
-//     swap-AB: the gate rows are MMA-M, the batch is MMA-N;
-//   * the epilogue threads (TMEM lane = hidden unit) read the 4 (3) gate accumulators
-//     with tcgen05.ld, add the hoisted x W_ih^T + b_ih, apply the gate nonlinearities
-//     and the cell update in fp32, keep c / h in registers across timesteps, write
-//     out / stash for BPTT, and store h (bf16) straight into the next step's B tile.
-// The BPTT twin runs dG . W_hh (K = G*H) the same way with W_hh^T resident.
+// One CTA owns one direction and a slice of 4 (16 at large batch) sequences for ALL timesteps
+// (the recurrence is independent across the batch, so no CTA ever waits for another):
+//   * W_hh (bf16) is loaded ONCE into TENSOR MEMORY (128 lanes x 64 packed columns per gate
+//     tile) and stays resident for the whole layer as the A operand of every MMA; reading it
+//     from shared memory instead costs 128 KB per step through a 128 B/clk port;
+//   * each step is D[gate rows (M=128 per gate tile), batch (N=16)] = W_hh_g . h^T issued by
+//     one elected thread as tcgen05.mma kind::f16 (A from TMEM, B = the h tile in shared
+//     memory, bf16 x bf16 -> fp32 in TMEM); swap-AB: gate rows are MMA-M, the batch is MMA-N;
+//   * the epilogue threads (TMEM lane = hidden unit) read the 4 (3) gate accumulators with
+//     tcgen05.ld, add the hoisted x W_ih^T + b_ih, apply the gate nonlinearities and the cell
+//     update in fp32, keep c / h in registers across timesteps, and store h (bf16) straight
+//     into the next step's B tile - the only store on the step-to-step critical path;
+//   * out / stash / activated gates go to HBM one iteration later and the next step's hoisted
+//     projection is prefetched into a second register set, both while the next MMAs run.
+// The BPTT twin runs dG . W_hh (K = G*H) the same way with W_hh^T resident in TMEM.
 //
 // Numerics: the recurrent product rounds h and W_hh (dG in BPTT) to bf16 with fp32
 // accumulation - the 2e-2 path of north_star.  Everything else is fp32.
@@ -21,10 +24,10 @@ namespace slnlp {
 
 constexpr int PH = 128;   // hidden size handled by this kernel
 constexpr int PN = 16;    // MMA N (the smallest N of an M = 128 instruction)
-constexpr int PSEQ = 8;   // sequences a CTA actually owns (columns PSEQ..PN-1 of the B tile stay zero): the
-                          // per-step gate math and stores scale with PSEQ and idle SMs are free at batch 50
+// PSEQ (template): sequences a CTA actually owns; columns PSEQ..PN-1 of the B tile stay zero.  The per-step
+// gate math and stores scale with PSEQ, and at the reference's batch of 50 most SMs are idle, so small
+// batches run 4 sequences per CTA (26 CTAs at B = 50) and large ones 16 (fewer W_hh loads, fewer waves).
 constexpr int PTHREADS = 512;  // 16 warps: TMEM lane quadrant = warp % 4, column group = warp / 4
-constexpr int PC = PSEQ / 4;   // batch columns per thread
 constexpr int NACC = 4;        // BPTT: partial accumulators (independent MMA chains)
 constexpr int A_COL0 = 64;     // TMEM: accumulators in columns [0, 64), the resident W_hh operand from 64 on
 constexpr int TMEM_COLS = 512; // 64 + up to 256 operand columns -> the whole tensor memory of the SM
@@ -50,8 +53,9 @@ struct PersistFwd {
   float* h_final;
 };
 
-template <int G>
+template <int G, int PSEQ>
 __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(PersistFwd p) {
+  constexpr int PC = PSEQ / 4;   // batch columns per thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int H = PH;
   uint8_t* sH = smem_raw;                       // [PN x 128] bf16, canonical (B operand)
@@ -270,8 +274,9 @@ struct PersistBwd {
   float* dc0;
 };
 
-template <int G>
+template <int G, int PSEQ>
 __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(PersistBwd p) {
+  constexpr int PC = PSEQ / 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int H = PH, GH = G * PH;
   uint8_t* sD = smem_raw;                        // B' = dG: [PN x GH] bf16, canonical
@@ -504,25 +509,34 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-static size_t persist_fwd_smem(int G) { return (size_t)PN * PH * 2 + 64; }
+static size_t persist_fwd_smem(int) { return (size_t)PN * PH * 2 + 64; }
 static size_t persist_bwd_smem(int G) { return (size_t)PN * G * PH * 2 + 64; }
 
 static bool tc_shape_ok(int H, const float* w_hh) { return H == PH && ((uintptr_t)w_hh & 15) == 0; }
+
+static int seqs_per_cta(int B, int ndir) { return ceil_div(B, 4) * ndir <= (sm_count() > 0 ? sm_count() : 148) ? 4 : 16; }
+
+template <int G, int PSEQ>
+static void launch_persist_fwd(const PersistFwd& p, cudaStream_t s) {
+  const size_t sm = persist_fwd_smem(G);
+  rnn_persistent_fwd_kernel<G, PSEQ><<<dim3(ceil_div(p.B, PSEQ), p.ndir), PTHREADS, sm, s>>>(p);
+}
+template <int G, int PSEQ>
+static void launch_persist_bwd(const PersistBwd& p, cudaStream_t s) {
+  const size_t sm = persist_bwd_smem(G);
+  rnn_persistent_bwd_kernel<G, PSEQ><<<dim3(ceil_div(p.B, PSEQ), p.ndir), PTHREADS, sm, s>>>(p);
+}
 
 int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh,
                      const float* b_hh, const int64_t* lengths, const float* h0, const float* c0,
                      float* out, float* stash, float* h_final, cudaStream_t s) {
   if (!tc_shape_ok(H, w_hh)) return -1;
   PersistFwd p{T, B, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final};
-  dim3 grid(ceil_div(B, PSEQ), ndir);
+  const bool small = seqs_per_cta(B, ndir) == 4;
   if (mode == SLNLP_MODE_LSTM) {
-    const size_t sm = persist_fwd_smem(4);
-    cudaFuncSetAttribute(rnn_persistent_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    rnn_persistent_fwd_kernel<4><<<grid, PTHREADS, sm, s>>>(p);
+    if (small) launch_persist_fwd<4, 4>(p, s); else launch_persist_fwd<4, 16>(p, s);
   } else {
-    const size_t sm = persist_fwd_smem(3);
-    cudaFuncSetAttribute(rnn_persistent_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    rnn_persistent_fwd_kernel<3><<<grid, PTHREADS, sm, s>>>(p);
+    if (small) launch_persist_fwd<3, 4>(p, s); else launch_persist_fwd<3, 16>(p, s);
   }
   SLNLP_LAUNCH_OK("rnn_layer_fwd(tcgen05)");
   return 0;
@@ -534,15 +548,11 @@ int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, floa
                      cudaStream_t s) {
   if (!tc_shape_ok(H, w_hh)) return -1;
   PersistBwd p{T, B, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0};
-  dim3 grid(ceil_div(B, PSEQ), ndir);
+  const bool small = seqs_per_cta(B, ndir) == 4;
   if (mode == SLNLP_MODE_LSTM) {
-    const size_t sm = persist_bwd_smem(4);
-    cudaFuncSetAttribute(rnn_persistent_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    rnn_persistent_bwd_kernel<4><<<grid, PTHREADS, sm, s>>>(p);
+    if (small) launch_persist_bwd<4, 4>(p, s); else launch_persist_bwd<4, 16>(p, s);
   } else {
-    const size_t sm = persist_bwd_smem(3);
-    cudaFuncSetAttribute(rnn_persistent_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    rnn_persistent_bwd_kernel<3><<<grid, PTHREADS, sm, s>>>(p);
+    if (small) launch_persist_bwd<3, 4>(p, s); else launch_persist_bwd<3, 16>(p, s);
   }
   SLNLP_LAUNCH_OK("rnn_layer_bwd(tcgen05)");
   return 0;
