@@ -1,5 +1,5 @@
 """Run one encoder-layer forward + BPTT call of the recurrent kernels (cfg1 shape) so that
-ncu can capture them in isolation:  python profiles/prof_rnn_layer.py [fp32|bf16] [lstm|gru]"""
+ncu can capture them in isolation:  python profiles/prof_rnn_layer.py [fp32|bf16] [lstm|gru] [H]"""
 import os
 import sys
 
@@ -11,7 +11,8 @@ from slnlp_b200 import _lib
 L = _lib
 prec = 1 if (len(sys.argv) > 1 and sys.argv[1] == "bf16") else 0
 mode = 1 if (len(sys.argv) > 2 and sys.argv[2] == "gru") else 0
-T, B, H, G = 64, 50, 128, (3 if mode else 4)
+H = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+T, B, G = 64, 50, (3 if mode else 4)
 S = torch.cuda.current_stream().cuda_stream
 torch.manual_seed(0)
 w_hh = (torch.rand(2, G * H, H, device="cuda") * 2 - 1) / H ** 0.5

@@ -31,6 +31,24 @@ static inline cudaStream_t as_stream(slnlp_stream_t s) { return reinterpret_cast
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 int sm_count();
+// SLNLP_PDL=0 in the environment turns programmatic dependent launch off (plain stream order)
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 // kernels launched by this process through the C ABI (bench.py's gpu_launches claim)
 void note_launches(int64_t n);
 
@@ -96,6 +114,11 @@ __device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t step, ui
 #pragma unroll
   for (int j = 0; j < 4; ++j) u[j] = (float)(c[j] >> 8) * (1.0f / 16777216.0f);
 }
+// programmatic dependent launch: a kernel launched with launch_pdl() may start while its
+// predecessor in the stream is still running; it must not touch memory the predecessor writes
+// before pdl_wait(), and lets ITS successor start early with pdl_launch_dependents()
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // full-precision gate nonlinearities of the fp32 path (expf/tanhf, no fast-math)
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 #endif

@@ -2,6 +2,8 @@
 //   K1 embedding gather/scatter, K10 log-softmax + CE-on-logp, K11/K12 grad-norm +
 //   clip + SGD-momentum, dropout (own Philox), pad fill, small elementwise glue.
 // Reference call sites are cited in include/slnlp_b200.h next to each entry point.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include <atomic>
 
@@ -22,6 +24,14 @@ int fail(const char* fmt, ...) {
 static std::atomic<int64_t> g_launches{0};
 void note_launches(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launches() { return g_launches.load(std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SLNLP_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;

@@ -22,8 +22,8 @@ namespace slnlp {
 constexpr int SB = 128;                 // sequences per CTA (MMA M)
 constexpr int SU = 32;                  // hidden units per CTA
 constexpr int SK = 32;                  // k-tile (floats) = one 128-byte swizzle row
-constexpr int S_THREADS = 192;
-constexpr int SA_STAGE = SB * SK * 4;   // 16 KB
+constexpr int S_THREADS = 320;          // producer, MMA, 8 epilogue warps (two per TMEM lane quadrant, 16 units each)
+constexpr int SUH = SU / 2;             // hidden units per epilogue thread
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
@@ -61,7 +61,7 @@ struct Ring {
   uint64_t *full, *empty, *acc_full;
   uint32_t tmem;
 };
-template <int STAGES, int B_STAGE, int TCOLS>
+template <int STAGES, int SA_STAGE, int B_STAGE, int TCOLS>
 __device__ __forceinline__ Ring ring_setup(uint8_t* smem_dyn, int warp, const CUtensorMap* m0, const CUtensorMap* m1,
                                            const CUtensorMap* m2) {
   Ring r;
@@ -90,16 +90,16 @@ __device__ __forceinline__ Ring ring_setup(uint8_t* smem_dyn, int warp, const CU
   return r;
 }
 
-constexpr int F_STAGES = 4;
-
-// grid (H/32, ceil(B/128), ndir), block 192.  mapH: out as [T][B][ndir*H]; mapH0: h0 as [ndir][B][H];
-// mapW: w_hh as [ndir][G*H][H], box {32 k, 32 rows}.
-template <int G>
+// grid (H/32, ceil(B/128), ndir), block 320.  mapH: out as [T][B][ndir*H]; mapH0: h0 as [ndir][B][H];
+// mapW: w_hh as [ndir][G*H][H], box {32 k, 32 rows}.  AROWS = rows the A box actually loads (64 when
+// the batch fits: the MMA still reads 128 rows, the upper 64 are whatever shared memory holds and only
+// reach accumulator rows nobody reads) - half the bytes per stage buys twice the stages in flight.
+template <int G, int F_STAGES, int AROWS>
 __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH,
                                                                     const __grid_constant__ CUtensorMap mapH0,
                                                                     const __grid_constant__ CUtensorMap mapW, TcFwd p) {
   extern __shared__ uint8_t smem_dyn[];
-  constexpr int B_STAGE = G * SU * SK * 4, NCOL = G * SU;
+  constexpr int SA_STAGE = AROWS * SK * 4, B_STAGE = G * SU * SK * 4, NCOL = G * SU;
   const int warp = warp_uniform(), lane = threadIdx.x & 31;
   const int H = p.H, B = p.B, T = p.T;
   const int d = blockIdx.z, u0 = blockIdx.x * SU, b0 = blockIdx.y * SB;
@@ -107,13 +107,28 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid
   const int tp = d == 0 ? t - 1 : t + 1;
   const bool has_prev = tp >= 0 && tp < T;
   const int nk = (has_prev || p.h0) ? H / SK : 0;   // zero initial state: the recurrent product is exactly 0
-  Ring r = ring_setup<F_STAGES, B_STAGE, 128>(smem_dyn, warp, &mapH, &mapH0, &mapW);
+  Ring r = ring_setup<F_STAGES, SA_STAGE, B_STAGE, 128>(smem_dyn, warp, &mapH, &mapH0, &mapW);
 
+  // the next timestep's launch may start now: its prologue and its W_hh tiles overlap this step
+  pdl_launch_dependents();
   if (warp == 0) {
     if (elect_one()) {
-      for (int i = 0; i < nk; ++i) {
+      // first ring round: W_hh tiles do not depend on the previous step - issue them, THEN wait for
+      // the previous launch (h_{t-1} must be complete in HBM before the A tiles are read)
+      const int first = nk < F_STAGES ? nk : F_STAGES;
+      for (int i = 0; i < first; ++i) {
+        mbar_expect_tx(&r.full[i], SA_STAGE + B_STAGE);
+#pragma unroll
+        for (int g = 0; g < G; ++g) tma_load_3d(r.sB + i * B_STAGE + g * 4096, &mapW, &r.full[i], i * SK, g * H + u0, d);
+      }
+      pdl_wait();
+      for (int i = 0; i < first; ++i) {
+        if (has_prev) tma_load_3d(r.sA + i * SA_STAGE, &mapH, &r.full[i], d * H + i * SK, b0, tp);
+        else tma_load_3d(r.sA + i * SA_STAGE, &mapH0, &r.full[i], i * SK, b0, d);
+      }
+      for (int i = first; i < nk; ++i) {
         const int s = i % F_STAGES, k0 = i * SK;
-        if (i >= F_STAGES) mbar_wait(&r.empty[s], (uint32_t)(i / F_STAGES - 1) & 1u);
+        mbar_wait(&r.empty[s], (uint32_t)(i / F_STAGES - 1) & 1u);
         mbar_expect_tx(&r.full[s], SA_STAGE + B_STAGE);
         if (has_prev) tma_load_3d(r.sA + s * SA_STAGE, &mapH, &r.full[s], d * H + k0, b0, tp);
         else tma_load_3d(r.sA + s * SA_STAGE, &mapH0, &r.full[s], k0, b0, d);
@@ -139,34 +154,61 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid
       __syncwarp();
     }
   } else {
-    const int q = warp & 3;
+    pdl_wait();   // everything below reads what the previous launch wrote
+    const int q = warp & 3, uh = ((warp - 2) >> 2) * SUH;   // lane quadrant, first unit of this thread's half
     const int b = b0 + q * 32 + lane;
     const bool valid = b < B;
     const int len = (valid && p.lengths) ? (int)p.lengths[b] : T;
     const bool active = valid && t < len;
     const int bb = valid ? b : 0;
     const int64_t row = (int64_t)t * B + bb;
-    float* gt = p.gates + (row * p.ndir + d) * G * H + u0;
-    float* o = p.out + row * p.ndir * H + (int64_t)d * H + u0;
-    float* st = p.stash + (row * p.ndir + d) * H + u0;
-    const float* bh = p.b_hh + (int64_t)d * G * H + u0;
-    const int64_t cidx = ((int64_t)d * B + bb) * H + u0;
+    float* gt = p.gates + (row * p.ndir + d) * G * H + u0 + uh;
+    float* o = p.out + row * p.ndir * H + (int64_t)d * H + u0 + uh;
+    float* st = p.stash + (row * p.ndir + d) * H + u0 + uh;
+    const float* bh = p.b_hh + (int64_t)d * G * H + u0 + uh;
+    const int64_t cidx = ((int64_t)d * B + bb) * H + u0 + uh;
     // predecessor state of this sequence (fp32, exact): c_{t-1} (LSTM) / h_{t-1} (GRU)
     const float* prev = nullptr;
-    if (G == 4) prev = has_prev ? p.stash + (((int64_t)tp * B + bb) * p.ndir + d) * H + u0 : (p.c0 ? p.c0 + cidx : nullptr);
-    else prev = has_prev ? p.out + ((int64_t)tp * B + bb) * p.ndir * H + (int64_t)d * H + u0 : (p.h0 ? p.h0 + cidx : nullptr);
+    if (G == 4) prev = has_prev ? p.stash + (((int64_t)tp * B + bb) * p.ndir + d) * H + u0 + uh : (p.c0 ? p.c0 + cidx : nullptr);
+    else prev = has_prev ? p.out + ((int64_t)tp * B + bb) * p.ndir * H + (int64_t)d * H + u0 + uh : (p.h0 ? p.h0 + cidx : nullptr);
+    // every operand of the cell update is fetched BEFORE waiting for the accumulator, so the loads
+    // overlap the TMA/MMA ring instead of extending the step by an L2 round trip per chunk
+    float xg[G][SUH], pv[SUH];
+#pragma unroll
+    for (int c = 0; c < SUH; c += 8) {
+      float tmp[8];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (active) {
+          ld8(gt + g * H + c, tmp);
+        } else {
+#pragma unroll
+          for (int x = 0; x < 8; ++x) tmp[x] = 0.f;
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) xg[g][c + x] = tmp[x];
+      }
+      if (active && prev) {
+        ld8(prev + c, tmp);
+      } else {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) tmp[x] = 0.f;
+      }
+#pragma unroll
+      for (int x = 0; x < 8; ++x) pv[c + x] = tmp[x];
+    }
     if (nk > 0) {
       mbar_wait(r.acc_full, 0);
       tc_fence_after();
     }
     const bool fin = active && p.h_final && (d == 0 ? t == len - 1 : t == 0);
-#pragma unroll 1
-    for (int c = 0; c < SU; c += 8) {
+#pragma unroll
+    for (int c = 0; c < SUH; c += 8) {
       float acc[G][8];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         if (nk > 0) {
-          tmem_ld8(r.tmem + ((uint32_t)(q * 32) << 16) + g * SU + c, acc[g]);
+          tmem_ld8(r.tmem + ((uint32_t)(q * 32) << 16) + g * SU + uh + c, acc[g]);
         } else {
 #pragma unroll
           for (int x = 0; x < 8; ++x) acc[g][x] = 0.f;
@@ -181,41 +223,32 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid
         st8(st + c, hv);
         continue;
       }
-      float xg[G][8], bv[G][8], pv[8];
+      float bv[G][8], go_[G][8];
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        ld8(gt + g * H + c, xg[g]);
-        ld8(bh + g * H + c, bv[g]);
-      }
-      if (prev) {
-        ld8(prev + c, pv);
-      } else {
-#pragma unroll
-        for (int x = 0; x < 8; ++x) pv[x] = 0.f;
-      }
+      for (int g = 0; g < G; ++g) ld8(bh + g * H + c, bv[g]);
 #pragma unroll
       for (int x = 0; x < 8; ++x) {
         if (G == 4) {
-          const float gi = sigmoid_fast(xg[0][x] + acc[0][x] + bv[0][x]);
-          const float gf = sigmoid_fast(xg[1][x] + acc[1][x] + bv[1][x]);
-          const float gg = tanh_fast(xg[2][x] + acc[2][x] + bv[2][x]);
-          const float go = sigmoid_fast(xg[G - 1][x] + acc[G - 1][x] + bv[G - 1][x]);
-          const float cc = gf * pv[x] + gi * gg;
+          const float gi = sigmoid_fast(xg[0][c + x] + acc[0][x] + bv[0][x]);
+          const float gf = sigmoid_fast(xg[1][c + x] + acc[1][x] + bv[1][x]);
+          const float gg = tanh_fast(xg[2][c + x] + acc[2][x] + bv[2][x]);
+          const float go = sigmoid_fast(xg[G - 1][c + x] + acc[G - 1][x] + bv[G - 1][x]);
+          const float cc = gf * pv[c + x] + gi * gg;
           hv[x] = go * tanh_fast(cc);
           sv[x] = cc;
-          xg[0][x] = gi; xg[1][x] = gf; xg[2][x] = gg; xg[G - 1][x] = go;
+          go_[0][x] = gi; go_[1][x] = gf; go_[2][x] = gg; go_[G - 1][x] = go;
         } else {
           const float hn = acc[2][x] + bv[2][x];
-          const float gr = sigmoid_fast(xg[0][x] + acc[0][x] + bv[0][x]);
-          const float gz = sigmoid_fast(xg[1][x] + acc[1][x] + bv[1][x]);
-          const float gn = tanh_fast(xg[2][x] + gr * hn);
-          hv[x] = (1.f - gz) * gn + gz * pv[x];
+          const float gr = sigmoid_fast(xg[0][c + x] + acc[0][x] + bv[0][x]);
+          const float gz = sigmoid_fast(xg[1][c + x] + acc[1][x] + bv[1][x]);
+          const float gn = tanh_fast(xg[2][c + x] + gr * hn);
+          hv[x] = (1.f - gz) * gn + gz * pv[c + x];
           sv[x] = hn;
-          xg[0][x] = gr; xg[1][x] = gz; xg[2][x] = gn;
+          go_[0][x] = gr; go_[1][x] = gz; go_[2][x] = gn;
         }
       }
 #pragma unroll
-      for (int g = 0; g < G; ++g) st8(gt + g * H + c, xg[g]);
+      for (int g = 0; g < G; ++g) st8(gt + g * H + c, go_[g]);
       st8(st + c, sv);
       st8(o + c, hv);
       if (fin) st8(p.h_final + cidx + c, hv);
@@ -236,17 +269,15 @@ struct TcBwd {
   float *dh0, *dc0, *carry;
 };
 
-constexpr int B_STAGES = 8;
-
 // grid (H/32, ceil(B/128), ndir), block 192.  mapG: gates as [T][B][ndir*G*H]; mapS: stash as
 // [T][B][ndir*H] (GRU: the d(W_hn h) part of the reduction range lives there); mapW: w_hh as
 // [ndir][G*H (j)][H (k)] read MN-major, box {32 k, 32 j}.
-template <int G>
+template <int G, int B_STAGES, int AROWS>
 __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapG,
                                                                     const __grid_constant__ CUtensorMap mapS,
                                                                     const __grid_constant__ CUtensorMap mapW, TcBwd p) {
   extern __shared__ uint8_t smem_dyn[];
-  constexpr int B_STAGE = SU * SK * 4;   // one {32 k, 32 j} box
+  constexpr int SA_STAGE = AROWS * SK * 4, B_STAGE = SU * SK * 4;   // B: one {32 k, 32 j} box
   const int warp = warp_uniform(), lane = threadIdx.x & 31;
   const int H = p.H, B = p.B, T = p.T, GH = G * p.H;
   const int d = blockIdx.z, u0 = blockIdx.x * SU, b0 = blockIdx.y * SB;
@@ -254,16 +285,27 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
   const int tn = d == 0 ? t + 1 : t - 1;   // the step processed just before this one
   const bool has_next = tn >= 0 && tn < T;
   const int nk = has_next ? GH / SK : 0;
-  Ring r = ring_setup<B_STAGES, B_STAGE, 32>(smem_dyn, warp, &mapG, &mapS, &mapW);
+  Ring r = ring_setup<B_STAGES, SA_STAGE, B_STAGE, 32>(smem_dyn, warp, &mapG, &mapS, &mapW);
 
+  pdl_launch_dependents();
   if (warp == 0) {
     if (elect_one()) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % B_STAGES, j0 = i * SK;
-        if (i >= B_STAGES) mbar_wait(&r.empty[s], (uint32_t)(i / B_STAGES - 1) & 1u);
-        mbar_expect_tx(&r.full[s], SA_STAGE + B_STAGE);
+      auto load_a = [&](int s, int j0) {
         if (G == 4 || j0 < 2 * H) tma_load_3d(r.sA + s * SA_STAGE, &mapG, &r.full[s], d * GH + j0, b0, tn);
         else tma_load_3d(r.sA + s * SA_STAGE, &mapS, &r.full[s], d * H + (j0 - 2 * H), b0, tn);
+      };
+      const int first = nk < B_STAGES ? nk : B_STAGES;
+      for (int i = 0; i < first; ++i) {
+        mbar_expect_tx(&r.full[i], SA_STAGE + B_STAGE);
+        tma_load_3d(r.sB + i * B_STAGE, &mapW, &r.full[i], u0, i * SK, d);
+      }
+      pdl_wait();   // dG of the step processed just before must be complete in HBM
+      for (int i = 0; i < first; ++i) load_a(i, i * SK);
+      for (int i = first; i < nk; ++i) {
+        const int s = i % B_STAGES, j0 = i * SK;
+        mbar_wait(&r.empty[s], (uint32_t)(i / B_STAGES - 1) & 1u);
+        mbar_expect_tx(&r.full[s], SA_STAGE + B_STAGE);
+        load_a(s, j0);
         tma_load_3d(r.sB + s * B_STAGE, &mapW, &r.full[s], u0, j0, d);
       }
     }
@@ -285,114 +327,138 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
       __syncwarp();
     }
   } else {
-    const int q = warp & 3;
+    pdl_wait();
+    const int q = warp & 3, uh = ((warp - 2) >> 2) * SUH;
     const int b = b0 + q * 32 + lane;
     const bool valid = b < B;
     const int bb = valid ? b : 0;
     const int len = (valid && p.lengths) ? (int)p.lengths[b] : T;
-    const int64_t cidx = ((int64_t)d * B + bb) * H + u0;
+    const int64_t cidx = ((int64_t)d * B + bb) * H + u0 + uh;
+    const int tt = p.final_only ? 0 : t;
+    const int64_t row = ((int64_t)tt * B + bb) * p.ndir + d;
+    float* gt = p.gates + row * GH + u0 + uh;
+    float* st = p.stash + row * H + u0 + uh;
+    const int tp = d == 0 ? t - 1 : t + 1;   // forward-time predecessor
+    const bool has_prev = tp >= 0 && tp < T;
+    const bool inject = d == 0 ? t == len - 1 : t == 0;
+    const bool live = valid && !p.final_only && t < len;   // this thread has a cell backward to do
+    // operands of the cell backward, fetched before waiting for the accumulator
+    float gv[G][SUH], sv[SUH], pv[SUH], dh[SUH], cr[SUH];
+    {
+      const float* pp = nullptr;
+      if (live) {
+        if (G == 4) pp = has_prev ? p.stash + (((int64_t)tp * B + b) * p.ndir + d) * H + u0 + uh : (p.c0 ? p.c0 + cidx : nullptr);
+        else pp = has_prev ? p.out + ((int64_t)tp * B + b) * p.ndir * H + (int64_t)d * H + u0 + uh : (p.h0 ? p.h0 + cidx : nullptr);
+      }
+      const float* dop = (live && p.dout) ? p.dout + ((int64_t)t * B + b) * p.ndir * H + (int64_t)d * H + u0 + uh : nullptr;
+#pragma unroll
+      for (int c = 0; c < SUH; c += 8) {
+        float tmp[8];
+        auto fetch = [&](const float* src, float* dst) {
+          if (src) {
+            ld8(src + c, tmp);
+          } else {
+#pragma unroll
+            for (int x = 0; x < 8; ++x) tmp[x] = 0.f;
+          }
+#pragma unroll
+          for (int x = 0; x < 8; ++x) dst[c + x] = tmp[x];
+        };
+#pragma unroll
+        for (int g = 0; g < G; ++g) fetch(live ? gt + g * H : nullptr, gv[g]);
+        fetch(live ? st : nullptr, sv);
+        fetch(pp, pv);
+        fetch(dop, dh);
+        fetch(valid ? p.carry + cidx : nullptr, cr);
+        if (live && inject) {   // final-state gradients enter here instead of the recurrent ones
+          float fin[8];
+          if (p.dh_final) {
+            ld8(p.dh_final + cidx + c, fin);
+#pragma unroll
+            for (int x = 0; x < 8; ++x) dh[c + x] += fin[x];
+          }
+          if (G == 4) {
+            if (p.dc_final) {
+              ld8(p.dc_final + cidx + c, fin);
+            } else {
+#pragma unroll
+              for (int x = 0; x < 8; ++x) fin[x] = 0.f;
+            }
+#pragma unroll
+            for (int x = 0; x < 8; ++x) cr[c + x] = fin[x];   // dc_in of the injection step
+          } else {
+#pragma unroll
+            for (int x = 0; x < 8; ++x) cr[c + x] = 0.f;
+          }
+        }
+      }
+    }
     if (nk > 0) {
       mbar_wait(r.acc_full, 0);
       tc_fence_after();
     }
-    const int tt = p.final_only ? 0 : t;
-    const int64_t row = ((int64_t)tt * B + bb) * p.ndir + d;
-    float* gt = p.gates + row * GH + u0;
-    float* st = p.stash + row * H + u0;
-    const int tp = d == 0 ? t - 1 : t + 1;   // forward-time predecessor
-    const bool has_prev = tp >= 0 && tp < T;
-    const bool inject = d == 0 ? t == len - 1 : t == 0;
-#pragma unroll 1
-    for (int c = 0; c < SU; c += 8) {
+#pragma unroll
+    for (int c = 0; c < SUH; c += 8) {
       float m[8];
       if (nk > 0) {
-        tmem_ld8(r.tmem + ((uint32_t)(q * 32) << 16) + c, m);
+        tmem_ld8(r.tmem + ((uint32_t)(q * 32) << 16) + uh + c, m);
       } else {
 #pragma unroll
         for (int x = 0; x < 8; ++x) m[x] = 0.f;
       }
       if (!valid) continue;
-      float cr[8];
-      ld8(p.carry + cidx + c, cr);
       if (p.final_only) {
+        float o8[8];
         if (G == 4) {
           if (p.dh0) st8(p.dh0 + cidx + c, m);
-          if (p.dc0) st8(p.dc0 + cidx + c, cr);
+#pragma unroll
+          for (int x = 0; x < 8; ++x) o8[x] = cr[c + x];
+          if (p.dc0) st8(p.dc0 + cidx + c, o8);
         } else if (p.dh0) {
 #pragma unroll
-          for (int x = 0; x < 8; ++x) m[x] += cr[x];
-          st8(p.dh0 + cidx + c, m);
+          for (int x = 0; x < 8; ++x) o8[x] = m[x] + cr[c + x];
+          st8(p.dh0 + cidx + c, o8);
         }
         continue;
       }
-      float z[8];
+      float og[G][8], dst[8], oc[8];
+      if (!live) {   // t >= len: zero gradients for the hoisted dW / dx GEMMs, carry untouched
 #pragma unroll
-      for (int x = 0; x < 8; ++x) z[x] = 0.f;
-      if (t >= len) {
+        for (int x = 0; x < 8; ++x) dst[x] = 0.f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) st8(gt + g * H + c, z);
-        if (G == 3) st8(st + c, z);
+        for (int g = 0; g < G; ++g) st8(gt + g * H + c, dst);
+        if (G == 3) st8(st + c, dst);
         continue;
       }
-      float dh[8], gv[G][8], sv[8], pv[8], fin[8], fc[8];
-      if (p.dout) ld8(p.dout + ((int64_t)t * B + b) * p.ndir * H + (int64_t)d * H + u0 + c, dh);
-      else {
-#pragma unroll
-        for (int x = 0; x < 8; ++x) dh[x] = 0.f;
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g) ld8(gt + g * H + c, gv[g]);
-      ld8(st + c, sv);
-      {
-        const float* pp;
-        if (G == 4) pp = has_prev ? p.stash + (((int64_t)tp * B + b) * p.ndir + d) * H + u0 + c : (p.c0 ? p.c0 + cidx + c : nullptr);
-        else pp = has_prev ? p.out + ((int64_t)tp * B + b) * p.ndir * H + (int64_t)d * H + u0 + c : (p.h0 ? p.h0 + cidx + c : nullptr);
-        if (pp) ld8(pp, pv);
-        else {
-#pragma unroll
-          for (int x = 0; x < 8; ++x) pv[x] = 0.f;
-        }
-      }
-      if (inject && p.dh_final) ld8(p.dh_final + cidx + c, fin);
-      else {
-#pragma unroll
-        for (int x = 0; x < 8; ++x) fin[x] = 0.f;
-      }
-      if (G == 4 && inject && p.dc_final) ld8(p.dc_final + cidx + c, fc);
-      else {
-#pragma unroll
-        for (int x = 0; x < 8; ++x) fc[x] = 0.f;
-      }
-      float dst[8];
 #pragma unroll
       for (int x = 0; x < 8; ++x) {
+        const int i = c + x;
         if (G == 4) {
-          const float dhx = dh[x] + (inject ? fin[x] : m[x]);
-          const float dc_in = inject ? fc[x] : cr[x];
-          const float gi = gv[0][x], gf = gv[1][x], gg = gv[2][x], go = gv[G - 1][x];
-          const float tc = tanh_fast(sv[x]);
-          const float dc = dhx * go * (1.f - tc * tc) + dc_in;
-          gv[0][x] = dc * gg * gi * (1.f - gi);
-          gv[1][x] = dc * pv[x] * gf * (1.f - gf);
-          gv[2][x] = dc * gi * (1.f - gg * gg);
-          gv[G - 1][x] = dhx * tc * go * (1.f - go);
-          cr[x] = dc * gf;
+          const float dhx = dh[i] + (inject ? 0.f : m[x]);
+          const float gi = gv[0][i], gf = gv[1][i], gg = gv[2][i], go = gv[G - 1][i];
+          const float tc = tanh_fast(sv[i]);
+          const float dc = dhx * go * (1.f - tc * tc) + cr[i];
+          og[0][x] = dc * gg * gi * (1.f - gi);
+          og[1][x] = dc * pv[i] * gf * (1.f - gf);
+          og[2][x] = dc * gi * (1.f - gg * gg);
+          og[G - 1][x] = dhx * tc * go * (1.f - go);
+          oc[x] = dc * gf;
           dst[x] = 0.f;
         } else {
-          const float dhx = dh[x] + (inject ? fin[x] : m[x] + cr[x]);
-          const float gr = gv[0][x], gz = gv[1][x], gn = gv[2][x], hn = sv[x];
+          const float dhx = dh[i] + (inject ? 0.f : m[x] + cr[i]);
+          const float gr = gv[0][i], gz = gv[1][i], gn = gv[2][i], hn = sv[i];
           const float da_n = dhx * (1.f - gz) * (1.f - gn * gn);
-          gv[0][x] = da_n * hn * gr * (1.f - gr);
-          gv[1][x] = dhx * (pv[x] - gn) * gz * (1.f - gz);
-          gv[2][x] = da_n;
+          og[0][x] = da_n * hn * gr * (1.f - gr);
+          og[1][x] = dhx * (pv[i] - gn) * gz * (1.f - gz);
+          og[2][x] = da_n;
           dst[x] = da_n * gr;
-          cr[x] = dhx * gz;
+          oc[x] = dhx * gz;
         }
       }
 #pragma unroll
-      for (int g = 0; g < G; ++g) st8(gt + g * H + c, gv[g]);
+      for (int g = 0; g < G; ++g) st8(gt + g * H + c, og[g]);
       if (G == 3) st8(st + c, dst);
-      st8(p.carry + cidx + c, cr);
+      st8(p.carry + cidx + c, oc);
     }
   }
   tc_fence_before();
@@ -413,28 +479,29 @@ int rnn_layer_fwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
   if (!step_tc_supported(B, H, gates, out, w_hh) || (((uintptr_t)stash | (uintptr_t)b_hh) & 15)) return -1;
   if ((h0 && ((uintptr_t)h0 & 15)) || (c0 && ((uintptr_t)c0 & 15)) || (h_final && ((uintptr_t)h_final & 15))) return -1;
   CUtensorMap mapH, mapH0, mapW;
-  if (!tensor_map3(out, (uint64_t)ndir * H, B, T, (uint64_t)ndir * H, (uint64_t)B * ndir * H, SB, false, &mapH)) return -1;
+  const bool small = B <= 64;            // the A box loads 64 rows, twice the ring depth
+  const uint32_t arows = small ? 64 : SB;
+  if (!tensor_map3(out, (uint64_t)ndir * H, B, T, (uint64_t)ndir * H, (uint64_t)B * ndir * H, arows, false, &mapH)) return -1;
   if (h0) {
-    if (!tensor_map3(h0, H, B, ndir, H, (uint64_t)B * H, SB, false, &mapH0)) return -1;
+    if (!tensor_map3(h0, H, B, ndir, H, (uint64_t)B * H, arows, false, &mapH0)) return -1;
   } else {
     mapH0 = mapH;
   }
   if (!tensor_map3(w_hh, H, (uint64_t)G * H, ndir, H, (uint64_t)G * H * H, SU, false, &mapW)) return -1;
   TcFwd p{T, B, H, ndir, 0, gates, b_hh, lengths, h0, c0, out, stash, h_final};
   dim3 grid(H / SU, ceil_div(B, SB), ndir);
-  const size_t sm = F_STAGES * (SA_STAGE + G * SU * SK * 4) + (2 * F_STAGES + 1) * 8 + 16 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(rnn_step_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(F_STAGES * (SA_STAGE + 4 * SU * SK * 4) + 2048));
-    cudaFuncSetAttribute(rnn_step_fwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(F_STAGES * (SA_STAGE + 4 * SU * SK * 4) + 2048));
-    attr = true;
-  }
-  for (int step = 0; step < T; ++step) {
-    p.step = step;
-    if (G == 4) rnn_step_fwd_tc_kernel<4><<<grid, S_THREADS, sm, s>>>(mapH, mapH0, mapW, p);
-    else rnn_step_fwd_tc_kernel<3><<<grid, S_THREADS, sm, s>>>(mapH, mapH0, mapW, p);
+  auto run = [&](auto kernel, int stages, int arows) {
+    const size_t sm = (size_t)stages * (arows * SK * 4 + G * SU * SK * 4) + (2 * stages + 1) * 8 + 16 + 1024;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    for (int step = 0; step < T; ++step) {
+      p.step = step;
+      launch_pdl(kernel, grid, dim3(S_THREADS), sm, s, mapH, mapH0, mapW, p);
+    }
+  };
+  if (small) {
+    if (G == 4) run(rnn_step_fwd_tc_kernel<4, 8, 64>, 8, 64); else run(rnn_step_fwd_tc_kernel<3, 8, 64>, 8, 64);
+  } else {
+    if (G == 4) run(rnn_step_fwd_tc_kernel<4, 4, 128>, 4, 128); else run(rnn_step_fwd_tc_kernel<3, 4, 128>, 4, 128);
   }
   note_launches(T);
   cudaError_t e = cudaGetLastError();
@@ -452,33 +519,33 @@ int rnn_layer_bwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
   for (const void* q : opt)
     if (q && ((uintptr_t)q & 15)) return -1;
   CUtensorMap mapG, mapS, mapW;
-  if (!tensor_map3(gates, (uint64_t)ndir * G * H, B, T, (uint64_t)ndir * G * H, (uint64_t)B * ndir * G * H, SB, false, &mapG)) return -1;
-  if (!tensor_map3(stash, (uint64_t)ndir * H, B, T, (uint64_t)ndir * H, (uint64_t)B * ndir * H, SB, false, &mapS)) return -1;
+  const bool small = B <= 64;
+  const uint32_t arows = small ? 64 : SB;
+  if (!tensor_map3(gates, (uint64_t)ndir * G * H, B, T, (uint64_t)ndir * G * H, (uint64_t)B * ndir * G * H, arows, false, &mapG)) return -1;
+  if (!tensor_map3(stash, (uint64_t)ndir * H, B, T, (uint64_t)ndir * H, (uint64_t)B * ndir * H, arows, false, &mapS)) return -1;
   if (!tensor_map3(w_hh, H, (uint64_t)G * H, ndir, H, (uint64_t)G * H * H, SK, true, &mapW)) return -1;
   TcBwd p{T, B, H, ndir, 0, 0, gates, stash, out, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0, carry};
   dim3 grid(H / SU, ceil_div(B, SB), ndir);
-  const size_t sm = B_STAGES * (SA_STAGE + SU * SK * 4) + (2 * B_STAGES + 1) * 8 + 16 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(rnn_step_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaFuncSetAttribute(rnn_step_bwd_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    attr = true;
-  }
-  // the carry buffer starts at zero (the fp32 step kernels only read it after writing it)
-  cudaMemsetAsync(carry, 0, sizeof(float) * (size_t)ndir * B * H, s);
-  auto go = [&]() {
-    if (G == 4) rnn_step_bwd_tc_kernel<4><<<grid, S_THREADS, sm, s>>>(mapG, mapS, mapW, p);
-    else rnn_step_bwd_tc_kernel<3><<<grid, S_THREADS, sm, s>>>(mapG, mapS, mapW, p);
-  };
-  for (int step = 0; step < T; ++step) {
-    p.step = step;
-    go();
-  }
+  // `carry` needs no initialisation: a sequence's entry is written at its injection step (t = len-1
+  // or 0) before any step consumes it
   int n = T;
-  if (dh0 || dc0) {
-    p.final_only = 1;
-    go();
-    ++n;
+  auto run = [&](auto kernel, int stages, int arows) {
+    const size_t sm = (size_t)stages * (arows * SK * 4 + SU * SK * 4) + (2 * stages + 1) * 8 + 16 + 1024;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    for (int step = 0; step < T; ++step) {
+      p.step = step;
+      launch_pdl(kernel, grid, dim3(S_THREADS), sm, s, mapG, mapS, mapW, p);
+    }
+    if (dh0 || dc0) {
+      p.final_only = 1;
+      launch_pdl(kernel, grid, dim3(S_THREADS), sm, s, mapG, mapS, mapW, p);
+      ++n;
+    }
+  };
+  if (small) {
+    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 16, 64>, 16, 64); else run(rnn_step_bwd_tc_kernel<3, 16, 64>, 16, 64);
+  } else {
+    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 8, 128>, 8, 128); else run(rnn_step_bwd_tc_kernel<3, 8, 128>, 8, 128);
   }
   note_launches(n);
   cudaError_t e = cudaGetLastError();
