@@ -157,13 +157,14 @@ int slnlp_attn_step_bwd(const float* dctx, const float* q, const float* pk, cons
  * applied on the log-probs (config/*.yaml:36, helper.py:67-70).
  * logits [B,V] -> logp [B,V]. */
 int slnlp_log_softmax_fwd(const float* logits, float* logp, int B, int V, slnlp_stream_t stream);
-/* dlogits = dlogp - exp(logp) * rowsum(dlogp) */
+/* dlogits = dlogp - exp(logp) * rowsum(dlogp).  dlogits rows are ld_dlogits floats apart (>= V; a
+ * multiple of 4 keeps the generator's dW / dx GEMMs on the TMA path when V_tgt is not one). */
 int slnlp_log_softmax_bwd(const float* dlogp, const float* logp, float* dlogits, int B, int V,
-                          slnlp_stream_t stream);
+                          int ld_dlogits, slnlp_stream_t stream);
 /* loss_out[0] = mean over y != ignore of -log_softmax(logp)[y]; loss_out[1] = count.
  * dlogits (may be NULL) = d loss / d logits through both log-softmaxes. */
 int slnlp_ce_on_logp(const float* logp, const int64_t* y, int64_t ignore_index, int B, int V,
-                     float* loss_out, float* dlogits, float* row_ws, slnlp_stream_t stream);
+                     float* loss_out, float* dlogits, int ld_dlogits, float* row_ws, slnlp_stream_t stream);
 
 /* ---- K11/K12: GradientNormClipping -> clip_grad_norm_(max_norm, 2) (helper.py:227-229)
  * and torch.optim.SGD(momentum, nesterov=False) (config/*.yaml:39-42), over flat buffers.

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
                                                        const int64_t* __restrict__ X, int64_t pad_idx,
                                                        int T, int B, int H, int W,
                                                        float* __restrict__ alpha, float* __restrict__ ctx) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float sc[];
   __shared__ float red[33];
   const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -62,6 +64,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
                                                        int H, int W, float* __restrict__ dval,
                                                        float* __restrict__ dpk, float* __restrict__ dq,
                                                        float* __restrict__ dv_part) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float ds[];
   __shared__ float red[33];
   const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -114,7 +118,7 @@ extern "C" int slnlp_attn_step_fwd(const float* q, const float* pk, const float*
                                    float* alpha, float* ctx, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(q && pk && v && val && X && alpha && ctx, "attn_step_fwd: null pointer");
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && W > 0 && T <= 12000, "attn_step_fwd: bad shape");
-  attn_fwd_kernel<<<B, 256, T * sizeof(float), as_stream(stream)>>>(q, pk, v, val, X, pad_idx, T, B, H, W, alpha, ctx);
+  launch_pdl(attn_fwd_kernel, dim3(B), dim3(256), T * sizeof(float), as_stream(stream), q, pk, v, val, X, pad_idx, T, B, H, W, alpha, ctx);
   SLNLP_LAUNCH_OK("attn_step_fwd");
   return 0;
 }
@@ -125,7 +129,7 @@ extern "C" int slnlp_attn_step_bwd(const float* dctx, const float* q, const floa
                                    slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(dctx && q && pk && v && val && alpha && dval && dpk && dq && dv_part, "attn_step_bwd: null pointer");
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && W > 0 && T <= 12000, "attn_step_bwd: bad shape");
-  attn_bwd_kernel<<<B, 256, T * sizeof(float), as_stream(stream)>>>(dctx, q, pk, v, val, alpha, T, B, H, W, dval, dpk, dq, dv_part);
+  launch_pdl(attn_bwd_kernel, dim3(B), dim3(256), T * sizeof(float), as_stream(stream), dctx, q, pk, v, val, alpha, T, B, H, W, dval, dpk, dq, dv_part);
   SLNLP_LAUNCH_OK("attn_step_bwd");
   return 0;
 }

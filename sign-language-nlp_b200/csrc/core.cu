@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
                                                         float* __restrict__ out, int B, int T,
                                                         FieldSpec fs, int time_major, float scale,
                                                         const float* __restrict__ pe) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (int64_t)B * T) return;
@@ -100,6 +102,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(float* __restrict__ dtab
                                                         const float* __restrict__ dout, int B, int T,
                                                         FieldSpec fs, int time_major, float scale,
                                                         int64_t padding_idx) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (int64_t)B * T) return;
@@ -132,6 +136,8 @@ static int make_fields(FieldSpec& fs, int F, const int64_t* off, const int* w, c
 // ------------------------------------------------------------------ log-softmax / CE
 __global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* __restrict__ x,
                                                               float* __restrict__ y, int V) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[33];
   const float* xr = x + (int64_t)blockIdx.x * V;
   float* yr = y + (int64_t)blockIdx.x * V;
@@ -147,13 +153,15 @@ __global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* __res
 
 __global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __restrict__ dy,
                                                               const float* __restrict__ y,
-                                                              float* __restrict__ dx, int V) {
+                                                              float* __restrict__ dx, int V, int ld) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[33];
-  const int64_t o = (int64_t)blockIdx.x * V;
+  const int64_t o = (int64_t)blockIdx.x * V, od = (int64_t)blockIdx.x * ld;
   float s = 0.f;
   for (int v = threadIdx.x; v < V; v += blockDim.x) s += dy[o + v];
   s = block_sum(s, red);
-  for (int v = threadIdx.x; v < V; v += blockDim.x) dx[o + v] = dy[o + v] - expf(y[o + v]) * s;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) dx[od + v] = dy[o + v] - expf(y[o + v]) * s;
 }
 
 // row_ws: [0,B) row loss, [B,2B) valid flag, [2B,3B) second logsumexp
@@ -161,6 +169,8 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
                                                       const int64_t* __restrict__ y,
                                                       int64_t ignore, int B, int V,
                                                       float* __restrict__ row_ws) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[33];
   const int b = blockIdx.x;
   const float* r = logp + (int64_t)b * V;
@@ -181,6 +191,8 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
 }
 __global__ void __launch_bounds__(256) ce_reduce_kernel(const float* __restrict__ row_ws, int B,
                                                         float* __restrict__ loss_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[33];
   float s = 0.f, c = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -198,7 +210,9 @@ __global__ void __launch_bounds__(256) ce_grad_kernel(const float* __restrict__ 
                                                       const int64_t* __restrict__ y, int B, int V,
                                                       const float* __restrict__ row_ws,
                                                       const float* __restrict__ loss_out,
-                                                      float* __restrict__ dlogits) {
+                                                      float* __restrict__ dlogits, int ld) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x;
   const float valid = row_ws[B + b], lse = row_ws[2 * B + b];
   const float inv = valid / loss_out[1];
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(256) ce_grad_kernel(const float* __restrict__ 
     // d/dlogp = softmax(logp) - onehot; through log_softmax(logits) the rowsum term is
     // (1 - 1) = 0, so the same expression is d/dlogits.
     float g = expf(logp[o + v] - lse) - (v == yb ? 1.f : 0.f);
-    dlogits[o + v] = valid != 0.f ? g * inv : 0.f;
+    dlogits[(int64_t)b * ld + v] = valid != 0.f ? g * inv : 0.f;
   }
 }
 
@@ -216,6 +230,8 @@ __global__ void __launch_bounds__(256) ce_grad_kernel(const float* __restrict__ 
 constexpr int kSumsqBlocks = 1024;
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, int64_t n,
                                                             float* __restrict__ partials) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[33];
   float s = 0.f;
   const int64_t n4 = n >> 2;
@@ -232,6 +248,8 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 }
 __global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partials, int np,
                                                           float* __restrict__ norm_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ double redd[256];
   double s = 0.0;
   for (int i = threadIdx.x; i < np; i += blockDim.x) s += (double)partials[i];
@@ -248,6 +266,8 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
                                                   float* __restrict__ buf, int64_t n,
                                                   const float* __restrict__ hyper,
                                                   const float* __restrict__ norm, float grad_scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const float lr = hyper[0], mom = hyper[1], max_norm = hyper[2];
   const bool first = hyper[3] != 0.f;
   float coef = grad_scale;
@@ -281,6 +301,8 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x,
                                                       float* __restrict__ y, int64_t n, float p,
                                                       const uint64_t* __restrict__ rng, uint32_t site) {
+  pdl_wait();
+  pdl_launch_dependents();
   const uint64_t seed = rng[0], step = rng[1];
   const float keep = 1.f - p, inv = 1.f / (1.f - p);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n;
@@ -298,12 +320,16 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ 
     }
   }
 }
-__global__ void rng_advance_kernel(uint64_t* rng) { rng[1] += 1; }
+__global__ void rng_advance_kernel(uint64_t* rng) {
+  pdl_wait();
+  pdl_launch_dependents(); rng[1] += 1; }
 
 // ------------------------------------------------------------------ small glue
 __global__ void __launch_bounds__(256) pad_fill_kernel(float* __restrict__ x,
                                                        const int64_t* __restrict__ lengths, int T,
                                                        int B, int W, float value) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x;  // t*B + b
   const int t = row / B, b = row % B;
   if (t < lengths[b]) return;
@@ -313,6 +339,8 @@ __global__ void __launch_bounds__(256) pad_fill_kernel(float* __restrict__ x,
 __global__ void __launch_bounds__(256) concat_dirs_kernel(const float* __restrict__ src,
                                                           float* __restrict__ dst, int B, int H,
                                                           int ndir, int inverse) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t n = (int64_t)ndir * B * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -324,26 +352,36 @@ __global__ void __launch_bounds__(256) concat_dirs_kernel(const float* __restric
   }
 }
 __global__ void __launch_bounds__(256) tanh_fwd_kernel(float* x, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     x[i] = tanhf(x[i]);
 }
 __global__ void __launch_bounds__(256) tanh_bwd_kernel(float* dy, const float* __restrict__ y, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     dy[i] *= 1.f - y[i] * y[i];
 }
 __global__ void __launch_bounds__(256) relu_fwd_kernel(float* x, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     x[i] = fmaxf(x[i], 0.f);
 }
 __global__ void __launch_bounds__(256) relu_bwd_kernel(float* dy, const float* __restrict__ y, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     dy[i] = y[i] > 0.f ? dy[i] : 0.f;
 }
 __global__ void __launch_bounds__(256) axpy_kernel(float* y, const float* __restrict__ x, float a, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     y[i] += a * x[i];
@@ -351,6 +389,8 @@ __global__ void __launch_bounds__(256) axpy_kernel(float* y, const float* __rest
 __global__ void __launch_bounds__(256) dec_input_fwd_kernel(const float* __restrict__ row,
                                                             const float* __restrict__ src,
                                                             float* __restrict__ dst, int B, int E, int W) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x;
   for (int e = threadIdx.x; e < E + W; e += blockDim.x)
     dst[(int64_t)b * (E + W) + e] = e < E ? row[e] : src[(int64_t)b * W + e - E];
@@ -359,6 +399,8 @@ __global__ void __launch_bounds__(256) dec_input_fwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) dec_input_bwd_kernel(const float* __restrict__ ddst,
                                                             float* __restrict__ drow,
                                                             float* __restrict__ dsrc, int B, int E, int W) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E + W) return;
   if (e < E) {
@@ -373,6 +415,8 @@ __global__ void __launch_bounds__(256) dec_input_bwd_kernel(const float* __restr
 // combination order (deterministic)
 __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ A, int rows, int cols,
                                                       int lda, float* __restrict__ out, float beta) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float sm[32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -430,9 +474,9 @@ int slnlp_embed_gather_fwd(const float* table, const int64_t* idx, float* out, i
   for (int f = 0; f < F; ++f) vec = vec && fs.w[f] % 4 == 0 && fs.off[f] % 4 == 0;
   const int grid = ceil_div((int64_t)B * T, 8);
   if (vec)
-    embed_fwd_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(table, idx, out, B, T, fs, time_major, scale, pe);
+    launch_pdl(embed_fwd_kernel<true>, dim3(grid), dim3(256), 0, as_stream(stream), table, idx, out, B, T, fs, time_major, scale, pe);
   else
-    embed_fwd_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(table, idx, out, B, T, fs, time_major, scale, pe);
+    launch_pdl(embed_fwd_kernel<false>, dim3(grid), dim3(256), 0, as_stream(stream), table, idx, out, B, T, fs, time_major, scale, pe);
   SLNLP_LAUNCH_OK("embed_gather_fwd");
   return 0;
 }
@@ -443,7 +487,7 @@ int slnlp_embed_gather_bwd(float* dtable, const int64_t* idx, const float* dout,
   SLNLP_CHECK_ARG(dtable && idx && dout && B > 0 && T > 0, "embed_gather_bwd: bad arguments");
   FieldSpec fs;
   if (make_fields(fs, F, field_off, field_w, field_rows)) return 1;
-  embed_bwd_kernel<<<ceil_div((int64_t)B * T, 8), 256, 0, as_stream(stream)>>>(
+  launch_pdl(embed_bwd_kernel, dim3(ceil_div((int64_t)B * T, 8)), dim3(256), 0, as_stream(stream), 
       dtable, idx, dout, B, T, fs, time_major, scale, padding_idx);
   SLNLP_LAUNCH_OK("embed_gather_bwd");
   return 0;
@@ -452,7 +496,7 @@ int slnlp_embed_gather_bwd(float* dtable, const int64_t* idx, const float* dout,
 int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
                      slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(A && out && rows >= 0 && cols > 0 && lda >= cols, "colsum: bad arguments");
-  colsum_kernel<<<ceil_div(cols, 32), 1024, 0, as_stream(stream)>>>(A, rows, cols, lda, out, beta);
+  launch_pdl(colsum_kernel, dim3(ceil_div(cols, 32)), dim3(1024), 0, as_stream(stream), A, rows, cols, lda, out, beta);
   SLNLP_LAUNCH_OK("colsum");
   return 0;
 }
@@ -460,7 +504,7 @@ int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, fl
 int slnlp_pad_fill(float* x, const int64_t* lengths, int T, int B, int W, float value,
                    slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(x && lengths && T > 0 && B > 0 && W > 0, "pad_fill: bad arguments");
-  pad_fill_kernel<<<T * B, 128, 0, as_stream(stream)>>>(x, lengths, T, B, W, value);
+  launch_pdl(pad_fill_kernel, dim3(T * B), dim3(128), 0, as_stream(stream), x, lengths, T, B, W, value);
   SLNLP_LAUNCH_OK("pad_fill");
   return 0;
 }
@@ -468,7 +512,7 @@ int slnlp_pad_fill(float* x, const int64_t* lengths, int T, int B, int W, float 
 int slnlp_concat_dirs(const float* src, float* dst, int B, int H, int ndir, int inverse,
                       slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(src && dst && B > 0 && H > 0 && ndir > 0, "concat_dirs: bad arguments");
-  concat_dirs_kernel<<<ew_grid((int64_t)ndir * B * H), 256, 0, as_stream(stream)>>>(src, dst, B, H, ndir, inverse);
+  launch_pdl(concat_dirs_kernel, dim3(ew_grid((int64_t)ndir * B * H)), dim3(256), 0, as_stream(stream), src, dst, B, H, ndir, inverse);
   SLNLP_LAUNCH_OK("concat_dirs");
   return 0;
 }
@@ -476,35 +520,35 @@ int slnlp_concat_dirs(const float* src, float* dst, int B, int H, int ndir, int 
 int slnlp_tanh_fwd(float* x, int64_t n, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(x && n >= 0, "tanh_fwd: bad arguments");
   if (n == 0) return 0;
-  tanh_fwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, n);
+  launch_pdl(tanh_fwd_kernel, dim3(ew_grid(n)), dim3(256), 0, as_stream(stream), x, n);
   SLNLP_LAUNCH_OK("tanh_fwd");
   return 0;
 }
 int slnlp_tanh_bwd(float* dy, const float* y, int64_t n, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(dy && y && n >= 0, "tanh_bwd: bad arguments");
   if (n == 0) return 0;
-  tanh_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(dy, y, n);
+  launch_pdl(tanh_bwd_kernel, dim3(ew_grid(n)), dim3(256), 0, as_stream(stream), dy, y, n);
   SLNLP_LAUNCH_OK("tanh_bwd");
   return 0;
 }
 int slnlp_relu_fwd(float* x, int64_t n, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(x && n >= 0, "relu_fwd: bad arguments");
   if (n == 0) return 0;
-  relu_fwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, n);
+  launch_pdl(relu_fwd_kernel, dim3(ew_grid(n)), dim3(256), 0, as_stream(stream), x, n);
   SLNLP_LAUNCH_OK("relu_fwd");
   return 0;
 }
 int slnlp_relu_bwd(float* dy, const float* y, int64_t n, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(dy && y && n >= 0, "relu_bwd: bad arguments");
   if (n == 0) return 0;
-  relu_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(dy, y, n);
+  launch_pdl(relu_bwd_kernel, dim3(ew_grid(n)), dim3(256), 0, as_stream(stream), dy, y, n);
   SLNLP_LAUNCH_OK("relu_bwd");
   return 0;
 }
 int slnlp_axpy(float* y, const float* x, float a, int64_t n, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(y && x && n >= 0, "axpy: bad arguments");
   if (n == 0) return 0;
-  axpy_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(y, x, a, n);
+  launch_pdl(axpy_kernel, dim3(ew_grid(n)), dim3(256), 0, as_stream(stream), y, x, a, n);
   SLNLP_LAUNCH_OK("axpy");
   return 0;
 }
@@ -512,50 +556,52 @@ int slnlp_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* 
                   slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(x && y && rng && n >= 0 && p >= 0.f && p < 1.f, "dropout: bad arguments");
   if (n == 0) return 0;
-  dropout_kernel<<<ew_grid((n + 3) / 4), 256, 0, as_stream(stream)>>>(x, y, n, p, rng, site);
+  launch_pdl(dropout_kernel, dim3(ew_grid((n + 3) / 4)), dim3(256), 0, as_stream(stream), x, y, n, p, rng, site);
   SLNLP_LAUNCH_OK("dropout");
   return 0;
 }
 int slnlp_rng_advance(uint64_t* rng, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(rng, "rng_advance: null");
-  rng_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(rng);
+  launch_pdl(rng_advance_kernel, dim3(1), dim3(1), 0, as_stream(stream), rng);
   SLNLP_LAUNCH_OK("rng_advance");
   return 0;
 }
 int slnlp_dec_input_fwd(const float* row, const float* src, float* dst, int B, int E, int W,
                         slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(row && src && dst && B > 0 && E > 0 && W > 0, "dec_input_fwd: bad arguments");
-  dec_input_fwd_kernel<<<B, 256, 0, as_stream(stream)>>>(row, src, dst, B, E, W);
+  launch_pdl(dec_input_fwd_kernel, dim3(B), dim3(256), 0, as_stream(stream), row, src, dst, B, E, W);
   SLNLP_LAUNCH_OK("dec_input_fwd");
   return 0;
 }
 int slnlp_dec_input_bwd(const float* ddst, float* drow, float* dsrc, int B, int E, int W,
                         slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(ddst && drow && dsrc && B > 0 && E > 0 && W > 0, "dec_input_bwd: bad arguments");
-  dec_input_bwd_kernel<<<ceil_div(E + W, 256), 256, 0, as_stream(stream)>>>(ddst, drow, dsrc, B, E, W);
+  launch_pdl(dec_input_bwd_kernel, dim3(ceil_div(E + W, 256)), dim3(256), 0, as_stream(stream), ddst, drow, dsrc, B, E, W);
   SLNLP_LAUNCH_OK("dec_input_bwd");
   return 0;
 }
 
 int slnlp_log_softmax_fwd(const float* logits, float* logp, int B, int V, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(logits && logp && B > 0 && V > 0, "log_softmax_fwd: bad arguments");
-  log_softmax_fwd_kernel<<<B, 256, 0, as_stream(stream)>>>(logits, logp, V);
+  launch_pdl(log_softmax_fwd_kernel, dim3(B), dim3(256), 0, as_stream(stream), logits, logp, V);
   SLNLP_LAUNCH_OK("log_softmax_fwd");
   return 0;
 }
 int slnlp_log_softmax_bwd(const float* dlogp, const float* logp, float* dlogits, int B, int V,
-                          slnlp_stream_t stream) {
+                          int ld_dlogits, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(ld_dlogits >= V, "log_softmax_bwd: ld_dlogits < V");
   SLNLP_CHECK_ARG(dlogp && logp && dlogits && B > 0 && V > 0, "log_softmax_bwd: bad arguments");
-  log_softmax_bwd_kernel<<<B, 256, 0, as_stream(stream)>>>(dlogp, logp, dlogits, V);
+  launch_pdl(log_softmax_bwd_kernel, dim3(B), dim3(256), 0, as_stream(stream), dlogp, logp, dlogits, V, ld_dlogits);
   SLNLP_LAUNCH_OK("log_softmax_bwd");
   return 0;
 }
 int slnlp_ce_on_logp(const float* logp, const int64_t* y, int64_t ignore_index, int B, int V,
-                     float* loss_out, float* dlogits, float* row_ws, slnlp_stream_t stream) {
+                     float* loss_out, float* dlogits, int ld_dlogits, float* row_ws, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(!dlogits || ld_dlogits >= V, "ce_on_logp: ld_dlogits < V");
   SLNLP_CHECK_ARG(logp && y && loss_out && row_ws && B > 0 && V > 0, "ce_on_logp: bad arguments");
-  ce_rows_kernel<<<B, 256, 0, as_stream(stream)>>>(logp, y, ignore_index, B, V, row_ws);
-  ce_reduce_kernel<<<1, 256, 0, as_stream(stream)>>>(row_ws, B, loss_out);
-  if (dlogits) ce_grad_kernel<<<B, 256, 0, as_stream(stream)>>>(logp, y, B, V, row_ws, loss_out, dlogits);
+  launch_pdl(ce_rows_kernel, dim3(B), dim3(256), 0, as_stream(stream), logp, y, ignore_index, B, V, row_ws);
+  launch_pdl(ce_reduce_kernel, dim3(1), dim3(256), 0, as_stream(stream), row_ws, B, loss_out);
+  if (dlogits) launch_pdl(ce_grad_kernel, dim3(B), dim3(256), 0, as_stream(stream), logp, y, B, V, row_ws, loss_out, dlogits, ld_dlogits);
   note_launches(dlogits ? 2 : 1);
   SLNLP_LAUNCH_OK("ce_on_logp");
   return 0;
@@ -567,8 +613,8 @@ int slnlp_gradnorm(const float* g, int64_t n, float* partials, float* norm_out, 
   SLNLP_CHECK_ARG((uintptr_t)g % 16 == 0, "gradnorm: g must be 16-byte aligned");
   int64_t want = (n / 4 + 255) / 256;
   int grid = (int)(want < 1 ? 1 : (want > kSumsqBlocks ? kSumsqBlocks : want));
-  sumsq_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, n, partials);
-  sumsq_final_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, grid, norm_out);
+  launch_pdl(sumsq_partial_kernel, dim3(grid), dim3(256), 0, as_stream(stream), g, n, partials);
+  launch_pdl(sumsq_final_kernel, dim3(1), dim3(256), 0, as_stream(stream), partials, grid, norm_out);
   note_launches(1);
   SLNLP_LAUNCH_OK("gradnorm");
   return 0;
@@ -581,7 +627,7 @@ int slnlp_sgd_momentum_clip(float* p, const float* g, float* buf, int64_t n, con
   int64_t want = (n / 4 + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 8;
   int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-  sgd_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, g, buf, n, hyper, norm, grad_scale);
+  launch_pdl(sgd_kernel, dim3(grid), dim3(256), 0, as_stream(stream), p, g, buf, n, hyper, norm, grad_scale);
   SLNLP_LAUNCH_OK("sgd_momentum_clip");
   return 0;
 }

@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(GT) gemm_bf16_kernel(int M, int N, int Kfull, 
                                                         float* __restrict__ C, int ldc,
                                                         const float* __restrict__ bias, float beta,
                                                         float* __restrict__ partial) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_BYTES = TM * TK * 2, B_BYTES = TN * TK * 2;
   uint8_t* sA = smem_raw;                  // 2 stages
@@ -192,7 +194,7 @@ static void launch_bf16(int transA, int transB, dim3 grid, size_t sm, cudaStream
 #define SLNLP_GO(AK, BN)                                                                                          \
   do {                                                                                                            \
     cudaFuncSetAttribute(gemm_bf16_kernel<TN, AK, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
-    gemm_bf16_kernel<TN, AK, BN><<<grid, GT, sm, s>>>(M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial); \
+    launch_pdl(gemm_bf16_kernel<TN, AK, BN>, dim3(grid), dim3(GT), sm, s, M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial); \
   } while (0)
   if (!transA && !transB) SLNLP_GO(true, true);
   else if (!transA && transB) SLNLP_GO(true, false);

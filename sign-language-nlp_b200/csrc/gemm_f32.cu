@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K,
                                                        const float* __restrict__ B, int64_t b_rs, int64_t b_cs,
                                                        float* __restrict__ C, int ldc,
                                                        const float* __restrict__ bias, float beta) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __align__(16) float As[2][GK][GM + 4];
   __shared__ __align__(16) float Bs[2][GK][GN + 4];
   const int tid = threadIdx.x;
@@ -107,6 +109,8 @@ __global__ void __launch_bounds__(256) gemm_f32_vec_kernel(int M, int N, int Kfu
                                                            float* __restrict__ C, int ldc,
                                                            const float* __restrict__ bias, float beta,
                                                            float* __restrict__ partial) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __align__(16) float As[2][VK][VM + 4];
   __shared__ __align__(16) float Bs[2][VK][VN + 4];
   // split-K: this CTA reduces k in [kbeg, K); partial sums go to partial[z][M][N]
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(256) gemm_f32_vec_kernel(int M, int N, int Kfu
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits,
                                                             int M, int N, float* __restrict__ C, int ldc,
                                                             const float* __restrict__ bias, float beta) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t total = (int64_t)M * N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -240,7 +246,7 @@ void launch_splitk_reduce(const float* partial, int splits, int M, int N, float*
   const int64_t total = (int64_t)M * N;
   int rg = (int)((total + 255) / 256);
   if (rg > sm_count() * 4) rg = sm_count() * 4;
-  splitk_reduce_kernel<<<rg, 256, 0, s>>>(partial, splits, M, N, C, ldc, bias, beta);
+  launch_pdl(splitk_reduce_kernel, dim3(rg), dim3(256), 0, s, partial, splits, M, N, C, ldc, bias, beta);
   note_launches(1);
 }
 
@@ -285,22 +291,22 @@ extern "C" int slnlp_gemm_f32(int transA, int transB, int M, int N, int K, const
       vgrid.z = splits;
       partial = workspace;
     }
-    if (!transA && !transB) gemm_f32_vec_kernel<true, true><<<vgrid, 256, 0, s>>>(M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
-    else if (!transA && transB) gemm_f32_vec_kernel<true, false><<<vgrid, 256, 0, s>>>(M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
-    else if (transA && !transB) gemm_f32_vec_kernel<false, true><<<vgrid, 256, 0, s>>>(M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
-    else gemm_f32_vec_kernel<false, false><<<vgrid, 256, 0, s>>>(M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
+    if (!transA && !transB) launch_pdl(gemm_f32_vec_kernel<true, true>, dim3(vgrid), dim3(256), 0, s, M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
+    else if (!transA && transB) launch_pdl(gemm_f32_vec_kernel<true, false>, dim3(vgrid), dim3(256), 0, s, M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
+    else if (transA && !transB) launch_pdl(gemm_f32_vec_kernel<false, true>, dim3(vgrid), dim3(256), 0, s, M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
+    else launch_pdl(gemm_f32_vec_kernel<false, false>, dim3(vgrid), dim3(256), 0, s, M, N, K, kchunk, A, lda, B, ldb, C, ldc, bias, beta, partial);
     if (partial) launch_splitk_reduce(partial, splits, M, N, C, ldc, bias, beta, s);
     SLNLP_LAUNCH_OK("gemm_f32");
     return 0;
   }
   if (!transA && !transB)
-    gemm_f32_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, beta);
+    launch_pdl(gemm_f32_kernel<true, true>, dim3(grid), dim3(256), 0, s, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, beta);
   else if (!transA && transB)
-    gemm_f32_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, beta);
+    launch_pdl(gemm_f32_kernel<true, false>, dim3(grid), dim3(256), 0, s, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, beta);
   else if (transA && !transB)
-    gemm_f32_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, beta);
+    launch_pdl(gemm_f32_kernel<false, true>, dim3(grid), dim3(256), 0, s, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, beta);
   else
-    gemm_f32_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, beta);
+    launch_pdl(gemm_f32_kernel<false, false>, dim3(grid), dim3(256), 0, s, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, beta);
   SLNLP_LAUNCH_OK("gemm_f32");
   return 0;
 }

@@ -67,6 +67,10 @@ __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // the prologue above overlapped the predecessor (programmatic dependent launch); operands and C
+  // are only touched from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -216,7 +220,8 @@ extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, cons
       cudaFuncSetAttribute(gemm_tma_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);        \
       attr = true;                                                                                                 \
     }                                                                                                              \
-    gemm_tma_kernel<AMN, BMN><<<grid, TMA_THREADS, sm, s>>>(mapA, mapB, M, N, K, kchunk, C, ldc, bias, beta, partial); \
+    launch_pdl(gemm_tma_kernel<AMN, BMN>, grid, dim3(TMA_THREADS), sm, s, mapA, mapB, M, N, K, kchunk, C, ldc, bias, beta, \
+               partial);                                                                                           \
   } while (0)
   if (!a_mn && !b_mn) SLNLP_GO(false, false);
   else if (!a_mn && b_mn) SLNLP_GO(false, true);

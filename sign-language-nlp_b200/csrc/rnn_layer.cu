@@ -33,6 +33,8 @@ struct StepFwd {
 
 template <int G, int RB>
 __global__ void __launch_bounds__(FJ * FTB) rnn_step_fwd_kernel(StepFwd p) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(16) float smem[];
   constexpr int BB = FTB * RB;
   constexpr int LDS_ = FKC + 4;
@@ -189,6 +191,8 @@ struct StepBwd {
 
 template <int G, int RB>
 __global__ void __launch_bounds__(BJS * 32) rnn_step_bwd_kernel(StepBwd p) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(16) float smem[];
   constexpr int BB = 8 * RB;
   constexpr int WLD = BKT + 4;
@@ -381,7 +385,7 @@ static int launch_fwd(const StepFwd& p, cudaStream_t s) {
   if (sm > 48 * 1024)
     cudaFuncSetAttribute(rnn_step_fwd_kernel<G, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   dim3 grid(ceil_div(p.H, FJ), ceil_div(p.B, FTB * RB), p.ndir);
-  rnn_step_fwd_kernel<G, RB><<<grid, FJ * FTB, sm, s>>>(p);
+  launch_pdl(rnn_step_fwd_kernel<G, RB>, dim3(grid), dim3(FJ * FTB), sm, s, p);
   return 0;
 }
 template <int G, int RB>
@@ -390,7 +394,7 @@ static int launch_bwd(const StepBwd& p, cudaStream_t s) {
   if (sm > 48 * 1024)
     cudaFuncSetAttribute(rnn_step_bwd_kernel<G, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   dim3 grid(ceil_div(p.H, BKT), ceil_div(p.B, 8 * RB), p.ndir);
-  rnn_step_bwd_kernel<G, RB><<<grid, BJS * 32, sm, s>>>(p);
+  launch_pdl(rnn_step_bwd_kernel<G, RB>, dim3(grid), dim3(BJS * 32), sm, s, p);
   return 0;
 }
 

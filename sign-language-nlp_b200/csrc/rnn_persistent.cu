@@ -55,6 +55,8 @@ struct PersistFwd {
 
 template <int G, int PSEQ>
 __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(PersistFwd p) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int PC = PSEQ / 4;   // batch columns per thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int H = PH;
@@ -276,6 +278,8 @@ struct PersistBwd {
 
 template <int G, int PSEQ>
 __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(PersistBwd p) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int PC = PSEQ / 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int H = PH, GH = G * PH;
@@ -519,12 +523,12 @@ static int seqs_per_cta(int B, int ndir) { return ceil_div(B, 4) * ndir <= (sm_c
 template <int G, int PSEQ>
 static void launch_persist_fwd(const PersistFwd& p, cudaStream_t s) {
   const size_t sm = persist_fwd_smem(G);
-  rnn_persistent_fwd_kernel<G, PSEQ><<<dim3(ceil_div(p.B, PSEQ), p.ndir), PTHREADS, sm, s>>>(p);
+  launch_pdl(rnn_persistent_fwd_kernel<G, PSEQ>, dim3(dim3(ceil_div(p.B, PSEQ), p.ndir)), dim3(PTHREADS), sm, s, p);
 }
 template <int G, int PSEQ>
 static void launch_persist_bwd(const PersistBwd& p, cudaStream_t s) {
   const size_t sm = persist_bwd_smem(G);
-  rnn_persistent_bwd_kernel<G, PSEQ><<<dim3(ceil_div(p.B, PSEQ), p.ndir), PTHREADS, sm, s>>>(p);
+  launch_pdl(rnn_persistent_bwd_kernel<G, PSEQ>, dim3(dim3(ceil_div(p.B, PSEQ), p.ndir)), dim3(PTHREADS), sm, s, p);
 }
 
 int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh,

@@ -106,6 +106,8 @@ __device__ __forceinline__ float drop_factor(const MhaArgs& p, uint64_t seed, ui
 // grid (ceil(Sq/N), nhead, B), block 256.  smem: Q, K, V tiles [N][dh+1] + P [N][N+1].
 template <int RPT, int NDC>
 __global__ void __launch_bounds__(256) mha_fwd_kernel(MhaArgs p) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int N = Tile<RPT>::N;
   extern __shared__ float sm[];
   const int dh = p.dh, st = dh + 1;
@@ -232,6 +234,8 @@ __device__ __forceinline__ void bwd_tile(const MhaArgs& p, const float* sQ, cons
 // writes dK and dV.  smem: four [N][dh+1] tiles + two [N][N+1] tiles.
 template <int RPT, int NDC, bool DKV>
 __global__ void __launch_bounds__(256) mha_bwd_kernel(MhaArgs p) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int N = Tile<RPT>::N;
   extern __shared__ float sm[];
   const int dh = p.dh, st = dh + 1;
@@ -366,6 +370,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(const 
                                                                         const float* __restrict__ beta,
                                                                         float* __restrict__ y, float* __restrict__ mean,
                                                                         float* __restrict__ rstd, int rows, int E, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int row = blockIdx.x * LN_WARPS + w;
   if (row >= rows) return;
@@ -410,6 +416,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
                                                                     const float* __restrict__ rstd, float* __restrict__ dx,
                                                                     float* __restrict__ partials, int rows, int E,
                                                                     int accumulate) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float sred[];   // [LN_WARPS][2][E]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int vpl = (E + 31) >> 5;
@@ -479,7 +487,7 @@ static int launch_mha_fwd(const MhaArgs& a, cudaStream_t s) {
     attr = true;
   }
   dim3 grid(ceil_div(a.Sq, N), a.nhead, a.B);
-  mha_fwd_kernel<RPT, NDC><<<grid, 256, smem, s>>>(a);
+  launch_pdl(mha_fwd_kernel<RPT, NDC>, dim3(grid), dim3(256), smem, s, a);
   SLNLP_LAUNCH_OK("mha_fwd");
   return 0;
 }
@@ -495,9 +503,9 @@ static int launch_mha_bwd(const MhaArgs& a, cudaStream_t s) {
       return fail("mha_bwd: cannot raise the shared-memory limit");
     attr = true;
   }
-  mha_bwd_kernel<RPT, NDC, false><<<dim3(ceil_div(a.Sq, N), a.nhead, a.B), 256, smem, s>>>(a);
+  launch_pdl(mha_bwd_kernel<RPT, NDC, false>, dim3(dim3(ceil_div(a.Sq, N), a.nhead, a.B)), dim3(256), smem, s, a);
   SLNLP_LAUNCH_OK("mha_bwd(dq)");
-  mha_bwd_kernel<RPT, NDC, true><<<dim3(ceil_div(a.Sk, N), a.nhead, a.B), 256, smem, s>>>(a);
+  launch_pdl(mha_bwd_kernel<RPT, NDC, true>, dim3(dim3(ceil_div(a.Sk, N), a.nhead, a.B)), dim3(256), smem, s, a);
   SLNLP_LAUNCH_OK("mha_bwd(dkv)");
   return 0;
 }
@@ -558,7 +566,7 @@ extern "C" int slnlp_add_layernorm_fwd(const float* x, const float* res, const f
                                        slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(x && gamma && beta && y, "add_layernorm_fwd: null pointer");
   SLNLP_CHECK_ARG(rows > 0 && E >= 1 && E <= 32 * LN_MAX_VPL, "add_layernorm_fwd: E must be in [1, 1024]");
-  add_layernorm_fwd_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, as_stream(stream)>>>(x, res, gamma, beta, y, mean, rstd, rows, E, eps);
+  launch_pdl(add_layernorm_fwd_kernel, dim3(ceil_div(rows, LN_WARPS)), dim3(LN_WARPS * 32), 0, as_stream(stream), x, res, gamma, beta, y, mean, rstd, rows, E, eps);
   SLNLP_LAUNCH_OK("add_layernorm_fwd");
   return 0;
 }
@@ -571,7 +579,7 @@ extern "C" int slnlp_layernorm_bwd(const float* dy, const float* x, const float*
   SLNLP_CHECK_ARG(dy && x && gamma && mean && rstd && dx && partials, "layernorm_bwd: null pointer");
   SLNLP_CHECK_ARG(rows > 0 && E >= 1 && E <= 32 * LN_MAX_VPL, "layernorm_bwd: E must be in [1, 1024]");
   const int nb = ln_bwd_blocks(rows);
-  layernorm_bwd_kernel<<<nb, LN_WARPS * 32, LN_WARPS * 2 * E * sizeof(float), as_stream(stream)>>>(
+  launch_pdl(layernorm_bwd_kernel, dim3(nb), dim3(LN_WARPS * 32), LN_WARPS * 2 * E * sizeof(float), as_stream(stream), 
       dy, x, res, gamma, mean, rstd, dx, partials, rows, E, accumulate);
   SLNLP_LAUNCH_OK("layernorm_bwd");
   return 0;

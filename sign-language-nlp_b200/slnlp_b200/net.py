@@ -213,7 +213,7 @@ class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
             out_logp[j:k].copy_(logp)
             if self.fused_:
                 check(lib.slnlp_ce_on_logp(logp.data_ptr(), yd[j:k].data_ptr(), m.tgt_pad, k - j, m.V_tgt, loss.data_ptr(),
-                                           None, row_ws.data_ptr(), _stream()), "ce")
+                                           None, 0, row_ws.data_ptr(), _stream()), "ce")
                 tot += loss[0] * (k - j)
             else:
                 tot += self.criterion_(logp, yd[j:k]) * (k - j)

@@ -189,9 +189,9 @@ class RnnEncDecB200(FlatParamModule):
         rng = self._rng_state().data_ptr() if drop else None
         GH = G * H
         # generator
-        self._gemm(1, 0, V, H, B, ws.dlogits.data_ptr(), V, ws.dec_h[L - 1].data_ptr(), H,
+        self._gemm(1, 0, V, H, B, ws.dlogits.data_ptr(), ws.Vp, ws.dec_h[L - 1].data_ptr(), H,
                    gp("model.generator.proj.weight"), H, None, 1.0)
-        self._gemm(0, 0, B, H, V, ws.dlogits.data_ptr(), V, self._ptr("model.generator.proj.weight"), H,
+        self._gemm(0, 0, B, H, V, ws.dlogits.data_ptr(), ws.Vp, self._ptr("model.generator.proj.weight"), H,
                    ws.d_h.data_ptr(), H)
         # decoder cells, top down
         pre = "model.decoder.rnn."
@@ -378,7 +378,8 @@ class _Workspace:
         self.dec_xin = [f(B, E + 2 * H)] + [f(B, H) if drop else self.dec_h[l - 1] for l in range(1, L)]
         self.logits, self.logp = f(B, V), f(B, V)
         if bwd:
-            self.dlogits = f(B, V)
+            self.Vp = (V + 3) & ~3                    # row stride of dlogits: 16-byte rows keep its GEMMs on TMA
+            self.dlogits = torch.zeros(B, self.Vp, device=dev)
             self.d_h, self.d_c0 = f(B, H), f(B, H)
             self.d_decx, self.d_ctx = f(B, E + 2 * H), f(B, 2 * H)
             self.d_seq = f(T, B, 2 * H)       # d enc_out / d layer outputs (reused down the stack)
@@ -412,7 +413,7 @@ class _ModuleFn(torch.autograd.Function):
             raise RuntimeError("slnlp_b200: gradient must be a CUDA tensor")
         dlogp = dlogp.contiguous().float()
         check(lib.slnlp_log_softmax_bwd(dlogp.data_ptr(), ws.logp.data_ptr(), ws.dlogits.data_ptr(),
-                                        ws.B, m.V_tgt, _stream()), "log_softmax_bwd")
+                                        ws.B, m.V_tgt, ws.Vp, _stream()), "log_softmax_bwd")
         g = torch.zeros_like(m._flat)
         if ws.train and m.uses_rng:  # replay the dropout masks of this forward
             saved = m._rng_state().clone()
@@ -492,7 +493,7 @@ class FusedTrainStep:
             check(lib.slnlp_rng_advance(m._rng_state().data_ptr(), s), "rng")
         m._run_forward(ws, self.X, self.lengths, self.y)
         check(lib.slnlp_ce_on_logp(ws.logp.data_ptr(), self.y.data_ptr(), m.tgt_pad, self.B, m.V_tgt,
-                                   ws.loss.data_ptr(), ws.dlogits.data_ptr(), ws.row_ws.data_ptr(), s), "ce")
+                                   ws.loss.data_ptr(), ws.dlogits.data_ptr(), ws.Vp, ws.row_ws.data_ptr(), s), "ce")
         m._run_backward(ws, self.X, self.lengths, self.gflat, self.y)
         if self.grad_sync is not None:
             self.grad_sync(self.gflat, ws.loss)

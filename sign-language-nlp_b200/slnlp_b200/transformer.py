@@ -241,7 +241,8 @@ class TransformerB200(FlatParamModule):
         R = B * S
         scale = math.sqrt(E)
         dzA, dzB = ws.dz[0].data_ptr(), ws.dz[1].data_ptr()
-        self._lin_bwd(g, ws.dlogits.data_ptr(), ws.zf.data_ptr(), B, "linear.weight", "linear.bias", dzA, self.V_tgt, E, 0.0)
+        self._lin_bwd(g, ws.dlogits.data_ptr(), ws.zf.data_ptr(), B, "linear.weight", "linear.bias", dzA, self.V_tgt, E, 0.0,
+                      lddy=ws.Vp)
         z_top = ws.dec[L - 1].x3
         self._ln_bwd(g, dzA, z_top.data_ptr(), None, "transformer.decoder.norm", ws.ln_dec, dzB, B, ws)
         cur, oth = dzB, dzA      # cur holds d(layer output)
@@ -390,7 +391,8 @@ class _TWorkspace:
         self.zf, self.ln_dec = f(B, E), stats(B)
         self.logits, self.logp = f(B, V), f(B, V)
         if bwd:
-            self.dlogits = f(B, V)
+            self.Vp = (V + 3) & ~3
+            self.dlogits = torch.zeros(B, self.Vp, device=dev)
             self.dz = (f(B, E), f(B, E))
             self.dx = (f(R, E), f(R, E))
             self.dmem = f(R, E)

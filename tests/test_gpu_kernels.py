@@ -142,8 +142,14 @@ def test_log_softmax_and_ce_on_logp(B, V):
     if B > 2:
         y[1] = 1  # ignored target
     loss, dlogits, ws = torch.zeros(2, device="cuda"), torch.empty_like(logits), torch.empty(3 * B, device="cuda")
-    L.check(L.lib.slnlp_ce_on_logp(logp.data_ptr(), y.data_ptr(), 1, B, V, loss.data_ptr(), dlogits.data_ptr(),
+    L.check(L.lib.slnlp_ce_on_logp(logp.data_ptr(), y.data_ptr(), 1, B, V, loss.data_ptr(), dlogits.data_ptr(), V,
                                    ws.data_ptr(), S()))
+    # padded row stride for dlogits (16-byte rows for the TMA GEMMs): same values, columns >= V untouched
+    Vp = (V + 3) // 4 * 4 + 4
+    dpad = torch.full((B, Vp), 7.0, device="cuda")
+    L.check(L.lib.slnlp_ce_on_logp(logp.data_ptr(), y.data_ptr(), 1, B, V, loss.data_ptr(), dpad.data_ptr(), Vp,
+                                   ws.data_ptr(), S()))
+    assert torch.equal(dpad[:, :V], dlogits) and bool((dpad[:, V:] == 7.0).all())
     lg = logits.double().clone().requires_grad_(True)
     ref_loss = torch.nn.functional.cross_entropy(torch.log_softmax(lg, -1), y, ignore_index=1)
     ref_loss.backward()
@@ -153,7 +159,7 @@ def test_log_softmax_and_ce_on_logp(B, V):
     # generic log-softmax backward
     dy = cuda(B, V, seed=13)
     dx = torch.empty_like(dy)
-    L.check(L.lib.slnlp_log_softmax_bwd(dy.data_ptr(), logp.data_ptr(), dx.data_ptr(), B, V, S()))
+    L.check(L.lib.slnlp_log_softmax_bwd(dy.data_ptr(), logp.data_ptr(), dx.data_ptr(), B, V, V, S()))
     lg2 = logits.double().clone().requires_grad_(True)
     torch.log_softmax(lg2, -1).backward(dy.double())
     assert rel_err(dx, lg2.grad) < 1e-5
