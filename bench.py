@@ -299,7 +299,13 @@ def main():
     d2h = 8
 
     # ---------------- dominant kernel, timed alone: the encoder layer-0 recurrence (T launches)
-    roof = dominant_kernel_roofline(m, ts, w, B, dev) if w["kind"] != "transformer" else None
+    peaks0 = {}
+    try:
+        peaks0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    roof_gemm = gemm_roofline(m, w, B, peaks0)
+    roof = dominant_kernel_roofline(m, ts, w, B, dev) if w["kind"] != "transformer" else dict(roof_gemm)
 
     if rank == 0:
         peaks = {}
@@ -331,8 +337,9 @@ def main():
             "model_frac_of_tensor_peak": value * flops_seq / 1e12 / tf_peak,
             "train_mflop_per_seq": flops_seq / 1e6,
             "roofline": roof,
+            "roofline_gemm": roof_gemm,
         }
-        if roof is not None:
+        if roof is not None and roof.get("bound") == "tensor":
             roof["peak"] = peaks.get("bf16_tflops", 1590.0)
             roof["peak_source"] = "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"
             roof["frac"] = roof["achieved"] / roof["peak"]
@@ -349,9 +356,65 @@ def main():
         dist.destroy_process_group()
 
 
+def _time_graph(call, reps=20):
+    """Device time of one `call()` (CUDA-graph replay, CUDA events on the launching stream)."""
+    import torch
+    for _ in range(3):
+        call()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        call()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / 1e3 / reps
+
+
+def _ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+    capture of this kernel (profiles/traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
+def gemm_roofline(m, w, B, peaks):
+    """The hoisted input projection of encoder layer 0 (x W_ih^T for all timesteps and both
+    directions; Transformer: the fused QKV projection), timed alone.  HBM-bound at these K."""
+    import torch
+    from slnlp_b200 import _lib
+    lib = _lib.lib
+    T, E, H = w["T"], w["E"], w["H"]
+    if w["kind"] == "transformer":
+        M, N, K, name = B * T, 3 * E, E, "transformer.encoder.layers.0.self_attn.in_proj_weight"
+    else:
+        G = 4 if w["kind"] == "lstm" else 3
+        M, N, K, name = B * T, 2 * G * H, E, "model.encoder.rnn.weight_ih_l0"
+    x = torch.randn(M, K, device=m._flat.device)
+    out = torch.empty(M, N, device=m._flat.device)
+    gws = m._gemm_ws()
+    fn, kname = (lib.slnlp_gemm_tf32, "gemm_tma_kernel") if m.precision == "bf16" else (lib.slnlp_gemm_f32, "gemm_f32_vec_kernel")
+    sec = _time_graph(lambda: _lib.check(fn(0, 1, M, N, K, x.data_ptr(), K, m._ptr(name), K, out.data_ptr(), N, None, 0.0,
+                                            gws.data_ptr(), gws.numel(), torch.cuda.current_stream().cuda_stream)))
+    by = 4.0 * (M * K + K * N + M * N)
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"kernel": f"{kname} [{M}x{K}]x[{K}x{N}]", "bound": "hbm", "achieved": by / sec / 1e9, "unit": "GB/s",
+            "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+            "frac": by / sec / 1e9 / peak, "us_per_launch": sec * 1e6, "bytes_per_launch": by,
+            "tflops": 2.0 * M * N * K / sec / 1e12, "traffic": _ncu_traffic(kname),
+            "note": "algorithmic bytes 4(MK+KN+MN); L2-warm graph replay, so a fraction above the HBM-only ceiling is possible"}
+
+
 def dominant_kernel_roofline(m, ts, w, B, dev):
-    """Time the dominant kernel (the recurrent step of encoder layer 0: T launches per layer
-    call, both directions per launch) alone with CUDA events on its launching stream."""
+    """Time the dominant kernel - the recurrence of encoder layer 0, both directions - alone with
+    CUDA events on its launching stream.  bf16 path: ONE persistent launch covers all T steps when
+    H = 128 (rnn_persistent_fwd_kernel), else one rnn_step_fwd_tc_kernel launch per step; fp32 path:
+    one rnn_step_fwd_kernel launch per step."""
     import torch
     from slnlp_b200 import _lib
     lib = _lib.lib
@@ -367,26 +430,21 @@ def dominant_kernel_roofline(m, ts, w, B, dev):
                                            ws.enc_stash[0].data_ptr(), ws.enc_hfin[0].data_ptr(),
                                            torch.cuda.current_stream().cuda_stream))
     ws.enc_gates[0].normal_(0, 0.5)
-    for _ in range(3):
-        call()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        call()
-    reps = 20
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    a.record()
-    for _ in range(reps):
-        g.replay()
-    b.record()
-    torch.cuda.synchronize()
-    per_launch_s = a.elapsed_time(b) / 1e3 / (reps * T)
-    flops = 2.0 * B * (G * H) * H * 2            # h_{t-1} W_hh^T, both directions, per launch
-    return {"kernel": "rnn_step_fwd_kernel (h W_hh^T + gates + cell, both directions)" if prec == 0 else "rnn persistent tcgen05",
-            "bound": "tensor", "achieved": flops / per_launch_s / 1e12, "unit": "TFLOP/s",
-            "us_per_launch": per_launch_s * 1e6, "flops_per_launch": flops, "traffic": None,
-            "note": "at batch 50 the 2*L*T dependent recurrence steps, not FLOPs or bytes, bound the step "
-                    "(SURVEY.md 8d); timed as a CUDA-graph replay of one layer call (T launches)"}
+    c0 = lib.slnlp_launch_count()
+    call()
+    launches = max(1, int(lib.slnlp_launch_count() - c0))
+    layer_s = _time_graph(call)
+    per_launch_s = layer_s / launches
+    flops = 2.0 * B * (G * H) * H * 2 * (T / launches)   # h_{t-1} W_hh^T, both directions, per launch
+    if prec == 0:
+        kernel = "rnn_step_fwd_kernel"
+    else:
+        kernel = "rnn_persistent_fwd_kernel" if launches == 1 else "rnn_step_fwd_tc_kernel"
+    return {"kernel": kernel, "bound": "tensor", "achieved": flops / per_launch_s / 1e12, "unit": "TFLOP/s",
+            "us_per_launch": per_launch_s * 1e6, "launches_per_layer": launches, "us_per_timestep": layer_s / T * 1e6,
+            "flops_per_launch": flops, "traffic": _ncu_traffic(kernel),
+            "note": "at batch 50 the 2*L*T strictly dependent recurrence steps, not FLOPs or bytes, bound this kernel "
+                    "(SURVEY.md 8d): read us_per_timestep; the HBM-bound hoisted GEMM is under roofline_gemm"}
 
 
 if __name__ == "__main__":
