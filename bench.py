@@ -41,6 +41,9 @@ WORKLOADS = {
     "cfg4": dict(kind="lstm", E=1024, H=512, L=6, p=0.5, B=4096, T=64, Vs=4098, Vt=1026,
                  name="EncoderDecoderLSTMAttn emb1024 hidden512 layers6 dropout0.5 batch4096 len64"),
 }
+    # BASELINE.json configs[4]: the full config-enc-dec-lstm-attn grid, farmed over the GPUs (no collective)
+WORKLOADS["cfg5"] = dict(kind="grid", B=50, T=64, Vs=4098, Vt=52, E=0, H=0, L=0, p=0.0,
+                         name="config-enc-dec-lstm-attn grid: 3 lr x 3 emb x 3 hidden x 3 layers x 2 dropout x 5-fold CV = 810 fits")
 METRIC, UNIT = "train_seq_per_s", "sequences/s"
 
 
@@ -167,6 +170,64 @@ def run_reference(args, w):
     print(json.dumps(line), flush=True)
 
 
+def run_grid(args, w):
+    """cfg5: the reference's LSTM grid (config-enc-dec-lstm-attn.yaml:45-51; 162 candidates x 5 folds
+    = 810 independent fits) through the estimator + GridSearchFarm, one worker per GPU, fits claimed
+    from a store counter - no NCCL.  Bounded so that it finishes in minutes: every fit trains
+    --grid-epochs epochs (early stopping off) on a --grid-seqs-sequence synthetic corpus; state it
+    when quoting fits/hour.  --impl reference runs the same fits on the CPU port for a sample of the grid."""
+    import numpy as np
+    import torch
+    import helper as h
+    from slnlp_b200.data import SeqDataset
+    from slnlp_b200.grid import GridSearchFarm
+    from slnlp_b200.net import NeuralNetClassifier
+    from slnlp_b200 import _lib
+    import model as dropin
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    ds = SeqDataset.synthetic(n_seq=args.grid_seqs, T=w["T"], v_src=w["Vs"], v_tgt=w["Vt"], ragged=True, seed=1)
+    grid = {"lr": [0.1, 0.01, 0.001], "module__embedding_size": [1024, 512, 128], "module__hidden_size": [512, 256, 128],
+            "module__num_layers": [6, 4, 2], "module__dropout": [0.5, 0.1]}
+    if args.grid_fraction < 1.0:      # a deterministic slice of the candidate list (every k-th), same folds
+        grid = {"lr": [0.01], "module__embedding_size": [1024, 512, 128], "module__hidden_size": [512, 256, 128],
+                "module__num_layers": [6, 4, 2], "module__dropout": [0.1]}
+    from slnlp_b200 import callbacks as cbs
+    net = NeuralNetClassifier(module=dropin.EncoderDecoderLSTMAttn, lr=0.01, max_epochs=args.grid_epochs, batch_size=w["B"],
+                              device=f"cuda:{local}", verbose=0, precision=args.precision,
+                              module__src_vocab=ds.vocab_X, module__tgt_vocab=ds.vocab_y, module__batch_first=True,
+                              optimizer__momentum=0.9, optimizer__nesterov=False, criterion__ignore_index=1,
+                              callbacks=[("gradient_clipping", cbs.GradientNormClipping(gradient_clip_value=0.5))])
+    y = ds.y().to_array()
+    gs = GridSearchFarm(net, grid, cv=5, scoring=h.build_scoring("neg_log_loss", ds.labels(), allow_multiple=False),
+                        refit=False, backend="torchrun" if world > 1 else "inline", per_fit_checkpoint_dirs=False)
+    l0 = _lib.lib.slnlp_launch_count()
+    t0 = time.perf_counter()
+    gs.fit(ds.X(), y)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    if rank != 0:
+        return
+    n_fits = gs.n_fits_
+    steps_per_fit = args.grid_epochs * int(np.ceil(0.8 * 0.8 * args.grid_seqs / w["B"]))
+    busy = {}
+    for r in gs.fit_results_.values():
+        busy[r.get("gpu", 0)] = busy.get(r.get("gpu", 0), 0.0) + r["fit_time"] + r["score_time"]
+    line = {"metric": "grid_fits_per_hour", "value": 3600.0 * n_fits / sec, "unit": "fits/hour", "n_gpus": world,
+            "steps": n_fits, "warmup": 0, "ms_per_step": sec / n_fits * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": w["name"] if args.grid_fraction >= 1.0 else w["name"] + " (lr 0.01, dropout 0.1 slice: 27 candidates x 5 folds)",
+                       "fits": n_fits, "epochs_per_fit": args.grid_epochs, "sequences": args.grid_seqs, "batch": w["B"],
+                       "train_steps_per_fit": steps_per_fit, "seq_len": w["T"], "v_src": w["Vs"], "v_tgt": w["Vt"], "early_stopping": "off (fixed epochs)",
+                       "parallelism": f"{world} worker(s), one per GPU, longest-first, fits claimed from a TCPStore counter, no collective"},
+            "gpu_launches": int(_lib.lib.slnlp_launch_count() - l0), "search_seconds": sec,
+            "worker_busy_seconds": {str(k): round(v, 2) for k, v in sorted(busy.items())},
+            "best_params": {k: v for k, v in gs.best_params_.items()}, "best_score": gs.best_score_}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -179,10 +240,15 @@ def main():
     ap.add_argument("--dp", action="store_true", help="data-parallel one global batch (NCCL all-reduce)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--grid-epochs", type=int, default=2, help="cfg5: epochs per fit")
+    ap.add_argument("--grid-seqs", type=int, default=500, help="cfg5: sequences in the synthetic corpus")
+    ap.add_argument("--grid-fraction", type=float, default=1.0, help="cfg5: < 1 runs the 27-candidate lr=0.01/dropout=0.1 slice")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.batch:
         w["B"] = args.batch
+    if w["kind"] == "grid":
+        return run_grid(args, w)
     if args.impl == "reference":
         return run_reference(args, w)
 
