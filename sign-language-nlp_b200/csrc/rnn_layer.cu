@@ -407,6 +407,15 @@ int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, floa
                      const float* dout, const float* dh_final, const float* dc_final, float* dh0, float* dc0,
                      cudaStream_t s);
 
+// cluster-persistent path, W_hh slices resident in the TMEM of a thread-block cluster, H = 256 / 512
+// (rnn_cluster.cu); -1 = unsupported
+int rnn_layer_fwd_cluster(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh, const float* b_hh,
+                          const int64_t* lengths, const float* h0, const float* c0, float* out, float* stash,
+                          float* h_final, cudaStream_t s);
+int rnn_layer_bwd_cluster(int mode, int T, int B, int H, int ndir, float* gates, float* stash, const float* out,
+                          const float* w_hh, const int64_t* lengths, const float* h0, const float* c0,
+                          const float* dout, const float* dh_final, const float* dc_final, float* dh0, float* dc0,
+                          cudaStream_t s);
 // per-timestep TMA + tcgen05 kind::tf32 path for any H % 32 == 0 (rnn_step_tc.cu); -1 = unsupported
 int rnn_layer_fwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh, const float* b_hh,
                          const int64_t* lengths, const float* h0, const float* c0, float* out, float* stash,
@@ -431,6 +440,8 @@ extern "C" int slnlp_rnn_layer_fwd(int mode, int precision, int T, int B, int H,
   if (precision == 1) {
     const int rc = rnn_layer_fwd_tc(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
     if (rc >= 0) return rc;
+    const int rc1 = rnn_layer_fwd_cluster(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
+    if (rc1 >= 0) return rc1;
     const int rc2 = rnn_layer_fwd_tcstep(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
     if (rc2 >= 0) return rc2;
     // unsupported shape for the tensor-core kernels: the general path below is still CUDA
@@ -461,6 +472,9 @@ extern "C" int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H,
     const int rc = rnn_layer_bwd_tc(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
                                     dc_final, dh0, dc0, s);
     if (rc >= 0) return rc;
+    const int rc1 = rnn_layer_bwd_cluster(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
+                                          dc_final, dh0, dc0, s);
+    if (rc1 >= 0) return rc1;
     const int rc2 = rnn_layer_bwd_tcstep(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
                                          dc_final, dh0, dc0, carry, s);
     if (rc2 >= 0) return rc2;
