@@ -27,10 +27,10 @@
 namespace slnlp {
 
 constexpr int CU = 32;        // hidden units per CTA
-constexpr int CN = 16;        // MMA N
+// MMA N (template NT): 16, or 32 when a cluster owns 32 sequences
 constexpr int CT = 128;       // threads: TMEM lane = thread
 constexpr int CACC = 4;       // forward: partial accumulators (independent MMA chains)
-constexpr int CA_COL0 = 64;   // TMEM: accumulators in [0, 64), resident operand from 64
+constexpr int CA_COL0 = 128;  // TMEM: accumulators in [0, 128), resident operand from 128 (<= 256 columns)
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(CT, 1) rnn_cluster_fwd_kernel(ClFwd p) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int PCB = NSEQ / 4;   // sequences per thread in the (unit, sequence) phase
+  constexpr int CN = NSEQ <= 16 ? 16 : 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int H = p.H, B = p.B, T = p.T;
   const int C = H / CU;
@@ -189,16 +190,15 @@ __global__ void __launch_bounds__(CT, 1) rnn_cluster_fwd_kernel(ClFwd p) {
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        uint32_t r4[CACC][NSEQ];
 #pragma unroll
-        for (int q = 0; q < CACC; ++q)
+        for (int q = 0; q < CACC; ++q) {
+          uint32_t r4[NSEQ];
 #pragma unroll
-          for (int n = 0; n < NSEQ; n += 4) tmem_ld4_nowait(lane_base + q * CN + n, reinterpret_cast<uint32_t(&)[4]>(r4[q][n]));
-        tmem_wait_ld();
+          for (int n = 0; n < NSEQ; n += 4) tmem_ld4_nowait(lane_base + q * CN + n, reinterpret_cast<uint32_t(&)[4]>(r4[n]));
+          tmem_wait_ld();
 #pragma unroll
-        for (int q = 0; q < CACC; ++q)
-#pragma unroll
-          for (int n = 0; n < NSEQ; ++n) a[n] += __uint_as_float(r4[q][n]);
+          for (int n = 0; n < NSEQ; ++n) a[n] += __uint_as_float(r4[n]);
+        }
       }
 #pragma unroll
       for (int n = 0; n < NSEQ; ++n) raw[(n * 4 + warp) * 32 + lane] = a[n];
@@ -235,12 +235,12 @@ __global__ void __launch_bounds__(CT, 1) rnn_cluster_fwd_kernel(ClFwd p) {
     }
     __syncwarp();
     // broadcast this warp's PCB x 32 new h values to the h tile `outb` of every CTA of the cluster:
-    // 16-byte chunks (8 consecutive k of one sequence) at canonical offset (k/8)*256 + n*16
+    // 16-byte chunks (8 consecutive k of one sequence) at canonical offset (k/8)*(CN*16) + n*16
     for (int item = lane; item < PCB * 4 * C; item += 32) {
       const int pr = item % C, j = (item / C) & 3, i = item / (4 * C);
       const int n = warp * PCB + i;
       const uint4 v = *reinterpret_cast<const uint4*>(hst + n * 32 + j * 8);
-      const uint32_t local = sB_addr + outb * tile_bytes + (uint32_t)((4 * (int)c + j) * 256 + n * 16);
+      const uint32_t local = sB_addr + outb * tile_bytes + (uint32_t)((4 * (int)c + j) * (CN * 16) + n * 16);
       st_cluster16(map_to_cta(local, (uint32_t)pr), v);
     }
     fence_proxy_async_all();
@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(CT, 1) rnn_cluster_bwd_kernel(ClBwd p) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int PCB = NSEQ / 4;
+  constexpr int CN = NSEQ <= 16 ? 16 : 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int H = p.H, B = p.B, T = p.T;
   const int C = H / CU, MT = H / 128;     // CTAs per cluster, M tiles of the partial dh product
@@ -514,6 +515,15 @@ static bool cluster_shape_ok(int H, int B, const void* w_hh) {
   return enabled && (H == 256 || H == 512) && B >= 1 && B <= 256 && ((uintptr_t)w_hh & 15) == 0;
 }
 
+// sequences per cluster: as few as keeps every cluster of the layer resident at once (16-CTA clusters
+// fit one per GPC, 8-CTA clusters two: a second wave would double the layer time)
+static int cluster_nseq(int H, int B) {
+  const int max_clusters = H == 256 ? 14 : 6;
+  for (int nseq : {8, 16, 32})
+    if (ceil_div(B, nseq) * 2 <= max_clusters) return nseq;
+  return 32;
+}
+
 template <typename K>
 static int prep_cluster_kernel(K kernel, int C, size_t smem) {
   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
@@ -526,18 +536,18 @@ int rnn_layer_fwd_cluster(int mode, int T, int B, int H, int ndir, float* gates,
                           const int64_t* lengths, const float* h0, const float* c0, float* out, float* stash,
                           float* h_final, cudaStream_t s) {
   if (h0 || c0 || !cluster_shape_ok(H, B, w_hh)) return -1;
-  const int C = H / CU, nseq = H == 256 ? 8 : 16;
+  const int C = H / CU, nseq = cluster_nseq(H, B), cn = nseq <= 16 ? 16 : 32;
   ClFwd p{T, B, H, ndir, gates, w_hh, b_hh, lengths, out, stash, h_final};
   dim3 grid(C, ceil_div(B, nseq), ndir);
-  const size_t sm = 2 * (size_t)CN * H * 2 + (size_t)nseq * 4 * 32 * 4 + (size_t)nseq * 32 * 2 + 64;
+  const size_t sm = 2 * (size_t)cn * H * 2 + (size_t)nseq * 4 * 32 * 4 + (size_t)nseq * 32 * 2 + 64;
   cudaError_t e;
 #define SLNLP_GO(GG, NS)                                                            \
   do {                                                                              \
     if (prep_cluster_kernel(rnn_cluster_fwd_kernel<GG, NS>, C, sm)) return -1;      \
     e = launch_cluster(rnn_cluster_fwd_kernel<GG, NS>, grid, C, sm, s, &p, sizeof(p)); \
   } while (0)
-  if (mode == SLNLP_MODE_LSTM) { if (nseq == 8) SLNLP_GO(4, 8); else SLNLP_GO(4, 16); }
-  else { if (nseq == 8) SLNLP_GO(3, 8); else SLNLP_GO(3, 16); }
+  if (mode == SLNLP_MODE_LSTM) { if (nseq == 8) SLNLP_GO(4, 8); else if (nseq == 16) SLNLP_GO(4, 16); else SLNLP_GO(4, 32); }
+  else { if (nseq == 8) SLNLP_GO(3, 8); else if (nseq == 16) SLNLP_GO(3, 16); else SLNLP_GO(3, 32); }
 #undef SLNLP_GO
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -552,18 +562,18 @@ int rnn_layer_bwd_cluster(int mode, int T, int B, int H, int ndir, float* gates,
                           const float* dout, const float* dh_final, const float* dc_final, float* dh0, float* dc0,
                           cudaStream_t s) {
   if (h0 || c0 || dh0 || dc0 || !cluster_shape_ok(H, B, w_hh)) return -1;
-  const int C = H / CU, nseq = H == 256 ? 8 : 16;
+  const int C = H / CU, nseq = cluster_nseq(H, B), cn = nseq <= 16 ? 16 : 32;
   ClBwd p{T, B, H, ndir, gates, stash, out, w_hh, lengths, dout, dh_final, dc_final};
   dim3 grid(C, ceil_div(B, nseq), ndir);
-  const size_t sm = (size_t)CN * 128 * 2 + 2 * (size_t)C * 32 * nseq * 4 + 64;
+  const size_t sm = (size_t)cn * 128 * 2 + 2 * (size_t)C * 32 * nseq * 4 + 64;
   cudaError_t e;
 #define SLNLP_GO(GG, NS)                                                            \
   do {                                                                              \
     if (prep_cluster_kernel(rnn_cluster_bwd_kernel<GG, NS>, C, sm)) return -1;      \
     e = launch_cluster(rnn_cluster_bwd_kernel<GG, NS>, grid, C, sm, s, &p, sizeof(p)); \
   } while (0)
-  if (mode == SLNLP_MODE_LSTM) { if (nseq == 8) SLNLP_GO(4, 8); else SLNLP_GO(4, 16); }
-  else { if (nseq == 8) SLNLP_GO(3, 8); else SLNLP_GO(3, 16); }
+  if (mode == SLNLP_MODE_LSTM) { if (nseq == 8) SLNLP_GO(4, 8); else if (nseq == 16) SLNLP_GO(4, 16); else SLNLP_GO(4, 32); }
+  else { if (nseq == 8) SLNLP_GO(3, 8); else if (nseq == 16) SLNLP_GO(3, 16); else SLNLP_GO(3, 32); }
 #undef SLNLP_GO
   if (e != cudaSuccess) {
     cudaGetLastError();
