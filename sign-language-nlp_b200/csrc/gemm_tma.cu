@@ -20,8 +20,12 @@
 
 namespace slnlp {
 
-constexpr int BM = 128, BN = 64, BK = 32, STAGES = 4;      // BK floats = 128 bytes = one swizzle row
-constexpr int A_STAGE = BM * BK * 4, B_STAGE = BN * BK * 4;
+constexpr int BM = 128, BK = 32;      // BK floats = 128 bytes = one swizzle row
+constexpr int A_STAGE = BM * BK * 4;
+// BN (template) = 64 / 128 / 256 with 4 / 3 / 4 ring stages: the host picks the smallest tile width that
+// lets the whole problem run as ONE wave (2 CTAs per SM for 64 and 128, 1 for 256) - at the K of these
+// GEMMs (128 ... 1536) a CTA's life is mostly fixed latency, so a second wave nearly doubles the time.
+__host__ __device__ constexpr int stages_for(int bn) { return bn == 128 ? 3 : 4; }
 constexpr int TMA_THREADS = 192;                             // producer, MMA, 4 epilogue warps
 
 // A_MN / B_MN: the operand is stored with its M (resp. N) index contiguous ("MN-major").
@@ -31,12 +35,13 @@ constexpr int TMA_THREADS = 192;                             // producer, MMA, 4
 //                operands only exist in that layout); inside a box k-row kk at kk*128 B, 4-row
 //                swizzle groups 512 B apart (SBO); LBO = 4096 B between mn blocks; an MMA of K = 8
 //                consumes two groups = 1024 B.
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                 const __grid_constant__ CUtensorMap mapB, int M, int N,
                                                                 int Kfull, int kchunk, float* __restrict__ C, int ldc,
                                                                 const float* __restrict__ bias, float beta,
                                                                 float* __restrict__ partial) {
+  constexpr int STAGES = stages_for(BN), B_STAGE = BN * BK * 4;
   extern __shared__ uint8_t smem_dyn[];
   // the 128-byte swizzle is a function of the shared-memory address: tiles must sit on 1024 B
   uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_cons
     }
     constexpr int SLD = BN + 1;
     float* stage = reinterpret_cast<float*>(smem_raw) + q * 32 * SLD;
-    static_assert(4 * 32 * SLD * 4 <= STAGES * A_STAGE, "staging tile must fit the operand ring");
+    static_assert(4 * 32 * SLD * 4 <= STAGES * (A_STAGE + B_STAGE), "staging tile must fit the operand ring");
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
@@ -190,11 +195,24 @@ extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, cons
   // A(m,k): transA=0 -> [M rows, K contiguous] (K-major); transA=1 -> stored [K rows, M contiguous] (MN-major)
   // B(k,n): transB=1 -> stored [N rows, K contiguous] (K-major); transB=0 -> [K rows, N contiguous] (MN-major)
   const bool a_mn = transA != 0, b_mn = transB == 0;
-  if (!ok || !(a_mn ? tensor_map(A, M, K, lda, 32, true, &mapA) : tensor_map(A, K, M, lda, BM, false, &mapA)) ||
-      !(b_mn ? tensor_map(B, N, K, ldb, 32, true, &mapB) : tensor_map(B, K, N, ldb, BN, false, &mapB)))
+  if (!ok || !(a_mn ? tensor_map(A, M, K, lda, 32, true, &mapA) : tensor_map(A, K, M, lda, BM, false, &mapA)))
     return slnlp_gemm_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, workspace, workspace_floats, stream);
   cudaStream_t s = as_stream(stream);
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  // tile width: fewest waves, then the narrowest tile (more CTAs, shorter epilogues)
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int BNsel = 64, best_waves = 1 << 30;
+  for (int bn : {64, 128, 256}) {
+    if (bn > 64 && N < bn) break;
+    const int t = ceil_div(N, bn) * ceil_div(M, BM), slots = (bn == 256 ? 1 : 2) * sms;
+    const int waves = ceil_div(t, slots);
+    if (waves < best_waves) {
+      best_waves = waves;
+      BNsel = bn;
+    }
+  }
+  if (!(b_mn ? tensor_map(B, N, K, ldb, 32, true, &mapB) : tensor_map(B, K, N, ldb, BNsel, false, &mapB)))
+    return slnlp_gemm_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, workspace, workspace_floats, stream);
+  dim3 grid(ceil_div(N, BNsel), ceil_div(M, BM));
   SLNLP_CHECK_ARG(grid.y <= 65535, "gemm_tf32: M too large");
   const int tiles = grid.x * grid.y;
   int splits = 1;
@@ -212,22 +230,29 @@ extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, cons
     grid.z = splits;
     partial = workspace;
   }
-  const size_t sm = STAGES * (A_STAGE + B_STAGE) + (2 * STAGES + 1) * 8 + 16 + 1024;
-#define SLNLP_GO(AMN, BMN)                                                                                         \
+#define SLNLP_GO2(AMN, BMN, BNV)                                                                                   \
   do {                                                                                                             \
+    constexpr size_t sm = stages_for(BNV) * (A_STAGE + BNV * BK * 4) + (2 * stages_for(BNV) + 1) * 8 + 16 + 1024;   \
     static bool attr = false;                                                                                      \
     if (!attr) {                                                                                                   \
-      cudaFuncSetAttribute(gemm_tma_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);        \
+      cudaFuncSetAttribute(gemm_tma_kernel<AMN, BMN, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
       attr = true;                                                                                                 \
     }                                                                                                              \
-    launch_pdl(gemm_tma_kernel<AMN, BMN>, grid, dim3(TMA_THREADS), sm, s, mapA, mapB, M, N, K, kchunk, C, ldc, bias, beta, \
-               partial);                                                                                           \
+    launch_pdl(gemm_tma_kernel<AMN, BMN, BNV>, grid, dim3(TMA_THREADS), sm, s, mapA, mapB, M, N, K, kchunk, C, ldc, \
+               bias, beta, partial);                                                                               \
+  } while (0)
+#define SLNLP_GO(AMN, BMN)                         \
+  do {                                             \
+    if (BNsel == 64) SLNLP_GO2(AMN, BMN, 64);      \
+    else if (BNsel == 128) SLNLP_GO2(AMN, BMN, 128); \
+    else SLNLP_GO2(AMN, BMN, 256);                 \
   } while (0)
   if (!a_mn && !b_mn) SLNLP_GO(false, false);
   else if (!a_mn && b_mn) SLNLP_GO(false, true);
   else if (a_mn && !b_mn) SLNLP_GO(true, false);
   else SLNLP_GO(true, true);
 #undef SLNLP_GO
+#undef SLNLP_GO2
   if (partial) launch_splitk_reduce(partial, splits, M, N, C, ldc, bias, beta, s);
   SLNLP_LAUNCH_OK("gemm_tf32");
   return 0;
