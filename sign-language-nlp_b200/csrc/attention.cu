@@ -46,10 +46,35 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
     alpha[(int64_t)b * T + t] = a;
   }
   __syncthreads();
-  // ctx[b,:] = sum_t alpha_t val[t,b,:]
+  // ctx[b,:] = sum_t alpha_t val[t,b,:]: warp w takes t = w, w+nw, ... (T/nw independent row loads in
+  // flight per warp instead of one T-long dependent chain per thread), partials meet in shared memory
+  float* part = sc + T;                       // [nw][W]
+  for (int c0 = 0; c0 < W; c0 += 32 * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int c = c0 + lane * 4;
+    if (c < W) {
+      for (int t = w; t < T; t += nw) {
+        const float a = sc[t];
+        const float* vr = val + ((int64_t)t * B + b) * W + c;
+        if (c + 3 < W && (((uintptr_t)vr & 15) == 0)) {
+          const float4 x = *reinterpret_cast<const float4*>(vr);
+          acc[0] = fmaf(a, x.x, acc[0]); acc[1] = fmaf(a, x.y, acc[1]);
+          acc[2] = fmaf(a, x.z, acc[2]); acc[3] = fmaf(a, x.w, acc[3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (c + u < W) acc[u] = fmaf(a, vr[u], acc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c + u < W) part[w * W + c + u] = acc[u];
+    }
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < W; c += blockDim.x) {
     float s = 0.f;
-    for (int t = 0; t < T; ++t) s = fmaf(sc[t], val[((int64_t)t * B + b) * W + c], s);
+    for (int ww = 0; ww < nw; ++ww) s += part[ww * W + c];
     ctx[(int64_t)b * W + c] = s;
   }
 }
@@ -90,12 +115,14 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
   dot = block_sum(dot, red);
   for (int t = threadIdx.x; t < T; t += blockDim.x) ds[t] = al[t] * (ds[t] - dot);  // dscore
   __syncthreads();
-  // u = tanh(q + pk); dpre = dscore * v * (1-u^2); dpk = dpre; dq = sum_t dpre; dv = sum_t dscore*u
+  // u = tanh(q + pk); dpre = dscore * v * (1-u^2); dpk = dpre; dq = sum_t dpre; dv = sum_t dscore*u.
+  // Warp w takes t = w, w+nw, ...; the two sums over t meet in shared memory.
   const float* qb = q + (int64_t)b * H;
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+  float* part = ds + T;                       // [nw][2][H]
+  for (int h = lane; h < H; h += 32) {
     const float qh = qb[h], vh = v[h];
     float sq = 0.f, sv = 0.f;
-    for (int t = 0; t < T; ++t) {
+    for (int t = w; t < T; t += nw) {
       const int64_t o = ((int64_t)t * B + b) * H + h;
       const float u = tanhf(qh + pk[o]);
       const float dsc = ds[t];
@@ -103,6 +130,16 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
       dpk[o] = dp;
       sq += dp;
       sv = fmaf(dsc, u, sv);
+    }
+    part[(w * 2 + 0) * H + h] = sq;
+    part[(w * 2 + 1) * H + h] = sv;
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float sq = 0.f, sv = 0.f;
+    for (int ww = 0; ww < nw; ++ww) {
+      sq += part[(ww * 2 + 0) * H + h];
+      sv += part[(ww * 2 + 1) * H + h];
     }
     dq[(int64_t)b * H + h] = sq;
     dv_part[(int64_t)b * H + h] = sv;
@@ -118,7 +155,10 @@ extern "C" int slnlp_attn_step_fwd(const float* q, const float* pk, const float*
                                    float* alpha, float* ctx, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(q && pk && v && val && X && alpha && ctx, "attn_step_fwd: null pointer");
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && W > 0 && T <= 12000, "attn_step_fwd: bad shape");
-  launch_pdl(attn_fwd_kernel, dim3(B), dim3(256), T * sizeof(float), as_stream(stream), q, pk, v, val, X, pad_idx, T, B, H, W, alpha, ctx);
+  const size_t smf = (size_t)(T + 8 * W) * sizeof(float);
+  SLNLP_CHECK_ARG(smf <= 200 * 1024, "attn_step_fwd: T + 8*W too large for shared memory");
+  if (smf > 48 * 1024) cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf);
+  launch_pdl(attn_fwd_kernel, dim3(B), dim3(256), smf, as_stream(stream), q, pk, v, val, X, pad_idx, T, B, H, W, alpha, ctx);
   SLNLP_LAUNCH_OK("attn_step_fwd");
   return 0;
 }
@@ -129,7 +169,10 @@ extern "C" int slnlp_attn_step_bwd(const float* dctx, const float* q, const floa
                                    slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(dctx && q && pk && v && val && alpha && dval && dpk && dq && dv_part, "attn_step_bwd: null pointer");
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && W > 0 && T <= 12000, "attn_step_bwd: bad shape");
-  launch_pdl(attn_bwd_kernel, dim3(B), dim3(256), T * sizeof(float), as_stream(stream), dctx, q, pk, v, val, alpha, T, B, H, W, dval, dpk, dq, dv_part);
+  const size_t smb = (size_t)(T + 16 * H) * sizeof(float);
+  SLNLP_CHECK_ARG(smb <= 200 * 1024, "attn_step_bwd: T + 16*H too large for shared memory");
+  if (smb > 48 * 1024) cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+  launch_pdl(attn_bwd_kernel, dim3(B), dim3(256), smb, as_stream(stream), dctx, q, pk, v, val, alpha, T, B, H, W, dval, dpk, dq, dv_part);
   SLNLP_LAUNCH_OK("attn_step_bwd");
   return 0;
 }
