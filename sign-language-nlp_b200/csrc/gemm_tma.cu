@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_cons
                                                                 const __grid_constant__ CUtensorMap mapB, int M, int N,
                                                                 int Kfull, int kchunk, float* __restrict__ C, int ldc,
                                                                 const float* __restrict__ bias, float beta,
-                                                                float* __restrict__ partial) {
+                                                                float* __restrict__ partial, int atomic_out) {
   constexpr int STAGES = stages_for(BN), B_STAGE = BN * BK * 4;
   extern __shared__ uint8_t smem_dyn[];
   // the 128-byte swizzle is a function of the shared-memory address: tiles must sit on 1024 B
@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_cons
         const float acc = stage[r * SLD + lane + 32 * j];
         if (P) {
           P[(int64_t)m * N + n] = acc;
+        } else if (atomic_out) {
+          atomicAdd(C + (int64_t)m * ldc + n, acc);   // split-K of a C += A B accumulation: red.global.add
         } else {
           float* c = C + (int64_t)m * ldc + n;
           float o = acc + bv[j];
@@ -224,11 +226,21 @@ extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, cons
   }
   int kchunk = K;
   float* partial = nullptr;
+  int atomic_out = 0;
   if (splits > 1) {
     kchunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
     splits = (K + kchunk - 1) / kchunk;
     grid.z = splits;
-    partial = workspace;
+    // gradient accumulation (C += A B, no bias): every K-slice adds its tile straight into C with
+    // red.global.add - no partials in HBM, no reduce launch.  The fp32 summation order then varies
+    // from run to run (~1e-7 relative); SLNLP_SPLITK_ATOMIC=0 keeps the deterministic two-pass form.
+    static int use_atomic = -1;
+    if (use_atomic < 0) {
+      const char* e = getenv("SLNLP_SPLITK_ATOMIC");
+      use_atomic = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_atomic && beta == 1.f && !bias) atomic_out = 1;
+    else partial = workspace;
   }
 #define SLNLP_GO2(AMN, BMN, BNV)                                                                                   \
   do {                                                                                                             \
@@ -239,7 +251,7 @@ extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, cons
       attr = true;                                                                                                 \
     }                                                                                                              \
     launch_pdl(gemm_tma_kernel<AMN, BMN, BNV>, grid, dim3(TMA_THREADS), sm, s, mapA, mapB, M, N, K, kchunk, C, ldc, \
-               bias, beta, partial);                                                                               \
+               bias, beta, partial, atomic_out);                                                                   \
   } while (0)
 #define SLNLP_GO(AMN, BMN)                         \
   do {                                             \

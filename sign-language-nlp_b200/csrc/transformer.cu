@@ -362,8 +362,11 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(MhaArgs p) {
 // ------------------------------------------------------------------ LayerNorm
 constexpr int LN_MAX_VPL = 32;   // values per lane: E <= 1024
 constexpr int LN_WARPS = 4;
+// the kernels are instantiated for VPLT = 4, 8, 16, 32 values per lane (E <= 128, 256, 512, 1024) so that
+// the per-lane arrays fit the register file with room for several CTAs per SM
 
 // y = LN(x + res) * gamma + beta; one warp per row.  mean / rstd [rows] saved for backward.
+template <int VPLT>
 __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(const float* __restrict__ x,
                                                                         const float* __restrict__ res,
                                                                         const float* __restrict__ gamma,
@@ -378,10 +381,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(const 
   const int vpl = (E + 31) >> 5;
   const float* xr = x + (int64_t)row * E;
   const float* rr = res ? res + (int64_t)row * E : nullptr;
-  float v[LN_MAX_VPL];
+  float v[VPLT];
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VPL; ++k)
+  for (int k = 0; k < VPLT; ++k)
     if (k < vpl && lane + 32 * k < E) {
       v[k] = xr[lane + 32 * k] + (rr ? rr[lane + 32 * k] : 0.f);
       s += v[k];
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(const 
   const float mu = warp_sum(s) / E;
   float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VPL; ++k)
+  for (int k = 0; k < VPLT; ++k)
     if (k < vpl && lane + 32 * k < E) {
       const float d = v[k] - mu;
       q = fmaf(d, d, q);
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(const 
   const float rs = rsqrtf(warp_sum(q) / E + eps);
   float* yr = y + (int64_t)row * E;
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VPL; ++k)
+  for (int k = 0; k < VPLT; ++k)
     if (k < vpl && lane + 32 * k < E) yr[lane + 32 * k] = (v[k] - mu) * rs * gamma[lane + 32 * k] + beta[lane + 32 * k];
   if (lane == 0) {
     if (mean) mean[row] = mu;
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(const 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma, xhat = (x + res - mean) * rstd.
 // dx is accumulated into when `accumulate` (the residual branch already holds a gradient).
 // partials [gridDim.x, 2, E]: per-block sums of dy * xhat (d gamma) and dy (d beta).
+template <int VPLT>
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const float* __restrict__ dy,
                                                                     const float* __restrict__ x,
                                                                     const float* __restrict__ res,
@@ -421,9 +425,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
   extern __shared__ float sred[];   // [LN_WARPS][2][E]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int vpl = (E + 31) >> 5;
-  float dg[LN_MAX_VPL], db[LN_MAX_VPL], gm[LN_MAX_VPL];
+  float dg[VPLT], db[VPLT], gm[VPLT];
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VPL; ++k) {
+  for (int k = 0; k < VPLT; ++k) {
     dg[k] = db[k] = 0.f;
     gm[k] = (k < vpl && lane + 32 * k < E) ? gamma[lane + 32 * k] : 0.f;
   }
@@ -432,10 +436,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
     const float* rr = res ? res + (int64_t)row * E : nullptr;
     const float* gr = dy + (int64_t)row * E;
     const float mu = mean[row], rs = rstd[row];
-    float xh[LN_MAX_VPL], g[LN_MAX_VPL];
+    float xh[VPLT], g[VPLT];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAX_VPL; ++k)
+    for (int k = 0; k < VPLT; ++k)
       if (k < vpl && lane + 32 * k < E) {
         const float d = gr[lane + 32 * k];
         xh[k] = (xr[lane + 32 * k] + (rr ? rr[lane + 32 * k] : 0.f) - mu) * rs;
@@ -449,14 +453,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
     s2 = warp_sum(s2) / E;
     float* o = dx + (int64_t)row * E;
 #pragma unroll
-    for (int k = 0; k < LN_MAX_VPL; ++k)
+    for (int k = 0; k < VPLT; ++k)
       if (k < vpl && lane + 32 * k < E) {
         const float val = rs * (g[k] - s1 - xh[k] * s2);
         o[lane + 32 * k] = accumulate ? o[lane + 32 * k] + val : val;
       }
   }
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VPL; ++k)
+  for (int k = 0; k < VPLT; ++k)
     if (k < vpl && lane + 32 * k < E) {
       sred[(w * 2 + 0) * E + lane + 32 * k] = dg[k];
       sred[(w * 2 + 1) * E + lane + 32 * k] = db[k];
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
 
 static int ln_bwd_blocks(int rows) {
   int nb = ceil_div(rows, LN_WARPS);
-  const int cap = 2 * (sm_count() > 0 ? sm_count() : 148);
+  const int cap = 4 * (sm_count() > 0 ? sm_count() : 148);
   return nb < cap ? nb : cap;
 }
 
@@ -566,7 +570,12 @@ extern "C" int slnlp_add_layernorm_fwd(const float* x, const float* res, const f
                                        slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(x && gamma && beta && y, "add_layernorm_fwd: null pointer");
   SLNLP_CHECK_ARG(rows > 0 && E >= 1 && E <= 32 * LN_MAX_VPL, "add_layernorm_fwd: E must be in [1, 1024]");
-  launch_pdl(add_layernorm_fwd_kernel, dim3(ceil_div(rows, LN_WARPS)), dim3(LN_WARPS * 32), 0, as_stream(stream), x, res, gamma, beta, y, mean, rstd, rows, E, eps);
+#define SLNLP_LN_FWD(V) launch_pdl(add_layernorm_fwd_kernel<V>, dim3(ceil_div(rows, LN_WARPS)), dim3(LN_WARPS * 32), 0, as_stream(stream), x, res, gamma, beta, y, mean, rstd, rows, E, eps)
+  if (E <= 128) SLNLP_LN_FWD(4);
+  else if (E <= 256) SLNLP_LN_FWD(8);
+  else if (E <= 512) SLNLP_LN_FWD(16);
+  else SLNLP_LN_FWD(32);
+#undef SLNLP_LN_FWD
   SLNLP_LAUNCH_OK("add_layernorm_fwd");
   return 0;
 }
@@ -579,8 +588,12 @@ extern "C" int slnlp_layernorm_bwd(const float* dy, const float* x, const float*
   SLNLP_CHECK_ARG(dy && x && gamma && mean && rstd && dx && partials, "layernorm_bwd: null pointer");
   SLNLP_CHECK_ARG(rows > 0 && E >= 1 && E <= 32 * LN_MAX_VPL, "layernorm_bwd: E must be in [1, 1024]");
   const int nb = ln_bwd_blocks(rows);
-  launch_pdl(layernorm_bwd_kernel, dim3(nb), dim3(LN_WARPS * 32), LN_WARPS * 2 * E * sizeof(float), as_stream(stream), 
-      dy, x, res, gamma, mean, rstd, dx, partials, rows, E, accumulate);
+#define SLNLP_LN_BWD(V) launch_pdl(layernorm_bwd_kernel<V>, dim3(nb), dim3(LN_WARPS * 32), LN_WARPS * 2 * E * sizeof(float), as_stream(stream),        dy, x, res, gamma, mean, rstd, dx, partials, rows, E, accumulate)
+  if (E <= 128) SLNLP_LN_BWD(4);
+  else if (E <= 256) SLNLP_LN_BWD(8);
+  else if (E <= 512) SLNLP_LN_BWD(16);
+  else SLNLP_LN_BWD(32);
+#undef SLNLP_LN_BWD
   SLNLP_LAUNCH_OK("layernorm_bwd");
   return 0;
 }

@@ -548,3 +548,20 @@ def test_gemm_tf32_tma(tA, tB, M, N, K):
     assert rel_err(C, exact) < BF16_RTOL
     assert rel_err(C, exact) < 2e-3                    # TF32: ~2^-11 per operand
     assert rel_err(C, trunc) < 2e-5 or rel_err(C, exact) < 1e-6   # (fp32 fallback shapes are exact)
+
+
+@pytest.mark.parametrize("tA,tB,M,N,K", [(1, 0, 1024, 256, 3200), (1, 0, 512, 128, 3150), (0, 1, 64, 32, 4000)])
+def test_gemm_tf32_split_k_accumulates_in_place(tA, tB, M, N, K):
+    """C += A B with a long K (the dW GEMMs): K-slices add into C with red.global.add instead of a
+    partial buffer + reduce pass.  Same values up to fp32 summation order."""
+    L = _lib()
+    A = cuda(*((K, M) if tA else (M, K)), seed=71)
+    B = cuda(*((N, K) if tB else (K, N)), seed=72)
+    C0 = cuda(M, N, seed=73)
+    ws = torch.empty(L.lib.slnlp_gemm_workspace_floats(), device="cuda")
+    C = C0.clone()
+    L.check(L.lib.slnlp_gemm_tf32(tA, tB, M, N, K, A.data_ptr(), A.shape[1], B.data_ptr(), B.shape[1],
+                                  C.data_ptr(), N, None, 1.0, ws.data_ptr(), ws.numel(), S()))
+    opA, opB = (A.t() if tA else A), (B.t() if tB else B)
+    tf = lambda x: (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+    assert rel_err(C, tf(opA) @ tf(opB) + C0.double()) < 2e-5
