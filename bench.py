@@ -505,7 +505,7 @@ def dominant_kernel_roofline(m, ts, w, B, dev):
     if prec == 0:
         kernel = "rnn_step_fwd_kernel"
     else:
-        kernel = "rnn_persistent_fwd_kernel" if launches == 1 else "rnn_step_fwd_tc_kernel"
+        kernel = ("rnn_persistent_fwd_kernel" if H == 128 else "rnn_cluster_fwd_kernel") if launches == 1 else "rnn_step_fwd_tc_kernel"
     return {"kernel": kernel, "bound": "tensor", "achieved": flops / per_launch_s / 1e12, "unit": "TFLOP/s",
             "us_per_launch": per_launch_s * 1e6, "launches_per_layer": launches, "us_per_timestep": layer_s / T * 1e6,
             "flops_per_launch": flops, "traffic": _ncu_traffic(kernel),

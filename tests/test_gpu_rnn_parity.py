@@ -181,3 +181,47 @@ def test_input_validation_and_edge_cases():
         a = m(X=X, y=y)
         b = m(X=X, y=y, lengths=lengths)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("kind,E,H,L,ragged", [("lstm", 128, 128, 2, True),      # cfg1: persistent kernel, W_hh in TMEM
+                                              ("gru", 512, 256, 4, True),       # cfg2: 8-CTA cluster kernel
+                                              ("lstm", 128, 256, 2, False),     # LSTM on the cluster kernel
+                                              ("lstm", 64, 512, 1, True),       # 16-CTA clusters
+                                              ("gru", 64, 96, 2, True)])        # per-step TMA kernels (H % 32 == 0)
+def test_tensor_core_path_within_bf16_tolerance_of_the_reference(kind, E, H, L, ragged):
+    """precision='bf16' (tcgen05 recurrence with bf16 operands, TF32 TMA GEMMs, MUFU activations)
+    against the torch.nn port of the reference on identical weights and inputs: logits and loss
+    within north_star's 2e-2, through two full training steps."""
+    import model as dropin
+    from helpers import BF16_RTOL
+    from oracle import port
+    from slnlp_b200.rnn import FusedTrainStep
+    from slnlp_b200.vocab import Vocab
+    B, T, Vs, Vt = 50, 64, 4098, 1026
+    torch.manual_seed(1)
+    ref = port.build_port(kind, Vs, Vt, E, H, L, dropout=0.0)
+    cls = dropin.EncoderDecoderLSTMAttn if kind == "lstm" else dropin.EncoderDecoderGRUAttn
+    m = cls(src_vocab=Vocab(size=Vs), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E,
+            hidden_size=H, num_layers=L, dropout=0.0, device=torch.device("cuda"), precision="bf16")
+    m.load_state_dict(ref.state_dict())
+    m = m.to(torch.device("cuda"))
+    X, lengths, y = _synthetic(B, T, Vs, Vt, ragged)
+    ref.eval()
+    with torch.no_grad():
+        want = ref(X=X, y=y, lengths=lengths)
+    m.eval()
+    with torch.no_grad():
+        got = m(X=X.cuda(), y=y.cuda(), lengths=lengths.cuda())
+    assert rel_err(got, want) < BF16_RTOL
+    m.train()
+    ts = FusedTrainStep(m, B, T, lr=0.01)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9)
+    for step in range(2):
+        want_loss = port.reference_train_step(ref, opt, X, y, lengths)
+        got_loss = ts.step(X.cuda(), y.cuda(), lengths.cuda())
+        assert abs(float(got_loss[0]) - float(want_loss)) < BF16_RTOL * abs(float(want_loss))
+    # the update itself: every tensor within 2e-2 of its own scale (floor 1e-3) after two steps
+    rsd, sd = ref.state_dict(), m.state_dict()
+    for k in rsd:
+        err = float((sd[k].cpu() - rsd[k]).abs().max()) / max(float(rsd[k].abs().max()), 1e-3)
+        assert err < BF16_RTOL, k
