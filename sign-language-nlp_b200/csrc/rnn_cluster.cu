@@ -282,8 +282,11 @@ __global__ void __launch_bounds__(CT, 1) rnn_cluster_bwd_kernel(ClBwd p) {
   const int H = p.H, B = p.B, T = p.T;
   const int C = H / CU, MT = H / 128;     // CTAs per cluster, M tiles of the partial dh product
   uint8_t* sD = smem_raw;                 // B' tile: this CTA's d(gate rows) [16 x 128] bf16, canonical
-  float* recv = reinterpret_cast<float*>(smem_raw + CN * 128 * 2);   // [2][C][32][NSEQ] partials for my units
-  const int recv_half = C * 32 * NSEQ;
+  // partials for my units: [2][C][32][NSEQ + 4].  The +4 keeps rows 16-byte aligned and spreads the
+  // per-unit rows over the banks (stride NSEQ alone puts every lane of a warp on the same bank)
+  constexpr int RLD = NSEQ + 4;
+  float* recv = reinterpret_cast<float*>(smem_raw + CN * 128 * 2);
+  const int recv_half = C * 32 * RLD;
   uint64_t* bar = reinterpret_cast<uint64_t*>(recv + 2 * recv_half);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
@@ -389,10 +392,22 @@ __global__ void __launch_bounds__(CT, 1) rnn_cluster_bwd_kernel(ClBwd p) {
 #pragma unroll
     for (int i = 0; i < PCB; ++i) m[i] = 0.f;
     if (step > 0) {
-      const float* rb = recv + ((step - 1) & 1) * recv_half;
-      for (int src = 0; src < C; ++src)
+      const float* rb = recv + ((step - 1) & 1) * recv_half + lane * RLD + warp * PCB;
+      for (int src = 0; src < C; ++src) {
+        if (PCB % 4 == 0) {
 #pragma unroll
-        for (int i = 0; i < PCB; ++i) m[i] += rb[(src * 32 + lane) * NSEQ + warp * PCB + i];
+          for (int i = 0; i < PCB; i += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(rb + src * 32 * RLD + i);
+            m[i] += v.x; m[i + 1] += v.y; m[i + 2] += v.z; m[i + 3] += v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < PCB; i += 2) {
+            const float2 v = *reinterpret_cast<const float2*>(rb + src * 32 * RLD + i);
+            m[i] += v.x; m[i + 1] += v.y;
+          }
+        }
+      }
     }
     // 2. cell backward for (unit = lane, sequences warp*PCB + i); d(gate rows) -> the B' tile
 #pragma unroll
@@ -470,7 +485,7 @@ __global__ void __launch_bounds__(CT, 1) rnn_cluster_bwd_kernel(ClBwd p) {
       for (int n = 0; n < NSEQ; n += 4) tmem_ld4_nowait(lane_base + i * CN + n, reinterpret_cast<uint32_t(&)[4]>(r4[n]));
       tmem_wait_ld();
       const uint32_t peer = (uint32_t)(4 * i + warp);
-      const uint32_t local = recv_addr + (uint32_t)(((step & 1) * recv_half + ((int)c * 32 + lane) * NSEQ) * 4);
+      const uint32_t local = recv_addr + (uint32_t)(((step & 1) * recv_half + ((int)c * 32 + lane) * RLD) * 4);
       const uint32_t remote = map_to_cta(local, peer);
 #pragma unroll
       for (int n = 0; n < NSEQ; n += 4) st_cluster16(remote + n * 4, make_uint4(r4[n], r4[n + 1], r4[n + 2], r4[n + 3]));
@@ -565,7 +580,7 @@ int rnn_layer_bwd_cluster(int mode, int T, int B, int H, int ndir, float* gates,
   const int C = H / CU, nseq = cluster_nseq(H, B), cn = nseq <= 16 ? 16 : 32;
   ClBwd p{T, B, H, ndir, gates, stash, out, w_hh, lengths, dout, dh_final, dc_final};
   dim3 grid(C, ceil_div(B, nseq), ndir);
-  const size_t sm = (size_t)cn * 128 * 2 + 2 * (size_t)C * 32 * nseq * 4 + 64;
+  const size_t sm = (size_t)cn * 128 * 2 + 2 * (size_t)C * 32 * (nseq + 4) * 4 + 64;
   cudaError_t e;
 #define SLNLP_GO(GG, NS)                                                            \
   do {                                                                              \

@@ -32,14 +32,6 @@ constexpr int NACC = 4;        // BPTT: partial accumulators (independent MMA ch
 constexpr int A_COL0 = 64;     // TMEM: accumulators in columns [0, 64), the resident W_hh operand from 64 on
 constexpr int TMEM_COLS = 512; // 64 + up to 256 operand columns -> the whole tensor memory of the SM
 
-#ifdef SLNLP_PERSIST_TIMING
-// debug build only: per-phase cycle counters of CTA (0,0), read back by slnlp_debug_persist_clocks
-__device__ unsigned long long g_clk[8];
-#define CLK(i, expr) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 200)) { expr; } } while (0)
-#else
-#define CLK(i, expr) do { } while (0)
-#endif
-
 struct PersistFwd {
   int T, B, ndir;
   float* gates;          // [T,B,ndir,G,H]
@@ -563,12 +555,3 @@ int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, floa
 }
 
 }  // namespace slnlp
-
-#ifdef SLNLP_PERSIST_TIMING
-extern "C" int slnlp_debug_persist_clocks(unsigned long long* out8, int reset) {
-  unsigned long long z[8] = {0};
-  if (cudaMemcpyFromSymbol(out8, slnlp::g_clk, sizeof(z)) != cudaSuccess) return 1;
-  if (reset && cudaMemcpyToSymbol(slnlp::g_clk, z, sizeof(z)) != cudaSuccess) return 1;
-  return 0;
-}
-#endif
