@@ -280,11 +280,9 @@ def main():
 
     grad_sync = None
     if args.dp and world > 1:
-        def grad_sync(gflat, loss):
-            dist.all_reduce(gflat)
+        from slnlp_b200.dp import sync_gradients     # count-weighted all-reduce: exact global-batch gradient
+        grad_sync = sync_gradients
     ts = FusedTrainStep(m, B, w["T"], lr=0.01, momentum=0.9, max_norm=0.5, grad_sync=grad_sync)
-    if args.dp and world > 1:
-        ts.grad_scale = 1.0 / world
 
     # ---------------- device-resident leg: whole dataset in HBM, batches sliced on device
     Xd, yd, ld = data["X"].to(dev), data["y"].to(dev), data["lengths"].to(dev)
