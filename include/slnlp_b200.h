@@ -165,6 +165,11 @@ int slnlp_log_softmax_bwd(const float* dlogp, const float* logp, float* dlogits,
  * dlogits (may be NULL) = d loss / d logits through both log-softmaxes. */
 int slnlp_ce_on_logp(const float* logp, const int64_t* y, int64_t ignore_index, int B, int V,
                      float* loss_out, float* dlogits, int ld_dlogits, float* row_ws, slnlp_stream_t stream);
+/* The two above in ONE pass per row (north_star: "fused CrossEntropy+log-softmax"): logits -> logp
+ * (written), loss_out = {mean loss, n_valid}, dlogits (may be NULL) with row stride ld_dlogits. */
+int slnlp_logsoftmax_ce_fused(const float* logits, const int64_t* y, int64_t ignore_index, int B, int V,
+                              float* logp, float* loss_out, float* dlogits, int ld_dlogits, float* row_ws,
+                              slnlp_stream_t stream);
 
 /* ---- K11/K12: GradientNormClipping -> clip_grad_norm_(max_norm, 2) (helper.py:227-229)
  * and torch.optim.SGD(momentum, nesterov=False) (config/*.yaml:39-42), over flat buffers.

@@ -189,6 +189,61 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
     row_ws[2 * B + b] = lse;
   }
 }
+// K10 fused: generator log_softmax (bkp:75-76) + CrossEntropyLoss(ignore_index) on the log-probs
+// (config/*.yaml:36) + d loss / d logits in ONE pass per row.  The row stays in registers/L1:
+// logits -> logp (written: the module's output) -> second log-sum-exp -> row loss, and the
+// gradient (softmax(logp) - onehot) * valid / n_valid, where n_valid is recounted by every CTA
+// from the B labels (cheaper than a grid-wide dependency).  The mean loss itself is off the
+// critical path and is reduced by ce_reduce_kernel afterwards.
+__global__ void __launch_bounds__(256) logsoftmax_ce_fused_kernel(const float* __restrict__ logits,
+                                                                  const int64_t* __restrict__ y, int64_t ignore,
+                                                                  int B, int V, float* __restrict__ logp,
+                                                                  float* __restrict__ row_ws,
+                                                                  float* __restrict__ dlogits, int ld) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float red[33];
+  const int b = blockIdx.x;
+  const float* xr = logits + (int64_t)b * V;
+  float* lr = logp + (int64_t)b * V;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, xr[v]);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(xr[v] - m);
+  s = block_sum(s, red);
+  const float lse1 = m + logf(s);
+  // second log-softmax, on the log-probs (what CrossEntropyLoss applies to the module output)
+  const float m2 = m - lse1;                      // max of logp
+  float s2 = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float lp = xr[v] - lse1;
+    lr[v] = lp;
+    s2 += expf(lp - m2);
+  }
+  s2 = block_sum(s2, red);
+  const float lse2 = m2 + logf(s2);
+  float cnt = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const int64_t yi = y[i];
+    cnt += (yi != ignore && yi >= 0 && yi < V) ? 1.f : 0.f;
+  }
+  cnt = block_sum(cnt, red);
+  const int64_t yb = y[b];
+  const bool valid = yb != ignore && yb >= 0 && yb < V;
+  if (threadIdx.x == 0) {
+    row_ws[b] = valid ? -((xr[yb] - lse1) - lse2) : 0.f;
+    row_ws[B + b] = valid ? 1.f : 0.f;
+    row_ws[2 * B + b] = lse2;
+  }
+  if (dlogits) {
+    const float inv = valid ? 1.f / cnt : 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float g = expf((xr[v] - lse1) - lse2) - (v == yb ? 1.f : 0.f);
+      dlogits[(int64_t)b * ld + v] = valid ? g * inv : 0.f;
+    }
+  }
+}
 __global__ void __launch_bounds__(256) ce_reduce_kernel(const float* __restrict__ row_ws, int B,
                                                         float* __restrict__ loss_out) {
   pdl_wait();
@@ -604,6 +659,19 @@ int slnlp_ce_on_logp(const float* logp, const int64_t* y, int64_t ignore_index, 
   if (dlogits) launch_pdl(ce_grad_kernel, dim3(B), dim3(256), 0, as_stream(stream), logp, y, B, V, row_ws, loss_out, dlogits, ld_dlogits);
   note_launches(dlogits ? 2 : 1);
   SLNLP_LAUNCH_OK("ce_on_logp");
+  return 0;
+}
+
+int slnlp_logsoftmax_ce_fused(const float* logits, const int64_t* y, int64_t ignore_index, int B, int V,
+                              float* logp, float* loss_out, float* dlogits, int ld_dlogits, float* row_ws,
+                              slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(logits && y && logp && loss_out && row_ws && B > 0 && V > 0, "logsoftmax_ce_fused: bad arguments");
+  SLNLP_CHECK_ARG(!dlogits || ld_dlogits >= V, "logsoftmax_ce_fused: ld_dlogits < V");
+  launch_pdl(logsoftmax_ce_fused_kernel, dim3(B), dim3(256), 0, as_stream(stream), logits, y, ignore_index, B, V, logp,
+             row_ws, dlogits, ld_dlogits);
+  launch_pdl(ce_reduce_kernel, dim3(1), dim3(256), 0, as_stream(stream), row_ws, B, loss_out);
+  note_launches(1);
+  SLNLP_LAUNCH_OK("logsoftmax_ce_fused");
   return 0;
 }
 

@@ -174,7 +174,8 @@ class RnnEncDecB200(FlatParamModule):
         # generator (bkp:73-76) on decoder_states, not pre_output (bkp:40-46)
         self._gemm(0, 1, B, self.V_tgt, H, ws.dec_h[L - 1].data_ptr(), H,
                    self._ptr("model.generator.proj.weight"), H, ws.logits.data_ptr(), self.V_tgt)
-        check(lib.slnlp_log_softmax_fwd(ws.logits.data_ptr(), ws.logp.data_ptr(), B, self.V_tgt, s), "log_softmax")
+        if not getattr(ws, "fused_ce", False):   # the fused train step folds it into the criterion kernel
+            check(lib.slnlp_log_softmax_fwd(ws.logits.data_ptr(), ws.logp.data_ptr(), B, self.V_tgt, s), "log_softmax")
         return ws.logp
 
     def _run_backward(self, ws, X, lengths, gflat, y=None):
@@ -465,6 +466,7 @@ class FusedTrainStep:
         self.m, self.B, self.T = module, batch_size, seq_len
         dev = module._flat.device
         self.ws = module._make_workspace(batch_size, seq_len, True, True)
+        self.ws.fused_ce = True      # log_softmax + CE + d logits run as one kernel (K10)
         self.X = torch.full((batch_size, seq_len), module.src_pad, dtype=torch.int64, device=dev)
         self.lengths = torch.ones(batch_size, dtype=torch.int64, device=dev)
         self.y = torch.zeros(batch_size, dtype=torch.int64, device=dev)
@@ -492,8 +494,9 @@ class FusedTrainStep:
         if m.uses_rng:
             check(lib.slnlp_rng_advance(m._rng_state().data_ptr(), s), "rng")
         m._run_forward(ws, self.X, self.lengths, self.y)
-        check(lib.slnlp_ce_on_logp(ws.logp.data_ptr(), self.y.data_ptr(), m.tgt_pad, self.B, m.V_tgt,
-                                   ws.loss.data_ptr(), ws.dlogits.data_ptr(), ws.Vp, ws.row_ws.data_ptr(), s), "ce")
+        check(lib.slnlp_logsoftmax_ce_fused(ws.logits.data_ptr(), self.y.data_ptr(), m.tgt_pad, self.B, m.V_tgt,
+                                            ws.logp.data_ptr(), ws.loss.data_ptr(), ws.dlogits.data_ptr(), ws.Vp,
+                                            ws.row_ws.data_ptr(), s), "logsoftmax_ce")
         m._run_backward(ws, self.X, self.lengths, self.gflat, self.y)
         if self.grad_sync is not None:
             self.grad_sync(self.gflat, ws.loss)

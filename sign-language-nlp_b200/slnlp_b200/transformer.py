@@ -231,7 +231,8 @@ class TransformerB200(FlatParamModule):
             z = st.x3
         self._ln_fwd(z.data_ptr(), None, "transformer.decoder.norm", ws.zf.data_ptr(), ws.ln_dec, B)
         self._lin_fwd(ws.zf.data_ptr(), B, "linear.weight", "linear.bias", ws.logits.data_ptr(), self.V_tgt, E)
-        check(lib.slnlp_log_softmax_fwd(ws.logits.data_ptr(), ws.logp.data_ptr(), B, self.V_tgt, s), "log_softmax")
+        if not getattr(ws, "fused_ce", False):   # the fused train step folds it into the criterion kernel
+            check(lib.slnlp_log_softmax_fwd(ws.logits.data_ptr(), ws.logp.data_ptr(), B, self.V_tgt, s), "log_softmax")
         return ws.logp
 
     # ------------------------------------------------------------------ backward

@@ -159,6 +159,12 @@ def test_log_softmax_and_ce_on_logp(B, V):
     # generic log-softmax backward
     dy = cuda(B, V, seed=13)
     dx = torch.empty_like(dy)
+    # the fused kernel (logits -> logp, loss, d logits in one pass per row) agrees with the three-kernel route
+    logp2, loss2, d2 = torch.empty_like(logp), torch.zeros(2, device="cuda"), torch.full((B, Vp), 7.0, device="cuda")
+    L.check(L.lib.slnlp_logsoftmax_ce_fused(logits.data_ptr(), y.data_ptr(), 1, B, V, logp2.data_ptr(), loss2.data_ptr(),
+                                            d2.data_ptr(), Vp, ws.data_ptr(), S()))
+    assert rel_err(logp2, logp) < 1e-6 and rel_err(d2[:, :V], dlogits) < 1e-5 and bool((d2[:, V:] == 7.0).all())
+    assert abs(float(loss2[0]) - float(loss[0])) < 1e-6 * abs(float(loss[0])) and float(loss2[1]) == float(loss[1])
     L.check(L.lib.slnlp_log_softmax_bwd(dy.data_ptr(), logp.data_ptr(), dx.data_ptr(), B, V, V, S()))
     lg2 = logits.double().clone().requires_grad_(True)
     torch.log_softmax(lg2, -1).backward(dy.double())
