@@ -159,8 +159,38 @@ class FlatParamModule(nn.Module):
         check(fn(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, ws.data_ptr(), ws.numel(), _stream()), "gemm")
 
     def _gemm_ws(self):
-        """Split-K scratch shared by every GEMM of this module (one stream per module)."""
-        ws = getattr(self, "_gemm_scratch", None)
+        """Split-K scratch of the GEMMs of this module: one buffer per stream the module launches on
+        (the main stream and the weight-gradient side stream never share partials)."""
+        side = getattr(self, "_side", None)
+        on_side = side is not None and torch.cuda.current_stream() == side
+        name = "_gemm_scratch_side" if on_side else "_gemm_scratch"
+        ws = getattr(self, name, None)
         if ws is None or ws.device != self._flat.device:
-            ws = self._gemm_scratch = torch.empty(lib.slnlp_gemm_workspace_floats(), device=self._flat.device)
+            ws = torch.empty(lib.slnlp_gemm_workspace_floats(), device=self._flat.device)
+            setattr(self, name, ws)
         return ws
+
+    # ---- weight-gradient side stream: dW / db kernels are not on the dependency chain of BPTT, so
+    # they run on a second stream (a parallel branch of the captured graph) next to the next layer's
+    # recurrent kernel, which occupies a fraction of the SMs at the reference's batch size
+    def _side_stream(self):
+        side = getattr(self, "_side", None)
+        if side is None or side.device != self._flat.device:
+            side = self._side = torch.cuda.Stream(device=self._flat.device)
+            self._gemm_scratch_side = None
+        return side
+
+    def _fork_side(self):
+        side = self._side_stream()
+        ev = torch.cuda.Event()
+        ev.record()
+        side.wait_event(ev)
+        return side
+
+    def _join_side(self):
+        side = getattr(self, "_side", None)
+        if side is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(side)
+        torch.cuda.current_stream().wait_event(ev)

@@ -16,7 +16,9 @@ Two ways in:
 """
 from __future__ import annotations
 
+import contextlib
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -55,6 +57,11 @@ class RnnEncDecB200(FlatParamModule):
         self.V_src, self.V_tgt = len(src_vocab), len(tgt_vocab)
         self.device = kwargs.get("device", None)
         self.validate_inputs = True
+        # weight-gradient kernels on a side stream, next to the next layer's BPTT.  It pays when the
+        # recurrent kernel leaves most SMs idle (H = 128: 26 CTAs; measured +3 % on cfg1) and not when the
+        # cluster kernels fill the GPU (H = 256: -1 % on cfg2).  SLNLP_OVERLAP_DW=0/1 overrides.
+        env = os.environ.get("SLNLP_OVERLAP_DW")
+        self.overlap_dw = (self.H == 128) if env is None else env != "0"
         self._build_parameters()
         self.seed = int(kwargs.get("seed", torch.initial_seed() & 0x7FFFFFFF))
 
@@ -266,31 +273,7 @@ class RnnEncDecB200(FlatParamModule):
             check(lib.slnlp_rnn_layer_bwd(mode, prec, T, B, H, 2, dg, st, out, self._ptr(f"{pre}weight_hh_l{l}"),
                                           lp, None, None, ws.d_seq.data_ptr(), ws.d_hfin.data_ptr(), None,
                                           None, None, ws.carry.data_ptr(), s), "rnn_layer_bwd")
-            xin = (ws.emb if l == 0 else ws.enc_xin[l]).data_ptr()
-            self._gemm(1, 0, 2 * GH, D, T * B, dg, 2 * GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0, big=True)
-            check(lib.slnlp_colsum_f32(dg, T * B, 2 * GH, 2 * GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
-            K = (T - 1) * B
-            for d in range(2):
-                # dW_hh[d] = sum_t dG_t^T h_{prev(t)}: a GEMM over rows shifted by one timestep
-                a_row = B if d == 0 else 0
-                b_row = 0 if d == 0 else B
-                gw = gp(f"{pre}weight_hh_l{l}") + 4 * d * GH * H
-                gb = gp(f"{pre}bias_hh_l{l}") + 4 * d * GH
-                hb = out + 4 * (b_row * 2 * H + d * H)
-                if mode == 0:
-                    if K > 0:
-                        self._gemm(1, 0, GH, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,
-                                   gw, H, None, 1.0, big=True)
-                    if d == 0:  # LSTM: d b_hh == d b_ih for both directions at once
-                        check(lib.slnlp_axpy(gb, gp(f"{pre}bias_ih_l{l}"), 1.0, 2 * GH, s), "axpy")
-                else:
-                    if K > 0:
-                        self._gemm(1, 0, 2 * H, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,
-                                   gw, H, None, 1.0, big=True)
-                        self._gemm(1, 0, H, H, K, st + 4 * (a_row * 2 * H + d * H), 2 * H, hb, 2 * H,
-                                   gw + 4 * 2 * H * H, H, None, 1.0, big=True)
-                    check(lib.slnlp_colsum_f32(dg + 4 * d * GH, T * B, 2 * H, 2 * GH, gb, 1.0, s), "colsum")
-                    check(lib.slnlp_colsum_f32(st + 4 * d * H, T * B, H, 2 * H, gb + 4 * 2 * H, 1.0, s), "colsum")
+            # critical path first: the gradient the next (lower) layer's BPTT is waiting for
             if l > 0:
                 self._gemm(0, 0, T * B, D, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), D,
                            ws.d_seq.data_ptr(), D, big=True)
@@ -303,6 +286,47 @@ class RnnEncDecB200(FlatParamModule):
                 check(lib.slnlp_embed_gather_bwd(gp("model.src_embed.weight"), Xp, ws.d_emb.data_ptr(), B, T, 1,
                                                  ws.f_off, ws.f_w_src, ws.f_rows_src, 1, 1.0, self.src_pad, s),
                       "embed_bwd")
+            # weight / bias gradients of this layer: off the chain, on the side stream
+            side = self._fork_side() if self.overlap_dw else None
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                self._encoder_weight_grads(ws, l, gp, _stream())
+        if self.overlap_dw:
+            self._join_side()
+
+    def _encoder_weight_grads(self, ws, l, gp, s):
+        """dW_ih, db_ih, dW_hh, db_hh of encoder layer l from its d(pre-activation) buffer."""
+        E, H, G = self.E, self.H, self.G
+        B, T = ws.B, ws.T
+        GH = G * H
+        mode = MODE[self.rnn_type]
+        D = E if l == 0 else 2 * H
+        pre = "model.encoder.rnn."
+        dg, st, out = ws.enc_gates[l].data_ptr(), ws.enc_stash[l].data_ptr(), ws.enc_out[l].data_ptr()
+        xin = (ws.emb if l == 0 else ws.enc_xin[l]).data_ptr()
+        self._gemm(1, 0, 2 * GH, D, T * B, dg, 2 * GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0, big=True)
+        check(lib.slnlp_colsum_f32(dg, T * B, 2 * GH, 2 * GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
+        K = (T - 1) * B
+        for d in range(2):
+            # dW_hh[d] = sum_t dG_t^T h_{prev(t)}: a GEMM over rows shifted by one timestep
+            a_row = B if d == 0 else 0
+            b_row = 0 if d == 0 else B
+            gw = gp(f"{pre}weight_hh_l{l}") + 4 * d * GH * H
+            gb = gp(f"{pre}bias_hh_l{l}") + 4 * d * GH
+            hb = out + 4 * (b_row * 2 * H + d * H)
+            if mode == 0:
+                if K > 0:
+                    self._gemm(1, 0, GH, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,
+                               gw, H, None, 1.0, big=True)
+                if d == 0:  # LSTM: d b_hh == d b_ih for both directions at once
+                    check(lib.slnlp_axpy(gb, gp(f"{pre}bias_ih_l{l}"), 1.0, 2 * GH, s), "axpy")
+            else:
+                if K > 0:
+                    self._gemm(1, 0, 2 * H, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,
+                               gw, H, None, 1.0, big=True)
+                    self._gemm(1, 0, H, H, K, st + 4 * (a_row * 2 * H + d * H), 2 * H, hb, 2 * H,
+                               gw + 4 * 2 * H * H, H, None, 1.0, big=True)
+                check(lib.slnlp_colsum_f32(dg + 4 * d * GH, T * B, 2 * H, 2 * GH, gb, 1.0, s), "colsum")
+                check(lib.slnlp_colsum_f32(st + 4 * d * H, T * B, H, 2 * H, gb + 4 * 2 * H, 1.0, s), "colsum")
 
     # ------------------------------------------------------------------ public forward
     def _check_inputs(self, X, lengths):
