@@ -17,6 +17,7 @@ claimed dynamically:
 from __future__ import annotations
 
 import itertools
+import json
 import os
 import pickle
 import time
@@ -80,11 +81,15 @@ def _worker_main(gpu, task_q, result_q, payload_bytes):
 class GridSearchFarm:
     def __init__(self, estimator, param_grid, *, scoring=None, n_jobs=None, refit=True, cv=None, verbose=0,
                  pre_dispatch=None, error_score="raise", return_train_score=False, n_gpus=None, backend="auto",
-                 per_fit_checkpoint_dirs=True):
+                 per_fit_checkpoint_dirs=True, resume_file=None):
         self.estimator, self.param_grid, self.scoring, self.n_jobs = estimator, param_grid, scoring, n_jobs
         self.refit, self.cv, self.verbose, self.pre_dispatch = refit, cv, verbose, pre_dispatch
         self.error_score, self.return_train_score = error_score, return_train_score
         self.n_gpus, self.backend, self.per_fit_checkpoint_dirs = n_gpus, backend, per_fit_checkpoint_dirs
+        # resume_file: JSON-lines journal of finished (candidate, fold) fits.  A search that is started
+        # again with the same grid and folds skips what the journal already holds (the reference aborts
+        # the whole grid on any failure, helper.py:162, and has no resume - SURVEY.md section 5)
+        self.resume_file = resume_file
 
     # ------------------------------------------------------------------ scheduling
     def _tasks(self, X, y):
@@ -115,6 +120,10 @@ class GridSearchFarm:
         cands, folds, tasks, order = self._tasks(X, y)
         scorer = self._scorer()
         backend = self._resolve_backend()
+        done = self._load_journal(cands, len(folds))
+        if done:
+            order = [t for t in order if t not in done]
+        self._journal_keys = {t: (json.dumps(cands[tasks[t][0]], sort_keys=True, default=str), tasks[t][1]) for t in range(len(tasks))}
         t0 = time.perf_counter()
         if backend == "torchrun":
             results = self._run_torchrun(cands, folds, tasks, order, X, y, scorer)
@@ -124,8 +133,10 @@ class GridSearchFarm:
                 results = self._run_inline(cands, folds, tasks, order, X, y, scorer)
             else:
                 results = self._run_spawn(n, cands, folds, tasks, order, X, y, scorer)
+        results.update(done)
         self.search_time_ = time.perf_counter() - t0
         self.n_fits_ = len(tasks)
+        self.n_resumed_ = len(done)
         self._collect(cands, folds, tasks, results)
         if self.refit and self._is_main():
             t1 = time.perf_counter()
@@ -133,6 +144,40 @@ class GridSearchFarm:
             self.best_estimator_.fit(X, y)
             self.refit_time_ = time.perf_counter() - t1
         return self
+
+    def _load_journal(self, cands, n_folds):
+        """{task id: result} of fits a previous, interrupted search already finished."""
+        done = {}
+        if not self.resume_file or not os.path.exists(self.resume_file):
+            return done
+        index = {json.dumps(c, sort_keys=True, default=str): ci for ci, c in enumerate(cands)}
+        with open(self.resume_file) as f:
+            for line in f:
+                try:
+                    rec = json.loads(line)
+                except ValueError:
+                    continue            # a torn last line of an interrupted run
+                ci = index.get(rec.get("params"))
+                if ci is not None and 0 <= rec.get("fold", -1) < n_folds:
+                    done[ci * n_folds + rec["fold"]] = rec["result"]
+        with open(self.resume_file, "rb+") as f:      # terminate a torn last line so that appends start clean
+            f.seek(0, os.SEEK_END)
+            if f.tell() > 0:
+                f.seek(-1, os.SEEK_END)
+                if f.read(1) != b"\n":
+                    f.write(b"\n")
+        return done
+
+    def _journal(self, t, res):
+        if not self.resume_file or not self._is_main_process_for_journal():
+            return
+        params, fold = self._journal_keys[t]
+        with open(self.resume_file, "a") as f:
+            f.write(json.dumps({"params": params, "fold": fold, "result": res}) + "\n")
+            f.flush()
+
+    def _is_main_process_for_journal(self):
+        return True
 
     def _is_main(self):
         return int(os.environ.get("RANK", "0")) == 0 or self._resolve_backend() != "torchrun"
@@ -145,6 +190,7 @@ class GridSearchFarm:
         for t in order:
             ci, fi = tasks[t]
             out[t] = _fit_and_score(self.estimator, cands[ci], X, y, folds[fi][0], folds[fi][1], scorer, self._sub(ci, fi))
+            self._journal(t, out[t])
             if self.verbose:
                 print(f"[grid] {len(out)}/{len(tasks)} cand {ci} fold {fi}: score {out[t]['score']:.4f} "
                       f"fit {out[t]['fit_time']:.2f}s", flush=True)
@@ -165,11 +211,12 @@ class GridSearchFarm:
             task_q.put(None)
         out = {}
         try:
-            while len(out) < len(tasks):
+            while len(out) < len(order):
                 tid, res, err = result_q.get()
                 if err is not None:
                     raise RuntimeError(f"grid-search fit failed (error_score='raise'):\n{err}")
                 out[tid] = res
+                self._journal(tid, res)
                 if self.verbose:
                     ci, fi = tasks[tid]
                     print(f"[grid] {len(out)}/{len(tasks)} cand {ci} fold {fi} on gpu {res['gpu']}: "
@@ -207,8 +254,9 @@ class GridSearchFarm:
             res = _fit_and_score(est, cands[ci], X, y, folds[fi][0], folds[fi][1], scorer, self._sub(ci, fi))
             res["gpu"] = rank
             store.set(f"{key}/res/{t}", pickle.dumps(res))
+            self._journal(t, res)       # every rank appends its own fits (O_APPEND lines, one writer per line)
         out = {}
-        for t in range(len(tasks)):     # blocks until the owning rank has published it
+        for t in order:                 # blocks until the owning rank has published it
             out[t] = pickle.loads(store.get(f"{key}/res/{t}"))
         return out
 

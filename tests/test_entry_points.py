@@ -187,3 +187,35 @@ def test_lr_scheduler_is_torch_reduce_on_plateau(tmp_path):
     net.history[-1]["valid_loss_best"] = True
     cp.on_epoch_end(net)
     assert (tmp_path / "ck" / "history.json").exists()
+
+
+def test_grid_search_resumes_from_its_journal(tmp_path):
+    """A search restarted with the same grid skips the (candidate, fold) fits its journal holds."""
+    from sklearn.linear_model import LogisticRegression
+    rng = np.random.RandomState(0)
+    X = rng.randn(90, 4)
+    y = (X[:, 0] > 0).astype(int)
+    journal = str(tmp_path / "grid.jsonl")
+    grid = {"C": [0.1, 1.0, 10.0]}
+    a = GridSearchFarm(LogisticRegression(max_iter=200), grid, cv=3, scoring="accuracy", refit=False, backend="inline",
+                       resume_file=journal).fit(X, y)
+    assert a.n_resumed_ == 0 and sum(1 for _ in open(journal)) == 9
+    lines = open(journal).read().splitlines()
+    open(journal, "w").write("\n".join(lines[:5]) + "\n{\"params\": \"torn")          # interrupted run: 5 fits + a torn line
+    b = GridSearchFarm(LogisticRegression(max_iter=200), grid, cv=3, scoring="accuracy", refit=False, backend="inline",
+                       resume_file=journal).fit(X, y)
+    assert b.n_resumed_ == 5 and np.allclose(a.cv_results_["mean_test_score"], b.cv_results_["mean_test_score"])
+    c = GridSearchFarm(LogisticRegression(max_iter=200), grid, cv=3, scoring="accuracy", refit=False, backend="inline",
+                       resume_file=journal).fit(X, y)
+    assert c.n_resumed_ == 9 and c.best_params_ == a.best_params_
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package may import it."""
+    import re
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sign-language-nlp_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(root, f)
