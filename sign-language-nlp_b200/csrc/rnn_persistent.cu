@@ -29,7 +29,8 @@ constexpr int PN = 16;    // MMA N (the smallest N of an M = 128 instruction)
 // batches run 4 sequences per CTA (26 CTAs at B = 50) and large ones 16 (fewer W_hh loads, fewer waves).
 constexpr int PTHREADS = 512;  // 16 warps: TMEM lane quadrant = warp % 4, column group = warp / 4
 constexpr int NACC = 4;        // BPTT: partial accumulators (independent MMA chains)
-constexpr int A_COL0 = 64;     // TMEM: accumulators in columns [0, 64), the resident W_hh operand from 64 on
+constexpr int FACC = 2;        // forward: partial accumulators per gate tile (two independent MMA chains)
+constexpr int A_COL0 = 128;    // TMEM: accumulators in columns [0, 128), the resident W_hh operand from 128 on
 constexpr int TMEM_COLS = 512; // 64 + up to 256 operand columns -> the whole tensor memory of the SM
 
 struct PersistFwd {
@@ -182,8 +183,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
       for (int kk = 0; kk < H / 16; ++kk)
 #pragma unroll
         for (int g = 0; g < G; ++g)
-          umma_bf16_ts(tmem + g * PN, tmem + A_COL0 + g * 64 + kk * 8,
-                       descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk > 0 ? 1u : 0u);
+          umma_bf16_ts(tmem + (g * FACC + (kk % FACC)) * PN, tmem + A_COL0 + g * 64 + kk * 8,
+                       descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk >= FACC ? 1u : 0u);
       umma_commit(bar);
     }
     __syncwarp();
@@ -195,14 +196,19 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
-      uint32_t raw[G][PC];
+      uint32_t raw[G * FACC][PC];
 #pragma unroll
-      for (int g = 0; g < G; ++g) tmem_ldn_nowait<PC>(tmem_mine + g * PN, raw[g]);
+      for (int g = 0; g < G * FACC; ++g) tmem_ldn_nowait<PC>(tmem_mine + g * PN, raw[g]);
       tmem_wait_ld();
 #pragma unroll
       for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int c = 0; c < PC; ++c) acc[g][c] = __uint_as_float(raw[g][c]);
+        for (int c = 0; c < PC; ++c) {
+          float a = 0.f;
+#pragma unroll
+          for (int q = 0; q < FACC; ++q) a += __uint_as_float(raw[g * FACC + q][c]);
+          acc[g][c] = a;
+        }
     } else {
 #pragma unroll
       for (int g = 0; g < G; ++g)
