@@ -272,20 +272,22 @@ struct TcBwd {
 // grid (H/32, ceil(B/128), ndir), block 192.  mapG: gates as [T][B][ndir*G*H]; mapS: stash as
 // [T][B][ndir*H] (GRU: the d(W_hn h) part of the reduction range lives there); mapW: w_hh as
 // [ndir][G*H (j)][H (k)] read MN-major, box {32 k, 32 j}.
-template <int G, int B_STAGES, int AROWS>
+// NCH = 32-unit output chunks per CTA: 1 at small batch (more CTAs share the W_hh stream), 4 at large
+// batch (the dG tile, re-read by every unit tile of the same sequences, is fetched 4x less often)
+template <int G, int B_STAGES, int AROWS, int NCH>
 __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapG,
                                                                     const __grid_constant__ CUtensorMap mapS,
                                                                     const __grid_constant__ CUtensorMap mapW, TcBwd p) {
   extern __shared__ uint8_t smem_dyn[];
-  constexpr int SA_STAGE = AROWS * SK * 4, B_STAGE = SU * SK * 4;   // B: one {32 k, 32 j} box
+  constexpr int SA_STAGE = AROWS * SK * 4, B_STAGE = NCH * SU * SK * 4;   // B: NCH {32 k, 32 j} boxes
   const int warp = warp_uniform(), lane = threadIdx.x & 31;
   const int H = p.H, B = p.B, T = p.T, GH = G * p.H;
-  const int d = blockIdx.z, u0 = blockIdx.x * SU, b0 = blockIdx.y * SB;
+  const int d = blockIdx.z, u0 = blockIdx.x * SU * NCH, b0 = blockIdx.y * SB;
   const int t = p.final_only ? (d == 0 ? -1 : T) : (d == 0 ? T - 1 - p.step : p.step);
   const int tn = d == 0 ? t + 1 : t - 1;   // the step processed just before this one
   const bool has_next = tn >= 0 && tn < T;
   const int nk = has_next ? GH / SK : 0;
-  Ring r = ring_setup<B_STAGES, SA_STAGE, B_STAGE, 32>(smem_dyn, warp, &mapG, &mapS, &mapW);
+  Ring r = ring_setup<B_STAGES, SA_STAGE, B_STAGE, NCH * SU>(smem_dyn, warp, &mapG, &mapS, &mapW);
 
   pdl_launch_dependents();
   if (warp == 0) {
@@ -297,7 +299,8 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
       const int first = nk < B_STAGES ? nk : B_STAGES;
       for (int i = 0; i < first; ++i) {
         mbar_expect_tx(&r.full[i], SA_STAGE + B_STAGE);
-        tma_load_3d(r.sB + i * B_STAGE, &mapW, &r.full[i], u0, i * SK, d);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tma_load_3d(r.sB + i * B_STAGE + c * 4096, &mapW, &r.full[i], u0 + c * SU, i * SK, d);
       }
       pdl_wait();   // dG of the step processed just before must be complete in HBM
       for (int i = 0; i < first; ++i) load_a(i, i * SK);
@@ -306,11 +309,12 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
         mbar_wait(&r.empty[s], (uint32_t)(i / B_STAGES - 1) & 1u);
         mbar_expect_tx(&r.full[s], SA_STAGE + B_STAGE);
         load_a(s, j0);
-        tma_load_3d(r.sB + s * B_STAGE, &mapW, &r.full[s], u0, j0, d);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tma_load_3d(r.sB + s * B_STAGE + c * 4096, &mapW, &r.full[s], u0 + c * SU, j0, d);
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_tf32(SB, SU, 0, 1);
+    constexpr uint32_t idesc = make_idesc_tf32(SB, NCH * SU, 0, 1);
     const uint64_t dA = make_desc_sw128(smem_u32(r.sA), 16, 1024, 2), dB = make_desc_sw128(smem_u32(r.sB), 4096, 512, 1);
     for (int i = 0; i < nk; ++i) {
       const int s = i % B_STAGES;
@@ -328,16 +332,18 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
     }
   } else {
     pdl_wait();
+    for (int ch = 0; ch < NCH; ++ch) {
+    const int ub = u0 + ch * SU;
     const int q = warp & 3, uh = ((warp - 2) >> 2) * SUH;
     const int b = b0 + q * 32 + lane;
     const bool valid = b < B;
     const int bb = valid ? b : 0;
     const int len = (valid && p.lengths) ? (int)p.lengths[b] : T;
-    const int64_t cidx = ((int64_t)d * B + bb) * H + u0 + uh;
+    const int64_t cidx = ((int64_t)d * B + bb) * H + ub + uh;
     const int tt = p.final_only ? 0 : t;
     const int64_t row = ((int64_t)tt * B + bb) * p.ndir + d;
-    float* gt = p.gates + row * GH + u0 + uh;
-    float* st = p.stash + row * H + u0 + uh;
+    float* gt = p.gates + row * GH + ub + uh;
+    float* st = p.stash + row * H + ub + uh;
     const int tp = d == 0 ? t - 1 : t + 1;   // forward-time predecessor
     const bool has_prev = tp >= 0 && tp < T;
     const bool inject = d == 0 ? t == len - 1 : t == 0;
@@ -347,10 +353,10 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
     {
       const float* pp = nullptr;
       if (live) {
-        if (G == 4) pp = has_prev ? p.stash + (((int64_t)tp * B + b) * p.ndir + d) * H + u0 + uh : (p.c0 ? p.c0 + cidx : nullptr);
-        else pp = has_prev ? p.out + ((int64_t)tp * B + b) * p.ndir * H + (int64_t)d * H + u0 + uh : (p.h0 ? p.h0 + cidx : nullptr);
+        if (G == 4) pp = has_prev ? p.stash + (((int64_t)tp * B + b) * p.ndir + d) * H + ub + uh : (p.c0 ? p.c0 + cidx : nullptr);
+        else pp = has_prev ? p.out + ((int64_t)tp * B + b) * p.ndir * H + (int64_t)d * H + ub + uh : (p.h0 ? p.h0 + cidx : nullptr);
       }
-      const float* dop = (live && p.dout) ? p.dout + ((int64_t)t * B + b) * p.ndir * H + (int64_t)d * H + u0 + uh : nullptr;
+      const float* dop = (live && p.dout) ? p.dout + ((int64_t)t * B + b) * p.ndir * H + (int64_t)d * H + ub + uh : nullptr;
 #pragma unroll
       for (int c = 0; c < SUH; c += 8) {
         float tmp[8];
@@ -393,7 +399,7 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
         }
       }
     }
-    if (nk > 0) {
+    if (nk > 0 && ch == 0) {
       mbar_wait(r.acc_full, 0);
       tc_fence_after();
     }
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
     for (int c = 0; c < SUH; c += 8) {
       float m[8];
       if (nk > 0) {
-        tmem_ld8(r.tmem + ((uint32_t)(q * 32) << 16) + uh + c, m);
+        tmem_ld8(r.tmem + ((uint32_t)(q * 32) << 16) + ch * SU + uh + c, m);
       } else {
 #pragma unroll
         for (int x = 0; x < 8; ++x) m[x] = 0.f;
@@ -460,10 +466,11 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
       if (G == 3) st8(st + c, dst);
       st8(p.carry + cidx + c, oc);
     }
+  }   // chunk loop
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(r.tmem, 32);
+  if (warp == 1) tmem_dealloc(r.tmem, NCH * SU);
 }
 
 static bool step_tc_supported(int B, int H, const void* a, const void* b, const void* c) {
@@ -525,12 +532,14 @@ int rnn_layer_bwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
   if (!tensor_map3(stash, (uint64_t)ndir * H, B, T, (uint64_t)ndir * H, (uint64_t)B * ndir * H, arows, false, &mapS)) return -1;
   if (!tensor_map3(w_hh, H, (uint64_t)G * H, ndir, H, (uint64_t)G * H * H, SK, true, &mapW)) return -1;
   TcBwd p{T, B, H, ndir, 0, 0, gates, stash, out, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0, carry};
-  dim3 grid(H / SU, ceil_div(B, SB), ndir);
+  // large batch: 128 output units per CTA, as long as the wide grid still fills the GPU
+  const bool wide = H % (4 * SU) == 0 && ceil_div(B, SB) * (H / (4 * SU)) * ndir >= (sm_count() > 0 ? sm_count() : 148);
+  dim3 grid(H / (wide ? 4 * SU : SU), ceil_div(B, SB), ndir);
   // `carry` needs no initialisation: a sequence's entry is written at its injection step (t = len-1
   // or 0) before any step consumes it
   int n = T;
   auto run = [&](auto kernel, int stages, int arows) {
-    const size_t sm = (size_t)stages * (arows * SK * 4 + SU * SK * 4) + (2 * stages + 1) * 8 + 16 + 1024;
+    const size_t sm = (size_t)stages * (arows * SK * 4 + (wide ? 4 : 1) * SU * SK * 4) + (2 * stages + 1) * 8 + 16 + 1024;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     for (int step = 0; step < T; ++step) {
       p.step = step;
@@ -543,9 +552,11 @@ int rnn_layer_bwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
     }
   };
   if (small) {
-    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 16, 64>, 16, 64); else run(rnn_step_bwd_tc_kernel<3, 16, 64>, 16, 64);
+    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 16, 64, 1>, 16, 64); else run(rnn_step_bwd_tc_kernel<3, 16, 64, 1>, 16, 64);
+  } else if (wide) {
+    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 6, 128, 4>, 6, 128); else run(rnn_step_bwd_tc_kernel<3, 6, 128, 4>, 6, 128);
   } else {
-    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 8, 128>, 8, 128); else run(rnn_step_bwd_tc_kernel<3, 8, 128>, 8, 128);
+    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 8, 128, 1>, 8, 128); else run(rnn_step_bwd_tc_kernel<3, 8, 128, 1>, 8, 128);
   }
   note_launches(n);
   cudaError_t e = cudaGetLastError();
