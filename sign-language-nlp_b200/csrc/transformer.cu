@@ -56,12 +56,29 @@ __device__ __forceinline__ float half_warp_sum(float v) {
 template <int N>
 __device__ __forceinline__ void load_tile(float* s, const float* g, int ld, int r0, int rows, int dh, float mul) {
   const int st = dh + 1;
-  for (int e = threadIdx.x; e < N * (dh >> 2); e += blockDim.x) {
-    const int r = e / (dh >> 2), c4 = (e % (dh >> 2)) << 2;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r0 + r < rows) v = *reinterpret_cast<const float4*>(g + (int64_t)(r0 + r) * ld + c4);
-    float* d = s + r * st + c4;
-    d[0] = v.x * mul; d[1] = v.y * mul; d[2] = v.z * mul; d[3] = v.w * mul;
+  const int total = N * (dh >> 2);
+  // four 16-byte global loads in flight per thread before the first shared store (one L2 round trip
+  // per batch instead of one per element)
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * blockDim.x;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < total) {
+        const int r = e / (dh >> 2), c4 = (e % (dh >> 2)) << 2;
+        if (r0 + r < rows) v[u] = *reinterpret_cast<const float4*>(g + (int64_t)(r0 + r) * ld + c4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * blockDim.x;
+      if (e < total) {
+        const int r = e / (dh >> 2), c4 = (e % (dh >> 2)) << 2;
+        float* d = s + r * st + c4;
+        d[0] = v[u].x * mul; d[1] = v[u].y * mul; d[2] = v[u].z * mul; d[3] = v[u].w * mul;
+      }
+    }
   }
 }
 
@@ -105,7 +122,7 @@ __device__ __forceinline__ float drop_factor(const MhaArgs& p, uint64_t seed, ui
 
 // grid (ceil(Sq/N), nhead, B), block 256.  smem: Q, K, V tiles [N][dh+1] + P [N][N+1].
 template <int RPT, int NDC>
-__global__ void __launch_bounds__(256) mha_fwd_kernel(MhaArgs p) {
+__global__ void __launch_bounds__(256, (NDC <= 4 ? 3 : 1)) mha_fwd_kernel(MhaArgs p) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int N = Tile<RPT>::N;
