@@ -2,8 +2,13 @@
 """Headline benchmark: training sequences/s of one fit of the reference's
 EncoderDecoderLSTMAttn on one B200, next to the reference's CPU path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1|cfg2|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1|cfg2|cfg3|cfg4|cfg5] [--precision bf16|fp32]
     python bench.py --impl reference ...        # the reference's CPU path (oracle port)
+
+cfg1 (default) = BASELINE.json configs[0], the configuration the metric is quoted on; cfg2 = GRU
+512/256/4; cfg3 = Transformer 512/256/4/h8; cfg4 = LSTM 1024/512/6 at batch 4096 (``--dp`` splits it
+over the ranks with an NCCL gradient all-reduce); cfg5 = the LSTM hyper-parameter grid farmed over
+the GPUs (fits/hour).
 
 A "step" is one skorch-equivalent training step (forward, CrossEntropyLoss on the
 log-probs, backward, global-norm clip 0.5, SGD momentum 0.9) on one batch of synthetic
