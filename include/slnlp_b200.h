@@ -92,6 +92,10 @@ int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K,
 int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
                      slnlp_stream_t stream);
 
+/* diagnostic: clusters of the cluster-persistent recurrent kernel (H = 256: 8 CTAs, H = 512: 16 CTAs)
+ * the device holds at once, or -1 */
+int slnlp_max_active_clusters(int H, int nseq);
+
 /* ---- K4/K8: one (bi)directional recurrent layer over all timesteps (nn.LSTM / nn.GRU
  * on a packed sequence, bkp:95-100,110-123; decoder step bkp:215-216 with T=1).
  * gates [T,B,ndir,G,H]: in = x W_ih^T + b_ih; out = activated gates (stash for bwd).

@@ -532,10 +532,17 @@ static bool cluster_shape_ok(int H, int B, const void* w_hh) {
 
 // sequences per cluster: as few as keeps every cluster of the layer resident at once (16-CTA clusters
 // fit one per GPC, 8-CTA clusters two: a second wave would double the layer time)
+extern "C" int slnlp_max_active_clusters(int H, int nseq);
 static int cluster_nseq(int H, int B) {
-  const int max_clusters = H == 256 ? 14 : 6;
-  for (int nseq : {8, 16, 32})
-    if (ceil_div(B, nseq) * 2 <= max_clusters) return nseq;
+  // measured on B200: 15 clusters of 8 CTAs, 7 clusters of 16 CTAs (cudaOccupancyMaxActiveClusters)
+  static int cap256 = 0, cap512 = 0;
+  int& cap = H == 256 ? cap256 : cap512;
+  if (cap == 0) {
+    cap = slnlp_max_active_clusters(H, 16);
+    if (cap <= 0) cap = H == 256 ? 14 : 6;
+  }
+  for (int nseq : {8, 16, 24, 32})
+    if (ceil_div(B, nseq) * 2 <= cap) return nseq;
   return 32;
 }
 
@@ -561,8 +568,11 @@ int rnn_layer_fwd_cluster(int mode, int T, int B, int H, int ndir, float* gates,
     if (prep_cluster_kernel(rnn_cluster_fwd_kernel<GG, NS>, C, sm)) return -1;      \
     e = launch_cluster(rnn_cluster_fwd_kernel<GG, NS>, grid, C, sm, s, &p, sizeof(p)); \
   } while (0)
-  if (mode == SLNLP_MODE_LSTM) { if (nseq == 8) SLNLP_GO(4, 8); else if (nseq == 16) SLNLP_GO(4, 16); else SLNLP_GO(4, 32); }
-  else { if (nseq == 8) SLNLP_GO(3, 8); else if (nseq == 16) SLNLP_GO(3, 16); else SLNLP_GO(3, 32); }
+  if (mode == SLNLP_MODE_LSTM) {
+    if (nseq == 8) SLNLP_GO(4, 8); else if (nseq == 16) SLNLP_GO(4, 16); else if (nseq == 24) SLNLP_GO(4, 24); else SLNLP_GO(4, 32);
+  } else {
+    if (nseq == 8) SLNLP_GO(3, 8); else if (nseq == 16) SLNLP_GO(3, 16); else if (nseq == 24) SLNLP_GO(3, 24); else SLNLP_GO(3, 32);
+  }
 #undef SLNLP_GO
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -587,8 +597,11 @@ int rnn_layer_bwd_cluster(int mode, int T, int B, int H, int ndir, float* gates,
     if (prep_cluster_kernel(rnn_cluster_bwd_kernel<GG, NS>, C, sm)) return -1;      \
     e = launch_cluster(rnn_cluster_bwd_kernel<GG, NS>, grid, C, sm, s, &p, sizeof(p)); \
   } while (0)
-  if (mode == SLNLP_MODE_LSTM) { if (nseq == 8) SLNLP_GO(4, 8); else if (nseq == 16) SLNLP_GO(4, 16); else SLNLP_GO(4, 32); }
-  else { if (nseq == 8) SLNLP_GO(3, 8); else if (nseq == 16) SLNLP_GO(3, 16); else SLNLP_GO(3, 32); }
+  if (mode == SLNLP_MODE_LSTM) {
+    if (nseq == 8) SLNLP_GO(4, 8); else if (nseq == 16) SLNLP_GO(4, 16); else if (nseq == 24) SLNLP_GO(4, 24); else SLNLP_GO(4, 32);
+  } else {
+    if (nseq == 8) SLNLP_GO(3, 8); else if (nseq == 16) SLNLP_GO(3, 16); else if (nseq == 24) SLNLP_GO(3, 24); else SLNLP_GO(3, 32);
+  }
 #undef SLNLP_GO
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -599,3 +612,35 @@ int rnn_layer_bwd_cluster(int mode, int T, int B, int H, int ndir, float* gates,
 }
 
 }  // namespace slnlp
+
+// how many clusters of the forward kernel the device can hold at once (diagnostic; used by
+// profiles/ scripts and by cluster_nseq's constants).  H = 256 -> 8-CTA clusters, 512 -> 16-CTA.
+extern "C" int slnlp_max_active_clusters(int H, int nseq) {
+  using namespace slnlp;
+  const int C = H / CU, cn = nseq <= 16 ? 16 : 32;
+  const size_t sm = 2 * (size_t)cn * H * 2 + (size_t)nseq * 4 * 32 * 4 + (size_t)nseq * 32 * 2 + 64;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C, 64, 2);
+  cfg.blockDim = dim3(CT);
+  cfg.dynamicSmemBytes = sm;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  auto q = [&](auto kernel) {
+    if (prep_cluster_kernel(kernel, C, sm)) return;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = -1;
+    }
+  };
+  if (nseq == 8) q(rnn_cluster_fwd_kernel<4, 8>);
+  else if (nseq == 16) q(rnn_cluster_fwd_kernel<4, 16>);
+  else q(rnn_cluster_fwd_kernel<4, 32>);
+  return n;
+}
+

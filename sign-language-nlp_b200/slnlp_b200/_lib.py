@@ -26,6 +26,7 @@ SIGNATURES = {
     "slnlp_last_error_string": [],
     "slnlp_device_sm_count": [],
     "slnlp_launch_count": [],
+    "slnlp_max_active_clusters": [I, I],
     "slnlp_embed_gather_fwd": [P, P, P, I, I, I, P, P, P, I, F, P, P],
     "slnlp_embed_gather_bwd": [P, P, P, I, I, I, P, P, P, I, F, L, P],
     "slnlp_gemm_f32": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],

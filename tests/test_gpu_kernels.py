@@ -405,7 +405,7 @@ def test_pad_fill_concat_dirs_dec_input():
 @pytest.mark.parametrize("mode", ["lstm", "gru"])
 @pytest.mark.parametrize("T,B,ragged,H", [(64, 50, False, 128), (17, 50, True, 128), (5, 3, True, 128), (9, 16, True, 128),
                                           (1, 20, False, 128), (17, 50, True, 256), (9, 16, True, 64), (5, 150, True, 512),
-                                          (64, 50, False, 256), (3, 700, True, 128), (3, 300, True, 256), (2, 300, True, 512), (2, 2400, True, 512)])
+                                          (64, 50, False, 256), (3, 700, True, 128), (3, 300, True, 256), (2, 300, True, 512), (2, 2400, True, 512), (6, 50, True, 512), (5, 30, True, 512)])
 def test_rnn_layer_tcgen05_path(mode, T, B, ragged, H):
     """precision=1: the persistent W_hh-resident tcgen05 kernel (H = 128: bf16 operands, fp32
     accumulation) and the per-step TMA + kind::tf32 kernels (any other H % 32 == 0).  north_star
