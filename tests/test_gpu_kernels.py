@@ -469,11 +469,12 @@ def test_rnn_layer_tcgen05_path(mode, T, B, ragged, H):
 
 
 @pytest.mark.parametrize("mode", ["lstm", "gru"])
-def test_rnn_tcgen05_single_step_initial_state(mode):
-    """tcgen05 path with h0/c0 and gradients to the initial state (T = 1)."""
+@pytest.mark.parametrize("B,H", [(50, 128), (50, 256), (200, 96)])
+def test_rnn_tcgen05_single_step_initial_state(mode, B, H):
+    """tensor-core paths with h0/c0 and gradients to the initial state (T = 1): the persistent kernel
+    (H = 128) and the per-step TMA kernels (the cluster kernels do not take an initial state)."""
     from helpers import BF16_RTOL
     L = _lib()
-    B, H = 50, 128
     G = 4 if mode == "lstm" else 3
     md = 0 if mode == "lstm" else 1
     g = torch.Generator().manual_seed(321)
