@@ -35,3 +35,11 @@ print(f"{wl} {prec}: sum of kernel time per step {tot / N:.1f} us")
 print(f"{'us/step':>9} {'n/step':>7} {'avg us':>8} {'share':>6}  kernel")
 for k, n, t in sorted(rows, key=lambda r: -r[2])[:28]:
     print(f"{t / N:9.1f} {n / N:7.1f} {t / n:8.2f} {100 * t / tot:5.1f}%  {k[:90]}")
+if os.environ.get("SLNLP_PROF_EVENTS"):
+    # individual launches of one kernel family, in launch order, for the last step
+    pat = os.environ["SLNLP_PROF_EVENTS"]
+    evs = [e for e in prof.events() if pat in e.name and e.device_time_total > 0]
+    per_step = len(evs) // N
+    print(f"last step, {per_step} launches matching {pat!r}:")
+    for e in evs[-per_step:]:
+        print(f"  {e.device_time_total:8.2f} us  {e.name[:100]}")

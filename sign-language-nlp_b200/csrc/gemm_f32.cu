@@ -80,6 +80,19 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K,
     }
   }
 
+  // read-modify-write epilogue: issue every load of the old C before the first store so the
+  // loads overlap instead of serialising behind possibly-aliasing stores
+  if (beta != 0.f) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (m < M && n < N) acc[i][j] += beta * C[(int64_t)m * ldc + n];
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
@@ -90,9 +103,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K,
       if (n >= N) continue;
       float v = acc[i][j];
       if (bias) v += bias[n];
-      float* c = C + (int64_t)m * ldc + n;
-      if (beta != 0.f) v += beta * *c;
-      *c = v;
+      C[(int64_t)m * ldc + n] = v;
     }
   }
 }
@@ -204,6 +215,17 @@ __global__ void __launch_bounds__(256) gemm_f32_vec_kernel(int M, int N, int Kfu
     }
     return;
   }
+  if (beta != 0.f) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + ty * 8 + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (m < M && n < N) acc[i][j] += beta * C[(int64_t)m * ldc + n];
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + ty * 8 + i;
@@ -214,9 +236,7 @@ __global__ void __launch_bounds__(256) gemm_f32_vec_kernel(int M, int N, int Kfu
       if (n >= N) continue;
       float v = acc[i][j];
       if (bias) v += bias[n];
-      float* c = C + (int64_t)m * ldc + n;
-      if (beta != 0.f) v += beta * *c;
-      *c = v;
+      C[(int64_t)m * ldc + n] = v;
     }
   }
 }

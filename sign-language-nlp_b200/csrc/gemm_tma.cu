@@ -148,24 +148,39 @@ __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_cons
       bv[j] = (bias && !P && n < N) ? bias[n] : 0.f;
     }
     const int mrow0 = m0 + q * 32;
-#pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      const int m = mrow0 + r;
-      if (m >= M) break;
+    const bool rmw = !P && !atomic_out && beta != 0.f;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+      // beta * C is fetched for 8 rows at once BEFORE any store of the group: interleaving a load of
+      // C with every store serialises on the possible aliasing and costs a round trip per row
+      float cold[8][BN / 32];
+      if (rmw) {
 #pragma unroll
-      for (int j = 0; j < BN / 32; ++j) {
-        const int n = n0 + lane + 32 * j;
-        if (n >= N) continue;
-        const float acc = stage[r * SLD + lane + 32 * j];
-        if (P) {
-          P[(int64_t)m * N + n] = acc;
-        } else if (atomic_out) {
-          atomicAdd(C + (int64_t)m * ldc + n, acc);   // split-K of a C += A B accumulation: red.global.add
-        } else {
-          float* c = C + (int64_t)m * ldc + n;
-          float o = acc + bv[j];
-          if (beta != 0.f) o += beta * *c;
-          *c = o;
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) {
+            const int m = mrow0 + r0 + r, n = n0 + lane + 32 * j;
+            cold[r][j] = (m < M && n < N) ? C[(int64_t)m * ldc + n] : 0.f;
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int m = mrow0 + r0 + r;
+        if (m >= M) break;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          const int n = n0 + lane + 32 * j;
+          if (n >= N) continue;
+          const float acc = stage[(r0 + r) * SLD + lane + 32 * j];
+          if (P) {
+            P[(int64_t)m * N + n] = acc;
+          } else if (atomic_out) {
+            atomicAdd(C + (int64_t)m * ldc + n, acc);   // split-K of a C += A B accumulation: red.global.add
+          } else {
+            float o = acc + bv[j];
+            if (rmw) o += beta * cold[r][j];
+            C[(int64_t)m * ldc + n] = o;
+          }
         }
       }
     }
