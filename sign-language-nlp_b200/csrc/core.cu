@@ -466,25 +466,28 @@ __global__ void __launch_bounds__(256) dec_input_bwd_kernel(const float* __restr
     for (int b = 0; b < B; ++b) dsrc[(int64_t)b * W + e - E] = ddst[(int64_t)b * (E + W) + e];
   }
 }
-// out[c] = beta*out[c] + sum_r A[r,c]; 32 columns per CTA, 32 warps stride the rows, fixed
-// combination order (deterministic)
+// out[c] = beta*out[c] + sum_r A[r,c]; 32 columns per CTA, 32 warps stride the rows of the CTA's
+// row chunk, fixed combination order inside a CTA.  gridDim.y > 1 (beta == 1 only): every row chunk
+// adds its partial sum with red.global.add, so that a tall matrix is read by the whole GPU instead
+// of cols/32 SMs.
 __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ A, int rows, int cols,
-                                                      int lda, float* __restrict__ out, float beta) {
+                                                      int lda, float* __restrict__ out, float beta, int chunk) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float sm[32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
+  const int r_end = min(rows, (int)(blockIdx.y + 1) * chunk);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (c < cols) {
-    int r = w;
-    for (; r + 96 < rows; r += 128) {
+    int r = blockIdx.y * chunk + w;
+    for (; r + 96 < r_end; r += 128) {
       s0 += A[(int64_t)r * lda + c];
       s1 += A[(int64_t)(r + 32) * lda + c];
       s2 += A[(int64_t)(r + 64) * lda + c];
       s3 += A[(int64_t)(r + 96) * lda + c];
     }
-    for (; r < rows; r += 32) s0 += A[(int64_t)r * lda + c];
+    for (; r < r_end; r += 32) s0 += A[(int64_t)r * lda + c];
   }
   sm[w][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
@@ -492,7 +495,8 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) t += sm[i][lane];
-    out[c] = (beta == 0.f ? 0.f : beta * out[c]) + t;
+    if (gridDim.y > 1) atomicAdd(out + c, t);
+    else out[c] = (beta == 0.f ? 0.f : beta * out[c]) + t;
   }
 }
 
@@ -551,7 +555,24 @@ int slnlp_embed_gather_bwd(float* dtable, const int64_t* idx, const float* dout,
 int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
                      slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(A && out && rows >= 0 && cols > 0 && lda >= cols, "colsum: bad arguments");
-  launch_pdl(colsum_kernel, dim3(ceil_div(cols, 32)), dim3(1024), 0, as_stream(stream), A, rows, cols, lda, out, beta);
+  // tall gradient reductions (out += colsum): split the rows over ~2 CTAs per SM.  The fp32 order of
+  // the chunk sums then varies (~1e-7 relative); SLNLP_SPLITK_ATOMIC=0 keeps the single-pass form.
+  static int use_atomic = -1;
+  if (use_atomic < 0) {
+    const char* e = getenv("SLNLP_SPLITK_ATOMIC");
+    use_atomic = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int cb = ceil_div(cols, 32);
+  int splits = 1;
+  if (use_atomic && beta == 1.f && rows >= 512) {
+    splits = ceil_div(2 * sm_count(), cb);
+    const int max_splits = rows / 128;   // at least 4 rows per warp
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  const int chunk = ceil_div(rows > 0 ? rows : 1, splits);
+  splits = ceil_div(rows > 0 ? rows : 1, chunk);
+  launch_pdl(colsum_kernel, dim3(cb, splits), dim3(1024), 0, as_stream(stream), A, rows, cols, lda, out, beta, chunk);
   SLNLP_LAUNCH_OK("colsum");
   return 0;
 }

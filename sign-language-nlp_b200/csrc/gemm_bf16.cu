@@ -155,22 +155,30 @@ __global__ void __launch_bounds__(GT) gemm_bf16_kernel(int M, int N, int Kfull, 
     bv[j] = (bias && !P && n < N) ? bias[n] : 0.f;
   }
   const int mrow0 = m0 + warp * 32;
-#pragma unroll 4
-  for (int r = 0; r < 32; ++r) {
-    const int m = mrow0 + r;
-    if (m >= M) break;
+  // old C for 8 rows is loaded before any of their stores: interleaved load/store pairs
+  // serialise on the load latency (3x slower for beta != 0)
+  const bool rmw = !P && beta != 0.f;
+#pragma unroll 1
+  for (int r0 = 0; r0 < 32; r0 += 8) {
+    float cold[8][TN / 32];
 #pragma unroll
-    for (int j = 0; j < TN / 32; ++j) {
-      const int n = n0 + lane + 32 * j;
-      if (n >= N) continue;
-      const float acc = stage[r * SLD + lane + 32 * j];
-      if (P) {
-        P[(int64_t)m * N + n] = acc;
-      } else {
-        float* c = C + (int64_t)m * ldc + n;
-        float o = acc + bv[j];
-        if (beta != 0.f) o += beta * *c;
-        *c = o;
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int j = 0; j < TN / 32; ++j) {
+        const int m = mrow0 + r0 + r, n = n0 + lane + 32 * j;
+        cold[r][j] = (rmw && m < M && n < N) ? C[(int64_t)m * ldc + n] : 0.f;
+      }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int m = mrow0 + r0 + r;
+      if (m >= M) break;
+#pragma unroll
+      for (int j = 0; j < TN / 32; ++j) {
+        const int n = n0 + lane + 32 * j;
+        if (n >= N) continue;
+        const float acc = stage[(r0 + r) * SLD + lane + 32 * j];
+        if (P) P[(int64_t)m * N + n] = acc;
+        else C[(int64_t)m * ldc + n] = acc + bv[j] + beta * cold[r][j];
       }
     }
   }

@@ -7,6 +7,7 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Sequence, Tuple
 
+import contextlib
 import torch
 import torch.nn as nn
 
@@ -186,6 +187,12 @@ class FlatParamModule(nn.Module):
         ev.record()
         side.wait_event(ev)
         return side
+
+    @contextlib.contextmanager
+    def _side_branch(self):
+        """Kernels launched inside run on the side stream, ordered after everything issued so far."""
+        with torch.cuda.stream(self._fork_side()):
+            yield
 
     def _join_side(self):
         side = getattr(self, "_side", None)

@@ -62,6 +62,8 @@ class RnnEncDecB200(FlatParamModule):
         # cluster kernels fill the GPU (H = 256: -1 % on cfg2).  SLNLP_OVERLAP_DW=0/1 overrides.
         env = os.environ.get("SLNLP_OVERLAP_DW")
         self.overlap_dw = (self.H == 128) if env is None else env != "0"
+        # the small decoder / generator / attention / bridge weight gradients always leave the chain
+        self.overlap_small = os.environ.get("SLNLP_OVERLAP_SMALL", "1") != "0"
         self._build_parameters()
         self.seed = int(kwargs.get("seed", torch.initial_seed() & 0x7FFFFFFF))
 
@@ -196,9 +198,13 @@ class RnnEncDecB200(FlatParamModule):
         drop = ws.train and self.p_rnn > 0.0
         rng = self._rng_state().data_ptr() if drop else None
         GH = G * H
+        # Weight gradients are leaves of the dependency graph: each is issued on the side stream as
+        # soon as its operands exist, so that the main stream carries only the d(activation) chain.
+        small = self._side_branch if self.overlap_small else contextlib.nullcontext
         # generator
-        self._gemm(1, 0, V, H, B, ws.dlogits.data_ptr(), ws.Vp, ws.dec_h[L - 1].data_ptr(), H,
-                   gp("model.generator.proj.weight"), H, None, 1.0)
+        with small():
+            self._gemm(1, 0, V, H, B, ws.dlogits.data_ptr(), ws.Vp, ws.dec_h[L - 1].data_ptr(), H,
+                       gp("model.generator.proj.weight"), H, None, 1.0)
         self._gemm(0, 0, B, H, V, ws.dlogits.data_ptr(), ws.Vp, self._ptr("model.generator.proj.weight"), H,
                    ws.d_h.data_ptr(), H)
         # decoder cells, top down
@@ -215,19 +221,21 @@ class RnnEncDecB200(FlatParamModule):
             if mode == 0:  # LSTM: c0 = h0 = hidden0 (bkp:278-279)
                 check(lib.slnlp_axpy(ws.d_hidden0[l].data_ptr(), ws.d_c0.data_ptr(), 1.0, B * H, s), "axpy")
             xin = ws.dec_xin[l].data_ptr()
-            self._gemm(1, 0, GH, D, B, dg, GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0)
-            check(lib.slnlp_colsum_f32(dg, B, GH, GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
-            if mode == 0:
-                self._gemm(1, 0, GH, H, B, dg, GH, h0, H, gp(f"{pre}weight_hh_l{l}"), H, None, 1.0)
-                # LSTM: d b_hh == d b_ih (both add to the same pre-activation)
-                check(lib.slnlp_axpy(gp(f"{pre}bias_hh_l{l}"), gp(f"{pre}bias_ih_l{l}"), 1.0, GH, s), "axpy")
-            else:
-                self._gemm(1, 0, 2 * H, H, B, dg, GH, h0, H, gp(f"{pre}weight_hh_l{l}"), H, None, 1.0)
-                self._gemm(1, 0, H, H, B, dst, H, h0, H, gp(f"{pre}weight_hh_l{l}") + 4 * 2 * H * H, H, None, 1.0)
-                check(lib.slnlp_colsum_f32(dg, B, 2 * H, GH, gp(f"{pre}bias_hh_l{l}"), 1.0, s), "colsum")
-                check(lib.slnlp_colsum_f32(dst, B, H, H, gp(f"{pre}bias_hh_l{l}") + 4 * 2 * H, 1.0, s), "colsum")
             dx = ws.d_decx if l == 0 else ws.d_h
             self._gemm(0, 0, B, D, GH, dg, GH, self._ptr(f"{pre}weight_ih_l{l}"), D, dx.data_ptr(), D)
+            with small():
+                ss = _stream()
+                self._gemm(1, 0, GH, D, B, dg, GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0)
+                check(lib.slnlp_colsum_f32(dg, B, GH, GH, gp(f"{pre}bias_ih_l{l}"), 1.0, ss), "colsum")
+                if mode == 0:
+                    self._gemm(1, 0, GH, H, B, dg, GH, h0, H, gp(f"{pre}weight_hh_l{l}"), H, None, 1.0)
+                    # LSTM: d b_hh == d b_ih (both add to the same pre-activation)
+                    check(lib.slnlp_axpy(gp(f"{pre}bias_hh_l{l}"), gp(f"{pre}bias_ih_l{l}"), 1.0, GH, ss), "axpy")
+                else:
+                    self._gemm(1, 0, 2 * H, H, B, dg, GH, h0, H, gp(f"{pre}weight_hh_l{l}"), H, None, 1.0)
+                    self._gemm(1, 0, H, H, B, dst, H, h0, H, gp(f"{pre}weight_hh_l{l}") + 4 * 2 * H * H, H, None, 1.0)
+                    check(lib.slnlp_colsum_f32(dg, B, 2 * H, GH, gp(f"{pre}bias_hh_l{l}"), 1.0, ss), "colsum")
+                    check(lib.slnlp_colsum_f32(dst, B, H, H, gp(f"{pre}bias_hh_l{l}") + 4 * 2 * H, 1.0, ss), "colsum")
             if l > 0 and drop:
                 check(lib.slnlp_dropout(dx.data_ptr(), dx.data_ptr(), B * H, self.p_rnn, rng, 100 + l - 1, s),
                       "dropout")
@@ -244,23 +252,27 @@ class RnnEncDecB200(FlatParamModule):
                                       self._ptr(att + "energy_layer.weight"), enc_out.data_ptr(),
                                       ws.alpha.data_ptr(), T, B, H, 2 * H, ws.d_seq.data_ptr(), ws.d_pk.data_ptr(),
                                       ws.d_q.data_ptr(), ws.dv_part.data_ptr(), s), "attn_bwd")
-        check(lib.slnlp_colsum_f32(ws.dv_part.data_ptr(), B, H, H, gp(att + "energy_layer.weight"), 1.0, s), "colsum")
-        self._gemm(1, 0, H, H, B, ws.d_q.data_ptr(), H, ws.hidden0[L - 1].data_ptr(), H,
-                   gp(att + "query_layer.weight"), H, None, 1.0)
         self._gemm(0, 0, B, H, H, ws.d_q.data_ptr(), H, self._ptr(att + "query_layer.weight"), H,
                    ws.d_hidden0[L - 1].data_ptr(), H, None, 1.0)
-        self._gemm(1, 0, H, 2 * H, T * B, ws.d_pk.data_ptr(), H, enc_out.data_ptr(), 2 * H,
-                   gp(att + "key_layer.weight"), 2 * H, None, 1.0, big=True)
         self._gemm(0, 0, T * B, 2 * H, H, ws.d_pk.data_ptr(), H, self._ptr(att + "key_layer.weight"), 2 * H,
                    ws.d_seq.data_ptr(), 2 * H, None, 1.0, big=True)
         # bridge
         check(lib.slnlp_tanh_bwd(ws.d_hidden0.data_ptr(), ws.hidden0.data_ptr(), L * B * H, s), "tanh_bwd")
-        self._gemm(1, 0, H, 2 * H, L * B, ws.d_hidden0.data_ptr(), H, ws.enc_final.data_ptr(), 2 * H,
-                   gp("model.decoder.bridge.weight"), 2 * H, None, 1.0)
-        check(lib.slnlp_colsum_f32(ws.d_hidden0.data_ptr(), L * B, H, H, gp("model.decoder.bridge.bias"), 1.0, s),
-              "colsum")
         self._gemm(0, 0, L * B, 2 * H, H, ws.d_hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.weight"),
                    2 * H, ws.d_enc_final.data_ptr(), 2 * H)
+        with small():
+            ss = _stream()
+            check(lib.slnlp_colsum_f32(ws.dv_part.data_ptr(), B, H, H, gp(att + "energy_layer.weight"), 1.0, ss), "colsum")
+            self._gemm(1, 0, H, H, B, ws.d_q.data_ptr(), H, ws.hidden0[L - 1].data_ptr(), H,
+                       gp(att + "query_layer.weight"), H, None, 1.0)
+            self._gemm(1, 0, H, 2 * H, L * B, ws.d_hidden0.data_ptr(), H, ws.enc_final.data_ptr(), 2 * H,
+                       gp("model.decoder.bridge.weight"), 2 * H, None, 1.0)
+            check(lib.slnlp_colsum_f32(ws.d_hidden0.data_ptr(), L * B, H, H, gp("model.decoder.bridge.bias"), 1.0, ss),
+                  "colsum")
+        # the key-layer gradient reads enc_out with its 1.0 pad fill, which the next kernel removes:
+        # it stays on the main stream
+        self._gemm(1, 0, H, 2 * H, T * B, ws.d_pk.data_ptr(), H, enc_out.data_ptr(), 2 * H,
+                   gp(att + "key_layer.weight"), 2 * H, None, 1.0, big=True)
         # encoder BPTT, top down.  Padded rows of enc_out go back to 0 first (the 1.0
         # fill of pad_packed_sequence is a constant and must not enter dW_hh).
         check(lib.slnlp_pad_fill(enc_out.data_ptr(), lp, T, B, 2 * H, 0.0, s), "pad_unfill")
@@ -290,7 +302,7 @@ class RnnEncDecB200(FlatParamModule):
             side = self._fork_side() if self.overlap_dw else None
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 self._encoder_weight_grads(ws, l, gp, _stream())
-        if self.overlap_dw:
+        if self.overlap_dw or self.overlap_small:
             self._join_side()
 
     def _encoder_weight_grads(self, ws, l, gp, s):
