@@ -376,11 +376,162 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(MhaArgs p) {
   }
 }
 
+// ------------------------------------------------------------------ few-query attention
+// The reference's decoder sees ONE target position (the label, model/transformer.py:82-87), so its
+// self-attention is 1 x 1 and its cross-attention 1 x S: a 64-query tile would be 63/64 padding.
+// One warp per (sequence, head) walks the Sq <= MHA_SMALL_SQ query rows: lanes own keys for the
+// scores (float4 dot products over the head dimension), lanes own head columns for P.V and for the
+// gradients.  Same masks, dropout stream, log-sum-exp and all-masked-row NaN as the tile kernels.
+constexpr int MHA_SMALL_SQ = 4;
+constexpr int MHA_SMALL_SK = 1024;
+constexpr int MHA_SMALL_WARPS = 4;
+
+__device__ __forceinline__ float dot_row(const float* __restrict__ sv, const float* __restrict__ g, int dh) {
+  float a0 = 0.f, a1 = 0.f;
+  for (int d = 0; d < dh; d += 8) {
+    const float4 x = *reinterpret_cast<const float4*>(g + d);
+    a0 = fmaf(sv[d], x.x, a0); a0 = fmaf(sv[d + 1], x.y, a0); a0 = fmaf(sv[d + 2], x.z, a0); a0 = fmaf(sv[d + 3], x.w, a0);
+    if (d + 4 < dh) {
+      const float4 y = *reinterpret_cast<const float4*>(g + d + 4);
+      a1 = fmaf(sv[d + 4], y.x, a1); a1 = fmaf(sv[d + 5], y.y, a1); a1 = fmaf(sv[d + 6], y.z, a1); a1 = fmaf(sv[d + 7], y.w, a1);
+    }
+  }
+  return a0 + a1;
+}
+
+// smem per warp: q [dh] | dO [dh] (bwd) | p [Sk] | ds [Sk] (bwd)
+template <bool BWD>
+__global__ void __launch_bounds__(MHA_SMALL_WARPS * 32) mha_small_kernel(MhaArgs p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int bh = blockIdx.x * MHA_SMALL_WARPS + w;
+  if (bh >= p.B * p.nhead) return;
+  const int b = bh / p.nhead, h = bh % p.nhead, dh = p.dh;
+  const int per_warp = (BWD ? 2 : 1) * (dh + p.Sk);
+  float* sq = sm + w * per_warp;
+  float* sdo = sq + dh;                       // bwd only
+  float* sp = sq + (BWD ? 2 : 1) * dh;
+  float* sds = sp + p.Sk;                     // bwd only
+  const float* k = p.k + (int64_t)b * p.Sk * p.ldk + h * dh;
+  const float* v = p.v + (int64_t)b * p.Sk * p.ldv + h * dh;
+  const int64_t* ktok = p.key_tokens ? p.key_tokens + (int64_t)b * p.Sk : nullptr;
+  const bool drop = p.p_drop > 0.f;
+  const uint64_t seed = drop ? p.rng[0] : 0, step = drop ? p.rng[1] : 0;
+  for (int i = 0; i < p.Sq; ++i) {
+    const float* q = p.q + ((int64_t)b * p.Sq + i) * p.ldq + h * dh;
+    __syncwarp();
+    if (!BWD) {
+      for (int d = lane; d < dh; d += 32) sq[d] = q[d] * p.scale;
+      __syncwarp();
+      float mx = -INFINITY;
+      for (int j = lane; j < p.Sk; j += 32) {
+        float sc = dot_row(sq, k + (int64_t)j * p.ldk, dh);
+        if (masked(p, ktok, i, j)) sc = -INFINITY;
+        sp[j] = sc;
+        mx = fmaxf(mx, sc);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < p.Sk; j += 32) {
+        float e = mx == -INFINITY ? 0.f : expf(sp[j] - mx);
+        sum += e;
+        if (drop && e != 0.f) e *= drop_factor(p, seed, step, bh, i, j);
+        sp[j] = e;
+      }
+      const float l = warp_sum(sum);
+      const float inv = 1.f / l;   // every key masked: 0/0 = NaN, as torch's softmax of all -inf
+      __syncwarp();
+      float* o = p.o + ((int64_t)b * p.Sq + i) * p.ldo + h * dh;
+      for (int d = lane; d < dh; d += 32) {
+        float a0 = 0.f, a1 = 0.f;
+        int j = 0;
+        for (; j + 1 < p.Sk; j += 2) {
+          a0 = fmaf(sp[j], v[(int64_t)j * p.ldv + d], a0);
+          a1 = fmaf(sp[j + 1], v[(int64_t)(j + 1) * p.ldv + d], a1);
+        }
+        if (j < p.Sk) a0 = fmaf(sp[j], v[(int64_t)j * p.ldv + d], a0);
+        o[d] = (a0 + a1) * inv;
+      }
+      if (lane == 0) p.lse[(int64_t)bh * p.Sq + i] = mx + logf(l);
+    } else {
+      const float* dO = p.dout + ((int64_t)b * p.Sq + i) * p.ldo + h * dh;
+      const float* O = p.o + ((int64_t)b * p.Sq + i) * p.ldo + h * dh;
+      float dsum = 0.f;
+      for (int d = lane; d < dh; d += 32) {
+        const float g = dO[d];
+        sq[d] = q[d] * p.scale;
+        sdo[d] = g;
+        dsum = fmaf(g, O[d], dsum);
+      }
+      const float D = warp_sum(dsum);
+      const float L = p.lse[(int64_t)bh * p.Sq + i];
+      if (lane == 0) p.dvec[(int64_t)bh * p.Sq + i] = D;
+      __syncwarp();
+      for (int j = lane; j < p.Sk; j += 32) {
+        float pr = 0.f, dsc = 0.f;
+        if (!masked(p, ktok, i, j)) {
+          const float sc = dot_row(sq, k + (int64_t)j * p.ldk, dh);
+          const float dp = dot_row(sdo, v + (int64_t)j * p.ldv, dh);
+          pr = expf(sc - L);
+          float f = 1.f;
+          if (drop) f = drop_factor(p, seed, step, bh, i, j);
+          dsc = pr * (dp * f - D);
+          pr *= f;
+        }
+        sp[j] = pr;
+        sds[j] = dsc;
+      }
+      __syncwarp();
+      float* gq = p.dq + ((int64_t)b * p.Sq + i) * p.ldq + h * dh;
+      float* gk = p.dk + (int64_t)b * p.Sk * p.ldk + h * dh;
+      float* gv = p.dv + (int64_t)b * p.Sk * p.ldv + h * dh;
+      for (int d = lane; d < dh; d += 32) {
+        float a0 = 0.f, a1 = 0.f;
+        int j = 0;
+        for (; j + 1 < p.Sk; j += 2) {
+          a0 = fmaf(sds[j], k[(int64_t)j * p.ldk + d], a0);
+          a1 = fmaf(sds[j + 1], k[(int64_t)(j + 1) * p.ldk + d], a1);
+        }
+        if (j < p.Sk) a0 = fmaf(sds[j], k[(int64_t)j * p.ldk + d], a0);
+        gq[d] = (a0 + a1) * p.scale;
+        const float qd = sq[d], od = sdo[d];   // q carries the 1/sqrt(dh) scale
+        if (i == 0) {
+          for (j = 0; j < p.Sk; ++j) {
+            gk[(int64_t)j * p.ldk + d] = sds[j] * qd;
+            gv[(int64_t)j * p.ldv + d] = sp[j] * od;
+          }
+        } else {   // later query rows of the same (sequence, head): this warp wrote the earlier ones
+          for (j = 0; j < p.Sk; ++j) {
+            gk[(int64_t)j * p.ldk + d] += sds[j] * qd;
+            gv[(int64_t)j * p.ldv + d] += sp[j] * od;
+          }
+        }
+      }
+    }
+  }
+}
+
+static bool mha_small_ok(const MhaArgs& a) { return a.Sq <= MHA_SMALL_SQ && a.Sk <= MHA_SMALL_SK; }
+
+template <bool BWD>
+static int launch_mha_small(const MhaArgs& a, cudaStream_t s) {
+  const size_t smem = (size_t)MHA_SMALL_WARPS * (BWD ? 2 : 1) * (a.dh + a.Sk) * sizeof(float);
+  launch_pdl(mha_small_kernel<BWD>, dim3(ceil_div(a.B * a.nhead, MHA_SMALL_WARPS)), dim3(MHA_SMALL_WARPS * 32), smem, s, a);
+  SLNLP_LAUNCH_OK(BWD ? "mha_bwd(small)" : "mha_fwd(small)");
+  return 0;
+}
+
 // ------------------------------------------------------------------ LayerNorm
 constexpr int LN_MAX_VPL = 32;   // values per lane: E <= 1024
 constexpr int LN_WARPS = 4;
 // the kernels are instantiated for VPLT = 4, 8, 16, 32 values per lane (E <= 128, 256, 512, 1024) so that
 // the per-lane arrays fit the register file with room for several CTAs per SM
+
+// Every global load of a row is issued before the first use (loads in separate unrolled loops,
+// out-of-range columns read as 0 through a select, no branch per element): interleaving load and
+// use serialises VPLT DRAM round trips per row.
 
 // y = LN(x + res) * gamma + beta; one warp per row.  mean / rstd [rows] saved for backward.
 template <int VPLT>
@@ -395,22 +546,29 @@ __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(const 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int row = blockIdx.x * LN_WARPS + w;
   if (row >= rows) return;
-  const int vpl = (E + 31) >> 5;
   const float* xr = x + (int64_t)row * E;
-  const float* rr = res ? res + (int64_t)row * E : nullptr;
-  float v[VPLT];
+  const float* rr = res ? res + (int64_t)row * E : xr;
+  float v[VPLT], rv[VPLT], gm[VPLT], bt[VPLT];
+#pragma unroll
+  for (int k = 0; k < VPLT; ++k) v[k] = (lane + 32 * k < E) ? xr[lane + 32 * k] : 0.f;
+#pragma unroll
+  for (int k = 0; k < VPLT; ++k) rv[k] = (res && lane + 32 * k < E) ? rr[lane + 32 * k] : 0.f;
+#pragma unroll
+  for (int k = 0; k < VPLT; ++k) {
+    gm[k] = (lane + 32 * k < E) ? gamma[lane + 32 * k] : 0.f;
+    bt[k] = (lane + 32 * k < E) ? beta[lane + 32 * k] : 0.f;
+  }
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < VPLT; ++k)
-    if (k < vpl && lane + 32 * k < E) {
-      v[k] = xr[lane + 32 * k] + (rr ? rr[lane + 32 * k] : 0.f);
-      s += v[k];
-    }
+  for (int k = 0; k < VPLT; ++k) {
+    v[k] += rv[k];
+    s += v[k];
+  }
   const float mu = warp_sum(s) / E;
   float q = 0.f;
 #pragma unroll
   for (int k = 0; k < VPLT; ++k)
-    if (k < vpl && lane + 32 * k < E) {
+    if (lane + 32 * k < E) {
       const float d = v[k] - mu;
       q = fmaf(d, d, q);
     }
@@ -418,7 +576,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(const 
   float* yr = y + (int64_t)row * E;
 #pragma unroll
   for (int k = 0; k < VPLT; ++k)
-    if (k < vpl && lane + 32 * k < E) yr[lane + 32 * k] = (v[k] - mu) * rs * gamma[lane + 32 * k] + beta[lane + 32 * k];
+    if (lane + 32 * k < E) yr[lane + 32 * k] = (v[k] - mu) * rs * gm[k] + bt[k];
   if (lane == 0) {
     if (mean) mean[row] = mu;
     if (rstd) rstd[row] = rs;
@@ -441,44 +599,52 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(const floa
   pdl_launch_dependents();
   extern __shared__ float sred[];   // [LN_WARPS][2][E]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int vpl = (E + 31) >> 5;
   float dg[VPLT], db[VPLT], gm[VPLT];
 #pragma unroll
   for (int k = 0; k < VPLT; ++k) {
     dg[k] = db[k] = 0.f;
-    gm[k] = (k < vpl && lane + 32 * k < E) ? gamma[lane + 32 * k] : 0.f;
+    gm[k] = (lane + 32 * k < E) ? gamma[lane + 32 * k] : 0.f;
   }
   for (int row = blockIdx.x * LN_WARPS + w; row < rows; row += gridDim.x * LN_WARPS) {
     const float* xr = x + (int64_t)row * E;
-    const float* rr = res ? res + (int64_t)row * E : nullptr;
+    const float* rr = res ? res + (int64_t)row * E : xr;
     const float* gr = dy + (int64_t)row * E;
+    float* o = dx + (int64_t)row * E;
     const float mu = mean[row], rs = rstd[row];
-    float xh[VPLT], g[VPLT];
+    float xh[VPLT], g[VPLT], rv[VPLT];
+#pragma unroll
+    for (int k = 0; k < VPLT; ++k) g[k] = (lane + 32 * k < E) ? gr[lane + 32 * k] : 0.f;
+#pragma unroll
+    for (int k = 0; k < VPLT; ++k) xh[k] = (lane + 32 * k < E) ? xr[lane + 32 * k] : 0.f;
+#pragma unroll
+    for (int k = 0; k < VPLT; ++k) rv[k] = (res && lane + 32 * k < E) ? rr[lane + 32 * k] : 0.f;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < VPLT; ++k)
-      if (k < vpl && lane + 32 * k < E) {
-        const float d = gr[lane + 32 * k];
-        xh[k] = (xr[lane + 32 * k] + (rr ? rr[lane + 32 * k] : 0.f) - mu) * rs;
-        g[k] = d * gm[k];
-        s1 += g[k];
-        s2 = fmaf(g[k], xh[k], s2);
-        dg[k] = fmaf(d, xh[k], dg[k]);
-        db[k] += d;
-      }
+    for (int k = 0; k < VPLT; ++k) {
+      const float d = g[k];
+      xh[k] = (lane + 32 * k < E) ? (xh[k] + rv[k] - mu) * rs : 0.f;
+      g[k] = d * gm[k];
+      s1 += g[k];
+      s2 = fmaf(g[k], xh[k], s2);
+      dg[k] = fmaf(d, xh[k], dg[k]);
+      db[k] += d;
+    }
+    if (accumulate) {   // old dx read before any of this row's stores
+#pragma unroll
+      for (int k = 0; k < VPLT; ++k) rv[k] = (lane + 32 * k < E) ? o[lane + 32 * k] : 0.f;
+    } else {
+#pragma unroll
+      for (int k = 0; k < VPLT; ++k) rv[k] = 0.f;
+    }
     s1 = warp_sum(s1) / E;
     s2 = warp_sum(s2) / E;
-    float* o = dx + (int64_t)row * E;
 #pragma unroll
     for (int k = 0; k < VPLT; ++k)
-      if (k < vpl && lane + 32 * k < E) {
-        const float val = rs * (g[k] - s1 - xh[k] * s2);
-        o[lane + 32 * k] = accumulate ? o[lane + 32 * k] + val : val;
-      }
+      if (lane + 32 * k < E) o[lane + 32 * k] = rv[k] + rs * (g[k] - s1 - xh[k] * s2);
   }
 #pragma unroll
   for (int k = 0; k < VPLT; ++k)
-    if (k < vpl && lane + 32 * k < E) {
+    if (lane + 32 * k < E) {
       sred[(w * 2 + 0) * E + lane + 32 * k] = dg[k];
       sred[(w * 2 + 1) * E + lane + 32 * k] = db[k];
     }
@@ -563,6 +729,7 @@ extern "C" int slnlp_mha_fwd(const float* q, int ldq, const float* k, int ldk, c
   a.key_tokens = key_tokens; a.pad_idx = pad_idx; a.scale = 1.f / sqrtf((float)dh);
   a.p_drop = p_drop; a.rng = rng; a.site = site;
   if (int rc = check_mha(a, "mha_fwd")) return rc;
+  if (mha_small_ok(a)) return launch_mha_small<false>(a, as_stream(stream));
   MHA_DISPATCH(launch_mha_fwd, a, as_stream(stream));
 }
 
@@ -579,6 +746,7 @@ extern "C" int slnlp_mha_bwd(const float* q, int ldq, const float* k, int ldk, c
   a.key_tokens = key_tokens; a.pad_idx = pad_idx; a.scale = 1.f / sqrtf((float)dh);
   a.p_drop = p_drop; a.rng = rng; a.site = site;
   if (int rc = check_mha(a, "mha_bwd")) return rc;
+  if (mha_small_ok(a)) return launch_mha_small<true>(a, as_stream(stream));
   MHA_DISPATCH(launch_mha_bwd, a, as_stream(stream));
 }
 

@@ -47,6 +47,10 @@ def _ref_attention(q, k, v, nhead, causal, keypad):
     (3, 1, 64, 4, 128, 0, False),     # decoder cross attention (one query)
     (4, 1, 1, 4, 16, 0, False),       # decoder self attention on one token
     (2, 70, 90, 1, 256, 0, True),     # head dim 256 (E 1024 / 4 heads), 32-row tiles
+    (3, 4, 37, 2, 24, 0, True),       # few-query kernel: 4 query rows, ragged keys, key padding
+    (2, 3, 3, 2, 12, 1, False),       # few-query kernel, causal
+    (5, 2, 65, 3, 40, 0, True),       # few-query kernel, head dim not a multiple of 8 or 32
+    (2, 5, 40, 2, 16, 0, True),       # one row past the few-query limit: tile kernel
 ])
 def test_mha_fwd_bwd_against_torch(B, Sq, Sk, nhead, dh, causal, pad):
     L = _lib()
@@ -100,30 +104,30 @@ def test_mha_all_keys_masked_gives_nan_like_torch():
     assert rel_err(o[1], x[1, :, 2 * E:]) < 1e-6          # one unmasked key: the value itself
 
 
-def test_mha_dropout_statistics_and_backward_replays_mask():
+@pytest.mark.parametrize("B,Sq,Sk", [(2, 64, 64), (64, 2, 64)])   # tile kernel, few-query kernel
+def test_mha_dropout_statistics_and_backward_replays_mask(B, Sq, Sk):
     L = _lib()
-    B, Sn, nhead, dh, p = 2, 64, 2, 32, 0.25
+    nhead, dh, p = 2, 32, 0.25
     E = nhead * dh
-    x = torch.randn(B, Sn, 3 * E, device="cuda")
-    x[..., 2 * E:] = 1.0                                # V = 1: each output is the kept mass / (1-p)
+    xq = torch.randn(B, Sq, E, device="cuda")
+    xkv = torch.randn(B, Sk, 2 * E, device="cuda")
+    xkv[..., E:] = 1.0                                  # V = 1: each output is the kept mass / (1-p)
     rng = torch.tensor([1234, 5], dtype=torch.int64, device="cuda")
-    o, lse = torch.empty(B, Sn, E, device="cuda"), torch.empty(B, nhead, Sn, device="cuda")
-    q = x.data_ptr()
-    args = (q, 3 * E, q + 4 * E, 3 * E, q + 8 * E, 3 * E)
-    L.check(L.lib.slnlp_mha_fwd(*args, o.data_ptr(), E, lse.data_ptr(), B, Sn, Sn, nhead, dh, 0, None, 0, p, rng.data_ptr(), 3, S()))
+    o, lse = torch.empty(B, Sq, E, device="cuda"), torch.empty(B, nhead, Sq, device="cuda")
+    args = (xq.data_ptr(), E, xkv.data_ptr(), 2 * E, xkv.data_ptr() + 4 * E, 2 * E)
+    L.check(L.lib.slnlp_mha_fwd(*args, o.data_ptr(), E, lse.data_ptr(), B, Sq, Sk, nhead, dh, 0, None, 0, p, rng.data_ptr(), 3, S()))
     assert abs(float(o.mean()) - 1.0) < 0.02            # E[mask/(1-p)] = 1
     assert float(o.std()) > 0.01
     o2 = torch.empty_like(o)
-    L.check(L.lib.slnlp_mha_fwd(*args, o2.data_ptr(), E, lse.data_ptr(), B, Sn, Sn, nhead, dh, 0, None, 0, p, rng.data_ptr(), 3, S()))
+    L.check(L.lib.slnlp_mha_fwd(*args, o2.data_ptr(), E, lse.data_ptr(), B, Sq, Sk, nhead, dh, 0, None, 0, p, rng.data_ptr(), 3, S()))
     assert torch.equal(o, o2)                           # same (seed, step, site) -> same mask
-    # backward with the same mask: d/dV of sum(o) = column sums of the dropped weights, whose total is B*nhead*Sn*E/E...
+    # backward with the same mask
     do = torch.ones_like(o)
-    dqkv, dvec = torch.empty_like(x), torch.empty(B, nhead, Sn, device="cuda")
-    d = dqkv.data_ptr()
-    L.check(L.lib.slnlp_mha_bwd(*args, o.data_ptr(), do.data_ptr(), E, lse.data_ptr(), dvec.data_ptr(), d, d + 4 * E, d + 8 * E,
-                                B, Sn, Sn, nhead, dh, 0, None, 0, p, rng.data_ptr(), 3, S()))
+    dq, dkv, dvec = torch.empty_like(xq), torch.empty_like(xkv), torch.empty(B, nhead, Sq, device="cuda")
+    L.check(L.lib.slnlp_mha_bwd(*args, o.data_ptr(), do.data_ptr(), E, lse.data_ptr(), dvec.data_ptr(), dq.data_ptr(),
+                                dkv.data_ptr(), dkv.data_ptr() + 4 * E, B, Sq, Sk, nhead, dh, 0, None, 0, p, rng.data_ptr(), 3, S()))
     # sum_j dV[j, d] = sum_i sum_j Pdrop[i, j] = sum_i o[i, d] for V = 1
-    dv = dqkv[..., 2 * E:]
+    dv = dkv[..., E:]
     assert rel_err(dv.sum(1), o.sum(1)) < 1e-5
 
 
