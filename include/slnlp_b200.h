@@ -211,6 +211,21 @@ int slnlp_mha_bwd(const float* q, int ldq, const float* k, int ldk, const float*
                   float* dq, float* dk, float* dv, int B, int Sq, int Sk, int nhead, int dh,
                   int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
                   const uint64_t* rng, uint32_t site, slnlp_stream_t stream);
+/* Tensor-core forms of the two calls above (same arguments and semantics): every tile product of
+ * the flash passes runs as warp-level tf32 MMA with fp32 accumulation (the "bf16" precision mode
+ * of the modules, tolerance 2e-2; the softmax, masks and dropout stay fp32).  Head dimensions 16,
+ * 32 and 64; any other shape runs the fp32 kernels.  Queries of <= 4 rows per sequence (the
+ * reference's one-position decoder, model/transformer.py:82-87) use a one-warp-per-(sequence,
+ * head) fp32 kernel in both forms. */
+int slnlp_mha_tf32_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                       float* o, int ldo, float* lse, int B, int Sq, int Sk, int nhead, int dh,
+                       int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                       const uint64_t* rng, uint32_t site, slnlp_stream_t stream);
+int slnlp_mha_tf32_bwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                       const float* o, const float* dout, int ldo, const float* lse, float* dvec,
+                       float* dq, float* dk, float* dv, int B, int Sq, int Sk, int nhead, int dh,
+                       int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                       const uint64_t* rng, uint32_t site, slnlp_stream_t stream);
 /* y = LayerNorm(x + res) * gamma + beta over rows of E floats (res may be NULL;
  * E <= 1024).  mean / rstd [rows] (may be NULL at inference) are saved for backward. */
 int slnlp_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,

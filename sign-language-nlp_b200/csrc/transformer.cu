@@ -376,149 +376,615 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(MhaArgs p) {
   }
 }
 
+// ------------------------------------------------------------------ tensor-core attention
+// The same flash-style passes with every tile product on the tensor cores (warp-level tf32 MMA,
+// m16n8k8, fp32 accumulate; operands rounded to tf32 as they leave shared memory).  64-query x
+// 64-key tiles, 4 warps, warp w owns query (or, in the dK/dV pass, key) rows 16w..16w+15, so the
+// softmax needs only quad shuffles and P / dS go through warp-private shared-memory rows.
+// A 64 x 64 x 64 tile is far below what tcgen05 needs to pay for its TMEM round trip and a
+// per-(sequence, head) M = 128 tile would be half padding, hence the register-fragment form here.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// fragment coordinates: g = lane / 4, t = lane % 4.
+// C[16, 8 NT] += A[m0.., :] B^T with A stored [m][k] and B stored [n][k]
+template <int NT, int KS>
+__device__ __forceinline__ void mma_nk(float (&c)[NT][4], const float* sA, int sta, int m0, const float* sB, int stb,
+                                       int g, int t) {
+#pragma unroll
+  for (int kk = 0; kk < KS; ++kk) {
+    uint32_t a[4];
+    a[0] = to_tf32(sA[(m0 + g) * sta + kk * 8 + t]);
+    a[1] = to_tf32(sA[(m0 + g + 8) * sta + kk * 8 + t]);
+    a[2] = to_tf32(sA[(m0 + g) * sta + kk * 8 + t + 4]);
+    a[3] = to_tf32(sA[(m0 + g + 8) * sta + kk * 8 + t + 4]);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+      mma_tf32(c[nt], a, to_tf32(sB[(nt * 8 + g) * stb + kk * 8 + t]), to_tf32(sB[(nt * 8 + g) * stb + kk * 8 + t + 4]));
+  }
+}
+// C[16, 8 NT] += A[m0.., :] B with A stored [m][k] and B stored [k][n]
+template <int NT, int KS>
+__device__ __forceinline__ void mma_kn(float (&c)[NT][4], const float* sA, int sta, int m0, const float* sB, int stb,
+                                       int g, int t) {
+#pragma unroll
+  for (int kk = 0; kk < KS; ++kk) {
+    uint32_t a[4];
+    a[0] = to_tf32(sA[(m0 + g) * sta + kk * 8 + t]);
+    a[1] = to_tf32(sA[(m0 + g + 8) * sta + kk * 8 + t]);
+    a[2] = to_tf32(sA[(m0 + g) * sta + kk * 8 + t + 4]);
+    a[3] = to_tf32(sA[(m0 + g + 8) * sta + kk * 8 + t + 4]);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+      mma_tf32(c[nt], a, to_tf32(sB[(kk * 8 + t) * stb + nt * 8 + g]), to_tf32(sB[(kk * 8 + t + 4) * stb + nt * 8 + g]));
+  }
+}
+// C[16, 8 NT] += A^T[m0.., :] B with A stored [k][m] and B stored [k][n]
+template <int NT, int KS>
+__device__ __forceinline__ void mma_tkn(float (&c)[NT][4], const float* sA, int sta, int m0, const float* sB, int stb,
+                                        int g, int t) {
+#pragma unroll
+  for (int kk = 0; kk < KS; ++kk) {
+    uint32_t a[4];
+    a[0] = to_tf32(sA[(kk * 8 + t) * sta + m0 + g]);
+    a[1] = to_tf32(sA[(kk * 8 + t) * sta + m0 + g + 8]);
+    a[2] = to_tf32(sA[(kk * 8 + t + 4) * sta + m0 + g]);
+    a[3] = to_tf32(sA[(kk * 8 + t + 4) * sta + m0 + g + 8]);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+      mma_tf32(c[nt], a, to_tf32(sB[(kk * 8 + t) * stb + nt * 8 + g]), to_tf32(sB[(kk * 8 + t + 4) * stb + nt * 8 + g]));
+  }
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// rows [r0, r0+64) x head columns [0, dh) -> smem tile [64][st] (st % 4 == 0), zero-filled
+__device__ __forceinline__ void load_tile_v(float* s, const float* g, int ld, int r0, int rows, int dh, int st, float mul) {
+  const int c4n = dh >> 2, total = 64 * c4n;
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * blockDim.x;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < total) {
+        const int r = e / c4n, c4 = (e % c4n) << 2;
+        if (r0 + r < rows) v[u] = *reinterpret_cast<const float4*>(g + (int64_t)(r0 + r) * ld + c4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * blockDim.x;
+      if (e < total) {
+        const int r = e / c4n, c4 = (e % c4n) << 2;
+        *reinterpret_cast<float4*>(s + r * st + c4) = make_float4(v[u].x * mul, v[u].y * mul, v[u].z * mul, v[u].w * mul);
+      }
+    }
+  }
+}
+
+// keep-factors of the two adjacent attention weights (b, h, i, j) and (b, h, i, j + 1): the same
+// Philox stream as drop_factor(), one block of four uniforms serving both whenever they share it
+__device__ __forceinline__ void drop_factor2(const MhaArgs& p, uint64_t seed, uint64_t step, int bh, int i, int j,
+                                             float& f0, float& f1) {
+  const uint64_t e = ((uint64_t)bh * p.Sq + i) * p.Sk + j;
+  const int ph = (int)(e & 3);
+  const float keep = 1.f - p.p_drop, inv = 1.f / keep;
+  float u[4];
+  philox_uniform4(seed, step, p.site, e >> 2, u);
+  const float u0 = ph == 0 ? u[0] : ph == 1 ? u[1] : ph == 2 ? u[2] : u[3];
+  float u1 = ph == 0 ? u[1] : ph == 1 ? u[2] : u[3];
+  if (ph == 3) {
+    philox_uniform4(seed, step, p.site, (e >> 2) + 1, u);
+    u1 = u[0];
+  }
+  f0 = u0 < keep ? inv : 0.f;
+  f1 = u1 < keep ? inv : 0.f;
+}
+// bit (2 n + e) set: key k0 + 8 n + 2 t + e is past the end or a padding token
+__device__ __forceinline__ uint32_t key_mask_bits(const MhaArgs& p, const int64_t* ktok, int k0, int t) {
+  int64_t tok[16];
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = k0 + n * 8 + 2 * t + e;
+      tok[2 * n + e] = (ktok != nullptr && j < p.Sk) ? ktok[j] : p.pad_idx + 1;
+    }
+  uint32_t bits = 0;
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = k0 + n * 8 + 2 * t + e;
+      if (j >= p.Sk || tok[2 * n + e] == p.pad_idx) bits |= 1u << (2 * n + e);
+    }
+  return bits;
+}
+
+constexpr int TC_N = 64;        // tile edge
+constexpr int TC_SP = TC_N + 4; // P / dS row stride
+
+// grid (ceil(Sq/64), nhead, B), block 128.  smem: Q, K, V [64][DH+4], P [64][68]
+template <int DH>
+__global__ void __launch_bounds__(128) mha_tc_fwd_kernel(MhaArgs p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int N = TC_N, ST = DH + 4, SP = TC_SP, NTD = DH / 8;
+  extern __shared__ float sm[];
+  float* sQ = sm;
+  float* sK = sQ + N * ST;
+  float* sV = sK + N * ST;
+  float* sP = sV + N * ST;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int i0 = blockIdx.x * N, h = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.nhead + h;
+  const float* q = p.q + (int64_t)b * p.Sq * p.ldq + h * DH;
+  const float* k = p.k + (int64_t)b * p.Sk * p.ldk + h * DH;
+  const float* v = p.v + (int64_t)b * p.Sk * p.ldv + h * DH;
+  const int64_t* ktok = p.key_tokens ? p.key_tokens + (int64_t)b * p.Sk : nullptr;
+  const bool drop = p.p_drop > 0.f;
+  const uint64_t seed = drop ? p.rng[0] : 0, step = drop ? p.rng[1] : 0;
+
+  load_tile_v(sQ, q, p.ldq, i0, p.Sq, DH, ST, p.scale);
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  float acc[NTD][4];
+#pragma unroll
+  for (int n = 0; n < NTD; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+  for (int k0 = 0; k0 < p.Sk; k0 += N) {
+    if (p.causal && k0 > i0 + N - 1) break;
+    __syncthreads();
+    load_tile_v(sK, k, p.ldk, k0, p.Sk, DH, ST, 1.f);
+    load_tile_v(sV, v, p.ldv, k0, p.Sk, DH, ST, 1.f);
+    __syncthreads();
+    const uint32_t kbits = key_mask_bits(p, ktok, k0, t);
+    float s[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    mma_nk<8, DH / 8>(s, sQ, ST, 16 * w, sK, ST, g, t);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = 16 * w + g + 8 * r, i = i0 + row;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = k0 + n * 8 + 2 * t + e;
+          if (((kbits >> (2 * n + e)) & 1u) || (p.causal && j > i)) s[n][2 * r + e] = -INFINITY;
+          mx = fmaxf(mx, s[n][2 * r + e]);
+        }
+      mx = quad_max(mx);
+      const float mn = fmaxf(m[r], mx);
+      const float corr = mn == -INFINITY ? 1.f : expf(m[r] - mn);
+      float sum = 0.f;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        float ev[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          ev[e] = mn == -INFINITY ? 0.f : expf(s[n][2 * r + e] - mn);
+          sum += ev[e];
+        }
+        if (drop && (ev[0] != 0.f || ev[1] != 0.f)) {
+          float f0, f1;
+          drop_factor2(p, seed, step, bh, i, k0 + n * 8 + 2 * t, f0, f1);
+          ev[0] *= f0;
+          ev[1] *= f1;
+        }
+        *reinterpret_cast<float2*>(sP + row * SP + n * 8 + 2 * t) = make_float2(ev[0], ev[1]);
+      }
+      sum = quad_sum(sum);
+      l[r] = l[r] * corr + sum;
+      m[r] = mn;
+#pragma unroll
+      for (int n = 0; n < NTD; ++n) {
+        acc[n][2 * r] *= corr;
+        acc[n][2 * r + 1] *= corr;
+      }
+    }
+    __syncwarp();
+    mma_kn<NTD, 8>(acc, sP, SP, 16 * w, sV, ST, g, t);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = i0 + 16 * w + g + 8 * r;
+    if (i >= p.Sq) continue;
+    const float inv = 1.f / l[r];   // every key masked: 0/0 = NaN, as torch's softmax of all -inf
+    float* o = p.o + ((int64_t)b * p.Sq + i) * p.ldo + h * DH;
+#pragma unroll
+    for (int n = 0; n < NTD; ++n)
+      *reinterpret_cast<float2*>(o + n * 8 + 2 * t) = make_float2(acc[n][2 * r] * inv, acc[n][2 * r + 1] * inv);
+    if (t == 0) p.lse[(int64_t)bh * p.Sq + i] = m[r] + logf(l[r]);
+  }
+}
+
+// P (dropped) and dS of one (query tile, key tile) pair into the warp's 16 query rows of sP / sDS
+template <int DH>
+__device__ __forceinline__ void tc_bwd_tile(const MhaArgs& p, const float* sQ, const float* sK, const float* sV,
+                                            const float* sDO, float* sP, float* sDS, const float* lse, const float* dvec,
+                                            const int64_t* ktok, int bh, int i0, int k0, uint64_t seed, uint64_t step,
+                                            int w, int g, int t) {
+  constexpr int ST = DH + 4, SP = TC_SP;
+  const bool drop = p.p_drop > 0.f;
+  // row statistics and key mask are fetched before the tile products so that their latency hides
+  float Lr[2], Dr[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = i0 + 16 * w + g + 8 * r;
+    Lr[r] = i < p.Sq ? lse[i] : 0.f;
+    Dr[r] = i < p.Sq ? dvec[i] : 0.f;
+  }
+  const uint32_t kbits = key_mask_bits(p, ktok, k0, t);
+  float s[8][4], dp[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+  }
+  mma_nk<8, DH / 8>(s, sQ, ST, 16 * w, sK, ST, g, t);      // Q carries the 1/sqrt(dh) scale
+  mma_nk<8, DH / 8>(dp, sDO, ST, 16 * w, sV, ST, g, t);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = 16 * w + g + 8 * r, i = i0 + row;
+    const bool row_ok = i < p.Sq;
+    const float L = Lr[r], D = Dr[r];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      float pr[2], dsc[2], f[2] = {1.f, 1.f};
+      bool live[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = k0 + n * 8 + 2 * t + e;
+        live[e] = row_ok && !((kbits >> (2 * n + e)) & 1u) && !(p.causal && j > i);
+      }
+      if (drop && (live[0] || live[1])) drop_factor2(p, seed, step, bh, i, k0 + n * 8 + 2 * t, f[0], f[1]);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        pr[e] = dsc[e] = 0.f;
+        if (live[e]) {
+          pr[e] = expf(s[n][2 * r + e] - L);
+          dsc[e] = pr[e] * (dp[n][2 * r + e] * f[e] - D);
+          pr[e] *= f[e];
+        }
+      }
+      *reinterpret_cast<float2*>(sP + row * SP + n * 8 + 2 * t) = make_float2(pr[0], pr[1]);
+      *reinterpret_cast<float2*>(sDS + row * SP + n * 8 + 2 * t) = make_float2(dsc[0], dsc[1]);
+    }
+  }
+}
+
+// DKV = false: grid (ceil(Sq/64), nhead, B), writes D and dQ.  DKV = true: grid (ceil(Sk/64), nhead, B),
+// writes dK and dV.  block 128.  smem: Q, K, V, dO [64][DH+4] + P, dS [64][68].
+template <int DH, bool DKV>
+__global__ void __launch_bounds__(128) mha_tc_bwd_kernel(MhaArgs p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int N = TC_N, ST = DH + 4, SP = TC_SP, NTD = DH / 8;
+  extern __shared__ float sm[];
+  float* sQ = sm;
+  float* sK = sQ + N * ST;
+  float* sV = sK + N * ST;
+  float* sDO = sV + N * ST;
+  float* sP = sDO + N * ST;
+  float* sDS = sP + N * SP;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.y, b = blockIdx.z, bh = b * p.nhead + h;
+  const float* q = p.q + (int64_t)b * p.Sq * p.ldq + h * DH;
+  const float* k = p.k + (int64_t)b * p.Sk * p.ldk + h * DH;
+  const float* v = p.v + (int64_t)b * p.Sk * p.ldv + h * DH;
+  const float* dO = p.dout + (int64_t)b * p.Sq * p.ldo + h * DH;
+  const float* lse = p.lse + (int64_t)bh * p.Sq;
+  float* dvec = p.dvec + (int64_t)bh * p.Sq;
+  const int64_t* ktok = p.key_tokens ? p.key_tokens + (int64_t)b * p.Sk : nullptr;
+  const bool drop = p.p_drop > 0.f;
+  const uint64_t seed = drop ? p.rng[0] : 0, step = drop ? p.rng[1] : 0;
+  float acc[NTD][4];
+#pragma unroll
+  for (int n = 0; n < NTD; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+
+  if (!DKV) {
+    const int i0 = blockIdx.x * N;
+    load_tile_v(sQ, q, p.ldq, i0, p.Sq, DH, ST, p.scale);
+    load_tile_v(sDO, dO, p.ldo, i0, p.Sq, DH, ST, 1.f);
+    // D_i = <dO_i, O_i>: two threads per row, each half a row of independent float4 loads
+    {
+      const float* O = p.o + (int64_t)b * p.Sq * p.ldo + h * DH;
+      const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+      constexpr int HW = DH / 2;
+      float sacc = 0.f;
+      if (i0 + r < p.Sq) {
+        const float4* a4 = reinterpret_cast<const float4*>(dO + (int64_t)(i0 + r) * p.ldo + half * HW);
+        const float4* b4 = reinterpret_cast<const float4*>(O + (int64_t)(i0 + r) * p.ldo + half * HW);
+        float4 av[HW / 4], bv[HW / 4];
+#pragma unroll
+        for (int c = 0; c < HW / 4; ++c) {
+          av[c] = a4[c];
+          bv[c] = b4[c];
+        }
+#pragma unroll
+        for (int c = 0; c < HW / 4; ++c)
+          sacc += av[c].x * bv[c].x + av[c].y * bv[c].y + av[c].z * bv[c].z + av[c].w * bv[c].w;
+      }
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+      if (half == 0 && i0 + r < p.Sq) dvec[i0 + r] = sacc;
+    }
+    __syncthreads();   // dvec rows of this tile are re-read below (same CTA wrote them)
+    for (int k0 = 0; k0 < p.Sk; k0 += N) {
+      if (p.causal && k0 > i0 + N - 1) break;
+      __syncthreads();
+      load_tile_v(sK, k, p.ldk, k0, p.Sk, DH, ST, 1.f);
+      load_tile_v(sV, v, p.ldv, k0, p.Sk, DH, ST, 1.f);
+      __syncthreads();
+      tc_bwd_tile<DH>(p, sQ, sK, sV, sDO, sP, sDS, lse, dvec, ktok, bh, i0, k0, seed, step, w, g, t);
+      __syncwarp();
+      mma_kn<NTD, 8>(acc, sDS, SP, 16 * w, sK, ST, g, t);   // dQ += dS K
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = i0 + 16 * w + g + 8 * r;
+      if (i >= p.Sq) continue;
+      float* gq = p.dq + ((int64_t)b * p.Sq + i) * p.ldq + h * DH;
+#pragma unroll
+      for (int n = 0; n < NTD; ++n)
+        *reinterpret_cast<float2*>(gq + n * 8 + 2 * t) = make_float2(acc[n][2 * r] * p.scale, acc[n][2 * r + 1] * p.scale);
+    }
+  } else {
+    float acc2[NTD][4];
+#pragma unroll
+    for (int n = 0; n < NTD; ++n) acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f;
+    const int k0 = blockIdx.x * N;
+    load_tile_v(sK, k, p.ldk, k0, p.Sk, DH, ST, 1.f);
+    load_tile_v(sV, v, p.ldv, k0, p.Sk, DH, ST, 1.f);
+    for (int i0 = 0; i0 < p.Sq; i0 += N) {
+      if (p.causal && i0 + N - 1 < k0) continue;
+      __syncthreads();
+      load_tile_v(sQ, q, p.ldq, i0, p.Sq, DH, ST, p.scale);
+      load_tile_v(sDO, dO, p.ldo, i0, p.Sq, DH, ST, 1.f);
+      __syncthreads();
+      tc_bwd_tile<DH>(p, sQ, sK, sV, sDO, sP, sDS, lse, dvec, ktok, bh, i0, k0, seed, step, w, g, t);
+      __syncthreads();
+      mma_tkn<NTD, 8>(acc, sP, SP, 16 * w, sDO, ST, g, t);    // dV += P^T dO
+      mma_tkn<NTD, 8>(acc2, sDS, SP, 16 * w, sQ, ST, g, t);   // dK += dS^T Q  (Q carries the scale)
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int j = k0 + 16 * w + g + 8 * r;
+      if (j >= p.Sk) continue;
+      float* gv = p.dv + ((int64_t)b * p.Sk + j) * p.ldv + h * DH;
+      float* gk = p.dk + ((int64_t)b * p.Sk + j) * p.ldk + h * DH;
+#pragma unroll
+      for (int n = 0; n < NTD; ++n) {
+        *reinterpret_cast<float2*>(gv + n * 8 + 2 * t) = make_float2(acc[n][2 * r], acc[n][2 * r + 1]);
+        *reinterpret_cast<float2*>(gk + n * 8 + 2 * t) = make_float2(acc2[n][2 * r], acc2[n][2 * r + 1]);
+      }
+    }
+  }
+}
+
+static bool mha_tc_ok(const MhaArgs& a) { return a.dh == 16 || a.dh == 32 || a.dh == 64; }
+
+template <int DH>
+static int launch_mha_tc_fwd(const MhaArgs& a, cudaStream_t s) {
+  constexpr size_t smem = (size_t)(3 * TC_N * (DH + 4) + TC_N * TC_SP) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(mha_tc_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return fail("mha_tf32_fwd: cannot raise the shared-memory limit");
+    attr = true;
+  }
+  launch_pdl(mha_tc_fwd_kernel<DH>, dim3(ceil_div(a.Sq, TC_N), a.nhead, a.B), dim3(128), smem, s, a);
+  SLNLP_LAUNCH_OK("mha_tf32_fwd");
+  return 0;
+}
+
+template <int DH>
+static int launch_mha_tc_bwd(const MhaArgs& a, cudaStream_t s) {
+  constexpr size_t smem = (size_t)(4 * TC_N * (DH + 4) + 2 * TC_N * TC_SP) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(mha_tc_bwd_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(mha_tc_bwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return fail("mha_tf32_bwd: cannot raise the shared-memory limit");
+    attr = true;
+  }
+  launch_pdl(mha_tc_bwd_kernel<DH, false>, dim3(ceil_div(a.Sq, TC_N), a.nhead, a.B), dim3(128), smem, s, a);
+  SLNLP_LAUNCH_OK("mha_tf32_bwd(dq)");
+  launch_pdl(mha_tc_bwd_kernel<DH, true>, dim3(ceil_div(a.Sk, TC_N), a.nhead, a.B), dim3(128), smem, s, a);
+  SLNLP_LAUNCH_OK("mha_tf32_bwd(dkv)");
+  return 0;
+}
+
 // ------------------------------------------------------------------ few-query attention
 // The reference's decoder sees ONE target position (the label, model/transformer.py:82-87), so its
 // self-attention is 1 x 1 and its cross-attention 1 x S: a 64-query tile would be 63/64 padding.
-// One warp per (sequence, head) walks the Sq <= MHA_SMALL_SQ query rows: lanes own keys for the
-// scores (float4 dot products over the head dimension), lanes own head columns for P.V and for the
-// gradients.  Same masks, dropout stream, log-sum-exp and all-masked-row NaN as the tile kernels.
+// One CTA per (sequence, head): all 128 threads stage 64-key K / V tiles in shared memory, warp i
+// then owns query row i (Sq <= 4) - lanes over keys for the scores, lanes over head columns for
+// P.V and dQ - and all threads write the dK / dV tile.  Same masks, dropout stream, log-sum-exp
+// and all-masked-row NaN as the tile kernels; fp32 throughout.
 constexpr int MHA_SMALL_SQ = 4;
-constexpr int MHA_SMALL_SK = 1024;
-constexpr int MHA_SMALL_WARPS = 4;
+constexpr int MHA_SMALL_C = 8;   // head columns per lane: dh <= 256
 
-__device__ __forceinline__ float dot_row(const float* __restrict__ sv, const float* __restrict__ g, int dh) {
-  float a0 = 0.f, a1 = 0.f;
-  for (int d = 0; d < dh; d += 8) {
-    const float4 x = *reinterpret_cast<const float4*>(g + d);
-    a0 = fmaf(sv[d], x.x, a0); a0 = fmaf(sv[d + 1], x.y, a0); a0 = fmaf(sv[d + 2], x.z, a0); a0 = fmaf(sv[d + 3], x.w, a0);
-    if (d + 4 < dh) {
-      const float4 y = *reinterpret_cast<const float4*>(g + d + 4);
-      a1 = fmaf(sv[d + 4], y.x, a1); a1 = fmaf(sv[d + 5], y.y, a1); a1 = fmaf(sv[d + 6], y.z, a1); a1 = fmaf(sv[d + 7], y.w, a1);
-    }
-  }
-  return a0 + a1;
-}
-
-// smem per warp: q [dh] | dO [dh] (bwd) | p [Sk] | ds [Sk] (bwd)
+// smem: K, V [64][dh+1] | q [4][dh] | dO [4][dh] | p [4][64] | ds [4][64]
 template <bool BWD>
-__global__ void __launch_bounds__(MHA_SMALL_WARPS * 32) mha_small_kernel(MhaArgs p) {
+__global__ void __launch_bounds__(128) mha_small_kernel(MhaArgs p) {
   pdl_wait();
   pdl_launch_dependents();
   extern __shared__ float sm[];
+  const int dh = p.dh, st = dh + 1;
+  float* sK = sm;
+  float* sV = sK + 64 * st;
+  float* sq = sV + 64 * st;
+  float* sdo = sq + 4 * dh;
+  float* sp = sdo + 4 * dh;
+  float* sds = sp + 4 * 64;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int bh = blockIdx.x * MHA_SMALL_WARPS + w;
-  if (bh >= p.B * p.nhead) return;
-  const int b = bh / p.nhead, h = bh % p.nhead, dh = p.dh;
-  const int per_warp = (BWD ? 2 : 1) * (dh + p.Sk);
-  float* sq = sm + w * per_warp;
-  float* sdo = sq + dh;                       // bwd only
-  float* sp = sq + (BWD ? 2 : 1) * dh;
-  float* sds = sp + p.Sk;                     // bwd only
+  const int bh = blockIdx.x, b = bh / p.nhead, h = bh % p.nhead;
+  const float* q = p.q + (int64_t)b * p.Sq * p.ldq + h * dh;
   const float* k = p.k + (int64_t)b * p.Sk * p.ldk + h * dh;
   const float* v = p.v + (int64_t)b * p.Sk * p.ldv + h * dh;
   const int64_t* ktok = p.key_tokens ? p.key_tokens + (int64_t)b * p.Sk : nullptr;
   const bool drop = p.p_drop > 0.f;
   const uint64_t seed = drop ? p.rng[0] : 0, step = drop ? p.rng[1] : 0;
-  for (int i = 0; i < p.Sq; ++i) {
-    const float* q = p.q + ((int64_t)b * p.Sq + i) * p.ldq + h * dh;
-    __syncwarp();
-    if (!BWD) {
-      for (int d = lane; d < dh; d += 32) sq[d] = q[d] * p.scale;
-      __syncwarp();
-      float mx = -INFINITY;
-      for (int j = lane; j < p.Sk; j += 32) {
-        float sc = dot_row(sq, k + (int64_t)j * p.ldk, dh);
-        if (masked(p, ktok, i, j)) sc = -INFINITY;
-        sp[j] = sc;
-        mx = fmaxf(mx, sc);
+  for (int idx = threadIdx.x; idx < p.Sq * dh; idx += blockDim.x) {
+    const int i = idx / dh, d = idx - i * dh;
+    sq[idx] = q[(int64_t)i * p.ldq + d] * p.scale;
+    if (BWD) sdo[idx] = p.dout[((int64_t)b * p.Sq + i) * p.ldo + h * dh + d];
+  }
+  const bool active = w < p.Sq;
+  const int i = w;   // this warp's query row
+  float m = -INFINITY, l = 0.f, L = 0.f, D = 0.f;
+  float acc[MHA_SMALL_C];
+#pragma unroll
+  for (int c = 0; c < MHA_SMALL_C; ++c) acc[c] = 0.f;
+  if (BWD && active) {
+    const float* dO = p.dout + ((int64_t)b * p.Sq + i) * p.ldo + h * dh;
+    const float* O = p.o + ((int64_t)b * p.Sq + i) * p.ldo + h * dh;
+    float ds = 0.f;
+    for (int d = lane; d < dh; d += 32) ds = fmaf(dO[d], O[d], ds);
+    D = warp_sum(ds);
+    L = p.lse[(int64_t)bh * p.Sq + i];
+    if (lane == 0) p.dvec[(int64_t)bh * p.Sq + i] = D;
+  }
+  for (int k0 = 0; k0 < p.Sk; k0 += 64) {
+    __syncthreads();
+    load_tile<64>(sK, k, p.ldk, k0, p.Sk, dh, 1.f);
+    load_tile<64>(sV, v, p.ldv, k0, p.Sk, dh, 1.f);
+    __syncthreads();
+    if (active) {
+      const float* qi = sq + i * dh;
+      const float* di = sdo + i * dh;
+      float s0 = 0.f, s1 = 0.f, dp0 = 0.f, dp1 = 0.f;
+      const float* ka = sK + lane * st;
+      const float* kb = sK + (lane + 32) * st;
+#pragma unroll 4
+      for (int d = 0; d < dh; ++d) {
+        s0 = fmaf(qi[d], ka[d], s0);
+        s1 = fmaf(qi[d], kb[d], s1);
       }
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int j = lane; j < p.Sk; j += 32) {
-        float e = mx == -INFINITY ? 0.f : expf(sp[j] - mx);
-        sum += e;
-        if (drop && e != 0.f) e *= drop_factor(p, seed, step, bh, i, j);
-        sp[j] = e;
-      }
-      const float l = warp_sum(sum);
-      const float inv = 1.f / l;   // every key masked: 0/0 = NaN, as torch's softmax of all -inf
-      __syncwarp();
-      float* o = p.o + ((int64_t)b * p.Sq + i) * p.ldo + h * dh;
-      for (int d = lane; d < dh; d += 32) {
-        float a0 = 0.f, a1 = 0.f;
-        int j = 0;
-        for (; j + 1 < p.Sk; j += 2) {
-          a0 = fmaf(sp[j], v[(int64_t)j * p.ldv + d], a0);
-          a1 = fmaf(sp[j + 1], v[(int64_t)(j + 1) * p.ldv + d], a1);
+      if (BWD) {
+        const float* va = sV + lane * st;
+        const float* vb = sV + (lane + 32) * st;
+#pragma unroll 4
+        for (int d = 0; d < dh; ++d) {
+          dp0 = fmaf(di[d], va[d], dp0);
+          dp1 = fmaf(di[d], vb[d], dp1);
         }
-        if (j < p.Sk) a0 = fmaf(sp[j], v[(int64_t)j * p.ldv + d], a0);
-        o[d] = (a0 + a1) * inv;
       }
-      if (lane == 0) p.lse[(int64_t)bh * p.Sq + i] = mx + logf(l);
-    } else {
-      const float* dO = p.dout + ((int64_t)b * p.Sq + i) * p.ldo + h * dh;
-      const float* O = p.o + ((int64_t)b * p.Sq + i) * p.ldo + h * dh;
-      float dsum = 0.f;
-      for (int d = lane; d < dh; d += 32) {
-        const float g = dO[d];
-        sq[d] = q[d] * p.scale;
-        sdo[d] = g;
-        dsum = fmaf(g, O[d], dsum);
-      }
-      const float D = warp_sum(dsum);
-      const float L = p.lse[(int64_t)bh * p.Sq + i];
-      if (lane == 0) p.dvec[(int64_t)bh * p.Sq + i] = D;
-      __syncwarp();
-      for (int j = lane; j < p.Sk; j += 32) {
-        float pr = 0.f, dsc = 0.f;
-        if (!masked(p, ktok, i, j)) {
-          const float sc = dot_row(sq, k + (int64_t)j * p.ldk, dh);
-          const float dp = dot_row(sdo, v + (int64_t)j * p.ldv, dh);
-          pr = expf(sc - L);
-          float f = 1.f;
-          if (drop) f = drop_factor(p, seed, step, bh, i, j);
-          dsc = pr * (dp * f - D);
-          pr *= f;
+      const int j0 = k0 + lane, j1 = k0 + lane + 32;
+      const bool mk0 = masked(p, ktok, i, j0), mk1 = masked(p, ktok, i, j1);
+      float corr = 1.f;
+      if (!BWD) {
+        if (mk0) s0 = -INFINITY;
+        if (mk1) s1 = -INFINITY;
+        const float mx = warp_max(fmaxf(s0, s1));
+        const float mn = fmaxf(m, mx);
+        corr = mn == -INFINITY ? 1.f : expf(m - mn);
+        float e0 = mn == -INFINITY ? 0.f : expf(s0 - mn);
+        float e1 = mn == -INFINITY ? 0.f : expf(s1 - mn);
+        const float sum = warp_sum(e0 + e1);
+        if (drop && e0 != 0.f) e0 *= drop_factor(p, seed, step, bh, i, j0);
+        if (drop && e1 != 0.f) e1 *= drop_factor(p, seed, step, bh, i, j1);
+        sp[w * 64 + lane] = e0;
+        sp[w * 64 + lane + 32] = e1;
+        l = l * corr + sum;
+        m = mn;
+      } else {
+        float pr0 = 0.f, pr1 = 0.f, ds0 = 0.f, ds1 = 0.f;
+        if (!mk0) {
+          pr0 = expf(s0 - L);
+          const float f = drop ? drop_factor(p, seed, step, bh, i, j0) : 1.f;
+          ds0 = pr0 * (dp0 * f - D);
+          pr0 *= f;
         }
-        sp[j] = pr;
-        sds[j] = dsc;
+        if (!mk1) {
+          pr1 = expf(s1 - L);
+          const float f = drop ? drop_factor(p, seed, step, bh, i, j1) : 1.f;
+          ds1 = pr1 * (dp1 * f - D);
+          pr1 *= f;
+        }
+        sp[w * 64 + lane] = pr0;
+        sp[w * 64 + lane + 32] = pr1;
+        sds[w * 64 + lane] = ds0;
+        sds[w * 64 + lane + 32] = ds1;
       }
       __syncwarp();
-      float* gq = p.dq + ((int64_t)b * p.Sq + i) * p.ldq + h * dh;
-      float* gk = p.dk + (int64_t)b * p.Sk * p.ldk + h * dh;
-      float* gv = p.dv + (int64_t)b * p.Sk * p.ldv + h * dh;
-      for (int d = lane; d < dh; d += 32) {
-        float a0 = 0.f, a1 = 0.f;
-        int j = 0;
-        for (; j + 1 < p.Sk; j += 2) {
-          a0 = fmaf(sds[j], k[(int64_t)j * p.ldk + d], a0);
-          a1 = fmaf(sds[j + 1], k[(int64_t)(j + 1) * p.ldk + d], a1);
-        }
-        if (j < p.Sk) a0 = fmaf(sds[j], k[(int64_t)j * p.ldk + d], a0);
-        gq[d] = (a0 + a1) * p.scale;
-        const float qd = sq[d], od = sdo[d];   // q carries the 1/sqrt(dh) scale
-        if (i == 0) {
-          for (j = 0; j < p.Sk; ++j) {
-            gk[(int64_t)j * p.ldk + d] = sds[j] * qd;
-            gv[(int64_t)j * p.ldv + d] = sp[j] * od;
+      // fwd: acc = acc * corr + P V;  bwd: acc += dS K   (lanes over head columns)
+      const float* wrow = (BWD ? sds : sp) + w * 64;
+      const float* tile = BWD ? sK : sV;
+#pragma unroll
+      for (int c = 0; c < MHA_SMALL_C; ++c) {
+        const int d = lane + 32 * c;
+        if (d < dh) {
+          float a0 = acc[c] * corr, a1 = 0.f;
+#pragma unroll 4
+          for (int j = 0; j < 64; j += 2) {
+            a0 = fmaf(wrow[j], tile[j * st + d], a0);
+            a1 = fmaf(wrow[j + 1], tile[(j + 1) * st + d], a1);
           }
-        } else {   // later query rows of the same (sequence, head): this warp wrote the earlier ones
-          for (j = 0; j < p.Sk; ++j) {
-            gk[(int64_t)j * p.ldk + d] += sds[j] * qd;
-            gv[(int64_t)j * p.ldv + d] += sp[j] * od;
-          }
+          acc[c] = a0 + a1;
         }
       }
     }
+    if (BWD) {
+      __syncthreads();
+      // dK[j] = sum_i dS[i][j] q_i (q carries the 1/sqrt(dh) scale), dV[j] = sum_i P[i][j] dO_i
+      for (int idx = threadIdx.x; idx < 64 * dh; idx += blockDim.x) {
+        const int j = idx / dh, d = idx - j * dh;
+        if (k0 + j >= p.Sk) break;
+        float gk = 0.f, gv = 0.f;
+        for (int ii = 0; ii < p.Sq; ++ii) {
+          gk = fmaf(sds[ii * 64 + j], sq[ii * dh + d], gk);
+          gv = fmaf(sp[ii * 64 + j], sdo[ii * dh + d], gv);
+        }
+        p.dk[((int64_t)b * p.Sk + k0 + j) * p.ldk + h * dh + d] = gk;
+        p.dv[((int64_t)b * p.Sk + k0 + j) * p.ldv + h * dh + d] = gv;
+      }
+    }
+  }
+  if (!active) return;
+  if (!BWD) {
+    const float inv = 1.f / l;   // every key masked: 0/0 = NaN, as torch's softmax of all -inf
+    float* o = p.o + ((int64_t)b * p.Sq + i) * p.ldo + h * dh;
+#pragma unroll
+    for (int c = 0; c < MHA_SMALL_C; ++c)
+      if (lane + 32 * c < dh) o[lane + 32 * c] = acc[c] * inv;
+    if (lane == 0) p.lse[(int64_t)bh * p.Sq + i] = m + logf(l);
+  } else {
+    float* gq = p.dq + ((int64_t)b * p.Sq + i) * p.ldq + h * dh;
+#pragma unroll
+    for (int c = 0; c < MHA_SMALL_C; ++c)
+      if (lane + 32 * c < dh) gq[lane + 32 * c] = acc[c] * p.scale;
   }
 }
 
-static bool mha_small_ok(const MhaArgs& a) { return a.Sq <= MHA_SMALL_SQ && a.Sk <= MHA_SMALL_SK; }
+static bool mha_small_ok(const MhaArgs& a) { return a.Sq <= MHA_SMALL_SQ; }
 
 template <bool BWD>
 static int launch_mha_small(const MhaArgs& a, cudaStream_t s) {
-  const size_t smem = (size_t)MHA_SMALL_WARPS * (BWD ? 2 : 1) * (a.dh + a.Sk) * sizeof(float);
-  launch_pdl(mha_small_kernel<BWD>, dim3(ceil_div(a.B * a.nhead, MHA_SMALL_WARPS)), dim3(MHA_SMALL_WARPS * 32), smem, s, a);
+  const size_t smem = (size_t)(2 * 64 * (a.dh + 1) + 8 * a.dh + 512) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(mha_small_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return fail("mha(small): cannot raise the shared-memory limit");
+    attr = true;
+  }
+  SLNLP_CHECK_ARG((int64_t)a.B * a.nhead <= 0x7fffffff, "mha: grid too large");
+  launch_pdl(mha_small_kernel<BWD>, dim3(a.B * a.nhead), dim3(128), smem, s, a);
   SLNLP_LAUNCH_OK(BWD ? "mha_bwd(small)" : "mha_fwd(small)");
   return 0;
 }
@@ -718,10 +1184,10 @@ using namespace slnlp;
   if ((a).dh <= 128) return FN<4, 8>(a, s);             \
   return FN<2, 16>(a, s);
 
-extern "C" int slnlp_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                             float* o, int ldo, float* lse, int B, int Sq, int Sk, int nhead, int dh,
-                             int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
-                             const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
+static int mha_fwd_entry(bool tc, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                         float* o, int ldo, float* lse, int B, int Sq, int Sk, int nhead, int dh,
+                         int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                         const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(q && k && v && o && lse, "mha_fwd: null pointer");
   MhaArgs a{};
   a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.o = o; a.ldo = ldo; a.lse = lse;
@@ -730,14 +1196,19 @@ extern "C" int slnlp_mha_fwd(const float* q, int ldq, const float* k, int ldk, c
   a.p_drop = p_drop; a.rng = rng; a.site = site;
   if (int rc = check_mha(a, "mha_fwd")) return rc;
   if (mha_small_ok(a)) return launch_mha_small<false>(a, as_stream(stream));
+  if (tc && mha_tc_ok(a)) {
+    if (dh == 16) return launch_mha_tc_fwd<16>(a, as_stream(stream));
+    if (dh == 32) return launch_mha_tc_fwd<32>(a, as_stream(stream));
+    return launch_mha_tc_fwd<64>(a, as_stream(stream));
+  }
   MHA_DISPATCH(launch_mha_fwd, a, as_stream(stream));
 }
 
-extern "C" int slnlp_mha_bwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                             const float* o, const float* dout, int ldo, const float* lse, float* dvec,
-                             float* dq, float* dk, float* dv, int B, int Sq, int Sk, int nhead, int dh,
-                             int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
-                             const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
+static int mha_bwd_entry(bool tc, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                         const float* o, const float* dout, int ldo, const float* lse, float* dvec,
+                         float* dq, float* dk, float* dv, int B, int Sq, int Sk, int nhead, int dh,
+                         int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                         const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(q && k && v && o && dout && lse && dvec && dq && dk && dv, "mha_bwd: null pointer");
   MhaArgs a{};
   a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.o = const_cast<float*>(o); a.dout = dout;
@@ -747,7 +1218,43 @@ extern "C" int slnlp_mha_bwd(const float* q, int ldq, const float* k, int ldk, c
   a.p_drop = p_drop; a.rng = rng; a.site = site;
   if (int rc = check_mha(a, "mha_bwd")) return rc;
   if (mha_small_ok(a)) return launch_mha_small<true>(a, as_stream(stream));
+  if (tc && mha_tc_ok(a)) {
+    if (dh == 16) return launch_mha_tc_bwd<16>(a, as_stream(stream));
+    if (dh == 32) return launch_mha_tc_bwd<32>(a, as_stream(stream));
+    return launch_mha_tc_bwd<64>(a, as_stream(stream));
+  }
   MHA_DISPATCH(launch_mha_bwd, a, as_stream(stream));
+}
+
+extern "C" int slnlp_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                             float* o, int ldo, float* lse, int B, int Sq, int Sk, int nhead, int dh,
+                             int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                             const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
+  return mha_fwd_entry(false, q, ldq, k, ldk, v, ldv, o, ldo, lse, B, Sq, Sk, nhead, dh, causal, key_tokens, pad_idx,
+                       p_drop, rng, site, stream);
+}
+extern "C" int slnlp_mha_tf32_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                                  float* o, int ldo, float* lse, int B, int Sq, int Sk, int nhead, int dh,
+                                  int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                                  const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
+  return mha_fwd_entry(true, q, ldq, k, ldk, v, ldv, o, ldo, lse, B, Sq, Sk, nhead, dh, causal, key_tokens, pad_idx,
+                       p_drop, rng, site, stream);
+}
+extern "C" int slnlp_mha_bwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                             const float* o, const float* dout, int ldo, const float* lse, float* dvec,
+                             float* dq, float* dk, float* dv, int B, int Sq, int Sk, int nhead, int dh,
+                             int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                             const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
+  return mha_bwd_entry(false, q, ldq, k, ldk, v, ldv, o, dout, ldo, lse, dvec, dq, dk, dv, B, Sq, Sk, nhead, dh, causal,
+                       key_tokens, pad_idx, p_drop, rng, site, stream);
+}
+extern "C" int slnlp_mha_tf32_bwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                                  const float* o, const float* dout, int ldo, const float* lse, float* dvec,
+                                  float* dq, float* dk, float* dv, int B, int Sq, int Sk, int nhead, int dh,
+                                  int causal, const int64_t* key_tokens, int64_t pad_idx, float p_drop,
+                                  const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
+  return mha_bwd_entry(true, q, ldq, k, ldk, v, ldv, o, dout, ldo, lse, dvec, dq, dk, dv, B, Sq, Sk, nhead, dh, causal,
+                       key_tokens, pad_idx, p_drop, rng, site, stream);
 }
 
 extern "C" int slnlp_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,

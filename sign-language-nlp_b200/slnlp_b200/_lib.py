@@ -58,6 +58,8 @@ SIGNATURES = {
     "slnlp_sgd_momentum_clip": [P, P, P, L, P, P, F, P],
     "slnlp_mha_fwd": [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, P, L, F, P, U32, P],
     "slnlp_mha_bwd": [P, I, P, I, P, I, P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, L, F, P, U32, P],
+    "slnlp_mha_tf32_fwd": [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, P, L, F, P, U32, P],
+    "slnlp_mha_tf32_bwd": [P, I, P, I, P, I, P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, L, F, P, U32, P],
     "slnlp_add_layernorm_fwd": [P, P, P, P, P, P, P, I, I, F, P],
     "slnlp_ln_bwd_blocks": [I],
     "slnlp_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, I, P],

@@ -186,6 +186,7 @@ class FlatParamModule(nn.Module):
         ev = torch.cuda.Event()
         ev.record()
         side.wait_event(ev)
+        self._side_pending = True
         return side
 
     @contextlib.contextmanager
@@ -196,8 +197,9 @@ class FlatParamModule(nn.Module):
 
     def _join_side(self):
         side = getattr(self, "_side", None)
-        if side is None:
-            return
+        if side is None or not getattr(self, "_side_pending", False):
+            return   # nothing forked since the last join (and, under graph capture, no branch to merge)
+        self._side_pending = False
         ev = torch.cuda.Event()
         ev.record(side)
         torch.cuda.current_stream().wait_event(ev)

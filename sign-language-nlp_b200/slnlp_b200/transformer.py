@@ -14,8 +14,10 @@ Quirks of the reference kept on purpose:
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
+import os
 from typing import List
 
 import torch
@@ -61,6 +63,7 @@ class TransformerB200(FlatParamModule):
         self.src_pad = src_vocab.stoi[PAD_WORD]            # generate_padding_mask, model/util/util.py:45-61
         self.tgt_pad = tgt_vocab.stoi[PAD_WORD]
         self.validate_inputs = True
+        self.overlap_small = os.environ.get("SLNLP_OVERLAP_SMALL", "1") != "0"
         self.seed = int(kwargs.get("seed", torch.initial_seed() & 0x7FFFFFFF))
         self._build_parameters()
 
@@ -108,13 +111,19 @@ class TransformerB200(FlatParamModule):
                  b_off=0):
         """gW += dy^T x; gb += colsum(dy); dx = beta_dx*dx + dy W   (dx may be None)"""
         lddy = lddy or n_out
-        self._gemm(1, 0, n_out, n_in, rows, dy, lddy, x, ldx or n_in, self._ptr(w, g) + 4 * w_off * n_in, n_in, None,
-                   1.0, big=big)
-        if b:
-            check(lib.slnlp_colsum_f32(dy, rows, n_out, lddy, self._ptr(b, g) + 4 * b_off, 1.0, _stream()), "colsum")
+        # The one-token decoder's weight gradients (rows = batch) are leaves of the dependency graph
+        # and a fraction of a wave: they run on the side stream next to the d(activation) chain.
+        # The previous side branch is joined first, so dy / x buffers recycled by later layers are
+        # never overwritten under a pending read.
+        self._join_side()
         if dx is not None:
             self._gemm(0, 0, rows, n_in, n_out, dy, lddy, self._ptr(w) + 4 * w_off * n_in, n_in, dx, n_in, None,
                        beta_dx, big=big)
+        with (self._side_branch() if (self.overlap_small and not big) else contextlib.nullcontext()):
+            self._gemm(1, 0, n_out, n_in, rows, dy, lddy, x, ldx or n_in, self._ptr(w, g) + 4 * w_off * n_in, n_in, None,
+                       1.0, big=big)
+            if b:
+                check(lib.slnlp_colsum_f32(dy, rows, n_out, lddy, self._ptr(b, g) + 4 * b_off, 1.0, _stream()), "colsum")
 
     def _ln_fwd(self, x, res, name, y, stats, rows):
         check(lib.slnlp_add_layernorm_fwd(x, res, self._ptr(name + ".weight"), self._ptr(name + ".bias"), y,
@@ -135,14 +144,16 @@ class TransformerB200(FlatParamModule):
 
     def _mha_fwd(self, ws, q, ldq, k, ldk, v, ldv, o, lse, Sq, Sk, causal, tokens, pad, site):
         p = self.p_drop if ws.train else 0.0
-        check(lib.slnlp_mha_fwd(q, ldq, k, ldk, v, ldv, o, self.E, lse, ws.B, Sq, Sk, self.nhead, self.dh, causal,
-                                tokens, pad, p, self._rng_state().data_ptr() if p > 0 else None, site, _stream()), "mha_fwd")
+        fn = lib.slnlp_mha_tf32_fwd if self.precision == "bf16" else lib.slnlp_mha_fwd
+        check(fn(q, ldq, k, ldk, v, ldv, o, self.E, lse, ws.B, Sq, Sk, self.nhead, self.dh, causal,
+                 tokens, pad, p, self._rng_state().data_ptr() if p > 0 else None, site, _stream()), "mha_fwd")
 
     def _mha_bwd(self, ws, q, ldq, k, ldk, v, ldv, o, do, lse, dq, dk, dv, Sq, Sk, causal, tokens, pad, site):
         p = self.p_drop if ws.train else 0.0
-        check(lib.slnlp_mha_bwd(q, ldq, k, ldk, v, ldv, o, do, self.E, lse, ws.dvec.data_ptr(), dq, dk, dv, ws.B, Sq, Sk,
-                                self.nhead, self.dh, causal, tokens, pad, p,
-                                self._rng_state().data_ptr() if p > 0 else None, site, _stream()), "mha_bwd")
+        fn = lib.slnlp_mha_tf32_bwd if self.precision == "bf16" else lib.slnlp_mha_bwd
+        check(fn(q, ldq, k, ldk, v, ldv, o, do, self.E, lse, ws.dvec.data_ptr(), dq, dk, dv, ws.B, Sq, Sk,
+                 self.nhead, self.dh, causal, tokens, pad, p,
+                 self._rng_state().data_ptr() if p > 0 else None, site, _stream()), "mha_bwd")
 
     def _ffn_fwd(self, ws, pre, x, st, rows, site, big):
         """st.hdn = dropout(relu(x W1^T + b1)); st.f = dropout(hdn W2^T + b2)"""
@@ -311,6 +322,7 @@ class TransformerB200(FlatParamModule):
         self._drop(ws, cur, R * E, 0)
         check(lib.slnlp_embed_gather_bwd(self._ptr("src_embedding.weight", g), X.data_ptr(), cur, B, S, 1, ws.f_off, ws.f_w,
                                          ws.f_rows_src, 0, scale, -1, s), "embed_bwd")
+        self._join_side()
 
     def _masked_grad(self, ws, src, tmp, n, site):
         """Gradient through a dropout site that must leave ``src`` intact (it also feeds the
