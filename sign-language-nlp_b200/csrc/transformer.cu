@@ -516,6 +516,45 @@ __device__ __forceinline__ uint32_t key_mask_bits(const MhaArgs& p, const int64_
   return bits;
 }
 
+// NT tiles at once: U float4 loads per tile and thread are in flight before the first shared
+// store, so a CTA pays one L2 / HBM round trip per pass for all its operands instead of one per tile
+struct TileSrc {
+  float* s;
+  const float* g;
+  int ld, r0, rows;
+  float mul;
+};
+template <int NT, int U>
+__device__ __forceinline__ void load_tiles_v(const TileSrc (&ts)[NT], int dh, int st) {
+  const int c4n = dh >> 2, total = 64 * c4n;
+  for (int e0 = threadIdx.x; e0 < total; e0 += U * blockDim.x) {
+    float4 v[NT][U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * blockDim.x;
+      const int r = e / c4n, c4 = (e - r * c4n) << 2;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        v[n][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < total && ts[n].r0 + r < ts[n].rows)
+          v[n][u] = *reinterpret_cast<const float4*>(ts[n].g + (int64_t)(ts[n].r0 + r) * ts[n].ld + c4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * blockDim.x;
+      const int r = e / c4n, c4 = (e - r * c4n) << 2;
+      if (e < total) {
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const float m = ts[n].mul;
+          *reinterpret_cast<float4*>(ts[n].s + r * st + c4) = make_float4(v[n][u].x * m, v[n][u].y * m, v[n][u].z * m, v[n][u].w * m);
+        }
+      }
+    }
+  }
+}
+
 constexpr int TC_N = 64;        // tile edge
 constexpr int TC_SP = TC_N + 4; // P / dS row stride
 
@@ -540,18 +579,22 @@ __global__ void __launch_bounds__(128) mha_tc_fwd_kernel(MhaArgs p) {
   const bool drop = p.p_drop > 0.f;
   const uint64_t seed = drop ? p.rng[0] : 0, step = drop ? p.rng[1] : 0;
 
-  load_tile_v(sQ, q, p.ldq, i0, p.Sq, DH, ST, p.scale);
   float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
   float acc[NTD][4];
 #pragma unroll
   for (int n = 0; n < NTD; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
   for (int k0 = 0; k0 < p.Sk; k0 += N) {
     if (p.causal && k0 > i0 + N - 1) break;
-    __syncthreads();
-    load_tile_v(sK, k, p.ldk, k0, p.Sk, DH, ST, 1.f);
-    load_tile_v(sV, v, p.ldv, k0, p.Sk, DH, ST, 1.f);
-    __syncthreads();
     const uint32_t kbits = key_mask_bits(p, ktok, k0, t);
+    __syncthreads();
+    if (k0 == 0) {
+      const TileSrc ts[3] = {{sQ, q, p.ldq, i0, p.Sq, p.scale}, {sK, k, p.ldk, k0, p.Sk, 1.f}, {sV, v, p.ldv, k0, p.Sk, 1.f}};
+      load_tiles_v<3, 4>(ts, DH, ST);
+    } else {
+      const TileSrc ts[2] = {{sK, k, p.ldk, k0, p.Sk, 1.f}, {sV, v, p.ldv, k0, p.Sk, 1.f}};
+      load_tiles_v<2, 4>(ts, DH, ST);
+    }
+    __syncthreads();
     float s[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
@@ -638,6 +681,7 @@ __device__ __forceinline__ void tc_bwd_tile(const MhaArgs& p, const float* sQ, c
   }
   mma_nk<8, DH / 8>(s, sQ, ST, 16 * w, sK, ST, g, t);      // Q carries the 1/sqrt(dh) scale
   mma_nk<8, DH / 8>(dp, sDO, ST, 16 * w, sV, ST, g, t);
+  __syncthreads();   // sP / sDS reuse the K / V tiles' shared memory: every warp is done reading them
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int row = 16 * w + g + 8 * r, i = i0 + row;
@@ -662,26 +706,30 @@ __device__ __forceinline__ void tc_bwd_tile(const MhaArgs& p, const float* sQ, c
           pr[e] *= f[e];
         }
       }
-      *reinterpret_cast<float2*>(sP + row * SP + n * 8 + 2 * t) = make_float2(pr[0], pr[1]);
+      if (sP) *reinterpret_cast<float2*>(sP + row * SP + n * 8 + 2 * t) = make_float2(pr[0], pr[1]);
       *reinterpret_cast<float2*>(sDS + row * SP + n * 8 + 2 * t) = make_float2(dsc[0], dsc[1]);
     }
   }
 }
 
 // DKV = false: grid (ceil(Sq/64), nhead, B), writes D and dQ.  DKV = true: grid (ceil(Sk/64), nhead, B),
-// writes dK and dV.  block 128.  smem: Q, K, V, dO [64][DH+4] + P, dS [64][68].
+// writes dK and dV.  block 128.  smem: Q, dO [64][DH+4] and two more tiles of max([64][DH+4],
+// [64][68]) floats that hold K / V for the tile products and then P / dS (dQ pass: K stays, dS
+// takes V's place) - four tiles, so that three CTAs fit an SM and 400 (sequence, head) CTAs are
+// one wave.
 template <int DH, bool DKV>
-__global__ void __launch_bounds__(128) mha_tc_bwd_kernel(MhaArgs p) {
+__global__ void __launch_bounds__(128, 3) mha_tc_bwd_kernel(MhaArgs p) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int N = TC_N, ST = DH + 4, SP = TC_SP, NTD = DH / 8;
+  constexpr int TS = N * (ST > SP ? ST : SP);
   extern __shared__ float sm[];
   float* sQ = sm;
-  float* sK = sQ + N * ST;
-  float* sV = sK + N * ST;
-  float* sDO = sV + N * ST;
-  float* sP = sDO + N * ST;
-  float* sDS = sP + N * SP;
+  float* sDO = sQ + N * ST;
+  float* sK = sDO + N * ST;
+  float* sV = sK + TS;
+  float* sP = DKV ? sK : nullptr;
+  float* sDS = sV;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z, bh = b * p.nhead + h;
   const float* q = p.q + (int64_t)b * p.Sq * p.ldq + h * DH;
@@ -699,8 +747,6 @@ __global__ void __launch_bounds__(128) mha_tc_bwd_kernel(MhaArgs p) {
 
   if (!DKV) {
     const int i0 = blockIdx.x * N;
-    load_tile_v(sQ, q, p.ldq, i0, p.Sq, DH, ST, p.scale);
-    load_tile_v(sDO, dO, p.ldo, i0, p.Sq, DH, ST, 1.f);
     // D_i = <dO_i, O_i>: two threads per row, each half a row of independent float4 loads
     {
       const float* O = p.o + (int64_t)b * p.Sq * p.ldo + h * DH;
@@ -727,8 +773,14 @@ __global__ void __launch_bounds__(128) mha_tc_bwd_kernel(MhaArgs p) {
     for (int k0 = 0; k0 < p.Sk; k0 += N) {
       if (p.causal && k0 > i0 + N - 1) break;
       __syncthreads();
-      load_tile_v(sK, k, p.ldk, k0, p.Sk, DH, ST, 1.f);
-      load_tile_v(sV, v, p.ldv, k0, p.Sk, DH, ST, 1.f);
+      if (k0 == 0) {
+        const TileSrc ts[4] = {{sQ, q, p.ldq, i0, p.Sq, p.scale}, {sDO, dO, p.ldo, i0, p.Sq, 1.f},
+                               {sK, k, p.ldk, k0, p.Sk, 1.f}, {sV, v, p.ldv, k0, p.Sk, 1.f}};
+        load_tiles_v<4, 2>(ts, DH, ST);
+      } else {
+        const TileSrc ts[2] = {{sK, k, p.ldk, k0, p.Sk, 1.f}, {sV, v, p.ldv, k0, p.Sk, 1.f}};
+        load_tiles_v<2, 4>(ts, DH, ST);
+      }
       __syncthreads();
       tc_bwd_tile<DH>(p, sQ, sK, sV, sDO, sP, sDS, lse, dvec, ktok, bh, i0, k0, seed, step, w, g, t);
       __syncwarp();
@@ -748,13 +800,14 @@ __global__ void __launch_bounds__(128) mha_tc_bwd_kernel(MhaArgs p) {
 #pragma unroll
     for (int n = 0; n < NTD; ++n) acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f;
     const int k0 = blockIdx.x * N;
-    load_tile_v(sK, k, p.ldk, k0, p.Sk, DH, ST, 1.f);
-    load_tile_v(sV, v, p.ldv, k0, p.Sk, DH, ST, 1.f);
     for (int i0 = 0; i0 < p.Sq; i0 += N) {
       if (p.causal && i0 + N - 1 < k0) continue;
       __syncthreads();
-      load_tile_v(sQ, q, p.ldq, i0, p.Sq, DH, ST, p.scale);
-      load_tile_v(sDO, dO, p.ldo, i0, p.Sq, DH, ST, 1.f);
+      {   // K / V again for every query tile: P / dS of the previous one lived in their place
+        const TileSrc ts[4] = {{sQ, q, p.ldq, i0, p.Sq, p.scale}, {sDO, dO, p.ldo, i0, p.Sq, 1.f},
+                               {sK, k, p.ldk, k0, p.Sk, 1.f}, {sV, v, p.ldv, k0, p.Sk, 1.f}};
+        load_tiles_v<4, 2>(ts, DH, ST);
+      }
       __syncthreads();
       tc_bwd_tile<DH>(p, sQ, sK, sV, sDO, sP, sDS, lse, dvec, ktok, bh, i0, k0, seed, step, w, g, t);
       __syncthreads();
@@ -794,7 +847,7 @@ static int launch_mha_tc_fwd(const MhaArgs& a, cudaStream_t s) {
 
 template <int DH>
 static int launch_mha_tc_bwd(const MhaArgs& a, cudaStream_t s) {
-  constexpr size_t smem = (size_t)(4 * TC_N * (DH + 4) + 2 * TC_N * TC_SP) * sizeof(float);
+  constexpr size_t smem = (size_t)(2 * TC_N * (DH + 4) + 2 * TC_N * (DH + 4 > TC_SP ? DH + 4 : TC_SP)) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(mha_tc_bwd_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
@@ -818,6 +871,36 @@ static int launch_mha_tc_bwd(const MhaArgs& a, cudaStream_t s) {
 // and all-masked-row NaN as the tile kernels; fp32 throughout.
 constexpr int MHA_SMALL_SQ = 4;
 constexpr int MHA_SMALL_C = 8;   // head columns per lane: dh <= 256
+
+// rows [k0, k0+nk) of K and V -> smem tiles [64][dh+1]; the loads of both tiles are in flight
+// together (one L2 round trip), rows past nk are left untouched (never read)
+__device__ __forceinline__ void stage_kv(float* sK, float* sV, const float* k, const float* v, int ldk, int ldv,
+                                         int k0, int nk, int dh) {
+  const int st = dh + 1, c4n = dh >> 2, total = nk * c4n;
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * blockDim.x;
+      if (e < total) {
+        const int r = e / c4n, c4 = (e - r * c4n) << 2;
+        a[u] = *reinterpret_cast<const float4*>(k + (int64_t)(k0 + r) * ldk + c4);
+        b[u] = *reinterpret_cast<const float4*>(v + (int64_t)(k0 + r) * ldv + c4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * blockDim.x;
+      if (e < total) {
+        const int r = e / c4n, c4 = (e - r * c4n) << 2;
+        float* dk = sK + r * st + c4;
+        float* dv = sV + r * st + c4;
+        dk[0] = a[u].x; dk[1] = a[u].y; dk[2] = a[u].z; dk[3] = a[u].w;
+        dv[0] = b[u].x; dv[1] = b[u].y; dv[2] = b[u].z; dv[3] = b[u].w;
+      }
+    }
+  }
+}
 
 // smem: K, V [64][dh+1] | q [4][dh] | dO [4][dh] | p [4][64] | ds [4][64]
 template <bool BWD>
@@ -861,9 +944,13 @@ __global__ void __launch_bounds__(128) mha_small_kernel(MhaArgs p) {
     if (lane == 0) p.dvec[(int64_t)bh * p.Sq + i] = D;
   }
   for (int k0 = 0; k0 < p.Sk; k0 += 64) {
+    const int nk = min(64, p.Sk - k0);   // keys present in this chunk (the 1 x 1 self-attention has one)
+    const int j0 = k0 + lane, j1 = k0 + lane + 32;
+    // key-padding tokens are fetched with the tiles, not when the mask is applied
+    const int64_t tok0 = (ktok && j0 < p.Sk) ? ktok[j0] : p.pad_idx + 1;
+    const int64_t tok1 = (ktok && j1 < p.Sk) ? ktok[j1] : p.pad_idx + 1;
     __syncthreads();
-    load_tile<64>(sK, k, p.ldk, k0, p.Sk, dh, 1.f);
-    load_tile<64>(sV, v, p.ldv, k0, p.Sk, dh, 1.f);
+    stage_kv(sK, sV, k, v, p.ldk, p.ldv, k0, nk, dh);
     __syncthreads();
     if (active) {
       const float* qi = sq + i * dh;
@@ -871,22 +958,32 @@ __global__ void __launch_bounds__(128) mha_small_kernel(MhaArgs p) {
       float s0 = 0.f, s1 = 0.f, dp0 = 0.f, dp1 = 0.f;
       const float* ka = sK + lane * st;
       const float* kb = sK + (lane + 32) * st;
+      if (nk > 32) {
 #pragma unroll 4
-      for (int d = 0; d < dh; ++d) {
-        s0 = fmaf(qi[d], ka[d], s0);
-        s1 = fmaf(qi[d], kb[d], s1);
+        for (int d = 0; d < dh; ++d) {
+          s0 = fmaf(qi[d], ka[d], s0);
+          s1 = fmaf(qi[d], kb[d], s1);
+        }
+      } else if (lane < nk) {
+#pragma unroll 4
+        for (int d = 0; d < dh; ++d) s0 = fmaf(qi[d], ka[d], s0);
       }
       if (BWD) {
         const float* va = sV + lane * st;
         const float* vb = sV + (lane + 32) * st;
+        if (nk > 32) {
 #pragma unroll 4
-        for (int d = 0; d < dh; ++d) {
-          dp0 = fmaf(di[d], va[d], dp0);
-          dp1 = fmaf(di[d], vb[d], dp1);
+          for (int d = 0; d < dh; ++d) {
+            dp0 = fmaf(di[d], va[d], dp0);
+            dp1 = fmaf(di[d], vb[d], dp1);
+          }
+        } else if (lane < nk) {
+#pragma unroll 4
+          for (int d = 0; d < dh; ++d) dp0 = fmaf(di[d], va[d], dp0);
         }
       }
-      const int j0 = k0 + lane, j1 = k0 + lane + 32;
-      const bool mk0 = masked(p, ktok, i, j0), mk1 = masked(p, ktok, i, j1);
+      const bool mk0 = j0 >= p.Sk || (p.causal && j0 > i) || tok0 == p.pad_idx;
+      const bool mk1 = j1 >= p.Sk || (p.causal && j1 > i) || tok1 == p.pad_idx;
       float corr = 1.f;
       if (!BWD) {
         if (mk0) s0 = -INFINITY;
@@ -931,11 +1028,13 @@ __global__ void __launch_bounds__(128) mha_small_kernel(MhaArgs p) {
         const int d = lane + 32 * c;
         if (d < dh) {
           float a0 = acc[c] * corr, a1 = 0.f;
+          int j = 0;
 #pragma unroll 4
-          for (int j = 0; j < 64; j += 2) {
+          for (; j + 1 < nk; j += 2) {
             a0 = fmaf(wrow[j], tile[j * st + d], a0);
             a1 = fmaf(wrow[j + 1], tile[(j + 1) * st + d], a1);
           }
+          if (j < nk) a0 = fmaf(wrow[j], tile[j * st + d], a0);
           acc[c] = a0 + a1;
         }
       }
