@@ -6,8 +6,10 @@
 
 namespace slnlp {
 
-// grid = B, block = 256.  Dynamic smem: T floats (scores -> alphas).
-__global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ q,
+// grid = B, block = 256 or 1024 (one warp per 2-8 timesteps: every phase is a short chain of
+// dependent global loads, so more warps = fewer serial round trips).  Dynamic smem: T floats
+// (scores -> alphas) + [warps][W] partial contexts.
+__global__ void __launch_bounds__(1024) attn_fwd_kernel(const float* __restrict__ q,
                                                        const float* __restrict__ pk,
                                                        const float* __restrict__ v,
                                                        const float* __restrict__ val,
@@ -79,8 +81,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
   }
 }
 
-// grid = B, block = 256.  Dynamic smem: T floats (dscore).
-__global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__ dctx,
+// grid = B, block = 256 or 1024.  Dynamic smem: T floats (dscore) + [warps][2][H] partial sums.
+__global__ void __launch_bounds__(1024) attn_bwd_kernel(const float* __restrict__ dctx,
                                                        const float* __restrict__ q,
                                                        const float* __restrict__ pk,
                                                        const float* __restrict__ v,
@@ -155,10 +157,12 @@ extern "C" int slnlp_attn_step_fwd(const float* q, const float* pk, const float*
                                    float* alpha, float* ctx, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(q && pk && v && val && X && alpha && ctx, "attn_step_fwd: null pointer");
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && W > 0 && T <= 12000, "attn_step_fwd: bad shape");
-  const size_t smf = (size_t)(T + 8 * W) * sizeof(float);
+  int threads = T >= 32 ? 1024 : 256;
+  if ((size_t)(T + (threads / 32) * W) * sizeof(float) > 200 * 1024) threads = 256;
+  const size_t smf = (size_t)(T + (threads / 32) * W) * sizeof(float);
   SLNLP_CHECK_ARG(smf <= 200 * 1024, "attn_step_fwd: T + 8*W too large for shared memory");
-  if (smf > 48 * 1024) cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf);
-  launch_pdl(attn_fwd_kernel, dim3(B), dim3(256), smf, as_stream(stream), q, pk, v, val, X, pad_idx, T, B, H, W, alpha, ctx);
+  if (smf > 48 * 1024) cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  launch_pdl(attn_fwd_kernel, dim3(B), dim3(threads), smf, as_stream(stream), q, pk, v, val, X, pad_idx, T, B, H, W, alpha, ctx);
   SLNLP_LAUNCH_OK("attn_step_fwd");
   return 0;
 }
@@ -169,10 +173,12 @@ extern "C" int slnlp_attn_step_bwd(const float* dctx, const float* q, const floa
                                    slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(dctx && q && pk && v && val && alpha && dval && dpk && dq && dv_part, "attn_step_bwd: null pointer");
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && W > 0 && T <= 12000, "attn_step_bwd: bad shape");
-  const size_t smb = (size_t)(T + 16 * H) * sizeof(float);
+  int threads = T >= 32 ? 1024 : 256;
+  if ((size_t)(T + (threads / 32) * 2 * H) * sizeof(float) > 200 * 1024) threads = 256;
+  const size_t smb = (size_t)(T + (threads / 32) * 2 * H) * sizeof(float);
   SLNLP_CHECK_ARG(smb <= 200 * 1024, "attn_step_bwd: T + 16*H too large for shared memory");
-  if (smb > 48 * 1024) cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
-  launch_pdl(attn_bwd_kernel, dim3(B), dim3(256), smb, as_stream(stream), dctx, q, pk, v, val, alpha, T, B, H, W, dval, dpk, dq, dv_part);
+  if (smb > 48 * 1024) cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  launch_pdl(attn_bwd_kernel, dim3(B), dim3(threads), smb, as_stream(stream), dctx, q, pk, v, val, alpha, T, B, H, W, dval, dpk, dq, dv_part);
   SLNLP_LAUNCH_OK("attn_step_bwd");
   return 0;
 }

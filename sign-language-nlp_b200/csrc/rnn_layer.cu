@@ -438,9 +438,10 @@ extern "C" int slnlp_rnn_layer_fwd(int mode, int precision, int T, int B, int H,
   SLNLP_CHECK_ARG(gates && w_hh && b_hh && out && stash, "rnn_layer_fwd: null pointer");
   cudaStream_t s = as_stream(stream);
   if (precision == 1) {
-    const int rc = rnn_layer_fwd_tc(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
+    // a single step (the decoder cell) is not worth staging W_hh into tensor memory: per-step kernel
+    const int rc = T > 1 ? rnn_layer_fwd_tc(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s) : -1;
     if (rc >= 0) return rc;
-    const int rc1 = rnn_layer_fwd_cluster(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
+    const int rc1 = T <= 1 ? -1 : rnn_layer_fwd_cluster(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
     if (rc1 >= 0) return rc1;
     const int rc2 = rnn_layer_fwd_tcstep(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
     if (rc2 >= 0) return rc2;
@@ -469,10 +470,10 @@ extern "C" int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H,
   SLNLP_CHECK_ARG(!(dh0 || dc0) || !lengths, "rnn_layer_bwd: dh0/dc0 need lengths == NULL");
   cudaStream_t s = as_stream(stream);
   if (precision == 1) {
-    const int rc = rnn_layer_bwd_tc(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
-                                    dc_final, dh0, dc0, s);
+    const int rc = T > 1 ? rnn_layer_bwd_tc(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
+                                            dc_final, dh0, dc0, s) : -1;
     if (rc >= 0) return rc;
-    const int rc1 = rnn_layer_bwd_cluster(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
+    const int rc1 = T <= 1 ? -1 : rnn_layer_bwd_cluster(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
                                           dc_final, dh0, dc0, s);
     if (rc1 >= 0) return rc1;
     const int rc2 = rnn_layer_bwd_tcstep(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,

@@ -164,7 +164,9 @@ class RnnEncDecB200(FlatParamModule):
                                       self._ptr("model.decoder.attention.energy_layer.weight"),
                                       enc_out.data_ptr(), Xp, self.src_pad, T, B, H, 2 * H,
                                       ws.alpha.data_ptr(), ws.ctx.data_ptr(), s), "attn_fwd")
-        # one decoder step (bkp:215-216)
+        # one decoder step (bkp:215-216): its cell stays on the fp32 step kernel (a single step gains
+        # nothing from the tensor-core kernels, measured); SLNLP_DEC_TC=1 routes it to them
+        dec_prec = prec if os.environ.get("SLNLP_DEC_TC", "0") == "1" else 0
         check(lib.slnlp_dec_input_fwd(self._ptr("model.trg_embed.weight") + 4 * self.bos_idx * E,
                                       ws.ctx.data_ptr(), ws.dec_xin[0].data_ptr(), B, E, 2 * H, s), "dec_input")
         for l in range(L):
@@ -173,7 +175,7 @@ class RnnEncDecB200(FlatParamModule):
             self._gemm(0, 1, B, G * H, D, ws.dec_xin[l].data_ptr(), D, self._ptr(f"{pre}weight_ih_l{l}"), D,
                        ws.dec_gates[l].data_ptr(), G * H, self._ptr(f"{pre}bias_ih_l{l}"))
             h0 = ws.hidden0[l].data_ptr()
-            check(lib.slnlp_rnn_layer_fwd(mode, 0, 1, B, H, 1, ws.dec_gates[l].data_ptr(),
+            check(lib.slnlp_rnn_layer_fwd(mode, dec_prec, 1, B, H, 1, ws.dec_gates[l].data_ptr(),
                                           self._ptr(f"{pre}weight_hh_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
                                           None, h0, h0 if mode == 0 else None, ws.dec_h[l].data_ptr(),
                                           ws.dec_stash[l].data_ptr(), None, s), "rnn_layer_fwd(dec)")
@@ -208,12 +210,13 @@ class RnnEncDecB200(FlatParamModule):
         self._gemm(0, 0, B, H, V, ws.dlogits.data_ptr(), ws.Vp, self._ptr("model.generator.proj.weight"), H,
                    ws.d_h.data_ptr(), H)
         # decoder cells, top down
+        dec_prec = prec if os.environ.get("SLNLP_DEC_TC", "0") == "1" else 0
         pre = "model.decoder.rnn."
         for l in range(L - 1, -1, -1):
             D = E + 2 * H if l == 0 else H
             h0 = ws.hidden0[l].data_ptr()
             dg, dst = ws.dec_gates[l].data_ptr(), ws.dec_stash[l].data_ptr()
-            check(lib.slnlp_rnn_layer_bwd(mode, 0, 1, B, H, 1, dg, dst, ws.dec_h[l].data_ptr(),
+            check(lib.slnlp_rnn_layer_bwd(mode, dec_prec, 1, B, H, 1, dg, dst, ws.dec_h[l].data_ptr(),
                                           self._ptr(f"{pre}weight_hh_l{l}"), None, h0, h0 if mode == 0 else None,
                                           ws.d_h.data_ptr(), None, None, ws.d_hidden0[l].data_ptr(),
                                           ws.d_c0.data_ptr() if mode == 0 else None, ws.carry.data_ptr(), s),
