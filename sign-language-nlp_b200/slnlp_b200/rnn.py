@@ -506,9 +506,15 @@ class FusedTrainStep:
         dev = module._flat.device
         self.ws = module._make_workspace(batch_size, seq_len, True, True)
         self.ws.fused_ce = True      # log_softmax + CE + d logits run as one kernel (K10)
-        self.X = torch.full((batch_size, seq_len), module.src_pad, dtype=torch.int64, device=dev)
-        self.lengths = torch.ones(batch_size, dtype=torch.int64, device=dev)
-        self.y = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        # static inputs of the captured graph, views of one int64 buffer [X | lengths | y].  (Packing a host
+        # batch into one pinned staging buffer + one H2D copy was measured: the extra host-side copies
+        # and the buffer-reuse event cost as much as the two H2D launches they save.)
+        BT = batch_size * seq_len
+        self._inputs = torch.empty(BT + 2 * batch_size, dtype=torch.int64, device=dev)
+        self.X = self._inputs[:BT].view(batch_size, seq_len)
+        self.lengths = self._inputs[BT:BT + batch_size]
+        self.y = self._inputs[BT + batch_size:]
+        self.X.fill_(module.src_pad); self.lengths.fill_(1); self.y.zero_()
         # optimizer state may be shared by several steps of different batch shape (tail batches)
         self.state = state if state is not None else OptimState(module, lr, momentum, max_norm)
         self.gflat = module.flat_grads()
@@ -546,7 +552,7 @@ class FusedTrainStep:
                                           self.hyper.data_ptr(), self.norm.data_ptr(), self.grad_scale, s), "sgd")
 
     def load_batch(self, X, y, lengths):
-        """Stage one batch into the graph's static input buffers (device or pinned host)."""
+        """Stage one batch into the graph's static input buffers (device or pinned host tensors)."""
         self.X.copy_(X, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.lengths.copy_(lengths, non_blocking=True)

@@ -73,14 +73,17 @@ def test_autograd_path_with_stock_clip_and_sgd(name):
 
 
 @pytest.mark.parametrize("name", RNN_CASES)
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_fused_train_step_matches_reference_golden(name, use_graph):
+@pytest.mark.parametrize("use_graph,host_batch", [(False, False), (True, False), (True, True)])
+def test_fused_train_step_matches_reference_golden(name, use_graph, host_batch):
+    """host_batch: the batch arrives as host tensors (packed into one pinned H2D copy per step)."""
     from slnlp_b200.rnn import FusedTrainStep
     m, g = build(name)
     m.train()
     B, T = g["X"].shape
     ts = FusedTrainStep(m, B, T, lr=g["lr"], momentum=0.9, max_norm=0.5, use_graph=use_graph)
-    X, y, lengths = g["X"].cuda(), g["y"].cuda(), g["lengths"].cuda()
+    X, y, lengths = g["X"], g["y"], g["lengths"]
+    if not host_batch:
+        X, y, lengths = X.cuda(), y.cuda(), lengths.cuda()
     for step in range(3):
         loss = ts.step(X, y, lengths)
         assert abs(float(loss[0]) - g["loss"][step]) < 2e-5 * abs(g["loss"][step])
