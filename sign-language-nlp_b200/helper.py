@@ -300,18 +300,25 @@ def create_worker_farm(gpus=None, dask_args=None, **kwargs):
 
 
 def load_dataset(dataset_args, debug=False, seed=1, **kwargs):
-    """The ASL-Phono front-end (dataset/builder, torchtext) is outside the accelerated path
-    (SURVEY.md section 2a #10).  Two sources produce its output contract:
-      dataset_args.tensor_file: a torch.save'd dict {X [N,T], lengths [N], y [N], src_itos, tgt_itos};
+    """``AslDataset(device, batch_first=True, **args).stoi()`` (main.py:25).  Three sources produce
+    its output contract (X [N,T] int64 padded with <pad>, lengths [N], y [N], torchtext-shaped vocabs):
+      dataset_args.tensor_file: a torch.save'd dict {X, lengths, y, src_itos, tgt_itos};
+      dataset_args.dataset_dir (an existing directory of ASL-Phono JSON samples): read and composed
+        like dataset/builder/dataset_builder.py does, without torchtext (slnlp_b200/phono.py);
       otherwise a synthetic corpus shaped like it (dataset_args.synthetic: {n_seq, T, v_src, v_tgt, ragged})."""
     from slnlp_b200.vocab import Vocab
-    tf = (dataset_args or {}).get("tensor_file")
+    da = dataset_args or {}
+    tf = da.get("tensor_file")
     if tf:
         d = torch.load(tf)
         return SeqDataset(d["X"], d["lengths"], d["y"], Vocab(d["src_itos"][2:]), Vocab(d["tgt_itos"][2:]))
+    if da.get("dataset_dir") and not da.get("synthetic"):
+        if os.path.isdir(da["dataset_dir"]):
+            from slnlp_b200.phono import build_dataset
+            return build_dataset(da["dataset_dir"], da["fields"], da.get("samples_min_freq", 1),
+                                 da.get("composition_strategy", "as_words"))
+        log(f"WARNING: corpus directory {da['dataset_dir']!r} does not exist; "
+            "using the synthetic ASL-Phono-shaped corpus")
     syn = dict(n_seq=2000, T=64, v_src=4098, v_tgt=1026, ragged=True, seed=seed)
-    syn.update((dataset_args or {}).get("synthetic") or {})
-    if (dataset_args or {}).get("dataset_dir") and not (dataset_args or {}).get("synthetic"):
-        log(f"WARNING: corpus directory {dataset_args['dataset_dir']!r} is not read by the B200 build "
-            "(no torchtext front-end); using the synthetic ASL-Phono-shaped corpus")
+    syn.update(da.get("synthetic") or {})
     return SeqDataset.synthetic(**syn)
