@@ -422,6 +422,11 @@ def main():
             line["speedup_e2e_vs_cpu"] = e2e / cval
         print(json.dumps(line), flush=True)
     if world > 1:
+        # a captured data-parallel step holds NCCL kernels: release the graph before the communicator
+        ts.graph = None
+        del ts
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

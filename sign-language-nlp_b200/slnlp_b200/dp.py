@@ -23,7 +23,7 @@ def sync_gradients(gflat: torch.Tensor, loss_and_count: torch.Tensor, group=None
     loss_and_count[0].mul_(n_local)
     # one collective for gradients, loss numerator and count: they travel as one flat buffer
     tail = loss_and_count.to(gflat.dtype)
-    if gflat.is_cuda:
+    if gflat.is_cuda and not torch.cuda.is_current_stream_capturing():
         work = dist.all_reduce(gflat, group=group, async_op=True)
         dist.all_reduce(tail, group=group)
         work.wait()

@@ -191,7 +191,12 @@ class FlatParamModule(nn.Module):
 
     @contextlib.contextmanager
     def _side_branch(self):
-        """Kernels launched inside run on the side stream, ordered after everything issued so far."""
+        """Kernels launched inside run on the side stream, ordered after everything issued so far.
+        Only while a CUDA graph is being captured (the fork / join are free graph edges there); an
+        eager step is bound by the host's launch rate and the event traffic would slow it down."""
+        if not torch.cuda.is_current_stream_capturing():
+            yield
+            return
         with torch.cuda.stream(self._fork_side()):
             yield
 
