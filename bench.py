@@ -412,7 +412,7 @@ def main():
             roof["peak"] = peaks.get("bf16_tflops", 1590.0)
             roof["peak_source"] = "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"
             roof["frac"] = roof["achieved"] / roof["peak"]
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU baseline is an N = 1 figure (rank 0 only)
             cdata = {k: (v[:1000] if hasattr(v, "shape") else v) for k, v in data.items()}
             cval, csec, cores, cB = time_cpu_port(w, cdata, steps=12 if w["B"] <= 50 and w["H"] <= 128 else 3, warmup=2)
             line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),

@@ -452,31 +452,6 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-// rows [r0, r0+64) x head columns [0, dh) -> smem tile [64][st] (st % 4 == 0), zero-filled
-__device__ __forceinline__ void load_tile_v(float* s, const float* g, int ld, int r0, int rows, int dh, int st, float mul) {
-  const int c4n = dh >> 2, total = 64 * c4n;
-  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + u * blockDim.x;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e < total) {
-        const int r = e / c4n, c4 = (e % c4n) << 2;
-        if (r0 + r < rows) v[u] = *reinterpret_cast<const float4*>(g + (int64_t)(r0 + r) * ld + c4);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + u * blockDim.x;
-      if (e < total) {
-        const int r = e / c4n, c4 = (e % c4n) << 2;
-        *reinterpret_cast<float4*>(s + r * st + c4) = make_float4(v[u].x * mul, v[u].y * mul, v[u].z * mul, v[u].w * mul);
-      }
-    }
-  }
-}
-
 // keep-factors of the two adjacent attention weights (b, h, i, j) and (b, h, i, j + 1): the same
 // Philox stream as drop_factor(), one block of four uniforms serving both whenever they share it
 __device__ __forceinline__ void drop_factor2(const MhaArgs& p, uint64_t seed, uint64_t step, int bh, int i, int j,
