@@ -12,7 +12,6 @@ most frequent composites (-> <unk>), a long tail like a real sign corpus.
 """
 from __future__ import annotations
 
-import collections
 
 import torch
 

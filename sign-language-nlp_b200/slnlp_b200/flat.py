@@ -5,7 +5,7 @@ clip+SGD kernels walk it in one pass, and ``state_dict`` keeps the reference's n
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, Sequence, Tuple
 
 import contextlib
 import torch

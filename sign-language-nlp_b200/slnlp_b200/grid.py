@@ -16,13 +16,12 @@ claimed dynamically:
 """
 from __future__ import annotations
 
-import itertools
 import json
 import os
 import pickle
 import time
 import traceback
-from typing import Dict, List
+from typing import Dict
 
 import numpy as np
 from sklearn.base import clone, is_classifier

@@ -17,14 +17,12 @@ Two ways in:
 from __future__ import annotations
 
 import contextlib
-import math
 import os
-from typing import Dict, List, Optional
+from typing import List
 
 import torch
 import torch.nn as nn
 
-from . import _lib
 from ._lib import check, lib
 
 PAD_WORD, BOS_WORD = "<pad>", "<bos>"  # dataset/constant/tokens.py:1,4
