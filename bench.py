@@ -424,9 +424,7 @@ def main():
     if world > 1:
         # a captured data-parallel step holds NCCL kernels: release the graph before the communicator
         ts.graph = None
-        del ts
         torch.cuda.synchronize()
-        dist.barrier()
         dist.destroy_process_group()
 
 
