@@ -207,7 +207,8 @@ def run_grid(args, w):
                               callbacks=[("gradient_clipping", cbs.GradientNormClipping(gradient_clip_value=0.5))])
     y = ds.y().to_array()
     gs = GridSearchFarm(net, grid, cv=5, scoring=h.build_scoring("neg_log_loss", ds.labels(), allow_multiple=False),
-                        refit=False, backend="torchrun" if world > 1 else "inline", per_fit_checkpoint_dirs=False)
+                        refit=False, backend="torchrun" if world > 1 else "inline", per_fit_checkpoint_dirs=False,
+                        fits_per_gpu=args.fits_per_gpu)
     l0 = _lib.lib.slnlp_launch_count()
     t0 = time.perf_counter()
     gs.fit(ds.X(), y)
@@ -226,7 +227,8 @@ def run_grid(args, w):
             "config": {"workload": w["name"] if args.grid_fraction >= 1.0 else w["name"] + " (lr 0.01, dropout 0.1 slice: 27 candidates x 5 folds)",
                        "fits": n_fits, "epochs_per_fit": args.grid_epochs, "sequences": args.grid_seqs, "batch": w["B"],
                        "train_steps_per_fit": steps_per_fit, "seq_len": w["T"], "v_src": w["Vs"], "v_tgt": w["Vt"], "early_stopping": "off (fixed epochs)",
-                       "parallelism": f"{world} worker(s), one per GPU, longest-first, fits claimed from a TCPStore counter, no collective"},
+                       "parallelism": f"{world} worker(s), one per GPU, longest-first, fits claimed from a TCPStore counter, no collective",
+                       "fits_per_gpu": args.fits_per_gpu if world == 1 else 1},
             "gpu_launches": int(_lib.lib.slnlp_launch_count() - l0), "search_seconds": sec,
             "worker_busy_seconds": {str(k): round(v, 2) for k, v in sorted(busy.items())},
             "best_params": {k: v for k, v in gs.best_params_.items()}, "best_score": gs.best_score_}
@@ -248,6 +250,7 @@ def main():
     ap.add_argument("--grid-epochs", type=int, default=2, help="cfg5: epochs per fit")
     ap.add_argument("--grid-seqs", type=int, default=500, help="cfg5: sequences in the synthetic corpus")
     ap.add_argument("--grid-fraction", type=float, default=1.0, help="cfg5: < 1 runs the 27-candidate lr=0.01/dropout=0.1 slice")
+    ap.add_argument("--fits-per-gpu", type=int, default=1, help="cfg5, one GPU: fits packed on the GPU (worker threads, private streams)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.batch:

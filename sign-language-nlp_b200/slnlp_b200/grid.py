@@ -7,6 +7,11 @@ GPU (main.py:70-78; helper.py:490-526; cluster/az-start-workers.sh:11-15).
 result surface: ``cv_results_`` (same column names), ``best_index_``, ``best_score_``,
 ``best_params_``, ``best_estimator_`` (refit on all the data).
 
+``fits_per_gpu`` > 1 (opt-in; default 1 or $SLNLP_FITS_PER_GPU) packs several fits on one GPU: at the
+reference's batch of 50 a fit's recurrent kernels occupy 26-50 of 148 SMs and its step is a chain
+of dependent launches, so k worker THREADS per process, each with its own CUDA stream, estimator
+and captured step graph, run side by side (one process per GPU: no context switches, no MPS).
+
 Units of work = (candidate, fold) fits.  They are ordered longest-first by a FLOP estimate and
 claimed dynamically:
   * ``backend="spawn"``: this process spawns one worker per GPU and feeds a queue;
@@ -16,9 +21,12 @@ claimed dynamically:
 """
 from __future__ import annotations
 
+import contextlib
 import json
 import os
 import pickle
+import queue
+import threading
 import time
 import traceback
 from typing import Dict
@@ -56,31 +64,63 @@ def _fit_and_score(estimator, params, X, y, train, test, scorer, fit_subdir=None
             "epochs": len(getattr(est, "history", [])), "n_train": len(train)}
 
 
-def _worker_main(gpu, task_q, result_q, payload_bytes):
+def _stream_scope():
+    """A private CUDA stream for a packed worker thread (nothing on a CPU-only host)."""
+    import torch
+    if not torch.cuda.is_available():
+        return contextlib.nullcontext()
+    return torch.cuda.stream(torch.cuda.Stream())
+
+
+def _pack_env(fits_per_gpu):
+    if fits_per_gpu > 1:
+        # several threads capture step graphs in one process: captures must not see each other's CUDA calls
+        os.environ.setdefault("SLNLP_CAPTURE_MODE", "thread_local")
+
+
+def _worker_loop(gpu, task_q, result_q, payload_bytes, own_stream):
+    import torch
     try:
-        import torch
-        torch.cuda.set_device(gpu)
-        estimator, X, y, scorer = pickle.loads(payload_bytes)
-        estimator.set_params(device=f"cuda:{gpu}")
-        while True:
-            task = task_q.get()
-            if task is None:
-                break
-            tid, params, train, test, sub = task
-            try:
-                out = _fit_and_score(estimator, params, X, y, train, test, scorer, sub)
-                out["gpu"] = gpu
-                result_q.put((tid, out, None))
-            except Exception:            # error_score="raise": reported to the parent, which raises
-                result_q.put((tid, None, traceback.format_exc()))
+        if torch.cuda.is_available():
+            torch.cuda.set_device(gpu)        # the current device is per thread
+        # a spawned process receives pickled bytes; threads of this process share the objects themselves
+        # (the estimator prototype is only ever cloned, never fitted)
+        estimator, X, y, scorer = pickle.loads(payload_bytes) if isinstance(payload_bytes, bytes) else payload_bytes
+        if gpu is not None and torch.cuda.is_available() and "device" in estimator.get_params():
+            estimator.set_params(device=f"cuda:{gpu}")
+        with (_stream_scope() if own_stream else contextlib.nullcontext()):
+            while True:
+                task = task_q.get()
+                if task is None:
+                    break
+                tid, params, train, test, sub = task
+                try:
+                    out = _fit_and_score(estimator, params, X, y, train, test, scorer, sub)
+                    out["gpu"] = gpu
+                    result_q.put((tid, out, None))
+                except Exception:            # error_score="raise": reported to the parent, which raises
+                    result_q.put((tid, None, traceback.format_exc()))
     except Exception:
         result_q.put((-1, None, traceback.format_exc()))
+
+
+def _worker_main(gpu, task_q, result_q, payload_bytes, fits_per_gpu=1):
+    """One process per GPU; fits_per_gpu threads inside it (each ends on its own None sentinel)."""
+    _pack_env(fits_per_gpu)
+    if fits_per_gpu <= 1:
+        return _worker_loop(gpu, task_q, result_q, payload_bytes, False)
+    threads = [threading.Thread(target=_worker_loop, args=(gpu, task_q, result_q, payload_bytes, True), daemon=True)
+               for _ in range(fits_per_gpu)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
 
 
 class GridSearchFarm:
     def __init__(self, estimator, param_grid, *, scoring=None, n_jobs=None, refit=True, cv=None, verbose=0,
                  pre_dispatch=None, error_score="raise", return_train_score=False, n_gpus=None, backend="auto",
-                 per_fit_checkpoint_dirs=True, resume_file=None):
+                 per_fit_checkpoint_dirs=True, resume_file=None, fits_per_gpu=None):
         self.estimator, self.param_grid, self.scoring, self.n_jobs = estimator, param_grid, scoring, n_jobs
         self.refit, self.cv, self.verbose, self.pre_dispatch = refit, cv, verbose, pre_dispatch
         self.error_score, self.return_train_score = error_score, return_train_score
@@ -89,6 +129,7 @@ class GridSearchFarm:
         # again with the same grid and folds skips what the journal already holds (the reference aborts
         # the whole grid on any failure, helper.py:162, and has no resume - SURVEY.md section 5)
         self.resume_file = resume_file
+        self.fits_per_gpu = fits_per_gpu
 
     # ------------------------------------------------------------------ scheduling
     def _tasks(self, X, y):
@@ -184,7 +225,45 @@ class GridSearchFarm:
     def _sub(self, ci, fi):
         return f"cand{ci:04d}_fold{fi}" if self.per_fit_checkpoint_dirs else None
 
+    def _fits_per_gpu(self):
+        k = self.fits_per_gpu if self.fits_per_gpu is not None else int(os.environ.get("SLNLP_FITS_PER_GPU", "1"))
+        return max(1, int(k))
+
+    def _run_packed(self, k, cands, folds, tasks, order, X, y, scorer):
+        """One GPU (or none), k fits at a time: worker threads of THIS process on private streams."""
+        import torch
+        _pack_env(k)
+        task_q, result_q = queue.Queue(), queue.Queue()
+        payload = (self.estimator, X, y, scorer)
+        gpu = torch.cuda.current_device() if torch.cuda.is_available() else None
+        threads = [threading.Thread(target=_worker_loop, args=(gpu, task_q, result_q, payload, True), daemon=True)
+                   for _ in range(k)]
+        for t in order:
+            ci, fi = tasks[t]
+            task_q.put((t, cands[ci], folds[fi][0], folds[fi][1], self._sub(ci, fi)))
+        for _ in threads:
+            task_q.put(None)
+        for th in threads:
+            th.start()
+        out = {}
+        while len(out) < len(order):
+            tid, res, err = result_q.get()
+            if err is not None:
+                raise RuntimeError(f"grid-search fit failed (error_score='raise'):\n{err}")
+            out[tid] = res
+            self._journal(tid, res)
+            if self.verbose:
+                ci, fi = tasks[tid]
+                print(f"[grid] {len(out)}/{len(tasks)} cand {ci} fold {fi}: score {res['score']:.4f} "
+                      f"fit {res['fit_time']:.2f}s", flush=True)
+        for th in threads:
+            th.join(timeout=30)
+        return out
+
     def _run_inline(self, cands, folds, tasks, order, X, y, scorer):
+        k = self._fits_per_gpu()
+        if k > 1:
+            return self._run_packed(k, cands, folds, tasks, order, X, y, scorer)
         out = {}
         for t in order:
             ci, fi = tasks[t]
@@ -200,13 +279,14 @@ class GridSearchFarm:
         ctx = mp.get_context("spawn")
         task_q, result_q = ctx.Queue(), ctx.Queue()
         payload = pickle.dumps((self.estimator, X, y, scorer))
-        procs = [ctx.Process(target=_worker_main, args=(g, task_q, result_q, payload), daemon=True) for g in range(n)]
+        k = self._fits_per_gpu()
+        procs = [ctx.Process(target=_worker_main, args=(g, task_q, result_q, payload, k), daemon=True) for g in range(n)]
         for p in procs:
             p.start()
         for t in order:
             ci, fi = tasks[t]
             task_q.put((t, cands[ci], folds[fi][0], folds[fi][1], self._sub(ci, fi)))
-        for _ in procs:
+        for _ in range(len(procs) * k):      # one sentinel per worker thread
             task_q.put(None)
         out = {}
         try:

@@ -575,7 +575,9 @@ class FusedTrainStep:
             torch.cuda.synchronize()
             self.m._flat.copy_(saved[0]); self.buf.copy_(saved[1]); self.m._rng_state().copy_(saved[2])
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # "thread_local" when several fits share the process (grid.py fits_per_gpu): another thread's
+            # allocations must not invalidate this capture
+            with torch.cuda.graph(self.graph, capture_error_mode=os.environ.get("SLNLP_CAPTURE_MODE", "global")):
                 self._step()
             self.m._flat.copy_(saved[0]); self.buf.copy_(saved[1]); self.m._rng_state().copy_(saved[2])
         self.graph.replay()

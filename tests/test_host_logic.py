@@ -1,5 +1,6 @@
 """CPU: host-side logic of the drop-in modules (construction, state_dict surface,
 initialisation stream, flat-parameter views, refusal to compute on CPU)."""
+import numpy as np
 import pytest
 import torch
 
@@ -80,3 +81,59 @@ def test_transformer_state_dict_surface_and_init_stream(name):
     with pytest.raises(RuntimeError, match="CUDA"):
         m(X=g["X"], y=g["y"], lengths=g["lengths"])
     assert dropin.EncoderDecoderTransformerAttn is dropin.Transformer
+
+
+# ---------------------------------------------------------------- grid farm: several fits per GPU (threads)
+from sklearn.base import BaseEstimator, ClassifierMixin  # noqa: E402
+
+
+class _SlowClassifier(ClassifierMixin, BaseEstimator):
+    """sklearn estimator whose fit takes a fixed wall time (stands in for a GPU-bound fit)."""
+
+    def __init__(self, C=1.0, delay=0.15):
+        self.C, self.delay = C, delay
+
+    def fit(self, X, y):
+        import time
+        time.sleep(self.delay)
+        self.classes_ = np.unique(y)
+        self.majority_ = np.bincount(y).argmax()
+        return self
+
+    def predict(self, X):
+        return np.full(len(X), self.majority_)
+
+    def score(self, X, y):
+        return float((self.predict(X) == y).mean()) + 1e-3 * self.C
+
+
+def test_grid_farm_packs_fits_per_gpu_with_threads(tmp_path):
+    import time
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.model_selection import GridSearchCV
+    from slnlp_b200.grid import GridSearchFarm
+    rng = np.random.RandomState(0)
+    X = rng.randn(120, 5)
+    y = (X[:, 0] + 0.5 * X[:, 1] > 0).astype(int)
+    grid = {"C": [0.01, 0.1, 1.0, 10.0]}
+    # same table as sklearn's own search, packed 3 at a time, with the resume journal written by the parent
+    journal = str(tmp_path / "fits.jsonl")
+    gs = GridSearchFarm(LogisticRegression(max_iter=200), grid, cv=3, scoring="accuracy", backend="inline", n_gpus=1,
+                        fits_per_gpu=3, resume_file=journal).fit(X, y)
+    ref = GridSearchCV(LogisticRegression(max_iter=200), grid, cv=3, scoring="accuracy").fit(X, y)
+    assert np.allclose(ref.cv_results_["mean_test_score"], gs.cv_results_["mean_test_score"])
+    assert gs.best_params_ == ref.best_params_ and len(open(journal).read().splitlines()) == 12
+    # the fits really overlap: 8 fits of 0.15 s, 4 at a time
+    t0 = time.perf_counter()
+    slow = GridSearchFarm(_SlowClassifier(), grid, cv=2, scoring=lambda e, X, y: e.score(X, y), backend="inline", n_gpus=1,
+                          fits_per_gpu=4, refit=False).fit(X, y)
+    packed = time.perf_counter() - t0
+    assert slow.n_fits_ == 8 and packed < 0.9 * 8 * 0.15
+    assert slow.best_params_ == {"C": 10.0}
+    # a failing fit surfaces in the parent (error_score="raise")
+    class Boom(_SlowClassifier):
+        def fit(self, X, y):
+            raise ValueError("boom")
+    with pytest.raises(RuntimeError, match="boom"):
+        GridSearchFarm(Boom(), grid, cv=2, scoring=lambda e, X, y: 0.0, backend="inline", n_gpus=1, fits_per_gpu=2,
+                       refit=False).fit(X, y)
