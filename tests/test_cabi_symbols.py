@@ -58,3 +58,35 @@ def test_library_is_cuda_only_sm100a():
         pytest.skip("cuobjdump unavailable")
     archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
     assert archs == {"100a"}, archs
+
+
+def test_hot_kernels_use_the_blackwell_paths_in_sass():
+    """The built library's SASS shows the hardware path each hot kernel claims (B200_PROFILING.md:
+    tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG, cluster barrier -> UCGABAR,
+    warp-level MMA -> HMMA): a guard against a silent regression to CUDA-core code."""
+    import subprocess
+    import sys
+    script = os.path.join(ROOT, "profiles", "sass_mnemonics.py")
+    out = subprocess.run([sys.executable, script], capture_output=True, text=True)
+    if out.returncode != 0 or not out.stdout.strip():
+        import pytest
+        pytest.skip("cuobjdump unavailable")
+    rows = {}
+    for line in out.stdout.splitlines()[1:]:
+        name, _, rest = line.partition("  ")
+        rows[name.strip()] = dict(kv.split("=") for kv in rest.split())
+    def need(prefix, *ops):
+        hits = [v for k, v in rows.items() if k.startswith(prefix)]
+        assert hits, prefix
+        for v in hits:
+            for op in ops:
+                assert int(v.get(op, 0)) > 0, (prefix, op, v)
+    need("rnn_persistent_fwd_kernel", "UTCHMMA", "LDTM", "STTM")      # W_hh resident in TMEM, A operand from TMEM
+    need("rnn_persistent_bwd_kernel", "UTCHMMA", "LDTM", "STTM")
+    need("rnn_cluster_fwd_kernel", "UTCHMMA", "LDTM", "UCGABAR")      # thread-block cluster + DSMEM exchange
+    need("rnn_cluster_bwd_kernel", "UTCHMMA", "LDTM", "UCGABAR")
+    need("rnn_step_fwd_tc_kernel", "UTCHMMA", "UTMALDG", "LDTM")      # TMA-fed tf32 step kernels
+    need("rnn_step_bwd_tc_kernel", "UTCHMMA", "UTMALDG", "LDTM")
+    need("gemm_tma_kernel", "UTCHMMA", "UTMALDG", "LDTM")             # TMA-fed tcgen05 GEMM
+    need("mha_tc_fwd_kernel", "HMMA")                                 # warp-level tf32 MMA attention
+    need("mha_tc_bwd_kernel", "HMMA")
