@@ -2,6 +2,7 @@
 grid-search scheduling and result table, callbacks) - everything around the kernels that can be
 checked without a GPU."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -15,7 +16,8 @@ from slnlp_b200.grid import GridSearchFarm, estimate_cost
 from slnlp_b200.net import CVSplit, History, NeuralNetClassifier
 
 REF_CFG = "/root/reference/config"
-OWN_CFG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sign-language-nlp_b200", "config")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OWN_CFG = os.path.join(ROOT, "sign-language-nlp_b200", "config")
 
 
 def _args(path, extra=()):
@@ -219,3 +221,23 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(root, f)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) needs no GPU: one JSON line
+    with the base contract's keys, `impl: reference`, its own cpu_baseline and a zero-copy e2e object."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "train_seq_per_s" and line["unit"] == "sequences/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert "workload" in line["config"] and "EncoderDecoderLSTMAttn" in line["config"]["workload"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"] and line["cpu_baseline"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
