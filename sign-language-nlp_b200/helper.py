@@ -305,7 +305,8 @@ def load_dataset(dataset_args, debug=False, seed=1, **kwargs):
       dataset_args.tensor_file: a torch.save'd dict {X, lengths, y, src_itos, tgt_itos};
       dataset_args.dataset_dir (an existing directory of ASL-Phono JSON samples): read and composed
         like dataset/builder/dataset_builder.py does, without torchtext (slnlp_b200/phono.py);
-      otherwise a synthetic corpus shaped like it (dataset_args.synthetic: {n_seq, T, v_src, v_tgt, ragged})."""
+      dataset_args.synthetic ({n_seq, T, v_src, v_tgt, ragged}; bench and tests): a synthetic corpus shaped
+        like it.  A dataset_dir that does not exist raises FileNotFoundError."""
     from slnlp_b200.vocab import Vocab
     da = dataset_args or {}
     tf = da.get("tensor_file")
@@ -317,8 +318,11 @@ def load_dataset(dataset_args, debug=False, seed=1, **kwargs):
             from slnlp_b200.phono import build_dataset
             return build_dataset(da["dataset_dir"], da["fields"], da.get("samples_min_freq", 1),
                                  da.get("composition_strategy", "as_words"))
-        log(f"WARNING: corpus directory {da['dataset_dir']!r} does not exist; "
-            "using the synthetic ASL-Phono-shaped corpus")
+        # a mis-set path must not silently train, grid-search and "test" on random labels
+        raise FileNotFoundError(f"corpus directory {da['dataset_dir']!r} does not exist "
+                                "(give dataset_args.synthetic explicitly to use the synthetic corpus)")
+    if "synthetic" not in da:
+        raise FileNotFoundError("dataset_args names no corpus: set dataset_dir, tensor_file, or synthetic: {...}")
     syn = dict(n_seq=2000, T=64, v_src=4098, v_tgt=1026, ragged=True, seed=seed)
     syn.update(da.get("synthetic") or {})
     return SeqDataset.synthetic(**syn)

@@ -36,6 +36,8 @@ def run(args):
     log(f"> Train data: {len(train_data)} entries")
     log(f"> Test data: {len(test_data)} entries")
     best_estimator = tune_hyperparams(estimator=net, callbacks_names=callbacks_names, train_data=train_data, **args)
+    if best_estimator is None:      # a non-main rank of a torchrun launch: the main rank refits, tests and writes
+        return None
     return test_model(estimator=best_estimator, test_data=test_data, **args)
 
 
@@ -47,6 +49,8 @@ def tune_hyperparams(estimator, callbacks_names, train_data, cuda, gpus=None, **
     log(gs_params)
     h.save_param_grid(gs.param_grid, phase=phase, **kwargs)
     gs.fit(X=train_data.X(), y=train_data.y().to_array())
+    if getattr(gs, "refit_skipped_", False):
+        return None
     gs_output = {"best_score": float(gs.best_score_), "best_params": gs.best_params_, "best_index": int(gs.best_index_),
                  "scoring": str(gs.scoring), "n_fits": gs.n_fits_, "search_seconds": gs.search_time_,
                  "fits_per_hour": 3600.0 * gs.n_fits_ / gs.search_time_}

@@ -178,11 +178,17 @@ class GridSearchFarm:
         self.n_fits_ = len(tasks)
         self.n_resumed_ = len(done)
         self._collect(cands, folds, tasks, results)
-        if self.refit and self._is_main():
-            t1 = time.perf_counter()
+        if self.refit:
+            # every rank holds the full result table (the store carries all fits), so best_params_ is
+            # the same everywhere; the refit itself runs once, on the main rank.  The other ranks of a
+            # torchrun launch get the configured-but-unfitted estimator and ``refit_skipped_ = True``
+            # (main.py skips test_model there) instead of an AttributeError on best_estimator_.
             self.best_estimator_ = clone(self.estimator).set_params(**self.best_params_)
-            self.best_estimator_.fit(X, y)
-            self.refit_time_ = time.perf_counter() - t1
+            self.refit_skipped_ = not self._is_main()
+            if not self.refit_skipped_:
+                t1 = time.perf_counter()
+                self.best_estimator_.fit(X, y)
+                self.refit_time_ = time.perf_counter() - t1
         return self
 
     def _load_journal(self, cands, n_folds):
@@ -247,7 +253,7 @@ class GridSearchFarm:
             th.start()
         out = {}
         while len(out) < len(order):
-            tid, res, err = result_q.get()
+            tid, res, err = self._next_result(result_q, threads)
             if err is not None:
                 raise RuntimeError(f"grid-search fit failed (error_score='raise'):\n{err}")
             out[tid] = res
@@ -259,6 +265,26 @@ class GridSearchFarm:
         for th in threads:
             th.join(timeout=30)
         return out
+
+    @staticmethod
+    def _next_result(result_q, workers, poll=2.0):
+        """Next (task id, result, error) from the workers.  A worker that died without reporting
+        (OOM kill, CUDA fault, a crash inside the CUDA library) would leave a bare ``get()`` waiting
+        forever: poll, and raise once nobody alive is left to produce the missing result or a
+        process ended abnormally (the journal allows the search to resume)."""
+        while True:
+            try:
+                return result_q.get(timeout=poll)
+            except queue.Empty:
+                pass
+            codes = [getattr(w, "exitcode", None) for w in workers]
+            bad = [c for c in codes if c not in (None, 0)]
+            if bad or not any(w.is_alive() for w in workers):
+                try:                        # a result may have landed between the timeout and the check
+                    return result_q.get(timeout=0.2)
+                except queue.Empty:
+                    raise RuntimeError(f"grid-search worker(s) ended without reporting (exit codes {codes}); "
+                                       "finished fits are in the resume journal") from None
 
     def _run_inline(self, cands, folds, tasks, order, X, y, scorer):
         k = self._fits_per_gpu()
@@ -291,7 +317,7 @@ class GridSearchFarm:
         out = {}
         try:
             while len(out) < len(order):
-                tid, res, err = result_q.get()
+                tid, res, err = self._next_result(result_q, procs)
                 if err is not None:
                     raise RuntimeError(f"grid-search fit failed (error_score='raise'):\n{err}")
                 out[tid] = res
@@ -300,6 +326,11 @@ class GridSearchFarm:
                     ci, fi = tasks[tid]
                     print(f"[grid] {len(out)}/{len(tasks)} cand {ci} fold {fi} on gpu {res['gpu']}: "
                           f"score {res['score']:.4f} fit {res['fit_time']:.2f}s", flush=True)
+        except BaseException:
+            for p in procs:               # a failed search must not leave workers training
+                if p.is_alive():
+                    p.terminate()
+            raise
         finally:
             for p in procs:
                 p.join(timeout=30)
@@ -309,34 +340,72 @@ class GridSearchFarm:
 
     def _run_torchrun(self, cands, folds, tasks, order, X, y, scorer):
         """SPMD under torchrun: work is claimed with a store counter, results travel through the
-        store.  No process-group collective is issued (no NCCL on the grid path)."""
+        store.  No process-group collective is issued (no NCCL on the grid path).  ``fits_per_gpu``
+        worker threads per rank claim from the same counter.  A fit that raises publishes an error
+        record under its own key, so every rank re-raises the SAME error instead of timing out on a
+        key that never arrives; waiting polls ``store.check`` (no store-timeout dependence: an
+        L6/H512 fit at 200 epochs outlasts the 300 s default)."""
+        import datetime
         import torch
         import torch.distributed as dist
         rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
         store = getattr(self, "store", None)
         if store is None:
             store = dist.TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ["MASTER_PORT"]) + 17,
-                                  world, is_master=(rank == 0), wait_for_workers=True)
+                                  world, is_master=(rank == 0), wait_for_workers=True,
+                                  timeout=datetime.timedelta(days=7))
             self.store = store
         gen = getattr(self, "_generation", 0)
         self._generation = gen + 1
         key = f"grid{gen}"
-        est = clone(self.estimator)
-        if torch.cuda.is_available() and "device" in est.get_params(deep=False):
-            est.set_params(device=f"cuda:{torch.cuda.current_device()}")
-        while True:
-            k = store.add(f"{key}/next", 1) - 1
-            if k >= len(order):
-                break
-            t = order[k]
-            ci, fi = tasks[t]
-            res = _fit_and_score(est, cands[ci], X, y, folds[fi][0], folds[fi][1], scorer, self._sub(ci, fi))
-            res["gpu"] = rank
-            store.set(f"{key}/res/{t}", pickle.dumps(res))
-            self._journal(t, res)       # every rank appends its own fits (O_APPEND lines, one writer per line)
+        k_threads = self._fits_per_gpu()
+        _pack_env(k_threads)
+        gpu = torch.cuda.current_device() if torch.cuda.is_available() else None
+        failed = threading.Event()
+
+        def claim_loop(own_stream):
+            if gpu is not None:
+                torch.cuda.set_device(gpu)
+            est = clone(self.estimator)
+            if gpu is not None and "device" in est.get_params(deep=False):
+                est.set_params(device=f"cuda:{gpu}")
+            with (_stream_scope() if own_stream else contextlib.nullcontext()):
+                while not failed.is_set():
+                    k = store.add(f"{key}/next", 1) - 1
+                    if k >= len(order):
+                        break
+                    t = order[k]
+                    ci, fi = tasks[t]
+                    try:
+                        res = _fit_and_score(est, cands[ci], X, y, folds[fi][0], folds[fi][1], scorer, self._sub(ci, fi))
+                    except Exception:
+                        failed.set()
+                        store.set(f"{key}/res/{t}", pickle.dumps({"error": traceback.format_exc(), "rank": rank}))
+                        store.set(f"{key}/failed", str(t))
+                        return
+                    res["gpu"] = rank
+                    store.set(f"{key}/res/{t}", pickle.dumps(res))
+                    self._journal(t, res)   # every rank appends its own fits (O_APPEND lines, one writer per line)
+
+        if k_threads <= 1:
+            claim_loop(False)
+        else:
+            threads = [threading.Thread(target=claim_loop, args=(True,), daemon=True) for _ in range(k_threads)]
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
         out = {}
-        for t in order:                 # blocks until the owning rank has published it
-            out[t] = pickle.loads(store.get(f"{key}/res/{t}"))
+        for t in order:                 # wait until the owning rank has published it (or a failure)
+            while not store.check([f"{key}/res/{t}"]):
+                if store.check([f"{key}/failed"]):
+                    t = int(store.get(f"{key}/failed"))
+                    break
+                time.sleep(0.05)
+            res = pickle.loads(store.get(f"{key}/res/{t}"))
+            if "error" in res:
+                raise RuntimeError(f"grid-search fit failed on rank {res['rank']} (error_score='raise'):\n{res['error']}")
+            out[t] = res
         return out
 
     # ------------------------------------------------------------------ GridSearchCV result surface

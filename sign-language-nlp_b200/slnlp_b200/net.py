@@ -29,7 +29,7 @@ from . import callbacks as cbs
 from ._lib import check, lib
 from .data import SeqDataset, SeqSlice
 from .flat import _stream
-from .rnn import FusedTrainStep, OptimState
+from .rnn import FusedTrainStep, InferStep, OptimState
 
 
 class History(list):
@@ -90,6 +90,7 @@ def _as_tensors(X, y=None):
 
 class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
     prefixes_ = ("module", "optimizer", "criterion", "callbacks", "iterator_train", "iterator_valid", "dataset")
+    _soft_params = ("lr", "max_epochs", "batch_size", "verbose", "warm_start", "train_split", "predict_nonlinearity")
 
     def __init__(self, module, criterion=torch.nn.CrossEntropyLoss, optimizer=torch.optim.SGD, lr=0.01,
                  max_epochs=10, batch_size=128, device="cuda", callbacks=None, train_split="default",
@@ -126,7 +127,14 @@ class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
             elif k not in BaseEstimator.get_params(self, deep=False):
                 raise ValueError(f"Invalid parameter {k!r} for estimator {type(self).__name__}")
             setattr(self, k, v)
-        self.initialized_ = False
+            # skorch semantics: only parameters that change what initialize() builds force a fresh
+            # initialisation; lr / max_epochs / batch_size / verbose / warm_start / iterator_* keep
+            # the trained module (partial_fit / warm_start continue from it)
+            if k not in self._soft_params and not k.startswith(("iterator_train__", "iterator_valid__")):
+                self.initialized_ = False
+            elif k == "lr" and getattr(self, "initialized_", False):
+                for grp in self.optimizer_.param_groups:
+                    grp["lr"] = v
         return self
 
     def _prefixed(self, prefix):
@@ -158,11 +166,31 @@ class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
         self.criterion_ = crit_cls(**ckw)
         clip = None
         self.callbacks_ = []
+        # callbacks__<name>__<param> (helper.build_callbacks_args; a grid over e.g.
+        # callbacks__early_stopping__patience) is routed to the callback of that name, on a per-fit
+        # copy so that candidates of one search never share callback state - skorch's routing
+        routed = {}
+        for key, val in self._prefixed("callbacks").items():
+            cb_name, sep, param = key.partition("__")
+            if not sep:
+                raise ValueError(f"callbacks__{key}: expected callbacks__<name>__<param>")
+            routed.setdefault(cb_name, {})[param] = val
         for item in (self.callbacks or []):
             name, cb = item if isinstance(item, tuple) else (type(item).__name__, item)
+            if name in routed:
+                import copy
+                cb = copy.copy(cb)
+                known = cb.get_params() if hasattr(cb, "get_params") else {}
+                for param in routed[name]:
+                    if param not in known and not hasattr(cb, param):
+                        raise ValueError(f"Invalid parameter {param!r} for callback {name!r} ({type(cb).__name__})")
+                cb.set_params(**routed.pop(name))
             self.callbacks_.append((name, cb))
             if isinstance(cb, cbs.GradientNormClipping):
                 clip = cb
+        if routed:
+            raise ValueError(f"callbacks__ parameters name unknown callbacks: {sorted(routed)} "
+                             f"(have {[n for n, _ in self.callbacks_]})")
         if self.verbose and not any(isinstance(cb, cbs.PrintLog) for _, cb in self.callbacks_):
             self.callbacks_.append(("print_log", cbs.PrintLog()))
         for _, cb in self.callbacks_:
@@ -185,12 +213,20 @@ class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
             self.optimizer_ = opt_cls(self.module_.parameters(), lr=self.lr, **okw)
         self.history = History()
         self._epoch_cache = {}
+        self.infer_steps_ = {}
         self._stop_training = False
         self.initialized_ = True
         return self
 
     def optimizer_state_dict(self):
-        return self.opt_state_.state_dict() if self.fused_ else self.optimizer_.state_dict()
+        """torch.optim.SGD.state_dict() layout on both routes (skorch Checkpoint's optimizer.pt)."""
+        return self.opt_state_.state_dict(self.module_) if self.fused_ else self.optimizer_.state_dict()
+
+    def load_optimizer_state_dict(self, sd):
+        if self.fused_:
+            self.opt_state_.load_state_dict(sd, self.module_)
+        else:
+            self.optimizer_.load_state_dict(sd)
 
     # ------------------------------------------------------------------ training
     def _fused_step(self, B, T):
@@ -198,6 +234,15 @@ class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
         if key not in self.steps_:
             self.steps_[key] = FusedTrainStep(self.module_, B, T, use_graph=self.use_graph, state=self.opt_state_)
         return self.steps_[key]
+
+    def _infer_step(self, B, T):
+        """Full batches of the scoring / validation forward: one captured graph per (batch, len) shape."""
+        if not self.use_graph:
+            return None
+        cache = self.__dict__.setdefault("infer_steps_", {})
+        if (B, T) not in cache:
+            cache[(B, T)] = InferStep(self.module_, B, T)
+        return cache[(B, T)]
 
     def _eval_loss_and_logp(self, Xd, ld, yd, out_logp, train_mode=False):
         """Forward-only pass over a device-resident split; returns the device scalar
@@ -207,9 +252,13 @@ class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
         loss = torch.zeros(2, device=Xd.device)
         row_ws = torch.empty(3 * bs, device=Xd.device)
         m.eval()
+        infer = self._infer_step(bs, Xd.shape[1]) if N >= bs else None
         for j in range(0, N, bs):
             k = min(N, j + bs)
-            logp = m.predict_logp(Xd[j:k], ld[j:k], yd[j:k])
+            if infer is not None and k - j == bs:
+                logp = infer.step(Xd[j:k], yd[j:k], ld[j:k])
+            else:
+                logp = m.predict_logp(Xd[j:k], ld[j:k], yd[j:k])
             out_logp[j:k].copy_(logp)
             if self.fused_:
                 check(lib.slnlp_ce_on_logp(logp.data_ptr(), yd[j:k].data_ptr(), m.tgt_pad, k - j, m.V_tgt, loss.data_ptr(),
@@ -325,8 +374,14 @@ class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
         out = torch.empty(tok.shape[0], self.V_, device=dev)
         was = m.training
         m.eval()
-        for j in range(0, tok.shape[0], bs):
-            out[j:j + bs].copy_(m.predict_logp(Xd[j:j + bs], ld[j:j + bs], yd[j:j + bs]))
+        n, T = tok.shape
+        infer = self._infer_step(bs, T) if n >= bs else None
+        for j in range(0, n, bs):
+            k = min(n, j + bs)
+            if infer is not None and k - j == bs:
+                out[j:k].copy_(infer.step(Xd[j:k], yd[j:k], ld[j:k]))
+            else:
+                out[j:k].copy_(m.predict_logp(Xd[j:k], ld[j:k], yd[j:k]))
         m.train(was)
         return out
 

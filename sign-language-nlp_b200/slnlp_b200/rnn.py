@@ -200,7 +200,12 @@ class RnnEncDecB200(FlatParamModule):
         GH = G * H
         # Weight gradients are leaves of the dependency graph: each is issued on the side stream as
         # soon as its operands exist, so that the main stream carries only the d(activation) chain.
-        small = self._side_branch if self.overlap_small else contextlib.nullcontext
+        # data parallel (dp.py): every finished range of the flat gradient buffer is announced so that its
+        # all-reduce overlaps the rest of backward; the announcing stream must own the writes, so the
+        # side-stream branches are off then (at data-parallel sizes the GPU is full anyway)
+        hook = getattr(self, "_grad_ready", None)
+        off, numel = self._off, self._numel
+        small = self._side_branch if (self.overlap_small and hook is None) else contextlib.nullcontext
         # generator
         with small():
             self._gemm(1, 0, V, H, B, ws.dlogits.data_ptr(), ws.Vp, ws.dec_h[L - 1].data_ptr(), H,
@@ -277,6 +282,9 @@ class RnnEncDecB200(FlatParamModule):
         # encoder BPTT, top down.  Padded rows of enc_out go back to 0 first (the 1.0
         # fill of pad_packed_sequence is a constant and must not enter dW_hh).
         check(lib.slnlp_pad_fill(enc_out.data_ptr(), lp, T, B, 2 * H, 0.0, s), "pad_unfill")
+        if hook is not None:      # attention + decoder + bridge, and target embedding + generator, are final
+            hook(gflat, off["model.decoder.attention.key_layer.weight"], off["model.src_embed.weight"])
+            hook(gflat, off["model.trg_embed.weight"], numel)
         pre = "model.encoder.rnn."
         for l in range(L - 1, -1, -1):
             D = E if l == 0 else 2 * H
@@ -300,9 +308,14 @@ class RnnEncDecB200(FlatParamModule):
                                                  ws.f_off, ws.f_w_src, ws.f_rows_src, 1, 1.0, self.src_pad, s),
                       "embed_bwd")
             # weight / bias gradients of this layer: off the chain, on the side stream
-            side = self._fork_side() if self.overlap_dw else None
+            side = self._fork_side() if (self.overlap_dw and hook is None) else None
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 self._encoder_weight_grads(ws, l, gp, _stream())
+            if hook is not None:  # this layer's range goes out while the layer below runs its BPTT
+                nxt = f"{pre}weight_ih_l{l + 1}" if l < L - 1 else "model.decoder.attention.key_layer.weight"
+                hook(gflat, off[f"{pre}weight_ih_l{l}"], off[nxt])
+                if l == 0:
+                    hook(gflat, off["model.src_embed.weight"], off["model.trg_embed.weight"])
         if self.overlap_dw or self.overlap_small:
             self._join_side()
 
@@ -484,8 +497,35 @@ class OptimState:
             self.hyper[0] = lr
             self._lr = lr
 
-    def state_dict(self):
-        return {"hyper": self.hyper.clone(), "momentum_buffer": self.buf.clone()}
+    def state_dict(self, module: FlatParamModule = None):
+        """With ``module``: the layout of ``torch.optim.SGD(module.parameters()).state_dict()`` - what
+        the reference's skorch Checkpoint writes to optimizer.pt and ``load_params(f_optimizer=...)``
+        reads - with every momentum buffer a copy of that parameter's slice of the flat buffer."""
+        if module is None:
+            return {"hyper": self.hyper.clone(), "momentum_buffer": self.buf.clone()}
+        lr, momentum = float(self.hyper[0]), float(self.hyper[1])
+        names = list(module._params)
+        stepped = bool(self.buf.abs().max() > 0)
+        state = {i: {"momentum_buffer": module._view(self.buf, n).clone()} for i, n in enumerate(names)
+                 if stepped and n not in module._dead}
+        group = {"lr": lr, "momentum": momentum, "dampening": 0, "weight_decay": 0, "nesterov": False,
+                 "maximize": False, "foreach": None, "differentiable": False, "fused": None,
+                 "params": list(range(len(names)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd, module: FlatParamModule):
+        """Inverse of ``state_dict(module)`` (also accepts the flat form)."""
+        if "momentum_buffer" in sd:
+            self.buf.copy_(sd["momentum_buffer"]); self.hyper.copy_(sd["hyper"])
+            return
+        names = list(module._params)
+        self.buf.zero_()
+        for i, st in sd["state"].items():
+            if st.get("momentum_buffer") is not None:
+                module._view(self.buf, names[int(i)]).copy_(st["momentum_buffer"])
+        grp = sd["param_groups"][0]
+        self.hyper[0] = grp["lr"]; self.hyper[1] = grp["momentum"]
+        self._lr = grp["lr"]
 
 
 class FusedTrainStep:
@@ -519,11 +559,11 @@ class FusedTrainStep:
         self.grad_sync = grad_sync                   # callable(gflat, loss) for data parallel
         self.grad_scale = 1.0
         self.graph = None
-        # The data-parallel step can be captured too (NCCL collectives are graph-capturable): measured
-        # 165 k vs 95 k seq/s at 2 GPUs (cfg1 model, global batch 100).  Opt-in with SLNLP_DP_GRAPH=1:
-        # the one run so far hung at process exit (communicator torn down under a live graph) - release
-        # the step (ts.graph = None) before destroy_process_group().
-        self.use_graph = use_graph and (grad_sync is None or os.environ.get("SLNLP_DP_GRAPH", "0") == "1")
+        # The data-parallel step is captured too (NCCL collectives are graph-capturable): measured
+        # 165 k vs 95 k seq/s at 2 GPUs (cfg1 model, global batch 100).  The captured graph holds NCCL
+        # kernels: release it (ts.graph = None; DataParallelStep.release()) before
+        # destroy_process_group().  SLNLP_DP_GRAPH=0 keeps the data-parallel step eager.
+        self.use_graph = use_graph and (grad_sync is None or os.environ.get("SLNLP_DP_GRAPH", "1") == "1")
 
     # optimizer state lives in self.state; these aliases keep call sites short
     hyper = property(lambda self: self.state.hyper)
@@ -544,10 +584,18 @@ class FusedTrainStep:
         check(lib.slnlp_logsoftmax_ce_fused(ws.logits.data_ptr(), self.y.data_ptr(), m.tgt_pad, self.B, m.V_tgt,
                                             ws.logp.data_ptr(), ws.loss.data_ptr(), ws.dlogits.data_ptr(), ws.Vp,
                                             ws.row_ws.data_ptr(), s), "logsoftmax_ce")
-        m._run_backward(ws, self.X, self.lengths, self.gflat, self.y)
-        if self.grad_sync is not None:
+        bucketed = getattr(self.grad_sync, "bucketed", False)
+        if bucketed:     # data parallel: gradient ranges are exchanged while the rest of backward runs (dp.py)
+            self.grad_sync.begin(ws.loss)
+            m._grad_ready = self.grad_sync.ready
+        try:
+            m._run_backward(ws, self.X, self.lengths, self.gflat, self.y)
+        finally:
+            m._grad_ready = None
+        if bucketed:
+            self.grad_sync.finish(self.gflat, ws.loss)
+        elif self.grad_sync is not None:
             self.grad_sync(self.gflat, ws.loss)
-            s = _stream()
         n = m._numel
         check(lib.slnlp_gradnorm(self.gflat.data_ptr(), n, self.partials.data_ptr(), self.norm.data_ptr(), s), "gradnorm")
         check(lib.slnlp_sgd_momentum_clip(m._flat.data_ptr(), self.gflat.data_ptr(), self.buf.data_ptr(), n,
@@ -590,3 +638,50 @@ class FusedTrainStep:
     @property
     def grad_norm(self):
         return self.norm
+
+
+class InferStep:
+    """The scoring forward (eval mode, no autograd: main.py:116-117 -> skorch predict) on a fixed
+    (B, T) as ONE CUDA-graph replay.  Inputs are staged into static buffers exactly like
+    ``FusedTrainStep``; ``run`` returns the module's log-prob buffer [B, V_tgt] (valid until the
+    next run)."""
+
+    def __init__(self, module: FlatParamModule, batch_size: int, seq_len: int, use_graph: bool = True):
+        module._ensure_flat()
+        self.m, self.B, self.T = module, batch_size, seq_len
+        dev = module._flat.device
+        self.ws = module._workspace(batch_size, seq_len, False)
+        BT = batch_size * seq_len
+        self._inputs = torch.empty(BT + 2 * batch_size, dtype=torch.int64, device=dev)
+        self.X = self._inputs[:BT].view(batch_size, seq_len)
+        self.lengths = self._inputs[BT:BT + batch_size]
+        self.y = self._inputs[BT + batch_size:]
+        self.X.fill_(module.src_pad); self.lengths.fill_(1); self.y.zero_()
+        self.use_graph, self.graph = use_graph, None
+
+    def load_batch(self, X, y, lengths):
+        self.X.copy_(X, non_blocking=True)
+        self.lengths.copy_(lengths, non_blocking=True)
+        if y is not None:
+            self.y.copy_(y, non_blocking=True)
+
+    def run(self):
+        m = self.m
+        if not self.use_graph:
+            return m._run_forward(self.ws, self.X, self.lengths, self.y)
+        if self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                m._run_forward(self.ws, self.X, self.lengths, self.y)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, capture_error_mode=os.environ.get("SLNLP_CAPTURE_MODE", "global")):
+                m._run_forward(self.ws, self.X, self.lengths, self.y)
+        self.graph.replay()
+        return self.ws.logp
+
+    def step(self, X, y, lengths):
+        self.load_batch(X, y, lengths)
+        return self.run()

@@ -5,17 +5,4 @@ The reference builds its vocabularies with torchtext Fields
 then tokens by descending frequency, ``stoi`` a defaultdict that maps unknown
 strings (including '<bos>') to 0.
 """
-import collections
-
-UNK_WORD, PAD_WORD, BOS_WORD, EOS_WORD = "<unk>", "<pad>", "<bos>", "<eos>"
-
-
-class Vocab:
-    def __init__(self, tokens=(), size=None):
-        self.itos = [UNK_WORD, PAD_WORD] + list(tokens)
-        if size is not None:
-            self.itos += [f"tok{i}" for i in range(len(self.itos), size)]
-        self.stoi = collections.defaultdict(int, {w: i for i, w in enumerate(self.itos)})
-
-    def __len__(self):
-        return len(self.itos)
+from phono_synth import BOS_WORD, EOS_WORD, PAD_WORD, UNK_WORD, Vocab  # noqa: F401  (torch-only home)

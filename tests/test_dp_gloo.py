@@ -70,3 +70,54 @@ def test_two_rank_gradient_sync_equals_single_process_global_batch(tmp_path):
     assert float(lc0[1]) == 9.0
     assert abs(float(lc0[0]) - float(loss)) < 1e-6 * abs(float(loss))
     assert float((g0 - want).abs().max()) < 1e-6 * float(want.abs().max())
+
+
+BUCKET_WORKER = textwrap.dedent("""
+    import os, pickle, sys
+    import importlib.util, torch, torch.distributed as dist
+    spec = importlib.util.spec_from_file_location("dp", os.path.join({root!r}, "sign-language-nlp_b200", "slnlp_b200", "dp.py"))
+    dp = importlib.util.module_from_spec(spec); spec.loader.exec_module(dp)
+    rank = int(os.environ["RANK"])
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    g = torch.Generator().manual_seed(10 + rank)
+    grad = torch.randn(1000, generator=g)             # this rank's MEAN gradient over its n_r valid labels
+    lc = torch.tensor([1.5 + rank, 3.0 if rank == 0 else 6.0])
+    sync = dp.BucketedGradSync()
+    out = []
+    for step in range(2):                               # the object is reused step after step
+        gflat, l = grad.clone(), lc.clone()
+        sync.begin(l)
+        sync.ready(gflat, 700, 1000)                    # announced out of order, as backward finishes them
+        sync.ready(gflat, 100, 400)
+        sync.ready(gflat, 0, 100)                       # [400, 700) is never announced: finish() sends it
+        sync.finish(gflat, l)
+        out.append((gflat, l, sync.n_collectives))
+    pickle.dump(out, open({out!r} + str(rank), "wb"))
+    dist.destroy_process_group()
+""")
+
+
+def test_bucketed_overlapped_exchange_equals_the_count_weighted_global_gradient(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port_no = s.getsockname()[1]
+    out = str(tmp_path / "bk")
+    script = tmp_path / "w.py"
+    script.write_text(BUCKET_WORKER.format(root=ROOT, out=out))
+    procs = [subprocess.Popen([sys.executable, str(script)],
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                                       MASTER_PORT=str(port_no), CUDA_VISIBLE_DEVICES=""),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    for p in procs:
+        o, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, o.decode()
+    res = [pickle.load(open(out + str(r), "rb")) for r in range(2)]
+    g0 = torch.randn(1000, generator=torch.Generator().manual_seed(10))
+    g1 = torch.randn(1000, generator=torch.Generator().manual_seed(11))
+    want = (3.0 * g0 + 6.0 * g1) / 9.0
+    want_loss = (3.0 * 1.5 + 6.0 * 2.5) / 9.0
+    for step in range(2):
+        (a, la, na), (b, lb, nb) = res[0][step], res[1][step]
+        assert torch.equal(a, b) and torch.equal(la, lb) and na == nb == 4
+        assert float((a - want).abs().max()) < 1e-6
+        assert abs(float(la[0]) - want_loss) < 1e-6 and float(la[1]) == 9.0

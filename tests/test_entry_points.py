@@ -241,3 +241,65 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["e2e"]["value"] == line["value"] and line["cpu_baseline"]["value"] == line["value"]
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+
+
+# ---------------------------------------------------------------- advisor findings, round 1
+class _FakeModule:
+    """Stands in for a CUDA module: initialize() needs only V_tgt / tgt_pad on a CPU-only host."""
+    V_tgt, tgt_pad = 5, 1
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def to(self, dev):
+        return self
+
+    def parameters(self):
+        return [torch.nn.Parameter(torch.zeros(1))]
+
+
+def _cpu_initialize(net):
+    """Run NeuralNetClassifier.initialize() up to the optimizer on a host without CUDA."""
+    import unittest.mock as mock
+    from slnlp_b200 import net as netmod
+    with mock.patch.object(netmod, "OptimState", lambda *a, **k: None):
+        return net.initialize()
+
+
+def test_callbacks_params_are_routed_to_the_named_callback():
+    es = cbs.EarlyStopping(patience=30)
+    clip = cbs.GradientNormClipping(gradient_clip_value=0.5)
+    net = NeuralNetClassifier(module=_FakeModule, device="cuda:0", verbose=0,
+                              callbacks=[("early_stopping", es), ("gradient_clipping", clip)],
+                              callbacks__early_stopping__patience=3, callbacks__gradient_clipping__gradient_clip_value=0.25)
+    _cpu_initialize(net)
+    routed = dict(net.callbacks_)
+    assert routed["early_stopping"].patience == 3 and routed["gradient_clipping"].gradient_clip_value == 0.25
+    assert es.patience == 30 and clip.gradient_clip_value == 0.5      # per-fit copies: the prototypes are untouched
+    assert net.max_norm_ == 0.25                                      # the fused clip reads the routed value
+    assert net.get_params()["callbacks__early_stopping__patience"] == 3
+    with pytest.raises(ValueError, match="unknown callbacks"):
+        _cpu_initialize(NeuralNetClassifier(module=_FakeModule, device="cuda:0", verbose=0, callbacks=[("early_stopping", es)],
+                                            callbacks__nope__patience=3))
+    with pytest.raises(ValueError, match="Invalid parameter"):
+        _cpu_initialize(NeuralNetClassifier(module=_FakeModule, device="cuda:0", verbose=0, callbacks=[("early_stopping", es)],
+                                            callbacks__early_stopping__patiense=3))
+
+
+def test_set_params_keeps_the_trained_module_for_soft_parameters():
+    net = NeuralNetClassifier(module=_FakeModule, device="cuda:0", verbose=0, lr=0.1)
+    _cpu_initialize(net)
+    assert net.initialized_
+    net.set_params(lr=0.01, max_epochs=3)
+    assert net.initialized_ and net.optimizer_.param_groups[0]["lr"] == 0.01     # skorch: lr does not re-initialise
+    net.set_params(module__hidden_size=64)
+    assert not net.initialized_                                                   # a structural parameter does
+
+
+def test_load_dataset_refuses_a_missing_corpus_directory(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        h.load_dataset(dataset_args={"dataset_dir": str(tmp_path / "nope"), "fields": ["handshape_dh"]})
+    with pytest.raises(FileNotFoundError):
+        h.load_dataset(dataset_args={})
+    ds = h.load_dataset(dataset_args={"dataset_dir": str(tmp_path / "nope"), "synthetic": {"n_seq": 20, "T": 6, "v_src": 12, "v_tgt": 5}})
+    assert len(ds) == 20

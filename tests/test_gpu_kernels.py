@@ -572,3 +572,66 @@ def test_gemm_tf32_split_k_accumulates_in_place(tA, tB, M, N, K):
     opA, opB = (A.t() if tA else A), (B.t() if tB else B)
     tf = lambda x: (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
     assert rel_err(C, tf(opA) @ tf(opB) + C0.double()) < 2e-5
+
+
+@pytest.mark.parametrize("mode", ["lstm", "gru"])
+def test_rnn_layer_at_cfg4_shape_batch_4096_hidden_512(mode):
+    """BASELINE.json configs[3]'s layer shape: T 64, B 4096, H 512, ragged.  The per-step TMA + tcgen05
+    kernels (precision 1; the family a batch > 256 takes) against the fp32 CUDA step kernels on the same
+    device inputs (2e-2), and BOTH against the CPU restatement on six sequences of the batch (a
+    sequence's recurrence never sees its neighbours, so a slice of the batch is a full check of it)."""
+    from oracle import restatement as R
+    from helpers import BF16_RTOL
+    L = _lib()
+    T, B, H, D = 64, 4096, 512, 64
+    G, md = (4, 0) if mode == "lstm" else (3, 1)
+    w, x, lengths = _rnn_inputs(mode, T, B, H, D, seed=4096, ragged=True)
+    pick = torch.tensor([0, 1, 2, 2047, 4094, 4095])
+    leaves = {k: [t.clone().requires_grad_(True) for t in v] for k, v in w.items()}
+    xr = x[pick].clone().requires_grad_(True)
+    outs, fins = [], []
+    for d in range(2):
+        o, hf = R._run_direction(xr, lengths[pick], leaves["w_ih"][d], leaves["w_hh"][d], leaves["b_ih"][d],
+                                 leaves["b_hh"][d], mode, reverse=(d == 1))
+        outs.append(o)
+        fins.append(hf)
+    out_ref = torch.cat(outs, 2)
+    gq = torch.Generator().manual_seed(5)
+    dout, dfin = torch.randn(B, T, 2 * H, generator=gq), torch.randn(2, B, H, generator=gq)
+    (out_ref * dout[pick]).sum().add((torch.stack(fins) * dfin[:, pick]).sum()).backward()
+    c = lambda t: t.cuda().contiguous()
+    w_ih, w_hh = c(torch.cat(w["w_ih"])), c(torch.stack(w["w_hh"]))
+    b_ih, b_hh = c(torch.cat(w["b_ih"])), c(torch.cat(w["b_hh"]))
+    x_tm, len_d = c(x.transpose(0, 1)), lengths.cuda()
+    dout_tm, dfin_d = c(dout.transpose(0, 1)), c(dfin)
+    pk = pick.cuda()
+    res = {}
+    for prec in (0, 1):
+        gates = torch.empty(T, B, 2, G, H, device="cuda")
+        L.check(L.lib.slnlp_gemm_f32(0, 1, T * B, 2 * G * H, D, x_tm.data_ptr(), D, w_ih.data_ptr(), D,
+                                     gates.data_ptr(), 2 * G * H, b_ih.data_ptr(), 0.0, None, 0, S()))
+        out, stash, hfin = (torch.empty(T, B, 2 * H, device="cuda"), torch.empty(T, B, 2, H, device="cuda"),
+                            torch.empty(2, B, H, device="cuda"))
+        c0 = L.lib.slnlp_launch_count()
+        L.check(L.lib.slnlp_rnn_layer_fwd(md, prec, T, B, H, 2, gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(),
+                                          len_d.data_ptr(), None, None, out.data_ptr(), stash.data_ptr(),
+                                          hfin.data_ptr(), S()))
+        if prec == 1:     # a batch of 4096 takes the per-step family (one launch per timestep), not a persistent kernel
+            assert L.lib.slnlp_launch_count() - c0 >= T
+        carry = torch.zeros(4, B, H, device="cuda")
+        L.check(L.lib.slnlp_rnn_layer_bwd(md, prec, T, B, H, 2, gates.data_ptr(), stash.data_ptr(), out.data_ptr(),
+                                          w_hh.data_ptr(), len_d.data_ptr(), None, None, dout_tm.data_ptr(),
+                                          dfin_d.data_ptr(), None, None, None, carry.data_ptr(), S()))
+        dx = torch.empty(T, B, D, device="cuda")
+        L.check(L.lib.slnlp_gemm_f32(0, 0, T * B, D, 2 * G * H, gates.data_ptr(), 2 * G * H, w_ih.data_ptr(), D,
+                                     dx.data_ptr(), D, None, 0.0, None, 0, S()))
+        torch.cuda.synchronize()
+        tol = 1e-5 if prec == 0 else BF16_RTOL
+        assert rel_err(out[:, pk].transpose(0, 1), out_ref) < tol, (prec, "out")
+        assert rel_err(hfin[:, pk], torch.stack(fins)) < tol, (prec, "h_final")
+        assert rel_err(dx[:, pk].transpose(0, 1), xr.grad) < 2 * tol, (prec, "dx")
+        res[prec] = (out, hfin, dx, gates)
+    for i, what in enumerate(("out", "h_final", "dx", "d_gates")):
+        assert rel_err(res[1][i], res[0][i]) < BF16_RTOL, what
+    pad = (torch.arange(T).view(T, 1) >= lengths.view(1, B)).cuda()
+    assert float(res[1][0][pad].abs().max()) == 0.0 and float(res[0][0][pad].abs().max()) == 0.0
