@@ -40,6 +40,12 @@ const char* slnlp_last_error_string(void);
 int64_t slnlp_launch_count(void);
 /* number of SMs of the current device (grid sizing), or -1 */
 int slnlp_device_sm_count(void);
+/* a NEW non-blocking CUDA stream on the current device (NULL on failure) / its release.  The host side
+ * wraps it as an external stream: framework stream POOLS hand the same stream to several owners, and a
+ * fit that captures its step graph on a stream another fit of the process is launching on would swallow
+ * that fit's work into the graph (grid search with several fits per GPU). */
+void* slnlp_stream_create(void);
+int slnlp_stream_destroy(void* stream);
 
 /* ---- K1: phonological embedding (nn.Embedding, bkp:49,60,374-379; Transformer
  * model/transformer.py:32-37,106-109).  One fused gather(+concat)(+scale)(+PE).
@@ -91,6 +97,19 @@ int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K,
 /* out[c] = beta*out[c] + sum_r A[r*lda + c]   (bias gradients) */
 int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
                      slnlp_stream_t stream);
+
+/* tuning / diagnostics of the persistent recurrent kernel (H = 128, rnn_persistent.cu).
+ *   variant >= 0: step-loop variant of the forward kernel (0 = k-major issue, one commit; 1 = gate-major
+ *                 issue, early commit, last gate tile overlapped with the early gates' activations; the
+ *                 default, or $SLNLP_PERSIST_VAR); -1 keeps the current one;
+ *   profile  1/0: launch the instrumented instantiations, which sum %clock deltas per phase of every step
+ *                 (0 MMA issue, 1 deferred stores + prefetch issue, 2 MMA wait, 3 tcgen05.ld, 4 gate math +
+ *                 h tile store, 5 proxy fence, 6 CTA barrier); -1 keeps the current setting;
+ *   out48 != NULL: synchronises the device and copies the table [fwd|bwd][3 threads of CTA (0,0): the MMA
+ *                 issuer, thread 160, thread 511][8 phases] (cycles summed over the steps of the last layer
+ *                 launched) to host memory.
+ * Process-wide switches, not per stream: set them before launching (profiles/prof_persist_phases.py). */
+int slnlp_debug_persist_config(int variant, int profile, uint32_t* out48);
 
 /* diagnostic: clusters of the cluster-persistent recurrent kernel (H = 256: 8 CTAs, H = 512: 16 CTAs)
  * the device holds at once, or -1 */

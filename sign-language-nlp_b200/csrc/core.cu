@@ -515,6 +515,19 @@ extern "C" {
 int slnlp_abi_version(void) { return SLNLP_ABI_VERSION; }
 const char* slnlp_last_error_string(void) { return err_buf(); }
 int64_t slnlp_launch_count(void) { return slnlp::launches(); }
+void* slnlp_stream_create(void) {
+  cudaStream_t st = nullptr;
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+    slnlp::fail("slnlp_stream_create: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return st;
+}
+int slnlp_stream_destroy(void* stream) {
+  const cudaError_t e = cudaStreamDestroy(reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return slnlp::fail("slnlp_stream_destroy: %s", cudaGetErrorString(e));
+  return 0;
+}
 int slnlp_device_sm_count(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;

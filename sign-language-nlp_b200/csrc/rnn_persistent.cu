@@ -1,7 +1,15 @@
 // K4 on the 5th-gen tensor cores: persistent recurrent layer for H = 128.
 //
 // One CTA owns one direction and a slice of 4 (16 at large batch) sequences for ALL timesteps
-// (the recurrence is independent across the batch, so no CTA ever waits for another):
+// (the recurrence is independent across the batch, so no CTA ever waits for another).  Warp
+// specialised: 16 epilogue warps (512 threads, one per (hidden unit, sequence column group)) and ONE
+// MMA warp that does nothing but issue the step's tcgen05.mma batch as soon as the CTA barrier that
+// publishes h_t releases.  (Round-2 per-phase %clock table of the previous single-role layout,
+// profiles/r02_persist_phases.txt: the issuing thread spent 419 cycles of a 1,253-cycle step issuing
+// the 32 MMAs and then another 317 issuing its own share of the deferred stores and prefetches while
+// the other 15 warps already waited for it; the step loop was instruction-issue bound - ~155
+// instructions per warp and step, a third of them 64-bit address arithmetic - not tensor bound: the
+// accumulators were ready 80 cycles after the issuer finally looked.):
 //   * W_hh (bf16) is loaded ONCE into TENSOR MEMORY (128 lanes x 64 packed columns per gate
 //     tile) and stays resident for the whole layer as the A operand of every MMA; reading it
 //     from shared memory instead costs 128 KB per step through a 128 B/clk port;
@@ -18,6 +26,7 @@
 //
 // Numerics: the recurrent product rounds h and W_hh (dG in BPTT) to bf16 with fp32
 // accumulation - the 2e-2 path of north_star.  Everything else is fp32.
+#include <stdlib.h>
 #include "tc05.cuh"
 
 namespace slnlp {
@@ -27,11 +36,46 @@ constexpr int PN = 16;    // MMA N (the smallest N of an M = 128 instruction)
 // PSEQ (template): sequences a CTA actually owns; columns PSEQ..PN-1 of the B tile stay zero.  The per-step
 // gate math and stores scale with PSEQ, and at the reference's batch of 50 most SMs are idle, so small
 // batches run 4 sequences per CTA (26 CTAs at B = 50) and large ones 16 (fewer W_hh loads, fewer waves).
-constexpr int PTHREADS = 512;  // 16 warps: TMEM lane quadrant = warp % 4, column group = warp / 4
-constexpr int NACC = 4;        // BPTT: partial accumulators (independent MMA chains)
-constexpr int FACC = 2;        // forward: partial accumulators per gate tile (two independent MMA chains)
+constexpr int PTHREADS = 512;  // 16 epilogue warps: TMEM lane quadrant = warp % 4, column group = warp / 4
+constexpr int PBLOCK = PTHREADS + 32;   // + the MMA warp (warp 16)
 constexpr int A_COL0 = 128;    // TMEM: accumulators in columns [0, 128), the resident W_hh operand from 128 on
 constexpr int TMEM_COLS = 512; // 64 + up to 256 operand columns -> the whole tensor memory of the SM
+
+// ---- per-phase cycle table of the step loop (slnlp_debug_persist_config): the PROF instantiations read
+// %clock at fixed points of every step and three threads of CTA (0,0) (the MMA warp's lane 0, thread 160
+// and thread 511 of the epilogue warps) publish the per-phase sums here.  [fwd|bwd][thread][phase]
+constexpr int NPHASE = 8;
+__device__ uint32_t g_persist_prof[2][3][NPHASE];
+__device__ __forceinline__ uint32_t clk32() {
+  uint32_t c;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+  return c;
+}
+struct PhaseClock {
+  uint32_t acc[NPHASE], last;
+  __device__ __forceinline__ void start() {
+#pragma unroll
+    for (int i = 0; i < NPHASE; ++i) acc[i] = 0;
+    last = clk32();
+  }
+  __device__ __forceinline__ void mark(int i) {
+    const uint32_t now = clk32();
+    acc[i] += now - last;
+    last = now;
+  }
+  __device__ __forceinline__ void publish(int which) {
+    const int tid = threadIdx.x;
+    const int slot = tid == PTHREADS ? 0 : tid == 160 ? 1 : tid == PTHREADS - 1 ? 2 : -1;
+    if (slot < 0 || blockIdx.x != 0 || blockIdx.y != 0) return;
+#pragma unroll
+    for (int i = 0; i < NPHASE; ++i) g_persist_prof[which][slot][i] = acc[i];
+  }
+};
+#define PROF_MARK(i) do { if (PROF) pclk.mark(i); } while (0)
+
+// CTA-wide barrier over the epilogue warps AND the MMA warp (reached from two code paths: bar.sync with an
+// explicit thread count instead of __syncthreads)
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PBLOCK) : "memory"); }
 
 struct PersistFwd {
   int T, B, ndir;
@@ -46,9 +90,9 @@ struct PersistFwd {
   float* h_final;
 };
 
-template <int G, int PSEQ>
-__global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(PersistFwd p) {
-  pdl_wait();
+// FA: partial accumulators per gate tile (FA independent MMA chains, summed by the epilogue).
+template <int G, int PSEQ, int FA, bool PROF>
+__global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_fwd_kernel(PersistFwd p) {
   pdl_launch_dependents();
   constexpr int PC = PSEQ / 4;   // batch columns per thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -58,23 +102,16 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, warp_u = warp_uniform();
+  const bool mma_warp = warp_u == PTHREADS / 32;
   const int d = blockIdx.y, b0 = blockIdx.x * PSEQ;
   const int T = p.T, B = p.B;
   const int j = tid & (H - 1);   // hidden unit = TMEM lane
-  const int cg = tid >> 7;       // column group: batch columns cg*PC .. cg*PC+PC-1
+  const int cg = (tid >> 7) & 3; // column group: batch columns cg*PC .. cg*PC+PC-1
 
-  // ---- one-time setup: h tile = h0 or 0 (W_hh goes to tensor memory below)
+  // ---- prologue that only touches the weights: it runs BEFORE griddepcontrol.wait, i.e. under the tail of
+  // the hoisted-projection GEMM that precedes this kernel in the stream (weights were last written by the
+  // previous training step's SGD kernel, complete long before that GEMM started)
   const float* W = p.w_hh + (int64_t)d * G * H * H;
-  float hreg[PC], creg[PC];
-  int len[PC];
-#pragma unroll
-  for (int c = 0; c < PC; ++c) {
-    const int n = cg * PC + c, b = b0 + n;
-    hreg[c] = (p.h0 && b < B) ? p.h0[((int64_t)d * B + b) * H + j] : 0.f;
-    creg[c] = (p.c0 && b < B) ? p.c0[((int64_t)d * B + b) * H + j] : 0.f;
-    len[c] = b < B ? (p.lengths ? (int)p.lengths[b] : T) : 0;
-    *reinterpret_cast<__nv_bfloat16*>(sH + canon_off(n, j, PN)) = __float2bfloat16(hreg[c]);
-  }
   if (tid == 0) mbar_init(bar, 1);
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   fence_async_smem();
@@ -87,7 +124,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
   // bf16 = 64 packed 32-bit columns at column A_COL0 + 64 g.  Reading A from TMEM instead of
   // shared memory takes the 128 KB-per-step operand fetch off the 128 B/clk shared-memory port
   // (it bounded the step at ~1000 cycles).  Warp w fills lane quadrant w % 4 of gate w / 4.
-  if (cg < G) {
+  if (!mma_warp && cg < G) {
     const float* wrow = W + ((int64_t)cg * H + j) * H;
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
@@ -102,158 +139,232 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_fwd_kernel(Persist
     }
     tmem_wait_st();
   }
+  const float* bh = p.b_hh + (int64_t)d * G * H;
+  float bias[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) bias[g] = mma_warp ? 0.f : bh[g * H + j];
+  // the h tile rows PSEQ..PN-1 are never written: zero them once
+  for (int e = tid; e < PN * H / 8; e += PBLOCK) {
+    const int n = e % PN;   // canonical tile: 16-byte core rows, row index = (e % (PN)) within a K-group
+    if (n >= PSEQ) reinterpret_cast<uint4*>(sH)[e] = make_uint4(0, 0, 0, 0);
+  }
+
+  pdl_wait();   // ---- from here on: data of this step (hoisted projection, lengths, initial state)
+
+  float hreg[PC], creg[PC];
+  int len[PC];
+  if (!mma_warp) {
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+      const int n = cg * PC + c, b = b0 + n;
+      hreg[c] = (p.h0 && b < B) ? p.h0[((int64_t)d * B + b) * H + j] : 0.f;
+      creg[c] = (p.c0 && b < B) ? p.c0[((int64_t)d * B + b) * H + j] : 0.f;
+      len[c] = b < B ? (p.lengths ? (int)p.lengths[b] : T) : 0;
+      *reinterpret_cast<__nv_bfloat16*>(sH + canon_off(n, j, PN)) = __float2bfloat16(hreg[c]);
+    }
+  }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   constexpr uint32_t idesc = make_idesc(128, PN);
   const uint64_t descB0 = make_desc(smem_u32(sH), PN * 16, 128);
   const bool have_state0 = p.h0 != nullptr;
-  const float* bh = p.b_hh + (int64_t)d * G * H;
-  float bias[G];
-#pragma unroll
-  for (int g = 0; g < G; ++g) bias[g] = bh[g * H + j];
+  PhaseClock pclk;
+  if (PROF) pclk.start();
 
-  // per-column base pointers; a timestep only adds t * (row stride) to them
-  const int64_t gstride = (int64_t)B * p.ndir * G * H, ostride = (int64_t)B * p.ndir * H;
-  float* gbase[PC];
-  float* obase[PC];
-  float* sbase[PC];
-  float* fin[PC];
-  uint32_t hoff[PC];
-  bool valid[PC];
+  if (mma_warp) {
+    // ================= MMA warp: one elected lane issues the step's batch, then the whole warp waits at
+    // the CTA barrier for the epilogue warps to publish h_t
+    for (int step = 0; step < T; ++step) {
+      const bool do_mma = step > 0 || have_state0;
+      if (do_mma && elect_one()) {
+        // G gate tiles x (H/16) k-steps, A = W_hh from tensor memory, B = the h tile in shared memory;
+        // issued k-major so that consecutive MMAs accumulate into different gate tiles
 #pragma unroll
-  for (int c = 0; c < PC; ++c) {
-    const int n = cg * PC + c;
-    valid[c] = b0 + n < B;
-    const int b = valid[c] ? b0 + n : 0;
-    gbase[c] = p.gates + ((int64_t)b * p.ndir + d) * G * H + j;
-    obase[c] = p.out + (int64_t)b * p.ndir * H + (int64_t)d * H + j;
-    sbase[c] = p.stash + ((int64_t)b * p.ndir + d) * H + j;
-    fin[c] = p.h_final ? p.h_final + ((int64_t)d * B + b) * H + j : nullptr;
-    hoff[c] = canon_off(n, j, PN);
-  }
-  // the h tile rows PSEQ..PN-1 are never written: zero them once
-  for (int e = tid; e < PN * H / 8; e += PTHREADS) {
-    const int n = e % PN;   // canonical tile: 16-byte core rows, row index = (e % (PN)) within a K-group
-    if (n >= PSEQ) reinterpret_cast<uint4*>(sH)[e] = make_uint4(0, 0, 0, 0);
-  }
-  fence_async_smem();
-  __syncthreads();
-  // hoisted input projection, loaded one step ahead into a second register set
-  float xg[G][PC], xn[G][PC];
-  auto load_x = [&](float (&x)[G][PC], int t) {
-    const int64_t off = (int64_t)t * gstride;
+        for (int kk = 0; kk < H / 16; ++kk)
 #pragma unroll
-    for (int c = 0; c < PC; ++c) {
-      const bool act = t < len[c];
-#pragma unroll
-      for (int g = 0; g < G; ++g) x[g][c] = act ? gbase[c][off + g * H] : 0.f;
-    }
-  };
-  load_x(xg, d == 0 ? 0 : T - 1);
-  // results of a step are written to HBM one iteration later, while the next step's MMAs run
-  float gout[G][PC], hv[PC], sv[PC];
-  auto store_step = [&](int t) {
-    const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride;
-#pragma unroll
-    for (int c = 0; c < PC; ++c) {
-      if (!valid[c]) continue;
-      if (t >= len[c]) {
-        obase[c][ooff] = 0.f;
-        sbase[c][ooff] = 0.f;
-        continue;
+          for (int g = 0; g < G; ++g)
+            umma_bf16_ts(tmem + (g * FA + (kk % FA)) * PN, tmem + A_COL0 + g * 64 + kk * 8,
+                         descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk >= FA ? 1u : 0u);
+        umma_commit(bar);
       }
-#pragma unroll
-      for (int g = 0; g < G; ++g) gbase[c][goff + g * H] = gout[g][c];
-      sbase[c][ooff] = sv[c];
-      obase[c][ooff] = hv[c];
-      if (fin[c] && (d == 0 ? t == len[c] - 1 : t == 0)) *fin[c] = hv[c];
-    }
-  };
-
-  uint32_t phase = 0;
-  int t_prev = 0;
-  for (int step = 0; step < T; ++step) {
-    const int t = d == 0 ? step : T - 1 - step;
-    const bool do_mma = step > 0 || have_state0;
-    if (do_mma && warp_u == 0 && elect_one()) {
-      // G gate tiles x (H/16) k-steps, A = W_hh from tensor memory, B = the h tile in shared memory;
-      // issued k-major so that consecutive MMAs accumulate into different gate tiles
-#pragma unroll
-      for (int kk = 0; kk < H / 16; ++kk)
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-          umma_bf16_ts(tmem + (g * FACC + (kk % FACC)) * PN, tmem + A_COL0 + g * 64 + kk * 8,
-                       descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk >= FACC ? 1u : 0u);
-      umma_commit(bar);
-    }
-    __syncwarp();
-    // off the critical path (the tensor core is busy): previous step -> HBM, next step's x <- HBM
-    if (step > 0) store_step(t_prev);
-    if (step + 1 < T) load_x(xn, d == 0 ? step + 1 : T - 2 - step);
-    float acc[G][PC];
-    if (do_mma) {
-      mbar_wait(bar, phase);
-      phase ^= 1;
+      __syncwarp();
+      PROF_MARK(0);   // MMA issue + commit
+      tc_fence_before();
+      cta_bar();
       tc_fence_after();
-      uint32_t raw[G * FACC][PC];
+      PROF_MARK(6);   // waiting for the epilogue warps (h_t published)
+    }
+  } else {
+    // ================= epilogue warps
+    // running pointers at the CURRENT step's row of every array; a step adds +-(row stride)
+    const int64_t gstride = (int64_t)B * p.ndir * G * H, ostride = (int64_t)B * p.ndir * H;
+    const int64_t gdelta = d == 0 ? gstride : -gstride, odelta = d == 0 ? ostride : -ostride;
+    const int t0 = d == 0 ? 0 : T - 1;
+    float* gcur[PC];
+    float* ocur[PC];
+    float* scur[PC];
+    float* fin[PC];
+    uint32_t hoff[PC];
+    bool valid[PC];
+    int tfin[PC];
 #pragma unroll
-      for (int g = 0; g < G * FACC; ++g) tmem_ldn_nowait<PC>(tmem_mine + g * PN, raw[g]);
-      tmem_wait_ld();
+    for (int c = 0; c < PC; ++c) {
+      const int n = cg * PC + c;
+      valid[c] = b0 + n < B;
+      const int b = valid[c] ? b0 + n : 0;
+      gcur[c] = p.gates + ((int64_t)b * p.ndir + d) * G * H + j + t0 * gstride;
+      ocur[c] = p.out + (int64_t)b * p.ndir * H + (int64_t)d * H + j + t0 * ostride;
+      scur[c] = p.stash + ((int64_t)b * p.ndir + d) * H + j + t0 * ostride;
+      fin[c] = p.h_final ? p.h_final + ((int64_t)d * B + b) * H + j : nullptr;
+      hoff[c] = canon_off(n, j, PN);
+      tfin[c] = d == 0 ? len[c] - 1 : 0;
+    }
+    // hoisted input projection, loaded one step ahead into a second register set.  The two sets swap
+    // roles every step (the loop is unrolled by two): a register copy at the end of the step would make
+    // every warp wait for its loads there, on the step-to-step chain.
+    float xa[G][PC], xb[G][PC];
 #pragma unroll
-      for (int g = 0; g < G; ++g)
+    for (int c = 0; c < PC; ++c)
+#pragma unroll
+      for (int g = 0; g < G; ++g) xa[g][c] = t0 < len[c] ? gcur[c][g * H] : 0.f;
+    // results of a step are written to HBM one iteration later, while the next step's MMAs run
+    float gout[G][PC], hv[PC], sv[PC];
+    uint32_t phase = 0;
+    auto one_step = [&](float (&xg)[G][PC], float (&xn)[G][PC], int step) {
+      const int t = d == 0 ? step : T - 1 - step;
+      const int t_prev = d == 0 ? t - 1 : t + 1, t_next = d == 0 ? t + 1 : t - 1;
+      const bool do_mma = step > 0 || have_state0;
+      // off the critical path (the tensor core is busy): previous step -> HBM, next step's x <- HBM
+      if (step > 0) {
 #pragma unroll
         for (int c = 0; c < PC; ++c) {
-          float a = 0.f;
+          if (!valid[c]) continue;
+          float* gp = gcur[c] - gdelta;
+          float* op = ocur[c] - odelta;
+          float* sp = scur[c] - odelta;
+          if (t_prev >= len[c]) {
+            *op = 0.f;
+            *sp = 0.f;
+            continue;
+          }
 #pragma unroll
-          for (int q = 0; q < FACC; ++q) a += __uint_as_float(raw[g * FACC + q][c]);
-          acc[g][c] = a;
+          for (int g = 0; g < G; ++g) gp[g * H] = gout[g][c];
+          *sp = sv[c];
+          *op = hv[c];
+          if (fin[c] && t_prev == tfin[c]) *fin[c] = hv[c];
         }
-    } else {
+      }
+      if (step + 1 < T) {
 #pragma unroll
-      for (int g = 0; g < G; ++g)
+        for (int c = 0; c < PC; ++c) {
+          const float* gp = gcur[c] + gdelta;
+          const bool act = t_next < len[c];
 #pragma unroll
-        for (int c = 0; c < PC; ++c) acc[g][c] = 0.f;
-    }
+          for (int g = 0; g < G; ++g) xn[g][c] = act ? gp[g * H] : 0.f;
+        }
+      }
+      PROF_MARK(1);   // issue of the deferred stores and of the next step's loads
+      float acc[G][PC];
+      if (do_mma) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        PROF_MARK(2);   // wait for the MMAs
+        uint32_t raw[G * FA][PC];
 #pragma unroll
-    for (int c = 0; c < PC; ++c) {
-      if (G == 4) {
-        const float gi = sigmoid_fast(xg[0][c] + acc[0][c] + bias[0]);
-        const float gf = sigmoid_fast(xg[1][c] + acc[1][c] + bias[1]);
-        const float gg = tanh_fast(xg[2][c] + acc[2][c] + bias[2]);
-        const float go = sigmoid_fast(xg[G - 1][c] + acc[G - 1][c] + bias[G - 1]);
-        const float cn = gf * creg[c] + gi * gg;
-        hv[c] = go * tanh_fast(cn);
-        sv[c] = cn;
-        gout[0][c] = gi; gout[1][c] = gf; gout[2][c] = gg; gout[G - 1][c] = go;
+        for (int g = 0; g < G * FA; ++g) tmem_ldn_nowait<PC>(tmem_mine + g * PN, raw[g]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+          for (int c = 0; c < PC; ++c) {
+            float a = __uint_as_float(raw[g * FA][c]);
+#pragma unroll
+            for (int q = 1; q < FA; ++q) a += __uint_as_float(raw[g * FA + q][c]);
+            acc[g][c] = a;
+          }
+        PROF_MARK(3);   // tcgen05.ld of the accumulators
       } else {
-        const float hn = acc[2][c] + bias[2];
-        const float gr = sigmoid_fast(xg[0][c] + acc[0][c] + bias[0]);
-        const float gz = sigmoid_fast(xg[1][c] + acc[1][c] + bias[1]);
-        const float gn = tanh_fast(xg[2][c] + gr * hn);
-        hv[c] = (1.f - gz) * gn + gz * hreg[c];
-        sv[c] = hn;
-        gout[0][c] = gr; gout[1][c] = gz; gout[2][c] = gn;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+          for (int c = 0; c < PC; ++c) acc[g][c] = 0.f;
       }
-      // state update + next step's B tile: the only stores the next MMA waits for
-      if (valid[c] && t < len[c]) {
-        if (G == 4) creg[c] = sv[c];
-        hreg[c] = hv[c];
-        *reinterpret_cast<__nv_bfloat16*>(sH + hoff[c]) = __float2bfloat16(hv[c]);
+#pragma unroll
+      for (int c = 0; c < PC; ++c) {
+        if (G == 4) {
+          const float gi = sigmoid_fast(xg[0][c] + acc[0][c] + bias[0]);
+          const float gf = sigmoid_fast(xg[1][c] + acc[1][c] + bias[1]);
+          const float gg = tanh_fast(xg[2][c] + acc[2][c] + bias[2]);
+          const float go = sigmoid_fast(xg[G - 1][c] + acc[G - 1][c] + bias[G - 1]);
+          const float cn = gf * creg[c] + gi * gg;
+          hv[c] = go * tanh_fast(cn);
+          sv[c] = cn;
+          gout[0][c] = gi; gout[1][c] = gf; gout[2][c] = gg; gout[G - 1][c] = go;
+        } else {
+          const float hn = acc[2][c] + bias[2];
+          const float gr = sigmoid_fast(xg[0][c] + acc[0][c] + bias[0]);
+          const float gz = sigmoid_fast(xg[1][c] + acc[1][c] + bias[1]);
+          const float gn = tanh_fast(xg[2][c] + gr * hn);
+          hv[c] = (1.f - gz) * gn + gz * hreg[c];
+          sv[c] = hn;
+          gout[0][c] = gr; gout[1][c] = gz; gout[2][c] = gn;
+        }
+        // state update + next step's B tile: the only stores the next MMA waits for
+        if (valid[c] && t < len[c]) {
+          if (G == 4) creg[c] = sv[c];
+          hreg[c] = hv[c];
+          *reinterpret_cast<__nv_bfloat16*>(sH + hoff[c]) = __float2bfloat16(hv[c]);
+        }
+      }
+      PROF_MARK(4);   // gate math + h (bf16) into the next step's B tile
+      // h tile (generic-proxy stores) -> visible to the tensor core; accumulators free to overwrite
+      fence_async_smem();
+      tc_fence_before();
+      PROF_MARK(5);   // proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC)
+      cta_bar();
+      if (PROF) {     // BAR.SYNC defers its blocking to the next consumer of barrier-protected state: make one
+        asm volatile("" ::"r"(*reinterpret_cast<volatile uint32_t*>(tmem_slot)) : "memory");
+      }
+      PROF_MARK(6);   // CTA barrier (time until the slowest warp arrives)
+#pragma unroll
+      for (int c = 0; c < PC; ++c) {
+        gcur[c] += gdelta;
+        ocur[c] += odelta;
+        scur[c] += odelta;
+      }
+    };
+    for (int step = 0; step < T; step += 2) {
+      one_step(xa, xb, step);
+      if (step + 1 < T) one_step(xb, xa, step + 1);
+    }
+    // the last step's results
+    {
+      const int t_last = d == 0 ? T - 1 : 0;
+#pragma unroll
+      for (int c = 0; c < PC; ++c) {
+        if (!valid[c]) continue;
+        float* gp = gcur[c] - gdelta;
+        float* op = ocur[c] - odelta;
+        float* sp = scur[c] - odelta;
+        if (t_last >= len[c]) {
+          *op = 0.f;
+          *sp = 0.f;
+          continue;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) gp[g * H] = gout[g][c];
+        *sp = sv[c];
+        *op = hv[c];
+        if (fin[c] && t_last == tfin[c]) *fin[c] = hv[c];
       }
     }
-    // h tile (generic-proxy stores) -> visible to the tensor core; accumulators free to overwrite
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    t_prev = t;
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-      for (int c = 0; c < PC; ++c) xg[g][c] = xn[g][c];
   }
-  store_step(t_prev);
+  if (PROF) pclk.publish(0);
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -274,9 +385,9 @@ struct PersistBwd {
   float* dc0;
 };
 
-template <int G, int PSEQ>
-__global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(PersistBwd p) {
-  pdl_wait();
+// NA: partial accumulators of the single [128 x PN] output tile (NA independent MMA chains).
+template <int G, int PSEQ, int NA, bool PROF>
+__global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_bwd_kernel(PersistBwd p) {
   pdl_launch_dependents();
   constexpr int PC = PSEQ / 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -286,13 +397,15 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, warp_u = warp_uniform();
+  const bool mma_warp = warp_u == PTHREADS / 32;
   const int d = blockIdx.y, b0 = blockIdx.x * PSEQ;
   const int T = p.T, B = p.B;
   const int k = tid & (H - 1);  // hidden unit = TMEM lane = output row of W_hh^T
-  const int cg = tid >> 7;
+  const int cg = (tid >> 7) & 3;
 
+  // ---- weights-only prologue, before griddepcontrol.wait (see the forward kernel)
   const float* W = p.w_hh + (int64_t)d * GH * H;
-  for (int e = tid; e < PN * GH / 8; e += PTHREADS) reinterpret_cast<uint4*>(sD)[e] = make_uint4(0, 0, 0, 0);
+  for (int e = tid; e < PN * GH / 8; e += PBLOCK) reinterpret_cast<uint4*>(sD)[e] = make_uint4(0, 0, 0, 0);
   if (tid == 0) mbar_init(bar, 1);
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   fence_async_smem();
@@ -304,7 +417,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
   // A' = W_hh^T -> tensor memory: lane = hidden unit k, K index = gate row j' (GH of them) = GH/2 packed
   // columns from A_COL0.  Column group cg fills rows j' in [cg*GH/4, (cg+1)*GH/4): global reads are
   // coalesced across the warp (consecutive k).
-  {
+  if (!mma_warp) {
     constexpr int JQ = GH / 4;   // 32 G gate rows -> 16 G packed columns = G stores of 16 columns
 #pragma unroll 1
     for (int i = 0; i < G; ++i) {
@@ -318,195 +431,230 @@ __global__ void __launch_bounds__(PTHREADS, 1) rnn_persistent_bwd_kernel(Persist
     }
     tmem_wait_st();
   }
+
+  pdl_wait();   // ---- from here on: activations and gradients of this step
+
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   constexpr uint32_t idesc = make_idesc(128, PN);
   const uint64_t descB0 = make_desc(smem_u32(sD), PN * 16, 128);
-
-  int len[PC];
-  float carry[PC];  // LSTM: dc carry; GRU: direct dh carry (dh * z)
-#pragma unroll
-  for (int c = 0; c < PC; ++c) {
-    const int b = b0 + cg * PC + c;
-    len[c] = b < B ? (p.lengths ? (int)p.lengths[b] : T) : 0;
-    carry[c] = 0.f;
-  }
-
-  // per-column base pointers; a timestep only adds t * (row stride) to them
-  const int64_t gstride = (int64_t)B * p.ndir * GH, ostride = (int64_t)B * p.ndir * H;
-  float* gbase[PC];
-  float* sbase[PC];
-  const float* obase[PC];
-  const float* dbase[PC];
-  int64_t cidx[PC];
-  uint32_t doff[PC];
-  bool valid[PC];
-#pragma unroll
-  for (int c = 0; c < PC; ++c) {
-    const int n = cg * PC + c;
-    valid[c] = b0 + n < B;
-    const int b = valid[c] ? b0 + n : 0;
-    gbase[c] = p.gates + ((int64_t)b * p.ndir + d) * GH + k;
-    sbase[c] = p.stash + ((int64_t)b * p.ndir + d) * H + k;
-    obase[c] = p.out + (int64_t)b * p.ndir * H + (int64_t)d * H + k;
-    dbase[c] = p.dout ? p.dout + (int64_t)b * p.ndir * H + (int64_t)d * H + k : nullptr;
-    cidx[c] = ((int64_t)d * B + b) * H + k;
-    doff[c] = canon_off(n, k, PN);
-  }
-  // per-step operands, loaded one step ahead into a second register set: activated gates, stash,
-  // predecessor state, dout
-  struct StepIn {
-    float g[G][PC], s[PC], pv[PC], d[PC];
-  };
-  StepIn cur, nxt;
-  auto load_step = [&](StepIn& in, int t) {
-    const int tp = d == 0 ? t - 1 : t + 1;
-    const bool has_prev = tp >= 0 && tp < T;
-    const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride, poff = (int64_t)tp * ostride;
-#pragma unroll
-    for (int c = 0; c < PC; ++c) {
-      const bool act = t < len[c];
-#pragma unroll
-      for (int g = 0; g < G; ++g) in.g[g][c] = act ? gbase[c][goff + g * H] : 0.f;
-      in.s[c] = act ? sbase[c][ooff] : 0.f;
-      in.d[c] = (act && dbase[c]) ? dbase[c][ooff] : 0.f;
-      float pv = 0.f;
-      if (act) {
-        if (G == 4) pv = has_prev ? sbase[c][poff] : (p.c0 ? p.c0[cidx[c]] : 0.f);
-        else pv = has_prev ? obase[c][poff] : (p.h0 ? p.h0[cidx[c]] : 0.f);
-      }
-      in.pv[c] = pv;
-    }
-  };
-  load_step(cur, d == 0 ? T - 1 : 0);
-  // d(pre-activations) of a step go to HBM one iteration later, while the next step's MMAs run
-  float dg[G][PC], dst[PC];
-  auto store_step = [&](int t) {
-    const int64_t goff = (int64_t)t * gstride, ooff = (int64_t)t * ostride;
-#pragma unroll
-    for (int c = 0; c < PC; ++c) {
-      if (!valid[c]) continue;
-#pragma unroll
-      for (int g = 0; g < G; ++g) gbase[c][goff + g * H] = dg[g][c];
-      if (G == 3) sbase[c][ooff] = dst[c];
-    }
-  };
-
-  uint32_t phase = 0;
   const int nsteps = T + ((p.dh0 || p.dc0) ? 1 : 0);
-  int t_prev = 0;
-  bool pending = false;
-  for (int step = 0; step < nsteps; ++step) {
-    const bool final_only = step == T;
-    const int t = final_only ? (d == 0 ? -1 : T) : (d == 0 ? T - 1 - step : step);
-    const bool do_mma = step > 0;
-    if (do_mma && warp_u == 0 && elect_one()) {
-      // A' = W_hh^T from tensor memory, B' = the dG tile; NACC partial accumulators: consecutive
-      // MMAs are independent, the epilogue adds them
+  PhaseClock pclk;
+  if (PROF) pclk.start();
+
+  if (mma_warp) {
+    for (int step = 0; step < nsteps; ++step) {
+      if (step > 0 && elect_one()) {
+        // A' = W_hh^T from tensor memory, B' = the dG tile; NA partial accumulators: consecutive
+        // MMAs are independent, the epilogue adds them
 #pragma unroll
-      for (int kk = 0; kk < GH / 16; ++kk)
-        umma_bf16_ts(tmem + (kk % NACC) * PN, tmem + A_COL0 + kk * 8,
-                     descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk >= NACC ? 1u : 0u);
-      umma_commit(bar);
-    }
-    __syncwarp();
-    // off the critical path: previous step's gradients -> HBM, next step's operands <- HBM
-    if (pending) {
-      store_step(t_prev);
-      pending = false;
-    }
-    if (step + 1 < T) load_step(nxt, d == 0 ? T - 2 - step : step + 1);
-    float m[PC];
-    if (do_mma) {
-      mbar_wait(bar, phase);
-      phase ^= 1;
+        for (int kk = 0; kk < GH / 16; ++kk)
+          umma_bf16_ts(tmem + (kk % NA) * PN, tmem + A_COL0 + kk * 8,
+                       descB0 + (uint64_t)((kk * 2 * (PN * 16)) >> 4), idesc, kk >= NA ? 1u : 0u);
+        umma_commit(bar);
+      }
+      __syncwarp();
+      PROF_MARK(0);
+      if (step == T) break;     // the final pseudo-step (state gradients) has no barrier
+      tc_fence_before();
+      cta_bar();
       tc_fence_after();
-      uint32_t raw[NACC][PC];
+      PROF_MARK(6);
+    }
+  } else {
+    int len[PC];
+    float carry[PC];  // LSTM: dc carry; GRU: direct dh carry (dh * z)
+    // running pointers at the CURRENT step's row; BPTT walks the time axis against the forward direction
+    const int64_t gstride = (int64_t)B * p.ndir * GH, ostride = (int64_t)B * p.ndir * H;
+    const int64_t gdelta = d == 0 ? -gstride : gstride, odelta = d == 0 ? -ostride : ostride;
+    const int t0 = d == 0 ? T - 1 : 0;
+    float* gcur[PC];
+    float* scur[PC];
+    const float* ocur[PC];
+    const float* dcur[PC];
+    int64_t cidx[PC];
+    uint32_t doff[PC];
+    bool valid[PC];
 #pragma unroll
-      for (int a = 0; a < NACC; ++a) tmem_ldn_nowait<PC>(tmem_mine + a * PN, raw[a]);
-      tmem_wait_ld();
+    for (int c = 0; c < PC; ++c) {
+      const int n = cg * PC + c;
+      valid[c] = b0 + n < B;
+      const int b = valid[c] ? b0 + n : 0;
+      len[c] = valid[c] ? (p.lengths ? (int)p.lengths[b] : T) : 0;
+      carry[c] = 0.f;
+      gcur[c] = p.gates + ((int64_t)b * p.ndir + d) * GH + k + t0 * gstride;
+      scur[c] = p.stash + ((int64_t)b * p.ndir + d) * H + k + t0 * ostride;
+      ocur[c] = p.out + (int64_t)b * p.ndir * H + (int64_t)d * H + k + t0 * ostride;
+      dcur[c] = p.dout ? p.dout + (int64_t)b * p.ndir * H + (int64_t)d * H + k + t0 * ostride : nullptr;
+      cidx[c] = ((int64_t)d * B + b) * H + k;
+      doff[c] = canon_off(n, k, PN);
+    }
+    // per-step operands, loaded one step ahead into a second register set (the two sets swap roles every
+    // step: loop unrolled by two): activated gates, stash, predecessor state, dout
+    struct StepIn {
+      float g[G][PC], s[PC], pv[PC], d[PC];
+    };
+    StepIn sa, sb;
+    // `rel` = rows ahead of the current step (0: this step, 1: the next one BPTT visits)
+    auto load_step = [&](StepIn& in, int t, int rel) {
+      // the state the forward step t started from sits one row AGAINST the BPTT walk: row t - 1 (d = 0)
+      const int tp = d == 0 ? t - 1 : t + 1;
+      const bool has_prev = tp >= 0 && tp < T;
 #pragma unroll
       for (int c = 0; c < PC; ++c) {
-        float acc = 0.f;
+        const bool act = t < len[c];
+        const float* gp = gcur[c] + rel * gdelta;
+        const float* sp = scur[c] + rel * odelta;
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) acc += __uint_as_float(raw[a][c]);
-        m[c] = acc;
+        for (int g = 0; g < G; ++g) in.g[g][c] = act ? gp[g * H] : 0.f;
+        in.s[c] = act ? *sp : 0.f;
+        in.d[c] = (act && dcur[c]) ? *(dcur[c] + rel * odelta) : 0.f;
+        float pv = 0.f;
+        if (act) {
+          if (G == 4) pv = has_prev ? *(sp + odelta) : (p.c0 ? p.c0[cidx[c]] : 0.f);
+          else pv = has_prev ? *(ocur[c] + (rel + 1) * odelta) : (p.h0 ? p.h0[cidx[c]] : 0.f);
+        }
+        in.pv[c] = pv;
       }
-    } else {
-#pragma unroll
-      for (int c = 0; c < PC; ++c) m[c] = 0.f;
-    }
-    if (final_only) {
+    };
+    load_step(sa, t0, 0);
+    // d(pre-activations) of a step go to HBM one iteration later, while the next step's MMAs run
+    float dg[G][PC], dst[PC];
+    auto store_prev = [&]() {
 #pragma unroll
       for (int c = 0; c < PC; ++c) {
         if (!valid[c]) continue;
-        if (G == 4) {
-          if (p.dh0) p.dh0[cidx[c]] = m[c];
-          if (p.dc0) p.dc0[cidx[c]] = carry[c];
-        } else if (p.dh0) {
-          p.dh0[cidx[c]] = m[c] + carry[c];
-        }
+        float* gp = gcur[c] - gdelta;
+#pragma unroll
+        for (int g = 0; g < G; ++g) gp[g * H] = dg[g][c];
+        if (G == 3) *(scur[c] - odelta) = dst[c];
       }
-      break;
-    }
+    };
+    uint32_t phase = 0;
+    bool pending = false;
+    // returns false after the final (state-gradient only) pseudo-step
+    auto one_step = [&](StepIn& cur, StepIn& nxt, int step) -> bool {
+      const bool final_only = step == T;
+      const int t = final_only ? (d == 0 ? -1 : T) : (d == 0 ? T - 1 - step : step);
+      const bool do_mma = step > 0;
+      // off the critical path: previous step's gradients -> HBM, next step's operands <- HBM
+      if (pending) {
+        store_prev();
+        pending = false;
+      }
+      if (step + 1 < T) load_step(nxt, d == 0 ? t - 1 : t + 1, 1);
+      PROF_MARK(1);
+      float m[PC];
+      if (do_mma) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        PROF_MARK(2);
+        uint32_t raw[NA][PC];
 #pragma unroll
-    for (int c = 0; c < PC; ++c) {
-      dst[c] = 0.f;
-      if (t >= len[c]) {
+        for (int a = 0; a < NA; ++a) tmem_ldn_nowait<PC>(tmem_mine + a * PN, raw[a]);
+        tmem_wait_ld();
 #pragma unroll
-        for (int g = 0; g < G; ++g) dg[g][c] = 0.f;
+        for (int c = 0; c < PC; ++c) {
+          float acc = __uint_as_float(raw[0][c]);
+#pragma unroll
+          for (int a = 1; a < NA; ++a) acc += __uint_as_float(raw[a][c]);
+          m[c] = acc;
+        }
+        PROF_MARK(3);
       } else {
-        const bool inject = d == 0 ? t == len[c] - 1 : t == 0;
-        float dh = cur.d[c];
-        if (G == 4) {
-          float dc_in;
-          if (inject) {
-            dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
-            dc_in = p.dc_final ? p.dc_final[cidx[c]] : 0.f;
-          } else {
-            dh += m[c];
-            dc_in = carry[c];
-          }
-          const float gi = cur.g[0][c], gf = cur.g[1][c], gg = cur.g[2][c], go = cur.g[G - 1][c];
-          const float tc = tanh_fast(cur.s[c]);
-          const float dc = dh * go * (1.f - tc * tc) + dc_in;
-          dg[0][c] = dc * gg * gi * (1.f - gi);
-          dg[1][c] = dc * cur.pv[c] * gf * (1.f - gf);
-          dg[2][c] = dc * gi * (1.f - gg * gg);
-          dg[G - 1][c] = dh * tc * go * (1.f - go);
-          carry[c] = dc * gf;
-        } else {
-          if (inject) dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
-          else dh += m[c] + carry[c];
-          const float gr = cur.g[0][c], gz = cur.g[1][c], gn = cur.g[2][c];
-          const float da_n = dh * (1.f - gz) * (1.f - gn * gn);
-          dg[0][c] = da_n * cur.s[c] * gr * (1.f - gr);
-          dg[1][c] = dh * (cur.pv[c] - gn) * gz * (1.f - gz);
-          dg[2][c] = da_n;
-          dst[c] = da_n * gr;
-          carry[c] = dh * gz;
-        }
-      }
-      // h-side gradients of this step = next step's B operand: dG[n][g*H + k]; consecutive gates are
-      // H/8 K-groups apart in the canonical tile.  The only stores the next MMA waits for.
-      if (valid[c]) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const float hv = (G == 3 && g == 2) ? dst[c] : dg[g][c];
-          *reinterpret_cast<__nv_bfloat16*>(sD + doff[c] + g * (H / 8) * (PN * 16)) = __float2bfloat16(hv);
+        for (int c = 0; c < PC; ++c) m[c] = 0.f;
+      }
+      if (final_only) {
+#pragma unroll
+        for (int c = 0; c < PC; ++c) {
+          if (!valid[c]) continue;
+          if (G == 4) {
+            if (p.dh0) p.dh0[cidx[c]] = m[c];
+            if (p.dc0) p.dc0[cidx[c]] = carry[c];
+          } else if (p.dh0) {
+            p.dh0[cidx[c]] = m[c] + carry[c];
+          }
+        }
+        return false;
+      }
+#pragma unroll
+      for (int c = 0; c < PC; ++c) {
+        dst[c] = 0.f;
+        if (t >= len[c]) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) dg[g][c] = 0.f;
+        } else {
+          const bool inject = d == 0 ? t == len[c] - 1 : t == 0;
+          float dh = cur.d[c];
+          if (G == 4) {
+            float dc_in;
+            if (inject) {
+              dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
+              dc_in = p.dc_final ? p.dc_final[cidx[c]] : 0.f;
+            } else {
+              dh += m[c];
+              dc_in = carry[c];
+            }
+            const float gi = cur.g[0][c], gf = cur.g[1][c], gg = cur.g[2][c], go = cur.g[G - 1][c];
+            const float tc = tanh_fast(cur.s[c]);
+            const float dc = dh * go * (1.f - tc * tc) + dc_in;
+            dg[0][c] = dc * gg * gi * (1.f - gi);
+            dg[1][c] = dc * cur.pv[c] * gf * (1.f - gf);
+            dg[2][c] = dc * gi * (1.f - gg * gg);
+            dg[G - 1][c] = dh * tc * go * (1.f - go);
+            carry[c] = dc * gf;
+          } else {
+            if (inject) dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
+            else dh += m[c] + carry[c];
+            const float gr = cur.g[0][c], gz = cur.g[1][c], gn = cur.g[2][c];
+            const float da_n = dh * (1.f - gz) * (1.f - gn * gn);
+            dg[0][c] = da_n * cur.s[c] * gr * (1.f - gr);
+            dg[1][c] = dh * (cur.pv[c] - gn) * gz * (1.f - gz);
+            dg[2][c] = da_n;
+            dst[c] = da_n * gr;
+            carry[c] = dh * gz;
+          }
+        }
+        // h-side gradients of this step = next step's B operand: dG[n][g*H + k]; consecutive gates are
+        // H/8 K-groups apart in the canonical tile.  The only stores the next MMA waits for.
+        if (valid[c]) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const float hv = (G == 3 && g == 2) ? dst[c] : dg[g][c];
+            *reinterpret_cast<__nv_bfloat16*>(sD + doff[c] + g * (H / 8) * (PN * 16)) = __float2bfloat16(hv);
+          }
         }
       }
+      PROF_MARK(4);
+      fence_async_smem();
+      tc_fence_before();
+      PROF_MARK(5);
+      cta_bar();
+      if (PROF) {
+        asm volatile("" ::"r"(*reinterpret_cast<volatile uint32_t*>(tmem_slot)) : "memory");
+      }
+      PROF_MARK(6);
+      pending = true;
+#pragma unroll
+      for (int c = 0; c < PC; ++c) {
+        gcur[c] += gdelta;
+        scur[c] += odelta;
+        ocur[c] += odelta;
+        if (dcur[c]) dcur[c] += odelta;
+      }
+      return true;
+    };
+    for (int step = 0; step < nsteps; step += 2) {
+      if (!one_step(sa, sb, step)) break;
+      if (step + 1 < nsteps && !one_step(sb, sa, step + 1)) break;
     }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    t_prev = t;
-    pending = true;
-    cur = nxt;
+    if (pending) store_prev();
   }
-  if (pending) store_step(t_prev);
+  if (PROF) pclk.publish(1);
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
@@ -518,15 +666,42 @@ static bool tc_shape_ok(int H, const float* w_hh) { return H == PH && ((uintptr_
 
 static int seqs_per_cta(int B, int ndir) { return ceil_div(B, 4) * ndir <= (sm_count() > 0 ? sm_count() : 148) ? 4 : 16; }
 
+// debug / tuning switches (slnlp_debug_persist_config): loop variant of the forward kernel and the
+// instrumented (per-phase %clock) instantiations.  Plain ints: set before launching, not per stream.
+static int g_persist_var = -1, g_persist_profile_on = 0;
+static int persist_var() {
+  if (g_persist_var < 0) {
+    const char* e = getenv("SLNLP_PERSIST_VAR");
+    g_persist_var = e ? atoi(e) : 0;
+  }
+  return g_persist_var;
+}
+
 template <int G, int PSEQ>
 static void launch_persist_fwd(const PersistFwd& p, cudaStream_t s) {
   const size_t sm = persist_fwd_smem(G);
-  launch_pdl(rnn_persistent_fwd_kernel<G, PSEQ>, dim3(dim3(ceil_div(p.B, PSEQ), p.ndir)), dim3(PTHREADS), sm, s, p);
+  const dim3 grid(ceil_div(p.B, PSEQ), p.ndir);
+  const bool fa1 = persist_var() & 1;     // one accumulator per gate tile instead of two partial ones
+  if (g_persist_profile_on) {
+    if (fa1) launch_pdl(rnn_persistent_fwd_kernel<G, PSEQ, 1, true>, grid, dim3(PBLOCK), sm, s, p);
+    else launch_pdl(rnn_persistent_fwd_kernel<G, PSEQ, 2, true>, grid, dim3(PBLOCK), sm, s, p);
+  } else {
+    if (fa1) launch_pdl(rnn_persistent_fwd_kernel<G, PSEQ, 1, false>, grid, dim3(PBLOCK), sm, s, p);
+    else launch_pdl(rnn_persistent_fwd_kernel<G, PSEQ, 2, false>, grid, dim3(PBLOCK), sm, s, p);
+  }
 }
 template <int G, int PSEQ>
 static void launch_persist_bwd(const PersistBwd& p, cudaStream_t s) {
   const size_t sm = persist_bwd_smem(G);
-  launch_pdl(rnn_persistent_bwd_kernel<G, PSEQ>, dim3(dim3(ceil_div(p.B, PSEQ), p.ndir)), dim3(PTHREADS), sm, s, p);
+  const dim3 grid(ceil_div(p.B, PSEQ), p.ndir);
+  const bool na2 = persist_var() & 2;     // two partial accumulators instead of four
+  if (g_persist_profile_on) {
+    if (na2) launch_pdl(rnn_persistent_bwd_kernel<G, PSEQ, 2, true>, grid, dim3(PBLOCK), sm, s, p);
+    else launch_pdl(rnn_persistent_bwd_kernel<G, PSEQ, 4, true>, grid, dim3(PBLOCK), sm, s, p);
+  } else {
+    if (na2) launch_pdl(rnn_persistent_bwd_kernel<G, PSEQ, 2, false>, grid, dim3(PBLOCK), sm, s, p);
+    else launch_pdl(rnn_persistent_bwd_kernel<G, PSEQ, 4, false>, grid, dim3(PBLOCK), sm, s, p);
+  }
 }
 
 int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh,
@@ -560,4 +735,19 @@ int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, floa
   return 0;
 }
 
+int persist_debug_config(int variant, int profile, uint32_t* out48) {
+  if (variant >= 0) g_persist_var = variant;
+  if (profile >= 0) g_persist_profile_on = profile;
+  if (out48) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out48, g_persist_prof, sizeof(uint32_t) * 2 * 3 * NPHASE);
+    if (e != cudaSuccess) return fail("persist profile read-back: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 }  // namespace slnlp
+
+extern "C" int slnlp_debug_persist_config(int variant, int profile, uint32_t* out48) {
+  return slnlp::persist_debug_config(variant, profile, out48);
+}

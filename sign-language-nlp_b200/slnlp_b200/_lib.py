@@ -25,8 +25,11 @@ SIGNATURES = {
     "slnlp_abi_version": [],
     "slnlp_last_error_string": [],
     "slnlp_device_sm_count": [],
+    "slnlp_stream_create": [],
+    "slnlp_stream_destroy": [P],
     "slnlp_launch_count": [],
     "slnlp_max_active_clusters": [I, I],
+    "slnlp_debug_persist_config": [I, I, P],
     "slnlp_embed_gather_fwd": [P, P, P, I, I, I, P, P, P, I, F, P, P],
     "slnlp_embed_gather_bwd": [P, P, P, I, I, I, P, P, P, I, F, L, P],
     "slnlp_gemm_f32": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],
@@ -64,7 +67,7 @@ SIGNATURES = {
     "slnlp_ln_bwd_blocks": [I],
     "slnlp_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, I, P],
 }
-_RESTYPES = {"slnlp_last_error_string": c_char_p, "slnlp_launch_count": c_int64,
+_RESTYPES = {"slnlp_last_error_string": c_char_p, "slnlp_launch_count": c_int64, "slnlp_stream_create": c_void_p,
              "slnlp_gemm_workspace_floats": c_int64}
 
 for _name, _args in SIGNATURES.items():

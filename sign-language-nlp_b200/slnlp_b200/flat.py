@@ -21,6 +21,60 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# torch.cuda.CUDAGraph registers every capture with the device's default RNG generator and unregisters
+# it in its destructor; neither side is synchronised, so several fits that capture / drop step graphs
+# from different threads of one process (grid.py fits_per_gpu) corrupt that registry ("The graph
+# should be registered to the state", abort).  Captures and graph releases therefore take this lock;
+# replays and ordinary launches of the other threads run freely meanwhile (thread-local capture mode).
+import threading as _threading
+CAPTURE_LOCK = _threading.RLock()
+
+
+_tls = _threading.local()
+
+
+def new_stream():
+    """A CUDA stream of its own (created through the C ABI, wrapped as an external stream).
+    ``torch.cuda.Stream()`` draws from a pool of 32 that is handed out round-robin, so two fits of one
+    process can end up sharing a stream - fatal when one of them is capturing on it."""
+    ptr = lib.slnlp_stream_create()
+    if not ptr:
+        check(1, "stream_create")
+    return torch.cuda.ExternalStream(ptr, device=torch.cuda.current_device())
+
+
+def thread_stream(role):
+    """Per-thread, per-device auxiliary streams ("capture", "warmup", "side", "main"), created once."""
+    key = (role, torch.cuda.current_device())
+    cache = _tls.__dict__.setdefault("streams", {})
+    if key not in cache:
+        cache[key] = new_stream()
+    return cache[key]
+
+
+@contextlib.contextmanager
+def capture_graph(graph):
+    """Capture the CUDA work issued inside into ``graph`` (a torch.cuda.CUDAGraph), under CAPTURE_LOCK.
+
+    ``torch.cuda.graph`` synchronises the whole device and empties the caching allocator before every
+    capture; a fit captures three or four graphs (full batch, tail batch, scoring) and several fits may
+    share the GPU, so this goes to capture_begin / capture_end directly on a private stream: no device-wide
+    sync (invalid anyway while another thread's stream is capturing), no cudaFree storm.
+    ``$SLNLP_CAPTURE_MODE`` = "thread_local" when several threads of the process capture (grid.py)."""
+    mode = _os.environ.get("SLNLP_CAPTURE_MODE", "global")
+    cur = torch.cuda.current_stream()
+    stream = thread_stream("capture")
+    stream.wait_stream(cur)
+    with CAPTURE_LOCK:
+        with torch.cuda.stream(stream):
+            graph.capture_begin(capture_error_mode=mode)
+            try:
+                yield
+            finally:
+                graph.capture_end()
+    cur.wait_stream(stream)
+
+
 def _align4(n):
     return (n + 3) & ~3
 
@@ -163,7 +217,7 @@ class FlatParamModule(nn.Module):
         """Split-K scratch of the GEMMs of this module: one buffer per stream the module launches on
         (the main stream and the weight-gradient side stream never share partials)."""
         side = getattr(self, "_side", None)
-        on_side = side is not None and torch.cuda.current_stream() == side
+        on_side = side is not None and torch.cuda.current_stream().cuda_stream == side.cuda_stream
         name = "_gemm_scratch_side" if on_side else "_gemm_scratch"
         ws = getattr(self, name, None)
         if ws is None or ws.device != self._flat.device:
@@ -177,7 +231,8 @@ class FlatParamModule(nn.Module):
     def _side_stream(self):
         side = getattr(self, "_side", None)
         if side is None or side.device != self._flat.device:
-            side = self._side = torch.cuda.Stream(device=self._flat.device)
+            with torch.cuda.device(self._flat.device):
+                side = self._side = thread_stream("side")
             self._gemm_scratch_side = None
         return side
 

@@ -56,10 +56,14 @@ def _fit_and_score(estimator, params, X, y, train, test, scorer, fit_subdir=None
     Xtr, ytr = _safe_indexing(X, train), _safe_indexing(y, train)
     Xte, yte = _safe_indexing(X, test), _safe_indexing(y, test)
     t0 = time.perf_counter()
-    est.fit(Xtr, ytr)
-    t1 = time.perf_counter()
-    score = float(scorer(est, Xte, yte))
-    t2 = time.perf_counter()
+    try:
+        est.fit(Xtr, ytr)
+        t1 = time.perf_counter()
+        score = float(scorer(est, Xte, yte))
+        t2 = time.perf_counter()
+    finally:
+        if hasattr(est, "release_graphs"):     # captured CUDA graphs go now, under the capture lock
+            est.release_graphs()
     return {"score": score, "fit_time": t1 - t0, "score_time": t2 - t1,
             "epochs": len(getattr(est, "history", [])), "n_train": len(train)}
 
@@ -69,7 +73,8 @@ def _stream_scope():
     import torch
     if not torch.cuda.is_available():
         return contextlib.nullcontext()
-    return torch.cuda.stream(torch.cuda.Stream())
+    from .flat import thread_stream     # a stream of this thread's own, not one from torch's shared pool
+    return torch.cuda.stream(thread_stream("main"))
 
 
 def _pack_env(fits_per_gpu):
@@ -395,6 +400,15 @@ class GridSearchFarm:
                 th.start()
             for th in threads:
                 th.join()
+        def leave(tag):
+            # the store lives in rank 0's process: rank 0 stays until every rank has read what it needs
+            # (a rank that returns or raises early would otherwise take the store down under the others)
+            store.add(f"{key}/{tag}", 1)
+            if rank == 0:
+                deadline = time.monotonic() + 120.0
+                while int(store.add(f"{key}/{tag}", 0)) < world and time.monotonic() < deadline:
+                    time.sleep(0.02)
+
         out = {}
         for t in order:                 # wait until the owning rank has published it (or a failure)
             while not store.check([f"{key}/res/{t}"]):
@@ -404,8 +418,10 @@ class GridSearchFarm:
                 time.sleep(0.05)
             res = pickle.loads(store.get(f"{key}/res/{t}"))
             if "error" in res:
+                leave("saw_failure")
                 raise RuntimeError(f"grid-search fit failed on rank {res['rank']} (error_score='raise'):\n{res['error']}")
             out[t] = res
+        leave("done")
         return out
 
     # ------------------------------------------------------------------ GridSearchCV result surface

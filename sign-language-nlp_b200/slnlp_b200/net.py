@@ -218,6 +218,16 @@ class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
         self.initialized_ = True
         return self
 
+    def release_graphs(self):
+        """Drop every captured step / scoring graph of this estimator (they are re-captured on demand).
+        The grid farm calls it when a fit is done: graph destruction must not race another worker
+        thread's capture (flat.CAPTURE_LOCK)."""
+        for step in list(getattr(self, "steps_", {}).values()) + list(getattr(self, "infer_steps_", {}).values()):
+            step.release()
+        if hasattr(self, "steps_"):
+            self.steps_ = {}
+        self.infer_steps_ = {}
+
     def optimizer_state_dict(self):
         """torch.optim.SGD.state_dict() layout on both routes (skorch Checkpoint's optimizer.pt)."""
         return self.opt_state_.state_dict(self.module_) if self.fused_ else self.optimizer_.state_dict()

@@ -30,7 +30,7 @@ MODE = {"lstm": 0, "gru": 1}
 GATES = {"lstm": 4, "gru": 3}
 
 
-from .flat import FlatParamModule, _Box, _align4, _stream  # noqa: F401
+from .flat import CAPTURE_LOCK, FlatParamModule, _Box, _align4, _stream, capture_graph, thread_stream  # noqa: F401
 
 
 class RnnEncDecB200(FlatParamModule):
@@ -614,22 +614,31 @@ class FusedTrainStep:
             return self.ws.loss
         if self.graph is None:
             # warm-up outside capture (lazy module/func attribute init), on a side stream
-            side = torch.cuda.Stream()
+            # (stream-level synchronisation only: a device-wide one is invalid while ANY stream of the
+            # device is capturing - another fit's thread under grid.py fits_per_gpu - and would also
+            # invalidate that capture)
+            side = thread_stream("warmup")
             side.wait_stream(torch.cuda.current_stream())
             saved = (self.m._flat.clone(), self.buf.clone(), self.m._rng_state().clone())
             with torch.cuda.stream(side):
                 self._step()
             torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
+            torch.cuda.current_stream().synchronize()
             self.m._flat.copy_(saved[0]); self.buf.copy_(saved[1]); self.m._rng_state().copy_(saved[2])
-            self.graph = torch.cuda.CUDAGraph()
             # "thread_local" when several fits share the process (grid.py fits_per_gpu): another thread's
             # allocations must not invalidate this capture
-            with torch.cuda.graph(self.graph, capture_error_mode=os.environ.get("SLNLP_CAPTURE_MODE", "global")):
+            graph = torch.cuda.CUDAGraph()
+            with capture_graph(graph):
                 self._step()
+            self.graph = graph
             self.m._flat.copy_(saved[0]); self.buf.copy_(saved[1]); self.m._rng_state().copy_(saved[2])
         self.graph.replay()
         return self.ws.loss
+
+    def release(self):
+        """Drop the captured graph (under the capture lock: see flat.CAPTURE_LOCK)."""
+        with CAPTURE_LOCK:
+            self.graph = None
 
     def step(self, X, y, lengths):
         self.load_batch(X, y, lengths)
@@ -670,17 +679,22 @@ class InferStep:
         if not self.use_graph:
             return m._run_forward(self.ws, self.X, self.lengths, self.y)
         if self.graph is None:
-            side = torch.cuda.Stream()
+            side = thread_stream("warmup")
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 m._run_forward(self.ws, self.X, self.lengths, self.y)
             torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, capture_error_mode=os.environ.get("SLNLP_CAPTURE_MODE", "global")):
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with capture_graph(graph):
                 m._run_forward(self.ws, self.X, self.lengths, self.y)
+            self.graph = graph
         self.graph.replay()
         return self.ws.logp
+
+    def release(self):
+        with CAPTURE_LOCK:
+            self.graph = None
 
     def step(self, X, y, lengths):
         self.load_batch(X, y, lengths)

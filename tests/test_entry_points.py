@@ -241,6 +241,23 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["e2e"]["value"] == line["value"] and line["cpu_baseline"]["value"] == line["value"]
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["infer"]["value"] > 0
+    # both arms print the SAME config object (a function of workload + command line only) ...
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert line["config"] == bench.common_config(bench.WORKLOADS["cfg1"], argparse.Namespace(dp=False, no_flush=False), 1)
+    # ... and the reference arm maps no product library (it times CPU code only)
+    code = ("import sys, runpy\n"
+            f"sys.argv = [{os.path.join(ROOT, 'bench.py')!r}, '--impl', 'reference', '--steps', '1', '--warmup', '1']\n"
+            f"runpy.run_path({os.path.join(ROOT, 'bench.py')!r}, run_name='__main__')\n"
+            "print('MAPPED', 'libslnlp' in open('/proc/self/maps').read(), any(m.startswith('slnlp_b200') for m in sys.modules))\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().splitlines()[-1] == "MAPPED False False"
 
 
 # ---------------------------------------------------------------- advisor findings, round 1
