@@ -7,7 +7,8 @@ For every forward variant (slnlp_debug_persist_config): (1) the un-instrumented 
 replay with CUDA events (us per dependent timestep), (2) the instrumented instantiation's %clock table,
 cycles per step averaged over the T steps, for three threads of CTA (0,0): the MMA issuer (thread 0),
 thread 160 (warp 5, column group 1) and thread 511.  Variant bits: 1 = one accumulator per gate tile in the
-forward kernel (instead of two partial ones), 2 = two partial accumulators in BPTT (instead of four)."""
+forward kernel (instead of two partial ones),
+$SLNLP_PERSIST_PSEQ = 1 | 2 | 4 | 16 forces the sequences per CTA (default: the smallest that fits one wave)."""
 import ctypes
 import os
 import sys
@@ -71,8 +72,8 @@ def table(which, buf):
 
 
 buf = (ctypes.c_uint32 * 48)()
-print(f"{'gru' if mode else 'lstm'} layer T {T} B {B} H {H}, both directions")
-for var in (0, 1, 2, 3):
+print(f"{'gru' if mode else 'lstm'} layer T {T} B {B} H {H}, both directions; sequences per CTA: {os.environ.get('SLNLP_PERSIST_PSEQ', 'auto')}")
+for var in (0, 1):
     L.check(L.lib.slnlp_debug_persist_config(var, 0, None))
     gates.copy_(gates0)
     us_f = timed(fwd)
@@ -86,6 +87,6 @@ for var in (0, 1, 2, 3):
     table(0, buf)
     bwd()
     L.check(L.lib.slnlp_debug_persist_config(-1, 0, buf))
-    if var in (0, 2):
+    if var == 0:
         print(" backward, instrumented:")
         table(1, buf)

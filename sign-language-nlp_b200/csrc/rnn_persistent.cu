@@ -36,8 +36,12 @@ constexpr int PN = 16;    // MMA N (the smallest N of an M = 128 instruction)
 // PSEQ (template): sequences a CTA actually owns; columns PSEQ..PN-1 of the B tile stay zero.  The per-step
 // gate math and stores scale with PSEQ, and at the reference's batch of 50 most SMs are idle, so small
 // batches run 4 sequences per CTA (26 CTAs at B = 50) and large ones 16 (fewer W_hh loads, fewer waves).
-constexpr int PTHREADS = 512;  // 16 epilogue warps: TMEM lane quadrant = warp % 4, column group = warp / 4
-constexpr int PBLOCK = PTHREADS + 32;   // + the MMA warp (warp 16)
+// epilogue threads = 128 x NCG (TMEM lane quadrant = warp % 4, column group = warp / 4), each owning PC batch
+// columns of one hidden unit: a CTA owns PSEQ = NCG x PC sequences.  The tensor-core part of a step costs the
+// same whatever PSEQ is (the MMA N is 16 at least), the epilogue scales with it, and at the reference's
+// batch of 50 most SMs are idle: the launcher takes the smallest PSEQ whose grid still fits the device in one
+// wave (B = 50: one sequence per CTA, 100 CTAs).  One more warp issues the MMAs.
+constexpr int NACC = 4;                 // BPTT: partial accumulators (independent MMA chains)
 constexpr int A_COL0 = 128;    // TMEM: accumulators in columns [0, 128), the resident W_hh operand from 128 on
 constexpr int TMEM_COLS = 512; // 64 + up to 256 operand columns -> the whole tensor memory of the SM
 
@@ -63,9 +67,9 @@ struct PhaseClock {
     acc[i] += now - last;
     last = now;
   }
-  __device__ __forceinline__ void publish(int which) {
+  __device__ __forceinline__ void publish(int which, int ethr) {
     const int tid = threadIdx.x;
-    const int slot = tid == PTHREADS ? 0 : tid == 160 ? 1 : tid == PTHREADS - 1 ? 2 : -1;
+    const int slot = tid == ethr ? 0 : tid == (ethr > 160 ? 160 : 32) ? 1 : tid == ethr - 1 ? 2 : -1;
     if (slot < 0 || blockIdx.x != 0 || blockIdx.y != 0) return;
 #pragma unroll
     for (int i = 0; i < NPHASE; ++i) g_persist_prof[which][slot][i] = acc[i];
@@ -75,7 +79,8 @@ struct PhaseClock {
 
 // CTA-wide barrier over the epilogue warps AND the MMA warp (reached from two code paths: bar.sync with an
 // explicit thread count instead of __syncthreads)
-__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PBLOCK) : "memory"); }
+template <int NTHREADS>
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
 struct PersistFwd {
   int T, B, ndir;
@@ -91,18 +96,22 @@ struct PersistFwd {
 };
 
 // FA: partial accumulators per gate tile (FA independent MMA chains, summed by the epilogue).
-template <int G, int PSEQ, int FA, bool PROF>
-__global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_fwd_kernel(PersistFwd p) {
+// (Issuing from four warps instead of one was measured: the issue sequence halves, 433 -> 196 cycles, but the
+// accumulators complete at the same time - the tensor pipe retires an M128 x N16 x K16 MMA every ~18 cycles,
+// ~27 when its B operand differs from the previous MMA's, so the k-major order below (four gate tiles per
+// h slice) is the fast one and a per-gate staged epilogue, which needs gate-major issue, loses.)
+template <int G, int NCG, int PC, int FA, bool PROF>
+__global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_fwd_kernel(PersistFwd p) {
+  constexpr int PSEQ = NCG * PC, ETHR = 128 * NCG, NTHR = ETHR + 32;
   pdl_launch_dependents();
-  constexpr int PC = PSEQ / 4;   // batch columns per thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int H = PH;
   uint8_t* sH = smem_raw;                       // [PN x 128] bf16, canonical (B operand)
   uint64_t* bar = reinterpret_cast<uint64_t*>(sH + PN * H * 2);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, warp_u = warp_uniform();
-  const bool mma_warp = warp_u == PTHREADS / 32;
+  const bool mma_warp = warp_u >= ETHR / 32;
   const int d = blockIdx.y, b0 = blockIdx.x * PSEQ;
   const int T = p.T, B = p.B;
   const int j = tid & (H - 1);   // hidden unit = TMEM lane
@@ -124,18 +133,21 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_fwd_kernel(PersistFw
   // bf16 = 64 packed 32-bit columns at column A_COL0 + 64 g.  Reading A from TMEM instead of
   // shared memory takes the 128 KB-per-step operand fetch off the 128 B/clk shared-memory port
   // (it bounded the step at ~1000 cycles).  Warp w fills lane quadrant w % 4 of gate w / 4.
-  if (!mma_warp && cg < G) {
-    const float* wrow = W + ((int64_t)cg * H + j) * H;
+  if (!mma_warp) {
 #pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-      uint32_t pk[16];
+    for (int g = cg; g < G; g += NCG) {
+      const float* wrow = W + ((int64_t)g * H + j) * H;
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        uint32_t pk[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(wrow + i * 32) + u);
-        pk[2 * u] = pack2_bf16(v.x, v.y);
-        pk[2 * u + 1] = pack2_bf16(v.z, v.w);
+        for (int u = 0; u < 8; ++u) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(wrow + i * 32) + u);
+          pk[2 * u] = pack2_bf16(v.x, v.y);
+          pk[2 * u + 1] = pack2_bf16(v.z, v.w);
+        }
+        tmem_st16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + A_COL0 + g * 64 + i * 16, pk);
       }
-      tmem_st16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + A_COL0 + cg * 64 + i * 16, pk);
     }
     tmem_wait_st();
   }
@@ -144,7 +156,7 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_fwd_kernel(PersistFw
 #pragma unroll
   for (int g = 0; g < G; ++g) bias[g] = mma_warp ? 0.f : bh[g * H + j];
   // the h tile rows PSEQ..PN-1 are never written: zero them once
-  for (int e = tid; e < PN * H / 8; e += PBLOCK) {
+  for (int e = tid; e < PN * H / 8; e += NTHR) {
     const int n = e % PN;   // canonical tile: 16-byte core rows, row index = (e % (PN)) within a K-group
     if (n >= PSEQ) reinterpret_cast<uint4*>(sH)[e] = make_uint4(0, 0, 0, 0);
   }
@@ -180,7 +192,7 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_fwd_kernel(PersistFw
       const bool do_mma = step > 0 || have_state0;
       if (do_mma && elect_one()) {
         // G gate tiles x (H/16) k-steps, A = W_hh from tensor memory, B = the h tile in shared memory;
-        // issued k-major so that consecutive MMAs accumulate into different gate tiles
+        // k-major: consecutive MMAs share the B slice and accumulate into different gate tiles
 #pragma unroll
         for (int kk = 0; kk < H / 16; ++kk)
 #pragma unroll
@@ -192,7 +204,7 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_fwd_kernel(PersistFw
       __syncwarp();
       PROF_MARK(0);   // MMA issue + commit
       tc_fence_before();
-      cta_bar();
+      cta_bar<NTHR>();
       tc_fence_after();
       PROF_MARK(6);   // waiting for the epilogue warps (h_t published)
     }
@@ -266,52 +278,63 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_fwd_kernel(PersistFw
         }
       }
       PROF_MARK(1);   // issue of the deferred stores and of the next step's loads
-      float acc[G][PC];
-      if (do_mma) {
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        tc_fence_after();
-        PROF_MARK(2);   // wait for the MMAs
-        uint32_t raw[G * FA][PC];
+      // accumulators of gate tile g (FA partial sums at columns (g*FA + q)*PN) -> a[]
+      auto read_gate = [&](int g, float (&a)[PC]) {
+        uint32_t raw[FA][PC];
 #pragma unroll
-        for (int g = 0; g < G * FA; ++g) tmem_ldn_nowait<PC>(tmem_mine + g * PN, raw[g]);
+        for (int q = 0; q < FA; ++q) tmem_ldn_nowait<PC>(tmem_mine + (g * FA + q) * PN, raw[q]);
         tmem_wait_ld();
 #pragma unroll
-        for (int g = 0; g < G; ++g)
+        for (int c = 0; c < PC; ++c) {
+          float v = __uint_as_float(raw[0][c]);
 #pragma unroll
-          for (int c = 0; c < PC; ++c) {
-            float a = __uint_as_float(raw[g * FA][c]);
+          for (int q = 1; q < FA; ++q) v += __uint_as_float(raw[q][c]);
+          a[c] = v;
+        }
+      };
+      // x + b_hh does not wait for the tensor core (sigmoid(v) = 0.5 tanh(0.5 v) + 0.5: the halving too)
+      float xb[G][PC];
 #pragma unroll
-            for (int q = 1; q < FA; ++q) a += __uint_as_float(raw[g * FA + q][c]);
-            acc[g][c] = a;
-          }
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int c = 0; c < PC; ++c) xb[g][c] = (G == 3 && g == 2) ? xg[g][c] : xg[g][c] + bias[g];
+      float acc[G][PC];
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int c = 0; c < PC; ++c) acc[g][c] = 0.f;
+      if (do_mma) {
+        mbar_wait(bar, phase);
+        tc_fence_after();
+        PROF_MARK(2);   // wait for the MMAs
+#pragma unroll
+        for (int g = 0; g < G; ++g) read_gate(g, acc[g]);
         PROF_MARK(3);   // tcgen05.ld of the accumulators
-      } else {
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-#pragma unroll
-          for (int c = 0; c < PC; ++c) acc[g][c] = 0.f;
       }
 #pragma unroll
       for (int c = 0; c < PC; ++c) {
         if (G == 4) {
-          const float gi = sigmoid_fast(xg[0][c] + acc[0][c] + bias[0]);
-          const float gf = sigmoid_fast(xg[1][c] + acc[1][c] + bias[1]);
-          const float gg = tanh_fast(xg[2][c] + acc[2][c] + bias[2]);
-          const float go = sigmoid_fast(xg[G - 1][c] + acc[G - 1][c] + bias[G - 1]);
+          const float gi = sigmoid_fast(xb[0][c] + acc[0][c]);
+          const float gf = sigmoid_fast(xb[1][c] + acc[1][c]);
+          const float gg = tanh_fast(xb[2][c] + acc[2][c]);
+          const float go = sigmoid_fast(xb[G - 1][c] + acc[G - 1][c]);
           const float cn = gf * creg[c] + gi * gg;
           hv[c] = go * tanh_fast(cn);
           sv[c] = cn;
           gout[0][c] = gi; gout[1][c] = gf; gout[2][c] = gg; gout[G - 1][c] = go;
         } else {
           const float hn = acc[2][c] + bias[2];
-          const float gr = sigmoid_fast(xg[0][c] + acc[0][c] + bias[0]);
-          const float gz = sigmoid_fast(xg[1][c] + acc[1][c] + bias[1]);
-          const float gn = tanh_fast(xg[2][c] + gr * hn);
+          const float gr = sigmoid_fast(xb[0][c] + acc[0][c]);
+          const float gz = sigmoid_fast(xb[1][c] + acc[1][c]);
+          const float gn = tanh_fast(xb[2][c] + gr * hn);
           hv[c] = (1.f - gz) * gn + gz * hreg[c];
           sv[c] = hn;
           gout[0][c] = gr; gout[1][c] = gz; gout[2][c] = gn;
         }
+      }
+      if (do_mma) phase ^= 1;
+#pragma unroll
+      for (int c = 0; c < PC; ++c) {
         // state update + next step's B tile: the only stores the next MMA waits for
         if (valid[c] && t < len[c]) {
           if (G == 4) creg[c] = sv[c];
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_fwd_kernel(PersistFw
       fence_async_smem();
       tc_fence_before();
       PROF_MARK(5);   // proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC)
-      cta_bar();
+      cta_bar<NTHR>();
       if (PROF) {     // BAR.SYNC defers its blocking to the next consumer of barrier-protected state: make one
         asm volatile("" ::"r"(*reinterpret_cast<volatile uint32_t*>(tmem_slot)) : "memory");
       }
@@ -362,7 +385,7 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_fwd_kernel(PersistFw
       }
     }
   }
-  if (PROF) pclk.publish(0);
+  if (PROF) pclk.publish(0, ETHR);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
@@ -385,11 +408,12 @@ struct PersistBwd {
   float* dc0;
 };
 
-// NA: partial accumulators of the single [128 x PN] output tile (NA independent MMA chains).
-template <int G, int PSEQ, int NA, bool PROF>
-__global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_bwd_kernel(PersistBwd p) {
+// NACC partial accumulators of the single [128 x PN] output tile (independent MMA chains).
+template <int G, int NCG, int PC, bool PROF>
+__global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_bwd_kernel(PersistBwd p) {
+  constexpr int NA = NACC;
+  constexpr int PSEQ = NCG * PC, ETHR = 128 * NCG, NTHR = ETHR + 32;
   pdl_launch_dependents();
-  constexpr int PC = PSEQ / 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int H = PH, GH = G * PH;
   uint8_t* sD = smem_raw;                        // B' = dG: [PN x GH] bf16, canonical
@@ -397,7 +421,7 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_bwd_kernel(PersistBw
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, warp_u = warp_uniform();
-  const bool mma_warp = warp_u == PTHREADS / 32;
+  const bool mma_warp = warp_u >= ETHR / 32;
   const int d = blockIdx.y, b0 = blockIdx.x * PSEQ;
   const int T = p.T, B = p.B;
   const int k = tid & (H - 1);  // hidden unit = TMEM lane = output row of W_hh^T
@@ -405,7 +429,7 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_bwd_kernel(PersistBw
 
   // ---- weights-only prologue, before griddepcontrol.wait (see the forward kernel)
   const float* W = p.w_hh + (int64_t)d * GH * H;
-  for (int e = tid; e < PN * GH / 8; e += PBLOCK) reinterpret_cast<uint4*>(sD)[e] = make_uint4(0, 0, 0, 0);
+  for (int e = tid; e < PN * GH / 8; e += NTHR) reinterpret_cast<uint4*>(sD)[e] = make_uint4(0, 0, 0, 0);
   if (tid == 0) mbar_init(bar, 1);
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   fence_async_smem();
@@ -415,12 +439,12 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_bwd_kernel(PersistBw
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_mine = tmem + ((uint32_t)((warp & 3) * 32) << 16) + cg * PC;
   // A' = W_hh^T -> tensor memory: lane = hidden unit k, K index = gate row j' (GH of them) = GH/2 packed
-  // columns from A_COL0.  Column group cg fills rows j' in [cg*GH/4, (cg+1)*GH/4): global reads are
+  // columns from A_COL0.  Column group cg fills rows j' in [cg*GH/NCG, (cg+1)*GH/NCG): global reads are
   // coalesced across the warp (consecutive k).
   if (!mma_warp) {
-    constexpr int JQ = GH / 4;   // 32 G gate rows -> 16 G packed columns = G stores of 16 columns
+    constexpr int JQ = GH / NCG;   // gate rows per column group -> JQ / 2 packed columns = JQ / 32 stores of 16
 #pragma unroll 1
-    for (int i = 0; i < G; ++i) {
+    for (int i = 0; i < JQ / 32; ++i) {
       uint32_t pk[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
@@ -458,7 +482,7 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_bwd_kernel(PersistBw
       PROF_MARK(0);
       if (step == T) break;     // the final pseudo-step (state gradients) has no barrier
       tc_fence_before();
-      cta_bar();
+      cta_bar<NTHR>();
       tc_fence_after();
       PROF_MARK(6);
     }
@@ -545,6 +569,40 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_bwd_kernel(PersistBw
       }
       if (step + 1 < T) load_step(nxt, d == 0 ? t - 1 : t + 1, 1);
       PROF_MARK(1);
+      // everything that does not depend on this step's W_hh^T dG product is computed while the MMAs run:
+      // dG is LINEAR in the incoming dh, so only a handful of multiplies remain after the wait
+      // (one column per thread - the small-batch shape; with four columns per thread the extra live
+      // registers would spill, so there the coefficients are formed after the wait as before)
+      constexpr bool PRE = PC == 1;
+      float k0[PC], k1[PC], k2[PC], k3[PC], a1[PC], dhb[PC], dcb[PC];
+      bool act[PC], inj[PC];
+      auto coeff = [&](int c) {
+        act[c] = t < len[c];
+        inj[c] = d == 0 ? t == len[c] - 1 : t == 0;
+        dhb[c] = cur.d[c] + ((inj[c] && p.dh_final && act[c]) ? p.dh_final[cidx[c]] : 0.f);
+        if (G == 4) {
+          const float gi = cur.g[0][c], gf = cur.g[1][c], gg = cur.g[2][c], go = cur.g[G - 1][c];
+          const float tc = tanh_fast(cur.s[c]);
+          a1[c] = go * (1.f - tc * tc);
+          k0[c] = gg * gi * (1.f - gi);
+          k1[c] = cur.pv[c] * gf * (1.f - gf);
+          k2[c] = gi * (1.f - gg * gg);
+          k3[c] = tc * go * (1.f - go);
+          dcb[c] = inj[c] ? ((p.dc_final && act[c]) ? p.dc_final[cidx[c]] : 0.f) : carry[c];
+        } else {
+          const float gr = cur.g[0][c], gz = cur.g[1][c], gn = cur.g[2][c];
+          a1[c] = (1.f - gz) * (1.f - gn * gn);
+          k0[c] = cur.s[c] * gr * (1.f - gr);
+          k1[c] = (cur.pv[c] - gn) * gz * (1.f - gz);
+          k2[c] = gr;
+          k3[c] = gz;
+          dcb[c] = inj[c] ? 0.f : carry[c];
+        }
+      };
+      if (PRE && !final_only) {
+#pragma unroll
+        for (int c = 0; c < PC; ++c) coeff(c);
+      }
       float m[PC];
       if (do_mma) {
         mbar_wait(bar, phase);
@@ -582,41 +640,27 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_bwd_kernel(PersistBw
       }
 #pragma unroll
       for (int c = 0; c < PC; ++c) {
+        if (!PRE) coeff(c);
         dst[c] = 0.f;
-        if (t >= len[c]) {
+        if (!act[c]) {
 #pragma unroll
           for (int g = 0; g < G; ++g) dg[g][c] = 0.f;
+        } else if (G == 4) {
+          const float dh = dhb[c] + (inj[c] ? 0.f : m[c]);
+          const float dc = dh * a1[c] + dcb[c];
+          dg[0][c] = dc * k0[c];
+          dg[1][c] = dc * k1[c];
+          dg[2][c] = dc * k2[c];
+          dg[G - 1][c] = dh * k3[c];
+          carry[c] = dc * cur.g[1][c];
         } else {
-          const bool inject = d == 0 ? t == len[c] - 1 : t == 0;
-          float dh = cur.d[c];
-          if (G == 4) {
-            float dc_in;
-            if (inject) {
-              dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
-              dc_in = p.dc_final ? p.dc_final[cidx[c]] : 0.f;
-            } else {
-              dh += m[c];
-              dc_in = carry[c];
-            }
-            const float gi = cur.g[0][c], gf = cur.g[1][c], gg = cur.g[2][c], go = cur.g[G - 1][c];
-            const float tc = tanh_fast(cur.s[c]);
-            const float dc = dh * go * (1.f - tc * tc) + dc_in;
-            dg[0][c] = dc * gg * gi * (1.f - gi);
-            dg[1][c] = dc * cur.pv[c] * gf * (1.f - gf);
-            dg[2][c] = dc * gi * (1.f - gg * gg);
-            dg[G - 1][c] = dh * tc * go * (1.f - go);
-            carry[c] = dc * gf;
-          } else {
-            if (inject) dh += p.dh_final ? p.dh_final[cidx[c]] : 0.f;
-            else dh += m[c] + carry[c];
-            const float gr = cur.g[0][c], gz = cur.g[1][c], gn = cur.g[2][c];
-            const float da_n = dh * (1.f - gz) * (1.f - gn * gn);
-            dg[0][c] = da_n * cur.s[c] * gr * (1.f - gr);
-            dg[1][c] = dh * (cur.pv[c] - gn) * gz * (1.f - gz);
-            dg[2][c] = da_n;
-            dst[c] = da_n * gr;
-            carry[c] = dh * gz;
-          }
+          const float dh = dhb[c] + (inj[c] ? 0.f : m[c] + dcb[c]);
+          const float da_n = dh * a1[c];
+          dg[0][c] = da_n * k0[c];
+          dg[1][c] = dh * k1[c];
+          dg[2][c] = da_n;
+          dst[c] = da_n * k2[c];
+          carry[c] = dh * k3[c];
         }
         // h-side gradients of this step = next step's B operand: dG[n][g*H + k]; consecutive gates are
         // H/8 K-groups apart in the canonical tile.  The only stores the next MMA waits for.
@@ -632,7 +676,7 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_bwd_kernel(PersistBw
       fence_async_smem();
       tc_fence_before();
       PROF_MARK(5);
-      cta_bar();
+      cta_bar<NTHR>();
       if (PROF) {
         asm volatile("" ::"r"(*reinterpret_cast<volatile uint32_t*>(tmem_slot)) : "memory");
       }
@@ -653,7 +697,7 @@ __global__ void __launch_bounds__(PBLOCK, 1) rnn_persistent_bwd_kernel(PersistBw
     }
     if (pending) store_prev();
   }
-  if (PROF) pclk.publish(1);
+  if (PROF) pclk.publish(1, ETHR);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
@@ -664,7 +708,20 @@ static size_t persist_bwd_smem(int G) { return (size_t)PN * G * PH * 2 + 64; }
 
 static bool tc_shape_ok(int H, const float* w_hh) { return H == PH && ((uintptr_t)w_hh & 15) == 0; }
 
-static int seqs_per_cta(int B, int ndir) { return ceil_div(B, 4) * ndir <= (sm_count() > 0 ? sm_count() : 148) ? 4 : 16; }
+// sequences per CTA: the smallest of 1 / 2 / 4 whose grid fits the device in one wave, else 16
+// ($SLNLP_PERSIST_PSEQ overrides)
+static int seqs_per_cta(int B, int ndir) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("SLNLP_PERSIST_PSEQ");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 16) return forced;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  for (int ps : {1, 2, 4})
+    if (ceil_div(B, ps) * ndir <= sms) return ps;
+  return 16;
+}
 
 // debug / tuning switches (slnlp_debug_persist_config): loop variant of the forward kernel and the
 // instrumented (per-phase %clock) instantiations.  Plain ints: set before launching, not per stream.
@@ -672,36 +729,43 @@ static int g_persist_var = -1, g_persist_profile_on = 0;
 static int persist_var() {
   if (g_persist_var < 0) {
     const char* e = getenv("SLNLP_PERSIST_VAR");
-    g_persist_var = e ? atoi(e) : 0;
+    g_persist_var = e ? atoi(e) : 1;
   }
   return g_persist_var;
 }
 
-template <int G, int PSEQ>
-static void launch_persist_fwd(const PersistFwd& p, cudaStream_t s) {
+template <int G, int NCG, int PC, int FA>
+static void launch_persist_fwd2(const PersistFwd& p, cudaStream_t s) {
   const size_t sm = persist_fwd_smem(G);
-  const dim3 grid(ceil_div(p.B, PSEQ), p.ndir);
-  const bool fa1 = persist_var() & 1;     // one accumulator per gate tile instead of two partial ones
-  if (g_persist_profile_on) {
-    if (fa1) launch_pdl(rnn_persistent_fwd_kernel<G, PSEQ, 1, true>, grid, dim3(PBLOCK), sm, s, p);
-    else launch_pdl(rnn_persistent_fwd_kernel<G, PSEQ, 2, true>, grid, dim3(PBLOCK), sm, s, p);
-  } else {
-    if (fa1) launch_pdl(rnn_persistent_fwd_kernel<G, PSEQ, 1, false>, grid, dim3(PBLOCK), sm, s, p);
-    else launch_pdl(rnn_persistent_fwd_kernel<G, PSEQ, 2, false>, grid, dim3(PBLOCK), sm, s, p);
-  }
+  const dim3 grid(ceil_div(p.B, NCG * PC), p.ndir), block(128 * NCG + 32);
+  if (g_persist_profile_on) launch_pdl(rnn_persistent_fwd_kernel<G, NCG, PC, FA, true>, grid, block, sm, s, p);
+  else launch_pdl(rnn_persistent_fwd_kernel<G, NCG, PC, FA, false>, grid, block, sm, s, p);
 }
-template <int G, int PSEQ>
-static void launch_persist_bwd(const PersistBwd& p, cudaStream_t s) {
+template <int G>
+static void launch_persist_fwd(const PersistFwd& p, cudaStream_t s) {
+  const bool fa1 = persist_var() & 1;       // one accumulator per gate tile instead of two partial ones
+  const int ps = seqs_per_cta(p.B, p.ndir);
+#define SLNLP_FWD(NCG, PC) do { if (fa1) launch_persist_fwd2<G, NCG, PC, 1>(p, s); else launch_persist_fwd2<G, NCG, PC, 2>(p, s); } while (0)
+  if (ps == 1) SLNLP_FWD(1, 1);
+  else if (ps == 2) SLNLP_FWD(2, 1);
+  else if (ps == 4) SLNLP_FWD(4, 1);
+  else SLNLP_FWD(4, 4);
+#undef SLNLP_FWD
+}
+template <int G, int NCG, int PC>
+static void launch_persist_bwd2(const PersistBwd& p, cudaStream_t s) {
   const size_t sm = persist_bwd_smem(G);
-  const dim3 grid(ceil_div(p.B, PSEQ), p.ndir);
-  const bool na2 = persist_var() & 2;     // two partial accumulators instead of four
-  if (g_persist_profile_on) {
-    if (na2) launch_pdl(rnn_persistent_bwd_kernel<G, PSEQ, 2, true>, grid, dim3(PBLOCK), sm, s, p);
-    else launch_pdl(rnn_persistent_bwd_kernel<G, PSEQ, 4, true>, grid, dim3(PBLOCK), sm, s, p);
-  } else {
-    if (na2) launch_pdl(rnn_persistent_bwd_kernel<G, PSEQ, 2, false>, grid, dim3(PBLOCK), sm, s, p);
-    else launch_pdl(rnn_persistent_bwd_kernel<G, PSEQ, 4, false>, grid, dim3(PBLOCK), sm, s, p);
-  }
+  const dim3 grid(ceil_div(p.B, NCG * PC), p.ndir), block(128 * NCG + 32);
+  if (g_persist_profile_on) launch_pdl(rnn_persistent_bwd_kernel<G, NCG, PC, true>, grid, block, sm, s, p);
+  else launch_pdl(rnn_persistent_bwd_kernel<G, NCG, PC, false>, grid, block, sm, s, p);
+}
+template <int G>
+static void launch_persist_bwd(const PersistBwd& p, cudaStream_t s) {
+  const int ps = seqs_per_cta(p.B, p.ndir);
+  if (ps == 1) launch_persist_bwd2<G, 1, 1>(p, s);
+  else if (ps == 2) launch_persist_bwd2<G, 2, 1>(p, s);
+  else if (ps == 4) launch_persist_bwd2<G, 4, 1>(p, s);
+  else launch_persist_bwd2<G, 4, 4>(p, s);
 }
 
 int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh,
@@ -709,12 +773,7 @@ int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, cons
                      float* out, float* stash, float* h_final, cudaStream_t s) {
   if (!tc_shape_ok(H, w_hh)) return -1;
   PersistFwd p{T, B, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final};
-  const bool small = seqs_per_cta(B, ndir) == 4;
-  if (mode == SLNLP_MODE_LSTM) {
-    if (small) launch_persist_fwd<4, 4>(p, s); else launch_persist_fwd<4, 16>(p, s);
-  } else {
-    if (small) launch_persist_fwd<3, 4>(p, s); else launch_persist_fwd<3, 16>(p, s);
-  }
+  if (mode == SLNLP_MODE_LSTM) launch_persist_fwd<4>(p, s); else launch_persist_fwd<3>(p, s);
   SLNLP_LAUNCH_OK("rnn_layer_fwd(tcgen05)");
   return 0;
 }
@@ -725,12 +784,7 @@ int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, floa
                      cudaStream_t s) {
   if (!tc_shape_ok(H, w_hh)) return -1;
   PersistBwd p{T, B, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0};
-  const bool small = seqs_per_cta(B, ndir) == 4;
-  if (mode == SLNLP_MODE_LSTM) {
-    if (small) launch_persist_bwd<4, 4>(p, s); else launch_persist_bwd<4, 16>(p, s);
-  } else {
-    if (small) launch_persist_bwd<3, 4>(p, s); else launch_persist_bwd<3, 16>(p, s);
-  }
+  if (mode == SLNLP_MODE_LSTM) launch_persist_bwd<4>(p, s); else launch_persist_bwd<3>(p, s);
   SLNLP_LAUNCH_OK("rnn_layer_bwd(tcgen05)");
   return 0;
 }
