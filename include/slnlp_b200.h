@@ -77,18 +77,11 @@ int slnlp_gemm_f32(int transA, int transB, int M, int N, int K,
                    const float* A, int lda, const float* B, int ldb,
                    float* C, int ldc, const float* bias, float beta,
                    float* workspace, int64_t workspace_floats, slnlp_stream_t stream);
-/* Same contraction on the 5th-gen tensor cores: A, B are read as fp32, rounded to bf16 on
- * the way into shared memory, multiplied by tcgen05.mma kind::f16 with fp32 accumulators
- * in TMEM.  The 2e-2 path of north_star.  Shapes the tile kernel does not cover (unaligned
- * k-contiguous operands, M < 64, N < 32, K < 32) are computed by slnlp_gemm_f32. */
-int slnlp_gemm_bf16(int transA, int transB, int M, int N, int K,
-                    const float* A, int lda, const float* B, int ldb,
-                    float* C, int ldc, const float* bias, float beta,
-                    float* workspace, int64_t workspace_floats, slnlp_stream_t stream);
-/* The TMA-fed variant (north_star: "x W_ih hoisted into one TMA-fed GEMM over all timesteps"):
+/* The same contraction on the 5th-gen tensor cores, TMA-fed (north_star: "x W_ih hoisted into one TMA-fed GEMM
+ * over all timesteps"):
  * operands stay fp32 in HBM and are consumed as TF32 by tcgen05.mma kind::tf32 from 128-byte
  * swizzled TMA tiles (4-stage mbarrier ring, warp-specialised producer / MMA / epilogue),
- * transposed operands as MN-major tiles.  Same contract as slnlp_gemm_bf16; needs 16-byte
+ * transposed operands as MN-major tiles.  Same contract as slnlp_gemm_f32 (shapes the tile kernel does not cover are computed by it); needs 16-byte
  * aligned A, B and lda, ldb multiples of 4, else it computes with slnlp_gemm_f32. */
 int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K,
                     const float* A, int lda, const float* B, int ldb,
@@ -126,6 +119,18 @@ int slnlp_rnn_layer_fwd(int mode, int precision, int T, int B, int H, int ndir,
                         float* gates, const float* w_hh, const float* b_hh,
                         const int64_t* lengths, const float* h0, const float* c0,
                         float* out, float* stash, float* h_final, slnlp_stream_t stream);
+/* ---- K8 fused: ONE decoder step of one layer (bkp:215-216; MAX_OUTPUT_LEN = 1, bkp:332) in one launch:
+ * gates = x W_ih^T + b_ih + h0 W_hh^T + b_hh, gate nonlinearities, cell update and - between layers - the
+ * inter-layer dropout of nn.LSTM / nn.GRU (bkp:190).  fp32 FMA, full-precision expf / tanhf (serves both
+ * precision paths).  x [B,D]; h0 / c0 [B,H] (LSTM: c0 may alias h0, bkp:278-279; GRU: c0 NULL);
+ * w_ih [G*H,D], w_hh [G*H,H], b_ih / b_hh [G*H].  Outputs: gates [B,G,H] = activated gates and
+ * stash [B,H] (LSTM c_1; GRU W_hn h0 + b_hn) - exactly what slnlp_rnn_layer_bwd(T = 1) consumes;
+ * h [B,H]; h_drop [B,H] = dropout(h, p_drop) with the mask slnlp_dropout(site) draws, or NULL. */
+int slnlp_dec_cell_fwd(int mode, int B, int H, int D, const float* x, const float* h0, const float* c0,
+                       const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                       float* gates, float* stash, float* h, float* h_drop, float p_drop,
+                       const uint64_t* rng, uint32_t site, slnlp_stream_t stream);
+
 /* BPTT of the same layer.  gates: in = activated gates, out = d(x-side pre-activations)
  * (zeros at frozen steps) ready for the hoisted dW_ih / dx GEMMs.  stash: GRU only,
  * out = d(W_hn h + b_hn).  dout [T,B,ndir*H] / dh_final / dc_final may be NULL.
@@ -196,7 +201,8 @@ int slnlp_logsoftmax_ce_fused(const float* logits, const int64_t* y, int64_t ign
 
 /* ---- K11/K12: GradientNormClipping -> clip_grad_norm_(max_norm, 2) (helper.py:227-229)
  * and torch.optim.SGD(momentum, nesterov=False) (config/*.yaml:39-42), over flat buffers.
- * partials: workspace of slnlp_sumsq_partials() floats; norm_out[0] = ||g||_2. */
+ * partials: ZERO-INITIALISED workspace of slnlp_sumsq_partials() floats (block partial sums + the ticket
+ * counter of the last-block reduction, which the kernel resets itself); norm_out[0] = ||g||_2.  One launch. */
 int slnlp_sumsq_partials(void);
 int slnlp_gradnorm(const float* g, int64_t n, float* partials, float* norm_out,
                    slnlp_stream_t stream);
@@ -206,6 +212,10 @@ int slnlp_gradnorm(const float* g, int64_t n, float* partials, float* norm_out,
 int slnlp_sgd_momentum_clip(float* p, const float* g, float* buf, int64_t n,
                             const float* hyper, const float* norm, float grad_scale,
                             slnlp_stream_t stream);
+/* the same update, and g <- 0 behind it: the gradient buffer is consumed and ready for the next step's
+ * accumulating weight-gradient GEMMs (the fused train step then needs no separate zero-fill launch) */
+int slnlp_sgd_momentum_clip_zero(float* p, float* g, float* buf, int64_t n, const float* hyper,
+                                 const float* norm, float grad_scale, slnlp_stream_t stream);
 
 /* ---- K13: nn.Transformer pieces (model/transformer.py:40-45,82-87; post-norm, ReLU, LayerNorm
  * eps 1e-5).  The projections are slnlp_gemm_*; the FFN activation is slnlp_relu_*.

@@ -36,7 +36,7 @@ for name, tA, tB, M, N, K in shapes:
     C = torch.zeros(M, N, device="cuda")
     bias = torch.randn(N, device="cuda")
     res = []
-    for fn in (L.lib.slnlp_gemm_tf32, L.lib.slnlp_gemm_bf16, L.lib.slnlp_gemm_f32):
+    for fn in (L.lib.slnlp_gemm_tf32, L.lib.slnlp_gemm_f32):
         call = lambda: L.check(fn(tA, tB, M, N, K, A.data_ptr(), A.shape[1], Bm.data_ptr(), Bm.shape[1], C.data_ptr(), N,
                                   bias.data_ptr(), 0.0, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
         for _ in range(3):

@@ -10,7 +10,7 @@ Bm = torch.randn((N, K) if tB else (K, N), device="cuda")
 C = torch.zeros(M, N, device="cuda")
 bias = torch.randn(N, device="cuda")
 ws = torch.empty(L.lib.slnlp_gemm_workspace_floats(), device="cuda")
-fn = L.lib.slnlp_gemm_bf16 if (len(sys.argv) > 6 and sys.argv[6] == "bf16") else L.lib.slnlp_gemm_tf32
+fn = L.lib.slnlp_gemm_f32 if (len(sys.argv) > 6 and sys.argv[6] == "f32") else L.lib.slnlp_gemm_tf32
 for _ in range(5):
     L.check(fn(tA, tB, M, N, K, A.data_ptr(), A.shape[1], Bm.data_ptr(), Bm.shape[1], C.data_ptr(), N,
                                   bias.data_ptr(), 0.0, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))

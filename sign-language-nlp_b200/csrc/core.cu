@@ -283,11 +283,16 @@ __global__ void __launch_bounds__(256) ce_grad_kernel(const float* __restrict__ 
 
 // ------------------------------------------------------------------ grad norm + clip + SGD
 constexpr int kSumsqBlocks = 1024;
+// One launch: every block leaves its partial sum, the LAST block to finish (ticket counter behind the
+// partials, reset for the next call) adds them in double and writes the norm.
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, int64_t n,
-                                                            float* __restrict__ partials) {
+                                                            float* __restrict__ partials, unsigned* __restrict__ ticket,
+                                                            float* __restrict__ norm_out) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float red[33];
+  __shared__ double redd[256];
+  __shared__ bool last;
   float s = 0.f;
   const int64_t n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -299,28 +304,31 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
   if (blockIdx.x == 0)
     for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s += g[i] * g[i];
   s = block_sum(s, red);
-  if (threadIdx.x == 0) partials[blockIdx.x] = s;
-}
-__global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partials, int np,
-                                                          float* __restrict__ norm_out) {
-  pdl_wait();
-  pdl_launch_dependents();
-  __shared__ double redd[256];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < np; i += blockDim.x) s += (double)partials[i];
-  redd[threadIdx.x] = s;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double t = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += (double)__ldcg(partials + i);
+  redd[threadIdx.x] = t;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) redd[threadIdx.x] += redd[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) norm_out[0] = (float)sqrt(redd[0]);
+  if (threadIdx.x == 0) {
+    norm_out[0] = (float)sqrt(redd[0]);
+    *ticket = 0u;
+  }
 }
-
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                   float* __restrict__ buf, int64_t n,
                                                   const float* __restrict__ hyper,
-                                                  const float* __restrict__ norm, float grad_scale) {
+                                                  const float* __restrict__ norm, float grad_scale, float* zero_g) {
   pdl_wait();
   pdl_launch_dependents();
   const float lr = hyper[0], mom = hyper[1], max_norm = hyper[2];
@@ -342,6 +350,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
     pv.x -= lr * bv.x; pv.y -= lr * bv.y; pv.z -= lr * bv.z; pv.w -= lr * bv.w;
     b4[i] = bv;
     p4[i] = pv;
+    if (zero_g) reinterpret_cast<float4*>(zero_g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // consumed: ready for the next step
   }
   if (blockIdx.x == 0)
     for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
@@ -349,6 +358,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
       const float bv = first ? gv : mom * buf[i] + gv;
       buf[i] = bv;
       p[i] -= lr * bv;
+      if (zero_g) zero_g[i] = 0.f;
     }
 }
 
@@ -709,29 +719,37 @@ int slnlp_logsoftmax_ce_fused(const float* logits, const int64_t* y, int64_t ign
   return 0;
 }
 
-int slnlp_sumsq_partials(void) { return kSumsqBlocks; }
+int slnlp_sumsq_partials(void) { return kSumsqBlocks + 4; }   // + the ticket counter (must start at 0)
 int slnlp_gradnorm(const float* g, int64_t n, float* partials, float* norm_out, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(g && partials && norm_out && n > 0, "gradnorm: bad arguments");
   SLNLP_CHECK_ARG((uintptr_t)g % 16 == 0, "gradnorm: g must be 16-byte aligned");
   int64_t want = (n / 4 + 255) / 256;
   int grid = (int)(want < 1 ? 1 : (want > kSumsqBlocks ? kSumsqBlocks : want));
-  launch_pdl(sumsq_partial_kernel, dim3(grid), dim3(256), 0, as_stream(stream), g, n, partials);
-  launch_pdl(sumsq_final_kernel, dim3(1), dim3(256), 0, as_stream(stream), partials, grid, norm_out);
-  note_launches(1);
+  launch_pdl(sumsq_partial_kernel, dim3(grid), dim3(256), 0, as_stream(stream), g, n, partials,
+             reinterpret_cast<unsigned*>(partials + kSumsqBlocks), norm_out);
   SLNLP_LAUNCH_OK("gradnorm");
   return 0;
 }
-int slnlp_sgd_momentum_clip(float* p, const float* g, float* buf, int64_t n, const float* hyper,
-                            const float* norm, float grad_scale, slnlp_stream_t stream) {
+static int sgd_launch(float* p, float* g, float* buf, int64_t n, const float* hyper, const float* norm,
+                      float grad_scale, bool zero_grad, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(p && g && buf && hyper && n > 0, "sgd_momentum_clip: bad arguments");
   SLNLP_CHECK_ARG(((uintptr_t)p | (uintptr_t)g | (uintptr_t)buf) % 16 == 0,
                   "sgd_momentum_clip: buffers must be 16-byte aligned");
   int64_t want = (n / 4 + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 8;
   int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-  launch_pdl(sgd_kernel, dim3(grid), dim3(256), 0, as_stream(stream), p, g, buf, n, hyper, norm, grad_scale);
+  launch_pdl(sgd_kernel, dim3(grid), dim3(256), 0, as_stream(stream), p, (const float*)g, buf, n, hyper, norm, grad_scale,
+             zero_grad ? g : (float*)nullptr);
   SLNLP_LAUNCH_OK("sgd_momentum_clip");
   return 0;
+}
+int slnlp_sgd_momentum_clip(float* p, const float* g, float* buf, int64_t n, const float* hyper,
+                            const float* norm, float grad_scale, slnlp_stream_t stream) {
+  return sgd_launch(p, const_cast<float*>(g), buf, n, hyper, norm, grad_scale, false, stream);
+}
+int slnlp_sgd_momentum_clip_zero(float* p, float* g, float* buf, int64_t n, const float* hyper,
+                                 const float* norm, float grad_scale, slnlp_stream_t stream) {
+  return sgd_launch(p, g, buf, n, hyper, norm, grad_scale, true, stream);
 }
 
 }  // extern "C"

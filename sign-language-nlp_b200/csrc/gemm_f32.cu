@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
-// host-side launcher shared with gemm_bf16.cu
+// host-side launcher shared with gemm_tma.cu
 void launch_splitk_reduce(const float* partial, int splits, int M, int N, float* C, int ldc, const float* bias,
                           float beta, cudaStream_t s) {
   const int64_t total = (int64_t)M * N;

@@ -425,6 +425,15 @@ int rnn_layer_bwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
                          const float* dout, const float* dh_final, const float* dc_final, float* dh0, float* dc0,
                          float* carry, cudaStream_t s);
 
+// persistent fp32-FMA path for H = 128 (rnn_persistent_f32.cu): W_hh resident in registers + shared memory,
+// one CTA per (sequence, direction); -1 = unsupported
+int rnn_layer_fwd_pf32(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh, const float* b_hh,
+                       const int64_t* lengths, const float* h0, const float* c0, float* out, float* stash,
+                       float* h_final, cudaStream_t s);
+int rnn_layer_bwd_pf32(int mode, int T, int B, int H, int ndir, float* gates, float* stash, const float* out,
+                       const float* w_hh, const int64_t* lengths, const float* h0, const float* c0, const float* dout,
+                       const float* dh_final, const float* dc_final, float* dh0, float* dc0, cudaStream_t s);
+
 }  // namespace slnlp
 
 using namespace slnlp;
@@ -446,6 +455,10 @@ extern "C" int slnlp_rnn_layer_fwd(int mode, int precision, int T, int B, int H,
     const int rc2 = rnn_layer_fwd_tcstep(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
     if (rc2 >= 0) return rc2;
     // unsupported shape for the tensor-core kernels: the general path below is still CUDA
+  }
+  if (precision == 0) {
+    const int rc = rnn_layer_fwd_pf32(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
+    if (rc >= 0) return rc;
   }
   StepFwd p{T, B, H, ndir, 0, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final};
   const bool big = B > 256;
@@ -479,6 +492,11 @@ extern "C" int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H,
     const int rc2 = rnn_layer_bwd_tcstep(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
                                          dc_final, dh0, dc0, carry, s);
     if (rc2 >= 0) return rc2;
+  }
+  if (precision == 0) {
+    const int rc = rnn_layer_bwd_pf32(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
+                                      dc_final, dh0, dc0, s);
+    if (rc >= 0) return rc;
   }
   StepBwd p{T, B, H, ndir, 0, 0, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0, carry};
   const bool big = B > 256;

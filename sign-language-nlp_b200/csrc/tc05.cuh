@@ -1,5 +1,5 @@
 // tcgen05 / TMEM / mbarrier PTX wrappers and UMMA descriptor helpers shared by the
-// tensor-core kernels (rnn_persistent.cu, gemm_bf16.cu).  Bit layouts follow
+// tensor-core kernels (rnn_persistent.cu, rnn_cluster.cu, rnn_step_tc.cu, gemm_tma.cu).  Bit layouts follow
 // cute::UMMA::SmemDescriptor / InstrDescriptor (CUTLASS mma_sm100_desc.hpp).
 #pragma once
 #include <cuda_bf16.h>

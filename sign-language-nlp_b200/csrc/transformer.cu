@@ -12,7 +12,7 @@
 //
 // fp32 FMA arithmetic: at the reference's shapes (S = tens of frames, head dim <= 256) the
 // attention is a few MFLOP per (sequence, head) and bound by reading Q/K/V once; the
-// projections around it are the GEMMs (gemm_bf16.cu / gemm_f32.cu).
+// projections around it are the GEMMs (gemm_tma.cu / gemm_f32.cu).
 #include "common.cuh"
 
 namespace slnlp {

@@ -34,11 +34,11 @@ SIGNATURES = {
     "slnlp_embed_gather_bwd": [P, P, P, I, I, I, P, P, P, I, F, L, P],
     "slnlp_gemm_f32": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],
     "slnlp_gemm_workspace_floats": [],
-    "slnlp_gemm_bf16": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],
     "slnlp_gemm_tf32": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],
     "slnlp_colsum_f32": [P, I, I, I, P, F, P],
     "slnlp_rnn_layer_fwd": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
     "slnlp_rnn_layer_bwd": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
+    "slnlp_dec_cell_fwd": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, F, P, U32, P],
     "slnlp_pad_fill": [P, P, I, I, I, F, P],
     "slnlp_concat_dirs": [P, P, I, I, I, I, P],
     "slnlp_tanh_fwd": [P, L, P],
@@ -59,6 +59,7 @@ SIGNATURES = {
     "slnlp_sumsq_partials": [],
     "slnlp_gradnorm": [P, L, P, P, P],
     "slnlp_sgd_momentum_clip": [P, P, P, L, P, P, F, P],
+    "slnlp_sgd_momentum_clip_zero": [P, P, P, L, P, P, F, P],
     "slnlp_mha_fwd": [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, P, L, F, P, U32, P],
     "slnlp_mha_bwd": [P, I, P, I, P, I, P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, L, F, P, U32, P],
     "slnlp_mha_tf32_fwd": [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, P, L, F, P, U32, P],

@@ -14,7 +14,7 @@ import torch.nn as nn
 from ._lib import check, lib
 
 import os as _os
-_TC_GEMM = lib.slnlp_gemm_bf16 if _os.environ.get("SLNLP_GEMM", "tf32") == "bf16" else lib.slnlp_gemm_tf32
+_TC_GEMM = lib.slnlp_gemm_tf32
 
 
 def _stream():
@@ -206,7 +206,7 @@ class FlatParamModule(nn.Module):
 
     # ------------------------------------------------------------------ kernels
     def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0, big=False):
-        # tensor-core path: the TMA-fed TF32 kernel (SLNLP_GEMM=bf16 selects the register-staged bf16 one)
+        # tensor-core path: the TMA-fed TF32 kernel
         # (`big` marks the [B*T]-row GEMMs; the tensor-core path takes the skinny ones too - the
         # library falls back to the fp32 kernel by itself for shapes a 128-row tile cannot cover)
         fn = _TC_GEMM if self.precision == "bf16" else lib.slnlp_gemm_f32
@@ -215,51 +215,56 @@ class FlatParamModule(nn.Module):
 
     def _gemm_ws(self):
         """Split-K scratch of the GEMMs of this module: one buffer per stream the module launches on
-        (the main stream and the weight-gradient side stream never share partials)."""
-        side = getattr(self, "_side", None)
-        on_side = side is not None and torch.cuda.current_stream().cuda_stream == side.cuda_stream
-        name = "_gemm_scratch_side" if on_side else "_gemm_scratch"
-        ws = getattr(self, name, None)
+        (the main stream and the weight-gradient side lanes never share partials)."""
+        key = torch.cuda.current_stream().cuda_stream
+        pool = self.__dict__.setdefault("_gemm_scratch", {})
+        if not isinstance(pool, dict):
+            pool = self.__dict__["_gemm_scratch"] = {}
+        ws = pool.get(key)
         if ws is None or ws.device != self._flat.device:
-            ws = torch.empty(lib.slnlp_gemm_workspace_floats(), device=self._flat.device)
-            setattr(self, name, ws)
+            ws = pool[key] = torch.empty(lib.slnlp_gemm_workspace_floats(), device=self._flat.device)
         return ws
 
-    # ---- weight-gradient side stream: dW / db kernels are not on the dependency chain of BPTT, so
-    # they run on a second stream (a parallel branch of the captured graph) next to the next layer's
-    # recurrent kernel, which occupies a fraction of the SMs at the reference's batch size
-    def _side_stream(self):
-        side = getattr(self, "_side", None)
-        if side is None or side.device != self._flat.device:
-            with torch.cuda.device(self._flat.device):
-                side = self._side = thread_stream("side")
-            self._gemm_scratch_side = None
+    # ---- weight-gradient side lanes: dW / db kernels are not on the dependency chain of BPTT, so
+    # they run on other streams (parallel branches of the captured graph) next to the next layer's
+    # recurrent kernel.  Several lanes: the weight-gradient products of one layer are independent of each
+    # other too, and each is a few CTAs of mostly fixed latency - side by side they cost one GEMM, in a
+    # row (the last layer's, with nothing left to hide behind) they cost four
+    N_LANES = 4
+
+    def _side_stream(self, lane=0):
+        with torch.cuda.device(self._flat.device):
+            side = thread_stream("side" if lane == 0 else f"side{lane}")
+        if lane == 0:
+            self._side = side
         return side
 
-    def _fork_side(self):
-        side = self._side_stream()
+    def _fork_side(self, lane=0):
+        side = self._side_stream(lane)
         ev = torch.cuda.Event()
         ev.record()
         side.wait_event(ev)
-        self._side_pending = True
+        self.__dict__.setdefault("_lanes_pending", set()).add(lane)
         return side
 
     @contextlib.contextmanager
-    def _side_branch(self):
-        """Kernels launched inside run on the side stream, ordered after everything issued so far.
-        Only while a CUDA graph is being captured (the fork / join are free graph edges there); an
-        eager step is bound by the host's launch rate and the event traffic would slow it down."""
+    def _side_branch(self, lane=0):
+        """Kernels launched inside run on side lane ``lane``, ordered after everything issued so far on
+        the current stream (and after that lane's earlier work).  Only while a CUDA graph is being
+        captured (the fork / join are free graph edges there); an eager step is bound by the host's
+        launch rate and the event traffic would slow it down."""
         if not torch.cuda.is_current_stream_capturing():
             yield
             return
-        with torch.cuda.stream(self._fork_side()):
+        with torch.cuda.stream(self._fork_side(lane % self.N_LANES)):
             yield
 
     def _join_side(self):
-        side = getattr(self, "_side", None)
-        if side is None or not getattr(self, "_side_pending", False):
+        pending = self.__dict__.get("_lanes_pending")
+        if not pending:
             return   # nothing forked since the last join (and, under graph capture, no branch to merge)
-        self._side_pending = False
-        ev = torch.cuda.Event()
-        ev.record(side)
-        torch.cuda.current_stream().wait_event(ev)
+        for lane in sorted(pending):
+            ev = torch.cuda.Event()
+            ev.record(self._side_stream(lane))
+            torch.cuda.current_stream().wait_event(ev)
+        pending.clear()

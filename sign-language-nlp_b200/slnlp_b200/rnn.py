@@ -167,12 +167,23 @@ class RnnEncDecB200(FlatParamModule):
         dec_prec = prec if os.environ.get("SLNLP_DEC_TC", "0") == "1" else 0
         check(lib.slnlp_dec_input_fwd(self._ptr("model.trg_embed.weight") + 4 * self.bos_idx * E,
                                       ws.ctx.data_ptr(), ws.dec_xin[0].data_ptr(), B, E, 2 * H, s), "dec_input")
+        fused_cell = os.environ.get("SLNLP_DEC_FUSED", "1") != "0" and dec_prec == 0
         for l in range(L):
             D = E + 2 * H if l == 0 else H
             pre = "model.decoder.rnn."
+            h0 = ws.hidden0[l].data_ptr()
+            if fused_cell:
+                # projection + recurrent product + cell + inter-layer dropout: one launch (dec_cell.cu)
+                to_drop = l < L - 1 and drop
+                check(lib.slnlp_dec_cell_fwd(mode, B, H, D, ws.dec_xin[l].data_ptr(), h0, h0 if mode == 0 else None,
+                                             self._ptr(f"{pre}weight_ih_l{l}"), self._ptr(f"{pre}weight_hh_l{l}"),
+                                             self._ptr(f"{pre}bias_ih_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
+                                             ws.dec_gates[l].data_ptr(), ws.dec_stash[l].data_ptr(), ws.dec_h[l].data_ptr(),
+                                             ws.dec_xin[l + 1].data_ptr() if to_drop else None, self.p_rnn,
+                                             rng if to_drop else None, 100 + l, s), "dec_cell_fwd")
+                continue
             self._gemm(0, 1, B, G * H, D, ws.dec_xin[l].data_ptr(), D, self._ptr(f"{pre}weight_ih_l{l}"), D,
                        ws.dec_gates[l].data_ptr(), G * H, self._ptr(f"{pre}bias_ih_l{l}"))
-            h0 = ws.hidden0[l].data_ptr()
             check(lib.slnlp_rnn_layer_fwd(mode, dec_prec, 1, B, H, 1, ws.dec_gates[l].data_ptr(),
                                           self._ptr(f"{pre}weight_hh_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
                                           None, h0, h0 if mode == 0 else None, ws.dec_h[l].data_ptr(),
@@ -307,10 +318,8 @@ class RnnEncDecB200(FlatParamModule):
                 check(lib.slnlp_embed_gather_bwd(gp("model.src_embed.weight"), Xp, ws.d_emb.data_ptr(), B, T, 1,
                                                  ws.f_off, ws.f_w_src, ws.f_rows_src, 1, 1.0, self.src_pad, s),
                       "embed_bwd")
-            # weight / bias gradients of this layer: off the chain, on the side stream
-            side = self._fork_side() if (self.overlap_dw and hook is None) else None
-            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-                self._encoder_weight_grads(ws, l, gp, _stream())
+            # weight / bias gradients of this layer: off the chain, on the side lanes
+            self._encoder_weight_grads(ws, l, gp, parallel=self.overlap_dw and hook is None)
             if hook is not None:  # this layer's range goes out while the layer below runs its BPTT
                 nxt = f"{pre}weight_ih_l{l + 1}" if l < L - 1 else "model.decoder.attention.key_layer.weight"
                 hook(gflat, off[f"{pre}weight_ih_l{l}"], off[nxt])
@@ -319,8 +328,9 @@ class RnnEncDecB200(FlatParamModule):
         if self.overlap_dw or self.overlap_small:
             self._join_side()
 
-    def _encoder_weight_grads(self, ws, l, gp, s):
-        """dW_ih, db_ih, dW_hh, db_hh of encoder layer l from its d(pre-activation) buffer."""
+    def _encoder_weight_grads(self, ws, l, gp, parallel=False):
+        """dW_ih, db_ih, dW_hh, db_hh of encoder layer l from its d(pre-activation) buffer: four
+        independent pieces, each on its own side lane when ``parallel`` (graph capture only)."""
         E, H, G = self.E, self.H, self.G
         B, T = ws.B, ws.T
         GH = G * H
@@ -329,30 +339,37 @@ class RnnEncDecB200(FlatParamModule):
         pre = "model.encoder.rnn."
         dg, st, out = ws.enc_gates[l].data_ptr(), ws.enc_stash[l].data_ptr(), ws.enc_out[l].data_ptr()
         xin = (ws.emb if l == 0 else ws.enc_xin[l]).data_ptr()
-        self._gemm(1, 0, 2 * GH, D, T * B, dg, 2 * GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0, big=True)
-        check(lib.slnlp_colsum_f32(dg, T * B, 2 * GH, 2 * GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
+        lane = (lambda i: self._side_branch(i)) if parallel else (lambda i: contextlib.nullcontext())
+        with lane(0):
+            self._gemm(1, 0, 2 * GH, D, T * B, dg, 2 * GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0, big=True)
+        with lane(3):
+            s = _stream()
+            check(lib.slnlp_colsum_f32(dg, T * B, 2 * GH, 2 * GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
+            if mode == 0:  # LSTM: d b_hh == d b_ih for both directions at once
+                check(lib.slnlp_axpy(gp(f"{pre}bias_hh_l{l}"), gp(f"{pre}bias_ih_l{l}"), 1.0, 2 * GH, s), "axpy")
+            else:
+                for d in range(2):
+                    gb = gp(f"{pre}bias_hh_l{l}") + 4 * d * GH
+                    check(lib.slnlp_colsum_f32(dg + 4 * d * GH, T * B, 2 * H, 2 * GH, gb, 1.0, s), "colsum")
+                    check(lib.slnlp_colsum_f32(st + 4 * d * H, T * B, H, 2 * H, gb + 4 * 2 * H, 1.0, s), "colsum")
         K = (T - 1) * B
         for d in range(2):
             # dW_hh[d] = sum_t dG_t^T h_{prev(t)}: a GEMM over rows shifted by one timestep
             a_row = B if d == 0 else 0
             b_row = 0 if d == 0 else B
             gw = gp(f"{pre}weight_hh_l{l}") + 4 * d * GH * H
-            gb = gp(f"{pre}bias_hh_l{l}") + 4 * d * GH
             hb = out + 4 * (b_row * 2 * H + d * H)
-            if mode == 0:
-                if K > 0:
+            if K <= 0:
+                continue
+            with lane(1 + d):
+                if mode == 0:
                     self._gemm(1, 0, GH, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,
                                gw, H, None, 1.0, big=True)
-                if d == 0:  # LSTM: d b_hh == d b_ih for both directions at once
-                    check(lib.slnlp_axpy(gb, gp(f"{pre}bias_ih_l{l}"), 1.0, 2 * GH, s), "axpy")
-            else:
-                if K > 0:
+                else:
                     self._gemm(1, 0, 2 * H, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,
                                gw, H, None, 1.0, big=True)
                     self._gemm(1, 0, H, H, K, st + 4 * (a_row * 2 * H + d * H), 2 * H, hb, 2 * H,
                                gw + 4 * 2 * H * H, H, None, 1.0, big=True)
-                check(lib.slnlp_colsum_f32(dg + 4 * d * GH, T * B, 2 * H, 2 * GH, gb, 1.0, s), "colsum")
-                check(lib.slnlp_colsum_f32(st + 4 * d * H, T * B, H, 2 * H, gb + 4 * 2 * H, 1.0, s), "colsum")
 
     # ------------------------------------------------------------------ public forward
     def _check_inputs(self, X, lengths):
@@ -556,6 +573,7 @@ class FusedTrainStep:
         # optimizer state may be shared by several steps of different batch shape (tail batches)
         self.state = state if state is not None else OptimState(module, lr, momentum, max_norm)
         self.gflat = module.flat_grads()
+        self._grads_clean = False                    # True once a step's SGD kernel has zeroed the gradient buffer
         self.grad_sync = grad_sync                   # callable(gflat, loss) for data parallel
         self.grad_scale = 1.0
         self.graph = None
@@ -577,7 +595,8 @@ class FusedTrainStep:
     def _step(self):
         m, ws = self.m, self.ws
         s = _stream()
-        self.gflat.zero_()
+        if not self._grads_clean:        # afterwards the SGD kernel leaves the consumed gradient buffer zeroed
+            self.gflat.zero_()
         if m.uses_rng:
             check(lib.slnlp_rng_advance(m._rng_state().data_ptr(), s), "rng")
         m._run_forward(ws, self.X, self.lengths, self.y)
@@ -598,8 +617,9 @@ class FusedTrainStep:
             self.grad_sync(self.gflat, ws.loss)
         n = m._numel
         check(lib.slnlp_gradnorm(self.gflat.data_ptr(), n, self.partials.data_ptr(), self.norm.data_ptr(), s), "gradnorm")
-        check(lib.slnlp_sgd_momentum_clip(m._flat.data_ptr(), self.gflat.data_ptr(), self.buf.data_ptr(), n,
-                                          self.hyper.data_ptr(), self.norm.data_ptr(), self.grad_scale, s), "sgd")
+        check(lib.slnlp_sgd_momentum_clip_zero(m._flat.data_ptr(), self.gflat.data_ptr(), self.buf.data_ptr(), n,
+                                               self.hyper.data_ptr(), self.norm.data_ptr(), self.grad_scale, s), "sgd")
+        self._grads_clean = True
 
     def load_batch(self, X, y, lengths):
         """Stage one batch into the graph's static input buffers (device or pinned host tensors)."""

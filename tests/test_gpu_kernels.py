@@ -502,31 +502,6 @@ def test_rnn_tcgen05_single_step_initial_state(mode, B, H):
 
 
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (3200, 1024, 128), (3200, 256, 1024), (1024, 256, 3200),
-                                   (512, 128, 3150), (200, 72, 136), (100, 128, 256)])
-def test_gemm_bf16_tcgen05(tA, tB, M, N, K):
-    """tcgen05 GEMM (bf16 operands, fp32 TMEM accumulate) vs fp64 on bf16-rounded inputs (tight) and vs
-    the exact product (the 2e-2 budget of the bf16 path)."""
-    from helpers import BF16_RTOL
-    L = _lib()
-    A = cuda(*((K, M) if tA else (M, K)), seed=51)
-    B = cuda(*((N, K) if tB else (K, N)), seed=52)
-    bias, C0 = cuda(N, seed=53), cuda(M, N, seed=54)
-    ws = torch.empty(L.lib.slnlp_gemm_workspace_floats(), device="cuda")
-    C = C0.clone()
-    L.check(L.lib.slnlp_gemm_bf16(tA, tB, M, N, K, A.data_ptr(), A.shape[1], B.data_ptr(), B.shape[1],
-                                  C.data_ptr(), N, bias.data_ptr(), 0.5, ws.data_ptr(), ws.numel(), S()))
-    opA, opB = (A.t() if tA else A), (B.t() if tB else B)
-    rounded = opA.bfloat16().double() @ opB.bfloat16().double() + bias.double() + 0.5 * C0.double()
-    exact = opA.double() @ opB.double() + bias.double() + 0.5 * C0.double()
-    # shapes outside the tile kernel's alignment rules (k-contiguous operand with K % 8 != 0) are
-    # computed by the fp32 kernel: those match the exact product instead of the bf16-rounded one
-    tile_path = (tA or K % 8 == 0) and (not tB or K % 8 == 0)
-    assert rel_err(C, rounded if tile_path else exact) < 1e-5   # exact up to fp32 accumulation order
-    assert rel_err(C, exact) < BF16_RTOL
-
-
-@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(128, 64, 32), (128, 64, 64), (3200, 1024, 128), (3200, 256, 1024), (1024, 256, 3200),
                                    (512, 128, 3150), (200, 72, 136), (100, 128, 256), (3200, 1536, 512), (64, 32, 4000),
                                    (50, 128, 1026), (50, 1026, 128), (50, 512, 384), (8, 64, 64)])
@@ -635,3 +610,59 @@ def test_rnn_layer_at_cfg4_shape_batch_4096_hidden_512(mode):
         assert rel_err(res[1][i], res[0][i]) < BF16_RTOL, what
     pad = (torch.arange(T).view(T, 1) >= lengths.view(1, B)).cuda()
     assert float(res[1][0][pad].abs().max()) == 0.0 and float(res[0][0][pad].abs().max()) == 0.0
+
+
+def test_sgd_zeroing_variant_leaves_the_gradient_buffer_clean():
+    L = _lib()
+    n = 4096 + 8
+    p, g, buf = cuda(n, seed=1), cuda(n, seed=2, scale=0.01), torch.zeros(n, device="cuda")
+    p2, g2, buf2 = p.clone(), g.clone(), buf.clone()
+    hyper = torch.tensor([0.1, 0.9, 0.5, 0.0], device="cuda")
+    partials, norm = torch.zeros(L.lib.slnlp_sumsq_partials(), device="cuda"), torch.zeros(1, device="cuda")
+    for _ in range(2):      # twice: the ticket counter of the one-launch norm resets itself
+        L.check(L.lib.slnlp_gradnorm(g.data_ptr(), n, partials.data_ptr(), norm.data_ptr(), S()))
+        assert abs(float(norm) - float(g.double().norm())) < 1e-5 * float(g.double().norm())
+    L.check(L.lib.slnlp_sgd_momentum_clip(p.data_ptr(), g.data_ptr(), buf.data_ptr(), n, hyper.data_ptr(), norm.data_ptr(), 1.0, S()))
+    L.check(L.lib.slnlp_sgd_momentum_clip_zero(p2.data_ptr(), g2.data_ptr(), buf2.data_ptr(), n, hyper.data_ptr(), norm.data_ptr(), 1.0, S()))
+    assert torch.equal(p, p2) and torch.equal(buf, buf2)
+    assert float(g2.abs().max()) == 0.0 and float(g.abs().max()) > 0.0
+
+
+@pytest.mark.parametrize("mode", ["lstm", "gru"])
+@pytest.mark.parametrize("B,H,D", [(50, 128, 384), (50, 128, 128), (6, 16, 48), (5, 20, 64), (3, 24, 37), (70, 256, 1024)])
+def test_fused_decoder_cell_forward(mode, B, H, D):
+    """slnlp_dec_cell_fwd (projection + recurrent product + cell + inter-layer dropout in one launch) against
+    the oracle's cell on the same inputs (1e-5), and its dropout output against slnlp_dropout's mask."""
+    from oracle import restatement as R
+    L = _lib()
+    G, md = (4, 0) if mode == "lstm" else (3, 1)
+    w, x, _ = _rnn_inputs(mode, 1, B, H, D, seed=11 + B, ragged=False)
+    g = torch.Generator().manual_seed(12)
+    h0 = torch.tanh(torch.randn(B, H, generator=g))
+    xp = x[:, 0] @ w["w_ih"][0].t() + w["b_ih"][0]
+    if mode == "lstm":
+        h_ref, c_ref = R.lstm_cell(xp, h0, h0, w["w_hh"][0], w["b_hh"][0])
+    else:
+        h_ref = R.gru_cell(xp, h0, w["w_hh"][0], w["b_hh"][0])
+    c = lambda t: t.cuda().contiguous()
+    xd, h0d = c(x[:, 0]), c(h0)
+    w_ih, w_hh, b_ih, b_hh = c(w["w_ih"][0]), c(w["w_hh"][0]), c(w["b_ih"][0]), c(w["b_hh"][0])
+    gates, stash = torch.empty(B, G, H, device="cuda"), torch.empty(B, H, device="cuda")
+    h, hd = torch.empty(B, H, device="cuda"), torch.empty(B, H, device="cuda")
+    rng = torch.tensor([1234, 7], dtype=torch.int64, device="cuda")
+    L.check(L.lib.slnlp_dec_cell_fwd(md, B, H, D, xd.data_ptr(), h0d.data_ptr(), h0d.data_ptr() if md == 0 else None,
+                                     w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), gates.data_ptr(),
+                                     stash.data_ptr(), h.data_ptr(), hd.data_ptr(), 0.3, rng.data_ptr(), 101, S()))
+    assert rel_err(h, h_ref) < 1e-5
+    if mode == "lstm":
+        assert rel_err(stash, c_ref) < 1e-5
+    # the same stash the unfused pair (projection GEMM + single-step layer kernel) leaves for BPTT
+    gates2 = (xd @ w_ih.t() + b_ih).view(1, B, 1, G, H).contiguous()
+    out2, stash2 = torch.empty(1, B, H, device="cuda"), torch.empty(1, B, 1, H, device="cuda")
+    L.check(L.lib.slnlp_rnn_layer_fwd(md, 0, 1, B, H, 1, gates2.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), None,
+                                      h0d.data_ptr(), h0d.data_ptr() if md == 0 else None, out2.data_ptr(),
+                                      stash2.data_ptr(), None, S()))
+    assert rel_err(gates, gates2.view(B, G, H)) < 1e-5 and rel_err(stash, stash2.view(B, H)) < 1e-5
+    want = torch.empty(B, H, device="cuda")
+    L.check(L.lib.slnlp_dropout(h.data_ptr(), want.data_ptr(), B * H, 0.3, rng.data_ptr(), 101, S()))
+    assert torch.equal(hd, want)

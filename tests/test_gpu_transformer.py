@@ -305,3 +305,47 @@ def test_transformer_dropout_train_and_eval():
     with torch.no_grad():
         c = m(X=X, y=y, lengths=lengths)
     assert rel_err(c, g["logp_eval"]) < FP32_RTOL
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_transformer_long_sequences_T512(precision):
+    """sequences far beyond the reference corpus' 64 frames (the positional table
+    holds 5000, positional_encoding.py:23).  S = 512 = eight 64-key tiles of the online-softmax attention
+    kernels, causal ENCODER mask + ragged key padding, against the torch.nn port: eval log-probs and two
+    training steps."""
+    import model as dropin
+    from oracle import port
+    from slnlp_b200.rnn import FusedTrainStep
+    from slnlp_b200.vocab import Vocab
+    B, T, Vs, Vt, E, F, L, heads = 6, 512, 300, 40, 128, 256, 2, 4
+    torch.manual_seed(1)
+    ref = port.build_port("transformer", Vs, Vt, E, F, L, dropout=0.0, num_heads=heads)
+    m = dropin.Transformer(src_vocab=Vocab(size=Vs), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E,
+                           hidden_size=F, num_layers=L, num_heads=heads, dropout=0.0, device=torch.device("cuda"),
+                           precision=precision)
+    m.load_state_dict(ref.state_dict())
+    m = m.to(torch.device("cuda"))
+    g = torch.Generator().manual_seed(5)
+    X = torch.randint(2, Vs, (B, T), generator=g)
+    lengths = torch.tensor([512, 511, 449, 130, 65, 7])
+    for b in range(B):
+        X[b, lengths[b]:] = 1
+    y = torch.randint(2, Vt, (B,), generator=g)
+    tol = FP32_RTOL if precision == "fp32" else BF16_RTOL
+    ref.eval()
+    with torch.no_grad():
+        want = ref(X=X, y=y, lengths=lengths)
+    m.eval()
+    with torch.no_grad():
+        got = m(X=X.cuda(), y=y.cuda(), lengths=lengths.cuda())
+    assert rel_err(got, want) < tol
+    if precision == "fp32":
+        assert torch.equal(got.argmax(1).cpu(), want.argmax(1))
+    m.train()
+    ref.train()
+    ts = FusedTrainStep(m, B, T, lr=0.01)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9)
+    for step in range(2):
+        want_loss = port.reference_train_step(ref, opt, X, y, lengths)
+        got_loss = ts.step(X.cuda(), y.cuda(), lengths.cuda())
+        assert abs(float(got_loss[0]) - float(want_loss)) < tol * abs(float(want_loss))
