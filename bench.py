@@ -718,7 +718,7 @@ def run_grid(env, args, w):
             "config": {k: g[k] for k in ("workload", "fits", "epochs_per_fit", "sequences", "batch", "train_steps_per_fit",
                                          "seq_len", "v_src", "v_tgt", "early_stopping", "parallelism", "fits_per_gpu")},
             "search_seconds": g["search_seconds"], "worker_busy_seconds": g["worker_busy_seconds"],
-            "best_params": g["best_params"], "best_score": g["best_score"]}
+            "best_params": g["best_params"], "best_score": g["best_score"], "mean_test_score": g["mean_test_score"]}
     print(json.dumps(line), flush=True)
 
 
@@ -778,7 +778,7 @@ def main():
         run_grid(env, args, w)
         return finish(env)
     if args.grid_fraction is None:
-        args.grid_fraction = 0.1
+        args.grid_fraction = 1.0        # the sub-record runs the FULL 162-candidate x 5-fold grid (810 fits)
     default_run = args.workload == "cfg1" and not args.dp and not args.batch and args.precision == "bf16"
     legs = args.legs if args.legs is not None else ("all" if default_run else "none")
     legs = set(ALL_LEGS) if legs == "all" else set() if legs == "none" else set(legs.split(","))

@@ -145,6 +145,11 @@ int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H, int ndir,
  * of x [T,B,W] are set to `value` (1.0 going forward, 0.0 before BPTT). */
 int slnlp_pad_fill(float* x, const int64_t* lengths, int T, int B, int W, float value,
                    slnlp_stream_t stream);
+/* out-of-place: dst = src with rows t >= lengths[b] set to `value`.  The encoder output then exists twice -
+ * zero-padded (what BPTT and dW_hh read) and pad-filled (what the key projection / attention read, bkp:121-123) -
+ * and nothing has to be un-filled on the backward critical path. */
+int slnlp_pad_fill_copy(const float* src, float* dst, const int64_t* lengths, int T, int B, int W, float value,
+                        slnlp_stream_t stream);
 /* concatenate_directions (bkp:155-159): [ndir,B,H] -> [B, ndir*H], and its inverse */
 int slnlp_concat_dirs(const float* h_final, float* enc_final, int B, int H, int ndir,
                       int inverse, slnlp_stream_t stream);

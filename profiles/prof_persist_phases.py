@@ -62,7 +62,7 @@ def timed(fn, reps=20):
 
 
 def table(which, buf):
-    print(f"  {'phase':24s} {'mma warp':>10s} {'t160':>8s} {'t511':>8s}   (cycles per step)")
+    print(f"  {'phase':24s} {'mma warp':>10s} {'epi A':>8s} {'epi B':>8s}   (cycles per step)")
     tot = [0.0, 0.0, 0.0]
     for ph in range(7):
         v = [buf[(which * 3 + th) * 8 + ph] / T for th in range(3)]

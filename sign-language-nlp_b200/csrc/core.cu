@@ -401,6 +401,26 @@ __global__ void __launch_bounds__(256) pad_fill_kernel(float* __restrict__ x,
   float* r = x + (int64_t)row * W;
   for (int e = threadIdx.x; e < W; e += blockDim.x) r[e] = value;
 }
+// out-of-place form: dst = src with the padded rows replaced by `value` (the BPTT keeps reading the
+// zero-padded original, so nothing has to be un-filled later)
+__global__ void __launch_bounds__(256) pad_fill_copy_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                            const int64_t* __restrict__ lengths, int T, int B, int W,
+                                                            float value) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x;  // t*B + b
+  const int t = row / B, b = row % B;
+  const bool pad = t >= lengths[b];
+  const float* s = src + (int64_t)row * W;
+  float* r = dst + (int64_t)row * W;
+  if ((W & 3) == 0 && ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0)) {
+    const float4 v4 = make_float4(value, value, value, value);
+    for (int e = threadIdx.x; e < W / 4; e += blockDim.x)
+      reinterpret_cast<float4*>(r)[e] = pad ? v4 : reinterpret_cast<const float4*>(s)[e];
+  } else {
+    for (int e = threadIdx.x; e < W; e += blockDim.x) r[e] = pad ? value : s[e];
+  }
+}
 __global__ void __launch_bounds__(256) concat_dirs_kernel(const float* __restrict__ src,
                                                           float* __restrict__ dst, int B, int H,
                                                           int ndir, int inverse) {
@@ -605,6 +625,14 @@ int slnlp_pad_fill(float* x, const int64_t* lengths, int T, int B, int W, float 
   SLNLP_CHECK_ARG(x && lengths && T > 0 && B > 0 && W > 0, "pad_fill: bad arguments");
   launch_pdl(pad_fill_kernel, dim3(T * B), dim3(128), 0, as_stream(stream), x, lengths, T, B, W, value);
   SLNLP_LAUNCH_OK("pad_fill");
+  return 0;
+}
+
+int slnlp_pad_fill_copy(const float* src, float* dst, const int64_t* lengths, int T, int B, int W, float value,
+                        slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(src && dst && src != dst && lengths && T > 0 && B > 0 && W > 0, "pad_fill_copy: bad arguments");
+  launch_pdl(pad_fill_copy_kernel, dim3(T * B), dim3(64), 0, as_stream(stream), src, dst, lengths, T, B, W, value);
+  SLNLP_LAUNCH_OK("pad_fill_copy");
   return 0;
 }
 

@@ -40,6 +40,7 @@ SIGNATURES = {
     "slnlp_rnn_layer_bwd": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "slnlp_dec_cell_fwd": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, F, P, U32, P],
     "slnlp_pad_fill": [P, P, I, I, I, F, P],
+    "slnlp_pad_fill_copy": [P, P, P, I, I, I, F, P],
     "slnlp_concat_dirs": [P, P, I, I, I, I, P],
     "slnlp_tanh_fwd": [P, L, P],
     "slnlp_tanh_bwd": [P, P, L, P],

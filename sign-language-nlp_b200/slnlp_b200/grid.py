@@ -44,10 +44,14 @@ def estimate_cost(params: Dict) -> float:
     return float(sum(H * ((E if l == 0 else 2 * H) + H) for l in range(L)))
 
 
-def _fit_and_score(estimator, params, X, y, train, test, scorer, fit_subdir=None):
-    """One (candidate, fold): clone -> set_params -> fit(train) -> scorer(test)."""
+def _fit_and_score(estimator, params, X, y, train, test, scorer, fit_subdir=None, seed=None):
+    """One (candidate, fold): clone -> set_params -> fit(train) -> scorer(test).  ``seed`` (derived from the
+    candidate and fold, not from scheduling) seeds the fit's weight initialisation and dropout stream, so a
+    fit's history does not depend on which worker ran it or on what ran beside it."""
     from sklearn.utils import _safe_indexing
     est = clone(estimator).set_params(**params)
+    if seed is not None:
+        est._fit_seed = int(seed)
     if fit_subdir is not None:      # per-fit checkpoint directory (the reference's fits clobber one dir)
         for item in (getattr(est, "callbacks", None) or []):
             cb = item[1] if isinstance(item, tuple) else item
@@ -98,9 +102,9 @@ def _worker_loop(gpu, task_q, result_q, payload_bytes, own_stream):
                 task = task_q.get()
                 if task is None:
                     break
-                tid, params, train, test, sub = task
+                tid, params, train, test, sub, seed = task
                 try:
-                    out = _fit_and_score(estimator, params, X, y, train, test, scorer, sub)
+                    out = _fit_and_score(estimator, params, X, y, train, test, scorer, sub, seed)
                     out["gpu"] = gpu
                     result_q.put((tid, out, None))
                 except Exception:            # error_score="raise": reported to the parent, which raises
@@ -125,7 +129,7 @@ def _worker_main(gpu, task_q, result_q, payload_bytes, fits_per_gpu=1):
 class GridSearchFarm:
     def __init__(self, estimator, param_grid, *, scoring=None, n_jobs=None, refit=True, cv=None, verbose=0,
                  pre_dispatch=None, error_score="raise", return_train_score=False, n_gpus=None, backend="auto",
-                 per_fit_checkpoint_dirs=True, resume_file=None, fits_per_gpu=None):
+                 per_fit_checkpoint_dirs=True, resume_file=None, fits_per_gpu=None, random_state=1):
         self.estimator, self.param_grid, self.scoring, self.n_jobs = estimator, param_grid, scoring, n_jobs
         self.refit, self.cv, self.verbose, self.pre_dispatch = refit, cv, verbose, pre_dispatch
         self.error_score, self.return_train_score = error_score, return_train_score
@@ -135,6 +139,9 @@ class GridSearchFarm:
         # the whole grid on any failure, helper.py:162, and has no resume - SURVEY.md section 5)
         self.resume_file = resume_file
         self.fits_per_gpu = fits_per_gpu
+        # every fit is seeded from (random_state, candidate, fold): the reference seeds the process once
+        # (main.py:21, seed 1) and its fits then draw from whatever the worker's RNG holds; None restores that
+        self.random_state = random_state
 
     # ------------------------------------------------------------------ scheduling
     def _tasks(self, X, y):
@@ -233,6 +240,12 @@ class GridSearchFarm:
     def _is_main(self):
         return int(os.environ.get("RANK", "0")) == 0 or self._resolve_backend() != "torchrun"
 
+    def _seed(self, ci, fi):
+        """Per-fit seed: a function of (random_state, candidate, fold) only."""
+        if self.random_state is None:
+            return None
+        return (int(self.random_state) * 1000003 + ci * 1009 + fi * 7919 + 12345) & 0x7FFFFFFF
+
     def _sub(self, ci, fi):
         return f"cand{ci:04d}_fold{fi}" if self.per_fit_checkpoint_dirs else None
 
@@ -251,7 +264,7 @@ class GridSearchFarm:
                    for _ in range(k)]
         for t in order:
             ci, fi = tasks[t]
-            task_q.put((t, cands[ci], folds[fi][0], folds[fi][1], self._sub(ci, fi)))
+            task_q.put((t, cands[ci], folds[fi][0], folds[fi][1], self._sub(ci, fi), self._seed(ci, fi)))
         for _ in threads:
             task_q.put(None)
         for th in threads:
@@ -298,7 +311,8 @@ class GridSearchFarm:
         out = {}
         for t in order:
             ci, fi = tasks[t]
-            out[t] = _fit_and_score(self.estimator, cands[ci], X, y, folds[fi][0], folds[fi][1], scorer, self._sub(ci, fi))
+            out[t] = _fit_and_score(self.estimator, cands[ci], X, y, folds[fi][0], folds[fi][1], scorer, self._sub(ci, fi),
+                                    self._seed(ci, fi))
             self._journal(t, out[t])
             if self.verbose:
                 print(f"[grid] {len(out)}/{len(tasks)} cand {ci} fold {fi}: score {out[t]['score']:.4f} "
@@ -316,7 +330,7 @@ class GridSearchFarm:
             p.start()
         for t in order:
             ci, fi = tasks[t]
-            task_q.put((t, cands[ci], folds[fi][0], folds[fi][1], self._sub(ci, fi)))
+            task_q.put((t, cands[ci], folds[fi][0], folds[fi][1], self._sub(ci, fi), self._seed(ci, fi)))
         for _ in range(len(procs) * k):      # one sentinel per worker thread
             task_q.put(None)
         out = {}
@@ -382,7 +396,8 @@ class GridSearchFarm:
                     t = order[k]
                     ci, fi = tasks[t]
                     try:
-                        res = _fit_and_score(est, cands[ci], X, y, folds[fi][0], folds[fi][1], scorer, self._sub(ci, fi))
+                        res = _fit_and_score(est, cands[ci], X, y, folds[fi][0], folds[fi][1], scorer, self._sub(ci, fi),
+                                             self._seed(ci, fi))
                     except Exception:
                         failed.set()
                         store.set(f"{key}/res/{t}", pickle.dumps({"error": traceback.format_exc(), "rank": rank}))

@@ -32,6 +32,10 @@ from .flat import _stream
 from .rnn import FusedTrainStep, InferStep, OptimState
 
 
+import threading as _threading
+_INIT_LOCK = _threading.Lock()
+
+
 class History(list):
     """skorch History subset: ``h[-1]['valid_loss']``, ``h[-1, 'valid_loss']``, ``h[:, 'train_loss']``."""
 
@@ -157,7 +161,22 @@ class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
         mkw = dict(self._prefixed("module"))
         mkw.setdefault("precision", self.precision)
         mkw["device"] = dev
-        self.module_ = mod_cls(**mkw).to(dev)
+        fit_seed = getattr(self, "_fit_seed", None)
+        if fit_seed is None:
+            self.module_ = mod_cls(**mkw).to(dev)
+        else:
+            # a seeded fit (grid farm): the process-global torch generator is shared by every worker thread,
+            # so the seeded construction is one critical section and leaves the generator as it found it
+            with _INIT_LOCK:
+                gen = torch.default_generator        # the CPU generator only: CUDA generators stay untouched
+                state = gen.get_state()
+                gen.manual_seed(fit_seed)
+                mkw.setdefault("seed", fit_seed)
+                try:
+                    module = mod_cls(**mkw)
+                finally:
+                    gen.set_state(state)
+            self.module_ = module.to(dev)
         self.V_ = self.module_.V_tgt
         self.classes_ = np.arange(self.V_) if self.classes is None else np.asarray(self.classes)
         # criterion / optimizer: the reference's configuration runs fused; anything else through autograd

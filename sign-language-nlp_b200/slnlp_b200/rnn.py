@@ -147,8 +147,11 @@ class RnnEncDecB200(FlatParamModule):
                                         ws.enc_out[l].numel(), self.p_rnn, rng, l, s), "dropout")
             check(lib.slnlp_concat_dirs(ws.enc_hfin[l].data_ptr(), ws.enc_final[l].data_ptr(), B, H, 2, 0, s),
                   "concat_dirs")
-        enc_out = ws.enc_out[L - 1]
-        check(lib.slnlp_pad_fill(enc_out.data_ptr(), lp, T, B, 2 * H, float(self.src_pad), s), "pad_fill")
+        # pad_packed_sequence(padding_value=<pad>) (bkp:121-123): a pad-FILLED copy for the key projection and
+        # the attention; BPTT and dW_hh keep reading the zero-padded original (no un-fill on the way back)
+        enc_out = ws.enc_filled
+        check(lib.slnlp_pad_fill_copy(ws.enc_out[L - 1].data_ptr(), enc_out.data_ptr(), lp, T, B, 2 * H,
+                                      float(self.src_pad), s), "pad_fill")
         # bridge (bkp:268-280)
         self._gemm(0, 1, L * B, H, 2 * H, ws.enc_final.data_ptr(), 2 * H, self._ptr("model.decoder.bridge.weight"),
                    2 * H, ws.hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.bias"))
@@ -263,7 +266,7 @@ class RnnEncDecB200(FlatParamModule):
             drow = ws.scratch_row.data_ptr()  # padding_idx row gets no gradient
         check(lib.slnlp_dec_input_bwd(ws.d_decx.data_ptr(), drow, ws.d_ctx.data_ptr(), B, E, 2 * H, s), "dec_input_bwd")
         # attention
-        enc_out = ws.enc_out[L - 1]
+        enc_out = ws.enc_filled
         att = "model.decoder.attention."
         check(lib.slnlp_attn_step_bwd(ws.d_ctx.data_ptr(), ws.q.data_ptr(), ws.pk.data_ptr(),
                                       self._ptr(att + "energy_layer.weight"), enc_out.data_ptr(),
@@ -286,13 +289,12 @@ class RnnEncDecB200(FlatParamModule):
                        gp("model.decoder.bridge.weight"), 2 * H, None, 1.0)
             check(lib.slnlp_colsum_f32(ws.d_hidden0.data_ptr(), L * B, H, H, gp("model.decoder.bridge.bias"), 1.0, ss),
                   "colsum")
-        # the key-layer gradient reads enc_out with its 1.0 pad fill, which the next kernel removes:
-        # it stays on the main stream
-        self._gemm(1, 0, H, 2 * H, T * B, ws.d_pk.data_ptr(), H, enc_out.data_ptr(), 2 * H,
-                   gp(att + "key_layer.weight"), 2 * H, None, 1.0, big=True)
-        # encoder BPTT, top down.  Padded rows of enc_out go back to 0 first (the 1.0
-        # fill of pad_packed_sequence is a constant and must not enter dW_hh).
-        check(lib.slnlp_pad_fill(enc_out.data_ptr(), lp, T, B, 2 * H, 0.0, s), "pad_unfill")
+        # the key-layer gradient reads the pad-filled copy: a leaf like the other weight gradients
+        with (self._side_branch(1) if (self.overlap_small and hook is None) else contextlib.nullcontext()):
+            self._gemm(1, 0, H, 2 * H, T * B, ws.d_pk.data_ptr(), H, enc_out.data_ptr(), 2 * H,
+                       gp(att + "key_layer.weight"), 2 * H, None, 1.0, big=True)
+        # encoder BPTT, top down, on the zero-padded encoder output (the 1.0 fill of pad_packed_sequence is a
+        # constant and must not enter dW_hh)
         if hook is not None:      # attention + decoder + bridge, and target embedding + generator, are final
             hook(gflat, off["model.decoder.attention.key_layer.weight"], off["model.src_embed.weight"])
             hook(gflat, off["model.trg_embed.weight"], numel)
@@ -434,6 +436,7 @@ class _Workspace:
         self.enc_gates = [f(T, B, 2, G, H) for _ in range(L)]
         self.enc_stash = [f(T, B, 2, H) for _ in range(L)]
         self.enc_out = [f(T, B, 2 * H) for _ in range(L)]
+        self.enc_filled = f(T, B, 2 * H)
         self.enc_xin = [None] + [f(T, B, 2 * H) if drop else self.enc_out[l - 1] for l in range(1, L)]
         self.enc_hfin = [f(2, B, H) for _ in range(L)]
         self.enc_final = f(L, B, 2 * H)

@@ -151,3 +151,24 @@ def test_main_run_end_to_end(tmp_path):
     assert go["n_fits"] == 4 and go["best_params"]["lr"] in (0.1, 0.01) and go["fits_per_hour"] > 0
     prof = json.load(open(os.path.join(wd, "test_profile.json")))
     assert prof["kernel_launches"] > 0
+
+
+def test_packed_grid_fits_reproduce_the_one_at_a_time_search():
+    """fits_per_gpu = 3 (worker threads on private streams, one captured step graph each, fits seeded from
+    (candidate, fold)) against the same search one fit at a time, fp32 path with dropout: per-candidate scores agree
+    (up to the order of atomic adds in the embedding / bias gradients), twice in a row."""
+    import helper as h
+    from slnlp_b200.data import SeqDataset
+    from slnlp_b200.grid import GridSearchFarm
+    ds = SeqDataset.synthetic(n_seq=150, T=12, v_src=40, v_tgt=6, ragged=True, seed=4)
+    grid = {"lr": [0.1, 0.01], "module__hidden_size": [16, 32], "module__num_layers": [1, 2], "module__dropout": [0.2]}
+    scoring = h.build_scoring("neg_log_loss", ds.labels(), allow_multiple=False)
+    y = ds.y().to_array()
+    runs = []
+    for k in (1, 3, 3):
+        gs = GridSearchFarm(_net(ds, "lstm", epochs=2), grid, cv=3, scoring=scoring, refit=False, backend="inline",
+                            fits_per_gpu=k).fit(ds.X(), y)
+        assert gs.n_fits_ == 24
+        runs.append(gs.cv_results_["mean_test_score"])
+    assert np.abs(runs[1] - runs[0]).max() < 1e-5 and np.abs(runs[2] - runs[1]).max() < 1e-5
+    assert len(set(np.round(runs[0], 6))) > 4            # the candidates really differ
