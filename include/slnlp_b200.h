@@ -141,6 +141,37 @@ int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H, int ndir,
                         const float* h0, const float* c0,
                         const float* dout, const float* dh_final, const float* dc_final,
                         float* dh0, float* dc0, float* carry, slnlp_stream_t stream);
+
+/* Extras of the persistent recurrent kernels (H = 128, T > 1, no initial state; ask
+ * slnlp_rnn_extras_supported first - the other kernel families reject them), each of which removes
+ * launches from the train step's critical path:
+ *   hfinal_cat   h_final (fwd) and dh_final / dc_final (bwd) are laid out [B, ndir*H], i.e. already as
+ *                concatenate_directions (bkp:155-159) / the bridge input wants them: no concat kernel;
+ *   out_drop     fwd: also write dropout(out, p_drop) - the next layer's input under nn.LSTM / nn.GRU's
+ *                inter-layer dropout (bkp:100) - with the mask slnlp_dropout(site) draws; NULL = off;
+ *   dout_dropped bwd: dout is the gradient of that DROPPED output: the forward's mask (p_drop, rng, site)
+ *                is applied while it is read, instead of a separate dropout pass over the gradient. */
+typedef struct slnlp_rnn_extras {
+  int hfinal_cat;
+  float* out_drop;
+  float p_drop;
+  const uint64_t* rng;
+  uint32_t site;
+  int dout_dropped;
+} slnlp_rnn_extras;
+int slnlp_rnn_extras_supported(int precision, int T, int B, int H, int ndir);
+int slnlp_rnn_layer_fwd_ex(int mode, int precision, int T, int B, int H, int ndir,
+                           float* gates, const float* w_hh, const float* b_hh,
+                           const int64_t* lengths, const float* h0, const float* c0,
+                           float* out, float* stash, float* h_final, const slnlp_rnn_extras* extras,
+                           slnlp_stream_t stream);
+int slnlp_rnn_layer_bwd_ex(int mode, int precision, int T, int B, int H, int ndir,
+                           float* gates, float* stash, const float* out,
+                           const float* w_hh, const int64_t* lengths,
+                           const float* h0, const float* c0,
+                           const float* dout, const float* dh_final, const float* dc_final,
+                           float* dh0, float* dc0, float* carry, const slnlp_rnn_extras* extras,
+                           slnlp_stream_t stream);
 /* pad_packed_sequence(padding_value) on the top layer (bkp:120-123): rows t >= len
  * of x [T,B,W] are set to `value` (1.0 going forward, 0.0 before BPTT). */
 int slnlp_pad_fill(float* x, const int64_t* lengths, int T, int B, int W, float value,

@@ -233,7 +233,13 @@ extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, cons
   SLNLP_CHECK_ARG(grid.y <= 65535, "gemm_tf32: M too large");
   const int tiles = grid.x * grid.y;
   int splits = 1;
-  if (workspace && tiles < sm_count() && K >= 512) {
+  // split-K pays when the tile grid leaves most SMs idle.  A gradient accumulation (C += A B) adds its slices
+  // in place (no second launch), so it splits whenever the grid is below one wave; every other case needs
+  // partials in HBM and a reduce LAUNCH - measured on the dX GEMMs of the LSTM ([3200 x 1024] x [1024 x 256 | 128],
+  // 100 / 50 tiles): 2 / 5 splits + the reduce cost 15 / 10 us on the backward critical path where the unsplit
+  // GEMM takes ~6 - so those split only below a quarter wave.
+  const bool accumulates = beta == 1.f && !bias;
+  if (workspace && K >= 512 && tiles < (accumulates ? sm_count() : sm_count() / 4)) {
     splits = (2 * sm_count()) / tiles;
     if (splits > K / 128) splits = K / 128;
     while (splits > 1 && (int64_t)splits * M * N > workspace_floats) --splits;

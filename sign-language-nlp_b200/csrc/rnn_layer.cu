@@ -10,6 +10,7 @@
 //
 // This is the shape-general path (any H, B); the W_hh-resident persistent
 // tcgen05 kernel in rnn_persistent.cu takes over for the shapes it supports.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace slnlp {
@@ -401,11 +402,11 @@ static int launch_bwd(const StepBwd& p, cudaStream_t s) {
 // persistent tcgen05 path (rnn_persistent.cu); returns -1 when the shape is not supported
 int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh,
                      const float* b_hh, const int64_t* lengths, const float* h0, const float* c0,
-                     float* out, float* stash, float* h_final, cudaStream_t s);
+                     float* out, float* stash, float* h_final, const slnlp_rnn_extras* ex, cudaStream_t s);
 int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, float* stash, const float* out,
                      const float* w_hh, const int64_t* lengths, const float* h0, const float* c0,
                      const float* dout, const float* dh_final, const float* dc_final, float* dh0, float* dc0,
-                     cudaStream_t s);
+                     const slnlp_rnn_extras* ex, cudaStream_t s);
 
 // cluster-persistent path, W_hh slices resident in the TMEM of a thread-block cluster, H = 256 / 512
 // (rnn_cluster.cu); -1 = unsupported
@@ -429,27 +430,61 @@ int rnn_layer_bwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
 // one CTA per (sequence, direction); -1 = unsupported
 int rnn_layer_fwd_pf32(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh, const float* b_hh,
                        const int64_t* lengths, const float* h0, const float* c0, float* out, float* stash,
-                       float* h_final, cudaStream_t s);
+                       float* h_final, const slnlp_rnn_extras* ex, cudaStream_t s);
 int rnn_layer_bwd_pf32(int mode, int T, int B, int H, int ndir, float* gates, float* stash, const float* out,
                        const float* w_hh, const int64_t* lengths, const float* h0, const float* c0, const float* dout,
-                       const float* dh_final, const float* dc_final, float* dh0, float* dc0, cudaStream_t s);
+                       const float* dh_final, const float* dc_final, float* dh0, float* dc0,
+                       const slnlp_rnn_extras* ex, cudaStream_t s);
 
 }  // namespace slnlp
 
 using namespace slnlp;
 
+// the families that implement slnlp_rnn_extras (h_final in the concatenated layout, fused inter-layer dropout)
+static bool extras_family(int precision, int T, int H, const float* w_hh) {
+  return T > 1 && H == 128 && (((uintptr_t)w_hh & 15) == 0) && (precision == 1 || precision == 0);
+}
+
+extern "C" int slnlp_rnn_extras_supported(int precision, int T, int B, int H, int ndir) {
+  (void)B; (void)ndir;
+  if (precision == 0) {
+    const char* e = getenv("SLNLP_PERSIST_F32");
+    if (e && e[0] == '0') return 0;
+  }
+  return (T > 1 && H == 128) ? 1 : 0;
+}
+
+extern "C" int slnlp_rnn_layer_fwd_ex(int mode, int precision, int T, int B, int H, int ndir, float* gates,
+                                      const float* w_hh, const float* b_hh, const int64_t* lengths,
+                                      const float* h0, const float* c0, float* out, float* stash,
+                                      float* h_final, const slnlp_rnn_extras* ex, slnlp_stream_t stream);
+
 extern "C" int slnlp_rnn_layer_fwd(int mode, int precision, int T, int B, int H, int ndir, float* gates,
                                    const float* w_hh, const float* b_hh, const int64_t* lengths,
                                    const float* h0, const float* c0, float* out, float* stash,
                                    float* h_final, slnlp_stream_t stream) {
+  return slnlp_rnn_layer_fwd_ex(mode, precision, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final,
+                                nullptr, stream);
+}
+
+extern "C" int slnlp_rnn_layer_fwd_ex(int mode, int precision, int T, int B, int H, int ndir, float* gates,
+                                      const float* w_hh, const float* b_hh, const int64_t* lengths,
+                                      const float* h0, const float* c0, float* out, float* stash,
+                                      float* h_final, const slnlp_rnn_extras* ex, slnlp_stream_t stream) {
+  const bool wants = ex && (ex->hfinal_cat || ex->out_drop);
+  SLNLP_CHECK_ARG(!wants || (extras_family(precision, T, H, w_hh) && !h0 && !c0),
+                  "rnn_layer_fwd_ex: extras need the persistent kernels (H = 128, T > 1, no initial state); "
+                  "ask slnlp_rnn_extras_supported first");
+  SLNLP_CHECK_ARG(!ex || !ex->out_drop || (ex->rng && ex->p_drop >= 0.f && ex->p_drop < 1.f), "rnn_layer_fwd_ex: bad dropout arguments");
   SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM || mode == SLNLP_MODE_GRU, "rnn_layer_fwd: bad mode %d", mode);
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_fwd: bad shape");
   SLNLP_CHECK_ARG(gates && w_hh && b_hh && out && stash, "rnn_layer_fwd: null pointer");
   cudaStream_t s = as_stream(stream);
   if (precision == 1) {
     // a single step (the decoder cell) is not worth staging W_hh into tensor memory: per-step kernel
-    const int rc = T > 1 ? rnn_layer_fwd_tc(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s) : -1;
+    const int rc = T > 1 ? rnn_layer_fwd_tc(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, ex, s) : -1;
     if (rc >= 0) return rc;
+    SLNLP_CHECK_ARG(!wants, "rnn_layer_fwd_ex: extras requested but the persistent kernel rejected the shape");
     const int rc1 = T <= 1 ? -1 : rnn_layer_fwd_cluster(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
     if (rc1 >= 0) return rc1;
     const int rc2 = rnn_layer_fwd_tcstep(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
@@ -457,8 +492,9 @@ extern "C" int slnlp_rnn_layer_fwd(int mode, int precision, int T, int B, int H,
     // unsupported shape for the tensor-core kernels: the general path below is still CUDA
   }
   if (precision == 0) {
-    const int rc = rnn_layer_fwd_pf32(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, s);
+    const int rc = rnn_layer_fwd_pf32(mode, T, B, H, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final, ex, s);
     if (rc >= 0) return rc;
+    SLNLP_CHECK_ARG(!wants, "rnn_layer_fwd_ex: extras requested but the persistent fp32 kernel is off or rejected the shape");
   }
   StepFwd p{T, B, H, ndir, 0, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final};
   const bool big = B > 256;
@@ -472,11 +508,32 @@ extern "C" int slnlp_rnn_layer_fwd(int mode, int precision, int T, int B, int H,
   return 0;
 }
 
+extern "C" int slnlp_rnn_layer_bwd_ex(int mode, int precision, int T, int B, int H, int ndir, float* gates,
+                                      float* stash, const float* out, const float* w_hh,
+                                      const int64_t* lengths, const float* h0, const float* c0,
+                                      const float* dout, const float* dh_final, const float* dc_final,
+                                      float* dh0, float* dc0, float* carry, const slnlp_rnn_extras* ex,
+                                      slnlp_stream_t stream);
+
 extern "C" int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H, int ndir, float* gates,
                                    float* stash, const float* out, const float* w_hh,
                                    const int64_t* lengths, const float* h0, const float* c0,
                                    const float* dout, const float* dh_final, const float* dc_final,
                                    float* dh0, float* dc0, float* carry, slnlp_stream_t stream) {
+  return slnlp_rnn_layer_bwd_ex(mode, precision, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
+                                dc_final, dh0, dc0, carry, nullptr, stream);
+}
+
+extern "C" int slnlp_rnn_layer_bwd_ex(int mode, int precision, int T, int B, int H, int ndir, float* gates,
+                                      float* stash, const float* out, const float* w_hh,
+                                      const int64_t* lengths, const float* h0, const float* c0,
+                                      const float* dout, const float* dh_final, const float* dc_final,
+                                      float* dh0, float* dc0, float* carry, const slnlp_rnn_extras* ex,
+                                      slnlp_stream_t stream) {
+  const bool wants = ex && (ex->hfinal_cat || (ex->dout_dropped && ex->p_drop > 0.f));
+  SLNLP_CHECK_ARG(!wants || (extras_family(precision, T, H, w_hh) && !h0 && !c0 && !dh0 && !dc0),
+                  "rnn_layer_bwd_ex: extras need the persistent kernels (H = 128, T > 1, no initial state)");
+  SLNLP_CHECK_ARG(!ex || !ex->dout_dropped || ex->p_drop <= 0.f || ex->rng, "rnn_layer_bwd_ex: dropout replay needs rng");
   SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM || mode == SLNLP_MODE_GRU, "rnn_layer_bwd: bad mode %d", mode);
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_bwd: bad shape");
   SLNLP_CHECK_ARG(gates && stash && out && w_hh && carry, "rnn_layer_bwd: null pointer");
@@ -484,8 +541,9 @@ extern "C" int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H,
   cudaStream_t s = as_stream(stream);
   if (precision == 1) {
     const int rc = T > 1 ? rnn_layer_bwd_tc(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
-                                            dc_final, dh0, dc0, s) : -1;
+                                            dc_final, dh0, dc0, ex, s) : -1;
     if (rc >= 0) return rc;
+    SLNLP_CHECK_ARG(!wants, "rnn_layer_bwd_ex: extras requested but the persistent kernel rejected the shape");
     const int rc1 = T <= 1 ? -1 : rnn_layer_bwd_cluster(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
                                           dc_final, dh0, dc0, s);
     if (rc1 >= 0) return rc1;
@@ -495,8 +553,9 @@ extern "C" int slnlp_rnn_layer_bwd(int mode, int precision, int T, int B, int H,
   }
   if (precision == 0) {
     const int rc = rnn_layer_bwd_pf32(mode, T, B, H, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final,
-                                      dc_final, dh0, dc0, s);
+                                      dc_final, dh0, dc0, ex, s);
     if (rc >= 0) return rc;
+    SLNLP_CHECK_ARG(!wants, "rnn_layer_bwd_ex: extras requested but the persistent fp32 kernel is off or rejected the shape");
   }
   StepBwd p{T, B, H, ndir, 0, 0, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0, carry};
   const bool big = B > 256;

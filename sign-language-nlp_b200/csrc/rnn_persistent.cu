@@ -93,7 +93,21 @@ struct PersistFwd {
   float* out;            // [T,B,ndir*H]
   float* stash;          // [T,B,ndir,H]
   float* h_final;
+  int64_t hf_d, hf_b;    // h_final strides: direction, batch ([ndir,B,H]: B*H, H; concatenated [B,ndir*H]: H, ndir*H)
+  float* out_drop;       // dropout(out) for the next layer's input, or null
+  float p_drop;
+  const uint64_t* rng;   // {seed, step} of the module's Philox stream
+  uint32_t site;
 };
+
+// the keep / scale factor slnlp_dropout(site) applies to element e of a tensor: Philox block e / 4, lane e % 4
+__device__ __forceinline__ float dropout_factor(uint64_t seed, uint64_t step, uint32_t site, int64_t e, float p) {
+  float u[4];
+  philox_uniform4(seed, step, site, (uint64_t)(e >> 2), u);
+  const int l = (int)(e & 3);
+  const float uu = l == 0 ? u[0] : l == 1 ? u[1] : l == 2 ? u[2] : u[3];
+  return uu < 1.f - p ? 1.f / (1.f - p) : 0.f;
+}
 
 // FA: partial accumulators per gate tile (FA independent MMA chains, summed by the epilogue).
 // (Issuing from four warps instead of one was measured: the issue sequence halves, 433 -> 196 cycles, but the
@@ -229,10 +243,15 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_fwd_kernel(P
       gcur[c] = p.gates + ((int64_t)b * p.ndir + d) * G * H + j + t0 * gstride;
       ocur[c] = p.out + (int64_t)b * p.ndir * H + (int64_t)d * H + j + t0 * ostride;
       scur[c] = p.stash + ((int64_t)b * p.ndir + d) * H + j + t0 * ostride;
-      fin[c] = p.h_final ? p.h_final + ((int64_t)d * B + b) * H + j : nullptr;
+      fin[c] = p.h_final ? p.h_final + (int64_t)d * p.hf_d + (int64_t)b * p.hf_b + j : nullptr;
       hoff[c] = canon_off(n, j, PN);
       tfin[c] = d == 0 ? len[c] - 1 : 0;
     }
+    // inter-layer dropout fused into the deferred store (one more store and one Philox block per element, in
+    // the slack under the MMAs): out_drop has out's layout
+    const bool drop = p.out_drop != nullptr;
+    const uint64_t rseed = drop ? p.rng[0] : 0, rstep = drop ? p.rng[1] : 0;
+    const int64_t ddelta = p.out_drop - p.out;
     // hoisted input projection, loaded one step ahead into a second register set.  The two sets swap
     // roles every step (the loop is unrolled by two): a register copy at the end of the step would make
     // every warp wait for its loads there, on the step-to-step chain.
@@ -259,12 +278,14 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_fwd_kernel(P
           if (t_prev >= len[c]) {
             *op = 0.f;
             *sp = 0.f;
+            if (drop) op[ddelta] = 0.f;
             continue;
           }
 #pragma unroll
           for (int g = 0; g < G; ++g) gp[g * H] = gout[g][c];
           *sp = sv[c];
           *op = hv[c];
+          if (drop) op[ddelta] = hv[c] * dropout_factor(rseed, rstep, p.site, op - p.out, p.p_drop);
           if (fin[c] && t_prev == tfin[c]) *fin[c] = hv[c];
         }
       }
@@ -375,12 +396,14 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_fwd_kernel(P
         if (t_last >= len[c]) {
           *op = 0.f;
           *sp = 0.f;
+          if (drop) op[ddelta] = 0.f;
           continue;
         }
 #pragma unroll
         for (int g = 0; g < G; ++g) gp[g * H] = gout[g][c];
         *sp = sv[c];
         *op = hv[c];
+        if (drop) op[ddelta] = hv[c] * dropout_factor(rseed, rstep, p.site, op - p.out, p.p_drop);
         if (fin[c] && t_last == tfin[c]) *fin[c] = hv[c];
       }
     }
@@ -406,6 +429,10 @@ struct PersistBwd {
   const float* dc_final;
   float* dh0;
   float* dc0;
+  int64_t hf_d, hf_b;    // dh_final / dc_final strides (direction, batch)
+  float p_drop;          // > 0: dout is the gradient of dropout(out): apply the forward's mask while reading it
+  const uint64_t* rng;
+  uint32_t site;
 };
 
 // NACC partial accumulators of the single [128 x PN] output tile (independent MMA chains).
@@ -497,7 +524,7 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_bwd_kernel(P
     float* scur[PC];
     const float* ocur[PC];
     const float* dcur[PC];
-    int64_t cidx[PC];
+    int64_t cidx[PC], fidx[PC];
     uint32_t doff[PC];
     bool valid[PC];
 #pragma unroll
@@ -512,8 +539,11 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_bwd_kernel(P
       ocur[c] = p.out + (int64_t)b * p.ndir * H + (int64_t)d * H + k + t0 * ostride;
       dcur[c] = p.dout ? p.dout + (int64_t)b * p.ndir * H + (int64_t)d * H + k + t0 * ostride : nullptr;
       cidx[c] = ((int64_t)d * B + b) * H + k;
+      fidx[c] = (int64_t)d * p.hf_d + (int64_t)b * p.hf_b + k;
       doff[c] = canon_off(n, k, PN);
     }
+    const bool undrop = p.p_drop > 0.f && p.dout != nullptr;
+    const uint64_t rseed = undrop ? p.rng[0] : 0, rstep = undrop ? p.rng[1] : 0;
     // per-step operands, loaded one step ahead into a second register set (the two sets swap roles every
     // step: loop unrolled by two): activated gates, stash, predecessor state, dout
     struct StepIn {
@@ -533,7 +563,13 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_bwd_kernel(P
 #pragma unroll
         for (int g = 0; g < G; ++g) in.g[g][c] = act ? gp[g * H] : 0.f;
         in.s[c] = act ? *sp : 0.f;
-        in.d[c] = (act && dcur[c]) ? *(dcur[c] + rel * odelta) : 0.f;
+        float dv = 0.f;
+        if (act && dcur[c]) {
+          const float* dq = dcur[c] + rel * odelta;
+          dv = *dq;
+          if (undrop) dv *= dropout_factor(rseed, rstep, p.site, dq - p.dout, p.p_drop);
+        }
+        in.d[c] = dv;
         float pv = 0.f;
         if (act) {
           if (G == 4) pv = has_prev ? *(sp + odelta) : (p.c0 ? p.c0[cidx[c]] : 0.f);
@@ -579,7 +615,7 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_bwd_kernel(P
       auto coeff = [&](int c) {
         act[c] = t < len[c];
         inj[c] = d == 0 ? t == len[c] - 1 : t == 0;
-        dhb[c] = cur.d[c] + ((inj[c] && p.dh_final && act[c]) ? p.dh_final[cidx[c]] : 0.f);
+        dhb[c] = cur.d[c] + ((inj[c] && p.dh_final && act[c]) ? p.dh_final[fidx[c]] : 0.f);
         if (G == 4) {
           const float gi = cur.g[0][c], gf = cur.g[1][c], gg = cur.g[2][c], go = cur.g[G - 1][c];
           const float tc = tanh_fast(cur.s[c]);
@@ -588,7 +624,7 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_bwd_kernel(P
           k1[c] = cur.pv[c] * gf * (1.f - gf);
           k2[c] = gi * (1.f - gg * gg);
           k3[c] = tc * go * (1.f - go);
-          dcb[c] = inj[c] ? ((p.dc_final && act[c]) ? p.dc_final[cidx[c]] : 0.f) : carry[c];
+          dcb[c] = inj[c] ? ((p.dc_final && act[c]) ? p.dc_final[fidx[c]] : 0.f) : carry[c];
         } else {
           const float gr = cur.g[0][c], gz = cur.g[1][c], gn = cur.g[2][c];
           a1[c] = (1.f - gz) * (1.f - gn * gn);
@@ -770,9 +806,12 @@ static void launch_persist_bwd(const PersistBwd& p, cudaStream_t s) {
 
 int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh,
                      const float* b_hh, const int64_t* lengths, const float* h0, const float* c0,
-                     float* out, float* stash, float* h_final, cudaStream_t s) {
+                     float* out, float* stash, float* h_final, const slnlp_rnn_extras* ex, cudaStream_t s) {
   if (!tc_shape_ok(H, w_hh)) return -1;
-  PersistFwd p{T, B, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final};
+  const bool cat = ex && ex->hfinal_cat;
+  PersistFwd p{T, B, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final,
+               cat ? (int64_t)H : (int64_t)B * H, cat ? (int64_t)ndir * H : (int64_t)H,
+               ex ? ex->out_drop : nullptr, ex ? ex->p_drop : 0.f, ex ? ex->rng : nullptr, ex ? ex->site : 0u};
   if (mode == SLNLP_MODE_LSTM) launch_persist_fwd<4>(p, s); else launch_persist_fwd<3>(p, s);
   SLNLP_LAUNCH_OK("rnn_layer_fwd(tcgen05)");
   return 0;
@@ -781,9 +820,13 @@ int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, cons
 int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, float* stash, const float* out,
                      const float* w_hh, const int64_t* lengths, const float* h0, const float* c0,
                      const float* dout, const float* dh_final, const float* dc_final, float* dh0, float* dc0,
-                     cudaStream_t s) {
+                     const slnlp_rnn_extras* ex, cudaStream_t s) {
   if (!tc_shape_ok(H, w_hh)) return -1;
-  PersistBwd p{T, B, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0};
+  const bool cat = ex && ex->hfinal_cat;
+  const bool undrop = ex && ex->dout_dropped && ex->p_drop > 0.f;
+  PersistBwd p{T, B, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0,
+               cat ? (int64_t)H : (int64_t)B * H, cat ? (int64_t)ndir * H : (int64_t)H,
+               undrop ? ex->p_drop : 0.f, undrop ? ex->rng : nullptr, undrop ? ex->site : 0u};
   if (mode == SLNLP_MODE_LSTM) launch_persist_bwd<4>(p, s); else launch_persist_bwd<3>(p, s);
   SLNLP_LAUNCH_OK("rnn_layer_bwd(tcgen05)");
   return 0;

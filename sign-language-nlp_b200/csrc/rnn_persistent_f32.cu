@@ -31,7 +31,20 @@ struct PF32Fwd {
   float* out;            // [T,B,ndir*H]
   float* stash;          // [T,B,ndir,H]
   float* h_final;        // [ndir,B,H] or null
+  int64_t hf_d, hf_b;    // h_final strides (direction, batch)
+  float* out_drop;       // dropout(out) for the next layer's input, or null
+  float p_drop;
+  const uint64_t* rng;
+  uint32_t site;
 };
+
+__device__ __forceinline__ float dropout_factor32(uint64_t seed, uint64_t step, uint32_t site, int64_t e, float p) {
+  float u[4];
+  philox_uniform4(seed, step, site, (uint64_t)(e >> 2), u);
+  const int l = (int)(e & 3);
+  const float uu = l == 0 ? u[0] : l == 1 ? u[1] : l == 2 ? u[2] : u[3];
+  return uu < 1.f - p ? 1.f / (1.f - p) : 0.f;
+}
 
 template <int G>
 __global__ void __launch_bounds__(G * FH, 1) rnn_pf32_fwd_kernel(PF32Fwd p) {
@@ -67,11 +80,15 @@ __global__ void __launch_bounds__(G * FH, 1) rnn_pf32_fwd_kernel(PF32Fwd p) {
   float* op = p.out + (int64_t)b * p.ndir * H + (int64_t)d * H + j;     // + t * ostride   (unit threads)
   float* sp = p.stash + ((int64_t)b * p.ndir + d) * H + j;
   float c_state = 0.f, h_state = 0.f;
+  const bool drop = p.out_drop != nullptr;
+  const uint64_t rseed = drop ? p.rng[0] : 0, rstep = drop ? p.rng[1] : 0;
+  const int64_t ddelta = p.out_drop - p.out;
   // frozen steps: out = stash = 0 (gates untouched), no recurrence
   if (tid < H)
     for (int t = len; t < T; ++t) {
       op[(int64_t)t * ostride] = 0.f;
       sp[(int64_t)t * ostride] = 0.f;
+      if (drop) op[(int64_t)t * ostride + ddelta] = 0.f;
     }
   __syncthreads();
   // the sequence's own steps: direction 0 walks t = 0 .. len-1, direction 1 walks t = len-1 .. 0
@@ -130,7 +147,11 @@ __global__ void __launch_bounds__(G * FH, 1) rnn_pf32_fwd_kernel(PF32Fwd p) {
       h_state = h;
       hs[j] = h;
       op[(int64_t)t * ostride] = h;
-      if (p.h_final && step == len - 1) p.h_final[((int64_t)d * B + b) * H + j] = h;
+      if (drop) {
+        float* oq = op + (int64_t)t * ostride;
+        oq[ddelta] = h * dropout_factor32(rseed, rstep, p.site, oq - p.out, p.p_drop);
+      }
+      if (p.h_final && step == len - 1) p.h_final[(int64_t)d * p.hf_d + (int64_t)b * p.hf_b + j] = h;
     }
     x = xnext;
     __syncthreads();
@@ -148,6 +169,10 @@ struct PF32Bwd {
   const float* dout;
   const float* dh_final;
   const float* dc_final;
+  int64_t hf_d, hf_b;    // dh_final / dc_final strides (direction, batch)
+  float p_drop;          // > 0: dout is the gradient of dropout(out)
+  const uint64_t* rng;
+  uint32_t site;
 };
 
 template <int G>
@@ -186,7 +211,9 @@ __global__ void __launch_bounds__(G * FH, 1) rnn_pf32_bwd_kernel(PF32Bwd p) {
   float* sp = p.stash + ((int64_t)b * p.ndir + d) * H + k;
   const float* op = p.out + (int64_t)b * p.ndir * H + (int64_t)d * H + k;
   const float* dp = p.dout ? p.dout + (int64_t)b * p.ndir * H + (int64_t)d * H + k : nullptr;
-  const int64_t cidx = ((int64_t)d * B + b) * H + k;
+  const int64_t cidx = (int64_t)d * p.hf_d + (int64_t)b * p.hf_b + k;
+  const bool undrop = p.p_drop > 0.f && dp != nullptr;
+  const uint64_t rseed = undrop ? p.rng[0] : 0, rstep = undrop ? p.rng[1] : 0;
   // frozen steps: d(pre-activations) = 0 (the hoisted dW / dx GEMMs read every row)
   for (int t = len; t < T; ++t) gp[(int64_t)t * gstride] = 0.f;
   if (G == 3 && tid < H)
@@ -204,7 +231,12 @@ __global__ void __launch_bounds__(G * FH, 1) rnn_pf32_bwd_kernel(PF32Bwd p) {
         for (int q = 0; q < G; ++q) m += part[q * H + k];
       }
       const bool inject = step == 0;
-      float dh = dp ? dp[(int64_t)t * ostride] : 0.f;
+      float dh = 0.f;
+      if (dp) {
+        const float* dq = dp + (int64_t)t * ostride;
+        dh = *dq;
+        if (undrop) dh *= dropout_factor32(rseed, rstep, p.site, dq - p.dout, p.p_drop);
+      }
       float* gt = g0 + (int64_t)t * gstride;
       if (G == 4) {
         float dc_in;
@@ -281,9 +313,12 @@ static bool pf32_enabled() {
 // -1 = shape not supported (the caller falls back to the per-step kernels)
 int rnn_layer_fwd_pf32(int mode, int T, int B, int H, int ndir, float* gates, const float* w_hh, const float* b_hh,
                        const int64_t* lengths, const float* h0, const float* c0, float* out, float* stash,
-                       float* h_final, cudaStream_t s) {
+                       float* h_final, const slnlp_rnn_extras* ex, cudaStream_t s) {
   if (!pf32_enabled() || H != FH || T <= 1 || h0 || c0 || ((uintptr_t)w_hh & 15)) return -1;
-  PF32Fwd p{T, B, ndir, gates, w_hh, b_hh, lengths, out, stash, h_final};
+  const bool cat = ex && ex->hfinal_cat;
+  PF32Fwd p{T, B, ndir, gates, w_hh, b_hh, lengths, out, stash, h_final,
+            cat ? (int64_t)H : (int64_t)B * H, cat ? (int64_t)ndir * H : (int64_t)H,
+            ex ? ex->out_drop : nullptr, ex ? ex->p_drop : 0.f, ex ? ex->rng : nullptr, ex ? ex->site : 0u};
   const dim3 grid(B, ndir);
   if (mode == SLNLP_MODE_LSTM) {
     static bool attr = false;
@@ -300,9 +335,14 @@ int rnn_layer_fwd_pf32(int mode, int T, int B, int H, int ndir, float* gates, co
 
 int rnn_layer_bwd_pf32(int mode, int T, int B, int H, int ndir, float* gates, float* stash, const float* out,
                        const float* w_hh, const int64_t* lengths, const float* h0, const float* c0, const float* dout,
-                       const float* dh_final, const float* dc_final, float* dh0, float* dc0, cudaStream_t s) {
+                       const float* dh_final, const float* dc_final, float* dh0, float* dc0,
+                       const slnlp_rnn_extras* ex, cudaStream_t s) {
   if (!pf32_enabled() || H != FH || T <= 1 || h0 || c0 || dh0 || dc0 || ((uintptr_t)w_hh & 15)) return -1;
-  PF32Bwd p{T, B, ndir, gates, stash, out, w_hh, lengths, dout, dh_final, dc_final};
+  const bool cat = ex && ex->hfinal_cat;
+  const bool undrop = ex && ex->dout_dropped && ex->p_drop > 0.f;
+  PF32Bwd p{T, B, ndir, gates, stash, out, w_hh, lengths, dout, dh_final, dc_final,
+            cat ? (int64_t)H : (int64_t)B * H, cat ? (int64_t)ndir * H : (int64_t)H,
+            undrop ? ex->p_drop : 0.f, undrop ? ex->rng : nullptr, undrop ? ex->site : 0u};
   const dim3 grid(B, ndir);
   if (mode == SLNLP_MODE_LSTM) {
     static bool attr = false;

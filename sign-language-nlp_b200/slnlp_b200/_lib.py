@@ -38,6 +38,9 @@ SIGNATURES = {
     "slnlp_colsum_f32": [P, I, I, I, P, F, P],
     "slnlp_rnn_layer_fwd": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
     "slnlp_rnn_layer_bwd": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
+    "slnlp_rnn_extras_supported": [I, I, I, I, I],
+    "slnlp_rnn_layer_fwd_ex": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P],
+    "slnlp_rnn_layer_bwd_ex": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "slnlp_dec_cell_fwd": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, F, P, U32, P],
     "slnlp_pad_fill": [P, P, I, I, I, F, P],
     "slnlp_pad_fill_copy": [P, P, P, I, I, I, F, P],
@@ -79,6 +82,12 @@ for _name, _args in SIGNATURES.items():
         continue  # declared for a later build stage; tests check header <-> exports
     _fn.argtypes = _args
     _fn.restype = _RESTYPES.get(_name, c_int)
+
+
+class RnnExtras(ctypes.Structure):
+    """slnlp_rnn_extras (include/slnlp_b200.h)."""
+    _fields_ = [("hfinal_cat", c_int), ("out_drop", c_void_p), ("p_drop", c_float), ("rng", c_void_p),
+                ("site", c_uint32), ("dout_dropped", c_int)]
 
 
 def last_error():

@@ -17,13 +17,14 @@ Two ways in:
 from __future__ import annotations
 
 import contextlib
+import ctypes
 import os
 from typing import List
 
 import torch
 import torch.nn as nn
 
-from ._lib import check, lib
+from ._lib import RnnExtras, check, lib
 
 PAD_WORD, BOS_WORD = "<pad>", "<bos>"  # dataset/constant/tokens.py:1,4
 MODE = {"lstm": 0, "gru": 1}
@@ -138,6 +139,19 @@ class RnnEncDecB200(FlatParamModule):
             pre = f"model.encoder.rnn."
             self._gemm(0, 1, T * B, 2 * G * H, D, xin.data_ptr(), D, self._ptr(f"{pre}weight_ih_l{l}"), D,
                        ws.enc_gates[l].data_ptr(), 2 * G * H, self._ptr(f"{pre}bias_ih_l{l}"), 0.0, big=True)
+            if ws.rnn_extras:
+                # persistent kernels: final states straight into the concatenated layout, the next layer's
+                # dropped input from the same deferred store (no concat / dropout launches)
+                to_drop = l < L - 1 and drop and ws.rnn_fused_dropout
+                ex = RnnExtras(1, ws.enc_xin[l + 1].data_ptr() if to_drop else None, self.p_rnn, rng if to_drop else None, l, 0)
+                check(lib.slnlp_rnn_layer_fwd_ex(mode, prec, T, B, H, 2, ws.enc_gates[l].data_ptr(),
+                                                 self._ptr(f"{pre}weight_hh_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
+                                                 lp, None, None, ws.enc_out[l].data_ptr(), ws.enc_stash[l].data_ptr(),
+                                                 ws.enc_final[l].data_ptr(), ctypes.byref(ex), s), "rnn_layer_fwd")
+                if l < L - 1 and drop and not to_drop:
+                    check(lib.slnlp_dropout(ws.enc_out[l].data_ptr(), ws.enc_xin[l + 1].data_ptr(),
+                                            ws.enc_out[l].numel(), self.p_rnn, rng, l, s), "dropout")
+                continue
             check(lib.slnlp_rnn_layer_fwd(mode, prec, T, B, H, 2, ws.enc_gates[l].data_ptr(),
                                           self._ptr(f"{pre}weight_hh_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
                                           lp, None, None, ws.enc_out[l].data_ptr(), ws.enc_stash[l].data_ptr(),
@@ -301,17 +315,26 @@ class RnnEncDecB200(FlatParamModule):
         pre = "model.encoder.rnn."
         for l in range(L - 1, -1, -1):
             D = E if l == 0 else 2 * H
-            check(lib.slnlp_concat_dirs(ws.d_enc_final[l].data_ptr(), ws.d_hfin.data_ptr(), B, H, 2, 1, s),
-                  "concat_dirs_inv")
             dg, st, out = ws.enc_gates[l].data_ptr(), ws.enc_stash[l].data_ptr(), ws.enc_out[l].data_ptr()
-            check(lib.slnlp_rnn_layer_bwd(mode, prec, T, B, H, 2, dg, st, out, self._ptr(f"{pre}weight_hh_l{l}"),
-                                          lp, None, None, ws.d_seq.data_ptr(), ws.d_hfin.data_ptr(), None,
-                                          None, None, ws.carry.data_ptr(), s), "rnn_layer_bwd")
+            if ws.rnn_extras:
+                # d(final states) read in the concatenated layout; for l < L-1 d_seq is the gradient of the DROPPED
+                # output of this layer: the forward's mask is applied while the kernel reads it
+                undrop = l < L - 1 and drop and ws.rnn_fused_dropout
+                ex = RnnExtras(1, None, self.p_rnn if undrop else 0.0, rng if undrop else None, l, 1 if undrop else 0)
+                check(lib.slnlp_rnn_layer_bwd_ex(mode, prec, T, B, H, 2, dg, st, out, self._ptr(f"{pre}weight_hh_l{l}"),
+                                                 lp, None, None, ws.d_seq.data_ptr(), ws.d_enc_final[l].data_ptr(), None,
+                                                 None, None, ws.carry.data_ptr(), ctypes.byref(ex), s), "rnn_layer_bwd")
+            else:
+                check(lib.slnlp_concat_dirs(ws.d_enc_final[l].data_ptr(), ws.d_hfin.data_ptr(), B, H, 2, 1, s),
+                      "concat_dirs_inv")
+                check(lib.slnlp_rnn_layer_bwd(mode, prec, T, B, H, 2, dg, st, out, self._ptr(f"{pre}weight_hh_l{l}"),
+                                              lp, None, None, ws.d_seq.data_ptr(), ws.d_hfin.data_ptr(), None,
+                                              None, None, ws.carry.data_ptr(), s), "rnn_layer_bwd")
             # critical path first: the gradient the next (lower) layer's BPTT is waiting for
             if l > 0:
                 self._gemm(0, 0, T * B, D, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), D,
                            ws.d_seq.data_ptr(), D, big=True)
-                if drop:
+                if drop and not ws.rnn_fused_dropout:
                     check(lib.slnlp_dropout(ws.d_seq.data_ptr(), ws.d_seq.data_ptr(), T * B * D, self.p_rnn,
                                             rng, l - 1, s), "dropout")
             else:
@@ -428,6 +451,13 @@ class _Workspace:
         dev = m._flat.device
         f = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
         self.B, self.T, self.train = B, T, train
+        self.rnn_extras = (os.environ.get("SLNLP_RNN_EXTRAS", "1") != "0" and
+                           bool(lib.slnlp_rnn_extras_supported(1 if m.precision == "bf16" else 0, T, B, H, 2)))
+        # the inter-layer dropout inside the recurrent kernels: one Philox block per element and step on the
+        # step-to-step chain.  Hidden by the fp32 kernel's 16 warps; measured a net loss on the tcgen05 kernel
+        # (4 epilogue warps, one per scheduler: the 10 dependent Philox rounds are not hidden): off there
+        env = os.environ.get("SLNLP_RNN_FUSED_DROPOUT")
+        self.rnn_fused_dropout = self.rnn_extras and ((m.precision != "bf16") if env is None else env != "0")
         self.f_off = (ctypes.c_int64 * 1)(0)
         self.f_w_src = (ctypes.c_int * 1)(E)
         self.f_rows_src = (ctypes.c_int64 * 1)(m.V_src)
