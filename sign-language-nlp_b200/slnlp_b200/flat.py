@@ -259,6 +259,16 @@ class FlatParamModule(nn.Module):
         with torch.cuda.stream(self._fork_side(lane % self.N_LANES)):
             yield
 
+    def _join_lane(self, lane):
+        """The current stream waits for ONE side lane (an activation branch the chain needs back)."""
+        pending = self.__dict__.get("_lanes_pending")
+        if not pending or lane not in pending:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self._side_stream(lane))
+        torch.cuda.current_stream().wait_event(ev)
+        pending.discard(lane)
+
     def _join_side(self):
         pending = self.__dict__.get("_lanes_pending")
         if not pending:

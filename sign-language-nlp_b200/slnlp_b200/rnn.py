@@ -164,17 +164,21 @@ class RnnEncDecB200(FlatParamModule):
         # pad_packed_sequence(padding_value=<pad>) (bkp:121-123): a pad-FILLED copy for the key projection and
         # the attention; BPTT and dW_hh keep reading the zero-padded original (no un-fill on the way back)
         enc_out = ws.enc_filled
-        check(lib.slnlp_pad_fill_copy(ws.enc_out[L - 1].data_ptr(), enc_out.data_ptr(), lp, T, B, 2 * H,
-                                      float(self.src_pad), s), "pad_fill")
+        # the pad-filled copy and the key projection (bkp:246) need only the encoder output: under capture they
+        # run on a side lane next to bridge -> tanh -> query, which need only the final states
+        with self._side_branch(2):
+            check(lib.slnlp_pad_fill_copy(ws.enc_out[L - 1].data_ptr(), enc_out.data_ptr(), lp, T, B, 2 * H,
+                                          float(self.src_pad), _stream()), "pad_fill")
+            self._gemm(0, 1, T * B, H, 2 * H, enc_out.data_ptr(), 2 * H,
+                       self._ptr("model.decoder.attention.key_layer.weight"), 2 * H, ws.pk.data_ptr(), H, big=True)
         # bridge (bkp:268-280)
         self._gemm(0, 1, L * B, H, 2 * H, ws.enc_final.data_ptr(), 2 * H, self._ptr("model.decoder.bridge.weight"),
                    2 * H, ws.hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.bias"))
         check(lib.slnlp_tanh_fwd(ws.hidden0.data_ptr(), ws.hidden0.numel(), s), "tanh")
-        # attention (bkp:246,304-327)
-        self._gemm(0, 1, T * B, H, 2 * H, enc_out.data_ptr(), 2 * H,
-                   self._ptr("model.decoder.attention.key_layer.weight"), 2 * H, ws.pk.data_ptr(), H, big=True)
+        # attention (bkp:304-327)
         self._gemm(0, 1, B, H, H, ws.hidden0[L - 1].data_ptr(), H,
                    self._ptr("model.decoder.attention.query_layer.weight"), H, ws.q.data_ptr(), H)
+        self._join_lane(2)
         check(lib.slnlp_attn_step_fwd(ws.q.data_ptr(), ws.pk.data_ptr(),
                                       self._ptr("model.decoder.attention.energy_layer.weight"),
                                       enc_out.data_ptr(), Xp, self.src_pad, T, B, H, 2 * H,
@@ -286,10 +290,13 @@ class RnnEncDecB200(FlatParamModule):
                                       self._ptr(att + "energy_layer.weight"), enc_out.data_ptr(),
                                       ws.alpha.data_ptr(), T, B, H, 2 * H, ws.d_seq.data_ptr(), ws.d_pk.data_ptr(),
                                       ws.d_q.data_ptr(), ws.dv_part.data_ptr(), s), "attn_bwd")
+        # d(encoder output) through the key projection: only the encoder BPTT waits for it - a side lane under
+        # capture, next to query -> tanh' -> bridge
+        with self._side_branch(2):
+            self._gemm(0, 0, T * B, 2 * H, H, ws.d_pk.data_ptr(), H, self._ptr(att + "key_layer.weight"), 2 * H,
+                       ws.d_seq.data_ptr(), 2 * H, None, 1.0, big=True)
         self._gemm(0, 0, B, H, H, ws.d_q.data_ptr(), H, self._ptr(att + "query_layer.weight"), H,
                    ws.d_hidden0[L - 1].data_ptr(), H, None, 1.0)
-        self._gemm(0, 0, T * B, 2 * H, H, ws.d_pk.data_ptr(), H, self._ptr(att + "key_layer.weight"), 2 * H,
-                   ws.d_seq.data_ptr(), 2 * H, None, 1.0, big=True)
         # bridge
         check(lib.slnlp_tanh_bwd(ws.d_hidden0.data_ptr(), ws.hidden0.data_ptr(), L * B * H, s), "tanh_bwd")
         self._gemm(0, 0, L * B, 2 * H, H, ws.d_hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.weight"),
@@ -313,6 +320,7 @@ class RnnEncDecB200(FlatParamModule):
             hook(gflat, off["model.decoder.attention.key_layer.weight"], off["model.src_embed.weight"])
             hook(gflat, off["model.trg_embed.weight"], numel)
         pre = "model.encoder.rnn."
+        self._join_lane(2)
         for l in range(L - 1, -1, -1):
             D = E if l == 0 else 2 * H
             dg, st, out = ws.enc_gates[l].data_ptr(), ws.enc_stash[l].data_ptr(), ws.enc_out[l].data_ptr()
@@ -330,7 +338,13 @@ class RnnEncDecB200(FlatParamModule):
                 check(lib.slnlp_rnn_layer_bwd(mode, prec, T, B, H, 2, dg, st, out, self._ptr(f"{pre}weight_hh_l{l}"),
                                               lp, None, None, ws.d_seq.data_ptr(), ws.d_hfin.data_ptr(), None,
                                               None, None, ws.carry.data_ptr(), s), "rnn_layer_bwd")
-            # critical path first: the gradient the next (lower) layer's BPTT is waiting for
+            # weight / bias gradients of this layer: off the chain, on the side lanes.  Under capture they fork
+            # HERE, right behind the BPTT kernel that produced their operand (forking after the dx GEMM would make
+            # them wait for it: the last layer's weight gradients then trail the whole step)
+            par = self.overlap_dw and hook is None and torch.cuda.is_current_stream_capturing()
+            if par:
+                self._encoder_weight_grads(ws, l, gp, parallel=True)
+            # the gradient the next (lower) layer's BPTT is waiting for
             if l > 0:
                 self._gemm(0, 0, T * B, D, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), D,
                            ws.d_seq.data_ptr(), D, big=True)
@@ -343,8 +357,8 @@ class RnnEncDecB200(FlatParamModule):
                 check(lib.slnlp_embed_gather_bwd(gp("model.src_embed.weight"), Xp, ws.d_emb.data_ptr(), B, T, 1,
                                                  ws.f_off, ws.f_w_src, ws.f_rows_src, 1, 1.0, self.src_pad, s),
                       "embed_bwd")
-            # weight / bias gradients of this layer: off the chain, on the side lanes
-            self._encoder_weight_grads(ws, l, gp, parallel=self.overlap_dw and hook is None)
+            if not par:       # eager / data-parallel: after the critical-path kernels, same stream
+                self._encoder_weight_grads(ws, l, gp, parallel=False)
             if hook is not None:  # this layer's range goes out while the layer below runs its BPTT
                 nxt = f"{pre}weight_ih_l{l + 1}" if l < L - 1 else "model.decoder.attention.key_layer.weight"
                 hook(gflat, off[f"{pre}weight_ih_l{l}"], off[nxt])
