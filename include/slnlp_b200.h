@@ -158,6 +158,8 @@ typedef struct slnlp_rnn_extras {
   const uint64_t* rng;
   uint32_t site;
   int dout_dropped;
+  const float* mask;  /* optional: the factors slnlp_dropout_mask(site) wrote (out's layout) - then neither kernel
+                       * runs Philox in its step loop (ten dependent rounds the tcgen05 kernel cannot hide) */
 } slnlp_rnn_extras;
 int slnlp_rnn_extras_supported(int precision, int T, int B, int H, int ndir);
 int slnlp_rnn_layer_fwd_ex(int mode, int precision, int T, int B, int H, int ndir,
@@ -194,6 +196,8 @@ int slnlp_tanh_bwd(float* dy, const float* y, int64_t n, slnlp_stream_t stream);
  * device array of two uint64.  In-place (y == x) allowed; bwd is the same call. */
 int slnlp_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* rng,
                   uint32_t site, slnlp_stream_t stream);
+/* y[i] = the keep / scale factor (0 or 1/(1-p)) slnlp_dropout(site) applies to element i under the same rng state */
+int slnlp_dropout_mask(float* y, int64_t n, float p, const uint64_t* rng, uint32_t site, slnlp_stream_t stream);
 int slnlp_rng_advance(uint64_t* rng, slnlp_stream_t stream);
 /* dst[b, 0:E] = row[E]; dst[b, E:E+W] = src[b, 0:W]  (B rows) */
 int slnlp_dec_input_fwd(const float* row, const float* src, float* dst, int B, int E, int W,

@@ -385,6 +385,26 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ 
     }
   }
 }
+// the keep / scale factors slnlp_dropout(site) applies, as a tensor: generated once per step off the critical
+// path, consumed by kernels that cannot afford ten Philox rounds in their loop (the persistent recurrent kernels)
+__global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ y, int64_t n, float p,
+                                                           const uint64_t* __restrict__ rng, uint32_t site) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const uint64_t seed = rng[0], step = rng[1];
+  const float keep = 1.f - p, inv = 1.f / (1.f - p);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32) ^ (site * 0x9E3779B9u), (uint32_t)step,
+                     (uint32_t)(step >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = q * 4 + j;
+      if (i < n) y[i] = (float)(c[j] >> 8) * (1.0f / 16777216.0f) < keep ? inv : 0.f;
+    }
+  }
+}
 __global__ void rng_advance_kernel(uint64_t* rng) {
   pdl_wait();
   pdl_launch_dependents(); rng[1] += 1; }
@@ -685,6 +705,13 @@ int slnlp_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* 
   if (n == 0) return 0;
   launch_pdl(dropout_kernel, dim3(ew_grid((n + 3) / 4)), dim3(256), 0, as_stream(stream), x, y, n, p, rng, site);
   SLNLP_LAUNCH_OK("dropout");
+  return 0;
+}
+int slnlp_dropout_mask(float* y, int64_t n, float p, const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(y && rng && n >= 0 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments");
+  if (n == 0) return 0;
+  launch_pdl(dropout_mask_kernel, dim3(ew_grid((n + 3) / 4)), dim3(256), 0, as_stream(stream), y, n, p, rng, site);
+  SLNLP_LAUNCH_OK("dropout_mask");
   return 0;
 }
 int slnlp_rng_advance(uint64_t* rng, slnlp_stream_t stream) {

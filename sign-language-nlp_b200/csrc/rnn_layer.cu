@@ -475,7 +475,8 @@ extern "C" int slnlp_rnn_layer_fwd_ex(int mode, int precision, int T, int B, int
   SLNLP_CHECK_ARG(!wants || (extras_family(precision, T, H, w_hh) && !h0 && !c0),
                   "rnn_layer_fwd_ex: extras need the persistent kernels (H = 128, T > 1, no initial state); "
                   "ask slnlp_rnn_extras_supported first");
-  SLNLP_CHECK_ARG(!ex || !ex->out_drop || (ex->rng && ex->p_drop >= 0.f && ex->p_drop < 1.f), "rnn_layer_fwd_ex: bad dropout arguments");
+  SLNLP_CHECK_ARG(!ex || !ex->out_drop || ((ex->rng || ex->mask) && ex->p_drop >= 0.f && ex->p_drop < 1.f),
+                  "rnn_layer_fwd_ex: bad dropout arguments");
   SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM || mode == SLNLP_MODE_GRU, "rnn_layer_fwd: bad mode %d", mode);
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_fwd: bad shape");
   SLNLP_CHECK_ARG(gates && w_hh && b_hh && out && stash, "rnn_layer_fwd: null pointer");
@@ -533,7 +534,8 @@ extern "C" int slnlp_rnn_layer_bwd_ex(int mode, int precision, int T, int B, int
   const bool wants = ex && (ex->hfinal_cat || (ex->dout_dropped && ex->p_drop > 0.f));
   SLNLP_CHECK_ARG(!wants || (extras_family(precision, T, H, w_hh) && !h0 && !c0 && !dh0 && !dc0),
                   "rnn_layer_bwd_ex: extras need the persistent kernels (H = 128, T > 1, no initial state)");
-  SLNLP_CHECK_ARG(!ex || !ex->dout_dropped || ex->p_drop <= 0.f || ex->rng, "rnn_layer_bwd_ex: dropout replay needs rng");
+  SLNLP_CHECK_ARG(!ex || !ex->dout_dropped || ex->p_drop <= 0.f || ex->rng || ex->mask,
+                  "rnn_layer_bwd_ex: dropout replay needs rng or a mask");
   SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM || mode == SLNLP_MODE_GRU, "rnn_layer_bwd: bad mode %d", mode);
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_bwd: bad shape");
   SLNLP_CHECK_ARG(gates && stash && out && w_hh && carry, "rnn_layer_bwd: null pointer");

@@ -98,6 +98,7 @@ struct PersistFwd {
   float p_drop;
   const uint64_t* rng;   // {seed, step} of the module's Philox stream
   uint32_t site;
+  const float* mask;     // precomputed keep / scale factors (out's layout) instead of Philox in the loop, or null
 };
 
 // the keep / scale factor slnlp_dropout(site) applies to element e of a tensor: Philox block e / 4, lane e % 4
@@ -250,8 +251,17 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_fwd_kernel(P
     // inter-layer dropout fused into the deferred store (one more store and one Philox block per element, in
     // the slack under the MMAs): out_drop has out's layout
     const bool drop = p.out_drop != nullptr;
-    const uint64_t rseed = drop ? p.rng[0] : 0, rstep = drop ? p.rng[1] : 0;
+    const uint64_t rseed = (drop && !p.mask) ? p.rng[0] : 0, rstep = (drop && !p.mask) ? p.rng[1] : 0;
     const int64_t ddelta = p.out_drop - p.out;
+    // with precomputed factors, the factor of the step being computed is loaded with the next step's prefetch
+    // and used one iteration later by the deferred store (a load right before the store would put an L2 round
+    // trip on the step-to-step chain)
+    float mk[PC];
+#pragma unroll
+    for (int c = 0; c < PC; ++c) mk[c] = 0.f;
+    auto keep = [&](const float* o, int c) {
+      return p.mask ? mk[c] : dropout_factor(rseed, rstep, p.site, o - p.out, p.p_drop);
+    };
     // hoisted input projection, loaded one step ahead into a second register set.  The two sets swap
     // roles every step (the loop is unrolled by two): a register copy at the end of the step would make
     // every warp wait for its loads there, on the step-to-step chain.
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_fwd_kernel(P
           for (int g = 0; g < G; ++g) gp[g * H] = gout[g][c];
           *sp = sv[c];
           *op = hv[c];
-          if (drop) op[ddelta] = hv[c] * dropout_factor(rseed, rstep, p.site, op - p.out, p.p_drop);
+          if (drop) op[ddelta] = hv[c] * keep(op, c);
           if (fin[c] && t_prev == tfin[c]) *fin[c] = hv[c];
         }
       }
@@ -297,6 +307,10 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_fwd_kernel(P
 #pragma unroll
           for (int g = 0; g < G; ++g) xn[g][c] = act ? gp[g * H] : 0.f;
         }
+      }
+      if (drop && p.mask) {
+#pragma unroll
+        for (int c = 0; c < PC; ++c) mk[c] = (valid[c] && t < len[c]) ? p.mask[ocur[c] - p.out] : 0.f;
       }
       PROF_MARK(1);   // issue of the deferred stores and of the next step's loads
       // accumulators of gate tile g (FA partial sums at columns (g*FA + q)*PN) -> a[]
@@ -403,7 +417,7 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_fwd_kernel(P
         for (int g = 0; g < G; ++g) gp[g * H] = gout[g][c];
         *sp = sv[c];
         *op = hv[c];
-        if (drop) op[ddelta] = hv[c] * dropout_factor(rseed, rstep, p.site, op - p.out, p.p_drop);
+        if (drop) op[ddelta] = hv[c] * keep(op, c);
         if (fin[c] && t_last == tfin[c]) *fin[c] = hv[c];
       }
     }
@@ -433,6 +447,7 @@ struct PersistBwd {
   float p_drop;          // > 0: dout is the gradient of dropout(out): apply the forward's mask while reading it
   const uint64_t* rng;
   uint32_t site;
+  const float* mask;     // precomputed factors (dout's layout) instead of Philox, or null
 };
 
 // NACC partial accumulators of the single [128 x PN] output tile (independent MMA chains).
@@ -543,7 +558,7 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_bwd_kernel(P
       doff[c] = canon_off(n, k, PN);
     }
     const bool undrop = p.p_drop > 0.f && p.dout != nullptr;
-    const uint64_t rseed = undrop ? p.rng[0] : 0, rstep = undrop ? p.rng[1] : 0;
+    const uint64_t rseed = (undrop && !p.mask) ? p.rng[0] : 0, rstep = (undrop && !p.mask) ? p.rng[1] : 0;
     // per-step operands, loaded one step ahead into a second register set (the two sets swap roles every
     // step: loop unrolled by two): activated gates, stash, predecessor state, dout
     struct StepIn {
@@ -567,7 +582,7 @@ __global__ void __launch_bounds__(128 * NCG + 32, 1) rnn_persistent_bwd_kernel(P
         if (act && dcur[c]) {
           const float* dq = dcur[c] + rel * odelta;
           dv = *dq;
-          if (undrop) dv *= dropout_factor(rseed, rstep, p.site, dq - p.dout, p.p_drop);
+          if (undrop) dv *= p.mask ? p.mask[dq - p.dout] : dropout_factor(rseed, rstep, p.site, dq - p.dout, p.p_drop);
         }
         in.d[c] = dv;
         float pv = 0.f;
@@ -811,7 +826,8 @@ int rnn_layer_fwd_tc(int mode, int T, int B, int H, int ndir, float* gates, cons
   const bool cat = ex && ex->hfinal_cat;
   PersistFwd p{T, B, ndir, gates, w_hh, b_hh, lengths, h0, c0, out, stash, h_final,
                cat ? (int64_t)H : (int64_t)B * H, cat ? (int64_t)ndir * H : (int64_t)H,
-               ex ? ex->out_drop : nullptr, ex ? ex->p_drop : 0.f, ex ? ex->rng : nullptr, ex ? ex->site : 0u};
+               ex ? ex->out_drop : nullptr, ex ? ex->p_drop : 0.f, ex ? ex->rng : nullptr, ex ? ex->site : 0u,
+               ex ? ex->mask : nullptr};
   if (mode == SLNLP_MODE_LSTM) launch_persist_fwd<4>(p, s); else launch_persist_fwd<3>(p, s);
   SLNLP_LAUNCH_OK("rnn_layer_fwd(tcgen05)");
   return 0;
@@ -826,7 +842,7 @@ int rnn_layer_bwd_tc(int mode, int T, int B, int H, int ndir, float* gates, floa
   const bool undrop = ex && ex->dout_dropped && ex->p_drop > 0.f;
   PersistBwd p{T, B, ndir, gates, stash, out, w_hh, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0,
                cat ? (int64_t)H : (int64_t)B * H, cat ? (int64_t)ndir * H : (int64_t)H,
-               undrop ? ex->p_drop : 0.f, undrop ? ex->rng : nullptr, undrop ? ex->site : 0u};
+               undrop ? ex->p_drop : 0.f, undrop ? ex->rng : nullptr, undrop ? ex->site : 0u, undrop ? ex->mask : nullptr};
   if (mode == SLNLP_MODE_LSTM) launch_persist_bwd<4>(p, s); else launch_persist_bwd<3>(p, s);
   SLNLP_LAUNCH_OK("rnn_layer_bwd(tcgen05)");
   return 0;

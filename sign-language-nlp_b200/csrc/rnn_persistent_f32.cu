@@ -36,6 +36,7 @@ struct PF32Fwd {
   float p_drop;
   const uint64_t* rng;
   uint32_t site;
+  const float* mask;     // precomputed factors instead of Philox, or null
 };
 
 __device__ __forceinline__ float dropout_factor32(uint64_t seed, uint64_t step, uint32_t site, int64_t e, float p) {
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(G * FH, 1) rnn_pf32_fwd_kernel(PF32Fwd p) {
   float* sp = p.stash + ((int64_t)b * p.ndir + d) * H + j;
   float c_state = 0.f, h_state = 0.f;
   const bool drop = p.out_drop != nullptr;
-  const uint64_t rseed = drop ? p.rng[0] : 0, rstep = drop ? p.rng[1] : 0;
+  const uint64_t rseed = (drop && !p.mask) ? p.rng[0] : 0, rstep = (drop && !p.mask) ? p.rng[1] : 0;
   const int64_t ddelta = p.out_drop - p.out;
   // frozen steps: out = stash = 0 (gates untouched), no recurrence
   if (tid < H)
@@ -97,6 +98,8 @@ __global__ void __launch_bounds__(G * FH, 1) rnn_pf32_fwd_kernel(PF32Fwd p) {
     const int t = d == 0 ? step : len - 1 - step;
     float xnext = 0.f;
     if (step + 1 < len) xnext = gp[(int64_t)(d == 0 ? t + 1 : t - 1) * gstride];
+    float mk = 0.f;      // precomputed dropout factor of this step's output: loaded ahead of the recurrent product
+    if (drop && p.mask && tid < H) mk = p.mask[(op + (int64_t)t * ostride) - p.out];
     // recurrent product: row tid of W_hh against h_{t-1}
     float a0 = 0.f, a1 = 0.f;
     if (step > 0) {
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(G * FH, 1) rnn_pf32_fwd_kernel(PF32Fwd p) {
       op[(int64_t)t * ostride] = h;
       if (drop) {
         float* oq = op + (int64_t)t * ostride;
-        oq[ddelta] = h * dropout_factor32(rseed, rstep, p.site, oq - p.out, p.p_drop);
+        oq[ddelta] = h * (p.mask ? mk : dropout_factor32(rseed, rstep, p.site, oq - p.out, p.p_drop));
       }
       if (p.h_final && step == len - 1) p.h_final[(int64_t)d * p.hf_d + (int64_t)b * p.hf_b + j] = h;
     }
@@ -173,6 +176,7 @@ struct PF32Bwd {
   float p_drop;          // > 0: dout is the gradient of dropout(out)
   const uint64_t* rng;
   uint32_t site;
+  const float* mask;
 };
 
 template <int G>
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(G * FH, 1) rnn_pf32_bwd_kernel(PF32Bwd p) {
   const float* dp = p.dout ? p.dout + (int64_t)b * p.ndir * H + (int64_t)d * H + k : nullptr;
   const int64_t cidx = (int64_t)d * p.hf_d + (int64_t)b * p.hf_b + k;
   const bool undrop = p.p_drop > 0.f && dp != nullptr;
-  const uint64_t rseed = undrop ? p.rng[0] : 0, rstep = undrop ? p.rng[1] : 0;
+  const uint64_t rseed = (undrop && !p.mask) ? p.rng[0] : 0, rstep = (undrop && !p.mask) ? p.rng[1] : 0;
   // frozen steps: d(pre-activations) = 0 (the hoisted dW / dx GEMMs read every row)
   for (int t = len; t < T; ++t) gp[(int64_t)t * gstride] = 0.f;
   if (G == 3 && tid < H)
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(G * FH, 1) rnn_pf32_bwd_kernel(PF32Bwd p) {
       if (dp) {
         const float* dq = dp + (int64_t)t * ostride;
         dh = *dq;
-        if (undrop) dh *= dropout_factor32(rseed, rstep, p.site, dq - p.dout, p.p_drop);
+        if (undrop) dh *= p.mask ? p.mask[dq - p.dout] : dropout_factor32(rseed, rstep, p.site, dq - p.dout, p.p_drop);
       }
       float* gt = g0 + (int64_t)t * gstride;
       if (G == 4) {
@@ -318,7 +322,8 @@ int rnn_layer_fwd_pf32(int mode, int T, int B, int H, int ndir, float* gates, co
   const bool cat = ex && ex->hfinal_cat;
   PF32Fwd p{T, B, ndir, gates, w_hh, b_hh, lengths, out, stash, h_final,
             cat ? (int64_t)H : (int64_t)B * H, cat ? (int64_t)ndir * H : (int64_t)H,
-            ex ? ex->out_drop : nullptr, ex ? ex->p_drop : 0.f, ex ? ex->rng : nullptr, ex ? ex->site : 0u};
+            ex ? ex->out_drop : nullptr, ex ? ex->p_drop : 0.f, ex ? ex->rng : nullptr, ex ? ex->site : 0u,
+            ex ? ex->mask : nullptr};
   const dim3 grid(B, ndir);
   if (mode == SLNLP_MODE_LSTM) {
     static bool attr = false;
@@ -342,7 +347,7 @@ int rnn_layer_bwd_pf32(int mode, int T, int B, int H, int ndir, float* gates, fl
   const bool undrop = ex && ex->dout_dropped && ex->p_drop > 0.f;
   PF32Bwd p{T, B, ndir, gates, stash, out, w_hh, lengths, dout, dh_final, dc_final,
             cat ? (int64_t)H : (int64_t)B * H, cat ? (int64_t)ndir * H : (int64_t)H,
-            undrop ? ex->p_drop : 0.f, undrop ? ex->rng : nullptr, undrop ? ex->site : 0u};
+            undrop ? ex->p_drop : 0.f, undrop ? ex->rng : nullptr, undrop ? ex->site : 0u, undrop ? ex->mask : nullptr};
   const dim3 grid(B, ndir);
   if (mode == SLNLP_MODE_LSTM) {
     static bool attr = false;

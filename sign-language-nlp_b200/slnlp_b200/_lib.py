@@ -51,6 +51,7 @@ SIGNATURES = {
     "slnlp_relu_bwd": [P, P, L, P],
     "slnlp_dropout": [P, P, L, F, P, U32, P],
     "slnlp_rng_advance": [P, P],
+    "slnlp_dropout_mask": [P, L, F, P, U32, P],
     "slnlp_dec_input_fwd": [P, P, P, I, I, I, P],
     "slnlp_dec_input_bwd": [P, P, P, I, I, I, P],
     "slnlp_axpy": [P, P, F, L, P],
@@ -87,7 +88,7 @@ for _name, _args in SIGNATURES.items():
 class RnnExtras(ctypes.Structure):
     """slnlp_rnn_extras (include/slnlp_b200.h)."""
     _fields_ = [("hfinal_cat", c_int), ("out_drop", c_void_p), ("p_drop", c_float), ("rng", c_void_p),
-                ("site", c_uint32), ("dout_dropped", c_int)]
+                ("site", c_uint32), ("dout_dropped", c_int), ("mask", c_void_p)]
 
 
 def last_error():

@@ -205,13 +205,24 @@ class FlatParamModule(nn.Module):
         return ws
 
     # ------------------------------------------------------------------ kernels
-    def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0, big=False):
-        # tensor-core path: the TMA-fed TF32 kernel
-        # (`big` marks the [B*T]-row GEMMs; the tensor-core path takes the skinny ones too - the
-        # library falls back to the fp32 kernel by itself for shapes a 128-row tile cannot cover)
+    def _gemm(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0, big=False, act=None, drop=None):
+        """C = op(A) op(B) (+ bias) (+ beta C) on the TMA-fed TF32 tensor-core kernel (fp32 path: the fp32-FMA
+        GEMM), then optionally ``act`` ("tanh") and ``drop`` = (p, rng_ptr, site): the element-wise dropout
+        slnlp_dropout(site) applies to C.  (A latency-built fp32-FMA "skinny" kernel with both epilogues and an
+        in-kernel split-K reduction was measured for the 50-row products of the decoder side: 4 us SLOWER per
+        call than the tensor-core kernel's 5.8 - two dependent L2 round trips for the slices cost what the TMA
+        pipeline's prologue does - and was dropped; only fusing the chain into fewer kernels pays.)
+        (`big` marks the [B*T]-row GEMMs; the library falls back to the fp32 kernel by itself for shapes a
+        128-row tile cannot cover)"""
         fn = _TC_GEMM if self.precision == "bf16" else lib.slnlp_gemm_f32
         ws = self._gemm_ws()
         check(fn(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, ws.data_ptr(), ws.numel(), _stream()), "gemm")
+        if act == "tanh":
+            assert ldc == N
+            check(lib.slnlp_tanh_fwd(C, M * N, _stream()), "tanh")
+        if drop is not None:
+            assert ldc == N
+            check(lib.slnlp_dropout(C, C, M * N, drop[0], drop[1], drop[2], _stream()), "dropout")
 
     def _gemm_ws(self):
         """Split-K scratch of the GEMMs of this module: one buffer per stream the module launches on

@@ -36,6 +36,7 @@ from .flat import CAPTURE_LOCK, FlatParamModule, _Box, _align4, _stream, capture
 
 class RnnEncDecB200(FlatParamModule):
     MAX_OUTPUT_LEN = 1  # bkp:332
+    _joins_rng_lane = True   # _run_forward joins side lane 3 (rng advance + dropout factors) before the first RNN layer
     _dead = ("model.decoder.pre_output_layer.weight",)
 
     def __init__(self, src_vocab, tgt_vocab, batch_first, rnn_type, embedding_size=256,
@@ -133,17 +134,28 @@ class RnnEncDecB200(FlatParamModule):
                                          ws.f_off, ws.f_w_src, ws.f_rows_src, 1, 1.0, None, s), "embed")
         drop = ws.train and self.p_rnn > 0.0
         rng = self._rng_state().data_ptr() if drop else None
+        if drop and ws.rnn_fused_dropout:
+            # the inter-layer dropout factors of this step as tensors, generated on a side lane (under capture)
+            # while the embedding and the first projection run: the persistent kernels then apply them with
+            # one load per step instead of ten dependent Philox rounds
+            with self._side_branch(3):
+                for l in range(L - 1):
+                    check(lib.slnlp_dropout_mask(ws.drop_mask[l].data_ptr(), ws.drop_mask[l].numel(), self.p_rnn, rng, l,
+                                                 _stream()), "dropout_mask")
         for l in range(L):
             D = E if l == 0 else 2 * H
             xin = ws.emb if l == 0 else ws.enc_xin[l]
             pre = f"model.encoder.rnn."
             self._gemm(0, 1, T * B, 2 * G * H, D, xin.data_ptr(), D, self._ptr(f"{pre}weight_ih_l{l}"), D,
                        ws.enc_gates[l].data_ptr(), 2 * G * H, self._ptr(f"{pre}bias_ih_l{l}"), 0.0, big=True)
+            if l == 0:
+                self._join_lane(3)        # rng advanced (FusedTrainStep) and dropout factors ready
             if ws.rnn_extras:
                 # persistent kernels: final states straight into the concatenated layout, the next layer's
                 # dropped input from the same deferred store (no concat / dropout launches)
                 to_drop = l < L - 1 and drop and ws.rnn_fused_dropout
-                ex = RnnExtras(1, ws.enc_xin[l + 1].data_ptr() if to_drop else None, self.p_rnn, rng if to_drop else None, l, 0)
+                ex = RnnExtras(1, ws.enc_xin[l + 1].data_ptr() if to_drop else None, self.p_rnn, rng if to_drop else None, l, 0,
+                               ws.drop_mask[l].data_ptr() if to_drop else None)
                 check(lib.slnlp_rnn_layer_fwd_ex(mode, prec, T, B, H, 2, ws.enc_gates[l].data_ptr(),
                                                  self._ptr(f"{pre}weight_hh_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
                                                  lp, None, None, ws.enc_out[l].data_ptr(), ws.enc_stash[l].data_ptr(),
@@ -173,8 +185,7 @@ class RnnEncDecB200(FlatParamModule):
                        self._ptr("model.decoder.attention.key_layer.weight"), 2 * H, ws.pk.data_ptr(), H, big=True)
         # bridge (bkp:268-280)
         self._gemm(0, 1, L * B, H, 2 * H, ws.enc_final.data_ptr(), 2 * H, self._ptr("model.decoder.bridge.weight"),
-                   2 * H, ws.hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.bias"))
-        check(lib.slnlp_tanh_fwd(ws.hidden0.data_ptr(), ws.hidden0.numel(), s), "tanh")
+                   2 * H, ws.hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.bias"), act="tanh")
         # attention (bkp:304-327)
         self._gemm(0, 1, B, H, H, ws.hidden0[L - 1].data_ptr(), H,
                    self._ptr("model.decoder.attention.query_layer.weight"), H, ws.q.data_ptr(), H)
@@ -260,7 +271,9 @@ class RnnEncDecB200(FlatParamModule):
                 check(lib.slnlp_axpy(ws.d_hidden0[l].data_ptr(), ws.d_c0.data_ptr(), 1.0, B * H, s), "axpy")
             xin = ws.dec_xin[l].data_ptr()
             dx = ws.d_decx if l == 0 else ws.d_h
-            self._gemm(0, 0, B, D, GH, dg, GH, self._ptr(f"{pre}weight_ih_l{l}"), D, dx.data_ptr(), D)
+            # d(input) of the cell; for l > 0 the input was dropout(h_{l-1}): the mask rides in the epilogue
+            ddrop = (self.p_rnn, rng, 100 + l - 1) if (l > 0 and drop) else None
+            self._gemm(0, 0, B, D, GH, dg, GH, self._ptr(f"{pre}weight_ih_l{l}"), D, dx.data_ptr(), D, drop=ddrop)
             with small():
                 ss = _stream()
                 self._gemm(1, 0, GH, D, B, dg, GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0)
@@ -274,9 +287,6 @@ class RnnEncDecB200(FlatParamModule):
                     self._gemm(1, 0, H, H, B, dst, H, h0, H, gp(f"{pre}weight_hh_l{l}") + 4 * 2 * H * H, H, None, 1.0)
                     check(lib.slnlp_colsum_f32(dg, B, 2 * H, GH, gp(f"{pre}bias_hh_l{l}"), 1.0, ss), "colsum")
                     check(lib.slnlp_colsum_f32(dst, B, H, H, gp(f"{pre}bias_hh_l{l}") + 4 * 2 * H, 1.0, ss), "colsum")
-            if l > 0 and drop:
-                check(lib.slnlp_dropout(dx.data_ptr(), dx.data_ptr(), B * H, self.p_rnn, rng, 100 + l - 1, s),
-                      "dropout")
         # decoder input = [trg_embed[bos] || ctx]
         if self.bos_idx != self.tgt_pad:
             drow = gp("model.trg_embed.weight") + 4 * self.bos_idx * E
@@ -328,7 +338,8 @@ class RnnEncDecB200(FlatParamModule):
                 # d(final states) read in the concatenated layout; for l < L-1 d_seq is the gradient of the DROPPED
                 # output of this layer: the forward's mask is applied while the kernel reads it
                 undrop = l < L - 1 and drop and ws.rnn_fused_dropout
-                ex = RnnExtras(1, None, self.p_rnn if undrop else 0.0, rng if undrop else None, l, 1 if undrop else 0)
+                ex = RnnExtras(1, None, self.p_rnn if undrop else 0.0, rng if undrop else None, l, 1 if undrop else 0,
+                               ws.drop_mask[l].data_ptr() if undrop else None)
                 check(lib.slnlp_rnn_layer_bwd_ex(mode, prec, T, B, H, 2, dg, st, out, self._ptr(f"{pre}weight_hh_l{l}"),
                                                  lp, None, None, ws.d_seq.data_ptr(), ws.d_enc_final[l].data_ptr(), None,
                                                  None, None, ws.carry.data_ptr(), ctypes.byref(ex), s), "rnn_layer_bwd")
@@ -467,11 +478,11 @@ class _Workspace:
         self.B, self.T, self.train = B, T, train
         self.rnn_extras = (os.environ.get("SLNLP_RNN_EXTRAS", "1") != "0" and
                            bool(lib.slnlp_rnn_extras_supported(1 if m.precision == "bf16" else 0, T, B, H, 2)))
-        # the inter-layer dropout inside the recurrent kernels: one Philox block per element and step on the
-        # step-to-step chain.  Hidden by the fp32 kernel's 16 warps; measured a net loss on the tcgen05 kernel
-        # (4 epilogue warps, one per scheduler: the 10 dependent Philox rounds are not hidden): off there
+        # the inter-layer dropout inside the recurrent kernels, from factors generated off the critical path
+        # (Philox in the step loop - ten dependent rounds - was measured a net loss on the tcgen05 kernel, whose
+        # 4 epilogue warps sit one per scheduler)
         env = os.environ.get("SLNLP_RNN_FUSED_DROPOUT")
-        self.rnn_fused_dropout = self.rnn_extras and ((m.precision != "bf16") if env is None else env != "0")
+        self.rnn_fused_dropout = self.rnn_extras and (env is None or env != "0")
         self.f_off = (ctypes.c_int64 * 1)(0)
         self.f_w_src = (ctypes.c_int * 1)(E)
         self.f_rows_src = (ctypes.c_int64 * 1)(m.V_src)
@@ -481,6 +492,7 @@ class _Workspace:
         self.enc_stash = [f(T, B, 2, H) for _ in range(L)]
         self.enc_out = [f(T, B, 2 * H) for _ in range(L)]
         self.enc_filled = f(T, B, 2 * H)
+        self.drop_mask = [f(T, B, 2 * H) for _ in range(L - 1)] if (drop and self.rnn_fused_dropout) else []
         self.enc_xin = [None] + [f(T, B, 2 * H) if drop else self.enc_out[l - 1] for l in range(1, L)]
         self.enc_hfin = [f(2, B, H) for _ in range(L)]
         self.enc_final = f(L, B, 2 * H)
@@ -645,7 +657,10 @@ class FusedTrainStep:
         if not self._grads_clean:        # afterwards the SGD kernel leaves the consumed gradient buffer zeroed
             self.gflat.zero_()
         if m.uses_rng:
-            check(lib.slnlp_rng_advance(m._rng_state().data_ptr(), s), "rng")
+            with m._side_branch(3):      # joined before the first kernel that draws from the stream
+                check(lib.slnlp_rng_advance(m._rng_state().data_ptr(), _stream()), "rng")
+            if not getattr(m, "_joins_rng_lane", False):
+                m._join_lane(3)
         m._run_forward(ws, self.X, self.lengths, self.y)
         check(lib.slnlp_logsoftmax_ce_fused(ws.logits.data_ptr(), self.y.data_ptr(), m.tgt_pad, self.B, m.V_tgt,
                                             ws.logp.data_ptr(), ws.loss.data_ptr(), ws.dlogits.data_ptr(), ws.Vp,
