@@ -137,8 +137,16 @@ def rnn_encdec_forward(sd: Dict[str, torch.Tensor], X, lengths, rnn_type: str,
     ``y`` is not an argument: its values never reach the RNN models' output
     (SURVEY.md section 0 quirk 2).
     """
+    if X.dim() == 3:
+        # factored phonological embedding (SURVEY.md section 8 f4; no reference counterpart): one table per
+        # field - orientation / movement / handshape of both hands - gathered and concatenated, torch.cat of
+        # per-field nn.Embedding being its oracle; a frame is padding when its FIRST field is <pad>
+        fields = X
+        emb = torch.cat([sd[f"model.src_embed.fields.{i}.weight"][fields[..., i]] for i in range(fields.shape[-1])], dim=-1)
+        X = fields[..., 0]
+    else:
+        emb = sd["model.src_embed.weight"][X]                               # bkp:49
     B, T = X.shape
-    emb = sd["model.src_embed.weight"][X]                                   # bkp:49
     enc_out, enc_final = encoder_forward(sd, emb, lengths, rnn_type, num_layers,
                                          pad_fill=float(pad_idx),
                                          dropout_masks=enc_dropout_masks)

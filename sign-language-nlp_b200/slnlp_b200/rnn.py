@@ -55,6 +55,19 @@ class RnnEncDecB200(FlatParamModule):
         self.tgt_pad = tgt_vocab.stoi[PAD_WORD]
         self.bos_idx = tgt_vocab.stoi[BOS_WORD]                  # util.py:8-9 (-> unk = 0)
         self.V_src, self.V_tgt = len(src_vocab), len(tgt_vocab)
+        # factored phonological embedding (a variant the reference does not have - it
+        # joins the six fields into one token before embedding): ``src_field_vocab_sizes`` = rows of one table
+        # per field, ``src_field_widths`` = their widths (sum = embedding_size; default: an even split).  X is
+        # then [B, T, F]; the F gathers and the concat are ONE kernel (K1); a frame is padding when its FIRST
+        # field is <pad>.  state_dict: model.src_embed.fields.{i}.weight.
+        fv = kwargs.get("src_field_vocab_sizes", None)
+        self.field_rows = [int(v) for v in fv] if fv else None
+        if self.field_rows:
+            F = len(self.field_rows)
+            fw = kwargs.get("src_field_widths", None)
+            self.field_widths = [int(w) for w in fw] if fw else [self.E // F + (1 if i < self.E % F else 0) for i in range(F)]
+            assert len(self.field_widths) == F and sum(self.field_widths) == self.E, "field widths must sum to embedding_size"
+            assert all(w % 4 == 0 for w in self.field_widths), "field widths must be multiples of 4 (16-byte rows)"
         self.device = kwargs.get("device", None)
         self.validate_inputs = True
         # weight-gradient kernels on a side stream, next to the next layer's BPTT.  It pays when the
@@ -81,7 +94,10 @@ class RnnEncDecB200(FlatParamModule):
         t_dec = rnn_cls(E + 2 * H, H, L, batch_first=True)
         t_bridge = nn.Linear(2 * H, H, bias=True)
         t_pre = nn.Linear(3 * H + E, H, bias=False)
-        t_src = nn.Embedding(self.V_src, E, padding_idx=self.src_pad)
+        if self.field_rows:
+            t_src_fields = [nn.Embedding(v, w, padding_idx=self.src_pad) for v, w in zip(self.field_rows, self.field_widths)]
+        else:
+            t_src = nn.Embedding(self.V_src, E, padding_idx=self.src_pad)
         t_trg = nn.Embedding(self.V_tgt, E, padding_idx=self.tgt_pad)
         t_gen = nn.Linear(H, self.V_tgt, bias=False)
 
@@ -99,9 +115,12 @@ class RnnEncDecB200(FlatParamModule):
                 segs.append((f"model.decoder.rnn.{kind}_l{l}", getattr(t_dec, f"{kind}_l{l}")))
         segs += [("model.decoder.bridge.weight", t_bridge.weight),
                  ("model.decoder.bridge.bias", t_bridge.bias),
-                 ("model.decoder.pre_output_layer.weight", t_pre.weight),
-                 ("model.src_embed.weight", t_src.weight),
-                 ("model.trg_embed.weight", t_trg.weight),
+                 ("model.decoder.pre_output_layer.weight", t_pre.weight)]
+        src_names = ([f"model.src_embed.fields.{i}.weight" for i in range(len(self.field_rows))] if self.field_rows
+                     else ["model.src_embed.weight"])
+        segs += ([(n, t.weight) for n, t in zip(src_names, t_src_fields)] if self.field_rows
+                 else [("model.src_embed.weight", t_src.weight)])
+        segs += [("model.trg_embed.weight", t_trg.weight),
                  ("model.generator.proj.weight", t_gen.weight)]
         # registration order = the reference's named_parameters() order
         order = []
@@ -112,8 +131,9 @@ class RnnEncDecB200(FlatParamModule):
         order += [n for n, _ in segs if n.startswith("model.decoder.attention")]
         order += [n for n, _ in segs if n.startswith("model.decoder.rnn")]
         order += ["model.decoder.bridge.weight", "model.decoder.bridge.bias",
-                  "model.decoder.pre_output_layer.weight", "model.src_embed.weight",
+                  "model.decoder.pre_output_layer.weight", *src_names,
                   "model.trg_embed.weight", "model.generator.proj.weight"]
+        self._src_names = src_names
         self._register_flat(segs, order, glue_suffix="_reverse")
 
     def _make_workspace(self, B, T, train, bwd):
@@ -129,9 +149,14 @@ class RnnEncDecB200(FlatParamModule):
         B, T = ws.B, ws.T
         s = _stream()
         mode, prec = MODE[self.rnn_type], (1 if self.precision == "bf16" else 0)
-        Xp, lp = X.data_ptr(), lengths.data_ptr()
-        check(lib.slnlp_embed_gather_fwd(self._ptr("model.src_embed.weight"), Xp, ws.emb.data_ptr(), B, T, 1,
+        lp = lengths.data_ptr()
+        check(lib.slnlp_embed_gather_fwd(self._ptr(self._src_names[0]), X.data_ptr(), ws.emb.data_ptr(), B, T, ws.F,
                                          ws.f_off, ws.f_w_src, ws.f_rows_src, 1, 1.0, None, s), "embed")
+        if ws.F > 1:      # the padding mask of the attention: the first field of every frame
+            ws.xmask.copy_(X[..., 0])
+            Xp = ws.xmask.data_ptr()
+        else:
+            Xp = X.data_ptr()
         drop = ws.train and self.p_rnn > 0.0
         rng = self._rng_state().data_ptr() if drop else None
         if drop and ws.rnn_fused_dropout:
@@ -236,7 +261,8 @@ class RnnEncDecB200(FlatParamModule):
         B, T, V = ws.B, ws.T, self.V_tgt
         s = _stream()
         mode, prec = MODE[self.rnn_type], (1 if self.precision == "bf16" else 0)
-        Xp, lp = X.data_ptr(), lengths.data_ptr()
+        lp = lengths.data_ptr()
+        Xp = ws.xmask.data_ptr() if ws.F > 1 else X.data_ptr()      # ws.xmask: filled by this step's forward
         gp = lambda n: self._ptr(n, gflat)
         drop = ws.train and self.p_rnn > 0.0
         rng = self._rng_state().data_ptr() if drop else None
@@ -327,7 +353,7 @@ class RnnEncDecB200(FlatParamModule):
         # encoder BPTT, top down, on the zero-padded encoder output (the 1.0 fill of pad_packed_sequence is a
         # constant and must not enter dW_hh)
         if hook is not None:      # attention + decoder + bridge, and target embedding + generator, are final
-            hook(gflat, off["model.decoder.attention.key_layer.weight"], off["model.src_embed.weight"])
+            hook(gflat, off["model.decoder.attention.key_layer.weight"], off[self._src_names[0]])
             hook(gflat, off["model.trg_embed.weight"], numel)
         pre = "model.encoder.rnn."
         self._join_lane(2)
@@ -365,7 +391,7 @@ class RnnEncDecB200(FlatParamModule):
             else:
                 self._gemm(0, 0, T * B, E, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), E,
                            ws.d_emb.data_ptr(), E, big=True)
-                check(lib.slnlp_embed_gather_bwd(gp("model.src_embed.weight"), Xp, ws.d_emb.data_ptr(), B, T, 1,
+                check(lib.slnlp_embed_gather_bwd(gp(self._src_names[0]), X.data_ptr(), ws.d_emb.data_ptr(), B, T, ws.F,
                                                  ws.f_off, ws.f_w_src, ws.f_rows_src, 1, 1.0, self.src_pad, s),
                       "embed_bwd")
             if not par:       # eager / data-parallel: after the critical-path kernels, same stream
@@ -374,7 +400,7 @@ class RnnEncDecB200(FlatParamModule):
                 nxt = f"{pre}weight_ih_l{l + 1}" if l < L - 1 else "model.decoder.attention.key_layer.weight"
                 hook(gflat, off[f"{pre}weight_ih_l{l}"], off[nxt])
                 if l == 0:
-                    hook(gflat, off["model.src_embed.weight"], off["model.trg_embed.weight"])
+                    hook(gflat, off[self._src_names[0]], off["model.trg_embed.weight"])
         if self.overlap_dw or self.overlap_small:
             self._join_side()
 
@@ -425,11 +451,16 @@ class RnnEncDecB200(FlatParamModule):
     def _check_inputs(self, X, lengths):
         if not (X.is_cuda and lengths.is_cuda):
             raise RuntimeError("slnlp_b200: inputs must be CUDA tensors (no CPU fallback)")
-        if X.dim() != 2 or lengths.dim() != 1 or lengths.numel() != X.shape[0]:
-            raise ValueError("expected X [B,T] and lengths [B]")
+        nd = 3 if self.field_rows else 2
+        if X.dim() != nd or lengths.dim() != 1 or lengths.numel() != X.shape[0]:
+            raise ValueError("expected X [B,T,F] (factored fields) and lengths [B]" if self.field_rows
+                             else "expected X [B,T] and lengths [B]")
+        if self.field_rows and X.shape[2] != len(self.field_rows):
+            raise ValueError(f"expected {len(self.field_rows)} fields per frame, got {X.shape[2]}")
         if self.validate_inputs:
             T = X.shape[1]
-            bad = ((lengths < 1) | (lengths > T)).any() | (X < 0).any() | (X >= self.V_src).any()
+            hi = (torch.tensor(self.field_rows, device=X.device) if self.field_rows else self.V_src)
+            bad = ((lengths < 1) | (lengths > T)).any() | (X < 0).any() | (X >= hi).any()
             if bool(bad):
                 raise ValueError("lengths must be in [1, T] (pack_padded_sequence) and tokens in [0, V_src)")
 
@@ -437,12 +468,12 @@ class RnnEncDecB200(FlatParamModule):
         """Returns log-probabilities [B, V_tgt].  ``y`` is accepted for interface parity;
         its values never reach the output of the RNN models."""
         if not self.batch_first:
-            X = X.t()
+            X = X.transpose(0, 1)
         self._ensure_flat()
         dev = self._flat.device
         X = X.to(dev, torch.int64).contiguous()
         if lengths is None:                                       # util.resolve_lengths
-            lengths = (X != self.src_pad).sum(1)
+            lengths = ((X[..., 0] if self.field_rows else X) != self.src_pad).sum(1)
         lengths = lengths.to(dev, torch.int64).contiguous()
         self._check_inputs(X, lengths)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self._params.values()):
@@ -483,9 +514,18 @@ class _Workspace:
         # 4 epilogue warps sit one per scheduler)
         env = os.environ.get("SLNLP_RNN_FUSED_DROPOUT")
         self.rnn_fused_dropout = self.rnn_extras and (env is None or env != "0")
-        self.f_off = (ctypes.c_int64 * 1)(0)
-        self.f_w_src = (ctypes.c_int * 1)(E)
-        self.f_rows_src = (ctypes.c_int64 * 1)(m.V_src)
+        if m.field_rows:      # factored embedding: F tables back to back in the flat buffer
+            F = self.F = len(m.field_rows)
+            base = m._off[m._src_names[0]]
+            self.f_off = (ctypes.c_int64 * F)(*[m._off[n] - base for n in m._src_names])
+            self.f_w_src = (ctypes.c_int * F)(*m.field_widths)
+            self.f_rows_src = (ctypes.c_int64 * F)(*m.field_rows)
+            self.xmask = torch.empty(B, T, dtype=torch.int64, device=dev)
+        else:
+            self.F = 1
+            self.f_off = (ctypes.c_int64 * 1)(0)
+            self.f_w_src = (ctypes.c_int * 1)(E)
+            self.f_rows_src = (ctypes.c_int64 * 1)(m.V_src)
         drop = train and m.p_rnn > 0
         self.emb = f(T, B, E)
         self.enc_gates = [f(T, B, 2, G, H) for _ in range(L)]
@@ -623,9 +663,10 @@ class FusedTrainStep:
         # static inputs of the captured graph, views of one int64 buffer [X | lengths | y].  (Packing a host
         # batch into one pinned staging buffer + one H2D copy was measured: the extra host-side copies
         # and the buffer-reuse event cost as much as the two H2D launches they save.)
-        BT = batch_size * seq_len
+        nf = len(getattr(module, "field_rows", None) or []) or 1
+        BT = batch_size * seq_len * nf
         self._inputs = torch.empty(BT + 2 * batch_size, dtype=torch.int64, device=dev)
-        self.X = self._inputs[:BT].view(batch_size, seq_len)
+        self.X = self._inputs[:BT].view(batch_size, seq_len, nf) if nf > 1 else self._inputs[:BT].view(batch_size, seq_len)
         self.lengths = self._inputs[BT:BT + batch_size]
         self.y = self._inputs[BT + batch_size:]
         self.X.fill_(module.src_pad); self.lengths.fill_(1); self.y.zero_()
@@ -742,9 +783,10 @@ class InferStep:
         self.m, self.B, self.T = module, batch_size, seq_len
         dev = module._flat.device
         self.ws = module._workspace(batch_size, seq_len, False)
-        BT = batch_size * seq_len
+        nf = len(getattr(module, "field_rows", None) or []) or 1
+        BT = batch_size * seq_len * nf
         self._inputs = torch.empty(BT + 2 * batch_size, dtype=torch.int64, device=dev)
-        self.X = self._inputs[:BT].view(batch_size, seq_len)
+        self.X = self._inputs[:BT].view(batch_size, seq_len, nf) if nf > 1 else self._inputs[:BT].view(batch_size, seq_len)
         self.lengths = self._inputs[BT:BT + batch_size]
         self.y = self._inputs[BT + batch_size:]
         self.X.fill_(module.src_pad); self.lengths.fill_(1); self.y.zero_()

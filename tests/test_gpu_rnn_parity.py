@@ -228,3 +228,56 @@ def test_tensor_core_path_within_bf16_tolerance_of_the_reference(kind, E, H, L, 
     for k in rsd:
         err = float((sd[k].cpu() - rsd[k]).abs().max()) / max(float(rsd[k].abs().max()), 1e-3)
         assert err < BF16_RTOL, k
+
+
+@pytest.mark.parametrize("kind", ["lstm", "gru"])
+def test_factored_six_field_embedding_variant(kind):
+    """the true F = 6 factored phonological embedding as a model variant - one table per
+    field (orientation / movement / handshape, dominant and non-dominant hand), gathered and concatenated by ONE
+    kernel.  No reference counterpart: the oracle is the restatement with torch.cat of per-field embeddings.
+    Forward 1e-5 + identical argmax, then two fused training steps (loss, gradient norm, every weight)."""
+    import model as dropin
+    from oracle import restatement as R
+    from slnlp_b200.phono_fields import FIELD_CARD          # (27, 27, 27, 27, 88, 88)
+    from slnlp_b200.rnn import FusedTrainStep
+    from slnlp_b200.vocab import Vocab
+    B, T, Vt, E, H, L = 9, 11, 13, 48, 32, 2
+    rows = [c + 2 for c in FIELD_CARD]                      # + <unk>, <pad>
+    widths = [8, 4, 8, 4, 16, 8]
+    cls = dropin.EncoderDecoderLSTMAttn if kind == "lstm" else dropin.EncoderDecoderGRUAttn
+    torch.manual_seed(3)
+    m = cls(src_vocab=Vocab(size=max(rows)), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E, hidden_size=H,
+            num_layers=L, dropout=0.0, device=torch.device("cuda"), src_field_vocab_sizes=rows, src_field_widths=widths)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    assert [k for k in sd0 if "src_embed" in k] == [f"model.src_embed.fields.{i}.weight" for i in range(6)]
+    assert [tuple(sd0[f"model.src_embed.fields.{i}.weight"].shape) for i in range(6)] == list(zip(rows, widths))
+    m = m.to(torch.device("cuda"))
+    g = torch.Generator().manual_seed(4)
+    X = torch.stack([torch.randint(2, r, (B, T), generator=g) for r in rows], dim=-1)
+    lengths = torch.randint(1, T + 1, (B,), generator=g)
+    lengths[0] = T
+    for b in range(B):
+        X[b, lengths[b]:] = 1
+    y = torch.randint(2, Vt, (B,), generator=g)
+    want = R.rnn_encdec_forward(sd0, X, lengths, kind, L)
+    m.eval()
+    with torch.no_grad():
+        got = m(X=X.cuda(), y=y.cuda(), lengths=lengths.cuda())
+        got2 = m(X=X.cuda(), y=y.cuda())                    # lengths resolved from the first field's padding
+    assert rel_err(got, want) < FP32_RTOL and torch.equal(got.argmax(1).cpu(), want.argmax(1)) and torch.equal(got, got2)
+    m.train()
+    ts = FusedTrainStep(m, B, T, lr=0.1)
+    sd, bufs = dict(sd0), {}
+    for step in range(2):
+        sd, want_loss, want_norm = R.train_step(sd, bufs, lambda p: R.rnn_encdec_forward(p, X, lengths, kind, L), y, 0.1)
+        loss = ts.step(X.cuda(), y.cuda(), lengths.cuda())
+        assert abs(float(loss[0]) - want_loss) < 2e-5 * abs(want_loss)
+        assert abs(float(ts.grad_norm) - want_norm) < 1e-4 * want_norm
+    got_sd = m.state_dict()
+    for k, v in sd.items():
+        assert rel_err(got_sd[k], v) < 2e-5, k
+    # the padding row of every field table received no gradient
+    for i in range(6):
+        assert torch.equal(got_sd[f"model.src_embed.fields.{i}.weight"][1].cpu(), sd0[f"model.src_embed.fields.{i}.weight"][1])
+    with pytest.raises(ValueError):
+        m(X=X[..., :5].cuda(), y=y.cuda(), lengths=lengths.cuda())

@@ -137,3 +137,24 @@ def test_grid_farm_packs_fits_per_gpu_with_threads(tmp_path):
     with pytest.raises(RuntimeError, match="boom"):
         GridSearchFarm(Boom(), grid, cv=2, scoring=lambda e, X, y: 0.0, backend="inline", n_gpus=1, fits_per_gpu=2,
                        refit=False).fit(X, y)
+
+
+def test_factored_embedding_variant_surface():
+    """F = 6 field tables: parameter names, shapes, adjacency in the flat buffer (one gather
+    kernel walks them), and the usual refusal to compute on the CPU."""
+    rows, widths = [29, 29, 29, 29, 90, 90], [8, 4, 8, 4, 16, 8]
+    m = dropin.EncoderDecoderGRUAttn(src_vocab=Vocab(size=90), tgt_vocab=Vocab(size=7), batch_first=True, embedding_size=48,
+                                     hidden_size=16, num_layers=1, dropout=0.0, device=torch.device("cpu"),
+                                     src_field_vocab_sizes=rows, src_field_widths=widths)
+    names = [n for n, _ in m.named_parameters() if "src_embed" in n]
+    assert names == [f"model.src_embed.fields.{i}.weight" for i in range(6)]
+    assert "model.src_embed.weight" not in dict(m.named_parameters())
+    for i in range(5):
+        a, b = names[i], names[i + 1]
+        assert m._off[b] >= m._off[a] + rows[i] * widths[i] and m._off[b] - (m._off[a] + rows[i] * widths[i]) < 4
+    assert float(dict(m.named_parameters())[names[4]][1].abs().max()) == 0.0      # padding_idx row of every table
+    with pytest.raises(AssertionError):
+        dropin.EncoderDecoderGRUAttn(src_vocab=Vocab(size=90), tgt_vocab=Vocab(size=7), batch_first=True, embedding_size=50,
+                                     hidden_size=16, num_layers=1, dropout=0.0, src_field_vocab_sizes=rows, src_field_widths=widths)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(X=torch.ones(2, 3, 6, dtype=torch.long), y=torch.ones(2, dtype=torch.long), lengths=torch.tensor([3, 3]))
