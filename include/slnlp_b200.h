@@ -87,6 +87,21 @@ int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K,
                     const float* A, int lda, const float* B, int ldb,
                     float* C, int ldc, const float* bias, float beta,
                     float* workspace, int64_t workspace_floats, slnlp_stream_t stream);
+/* The same contraction at data-parallel batch sizes (BASELINE.json configs[3]: the hoisted x W_ih^T of
+ * bkp:114 over T*B = 262,144 rows, and its dX / dW twins) on CTA PAIRS: A and B are bf16 in HBM (row strides
+ * lda / ldb in ELEMENTS, multiples of 8; 16-byte aligned bases), C / bias / beta as above (fp32).  Persistent
+ * 2-CTA clusters, 256 x 256 tiles, tcgen05.mma.cta_group::2 kind::f16 with fp32 accumulators double-buffered
+ * in tensor memory, TMA 128-byte-swizzled operand ring, transposed operands consumed in place as MN-major
+ * tiles.  Any M, N, K > 0 computes correctly; slnlp_gemm_bf16_supported says whether the shape is worth a
+ * 256 x 256 tile (the host keeps smaller products on slnlp_gemm_tf32). */
+int slnlp_gemm_bf16_supported(int transA, int transB, int M, int N, int K);
+int slnlp_gemm_bf16(int transA, int transB, int M, int N, int K,
+                    const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb,
+                    float* C, int ldc, const float* bias, float beta, slnlp_stream_t stream);
+/* dst (bf16) = src (fp32), rows x cols with row strides lds / ldd in elements; transpose != 0 writes
+ * dst[c*rows + r] (dense operands only): the K-major copy of a transposed weight matrix. */
+int slnlp_cast_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols,
+                    int transpose, slnlp_stream_t stream);
 /* out[c] = beta*out[c] + sum_r A[r*lda + c]   (bias gradients) */
 int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
                      slnlp_stream_t stream);

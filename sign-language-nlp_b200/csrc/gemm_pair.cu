@@ -1,0 +1,444 @@
+// The large dense contractions of the tensor-core path (the hoisted x W_ih^T over all timesteps at
+// data-parallel batch sizes, bkp:114, and its dX / dW twins) on CTA PAIRS:
+//
+//   C[M,N] (fp32) = op(A) op(B) + bias + beta*C, A and B bf16 in HBM, fp32 accumulation in TMEM.
+//
+//   * persistent: one 2-CTA cluster per SM pair (74 clusters), tiles of 256 x 256 handed out round-robin,
+//     n fastest, so the clusters of a wave share A panels through L2;
+//   * tcgen05.mma.cta_group::2 kind::f16, M 256 x N 256 x K 16: CTA r of the pair stages rows
+//     [128 r, 128 r + 128) of the A tile and columns [128 r, 128 r + 128) of the B tile - every operand byte
+//     crosses L2 -> shared memory once per PAIR - and holds the [128 x 256] half of the accumulator in
+//     its own tensor memory;
+//   * TMA (cp.async.bulk.tensor, 128-byte swizzle, 64-element k-blocks) into a 6-stage ring; both CTAs'
+//     loads complete on the LEADER's mbarrier (.cta_group::2), the leader's single MMA thread issues for the
+//     pair and hands a stage back to both producers with a multicast tcgen05.commit;
+//   * two accumulator stages (2 x 256 of the 512 TMEM columns): the epilogue warps of both CTAs drain tile i
+//     (tcgen05.ld -> shared-memory transpose -> coalesced rows with bias / beta) while the MMAs of tile i+1 run;
+//   * transposed operands are consumed in place as MN-major tiles (dW = dG^T X needs both), so nothing is
+//     transposed in HBM.
+//
+// Companion kernels: fp32 -> bf16 casts (optionally transposing, for weight matrices).
+#include "tma.cuh"
+
+namespace slnlp {
+
+constexpr int PB_M = 128;                          // A rows per CTA (the pair's tile is 256 tall)
+constexpr int PB_N = 256;                          // tile width; each CTA stages 128 of the B rows
+constexpr int PB_K = 64;                           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int P_STAGES = 6;
+constexpr int P_A_STAGE = PB_M * PB_K * 2;         // 16 KB
+constexpr int P_B_STAGE = (PB_N / 2) * PB_K * 2;   // 16 KB
+constexpr int P_SLD = 33;                          // padded row of the epilogue's transpose tile
+// EG = epilogue warp groups (4 warps each, one per TMEM lane quadrant; group g drains columns [g*256/EG, ...))
+__host__ __device__ constexpr int p_threads(int eg) { return 64 + 128 * eg; }   // producer, MMA, 4*EG epilogue warps
+__host__ __device__ constexpr int p_staging(int eg) { return eg * 4 * 32 * P_SLD * 4; }
+__host__ __device__ constexpr size_t p_smem(int eg) {
+  return (size_t)P_STAGES * (P_A_STAGE + P_B_STAGE) + p_staging(eg) + (2 * P_STAGES + 4) * 8 + 16 + 1024;
+}
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on an mbarrier of either CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once) on the barrier at the same shared-memory offset in BOTH CTAs when the pair's MMAs so far are done
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// c = f32, a = b = bf16, per-operand major bit (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Operand tiles in shared memory (both 128 rows of M resp. N by 64 of K, bf16, 16 KB):
+//   K-major : one TMA box {64 k, 128 rows}; row r at r*128 B, 8-row swizzle groups 1024 B apart (SBO);
+//             an MMA of K = 16 advances 32 B inside the swizzled row;
+//   MN-major: two TMA boxes {64 mn, 64 k} of 8 KB; inside a box k-row kk at kk*128 B, 8-row groups 1024 B
+//             apart (SBO), LBO = 8192 B between the 64-wide mn blocks; an MMA of K = 16 consumes two groups.
+template <bool A_MN, bool B_MN, int EG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(p_threads(EG), 1)
+    gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K,
+                     float* __restrict__ C, int ldc, const float* __restrict__ bias, float beta, int tiles_n, int tiles, int dbg) {
+  constexpr int P_STAGING = p_staging(EG);
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  uint8_t* sA = smem_raw;
+  uint8_t* sB = sA + P_STAGES * P_A_STAGE;
+  float* staging = reinterpret_cast<float*>(sB + P_STAGES * P_B_STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + P_STAGING);
+  uint64_t* empty = full + P_STAGES;
+  uint64_t* tfull = empty + P_STAGES;     // [2] accumulator stage complete (multicast commit)
+  uint64_t* tempty = tfull + 2;           // [2] accumulator stage drained (leader's copy is the live one)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = warp_uniform(), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int nk = (K + PB_K - 1) / PB_K;
+
+  if (warp == 0 && elect_one()) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 8 * EG);       // 4*EG epilogue warps of each CTA
+    }
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // the peer's barriers exist before anything is signalled on them
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < tiles; tile += nclusters) {
+        const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+        const int m0 = mt * (2 * PB_M) + (int)rank * PB_M, n0 = nt * PB_N + (int)rank * (PB_N / 2);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const uint32_t s = it % P_STAGES, round = it / P_STAGES;
+          if (round > 0) mbar_wait(&empty[s], (round - 1) & 1u);
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * (P_A_STAGE + P_B_STAGE));
+          const uint32_t bar = map_to_cta(smem_u32(&full[s]), 0);
+          const int k0 = kb * PB_K;
+          uint8_t* a = sA + s * P_A_STAGE;
+          uint8_t* b = sB + s * P_B_STAGE;
+          if (!A_MN) {
+            tma_load_2d_pair(a, &mapA, bar, k0, m0);
+          } else {
+            tma_load_2d_pair(a, &mapA, bar, m0, k0);
+            tma_load_2d_pair(a + 8192, &mapA, bar, m0 + 64, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d_pair(b, &mapB, bar, k0, n0);
+          } else {
+            tma_load_2d_pair(b, &mapB, bar, n0, k0);
+            tma_load_2d_pair(b + 8192, &mapB, bar, n0 + 64, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * PB_M, PB_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint64_t dA = A_MN ? make_desc_sw128(smem_u32(sA), 8192, 1024, 2) : make_desc_sw128(smem_u32(sA), 16, 1024, 2);
+      const uint64_t dB = B_MN ? make_desc_sw128(smem_u32(sB), 8192, 1024, 2) : make_desc_sw128(smem_u32(sB), 16, 1024, 2);
+      constexpr uint32_t a_step = A_MN ? 2048 : 32, b_step = B_MN ? 2048 : 32;   // bytes per K = 16
+      uint32_t it = 0, tl = 0;
+      for (int tile = cluster_id; tile < tiles; tile += nclusters, ++tl) {
+        const uint32_t as = tl & 1u, use = tl >> 1;
+        if (use > 0) mbar_wait(&tempty[as], (use - 1) & 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem + as * PB_N;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const uint32_t s = it % P_STAGES, round = it / P_STAGES;
+          mbar_wait(&full[s], round & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < PB_K / 16; ++kk)
+              umma_bf16_pair(acc, dA + (uint64_t)((s * P_A_STAGE + kk * a_step) >> 4),
+                             dB + (uint64_t)((s * P_B_STAGE + kk * b_step) >> 4), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            umma_commit_pair(&empty[s]);
+            if (kb == nk - 1) umma_commit_pair(&tfull[as]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // epilogue warps 2..5 own TMEM lane quadrants 2, 3, 0, 1
+    const int q = warp & 3, eg = (warp - 2) >> 2;
+    float* stage = staging + (warp - 2) * 32 * P_SLD;
+    constexpr int CW = PB_N / EG;           // columns of this warp group
+    const uint32_t tempty_leader = map_to_cta(smem_u32(&tempty[0]), 0);
+    uint32_t tl = 0;
+    for (int tile = cluster_id; tile < tiles; tile += nclusters, ++tl) {
+      const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+      const uint32_t as = tl & 1u, use = tl >> 1;
+      const int mrow0 = mt * (2 * PB_M) + (int)rank * PB_M + q * 32, ncol0 = nt * PB_N;
+      mbar_wait(&tfull[as], use & 1u);
+      tc_fence_after();
+      const bool rmw = beta != 0.f;
+#pragma unroll 1
+      for (int c0 = eg * CW; c0 < (eg + 1) * CW; c0 += 32) {
+        if (ncol0 + c0 >= N || dbg == 2) break;
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * PB_N + c0, v);
+#pragma unroll
+        for (int x = 0; x < 32; ++x) stage[lane * P_SLD + x] = v[x];
+        __syncwarp();
+        const int n = ncol0 + c0 + lane;
+        const bool nok = n < N;
+        const float bv = (bias && nok) ? bias[n] : 0.f;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+          float cold[8];
+          if (rmw) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int m = mrow0 + r0 + r;
+              cold[r] = (nok && m < M) ? C[(int64_t)m * ldc + n] : 0.f;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int m = mrow0 + r0 + r;
+            if (nok && m < M && dbg == 0) {
+              float o = stage[(r0 + r) * P_SLD + lane] + bv;
+              if (rmw) o += beta * cold[r];
+              C[(int64_t)m * ldc + n] = o;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // this warp's quarter of the accumulator stage is drained: tell the leader's MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + as * 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // no CTA of the pair frees tensor memory or exits while the other still uses it
+  if (warp == 1) tmem_dealloc_pair(tmem, 512);
+}
+
+// ---------------------------------------------------------------- fp32 -> bf16 casts
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n8) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    reinterpret_cast<uint4*>(dst)[i] = pack8_bf16(v);
+  }
+}
+__global__ void __launch_bounds__(256) cast_bf16_tail_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t lo,
+                                                              int64_t n) {
+  const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+// strided rows: dst[r*ldd + c] = bf16(src[r*lds + c])
+__global__ void __launch_bounds__(256) cast_bf16_rows_kernel(const float* __restrict__ src, int64_t lds, __nv_bfloat16* __restrict__ dst,
+                                                              int64_t ldd, int rows, int cols) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int c4 = cols >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)rows * c4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4;
+    const int c = (int)(i - r * c4) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(src + r * lds + c);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst + r * ldd + c) = pk;
+  }
+}
+// dst[c*rows + r] = bf16(src[r*cols + c]) (weight matrices: a K-major copy of the transposed operand)
+__global__ void __launch_bounds__(256) cast_bf16_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
+                                                                   int cols) {
+  __shared__ float tile[32][33];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < rows && c < cols) ? src[(int64_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (r < rows && c < cols) dst[(int64_t)c * rows + r] = __float2bfloat16_rn(tile[tx][j]);
+  }
+}
+
+// bf16 tensor [d1][d0] (d0 contiguous, row stride ld elements), TMA box {64, b1}, 128-byte swizzle
+static bool tensor_map_bf16(const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b1, CUtensorMap* out) {
+  thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, d0, d1, 2, ld, 0, b1};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  if (((uintptr_t)ptr & 15) || (ld & 7)) return false;
+  const cuuint64_t gdim[2] = {d0, d1};
+  const cuuint64_t gstr[1] = {ld * 2};
+  const cuuint32_t box[2] = {64, b1};
+  const cuuint32_t estr[2] = {1, 1};
+  if (fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return true;
+}
+
+}  // namespace slnlp
+
+using namespace slnlp;
+
+extern "C" int slnlp_cast_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols,
+                               int transpose, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(src && dst && rows >= 0 && cols >= 0, "cast_bf16: bad arguments");
+  if (rows == 0 || cols == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  if (transpose) {
+    SLNLP_CHECK_ARG(lds == cols && ldd == rows && rows < (1 << 30) && cols < (1 << 30), "cast_bf16: transpose needs dense operands");
+    dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
+    launch_pdl(cast_bf16_transpose_kernel, grid, dim3(256), 0, s, src, d, (int)rows, (int)cols);
+    SLNLP_LAUNCH_OK("cast_bf16(transpose)");
+    return 0;
+  }
+  if (lds == cols && ldd == cols && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+    const int64_t n = rows * cols, n8 = n / 8;
+    if (n8 > 0) {
+      const int blocks = (int)std::min<int64_t>((n8 + 255) / 256, (int64_t)sms * 8);
+      launch_pdl(cast_bf16_kernel, dim3(blocks), dim3(256), 0, s, src, d, n8);
+      note_launches(1);
+    }
+    if (n8 * 8 < n) {
+      cast_bf16_tail_kernel<<<1, 256, 0, s>>>(src, d, n8 * 8, n);
+      note_launches(1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("cast_bf16: launch failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  SLNLP_CHECK_ARG(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0 &&
+                      rows < (1 << 30) && cols < (1 << 30),
+                  "cast_bf16: strided form needs cols, lds, ldd multiples of 4 and aligned bases");
+  const int64_t work = rows * (cols / 4);
+  const int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)sms * 8);
+  launch_pdl(cast_bf16_rows_kernel, dim3(blocks), dim3(256), 0, s, src, lds, d, ldd, (int)rows, (int)cols);
+  SLNLP_LAUNCH_OK("cast_bf16(rows)");
+  return 0;
+}
+
+extern "C" int slnlp_gemm_bf16_supported(int transA, int transB, int M, int N, int K) {
+  (void)transA; (void)transB;
+  if (encode_fn() == nullptr) return 0;
+  return (M >= 256 && N >= 128 && K >= 64) ? 1 : 0;
+}
+
+extern "C" int slnlp_gemm_bf16(int transA, int transB, int M, int N, int K, const uint16_t* A, int64_t lda, const uint16_t* B,
+                               int64_t ldb, float* C, int ldc, const float* bias, float beta, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(A && B && C, "gemm_bf16: null pointer");
+  SLNLP_CHECK_ARG(M > 0 && N > 0 && K > 0 && ldc >= N, "gemm_bf16: bad shape M=%d N=%d K=%d ldc=%d", M, N, K, ldc);
+  SLNLP_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N), "gemm_bf16: bad lda/ldb");
+  SLNLP_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && lda % 8 == 0 && ldb % 8 == 0,
+                  "gemm_bf16: operands need 16-byte aligned bases and row strides (multiples of 8 elements)");
+  // A(m,k): transA=0 -> [M rows, K contiguous] (K-major); transA=1 -> stored [K rows, M contiguous] (MN-major)
+  // B(k,n): transB=1 -> stored [N rows, K contiguous] (K-major); transB=0 -> [K rows, N contiguous] (MN-major)
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  CUtensorMap mapA, mapB;
+  const bool okA = a_mn ? tensor_map_bf16(A, M, K, lda, 64, &mapA) : tensor_map_bf16(A, K, M, lda, PB_M, &mapA);
+  const bool okB = b_mn ? tensor_map_bf16(B, N, K, ldb, 64, &mapB) : tensor_map_bf16(B, K, N, ldb, PB_N / 2, &mapB);
+  SLNLP_CHECK_ARG(okA && okB, "gemm_bf16: cuTensorMapEncodeTiled failed");
+  cudaStream_t s = as_stream(stream);
+  const int tiles_m = ceil_div(M, 2 * PB_M), tiles_n = ceil_div(N, PB_N), tiles = tiles_m * tiles_n;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  const int nclusters = std::min(tiles, sms / 2);
+  dim3 grid(2 * nclusters);
+  static int eg_sel = -1, dbg = 0;
+  if (eg_sel < 0) {
+    const char* e = getenv("SLNLP_PAIR_EG");
+    eg_sel = (e && e[0] == '1') ? 1 : 2;
+    const char* d = getenv("SLNLP_PAIR_DBG");
+    dbg = d ? atoi(d) : 0;
+  }
+#define SLNLP_PAIR2(AMN, BMN, EGV)                                                                                       \
+  do {                                                                                                                   \
+    static bool attr = false;                                                                                            \
+    if (!attr) {                                                                                                         \
+      cudaFuncSetAttribute(gemm_pair_kernel<AMN, BMN, EGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem(EGV)); \
+      attr = true;                                                                                                       \
+    }                                                                                                                    \
+    launch_pdl(gemm_pair_kernel<AMN, BMN, EGV>, grid, dim3(p_threads(EGV)), p_smem(EGV), s, mapA, mapB, M, N, K, C, ldc,  \
+               bias, beta, tiles_n, tiles, dbg);                                                                         \
+  } while (0)
+#define SLNLP_PAIR(AMN, BMN)                       \
+  do {                                             \
+    if (eg_sel == 1) SLNLP_PAIR2(AMN, BMN, 1);     \
+    else SLNLP_PAIR2(AMN, BMN, 2);                 \
+  } while (0)
+  if (!a_mn && !b_mn) SLNLP_PAIR(false, false);
+  else if (!a_mn && b_mn) SLNLP_PAIR(false, true);
+  else if (a_mn && !b_mn) SLNLP_PAIR(true, false);
+  else SLNLP_PAIR(true, true);
+#undef SLNLP_PAIR
+#undef SLNLP_PAIR2
+  SLNLP_LAUNCH_OK("gemm_bf16");
+  return 0;
+}

@@ -35,6 +35,9 @@ SIGNATURES = {
     "slnlp_gemm_f32": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],
     "slnlp_gemm_workspace_floats": [],
     "slnlp_gemm_tf32": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],
+    "slnlp_gemm_bf16_supported": [I, I, I, I, I],
+    "slnlp_gemm_bf16": [I, I, I, I, I, P, L, P, L, P, I, P, F, P],
+    "slnlp_cast_bf16": [P, L, P, L, L, L, I, P],
     "slnlp_colsum_f32": [P, I, I, I, P, F, P],
     "slnlp_rnn_layer_fwd": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
     "slnlp_rnn_layer_bwd": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],

@@ -666,3 +666,47 @@ def test_fused_decoder_cell_forward(mode, B, H, D):
     want = torch.empty(B, H, device="cuda")
     L.check(L.lib.slnlp_dropout(h.data_ptr(), want.data_ptr(), B * H, 0.3, rng.data_ptr(), 101, S()))
     assert torch.equal(hd, want)
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(512, 512, 256), (1000, 700, 1000), (4096, 1024, 520), (300, 136, 72)])
+def test_gemm_bf16_cta_pair(tA, tB, M, N, K):
+    """CTA-pair (tcgen05 cta_group::2) bf16 GEMM vs fp64 on the bf16-rounded operands (tight: tile addressing,
+    both operand majors, the peer CTA's half tiles, ragged edges in M, N and K, several tiles per cluster, both
+    accumulator stages) and vs the exact product (the 2e-2 budget of the tensor-core path)."""
+    from helpers import BF16_RTOL
+    L = _lib()
+    ldA, ldB = ((M if tA else K) + 7) // 8 * 8 + 8, ((K if tB else N) + 7) // 8 * 8      # padded leading dimensions
+    Af = cuda(*((K, ldA) if tA else (M, ldA)), seed=81)
+    Bf = cuda(*((N, ldB) if tB else (K, ldB)), seed=82)
+    Ab, Bb = torch.empty_like(Af, dtype=torch.bfloat16), torch.empty_like(Bf, dtype=torch.bfloat16)
+    for src, dst in ((Af, Ab), (Bf, Bb)):
+        L.check(L.lib.slnlp_cast_bf16(src.data_ptr(), src.shape[1], dst.data_ptr(), dst.shape[1], src.shape[0], src.shape[1], 0, S()))
+        assert torch.equal(dst, src.to(torch.bfloat16))               # round-to-nearest-even, like torch
+    A = Af[:, :(M if tA else K)]
+    B = Bf[:, :(K if tB else N)]
+    bias, C0 = cuda(N, seed=83), cuda(M, N, seed=84)
+    for beta, bs in ((0.5, bias), (0.0, None), (1.0, None)):
+        C = C0.clone()
+        L.check(L.lib.slnlp_gemm_bf16(tA, tB, M, N, K, Ab.data_ptr(), ldA, Bb.data_ptr(), ldB, C.data_ptr(), N,
+                                      bs.data_ptr() if bs is not None else None, beta, S()))
+        opA, opB = (A.t() if tA else A), (B.t() if tB else B)
+        rb = lambda x: x.to(torch.bfloat16).double()
+        extra = (bias.double() if bs is not None else 0.0) + beta * C0.double()
+        assert rel_err(C, rb(opA) @ rb(opB) + extra) < 2e-5
+        assert rel_err(C, opA.double() @ opB.double() + extra) < BF16_RTOL
+
+
+def test_cast_bf16_forms():
+    """fp32 -> bf16 copies: dense, strided rows, transposed (K-major copies of weight matrices)."""
+    L = _lib()
+    x = cuda(37, 52, seed=85)
+    d = torch.empty(37 * 52, dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib.slnlp_cast_bf16(x.data_ptr(), 52, d.data_ptr(), 52, 37, 52, 0, S()))
+    assert torch.equal(d.view(37, 52), x.to(torch.bfloat16))
+    d2 = torch.zeros(37, 64, dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib.slnlp_cast_bf16(x.data_ptr() + 4 * 4, 52, d2.data_ptr(), 64, 37, 40, 0, S()))
+    assert torch.equal(d2[:, :40], x[:, 4:44].to(torch.bfloat16)) and float(d2[:, 40:].abs().max()) == 0.0
+    d3 = torch.empty(52, 37, dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib.slnlp_cast_bf16(x.data_ptr(), 52, d3.data_ptr(), 37, 37, 52, 1, S()))
+    assert torch.equal(d3, x.t().contiguous().to(torch.bfloat16))
