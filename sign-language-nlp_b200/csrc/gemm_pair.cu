@@ -113,7 +113,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, i
 template <bool A_MN, bool B_MN, int EG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(p_threads(EG), 1)
     gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K,
-                     float* __restrict__ C, int ldc, const float* __restrict__ bias, float beta, int tiles_n, int tiles, int dbg) {
+                     float* __restrict__ C, int ldc, const float* __restrict__ bias, float beta, int tiles_n, int tiles_mn, int tiles,
+                     int kb_split, int dbg) {
   constexpr int P_STAGING = p_staging(EG);
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -156,9 +157,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(p_threads(EG), 1)
     if (elect_one()) {
       uint32_t it = 0;
       for (int tile = cluster_id; tile < tiles; tile += nclusters) {
-        const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+        const int sp = tile / tiles_mn, t2 = tile - sp * tiles_mn;
+        const int mt = t2 / tiles_n, nt = t2 - mt * tiles_n;
         const int m0 = mt * (2 * PB_M) + (int)rank * PB_M, n0 = nt * PB_N + (int)rank * (PB_N / 2);
-        for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int kb0 = sp * kb_split, kb1 = min(nk, kb0 + kb_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % P_STAGES, round = it / P_STAGES;
           if (round > 0) mbar_wait(&empty[s], (round - 1) & 1u);
           if (rank == 0) mbar_expect_tx(&full[s], 2 * (P_A_STAGE + P_B_STAGE));
@@ -193,7 +196,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(p_threads(EG), 1)
         if (use > 0) mbar_wait(&tempty[as], (use - 1) & 1u);
         tc_fence_after();
         const uint32_t acc = tmem + as * PB_N;
-        for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int kb0 = (tile / tiles_mn) * kb_split, kb1 = min(nk, kb0 + kb_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % P_STAGES, round = it / P_STAGES;
           mbar_wait(&full[s], round & 1u);
           tc_fence_after();
@@ -201,9 +205,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(p_threads(EG), 1)
 #pragma unroll
             for (int kk = 0; kk < PB_K / 16; ++kk)
               umma_bf16_pair(acc, dA + (uint64_t)((s * P_A_STAGE + kk * a_step) >> 4),
-                             dB + (uint64_t)((s * P_B_STAGE + kk * b_step) >> 4), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                             dB + (uint64_t)((s * P_B_STAGE + kk * b_step) >> 4), idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
             umma_commit_pair(&empty[s]);
-            if (kb == nk - 1) umma_commit_pair(&tfull[as]);
+            if (kb == kb1 - 1) umma_commit_pair(&tfull[as]);
           }
           __syncwarp();
         }
@@ -217,12 +221,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(p_threads(EG), 1)
     const uint32_t tempty_leader = map_to_cta(smem_u32(&tempty[0]), 0);
     uint32_t tl = 0;
     for (int tile = cluster_id; tile < tiles; tile += nclusters, ++tl) {
-      const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+      const int t2 = tile % tiles_mn;
+      const int mt = t2 / tiles_n, nt = t2 - mt * tiles_n;
       const uint32_t as = tl & 1u, use = tl >> 1;
       const int mrow0 = mt * (2 * PB_M) + (int)rank * PB_M + q * 32, ncol0 = nt * PB_N;
       mbar_wait(&tfull[as], use & 1u);
       tc_fence_after();
-      const bool rmw = beta != 0.f;
+      const bool split = tiles > tiles_mn;     // K-slices of a C += A B accumulation add in place (red.global.add)
+      const bool rmw = beta != 0.f && !split;
 #pragma unroll 1
       for (int c0 = eg * CW; c0 < (eg + 1) * CW; c0 += 32) {
         if (ncol0 + c0 >= N || dbg == 2) break;
@@ -250,7 +256,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(p_threads(EG), 1)
             if (nok && m < M && dbg == 0) {
               float o = stage[(r0 + r) * P_SLD + lane] + bv;
               if (rmw) o += beta * cold[r];
-              C[(int64_t)m * ldc + n] = o;
+              if (split) atomicAdd(C + (int64_t)m * ldc + n, o);
+              else C[(int64_t)m * ldc + n] = o;
             }
           }
         }
@@ -407,8 +414,24 @@ extern "C" int slnlp_gemm_bf16(int transA, int transB, int M, int N, int K, cons
   const bool okB = b_mn ? tensor_map_bf16(B, N, K, ldb, 64, &mapB) : tensor_map_bf16(B, K, N, ldb, PB_N / 2, &mapB);
   SLNLP_CHECK_ARG(okA && okB, "gemm_bf16: cuTensorMapEncodeTiled failed");
   cudaStream_t s = as_stream(stream);
-  const int tiles_m = ceil_div(M, 2 * PB_M), tiles_n = ceil_div(N, PB_N), tiles = tiles_m * tiles_n;
+  const int tiles_m = ceil_div(M, 2 * PB_M), tiles_n = ceil_div(N, PB_N), tiles_mn = tiles_m * tiles_n;
   const int sms = sm_count() > 0 ? sm_count() : 148;
+  // few output tiles and a long K (dW_hh = dG^T h over K = (T-1) B): K-slices on otherwise idle clusters add
+  // into C in place.  Only for gradient accumulations (beta = 1, no bias); fp32 summation order then varies
+  // from run to run, like the tf32 kernel's split-K (SLNLP_SPLITK_ATOMIC=0 turns both off)
+  const int nk = ceil_div(K, PB_K);
+  int splits = 1;
+  if (beta == 1.f && !bias && tiles_mn <= sms / 4 && nk >= 64) {
+    static int use_atomic = -1;
+    if (use_atomic < 0) {
+      const char* e = getenv("SLNLP_SPLITK_ATOMIC");
+      use_atomic = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_atomic) splits = std::max(1, std::min((sms / 2) / tiles_mn, nk / 16));
+  }
+  const int kb_split = ceil_div(nk, splits);
+  splits = ceil_div(nk, kb_split);
+  const int tiles = tiles_mn * splits;
   const int nclusters = std::min(tiles, sms / 2);
   dim3 grid(2 * nclusters);
   static int eg_sel = -1, dbg = 0;
@@ -426,7 +449,7 @@ extern "C" int slnlp_gemm_bf16(int transA, int transB, int M, int N, int K, cons
       attr = true;                                                                                                       \
     }                                                                                                                    \
     launch_pdl(gemm_pair_kernel<AMN, BMN, EGV>, grid, dim3(p_threads(EGV)), p_smem(EGV), s, mapA, mapB, M, N, K, C, ldc,  \
-               bias, beta, tiles_n, tiles, dbg);                                                                         \
+               bias, beta, tiles_n, tiles_mn, tiles, kb_split, dbg);                                                                         \
   } while (0)
 #define SLNLP_PAIR(AMN, BMN)                       \
   do {                                             \

@@ -224,6 +224,23 @@ class FlatParamModule(nn.Module):
             assert ldc == N
             check(lib.slnlp_dropout(C, C, M * N, drop[0], drop[1], drop[2], _stream()), "dropout")
 
+    # ---- CTA-pair bf16 GEMM (gemm_pair.cu): the [T*B]-row contractions at data-parallel batch sizes
+    @staticmethod
+    def _pair_ok(M, N, K):
+        """Worth a 256 x 256 pair tile: at least ~two waves of tiles (or a long-K accumulation) and a K that
+        amortises the accumulator drain."""
+        if _os.environ.get("SLNLP_PAIR", "1") == "0" or M % 8 or N % 8 or K % 8:
+            return False
+        tiles = ((M + 255) // 256) * ((N + 255) // 256)
+        return bool(lib.slnlp_gemm_bf16_supported(0, 0, M, N, K)) and K >= 256 and (tiles >= 148 or K >= 16384)
+
+    def _cast_bf16(self, src_ptr, lds, dst, rows, cols, ldd=None):
+        check(lib.slnlp_cast_bf16(src_ptr, lds, dst.data_ptr(), cols if ldd is None else ldd, rows, cols, 0, _stream()),
+              "cast_bf16")
+
+    def _gemm_bf16(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0):
+        check(lib.slnlp_gemm_bf16(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, _stream()), "gemm_bf16")
+
     def _gemm_ws(self):
         """Split-K scratch of the GEMMs of this module: one buffer per stream the module launches on
         (the main stream and the weight-gradient side lanes never share partials)."""

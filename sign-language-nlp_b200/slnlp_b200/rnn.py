@@ -171,8 +171,16 @@ class RnnEncDecB200(FlatParamModule):
             D = E if l == 0 else 2 * H
             xin = ws.emb if l == 0 else ws.enc_xin[l]
             pre = f"model.encoder.rnn."
-            self._gemm(0, 1, T * B, 2 * G * H, D, xin.data_ptr(), D, self._ptr(f"{pre}weight_ih_l{l}"), D,
-                       ws.enc_gates[l].data_ptr(), 2 * G * H, self._ptr(f"{pre}bias_ih_l{l}"), 0.0, big=True)
+            if ws.pair[l]:
+                # data-parallel batch sizes: bf16 copies of the layer input (kept for dW_ih) and of W_ih (serves
+                # the forward as a K-major and dX as an MN-major operand), CTA-pair tcgen05 GEMM
+                self._cast_bf16(xin.data_ptr(), D, ws.xin_bf[l], T * B, D)
+                self._cast_bf16(self._ptr(f"{pre}weight_ih_l{l}"), D, ws.w_ih_bf[l], 2 * G * H, D)
+                self._gemm_bf16(0, 1, T * B, 2 * G * H, D, ws.xin_bf[l].data_ptr(), D, ws.w_ih_bf[l].data_ptr(), D,
+                                ws.enc_gates[l].data_ptr(), 2 * G * H, self._ptr(f"{pre}bias_ih_l{l}"))
+            else:
+                self._gemm(0, 1, T * B, 2 * G * H, D, xin.data_ptr(), D, self._ptr(f"{pre}weight_ih_l{l}"), D,
+                           ws.enc_gates[l].data_ptr(), 2 * G * H, self._ptr(f"{pre}bias_ih_l{l}"), 0.0, big=True)
             if l == 0:
                 self._join_lane(3)        # rng advanced (FusedTrainStep) and dropout factors ready
             if ws.rnn_extras:
@@ -379,18 +387,29 @@ class RnnEncDecB200(FlatParamModule):
             # HERE, right behind the BPTT kernel that produced their operand (forking after the dx GEMM would make
             # them wait for it: the last layer's weight gradients then trail the whole step)
             par = self.overlap_dw and hook is None and torch.cuda.is_current_stream_capturing()
+            if ws.pair[l]:
+                # bf16 copies of d(pre-activations) (A of dX, dW_ih, dW_hh) and of the layer output (B of dW_hh)
+                self._cast_bf16(dg, 2 * GH, ws.dg_bf[l], T * B, 2 * GH)
+                if mode == 0:
+                    self._cast_bf16(out, 2 * H, ws.out_bf[l], T * B, 2 * H)
             if par:
                 self._encoder_weight_grads(ws, l, gp, parallel=True)
             # the gradient the next (lower) layer's BPTT is waiting for
+            dx_pair = ws.pair[l] and self._pair_ok(T * B, D, 2 * GH)
+            if dx_pair:
+                self._gemm_bf16(0, 0, T * B, D, 2 * GH, ws.dg_bf[l].data_ptr(), 2 * GH, ws.w_ih_bf[l].data_ptr(), D,
+                                (ws.d_seq if l > 0 else ws.d_emb).data_ptr(), D)
             if l > 0:
-                self._gemm(0, 0, T * B, D, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), D,
-                           ws.d_seq.data_ptr(), D, big=True)
+                if not dx_pair:
+                    self._gemm(0, 0, T * B, D, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), D,
+                               ws.d_seq.data_ptr(), D, big=True)
                 if drop and not ws.rnn_fused_dropout:
                     check(lib.slnlp_dropout(ws.d_seq.data_ptr(), ws.d_seq.data_ptr(), T * B * D, self.p_rnn,
                                             rng, l - 1, s), "dropout")
             else:
-                self._gemm(0, 0, T * B, E, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), E,
-                           ws.d_emb.data_ptr(), E, big=True)
+                if not dx_pair:
+                    self._gemm(0, 0, T * B, E, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), E,
+                               ws.d_emb.data_ptr(), E, big=True)
                 check(lib.slnlp_embed_gather_bwd(gp(self._src_names[0]), X.data_ptr(), ws.d_emb.data_ptr(), B, T, ws.F,
                                                  ws.f_off, ws.f_w_src, ws.f_rows_src, 1, 1.0, self.src_pad, s),
                       "embed_bwd")
@@ -416,8 +435,13 @@ class RnnEncDecB200(FlatParamModule):
         dg, st, out = ws.enc_gates[l].data_ptr(), ws.enc_stash[l].data_ptr(), ws.enc_out[l].data_ptr()
         xin = (ws.emb if l == 0 else ws.enc_xin[l]).data_ptr()
         lane = (lambda i: self._side_branch(i)) if parallel else (lambda i: contextlib.nullcontext())
+        pair = ws.pair[l]
         with lane(0):
-            self._gemm(1, 0, 2 * GH, D, T * B, dg, 2 * GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0, big=True)
+            if pair and self._pair_ok(2 * GH, D, T * B):
+                self._gemm_bf16(1, 0, 2 * GH, D, T * B, ws.dg_bf[l].data_ptr(), 2 * GH, ws.xin_bf[l].data_ptr(), D,
+                                gp(f"{pre}weight_ih_l{l}"), D, None, 1.0)
+            else:
+                self._gemm(1, 0, 2 * GH, D, T * B, dg, 2 * GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0, big=True)
         with lane(3):
             s = _stream()
             check(lib.slnlp_colsum_f32(dg, T * B, 2 * GH, 2 * GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
@@ -438,7 +462,10 @@ class RnnEncDecB200(FlatParamModule):
             if K <= 0:
                 continue
             with lane(1 + d):
-                if mode == 0:
+                if mode == 0 and pair and self._pair_ok(GH, H, K):
+                    self._gemm_bf16(1, 0, GH, H, K, ws.dg_bf[l].data_ptr() + 2 * (a_row * 2 * GH + d * GH), 2 * GH,
+                                    ws.out_bf[l].data_ptr() + 2 * (b_row * 2 * H + d * H), 2 * H, gw, H, None, 1.0)
+                elif mode == 0:
                     self._gemm(1, 0, GH, H, K, dg + 4 * (a_row * 2 * GH + d * GH), 2 * GH, hb, 2 * H,
                                gw, H, None, 1.0, big=True)
                 else:
@@ -527,6 +554,13 @@ class _Workspace:
             self.f_w_src = (ctypes.c_int * 1)(E)
             self.f_rows_src = (ctypes.c_int64 * 1)(m.V_src)
         drop = train and m.p_rnn > 0
+        # CTA-pair bf16 GEMM for the hoisted projections (and their dX / dW twins) where T*B rows are worth it
+        bf = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)
+        self.pair = [m.precision == "bf16" and m._pair_ok(T * B, 2 * G * H, E if l == 0 else 2 * H) for l in range(L)]
+        self.xin_bf = [bf(T * B, E if l == 0 else 2 * H) if self.pair[l] else None for l in range(L)]
+        self.w_ih_bf = [bf(2 * G * H, E if l == 0 else 2 * H) if self.pair[l] else None for l in range(L)]
+        self.dg_bf = [bf(T * B, 2 * G * H) if (self.pair[l] and bwd) else None for l in range(L)]
+        self.out_bf = [bf(T * B, 2 * H) if (self.pair[l] and bwd and G == 4) else None for l in range(L)]
         self.emb = f(T, B, E)
         self.enc_gates = [f(T, B, 2, G, H) for _ in range(L)]
         self.enc_stash = [f(T, B, 2, H) for _ in range(L)]

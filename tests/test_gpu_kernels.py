@@ -669,11 +669,11 @@ def test_fused_decoder_cell_forward(mode, B, H, D):
 
 
 @pytest.mark.parametrize("tA,tB", [(0, 1), (0, 0), (1, 0), (1, 1)])
-@pytest.mark.parametrize("M,N,K", [(512, 512, 256), (1000, 700, 1000), (4096, 1024, 520), (300, 136, 72)])
+@pytest.mark.parametrize("M,N,K", [(512, 512, 256), (1000, 700, 1000), (4096, 1024, 520), (300, 136, 72), (512, 256, 8200)])
 def test_gemm_bf16_cta_pair(tA, tB, M, N, K):
     """CTA-pair (tcgen05 cta_group::2) bf16 GEMM vs fp64 on the bf16-rounded operands (tight: tile addressing,
     both operand majors, the peer CTA's half tiles, ragged edges in M, N and K, several tiles per cluster, both
-    accumulator stages) and vs the exact product (the 2e-2 budget of the tensor-core path)."""
+    accumulator stages, in-place split-K of the long-K accumulation) and vs the exact product (the 2e-2 budget of the tensor-core path)."""
     from helpers import BF16_RTOL
     L = _lib()
     ldA, ldB = ((M if tA else K) + 7) // 8 * 8 + 8, ((K if tB else N) + 7) // 8 * 8      # padded leading dimensions
