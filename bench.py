@@ -450,6 +450,8 @@ def dominant_kernel_roofline(m, ts, w, B, peaks, sustained=False):
                                            ts.lengths.data_ptr(), None, None, ws.enc_out[0].data_ptr(),
                                            ws.enc_stash[0].data_ptr(), ws.enc_hfin[0].data_ptr(),
                                            torch.cuda.current_stream().cuda_stream))
+    if getattr(ws, "bf_step", False):
+        return _large_batch_rooflines(m, ts, w, B, peaks)
     ws.enc_gates[0].normal_(0, 0.5)
     c0 = lib.slnlp_launch_count()
     call()
@@ -471,6 +473,48 @@ def dominant_kernel_roofline(m, ts, w, B, peaks, sustained=False):
             "note": ("one launch per timestep: [B,H]x[H,4H] per direction, tensor-bound at this batch" if launches > 1 else
                      "at batch 50 the 2*L*T strictly dependent recurrence steps, not FLOPs or bytes, bound this kernel "
                      "(SURVEY.md 8d): read us_per_timestep; the HBM-bound hoisted GEMM is under roofline_gemm")}
+
+
+def _large_batch_rooflines(m, ts, w, B, peaks):
+    """Data-parallel batch sizes (cfg4): the recurrence runs as one persistent CTA-pair kernel launch per timestep
+    (rnn_step_pair.cu) whose epilogue moves 46 B per (sequence, unit, direction) - hoisted projection and c_{t-1} in,
+    activated gates, c_t, h_t (fp32 + bf16) out: HBM-bound.  The hoisted projection runs on the CTA-pair bf16 GEMM
+    (gemm_pair.cu): tensor-bound, reported under `gemm`."""
+    import torch
+    from slnlp_b200 import _lib
+    lib = _lib.lib
+    T, H, E = w["T"], w["H"], w["E"]
+    ws = ts.ws
+    S = lambda: torch.cuda.current_stream().cuda_stream
+    ws.enc_gates[0].normal_(0, 0.5)
+
+    def call():
+        _lib.check(lib.slnlp_rnn_layer_fwd_bf16(0, T, B, H, 2, ws.enc_gates[0].data_ptr(), ws.w_hh_bf[0].data_ptr(),
+                                                m._ptr("model.encoder.rnn.bias_hh_l0"), ts.lengths.data_ptr(),
+                                                ws.enc_out[0].data_ptr(), ws.out_bf[0].data_ptr(), ws.enc_stash[0].data_ptr(),
+                                                ws.enc_hfin[0].data_ptr(), S()))
+    layer_s = _time_graph(call, reps=3)
+    per_step = layer_s / T
+    by = 46.0 * B * H * 2
+    flops = 2.0 * B * (4 * H) * H * 2
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    rec = {"kernel": "lstm_step_fwd_pair_kernel", "bound": "hbm", "achieved": by / per_step / 1e9, "unit": "GB/s", "peak": hbm,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s", "frac": by / per_step / 1e9 / hbm,
+           "us_per_launch": per_step * 1e6, "launches_per_layer": T, "us_per_timestep": per_step * 1e6,
+           "bytes_per_launch": by, "tflops": flops / per_step / 1e12, "traffic": _ncu_traffic("lstm_step_fwd_pair_kernel"),
+           "note": "one persistent CTA-pair launch per timestep; algorithmic bytes 46 B per (sequence, unit, direction): "
+                   "16 hoisted projection + 4 c_{t-1} in, 16 activated gates + 4 c_t + 4 h_t + 2 h_t(bf16) out"}
+    M, N, K = T * B, 8 * H, E
+    xb, wb, out = ws.xin_bf[0], ws.w_ih_bf[0], ws.enc_gates[0]
+    sec = _time_graph(lambda: _lib.check(lib.slnlp_gemm_bf16(0, 1, M, N, K, xb.data_ptr(), K, wb.data_ptr(), K, out.data_ptr(), N,
+                                                              None, 0.0, S())), reps=3)
+    tf = peaks.get("bf16_tflops_sustained", 1370.0)
+    rec["gemm"] = {"kernel": f"gemm_pair_kernel [{M}x{K}]x[{K}x{N}]", "bound": "tensor", "achieved": 2.0 * M * N * K / sec / 1e12,
+                   "unit": "TFLOP/s", "peak": tf, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                   "frac": 2.0 * M * N * K / sec / 1e12 / tf, "us_per_launch": sec * 1e6,
+                   "note": "hoisted x W_ih^T of encoder layer 0, bf16 operands, CTA pairs (tcgen05 cta_group::2); the fp32 C "
+                           "write (M*N*4 bytes) shares L2 bandwidth with the operand tiles"}
+    return rec
 
 
 # ---------------------------------------------------------------- sub-records

@@ -102,6 +102,14 @@ int slnlp_gemm_bf16(int transA, int transB, int M, int N, int K,
  * dst[c*rows + r] (dense operands only): the K-major copy of a transposed weight matrix. */
 int slnlp_cast_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols,
                     int transpose, slnlp_stream_t stream);
+/* y (bf16) = dropout(x): the mask slnlp_dropout(site) draws, written as the bf16 operand the next layer's
+ * CTA-pair GEMM reads (nn.LSTM inter-layer dropout, bkp:100, at data-parallel batch sizes). */
+int slnlp_dropout_bf16(const float* x, uint16_t* y, int64_t n, float p, const uint64_t* rng, uint32_t site,
+                       slnlp_stream_t stream);
+/* slnlp_colsum_f32 over a bf16 matrix (the bf16 d(pre-activations) of the large-batch path); cols and lda
+ * multiples of 4. */
+int slnlp_colsum_bf16(const uint16_t* A, int rows, int cols, int64_t lda, float* out, float beta,
+                      slnlp_stream_t stream);
 /* out[c] = beta*out[c] + sum_r A[r*lda + c]   (bias gradients) */
 int slnlp_colsum_f32(const float* A, int rows, int cols, int lda, float* out, float beta,
                      slnlp_stream_t stream);
@@ -189,6 +197,25 @@ int slnlp_rnn_layer_bwd_ex(int mode, int precision, int T, int B, int H, int ndi
                            const float* dout, const float* dh_final, const float* dc_final,
                            float* dh0, float* dc0, float* carry, const slnlp_rnn_extras* extras,
                            slnlp_stream_t stream);
+
+/* The same recurrence with bf16 OPERANDS for the per-step family (batches beyond the persistent / cluster
+ * kernels' reach, BASELINE.json configs[3]: batch 4096, H 512; nn.LSTM recurrence bkp:95-123): h_{t-1} is read
+ * from out_bf - a bf16 copy [T][B][ndir*H] of `out` that the forward kernels write next to the fp32 one - and
+ * W_hh from a bf16 copy (slnlp_cast_bf16), through tcgen05.mma kind::f16; everything else (hoisted
+ * projection, gates, stash, h_final [ndir][B][H]) is fp32 exactly as in slnlp_rnn_layer_fwd.  Zero initial state
+ * only.  The backward (LSTM only) reads d(pre-activations)_{t+1} from dg_bf, a bf16 copy [T][B][ndir*G*H] it
+ * writes next to the in-place fp32 one (the dX / dW GEMMs read it too), and W_hh^T from w_hhT_bf
+ * [ndir][H][G*H] (slnlp_cast_bf16 with transpose); write_f32 = 0 lets a kernel skip the fp32 in-place copy when every
+ * consumer of d(pre-activations) reads dg_bf.  slnlp_rnn_bf16_step_supported: 1 where this family is
+ * the right one (LSTM, B > 256, H a multiple of 128). */
+int slnlp_rnn_bf16_step_supported(int mode, int T, int B, int H, int ndir);
+int slnlp_rnn_layer_fwd_bf16(int mode, int T, int B, int H, int ndir, float* gates, const uint16_t* w_hh_bf,
+                             const float* b_hh, const int64_t* lengths, float* out, uint16_t* out_bf, float* stash,
+                             float* h_final, slnlp_stream_t stream);
+int slnlp_rnn_layer_bwd_bf16(int mode, int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, float* stash,
+                             const float* out, const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout,
+                             const float* dh_final, const float* dc_final, float* carry, int write_f32,
+                             slnlp_stream_t stream);
 /* pad_packed_sequence(padding_value) on the top layer (bkp:120-123): rows t >= len
  * of x [T,B,W] are set to `value` (1.0 going forward, 0.0 before BPTT). */
 int slnlp_pad_fill(float* x, const int64_t* lengths, int T, int B, int W, float value,

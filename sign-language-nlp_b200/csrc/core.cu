@@ -447,6 +447,19 @@ __global__ void __launch_bounds__(256) concat_dirs_kernel(const float* __restric
   pdl_wait();
   pdl_launch_dependents();
   const int64_t n = (int64_t)ndir * B * H;
+  if (n < (1ll << 31) && (H & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    // 32-bit index arithmetic, float4 rows (64-bit div / mod per element made this 260 us at B 4096 x H 512)
+    const uint32_t h4 = (uint32_t)H >> 2, n4 = (uint32_t)(n >> 2);
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      const uint32_t row = i / h4, k = i - row * h4;      // row = d * B + b
+      const uint32_t d = row / (uint32_t)B, b = row - d * (uint32_t)B;
+      const uint32_t j = (b * (uint32_t)ndir + d) * h4 + k;
+      if (inverse) d4[i] = s4[j]; else d4[j] = s4[i];
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % H);

@@ -18,7 +18,7 @@
 //     transposed in HBM.
 //
 // Companion kernels: fp32 -> bf16 casts (optionally transposing, for weight matrices).
-#include "tma.cuh"
+#include "pair.cuh"
 
 namespace slnlp {
 
@@ -34,75 +34,6 @@ __host__ __device__ constexpr int p_threads(int eg) { return 64 + 128 * eg; }   
 __host__ __device__ constexpr int p_staging(int eg) { return eg * 4 * 32 * P_SLD * 4; }
 __host__ __device__ constexpr size_t p_smem(int eg) {
   return (size_t)P_STAGES * (P_A_STAGE + P_B_STAGE) + p_staging(eg) + (2 * P_STAGES + 4) * 8 + 16 + 1024;
-}
-
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load whose completion is signalled on an mbarrier of either CTA of the pair
-__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives (once) on the barrier at the same shared-memory offset in BOTH CTAs when the pair's MMAs so far are done
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-// c = f32, a = b = bf16, per-operand major bit (0 = K-major, 1 = MN-major)
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // Operand tiles in shared memory (both 128 rows of M resp. N by 64 of K, bf16, 16 KB):
@@ -324,30 +255,6 @@ __global__ void __launch_bounds__(256) cast_bf16_transpose_kernel(const float* _
     const int c = c0 + j, r = r0 + tx;
     if (r < rows && c < cols) dst[(int64_t)c * rows + r] = __float2bfloat16_rn(tile[tx][j]);
   }
-}
-
-// bf16 tensor [d1][d0] (d0 contiguous, row stride ld elements), TMA box {64, b1}, 128-byte swizzle
-static bool tensor_map_bf16(const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b1, CUtensorMap* out) {
-  thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  const MapKey key{ptr, d0, d1, 2, ld, 0, b1};
-  auto it = cache.find(key);
-  if (it != cache.end()) {
-    *out = it->second;
-    return true;
-  }
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  if (((uintptr_t)ptr & 15) || (ld & 7)) return false;
-  const cuuint64_t gdim[2] = {d0, d1};
-  const cuuint64_t gstr[1] = {ld * 2};
-  const cuuint32_t box[2] = {64, b1};
-  const cuuint32_t estr[2] = {1, 1};
-  if (fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return false;
-  if (cache.size() > 8192) cache.clear();
-  cache.emplace(key, *out);
-  return true;
 }
 
 }  // namespace slnlp

@@ -42,6 +42,7 @@ __device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8]) { *reinterpret_cast<uint4*>(p) = pack8_bf16(v); }
 
 struct TcFwd {
   int T, B, H, ndir, step;
@@ -53,6 +54,7 @@ struct TcFwd {
   float* out;
   float* stash;
   float* h_final;
+  __nv_bfloat16* out_bf;   // BF kernels: bf16 copy of out (the next step's A operand, and dW_hh's B operand)
 };
 
 // shared pipeline prologue: carve smem, init barriers, allocate TMEM
@@ -94,7 +96,9 @@ __device__ __forceinline__ Ring ring_setup(uint8_t* smem_dyn, int warp, const CU
 // mapW: w_hh as [ndir][G*H][H], box {32 k, 32 rows}.  AROWS = rows the A box actually loads (64 when
 // the batch fits: the MMA still reads 128 rows, the upper 64 are whatever shared memory holds and only
 // reach accumulator rows nobody reads) - half the bytes per stage buys twice the stages in flight.
-template <int G, int F_STAGES, int AROWS>
+// BF: operands are bf16 copies (out_bf, a bf16 W_hh; tcgen05 kind::f16, 64-element k-blocks - the same 128-byte rows,
+// half the L2 -> shared-memory bytes per flop) and the epilogue also writes h_t as bf16.
+template <int G, int F_STAGES, int AROWS, bool BF>
 __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH,
                                                                     const __grid_constant__ CUtensorMap mapH0,
                                                                     const __grid_constant__ CUtensorMap mapW, TcFwd p) {
@@ -106,7 +110,8 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid
   const int t = d == 0 ? p.step : T - 1 - p.step;
   const int tp = d == 0 ? t - 1 : t + 1;
   const bool has_prev = tp >= 0 && tp < T;
-  const int nk = (has_prev || p.h0) ? H / SK : 0;   // zero initial state: the recurrent product is exactly 0
+  constexpr int KE = BF ? 64 : SK;                  // elements per k-block (one 128-byte row)
+  const int nk = (has_prev || p.h0) ? H / KE : 0;   // zero initial state: the recurrent product is exactly 0
   Ring r = ring_setup<F_STAGES, SA_STAGE, B_STAGE, 128>(smem_dyn, warp, &mapH, &mapH0, &mapW);
 
   // the next timestep's launch may start now: its prologue and its W_hh tiles overlap this step
@@ -119,15 +124,15 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid
       for (int i = 0; i < first; ++i) {
         mbar_expect_tx(&r.full[i], SA_STAGE + B_STAGE);
 #pragma unroll
-        for (int g = 0; g < G; ++g) tma_load_3d(r.sB + i * B_STAGE + g * 4096, &mapW, &r.full[i], i * SK, g * H + u0, d);
+        for (int g = 0; g < G; ++g) tma_load_3d(r.sB + i * B_STAGE + g * 4096, &mapW, &r.full[i], i * KE, g * H + u0, d);
       }
       pdl_wait();
       for (int i = 0; i < first; ++i) {
-        if (has_prev) tma_load_3d(r.sA + i * SA_STAGE, &mapH, &r.full[i], d * H + i * SK, b0, tp);
-        else tma_load_3d(r.sA + i * SA_STAGE, &mapH0, &r.full[i], i * SK, b0, d);
+        if (has_prev) tma_load_3d(r.sA + i * SA_STAGE, &mapH, &r.full[i], d * H + i * KE, b0, tp);
+        else tma_load_3d(r.sA + i * SA_STAGE, &mapH0, &r.full[i], i * KE, b0, d);
       }
       for (int i = first; i < nk; ++i) {
-        const int s = i % F_STAGES, k0 = i * SK;
+        const int s = i % F_STAGES, k0 = i * KE;
         mbar_wait(&r.empty[s], (uint32_t)(i / F_STAGES - 1) & 1u);
         mbar_expect_tx(&r.full[s], SA_STAGE + B_STAGE);
         if (has_prev) tma_load_3d(r.sA + s * SA_STAGE, &mapH, &r.full[s], d * H + k0, b0, tp);
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_tf32(SB, NCOL, 0, 0);
+    constexpr uint32_t idesc = BF ? make_idesc_bf16(SB, NCOL, 0, 0) : make_idesc_tf32(SB, NCOL, 0, 0);
     const uint64_t dA = make_desc_sw128(smem_u32(r.sA), 16, 1024, 2), dB = make_desc_sw128(smem_u32(r.sB), 16, 1024, 2);
     for (int i = 0; i < nk; ++i) {
       const int s = i % F_STAGES;
@@ -145,9 +150,11 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < SK / UMMA_K; ++kk)
-          umma_tf32(r.tmem, dA + (uint64_t)((s * SA_STAGE + kk * 32) >> 4), dB + (uint64_t)((s * B_STAGE + kk * 32) >> 4),
-                    idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk) {   // four MMAs of 32 bytes of K each (tf32: K = 8, bf16: K = 16)
+          const uint64_t a = dA + (uint64_t)((s * SA_STAGE + kk * 32) >> 4), b = dB + (uint64_t)((s * B_STAGE + kk * 32) >> 4);
+          if (BF) umma_bf16(r.tmem, a, b, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          else umma_tf32(r.tmem, a, b, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
         umma_commit(&r.empty[s]);
         if (i == nk - 1) umma_commit(r.acc_full);
       }
@@ -165,6 +172,7 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid
     float* gt = p.gates + (row * p.ndir + d) * G * H + u0 + uh;
     float* o = p.out + row * p.ndir * H + (int64_t)d * H + u0 + uh;
     float* st = p.stash + (row * p.ndir + d) * H + u0 + uh;
+    __nv_bfloat16* ob = BF ? p.out_bf + row * p.ndir * H + (int64_t)d * H + u0 + uh : nullptr;
     const float* bh = p.b_hh + (int64_t)d * G * H + u0 + uh;
     const int64_t cidx = ((int64_t)d * B + bb) * H + u0 + uh;
     // predecessor state of this sequence (fp32, exact): c_{t-1} (LSTM) / h_{t-1} (GRU)
@@ -221,6 +229,7 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid
         for (int x = 0; x < 8; ++x) hv[x] = 0.f;
         st8(o + c, hv);
         st8(st + c, hv);
+        if (BF) st8_bf16(ob + c, hv);
         continue;
       }
       float bv[G][8], go_[G][8];
@@ -251,6 +260,7 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_fwd_tc_kernel(const __grid
       for (int g = 0; g < G; ++g) st8(gt + g * H + c, go_[g]);
       st8(st + c, sv);
       st8(o + c, hv);
+      if (BF) st8_bf16(ob + c, hv);
       if (fin) st8(p.h_final + cidx + c, hv);
     }
   }
@@ -267,6 +277,7 @@ struct TcBwd {
   const int64_t* lengths;
   const float *h0, *c0, *dout, *dh_final, *dc_final;
   float *dh0, *dc0, *carry;
+  __nv_bfloat16* dg_bf;    // BF kernels: bf16 copy of d(pre-activations) (the next step's A operand; dX / dW GEMMs)
 };
 
 // grid (H/32, ceil(B/128), ndir), block 192.  mapG: gates as [T][B][ndir*G*H]; mapS: stash as
@@ -274,7 +285,9 @@ struct TcBwd {
 // [ndir][G*H (j)][H (k)] read MN-major, box {32 k, 32 j}.
 // NCH = 32-unit output chunks per CTA: 1 at small batch (more CTAs share the W_hh stream), 4 at large
 // batch (the dG tile, re-read by every unit tile of the same sequences, is fetched 4x less often)
-template <int G, int B_STAGES, int AROWS, int NCH>
+// BF (LSTM): A = the bf16 copy of dG (mapG), B = a bf16 copy of W_hh^T as [ndir][H][G*H] (K-major, mapW); the epilogue
+// also writes d(pre-activations) as bf16.
+template <int G, int B_STAGES, int AROWS, int NCH, bool BF>
 __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapG,
                                                                     const __grid_constant__ CUtensorMap mapS,
                                                                     const __grid_constant__ CUtensorMap mapW, TcBwd p) {
@@ -286,45 +299,55 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
   const int t = p.final_only ? (d == 0 ? -1 : T) : (d == 0 ? T - 1 - p.step : p.step);
   const int tn = d == 0 ? t + 1 : t - 1;   // the step processed just before this one
   const bool has_next = tn >= 0 && tn < T;
-  const int nk = has_next ? GH / SK : 0;
+  constexpr int KE = BF ? 64 : SK;
+  const int nk = has_next ? GH / KE : 0;
   Ring r = ring_setup<B_STAGES, SA_STAGE, B_STAGE, NCH * SU>(smem_dyn, warp, &mapG, &mapS, &mapW);
 
   pdl_launch_dependents();
   if (warp == 0) {
     if (elect_one()) {
       auto load_a = [&](int s, int j0) {
-        if (G == 4 || j0 < 2 * H) tma_load_3d(r.sA + s * SA_STAGE, &mapG, &r.full[s], d * GH + j0, b0, tn);
+        if (BF || G == 4 || j0 < 2 * H) tma_load_3d(r.sA + s * SA_STAGE, &mapG, &r.full[s], d * GH + j0, b0, tn);
         else tma_load_3d(r.sA + s * SA_STAGE, &mapS, &r.full[s], d * H + (j0 - 2 * H), b0, tn);
       };
       const int first = nk < B_STAGES ? nk : B_STAGES;
       for (int i = 0; i < first; ++i) {
         mbar_expect_tx(&r.full[i], SA_STAGE + B_STAGE);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) tma_load_3d(r.sB + i * B_STAGE + c * 4096, &mapW, &r.full[i], u0 + c * SU, i * SK, d);
+        for (int c = 0; c < NCH; ++c) {
+          if (BF) tma_load_3d(r.sB + i * B_STAGE + c * 4096, &mapW, &r.full[i], i * KE, u0 + c * SU, d);
+          else tma_load_3d(r.sB + i * B_STAGE + c * 4096, &mapW, &r.full[i], u0 + c * SU, i * KE, d);
+        }
       }
       pdl_wait();   // dG of the step processed just before must be complete in HBM
-      for (int i = 0; i < first; ++i) load_a(i, i * SK);
+      for (int i = 0; i < first; ++i) load_a(i, i * KE);
       for (int i = first; i < nk; ++i) {
-        const int s = i % B_STAGES, j0 = i * SK;
+        const int s = i % B_STAGES, j0 = i * KE;
         mbar_wait(&r.empty[s], (uint32_t)(i / B_STAGES - 1) & 1u);
         mbar_expect_tx(&r.full[s], SA_STAGE + B_STAGE);
         load_a(s, j0);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) tma_load_3d(r.sB + s * B_STAGE + c * 4096, &mapW, &r.full[s], u0 + c * SU, j0, d);
+        for (int c = 0; c < NCH; ++c) {
+          if (BF) tma_load_3d(r.sB + s * B_STAGE + c * 4096, &mapW, &r.full[s], j0, u0 + c * SU, d);
+          else tma_load_3d(r.sB + s * B_STAGE + c * 4096, &mapW, &r.full[s], u0 + c * SU, j0, d);
+        }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_tf32(SB, NCH * SU, 0, 1);
-    const uint64_t dA = make_desc_sw128(smem_u32(r.sA), 16, 1024, 2), dB = make_desc_sw128(smem_u32(r.sB), 4096, 512, 1);
+    constexpr uint32_t idesc = BF ? make_idesc_bf16(SB, NCH * SU, 0, 0) : make_idesc_tf32(SB, NCH * SU, 0, 1);
+    const uint64_t dA = make_desc_sw128(smem_u32(r.sA), 16, 1024, 2);
+    const uint64_t dB = BF ? make_desc_sw128(smem_u32(r.sB), 16, 1024, 2) : make_desc_sw128(smem_u32(r.sB), 4096, 512, 1);
     for (int i = 0; i < nk; ++i) {
       const int s = i % B_STAGES;
       mbar_wait(&r.full[s], (uint32_t)(i / B_STAGES) & 1u);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < SK / UMMA_K; ++kk)
-          umma_tf32(r.tmem, dA + (uint64_t)((s * SA_STAGE + kk * 32) >> 4), dB + (uint64_t)((s * B_STAGE + kk * 1024) >> 4),
-                    idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t a = dA + (uint64_t)((s * SA_STAGE + kk * 32) >> 4);
+          if (BF) umma_bf16(r.tmem, a, dB + (uint64_t)((s * B_STAGE + kk * 32) >> 4), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          else umma_tf32(r.tmem, a, dB + (uint64_t)((s * B_STAGE + kk * 1024) >> 4), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
         umma_commit(&r.empty[s]);
         if (i == nk - 1) umma_commit(r.acc_full);
       }
@@ -344,6 +367,7 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
     const int64_t row = ((int64_t)tt * B + bb) * p.ndir + d;
     float* gt = p.gates + row * GH + ub + uh;
     float* st = p.stash + row * H + ub + uh;
+    __nv_bfloat16* gb = BF ? p.dg_bf + row * GH + ub + uh : nullptr;
     const int tp = d == 0 ? t - 1 : t + 1;   // forward-time predecessor
     const bool has_prev = tp >= 0 && tp < T;
     const bool inject = d == 0 ? t == len - 1 : t == 0;
@@ -432,7 +456,10 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
 #pragma unroll
         for (int x = 0; x < 8; ++x) dst[x] = 0.f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) st8(gt + g * H + c, dst);
+        for (int g = 0; g < G; ++g) {
+          st8(gt + g * H + c, dst);
+          if (BF) st8_bf16(gb + g * H + c, dst);
+        }
         if (G == 3) st8(st + c, dst);
         continue;
       }
@@ -462,7 +489,10 @@ __global__ void __launch_bounds__(S_THREADS) rnn_step_bwd_tc_kernel(const __grid
         }
       }
 #pragma unroll
-      for (int g = 0; g < G; ++g) st8(gt + g * H + c, og[g]);
+      for (int g = 0; g < G; ++g) {
+        st8(gt + g * H + c, og[g]);
+        if (BF) st8_bf16(gb + g * H + c, og[g]);
+      }
       if (G == 3) st8(st + c, dst);
       st8(p.carry + cidx + c, oc);
     }
@@ -495,7 +525,7 @@ int rnn_layer_fwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
     mapH0 = mapH;
   }
   if (!tensor_map3(w_hh, H, (uint64_t)G * H, ndir, H, (uint64_t)G * H * H, SU, false, &mapW)) return -1;
-  TcFwd p{T, B, H, ndir, 0, gates, b_hh, lengths, h0, c0, out, stash, h_final};
+  TcFwd p{T, B, H, ndir, 0, gates, b_hh, lengths, h0, c0, out, stash, h_final, nullptr};
   dim3 grid(H / SU, ceil_div(B, SB), ndir);
   auto run = [&](auto kernel, int stages, int arows) {
     const size_t sm = (size_t)stages * (arows * SK * 4 + G * SU * SK * 4) + (2 * stages + 1) * 8 + 16 + 1024;
@@ -506,9 +536,9 @@ int rnn_layer_fwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
     }
   };
   if (small) {
-    if (G == 4) run(rnn_step_fwd_tc_kernel<4, 8, 64>, 8, 64); else run(rnn_step_fwd_tc_kernel<3, 8, 64>, 8, 64);
+    if (G == 4) run(rnn_step_fwd_tc_kernel<4, 8, 64, false>, 8, 64); else run(rnn_step_fwd_tc_kernel<3, 8, 64, false>, 8, 64);
   } else {
-    if (G == 4) run(rnn_step_fwd_tc_kernel<4, 4, 128>, 4, 128); else run(rnn_step_fwd_tc_kernel<3, 4, 128>, 4, 128);
+    if (G == 4) run(rnn_step_fwd_tc_kernel<4, 4, 128, false>, 4, 128); else run(rnn_step_fwd_tc_kernel<3, 4, 128, false>, 4, 128);
   }
   note_launches(T);
   cudaError_t e = cudaGetLastError();
@@ -531,7 +561,7 @@ int rnn_layer_bwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
   if (!tensor_map3(gates, (uint64_t)ndir * G * H, B, T, (uint64_t)ndir * G * H, (uint64_t)B * ndir * G * H, arows, false, &mapG)) return -1;
   if (!tensor_map3(stash, (uint64_t)ndir * H, B, T, (uint64_t)ndir * H, (uint64_t)B * ndir * H, arows, false, &mapS)) return -1;
   if (!tensor_map3(w_hh, H, (uint64_t)G * H, ndir, H, (uint64_t)G * H * H, SK, true, &mapW)) return -1;
-  TcBwd p{T, B, H, ndir, 0, 0, gates, stash, out, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0, carry};
+  TcBwd p{T, B, H, ndir, 0, 0, gates, stash, out, lengths, h0, c0, dout, dh_final, dc_final, dh0, dc0, carry, nullptr};
   // large batch: 128 output units per CTA, as long as the wide grid still fills the GPU
   const bool wide = H % (4 * SU) == 0 && ceil_div(B, SB) * (H / (4 * SU)) * ndir >= (sm_count() > 0 ? sm_count() : 148);
   dim3 grid(H / (wide ? 4 * SU : SU), ceil_div(B, SB), ndir);
@@ -552,11 +582,11 @@ int rnn_layer_bwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
     }
   };
   if (small) {
-    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 16, 64, 1>, 16, 64); else run(rnn_step_bwd_tc_kernel<3, 16, 64, 1>, 16, 64);
+    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 16, 64, 1, false>, 16, 64); else run(rnn_step_bwd_tc_kernel<3, 16, 64, 1, false>, 16, 64);
   } else if (wide) {
-    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 6, 128, 4>, 6, 128); else run(rnn_step_bwd_tc_kernel<3, 6, 128, 4>, 6, 128);
+    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 6, 128, 4, false>, 6, 128); else run(rnn_step_bwd_tc_kernel<3, 6, 128, 4, false>, 6, 128);
   } else {
-    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 8, 128, 1>, 8, 128); else run(rnn_step_bwd_tc_kernel<3, 8, 128, 1>, 8, 128);
+    if (G == 4) run(rnn_step_bwd_tc_kernel<4, 8, 128, 1, false>, 8, 128); else run(rnn_step_bwd_tc_kernel<3, 8, 128, 1, false>, 8, 128);
   }
   note_launches(n);
   cudaError_t e = cudaGetLastError();
@@ -564,4 +594,119 @@ int rnn_layer_bwd_tcstep(int mode, int T, int B, int H, int ndir, float* gates, 
   return 0;
 }
 
+// ---- bf16-operand launchers (large batch: the recurrence is L2-bandwidth bound on its operand tiles)
+// w_hh_bf: [ndir][G*H][H] bf16 copy of W_hh; out_bf: [T][B][ndir*H] bf16, written here (h_t), read as the next step's A
+int rnn_layer_fwd_bfstep(int mode, int T, int B, int H, int ndir, float* gates, const uint16_t* w_hh_bf, const float* b_hh,
+                         const int64_t* lengths, float* out, uint16_t* out_bf, float* stash, float* h_final, cudaStream_t s) {
+  const int G = mode == SLNLP_MODE_LSTM ? 4 : 3;
+  if (H % 64 != 0 || H < 64 || H > 4096 || B < 1 || encode_fn() == nullptr) return -1;
+  if ((((uintptr_t)gates | (uintptr_t)out | (uintptr_t)w_hh_bf | (uintptr_t)out_bf | (uintptr_t)stash | (uintptr_t)b_hh) & 15) ||
+      (h_final && ((uintptr_t)h_final & 15)))
+    return -1;
+  CUtensorMap mapH, mapW;
+  if (!tensor_map3_bf16(out_bf, (uint64_t)ndir * H, B, T, (uint64_t)ndir * H, (uint64_t)B * ndir * H, SB, &mapH)) return -1;
+  if (!tensor_map3_bf16(w_hh_bf, H, (uint64_t)G * H, ndir, H, (uint64_t)G * H * H, SU, &mapW)) return -1;
+  TcFwd p{T, B, H, ndir, 0, gates, b_hh, lengths, nullptr, nullptr, out, stash, h_final, reinterpret_cast<__nv_bfloat16*>(out_bf)};
+  dim3 grid(H / SU, ceil_div(B, SB), ndir);
+  auto run = [&](auto kernel, int stages) {
+    const size_t sm = (size_t)stages * (SB * SK * 4 + G * SU * SK * 4) + (2 * stages + 1) * 8 + 16 + 1024;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    for (int step = 0; step < T; ++step) {
+      p.step = step;
+      launch_pdl(kernel, grid, dim3(S_THREADS), sm, s, mapH, mapH, mapW, p);
+    }
+  };
+  if (G == 4) run(rnn_step_fwd_tc_kernel<4, 6, 128, true>, 6); else run(rnn_step_fwd_tc_kernel<3, 6, 128, true>, 6);
+  note_launches(T);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("rnn_layer_fwd(bf16 step): launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// LSTM only.  w_hhT_bf: [ndir][H][G*H] bf16 copy of W_hh^T; dg_bf: [T][B][ndir*G*H] bf16, written here
+int rnn_layer_bwd_bfstep(int mode, int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, float* stash, const float* out,
+                         const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout, const float* dh_final,
+                         const float* dc_final, float* carry, cudaStream_t s) {
+  if (mode != SLNLP_MODE_LSTM) return -1;
+  constexpr int G = 4;
+  if (H % (4 * SU) != 0 || H > 4096 || B < 1 || encode_fn() == nullptr) return -1;
+  const void* ptrs[] = {gates, dg_bf, stash, out, w_hhT_bf, dout, dh_final, dc_final, carry};
+  for (const void* q : ptrs)
+    if (q && ((uintptr_t)q & 15)) return -1;
+  CUtensorMap mapG, mapW;
+  if (!tensor_map3_bf16(dg_bf, (uint64_t)ndir * G * H, B, T, (uint64_t)ndir * G * H, (uint64_t)B * ndir * G * H, SB, &mapG)) return -1;
+  if (!tensor_map3_bf16(w_hhT_bf, (uint64_t)G * H, H, ndir, (uint64_t)G * H, (uint64_t)G * H * H, SU, &mapW)) return -1;
+  TcBwd p{T, B, H, ndir, 0, 0, gates, stash, out, lengths, nullptr, nullptr, dout, dh_final, dc_final, nullptr, nullptr, carry,
+          reinterpret_cast<__nv_bfloat16*>(dg_bf)};
+  dim3 grid(H / (4 * SU), ceil_div(B, SB), ndir);
+  constexpr int stages = 6;
+  const size_t sm = (size_t)stages * (SB * SK * 4 + 4 * SU * SK * 4) + (2 * stages + 1) * 8 + 16 + 1024;
+  auto kernel = rnn_step_bwd_tc_kernel<4, stages, 128, 4, true>;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  for (int step = 0; step < T; ++step) {
+    p.step = step;
+    launch_pdl(kernel, grid, dim3(S_THREADS), sm, s, mapG, mapG, mapW, p);
+  }
+  note_launches(T);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("rnn_layer_bwd(bf16 step): launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// persistent CTA-pair form of the same step (rnn_step_pair.cu; LSTM); -1 = unsupported
+int lstm_layer_fwd_pairstep(int T, int B, int H, int ndir, float* gates, const uint16_t* w_hh_bf, const float* b_hh,
+                            const int64_t* lengths, float* out, uint16_t* out_bf, float* stash, float* h_final, cudaStream_t s);
+int lstm_layer_bwd_pairstep(int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, const float* stash,
+                            const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout, const float* dh_final,
+                            const float* dc_final, float* carry, int write_f32, cudaStream_t s);
+static bool pair_step_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SLNLP_PAIR_STEP");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 }  // namespace slnlp
+
+extern "C" int slnlp_rnn_layer_fwd_bf16(int mode, int T, int B, int H, int ndir, float* gates, const uint16_t* w_hh_bf,
+                                        const float* b_hh, const int64_t* lengths, float* out, uint16_t* out_bf, float* stash,
+                                        float* h_final, slnlp_stream_t stream) {
+  using namespace slnlp;
+  SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM || mode == SLNLP_MODE_GRU, "rnn_layer_fwd_bf16: bad mode %d", mode);
+  SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_fwd_bf16: bad shape");
+  SLNLP_CHECK_ARG(gates && w_hh_bf && b_hh && out && out_bf && stash, "rnn_layer_fwd_bf16: null pointer");
+  if (mode == SLNLP_MODE_LSTM && pair_step_enabled()) {
+    const int rp = lstm_layer_fwd_pairstep(T, B, H, ndir, gates, w_hh_bf, b_hh, lengths, out, out_bf, stash, h_final, as_stream(stream));
+    if (rp >= 0) return rp;
+  }
+  const int rc = rnn_layer_fwd_bfstep(mode, T, B, H, ndir, gates, w_hh_bf, b_hh, lengths, out, out_bf, stash, h_final, as_stream(stream));
+  SLNLP_CHECK_ARG(rc >= 0, "rnn_layer_fwd_bf16: needs H a multiple of 64 and 16-byte aligned operands");
+  return rc;
+}
+
+extern "C" int slnlp_rnn_layer_bwd_bf16(int mode, int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, float* stash,
+                                        const float* out, const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout,
+                                        const float* dh_final, const float* dc_final, float* carry, int write_f32,
+                                        slnlp_stream_t stream) {
+  using namespace slnlp;
+  SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM, "rnn_layer_bwd_bf16: LSTM only (mode %d)", mode);
+  SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_bwd_bf16: bad shape");
+  SLNLP_CHECK_ARG(gates && dg_bf && stash && out && w_hhT_bf && carry, "rnn_layer_bwd_bf16: null pointer");
+  if (pair_step_enabled()) {
+    const int rp = lstm_layer_bwd_pairstep(T, B, H, ndir, gates, dg_bf, stash, w_hhT_bf, lengths, dout, dh_final, dc_final, carry, write_f32,
+                                           as_stream(stream));
+    if (rp >= 0) return rp;
+  }
+  const int rc = rnn_layer_bwd_bfstep(mode, T, B, H, ndir, gates, dg_bf, stash, out, w_hhT_bf, lengths, dout, dh_final, dc_final,
+                                      carry, as_stream(stream));
+  SLNLP_CHECK_ARG(rc >= 0, "rnn_layer_bwd_bf16: needs H a multiple of 128 and 16-byte aligned operands");
+  return rc;
+}
+
+extern "C" int slnlp_rnn_bf16_step_supported(int mode, int T, int B, int H, int ndir) {
+  (void)ndir;
+  // the per-step kernels are the family of batches beyond the persistent / cluster kernels' reach
+  return (mode == SLNLP_MODE_LSTM && T > 1 && B > 256 && H % 128 == 0 && H >= 256 && H <= 4096 && slnlp::encode_fn() != nullptr) ? 1 : 0;
+}

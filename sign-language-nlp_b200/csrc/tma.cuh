@@ -110,6 +110,41 @@ inline bool tensor_map(const float* ptr, uint64_t d0, uint64_t d1, uint64_t ld, 
   return tensor_map3(ptr, d0, d1, 1, ld, ld * d1, b1, mn_major, out, false);
 }
 
+// bf16 tensor [d2][d1][d0] (d0 contiguous; row stride ld1, slab stride ld2, in elements), TMA box {64, b1, 1},
+// 128-byte swizzle (K-major and MN-major 16-bit UMMA operands both use it).  d2 = 0: a rank-2 map.
+inline bool tensor_map3_bf16(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1, uint64_t ld2, uint32_t b1,
+                             CUtensorMap* out) {
+  thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, d0, d1, d2, ld1, ld2, b1};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  if (((uintptr_t)ptr & 15) || (ld1 & 7) || (ld2 & 7)) return false;
+  const cuuint64_t gdim[3] = {d0, d1, d2 ? d2 : 1};
+  const cuuint64_t gstr[2] = {ld1 * 2, ld2 * 2};
+  const cuuint32_t box[3] = {64, b1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d2 ? 3 : 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return true;
+}
+inline bool tensor_map_bf16(const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b1, CUtensorMap* out) {
+  return tensor_map3_bf16(ptr, d0, d1, 0, ld, 0, b1, out);
+}
+// c = f32, a = b = bf16, per-operand major bit (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(

@@ -174,7 +174,8 @@ class RnnEncDecB200(FlatParamModule):
             if ws.pair[l]:
                 # data-parallel batch sizes: bf16 copies of the layer input (kept for dW_ih) and of W_ih (serves
                 # the forward as a K-major and dX as an MN-major operand), CTA-pair tcgen05 GEMM
-                self._cast_bf16(xin.data_ptr(), D, ws.xin_bf[l], T * B, D)
+                if not ws.xin_bf_ready[l]:     # else: the layer below (or its dropout) already wrote it as bf16
+                    self._cast_bf16(xin.data_ptr(), D, ws.xin_bf[l], T * B, D)
                 self._cast_bf16(self._ptr(f"{pre}weight_ih_l{l}"), D, ws.w_ih_bf[l], 2 * G * H, D)
                 self._gemm_bf16(0, 1, T * B, 2 * G * H, D, ws.xin_bf[l].data_ptr(), D, ws.w_ih_bf[l].data_ptr(), D,
                                 ws.enc_gates[l].data_ptr(), 2 * G * H, self._ptr(f"{pre}bias_ih_l{l}"))
@@ -197,13 +198,26 @@ class RnnEncDecB200(FlatParamModule):
                     check(lib.slnlp_dropout(ws.enc_out[l].data_ptr(), ws.enc_xin[l + 1].data_ptr(),
                                             ws.enc_out[l].numel(), self.p_rnn, rng, l, s), "dropout")
                 continue
-            check(lib.slnlp_rnn_layer_fwd(mode, prec, T, B, H, 2, ws.enc_gates[l].data_ptr(),
-                                          self._ptr(f"{pre}weight_hh_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
-                                          lp, None, None, ws.enc_out[l].data_ptr(), ws.enc_stash[l].data_ptr(),
-                                          ws.enc_hfin[l].data_ptr(), s), "rnn_layer_fwd")
+            if ws.bf_step:
+                # large batch: the per-step kernels read bf16 operands (h_{t-1} from the bf16 copy of `out` they
+                # write themselves, W_hh from a bf16 copy) - the recurrence there is bound by operand bytes
+                self._cast_bf16(self._ptr(f"{pre}weight_hh_l{l}"), H, ws.w_hh_bf[l], 2 * G * H, H)
+                check(lib.slnlp_rnn_layer_fwd_bf16(mode, T, B, H, 2, ws.enc_gates[l].data_ptr(), ws.w_hh_bf[l].data_ptr(),
+                                                   self._ptr(f"{pre}bias_hh_l{l}"), lp, ws.enc_out[l].data_ptr(),
+                                                   ws.out_bf[l].data_ptr(), ws.enc_stash[l].data_ptr(),
+                                                   ws.enc_hfin[l].data_ptr(), s), "rnn_layer_fwd_bf16")
+            else:
+                check(lib.slnlp_rnn_layer_fwd(mode, prec, T, B, H, 2, ws.enc_gates[l].data_ptr(),
+                                              self._ptr(f"{pre}weight_hh_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
+                                              lp, None, None, ws.enc_out[l].data_ptr(), ws.enc_stash[l].data_ptr(),
+                                              ws.enc_hfin[l].data_ptr(), s), "rnn_layer_fwd")
             if l < L - 1 and drop:
-                check(lib.slnlp_dropout(ws.enc_out[l].data_ptr(), ws.enc_xin[l + 1].data_ptr(),
-                                        ws.enc_out[l].numel(), self.p_rnn, rng, l, s), "dropout")
+                if ws.bf_in[l + 1]:    # every consumer of the next layer's input reads bf16: one pass, no fp32 copy
+                    check(lib.slnlp_dropout_bf16(ws.enc_out[l].data_ptr(), ws.xin_bf[l + 1].data_ptr(),
+                                                 ws.enc_out[l].numel(), self.p_rnn, rng, l, s), "dropout_bf16")
+                else:
+                    check(lib.slnlp_dropout(ws.enc_out[l].data_ptr(), ws.enc_xin[l + 1].data_ptr(),
+                                            ws.enc_out[l].numel(), self.p_rnn, rng, l, s), "dropout")
             check(lib.slnlp_concat_dirs(ws.enc_hfin[l].data_ptr(), ws.enc_final[l].data_ptr(), B, H, 2, 0, s),
                   "concat_dirs")
         # pad_packed_sequence(padding_value=<pad>) (bkp:121-123): a pad-FILLED copy for the key projection and
@@ -227,9 +241,10 @@ class RnnEncDecB200(FlatParamModule):
                                       self._ptr("model.decoder.attention.energy_layer.weight"),
                                       enc_out.data_ptr(), Xp, self.src_pad, T, B, H, 2 * H,
                                       ws.alpha.data_ptr(), ws.ctx.data_ptr(), s), "attn_fwd")
-        # one decoder step (bkp:215-216): its cell stays on the fp32 step kernel (a single step gains
-        # nothing from the tensor-core kernels, measured); SLNLP_DEC_TC=1 routes it to them
-        dec_prec = prec if os.environ.get("SLNLP_DEC_TC", "0") == "1" else 0
+        # one decoder step (bkp:215-216): at the reference's batch its cell stays on the fused fp32 kernel (a single
+        # step of 50 sequences gains nothing from the tensor-core kernels, measured); batches > 256 (or
+        # SLNLP_DEC_TC=1) take the tensor-core GEMM + step kernels (the skinny fp32 cell was 1.6 ms per layer at 4096)
+        dec_prec = prec if (os.environ.get("SLNLP_DEC_TC", "0") == "1" or B > 256) else 0
         check(lib.slnlp_dec_input_fwd(self._ptr("model.trg_embed.weight") + 4 * self.bos_idx * E,
                                       ws.ctx.data_ptr(), ws.dec_xin[0].data_ptr(), B, E, 2 * H, s), "dec_input")
         fused_cell = os.environ.get("SLNLP_DEC_FUSED", "1") != "0" and dec_prec == 0
@@ -290,7 +305,7 @@ class RnnEncDecB200(FlatParamModule):
         self._gemm(0, 0, B, H, V, ws.dlogits.data_ptr(), ws.Vp, self._ptr("model.generator.proj.weight"), H,
                    ws.d_h.data_ptr(), H)
         # decoder cells, top down
-        dec_prec = prec if os.environ.get("SLNLP_DEC_TC", "0") == "1" else 0
+        dec_prec = prec if (os.environ.get("SLNLP_DEC_TC", "0") == "1" or B > 256) else 0
         pre = "model.decoder.rnn."
         for l in range(L - 1, -1, -1):
             D = E + 2 * H if l == 0 else H
@@ -377,6 +392,16 @@ class RnnEncDecB200(FlatParamModule):
                 check(lib.slnlp_rnn_layer_bwd_ex(mode, prec, T, B, H, 2, dg, st, out, self._ptr(f"{pre}weight_hh_l{l}"),
                                                  lp, None, None, ws.d_seq.data_ptr(), ws.d_enc_final[l].data_ptr(), None,
                                                  None, None, ws.carry.data_ptr(), ctypes.byref(ex), s), "rnn_layer_bwd")
+            elif ws.bf_step:
+                check(lib.slnlp_concat_dirs(ws.d_enc_final[l].data_ptr(), ws.d_hfin.data_ptr(), B, H, 2, 1, s),
+                      "concat_dirs_inv")
+                for d in range(2):       # W_hh^T of each direction as a K-major bf16 operand
+                    check(lib.slnlp_cast_bf16(self._ptr(f"{pre}weight_hh_l{l}") + 4 * d * GH * H, H,
+                                              ws.w_hhT_bf[l].data_ptr() + 2 * d * GH * H, GH, GH, H, 1, s), "cast_bf16")
+                check(lib.slnlp_rnn_layer_bwd_bf16(mode, T, B, H, 2, dg, ws.dg_bf[l].data_ptr(), st, out,
+                                                   ws.w_hhT_bf[l].data_ptr(), lp, ws.d_seq.data_ptr(), ws.d_hfin.data_ptr(),
+                                                   None, ws.carry.data_ptr(), 0 if ws.dg_bf_only[l] else 1, s),
+                      "rnn_layer_bwd_bf16")
             else:
                 check(lib.slnlp_concat_dirs(ws.d_enc_final[l].data_ptr(), ws.d_hfin.data_ptr(), B, H, 2, 1, s),
                       "concat_dirs_inv")
@@ -387,8 +412,9 @@ class RnnEncDecB200(FlatParamModule):
             # HERE, right behind the BPTT kernel that produced their operand (forking after the dx GEMM would make
             # them wait for it: the last layer's weight gradients then trail the whole step)
             par = self.overlap_dw and hook is None and torch.cuda.is_current_stream_capturing()
-            if ws.pair[l]:
-                # bf16 copies of d(pre-activations) (A of dX, dW_ih, dW_hh) and of the layer output (B of dW_hh)
+            if ws.pair[l] and not ws.bf_step:
+                # bf16 copies of d(pre-activations) (A of dX, dW_ih, dW_hh) and of the layer output (B of dW_hh);
+                # the bf16 step kernels have written both already
                 self._cast_bf16(dg, 2 * GH, ws.dg_bf[l], T * B, 2 * GH)
                 if mode == 0:
                     self._cast_bf16(out, 2 * H, ws.out_bf[l], T * B, 2 * H)
@@ -444,7 +470,11 @@ class RnnEncDecB200(FlatParamModule):
                 self._gemm(1, 0, 2 * GH, D, T * B, dg, 2 * GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0, big=True)
         with lane(3):
             s = _stream()
-            check(lib.slnlp_colsum_f32(dg, T * B, 2 * GH, 2 * GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
+            if pair:
+                check(lib.slnlp_colsum_bf16(ws.dg_bf[l].data_ptr(), T * B, 2 * GH, 2 * GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s),
+                      "colsum_bf16")
+            else:
+                check(lib.slnlp_colsum_f32(dg, T * B, 2 * GH, 2 * GH, gp(f"{pre}bias_ih_l{l}"), 1.0, s), "colsum")
             if mode == 0:  # LSTM: d b_hh == d b_ih for both directions at once
                 check(lib.slnlp_axpy(gp(f"{pre}bias_hh_l{l}"), gp(f"{pre}bias_ih_l{l}"), 1.0, 2 * GH, s), "axpy")
             else:
@@ -559,8 +589,24 @@ class _Workspace:
         self.pair = [m.precision == "bf16" and m._pair_ok(T * B, 2 * G * H, E if l == 0 else 2 * H) for l in range(L)]
         self.xin_bf = [bf(T * B, E if l == 0 else 2 * H) if self.pair[l] else None for l in range(L)]
         self.w_ih_bf = [bf(2 * G * H, E if l == 0 else 2 * H) if self.pair[l] else None for l in range(L)]
+        # ... and bf16-operand per-step recurrent kernels where that family applies (LSTM, batch > 256)
+        self.bf_step = (m.precision == "bf16" and all(self.pair) and os.environ.get("SLNLP_BF_STEP", "1") != "0" and
+                        bool(lib.slnlp_rnn_bf16_step_supported(MODE[m.rnn_type], T, B, H, 2)))
         self.dg_bf = [bf(T * B, 2 * G * H) if (self.pair[l] and bwd) else None for l in range(L)]
-        self.out_bf = [bf(T * B, 2 * H) if (self.pair[l] and bwd and G == 4) else None for l in range(L)]
+        self.out_bf = [bf(T * B, 2 * H) if (self.pair[l] and ((bwd and G == 4) or self.bf_step)) else None for l in range(L)]
+        if self.bf_step:
+            self.w_hh_bf = [bf(2, G * H, H) for _ in range(L)]
+            self.w_hhT_bf = [bf(2, H, G * H) for _ in range(L)] if bwd else []
+            if not drop:       # layer l+1 reads layer l's bf16 output directly
+                for l in range(1, L):
+                    self.xin_bf[l] = self.out_bf[l - 1]
+        dims = [(E if l == 0 else 2 * H) for l in range(L)]
+        # bf_in[l]: every consumer of layer l's input (projection, dW_ih) reads the bf16 copy; dg_bf_only[l]: every
+        # consumer of its d(pre-activations) (dX, dW_ih, dW_hh, bias sums, the next BPTT step) reads the bf16 copy
+        self.bf_in = [self.pair[l] and m._pair_ok(2 * G * H, dims[l], T * B) for l in range(L)]
+        self.dg_bf_only = [self.bf_step and self.bf_in[l] and m._pair_ok(T * B, dims[l], 2 * G * H) and
+                           m._pair_ok(G * H, H, (T - 1) * B) for l in range(L)]
+        self.xin_bf_ready = [l > 0 and ((drop and self.bf_in[l]) or (not drop and self.bf_step)) for l in range(L)]
         self.emb = f(T, B, E)
         self.enc_gates = [f(T, B, 2, G, H) for _ in range(L)]
         self.enc_stash = [f(T, B, 2, H) for _ in range(L)]

@@ -581,22 +581,40 @@ def test_rnn_layer_at_cfg4_shape_batch_4096_hidden_512(mode):
     dout_tm, dfin_d = c(dout.transpose(0, 1)), c(dfin)
     pk = pick.cuda()
     res = {}
-    for prec in (0, 1):
+    # precision 2 = the bf16-operand per-step kernels (slnlp_rnn_layer_fwd/bwd_bf16: LSTM at batches > 256)
+    precs = (0, 1, 2) if L.lib.slnlp_rnn_bf16_step_supported(md, T, B, H, 2) else (0, 1)
+    assert (2 in precs) == (mode == "lstm")
+    for prec in precs:
         gates = torch.empty(T, B, 2, G, H, device="cuda")
         L.check(L.lib.slnlp_gemm_f32(0, 1, T * B, 2 * G * H, D, x_tm.data_ptr(), D, w_ih.data_ptr(), D,
                                      gates.data_ptr(), 2 * G * H, b_ih.data_ptr(), 0.0, None, 0, S()))
         out, stash, hfin = (torch.empty(T, B, 2 * H, device="cuda"), torch.empty(T, B, 2, H, device="cuda"),
                             torch.empty(2, B, H, device="cuda"))
-        c0 = L.lib.slnlp_launch_count()
-        L.check(L.lib.slnlp_rnn_layer_fwd(md, prec, T, B, H, 2, gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(),
-                                          len_d.data_ptr(), None, None, out.data_ptr(), stash.data_ptr(),
-                                          hfin.data_ptr(), S()))
-        if prec == 1:     # a batch of 4096 takes the per-step family (one launch per timestep), not a persistent kernel
-            assert L.lib.slnlp_launch_count() - c0 >= T
         carry = torch.zeros(4, B, H, device="cuda")
-        L.check(L.lib.slnlp_rnn_layer_bwd(md, prec, T, B, H, 2, gates.data_ptr(), stash.data_ptr(), out.data_ptr(),
-                                          w_hh.data_ptr(), len_d.data_ptr(), None, None, dout_tm.data_ptr(),
-                                          dfin_d.data_ptr(), None, None, None, carry.data_ptr(), S()))
+        if prec == 2:
+            bf = lambda *shape: torch.empty(*shape, device="cuda", dtype=torch.bfloat16)
+            w_bf, wT_bf, out_bf, dg_bf = bf(2, G * H, H), bf(2, H, G * H), bf(T, B, 2 * H), bf(T, B, 2, G, H)
+            L.check(L.lib.slnlp_cast_bf16(w_hh.data_ptr(), H, w_bf.data_ptr(), H, 2 * G * H, H, 0, S()))
+            for d in range(2):
+                L.check(L.lib.slnlp_cast_bf16(w_hh[d].data_ptr(), H, wT_bf[d].data_ptr(), G * H, G * H, H, 1, S()))
+            L.check(L.lib.slnlp_rnn_layer_fwd_bf16(md, T, B, H, 2, gates.data_ptr(), w_bf.data_ptr(), b_hh.data_ptr(),
+                                                   len_d.data_ptr(), out.data_ptr(), out_bf.data_ptr(), stash.data_ptr(),
+                                                   hfin.data_ptr(), S()))
+            assert torch.equal(out_bf, out.to(torch.bfloat16))        # the bf16 copy the GEMMs and the next step read
+            L.check(L.lib.slnlp_rnn_layer_bwd_bf16(md, T, B, H, 2, gates.data_ptr(), dg_bf.data_ptr(), stash.data_ptr(),
+                                                   out.data_ptr(), wT_bf.data_ptr(), len_d.data_ptr(), dout_tm.data_ptr(),
+                                                   dfin_d.data_ptr(), None, carry.data_ptr(), 1, S()))
+            assert torch.equal(dg_bf, gates.to(torch.bfloat16))
+        else:
+            c0 = L.lib.slnlp_launch_count()
+            L.check(L.lib.slnlp_rnn_layer_fwd(md, prec, T, B, H, 2, gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(),
+                                              len_d.data_ptr(), None, None, out.data_ptr(), stash.data_ptr(),
+                                              hfin.data_ptr(), S()))
+            if prec == 1:     # a batch of 4096 takes the per-step family (one launch per timestep), not a persistent kernel
+                assert L.lib.slnlp_launch_count() - c0 >= T
+            L.check(L.lib.slnlp_rnn_layer_bwd(md, prec, T, B, H, 2, gates.data_ptr(), stash.data_ptr(), out.data_ptr(),
+                                              w_hh.data_ptr(), len_d.data_ptr(), None, None, dout_tm.data_ptr(),
+                                              dfin_d.data_ptr(), None, None, None, carry.data_ptr(), S()))
         dx = torch.empty(T, B, D, device="cuda")
         L.check(L.lib.slnlp_gemm_f32(0, 0, T * B, D, 2 * G * H, gates.data_ptr(), 2 * G * H, w_ih.data_ptr(), D,
                                      dx.data_ptr(), D, None, 0.0, None, 0, S()))
@@ -606,8 +624,9 @@ def test_rnn_layer_at_cfg4_shape_batch_4096_hidden_512(mode):
         assert rel_err(hfin[:, pk], torch.stack(fins)) < tol, (prec, "h_final")
         assert rel_err(dx[:, pk].transpose(0, 1), xr.grad) < 2 * tol, (prec, "dx")
         res[prec] = (out, hfin, dx, gates)
-    for i, what in enumerate(("out", "h_final", "dx", "d_gates")):
-        assert rel_err(res[1][i], res[0][i]) < BF16_RTOL, what
+    for prec in precs[1:]:
+        for i, what in enumerate(("out", "h_final", "dx", "d_gates")):
+            assert rel_err(res[prec][i], res[0][i]) < BF16_RTOL, (prec, what)
     pad = (torch.arange(T).view(T, 1) >= lengths.view(1, B)).cuda()
     assert float(res[1][0][pad].abs().max()) == 0.0 and float(res[0][0][pad].abs().max()) == 0.0
 
@@ -710,3 +729,33 @@ def test_cast_bf16_forms():
     d3 = torch.empty(52, 37, dtype=torch.bfloat16, device="cuda")
     L.check(L.lib.slnlp_cast_bf16(x.data_ptr(), 52, d3.data_ptr(), 37, 37, 52, 1, S()))
     assert torch.equal(d3, x.t().contiguous().to(torch.bfloat16))
+
+
+def test_dropout_bf16_draws_the_mask_of_dropout_and_colsum_bf16_sums():
+    L = _lib()
+    n = 4096 * 3 + 4
+    x = cuda(n, seed=91)
+    rng = torch.tensor([77, 5], dtype=torch.int64, device="cuda")
+    y32, y16 = torch.empty(n, device="cuda"), torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib.slnlp_dropout(x.data_ptr(), y32.data_ptr(), n, 0.5, rng.data_ptr(), 3, S()))
+    L.check(L.lib.slnlp_dropout_bf16(x.data_ptr(), y16.data_ptr(), n, 0.5, rng.data_ptr(), 3, S()))
+    assert torch.equal(y16, y32.to(torch.bfloat16))
+    A = cuda(3000, 264, seed=92).to(torch.bfloat16)
+    out = torch.ones(200, device="cuda")
+    L.check(L.lib.slnlp_colsum_bf16(A.data_ptr() + 2 * 8, 3000, 200, 264, out.data_ptr(), 1.0, S()))
+    assert rel_err(out, A[:, 8:208].double().sum(0) + 1.0) < 1e-5
+    out2 = torch.ones(200, device="cuda")
+    L.check(L.lib.slnlp_colsum_bf16(A.data_ptr() + 2 * 8, 100, 200, 264, out2.data_ptr(), 0.0, S()))
+    assert rel_err(out2, A[:100, 8:208].double().sum(0)) < 1e-5
+
+
+def test_concat_dirs_both_layouts():
+    L = _lib()
+    for B, H in ((4096, 512), (7, 6)):
+        x = cuda(2, B, H, seed=93)
+        y = torch.empty(B, 2 * H, device="cuda")
+        L.check(L.lib.slnlp_concat_dirs(x.data_ptr(), y.data_ptr(), B, H, 2, 0, S()))
+        assert torch.equal(y, torch.cat([x[0], x[1]], 1))
+        z = torch.empty_like(x)
+        L.check(L.lib.slnlp_concat_dirs(y.data_ptr(), z.data_ptr(), B, H, 2, 1, S()))
+        assert torch.equal(z, x)

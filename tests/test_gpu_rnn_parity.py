@@ -281,3 +281,43 @@ def test_factored_six_field_embedding_variant(kind):
         assert torch.equal(got_sd[f"model.src_embed.fields.{i}.weight"][1].cpu(), sd0[f"model.src_embed.fields.{i}.weight"][1])
     with pytest.raises(ValueError):
         m(X=X[..., :5].cuda(), y=y.cuda(), lengths=lengths.cuda())
+
+
+@pytest.mark.parametrize("B,T,E,H,L", [(512, 16, 256, 256, 3), (300, 40, 256, 384, 2)])
+def test_large_batch_bf16_operand_path_against_the_reference(B, T, E, H, L):
+    """The family BASELINE.json configs[3] (data-parallel LSTM, batch 4096) runs on: CTA-pair bf16 GEMMs for the
+    hoisted projections / dX / dW, bf16-operand per-step recurrent kernels writing bf16 copies of h_t and of
+    d(pre-activations), bias sums over the bf16 copy, tensor-core decoder cell - against the torch.nn port of the
+    reference on identical weights and ragged inputs (2e-2: logits, two training losses, every updated tensor)."""
+    import model as dropin
+    from helpers import BF16_RTOL
+    from oracle import port
+    from slnlp_b200.rnn import FusedTrainStep
+    from slnlp_b200.vocab import Vocab
+    Vs, Vt = 4098, 1026
+    torch.manual_seed(7)
+    ref = port.build_port("lstm", Vs, Vt, E, H, L, dropout=0.0)
+    m = dropin.EncoderDecoderLSTMAttn(src_vocab=Vocab(size=Vs), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E,
+                                      hidden_size=H, num_layers=L, dropout=0.0, device=torch.device("cuda"), precision="bf16")
+    m.load_state_dict(ref.state_dict())
+    m = m.to(torch.device("cuda"))
+    X, lengths, y = _synthetic(B, T, Vs, Vt, True)
+    ref.eval()
+    with torch.no_grad():
+        want = ref(X=X, y=y, lengths=lengths)
+    m.eval()
+    with torch.no_grad():
+        got = m(X=X.cuda(), y=y.cuda(), lengths=lengths.cuda())
+    assert rel_err(got, want) < BF16_RTOL
+    m.train()
+    ts = FusedTrainStep(m, B, T, lr=0.01)
+    assert all(ts.ws.pair) and ts.ws.bf_step, "the shape must take the large-batch kernels this test is about"
+    opt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9)
+    for step in range(2):
+        want_loss = port.reference_train_step(ref, opt, X, y, lengths)
+        got_loss = ts.step(X.cuda(), y.cuda(), lengths.cuda())
+        assert abs(float(got_loss[0]) - float(want_loss)) < BF16_RTOL * abs(float(want_loss))
+    rsd, sd = ref.state_dict(), m.state_dict()
+    for k in rsd:
+        err = float((sd[k].cpu() - rsd[k]).abs().max()) / max(float(rsd[k].abs().max()), 1e-3)
+        assert err < BF16_RTOL, k
