@@ -45,6 +45,10 @@ int slnlp_device_sm_count(void);
  * fit that captures its step graph on a stream another fit of the process is launching on would swallow
  * that fit's work into the graph (grid search with several fits per GPU). */
 void* slnlp_stream_create(void);
+/* the same with the device's highest (high != 0) or lowest stream priority: kernels captured from a
+ * high-priority stream keep that priority as graph nodes, so the dependency chain of a step (the recurrent
+ * kernels) is scheduled ahead of the weight-gradient GEMMs that run beside it on side lanes */
+void* slnlp_stream_create_priority(int high);
 int slnlp_stream_destroy(void* stream);
 
 /* ---- K1: phonological embedding (nn.Embedding, bkp:49,60,374-379; Transformer

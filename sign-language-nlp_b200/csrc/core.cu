@@ -586,6 +586,16 @@ void* slnlp_stream_create(void) {
   }
   return st;
 }
+void* slnlp_stream_create_priority(int high) {
+  int lo = 0, hi = 0;      // numerically lower = higher priority
+  cudaStream_t st = nullptr;
+  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, high ? hi : lo) != cudaSuccess) {
+    slnlp::fail("slnlp_stream_create_priority: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return st;
+}
 int slnlp_stream_destroy(void* stream) {
   const cudaError_t e = cudaStreamDestroy(reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return slnlp::fail("slnlp_stream_destroy: %s", cudaGetErrorString(e));

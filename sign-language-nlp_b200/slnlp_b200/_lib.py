@@ -26,6 +26,7 @@ SIGNATURES = {
     "slnlp_last_error_string": [],
     "slnlp_device_sm_count": [],
     "slnlp_stream_create": [],
+    "slnlp_stream_create_priority": [I],
     "slnlp_stream_destroy": [P],
     "slnlp_launch_count": [],
     "slnlp_max_active_clusters": [I, I],
@@ -81,7 +82,7 @@ SIGNATURES = {
     "slnlp_ln_bwd_blocks": [I],
     "slnlp_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, I, P],
 }
-_RESTYPES = {"slnlp_last_error_string": c_char_p, "slnlp_launch_count": c_int64, "slnlp_stream_create": c_void_p,
+_RESTYPES = {"slnlp_last_error_string": c_char_p, "slnlp_launch_count": c_int64, "slnlp_stream_create": c_void_p, "slnlp_stream_create_priority": c_void_p,
              "slnlp_gemm_workspace_floats": c_int64}
 
 for _name, _args in SIGNATURES.items():

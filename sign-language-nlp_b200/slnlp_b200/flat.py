@@ -33,11 +33,12 @@ CAPTURE_LOCK = _threading.RLock()
 _tls = _threading.local()
 
 
-def new_stream():
+def new_stream(priority=None):
     """A CUDA stream of its own (created through the C ABI, wrapped as an external stream).
     ``torch.cuda.Stream()`` draws from a pool of 32 that is handed out round-robin, so two fits of one
-    process can end up sharing a stream - fatal when one of them is capturing on it."""
-    ptr = lib.slnlp_stream_create()
+    process can end up sharing a stream - fatal when one of them is capturing on it.
+    ``priority``: "high" / "low" = the device's extreme stream priorities (kept by captured graph nodes)."""
+    ptr = lib.slnlp_stream_create() if priority is None else lib.slnlp_stream_create_priority(1 if priority == "high" else 0)
     if not ptr:
         check(1, "stream_create")
     return torch.cuda.ExternalStream(ptr, device=torch.cuda.current_device())
@@ -48,7 +49,12 @@ def thread_stream(role):
     key = (role, torch.cuda.current_device())
     cache = _tls.__dict__.setdefault("streams", {})
     if key not in cache:
-        cache[key] = new_stream()
+        # the step's dependency chain is captured on a high-priority stream, the "sidelo" weight-gradient lanes on
+        # low-priority ones: where both have CTAs pending, the chain's are placed first ($SLNLP_STREAM_PRIO=0: off)
+        prio = None
+        if _os.environ.get("SLNLP_STREAM_PRIO", "1") != "0":
+            prio = "high" if role == "capture" else ("low" if role.startswith("sidelo") else None)
+        cache[key] = new_stream(prio)
     return cache[key]
 
 
@@ -261,8 +267,12 @@ class FlatParamModule(nn.Module):
     N_LANES = 4
 
     def _side_stream(self, lane=0):
+        # H = 128 models (overlap_dw): the recurrent kernels leave SMs free and the weight-gradient GEMMs beside them
+        # take low-priority lanes (cfg1 +2.3 %); where the recurrence fills the GPU the lanes keep the default
+        # priority (low-priority lanes measured -1.9 % on cfg2)
+        base = "sidelo" if getattr(self, "overlap_dw", False) else "side"
         with torch.cuda.device(self._flat.device):
-            side = thread_stream("side" if lane == 0 else f"side{lane}")
+            side = thread_stream(base if lane == 0 else f"{base}{lane}")
         if lane == 0:
             self._side = side
         return side
