@@ -49,17 +49,18 @@ def thread_stream(role):
     key = (role, torch.cuda.current_device())
     cache = _tls.__dict__.setdefault("streams", {})
     if key not in cache:
-        # the step's dependency chain is captured on a high-priority stream, the "sidelo" weight-gradient lanes on
-        # low-priority ones: where both have CTAs pending, the chain's are placed first ($SLNLP_STREAM_PRIO=0: off)
+        # "capturehi": the step's dependency chain captured on a high-priority stream (graph nodes keep the priority),
+        # so that where its CTAs and those of the weight-gradient side lanes (default = lowest priority) are both
+        # pending, the chain's are placed first ($SLNLP_STREAM_PRIO=0: off)
         prio = None
         if _os.environ.get("SLNLP_STREAM_PRIO", "1") != "0":
-            prio = "high" if role == "capture" else ("low" if role.startswith("sidelo") else None)
+            prio = "high" if role == "capturehi" else None
         cache[key] = new_stream(prio)
     return cache[key]
 
 
 @contextlib.contextmanager
-def capture_graph(graph):
+def capture_graph(graph, high_priority=False):
     """Capture the CUDA work issued inside into ``graph`` (a torch.cuda.CUDAGraph), under CAPTURE_LOCK.
 
     ``torch.cuda.graph`` synchronises the whole device and empties the caching allocator before every
@@ -69,7 +70,9 @@ def capture_graph(graph):
     ``$SLNLP_CAPTURE_MODE`` = "thread_local" when several threads of the process capture (grid.py)."""
     mode = _os.environ.get("SLNLP_CAPTURE_MODE", "global")
     cur = torch.cuda.current_stream()
-    stream = thread_stream("capture")
+    # high_priority: H = 128 models, whose recurrent kernels leave SMs free for the weight-gradient GEMMs beside them
+    # (cfg1 +2.3 %; where the recurrence fills the GPU it measured -1.9 %, cfg2)
+    stream = thread_stream("capturehi" if high_priority else "capture")
     stream.wait_stream(cur)
     with CAPTURE_LOCK:
         with torch.cuda.stream(stream):
@@ -267,12 +270,8 @@ class FlatParamModule(nn.Module):
     N_LANES = 4
 
     def _side_stream(self, lane=0):
-        # H = 128 models (overlap_dw): the recurrent kernels leave SMs free and the weight-gradient GEMMs beside them
-        # take low-priority lanes (cfg1 +2.3 %); where the recurrence fills the GPU the lanes keep the default
-        # priority (low-priority lanes measured -1.9 % on cfg2)
-        base = "sidelo" if getattr(self, "overlap_dw", False) else "side"
         with torch.cuda.device(self._flat.device):
-            side = thread_stream(base if lane == 0 else f"{base}{lane}")
+            side = thread_stream("side" if lane == 0 else f"side{lane}")
         if lane == 0:
             self._side = side
         return side

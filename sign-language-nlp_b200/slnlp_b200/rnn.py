@@ -831,7 +831,7 @@ class FusedTrainStep:
             # "thread_local" when several fits share the process (grid.py fits_per_gpu): another thread's
             # allocations must not invalidate this capture
             graph = torch.cuda.CUDAGraph()
-            with capture_graph(graph):
+            with capture_graph(graph, high_priority=bool(getattr(self.m, "overlap_dw", False))):
                 self._step()
             self.graph = graph
             self.m._flat.copy_(saved[0]); self.buf.copy_(saved[1]); self.m._rng_state().copy_(saved[2])
