@@ -91,6 +91,14 @@ int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K,
                     const float* A, int lda, const float* B, int ldb,
                     float* C, int ldc, const float* bias, float beta,
                     float* workspace, int64_t workspace_floats, slnlp_stream_t stream);
+/* slnlp_gemm_tf32's kernel with fp32-ACCURATE products (the 1e-5 / identical-argmax path on the tensor cores):
+ * every operand tile is split in shared memory into the 19 bits the tensor core reads and the exact fp32
+ * remainder, and each k-step issues hi*hi + hi*lo + lo*hi (error ~2^-22 per product, fp32 accumulation).
+ * Same contract and fallbacks as slnlp_gemm_tf32. */
+int slnlp_gemm_tf32x3(int transA, int transB, int M, int N, int K,
+                      const float* A, int lda, const float* B, int ldb,
+                      float* C, int ldc, const float* bias, float beta,
+                      float* workspace, int64_t workspace_floats, slnlp_stream_t stream);
 /* The same contraction at data-parallel batch sizes (BASELINE.json configs[3]: the hoisted x W_ih^T of
  * bkp:114 over T*B = 262,144 rows, and its dX / dW twins) on CTA PAIRS: A and B are bf16 in HBM (row strides
  * lda / ldb in ELEMENTS, multiples of 8; 16-byte aligned bases), C / bias / beta as above (fp32).  Persistent

@@ -26,6 +26,7 @@ constexpr int A_STAGE = BM * BK * 4;
 // lets the whole problem run as ONE wave (2 CTAs per SM for 64 and 128, 1 for 256) - at the K of these
 // GEMMs (128 ... 1536) a CTA's life is mostly fixed latency, so a second wave nearly doubles the time.
 __host__ __device__ constexpr int stages_for(int bn) { return bn == 128 ? 3 : 4; }
+__host__ __device__ constexpr int stages_x3(int bn) { return bn == 64 ? 4 : (bn == 128 ? 3 : 2); }   // hi + lo tiles per stage
 constexpr int TMA_THREADS = 192;                             // producer, MMA, 4 epilogue warps
 
 // A_MN / B_MN: the operand is stored with its M (resp. N) index contiguous ("MN-major").
@@ -35,22 +36,28 @@ constexpr int TMA_THREADS = 192;                             // producer, MMA, 4
 //                operands only exist in that layout); inside a box k-row kk at kk*128 B, 4-row
 //                swizzle groups 512 B apart (SBO); LBO = 4096 B between mn blocks; an MMA of K = 8
 //                consumes two groups = 1024 B.
-template <bool A_MN, bool B_MN, int BN>
+// X3: fp32-ACCURATE products on the tf32 tensor cores (the 1e-5 path).  Each operand tile x is split in shared memory
+// into hi = the 19 bits the tensor core reads and lo = x - hi (exact in fp32; the idle epilogue warps compute the lo
+// tiles while the ring runs), and every k-step issues three MMAs: hi*hi + hi*lo + lo*hi.  The dropped lo*lo term and
+// the truncation of lo are ~2^-22 relative per product - fp32-FMA class, two orders inside the path's 1e-5 budget.
+template <bool A_MN, bool B_MN, int BN, bool X3>
 __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                 const __grid_constant__ CUtensorMap mapB, int M, int N,
                                                                 int Kfull, int kchunk, float* __restrict__ C, int ldc,
                                                                 const float* __restrict__ bias, float beta,
                                                                 float* __restrict__ partial, int atomic_out) {
-  constexpr int STAGES = stages_for(BN), B_STAGE = BN * BK * 4;
+  constexpr int STAGES = X3 ? stages_x3(BN) : stages_for(BN), B_STAGE = BN * BK * 4;
+  constexpr int LO = X3 ? STAGES * (A_STAGE + B_STAGE) : 0;     // the lo tiles mirror the ring, LO bytes further on
   extern __shared__ uint8_t smem_dyn[];
   // the 128-byte swizzle is a function of the shared-memory address: tiles must sit on 1024 B
   uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   uint8_t* sA = smem_raw;
   uint8_t* sB = smem_raw + STAGES * A_STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE + LO);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* conv = acc_full + 1;           // X3: lo tiles of a stage written (one arrival per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv + STAGES);
 
   const int warp = warp_uniform(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -64,6 +71,7 @@ __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_cons
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&conv[s], 4);
     }
     mbar_init(acc_full, 1);
   }
@@ -105,13 +113,18 @@ __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_cons
     constexpr uint32_t a_step = A_MN ? 1024 : UMMA_K * 4, b_step = B_MN ? 1024 : UMMA_K * 4;   // bytes per K = 8
     for (int i = 0; i < nk; ++i) {
       const int s = i % STAGES;
-      mbar_wait(&full[s], (uint32_t)(i / STAGES) & 1u);
+      mbar_wait(X3 ? &conv[s] : &full[s], (uint32_t)(i / STAGES) & 1u);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BK / UMMA_K; ++kk)
-          umma_tf32(tmem, dA + (uint64_t)((s * A_STAGE + kk * a_step) >> 4), dB + (uint64_t)((s * B_STAGE + kk * b_step) >> 4),
-                    idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          const uint64_t a = dA + (uint64_t)((s * A_STAGE + kk * a_step) >> 4), b = dB + (uint64_t)((s * B_STAGE + kk * b_step) >> 4);
+          umma_tf32(tmem, a, b, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          if (X3) {
+            umma_tf32(tmem, a, b + (uint64_t)(LO >> 4), idesc, 1u);
+            umma_tf32(tmem, a + (uint64_t)(LO >> 4), b, idesc, 1u);
+          }
+        }
         umma_commit(&empty[s]);
         if (i == nk - 1) umma_commit(acc_full);
       }
@@ -120,13 +133,37 @@ __global__ void __launch_bounds__(TMA_THREADS) gemm_tma_kernel(const __grid_cons
   } else {
     // epilogue warps 2..5 own TMEM lane quadrants 2, 3, 0, 1 (a warp may only touch lanes 32*(warp%4)..)
     const int q = warp & 3;
+    if (X3) {
+      // while the ring runs: lo = x - (the 19 bits the tensor core reads), element for element at the same offset
+      const int tid = (warp - 2) * 32 + lane;
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&full[s], (uint32_t)(i / STAGES) & 1u);
+        auto split = [&](uint8_t* tile, int bytes) {
+          for (int o = tid * 16; o < bytes; o += 128 * 16) {
+            const uint4 x = *reinterpret_cast<const uint4*>(tile + o);
+            uint4 l;
+            l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(x.x & 0xFFFFE000u));
+            l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(x.y & 0xFFFFE000u));
+            l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(x.z & 0xFFFFE000u));
+            l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(x.w & 0xFFFFE000u));
+            *reinterpret_cast<uint4*>(tile + LO + o) = l;
+          }
+        };
+        split(sA + s * A_STAGE, A_STAGE);
+        split(sB + s * B_STAGE, B_STAGE);
+        fence_async_smem();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
+      }
+    }
     if (nk > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
     }
     constexpr int SLD = BN + 1;
     float* stage = reinterpret_cast<float*>(smem_raw) + q * 32 * SLD;
-    static_assert(4 * 32 * SLD * 4 <= STAGES * (A_STAGE + B_STAGE), "staging tile must fit the operand ring");
+    static_assert(4 * 32 * SLD * 4 <= STAGES * (A_STAGE + B_STAGE) * (X3 ? 2 : 1), "staging tile must fit the operand ring");
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
@@ -197,9 +234,9 @@ void launch_splitk_reduce(const float* partial, int splits, int M, int N, float*
 
 using namespace slnlp;
 
-extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda,
-                               const float* B, int ldb, float* C, int ldc, const float* bias, float beta,
-                               float* workspace, int64_t workspace_floats, slnlp_stream_t stream) {
+static int gemm_tma_launch(bool x3, int transA, int transB, int M, int N, int K, const float* A, int lda,
+                           const float* B, int ldb, float* C, int ldc, const float* bias, float beta,
+                           float* workspace, int64_t workspace_floats, slnlp_stream_t stream) {
   SLNLP_CHECK_ARG(A && B && C, "gemm_tf32: null pointer");
   SLNLP_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "gemm_tf32: bad shape M=%d N=%d K=%d ldc=%d", M, N, K, ldc);
   SLNLP_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N), "gemm_tf32: bad lda/ldb");
@@ -245,6 +282,14 @@ extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, cons
     while (splits > 1 && (int64_t)splits * M * N > workspace_floats) --splits;
     if (splits < 1) splits = 1;
   }
+  // fp32-accurate mode: at most 512 of K per accumulator (see below) - longer reductions are split even when the
+  // tile grid is full: in place for gradient accumulations, through the workspace + one reduce launch otherwise
+  if (x3 && K > 512) {
+    const int need = ceil_div(K, 512);
+    if (splits < need) splits = need;
+    const bool in_place = accumulates && !(getenv("SLNLP_SPLITK_ATOMIC") && getenv("SLNLP_SPLITK_ATOMIC")[0] == '0');
+    if (!in_place && (!workspace || (int64_t)splits * M * N > workspace_floats)) splits = 1;   // no room: fp32-FMA kernel below
+  }
   int kchunk = K;
   float* partial = nullptr;
   int atomic_out = 0;
@@ -263,16 +308,27 @@ extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, cons
     if (use_atomic && beta == 1.f && !bias) atomic_out = 1;
     else partial = workspace;
   }
-#define SLNLP_GO2(AMN, BMN, BNV)                                                                                   \
+  // fp32-accurate mode: the tensor core adds into its accumulator with truncation, an error that grows with the k-steps
+  // one accumulator sees (measured 1.5e-6 of the output scale at K = 128, 1e-5 at K = 1024).  Longer reductions that
+  // are not split stay on the fp32-FMA kernel, so the path keeps ~5e-6 per GEMM.
+  if (x3 && kchunk > 512)
+    return slnlp_gemm_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, workspace, workspace_floats, stream);
+#define SLNLP_GO3(AMN, BMN, BNV, X3V)                                                                              \
   do {                                                                                                             \
-    constexpr size_t sm = stages_for(BNV) * (A_STAGE + BNV * BK * 4) + (2 * stages_for(BNV) + 1) * 8 + 16 + 1024;   \
+    constexpr int st = X3V ? stages_x3(BNV) : stages_for(BNV);                                                     \
+    constexpr size_t sm = (size_t)st * (A_STAGE + BNV * BK * 4) * (X3V ? 2 : 1) + (3 * st + 1) * 8 + 16 + 1024;     \
     static bool attr = false;                                                                                      \
     if (!attr) {                                                                                                   \
-      cudaFuncSetAttribute(gemm_tma_kernel<AMN, BMN, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
+      cudaFuncSetAttribute(gemm_tma_kernel<AMN, BMN, BNV, X3V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
       attr = true;                                                                                                 \
     }                                                                                                              \
-    launch_pdl(gemm_tma_kernel<AMN, BMN, BNV>, grid, dim3(TMA_THREADS), sm, s, mapA, mapB, M, N, K, kchunk, C, ldc, \
+    launch_pdl(gemm_tma_kernel<AMN, BMN, BNV, X3V>, grid, dim3(TMA_THREADS), sm, s, mapA, mapB, M, N, K, kchunk, C, ldc, \
                bias, beta, partial, atomic_out);                                                                   \
+  } while (0)
+#define SLNLP_GO2(AMN, BMN, BNV)              \
+  do {                                        \
+    if (x3) SLNLP_GO3(AMN, BMN, BNV, true);   \
+    else SLNLP_GO3(AMN, BMN, BNV, false);     \
   } while (0)
 #define SLNLP_GO(AMN, BMN)                         \
   do {                                             \
@@ -286,7 +342,20 @@ extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, cons
   else SLNLP_GO(true, true);
 #undef SLNLP_GO
 #undef SLNLP_GO2
+#undef SLNLP_GO3
   if (partial) launch_splitk_reduce(partial, splits, M, N, C, ldc, bias, beta, s);
   SLNLP_LAUNCH_OK("gemm_tf32");
   return 0;
+}
+
+extern "C" int slnlp_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda,
+                               const float* B, int ldb, float* C, int ldc, const float* bias, float beta,
+                               float* workspace, int64_t workspace_floats, slnlp_stream_t stream) {
+  return gemm_tma_launch(false, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, workspace, workspace_floats, stream);
+}
+
+extern "C" int slnlp_gemm_tf32x3(int transA, int transB, int M, int N, int K, const float* A, int lda,
+                                 const float* B, int ldb, float* C, int ldc, const float* bias, float beta,
+                                 float* workspace, int64_t workspace_floats, slnlp_stream_t stream) {
+  return gemm_tma_launch(true, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, workspace, workspace_floats, stream);
 }

@@ -36,6 +36,7 @@ SIGNATURES = {
     "slnlp_gemm_f32": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],
     "slnlp_gemm_workspace_floats": [],
     "slnlp_gemm_tf32": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],
+    "slnlp_gemm_tf32x3": [I, I, I, I, I, P, I, P, I, P, I, P, F, P, L, P],
     "slnlp_gemm_bf16_supported": [I, I, I, I, I],
     "slnlp_gemm_bf16": [I, I, I, I, I, P, L, P, L, P, I, P, F, P],
     "slnlp_cast_bf16": [P, L, P, L, L, L, I, P],

@@ -15,6 +15,7 @@ from ._lib import check, lib
 
 import os as _os
 _TC_GEMM = lib.slnlp_gemm_tf32
+_F32_GEMM = lib.slnlp_gemm_tf32x3
 
 
 def _stream():
@@ -223,7 +224,9 @@ class FlatParamModule(nn.Module):
         pipeline's prologue does - and was dropped; only fusing the chain into fewer kernels pays.)
         (`big` marks the [B*T]-row GEMMs; the library falls back to the fp32 kernel by itself for shapes a
         128-row tile cannot cover)"""
-        fn = _TC_GEMM if self.precision == "bf16" else lib.slnlp_gemm_f32
+        # fp32 path: the same TMA / tcgen05 kernel with split operands (three tf32 MMAs per k-step, fp32-accurate:
+        # slnlp_gemm_tf32x3); $SLNLP_F32_TC=0 keeps the fp32-FMA GEMM
+        fn = _TC_GEMM if self.precision == "bf16" else (_F32_GEMM if self._f32_tc_ok() else lib.slnlp_gemm_f32)
         ws = self._gemm_ws()
         check(fn(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, ws.data_ptr(), ws.numel(), _stream()), "gemm")
         if act == "tanh":
@@ -249,6 +252,12 @@ class FlatParamModule(nn.Module):
 
     def _gemm_bf16(self, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, beta=0.0):
         check(lib.slnlp_gemm_bf16(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, bias, beta, _stream()), "gemm_bf16")
+
+    f32_tensor_cores = True      # class default: the fp32 path's GEMMs run as split-operand tf32 MMAs
+
+    def _f32_tc_ok(self):
+        env = _os.environ.get("SLNLP_F32_TC")
+        return self.f32_tensor_cores if env is None else env != "0"
 
     def _gemm_ws(self):
         """Split-K scratch of the GEMMs of this module: one buffer per stream the module launches on

@@ -47,6 +47,12 @@ class _PEBox(nn.Module):
 
 
 class TransformerB200(FlatParamModule):
+    # The split-operand tf32 GEMM (slnlp_gemm_tf32x3) keeps every product fp32-accurate, but the tensor core adds
+    # into its accumulator with truncation: ~1e-6 (K = 128) to 1e-5 (K = 1024) of the output scale.  The RNN models'
+    # fp32 fixtures hold their 1e-5 / identical-argmax / 1e-4 gradient-norm bars with it; this model's deeper chain of
+    # K = 512 ... 2048 products missed the gradient-norm bar (2.3e-4), so its fp32 path stays on the fp32-FMA GEMM.
+    f32_tensor_cores = False
+
     def __init__(self, embedding_size, num_heads, num_layers, hidden_size, dropout, src_vocab, tgt_vocab,
                  device=None, batch_first=False, precision="fp32", **kwargs):
         super().__init__()

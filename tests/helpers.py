@@ -19,7 +19,9 @@ RNN_CASES = [k for k, v in GOLDEN_CASES.items() if v[0] != "transformer"]
 TRANSFORMER_CASES = [k for k, v in GOLDEN_CASES.items() if v[0] == "transformer"]
 
 # north_star tolerances
-FP32_RTOL = 1e-5     # logits / loss, fp32 path
+import os as _os
+# $SLNLP_TEST_TOL_SCALE < 1 tightens the fp32 tolerances (margin checks when a kernel changes; the default run uses 1)
+FP32_RTOL = 1e-5 * float(_os.environ.get("SLNLP_TEST_TOL_SCALE", "1"))     # logits / loss, fp32 path
 BF16_RTOL = 2e-2     # bf16 tensor-core path
 
 

@@ -759,3 +759,29 @@ def test_concat_dirs_both_layouts():
         z = torch.empty_like(x)
         L.check(L.lib.slnlp_concat_dirs(y.data_ptr(), z.data_ptr(), B, H, 2, 1, S()))
         assert torch.equal(z, x)
+
+
+@pytest.mark.parametrize("tA,tB,M,N,K", [(0, 1, 3200, 1024, 128), (0, 0, 3200, 256, 1024), (1, 0, 1024, 128, 3200), (0, 1, 50, 1026, 128),
+                                         (1, 1, 300, 200, 520), (0, 1, 3200, 1536, 512), (1, 0, 512, 128, 3150), (0, 1, 262, 64, 96)])
+def test_gemm_tf32x3_is_fp32_accurate(tA, tB, M, N, K):
+    """The split-operand tensor-core GEMM of the fp32 path (hi*hi + hi*lo + lo*hi on tcgen05 kind::tf32) against fp64,
+    bias / beta / split-K included."""
+    L = _lib()
+    A = cuda(*((K, M) if tA else (M, K)), seed=95)
+    B = cuda(*((N, K) if tB else (K, N)), seed=96)
+    bias, C0 = cuda(N, seed=97), cuda(M, N, seed=98)
+    ws = torch.empty(L.lib.slnlp_gemm_workspace_floats(), device="cuda")
+    opA, opB = (A.t() if tA else A), (B.t() if tB else B)
+    for beta, bs in ((0.5, bias), (0.0, None), (1.0, None)):
+        C = C0.clone()
+        L.check(L.lib.slnlp_gemm_tf32x3(tA, tB, M, N, K, A.data_ptr(), A.shape[1], B.data_ptr(), B.shape[1], C.data_ptr(), N,
+                                        bs.data_ptr() if bs is not None else None, beta, ws.data_ptr(), ws.numel(), S()))
+        ref = opA.double() @ opB.double() + (bias.double() if bs is not None else 0.0) + beta * C0.double()
+        # products are fp32-accurate (hi*lo terms); what remains is the tensor core's truncating accumulation, which
+        # grows with the k-steps per accumulator: measured 1.5e-6 (K 128) ... 1.0e-5 (K 1024) of the output scale;
+        # reductions longer than 512 per accumulator are routed to the fp32-FMA kernel
+        assert rel_err(C, ref) < 6e-6
+        C1 = C0.clone()
+        L.check(L.lib.slnlp_gemm_tf32(tA, tB, M, N, K, A.data_ptr(), A.shape[1], B.data_ptr(), B.shape[1], C1.data_ptr(), N,
+                                      bs.data_ptr() if bs is not None else None, beta, ws.data_ptr(), ws.numel(), S()))
+        assert rel_err(C, ref) < 0.1 * rel_err(C1, ref) or rel_err(C1, ref) < 1e-6      # >= 10x closer than one tf32 MMA
