@@ -1,12 +1,12 @@
 """Per-kernel counts of the SASS mnemonics that prove which hardware path a kernel uses
-(B200_PROFILING.md: tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG/UTMASTG,
+(B200_PROFILING.md: tcgen05.mma -> UTC*MMA (cta_group::2 -> UTCHMMA.2CTA), tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG/UTMASTG,
 mma.sync -> HMMA/*MMA.16816..., clusters -> UCGABAR / cluster barrier, PDL -> ACQBULK/...):
     python profiles/sass_mnemonics.py > profiles/r01_sass_mnemonics.txt
 Runs offline (cuobjdump on the built .so), no GPU needed."""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "sign-language-nlp_b200", "libslnlp_b200.so")
-PAT = ("UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA", "IMMA",
+PAT = ("UTCHMMA", "UTCHMMA.2CTA", "UTCQMMA", "UTCIMMA", "UTCMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA", "IMMA",
        "SYNCS", "UCGABAR", "MUFU.TANH", "MUFU.EX2", "RED.E.ADD", "REDG", "ATOMG", "LDGSTS", "ACQBULK", "ELECT")
 out = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True).stdout
 counts, name = collections.OrderedDict(), None

@@ -88,5 +88,8 @@ def test_hot_kernels_use_the_blackwell_paths_in_sass():
     need("rnn_step_fwd_tc_kernel", "UTCHMMA", "UTMALDG", "LDTM")      # TMA-fed tf32 step kernels
     need("rnn_step_bwd_tc_kernel", "UTCHMMA", "UTMALDG", "LDTM")
     need("gemm_tma_kernel", "UTCHMMA", "UTMALDG", "LDTM")             # TMA-fed tcgen05 GEMM
+    need("gemm_pair_kernel", "UTCHMMA.2CTA", "UTMALDG", "LDTM", "UCGABAR")            # CTA-pair (cta_group::2) bf16 GEMM
+    need("lstm_step_fwd_pair_kernel", "UTCHMMA.2CTA", "UTMALDG", "LDTM", "UCGABAR")   # CTA-pair recurrent step kernels
+    need("lstm_step_bwd_pair_kernel", "UTCHMMA.2CTA", "UTMALDG", "LDTM", "UCGABAR")
     need("mha_tc_fwd_kernel", "HMMA")                                 # warp-level tf32 MMA attention
     need("mha_tc_bwd_kernel", "HMMA")
