@@ -118,6 +118,9 @@ int slnlp_cast_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, i
  * CTA-pair GEMM reads (nn.LSTM inter-layer dropout, bkp:100, at data-parallel batch sizes). */
 int slnlp_dropout_bf16(const float* x, uint16_t* y, int64_t n, float p, const uint64_t* rng, uint32_t site,
                        slnlp_stream_t stream);
+/* the same from a bf16 input, also leaving the keep mask (bit i % 32 of word i / 32; n a multiple of 128) */
+int slnlp_dropout_bf16_masked(const uint16_t* xb, uint16_t* y, uint32_t* keep_bits, int64_t n, float p,
+                              const uint64_t* rng, uint32_t site, slnlp_stream_t stream);
 /* slnlp_colsum_f32 over a bf16 matrix (the bf16 d(pre-activations) of the large-batch path); cols and lda
  * multiples of 4. */
 int slnlp_colsum_bf16(const uint16_t* A, int rows, int cols, int64_t lda, float* out, float beta,
@@ -227,7 +230,13 @@ int slnlp_rnn_layer_fwd_bf16(int mode, int T, int B, int H, int ndir, float* gat
 int slnlp_rnn_layer_bwd_bf16(int mode, int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, float* stash,
                              const float* out, const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout,
                              const float* dh_final, const float* dc_final, float* carry, int write_f32,
-                             slnlp_stream_t stream);
+                             const uint32_t* dout_keep, float dout_scale, slnlp_stream_t stream);
+/* 1 where the two calls above run the persistent CTA-pair step kernels (rnn_step_pair.cu: LSTM, two directions,
+ * B > 256, H = 256 / 512 / 1024).  Only those accept out = NULL in the forward (nobody reads the fp32 copy of a
+ * lower layer's output once its consumers take out_bf) and, in the backward, dout_keep: the keep mask of the
+ * inter-layer dropout above this layer (slnlp_dropout_bf16_masked), one bit per element of dout, applied with
+ * dout_scale = 1 / (1 - p) while dout is read - instead of a dropout pass over the gradient. */
+int slnlp_rnn_bf16_pair_supported(int mode, int T, int B, int H, int ndir);
 /* pad_packed_sequence(padding_value) on the top layer (bkp:120-123): rows t >= len
  * of x [T,B,W] are set to `value` (1.0 going forward, 0.0 before BPTT). */
 int slnlp_pad_fill(float* x, const int64_t* lengths, int T, int B, int W, float value,

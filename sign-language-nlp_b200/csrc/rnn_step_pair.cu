@@ -175,7 +175,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
       float* gp = p.gates + rb * GH + unit;
       float* sp = p.stash + rb * HT + unit;
       const float* pp = sp + (int64_t)(tp - t) * B * SH;                // c_{t-1} of the same sequences
-      float* op = p.out + rb * HT + unit;
+      float* op = p.out ? p.out + rb * HT + unit : nullptr;      // NULL: nobody reads the fp32 copy of this layer's output
       __nv_bfloat16* obp = p.out_bf + rb * HT + unit;
       float* hfp = p.h_final ? p.h_final + ((int64_t)d * B + b0) * HT + unit : nullptr;
       const int64_t* lp = p.lengths ? p.lengths + b0 : nullptr;
@@ -236,7 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
           const int ln = len[buf][x];
           if (ln < 0) continue;
           if (t >= ln) {
-            op[j * SH] = 0.f;
+            if (op) op[j * SH] = 0.f;
             sp[j * SH] = 0.f;
             obp[j * SH] = __float2bfloat16_rn(0.f);
             continue;
@@ -249,7 +249,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
           const float hv = go * tanh_fast(cc);
           gp[j * SG] = gi; gp[j * SG + HT] = gf; gp[j * SG + 2 * HT] = gg; gp[j * SG + 3 * HT] = go;
           sp[j * SH] = cc;
-          op[j * SH] = hv;
+          if (op) op[j * SH] = hv;
           obp[j * SH] = __float2bfloat16_rn(hv);
           if (hfp && (d == 0 ? t == ln - 1 : t == 0)) hfp[j * HT] = hv;
         }
@@ -270,6 +270,8 @@ struct PairBwd {
   const int64_t* lengths;
   const float *dout, *dh_final, *dc_final;
   float* carry;
+  const uint32_t* dout_keep;   // optional keep mask of the dropout between this layer and the next (1 bit per element of dout)
+  float dout_scale;            // 1 / (1 - p)
 };
 
 // mapW: w_hhT_bf as [ndir][H][4H], box {64, 128, 1}; mapG: dg_bf as [T][B][ndir*4H], box {64, 64, 1}
@@ -356,11 +358,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
       const float* sp = p.stash + rb * HT + unit;
       const float* pp = sp + (int64_t)(tp - t) * B * SH;
       const float* dop = p.dout ? p.dout + rb * HT + unit : nullptr;
+      // dout is the gradient of the DROPPED output when a keep mask comes along: 32 lanes = 32 consecutive units = one word
+      const uint32_t* kp = (p.dout_keep && dop) ? p.dout_keep + ((rb * HT + (unit & ~31)) >> 5) : nullptr;
       const int64_t ci0 = ((int64_t)d * B + b0) * HT + unit;
       float* cp = p.carry + ci0;
       const int64_t* lp = p.lengths ? p.lengths + b0 : nullptr;
       float gv[2][G][4], sv[2][4], pv[2][4], dh[2][4], cr[2][4];
+      uint32_t kw[2][4];
       int len[2][4];
+      const float dscale = kp ? p.dout_scale : 1.f;
       auto fetch = [&](int ch, int buf) {
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
@@ -376,6 +382,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
           sv[buf][x] = live ? sp[j * SH] : 0.f;
           pv[buf][x] = (live && has_prev) ? pp[j * SH] : 0.f;
           dh[buf][x] = (live && dop) ? dop[j * SH] : 0.f;
+          kw[buf][x] = (kp && live) ? kp[j * (SH / 32)] : 0xFFFFFFFFu;      // only LOADS here: arithmetic on a loaded value
+                                                                            // would wait for it and end the prefetch
           cr[buf][x] = live ? cp[j * HT] : 0.f;
         }
       };
@@ -415,7 +423,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
             for (int g = 0; g < G; ++g) og[g] = 0.f;
           } else {
             const bool inject = d == 0 ? t == ln - 1 : t == 0;
-            float dhx = dh[buf][x], cin = cr[buf][x];
+            float dhx = ((kw[buf][x] >> lane) & 1u) ? dh[buf][x] * dscale : 0.f, cin = cr[buf][x];
             if (inject) {          // final-state gradients enter here instead of the recurrent ones (warp-uniform: one sequence)
               if (p.dh_final) dhx += p.dh_final[ci0 + j * HT];
               cin = p.dc_final ? p.dc_final[ci0 + j * HT] : 0.f;
@@ -494,14 +502,15 @@ int lstm_layer_fwd_pairstep(int T, int B, int H, int ndir, float* gates, const u
 
 int lstm_layer_bwd_pairstep(int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, const float* stash,
                             const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout, const float* dh_final,
-                            const float* dc_final, float* carry, int write_f32, cudaStream_t s) {
+                            const float* dc_final, float* carry, int write_f32, const uint32_t* dout_keep, float dout_scale,
+                            cudaStream_t s) {
   if (!pair_step_ok(T, B, H, ndir)) return -1;
   if (((uintptr_t)w_hhT_bf | (uintptr_t)dg_bf) & 15) return -1;
   CUtensorMap mapW, mapG;
   if (!tensor_map3_bf16(w_hhT_bf, (uint64_t)4 * H, H, ndir, (uint64_t)4 * H, (uint64_t)4 * H * H, 128, &mapW)) return -1;
   if (!tensor_map3_bf16(dg_bf, (uint64_t)ndir * 4 * H, B, T, (uint64_t)ndir * 4 * H, (uint64_t)B * ndir * 4 * H, 64, &mapG)) return -1;
   PairBwd p{T, B, H, ndir, 0, H / 256, ceil_div(B, 128), 0, write_f32, gates, reinterpret_cast<__nv_bfloat16*>(dg_bf), stash,
-            lengths, dout, dh_final, dc_final, carry};
+            lengths, dout, dh_final, dc_final, carry, dout_keep, dout_scale};
   p.tiles = ndir * p.tiles_u * p.tiles_s;
   const int sms = sm_count() > 0 ? sm_count() : 148;
   dim3 grid(2 * std::min(p.tiles, sms / 2));

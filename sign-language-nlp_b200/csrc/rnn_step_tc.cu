@@ -658,7 +658,8 @@ int lstm_layer_fwd_pairstep(int T, int B, int H, int ndir, float* gates, const u
                             const int64_t* lengths, float* out, uint16_t* out_bf, float* stash, float* h_final, cudaStream_t s);
 int lstm_layer_bwd_pairstep(int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, const float* stash,
                             const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout, const float* dh_final,
-                            const float* dc_final, float* carry, int write_f32, cudaStream_t s);
+                            const float* dc_final, float* carry, int write_f32, const uint32_t* dout_keep, float dout_scale,
+                            cudaStream_t s);
 static bool pair_step_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -676,11 +677,12 @@ extern "C" int slnlp_rnn_layer_fwd_bf16(int mode, int T, int B, int H, int ndir,
   using namespace slnlp;
   SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM || mode == SLNLP_MODE_GRU, "rnn_layer_fwd_bf16: bad mode %d", mode);
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_fwd_bf16: bad shape");
-  SLNLP_CHECK_ARG(gates && w_hh_bf && b_hh && out && out_bf && stash, "rnn_layer_fwd_bf16: null pointer");
+  SLNLP_CHECK_ARG(gates && w_hh_bf && b_hh && out_bf && stash, "rnn_layer_fwd_bf16: null pointer");
   if (mode == SLNLP_MODE_LSTM && pair_step_enabled()) {
     const int rp = lstm_layer_fwd_pairstep(T, B, H, ndir, gates, w_hh_bf, b_hh, lengths, out, out_bf, stash, h_final, as_stream(stream));
     if (rp >= 0) return rp;
   }
+  SLNLP_CHECK_ARG(out, "rnn_layer_fwd_bf16: out = NULL (bf16 copy only) needs the CTA-pair kernels: ask slnlp_rnn_bf16_pair_supported");
   const int rc = rnn_layer_fwd_bfstep(mode, T, B, H, ndir, gates, w_hh_bf, b_hh, lengths, out, out_bf, stash, h_final, as_stream(stream));
   SLNLP_CHECK_ARG(rc >= 0, "rnn_layer_fwd_bf16: needs H a multiple of 64 and 16-byte aligned operands");
   return rc;
@@ -689,20 +691,27 @@ extern "C" int slnlp_rnn_layer_fwd_bf16(int mode, int T, int B, int H, int ndir,
 extern "C" int slnlp_rnn_layer_bwd_bf16(int mode, int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, float* stash,
                                         const float* out, const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout,
                                         const float* dh_final, const float* dc_final, float* carry, int write_f32,
-                                        slnlp_stream_t stream) {
+                                        const uint32_t* dout_keep, float dout_scale, slnlp_stream_t stream) {
   using namespace slnlp;
   SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM, "rnn_layer_bwd_bf16: LSTM only (mode %d)", mode);
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_bwd_bf16: bad shape");
   SLNLP_CHECK_ARG(gates && dg_bf && stash && out && w_hhT_bf && carry, "rnn_layer_bwd_bf16: null pointer");
   if (pair_step_enabled()) {
     const int rp = lstm_layer_bwd_pairstep(T, B, H, ndir, gates, dg_bf, stash, w_hhT_bf, lengths, dout, dh_final, dc_final, carry, write_f32,
-                                           as_stream(stream));
+                                           dout_keep, dout_scale, as_stream(stream));
     if (rp >= 0) return rp;
   }
+  SLNLP_CHECK_ARG(!dout_keep, "rnn_layer_bwd_bf16: a dropout keep mask needs the CTA-pair kernels: ask slnlp_rnn_bf16_pair_supported");
   const int rc = rnn_layer_bwd_bfstep(mode, T, B, H, ndir, gates, dg_bf, stash, out, w_hhT_bf, lengths, dout, dh_final, dc_final,
                                       carry, as_stream(stream));
   SLNLP_CHECK_ARG(rc >= 0, "rnn_layer_bwd_bf16: needs H a multiple of 128 and 16-byte aligned operands");
   return rc;
+}
+
+// 1 where slnlp_rnn_layer_fwd/bwd_bf16 run the persistent CTA-pair kernels (the forms with out = NULL / a keep mask)
+extern "C" int slnlp_rnn_bf16_pair_supported(int mode, int T, int B, int H, int ndir) {
+  return (mode == SLNLP_MODE_LSTM && slnlp::pair_step_enabled() && T > 1 && B > 256 && ndir == 2 && (H == 256 || H == 512 || H == 1024) &&
+          slnlp::encode_fn() != nullptr) ? 1 : 0;
 }
 
 extern "C" int slnlp_rnn_bf16_step_supported(int mode, int T, int B, int H, int ndir) {

@@ -43,12 +43,14 @@ SIGNATURES = {
     "slnlp_colsum_f32": [P, I, I, I, P, F, P],
     "slnlp_colsum_bf16": [P, I, I, L, P, F, P],
     "slnlp_dropout_bf16": [P, P, L, F, P, U32, P],
+    "slnlp_dropout_bf16_masked": [P, P, P, L, F, P, U32, P],
     "slnlp_rnn_layer_fwd": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
     "slnlp_rnn_layer_bwd": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "slnlp_rnn_extras_supported": [I, I, I, I, I],
     "slnlp_rnn_bf16_step_supported": [I, I, I, I, I],
     "slnlp_rnn_layer_fwd_bf16": [I, I, I, I, I, P, P, P, P, P, P, P, P, P],
-    "slnlp_rnn_layer_bwd_bf16": [I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P],
+    "slnlp_rnn_layer_bwd_bf16": [I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P, F, P],
+    "slnlp_rnn_bf16_pair_supported": [I, I, I, I, I],
     "slnlp_rnn_layer_fwd_ex": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "slnlp_rnn_layer_bwd_ex": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "slnlp_dec_cell_fwd": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, F, P, U32, P],

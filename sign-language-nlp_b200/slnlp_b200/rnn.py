@@ -203,7 +203,8 @@ class RnnEncDecB200(FlatParamModule):
                 # write themselves, W_hh from a bf16 copy) - the recurrence there is bound by operand bytes
                 self._cast_bf16(self._ptr(f"{pre}weight_hh_l{l}"), H, ws.w_hh_bf[l], 2 * G * H, H)
                 check(lib.slnlp_rnn_layer_fwd_bf16(mode, T, B, H, 2, ws.enc_gates[l].data_ptr(), ws.w_hh_bf[l].data_ptr(),
-                                                   self._ptr(f"{pre}bias_hh_l{l}"), lp, ws.enc_out[l].data_ptr(),
+                                                   self._ptr(f"{pre}bias_hh_l{l}"), lp,
+                                                   None if ws.skip_out32[l] else ws.enc_out[l].data_ptr(),
                                                    ws.out_bf[l].data_ptr(), ws.enc_stash[l].data_ptr(),
                                                    ws.enc_hfin[l].data_ptr(), s), "rnn_layer_fwd_bf16")
             else:
@@ -212,7 +213,11 @@ class RnnEncDecB200(FlatParamModule):
                                               lp, None, None, ws.enc_out[l].data_ptr(), ws.enc_stash[l].data_ptr(),
                                               ws.enc_hfin[l].data_ptr(), s), "rnn_layer_fwd")
             if l < L - 1 and drop:
-                if ws.bf_in[l + 1]:    # every consumer of the next layer's input reads bf16: one pass, no fp32 copy
+                if ws.masked[l]:       # bf16 in, bf16 out, and the keep mask as bits for this layer's BPTT
+                    check(lib.slnlp_dropout_bf16_masked(ws.out_bf[l].data_ptr(), ws.xin_bf[l + 1].data_ptr(),
+                                                        ws.keep_bits[l].data_ptr(), ws.out_bf[l].numel(), self.p_rnn, rng, l, s),
+                          "dropout_bf16_masked")
+                elif ws.bf_in[l + 1]:    # every consumer of the next layer's input reads bf16: one pass, no fp32 copy
                     check(lib.slnlp_dropout_bf16(ws.enc_out[l].data_ptr(), ws.xin_bf[l + 1].data_ptr(),
                                                  ws.enc_out[l].numel(), self.p_rnn, rng, l, s), "dropout_bf16")
                 else:
@@ -400,7 +405,9 @@ class RnnEncDecB200(FlatParamModule):
                                               ws.w_hhT_bf[l].data_ptr() + 2 * d * GH * H, GH, GH, H, 1, s), "cast_bf16")
                 check(lib.slnlp_rnn_layer_bwd_bf16(mode, T, B, H, 2, dg, ws.dg_bf[l].data_ptr(), st, out,
                                                    ws.w_hhT_bf[l].data_ptr(), lp, ws.d_seq.data_ptr(), ws.d_hfin.data_ptr(),
-                                                   None, ws.carry.data_ptr(), 0 if ws.dg_bf_only[l] else 1, s),
+                                                   None, ws.carry.data_ptr(), 0 if ws.dg_bf_only[l] else 1,
+                                                   ws.keep_bits[l].data_ptr() if ws.masked[l] else None,
+                                                   1.0 / (1.0 - self.p_rnn) if ws.masked[l] else 1.0, s),
                       "rnn_layer_bwd_bf16")
             else:
                 check(lib.slnlp_concat_dirs(ws.d_enc_final[l].data_ptr(), ws.d_hfin.data_ptr(), B, H, 2, 1, s),
@@ -429,7 +436,7 @@ class RnnEncDecB200(FlatParamModule):
                 if not dx_pair:
                     self._gemm(0, 0, T * B, D, 2 * GH, dg, 2 * GH, self._ptr(f"{pre}weight_ih_l{l}"), D,
                                ws.d_seq.data_ptr(), D, big=True)
-                if drop and not ws.rnn_fused_dropout:
+                if drop and not ws.rnn_fused_dropout and not ws.masked[l - 1]:    # masked: applied by layer l-1's BPTT
                     check(lib.slnlp_dropout(ws.d_seq.data_ptr(), ws.d_seq.data_ptr(), T * B * D, self.p_rnn,
                                             rng, l - 1, s), "dropout")
             else:
@@ -607,6 +614,14 @@ class _Workspace:
         self.dg_bf_only = [self.bf_step and self.bf_in[l] and m._pair_ok(T * B, dims[l], 2 * G * H) and
                            m._pair_ok(G * H, H, (T - 1) * B) for l in range(L)]
         self.xin_bf_ready = [l > 0 and ((drop and self.bf_in[l]) or (not drop and self.bf_step)) for l in range(L)]
+        # the persistent CTA-pair step kernels also take the inter-layer dropout's keep mask as bits (no dropout pass
+        # over the gradient) and can skip the fp32 copy of a lower layer's output when nothing reads it
+        pairk = self.bf_step and bool(lib.slnlp_rnn_bf16_pair_supported(MODE[m.rnn_type], T, B, H, 2))
+        self.masked = [pairk and drop and bwd and l < L - 1 and self.bf_in[l + 1] and (T * B * 2 * H) % 128 == 0 for l in range(L)]
+        self.keep_bits = [torch.empty(T * B * 2 * H // 32, dtype=torch.int32, device=dev) if self.masked[l] else None
+                          for l in range(L)]
+        self.skip_out32 = [pairk and l < L - 1 and (self.dg_bf_only[l] or not bwd) and
+                           (self.masked[l] if (drop and bwd) else (self.bf_in[l + 1] and not drop)) for l in range(L)]
         self.emb = f(T, B, E)
         self.enc_gates = [f(T, B, 2, G, H) for _ in range(L)]
         self.enc_stash = [f(T, B, 2, H) for _ in range(L)]

@@ -603,8 +603,33 @@ def test_rnn_layer_at_cfg4_shape_batch_4096_hidden_512(mode):
             assert torch.equal(out_bf, out.to(torch.bfloat16))        # the bf16 copy the GEMMs and the next step read
             L.check(L.lib.slnlp_rnn_layer_bwd_bf16(md, T, B, H, 2, gates.data_ptr(), dg_bf.data_ptr(), stash.data_ptr(),
                                                    out.data_ptr(), wT_bf.data_ptr(), len_d.data_ptr(), dout_tm.data_ptr(),
-                                                   dfin_d.data_ptr(), None, carry.data_ptr(), 1, S()))
+                                                   dfin_d.data_ptr(), None, carry.data_ptr(), 1, None, 1.0, S()))
             assert torch.equal(dg_bf, gates.to(torch.bfloat16))
+            if L.lib.slnlp_rnn_bf16_pair_supported(md, T, B, H, 2):
+                # the CTA-pair kernels' extras: forward without the fp32 copy of `out`; backward applying an inter-layer
+                # dropout keep mask (bits) to dout while reading it, bf16-only d(pre-activations)
+                g2 = torch.empty_like(gates)
+                L.check(L.lib.slnlp_gemm_f32(0, 1, T * B, 2 * G * H, D, x_tm.data_ptr(), D, w_ih.data_ptr(), D,
+                                             g2.data_ptr(), 2 * G * H, b_ih.data_ptr(), 0.0, None, 0, S()))
+                out_bf2, stash2, hfin2 = torch.empty_like(out_bf), torch.empty_like(stash), torch.empty_like(hfin)
+                L.check(L.lib.slnlp_rnn_layer_fwd_bf16(md, T, B, H, 2, g2.data_ptr(), w_bf.data_ptr(), b_hh.data_ptr(),
+                                                       len_d.data_ptr(), None, out_bf2.data_ptr(), stash2.data_ptr(),
+                                                       hfin2.data_ptr(), S()))
+                assert torch.equal(out_bf2, out_bf) and torch.equal(stash2, stash) and torch.equal(hfin2, hfin)
+                gk = torch.Generator().manual_seed(9)
+                keep = torch.rand(T, B, 2 * H, generator=gk) < 0.7
+                bits = (keep.view(-1, 32).to(torch.int64) << torch.arange(32)).sum(1)
+                bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32).cuda()
+                scale = 1.0 / 0.7
+                dg_a, dg_b = torch.empty_like(dg_bf), torch.empty_like(dg_bf)
+                for dgx, dsrc, kb, sc in ((dg_a, dout_tm * keep.cuda() * scale, None, 1.0), (dg_b, dout_tm, bits, scale)):
+                    carry.zero_()
+                    L.check(L.lib.slnlp_rnn_layer_bwd_bf16(md, T, B, H, 2, g2.data_ptr(), dgx.data_ptr(), stash2.data_ptr(),
+                                                           out.data_ptr(), wT_bf.data_ptr(), len_d.data_ptr(), dsrc.data_ptr(),
+                                                           dfin_d.data_ptr(), None, carry.data_ptr(), 0,
+                                                           kb.data_ptr() if kb is not None else None, sc, S()))
+                assert torch.equal(dg_a, dg_b)
+                assert rel_err(dg_a.float(), gates) > 1e-3          # the mask did change the gradient
         else:
             c0 = L.lib.slnlp_launch_count()
             L.check(L.lib.slnlp_rnn_layer_fwd(md, prec, T, B, H, 2, gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(),
@@ -747,6 +772,17 @@ def test_dropout_bf16_draws_the_mask_of_dropout_and_colsum_bf16_sums():
     out2 = torch.ones(200, device="cuda")
     L.check(L.lib.slnlp_colsum_bf16(A.data_ptr() + 2 * 8, 100, 200, 264, out2.data_ptr(), 0.0, S()))
     assert rel_err(out2, A[:100, 8:208].double().sum(0)) < 1e-5
+    # bf16 in, bf16 out, keep mask as bits: the mask of slnlp_dropout(site)
+    n2 = 128 * 37
+    xb = cuda(n2, seed=94).to(torch.bfloat16)
+    yb, bits = torch.empty(n2, dtype=torch.bfloat16, device="cuda"), torch.empty(n2 // 32, dtype=torch.int32, device="cuda")
+    L.check(L.lib.slnlp_dropout_bf16_masked(xb.data_ptr(), yb.data_ptr(), bits.data_ptr(), n2, 0.3, rng.data_ptr(), 4, S()))
+    ones, m32 = torch.ones(n2, device="cuda"), torch.empty(n2, device="cuda")
+    L.check(L.lib.slnlp_dropout(ones.data_ptr(), m32.data_ptr(), n2, 0.3, rng.data_ptr(), 4, S()))
+    keep = m32 != 0
+    got = ((bits.view(-1, 1).to(torch.int64) >> torch.arange(32, device="cuda")) & 1).view(-1).bool()
+    assert torch.equal(got, keep)
+    assert torch.equal(yb, torch.where(keep, xb.float() * (1.0 / 0.7), torch.zeros(n2, device="cuda")).to(torch.bfloat16))
 
 
 def test_concat_dirs_both_layouts():

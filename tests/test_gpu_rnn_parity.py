@@ -321,3 +321,30 @@ def test_large_batch_bf16_operand_path_against_the_reference(B, T, E, H, L):
     for k in rsd:
         err = float((sd[k].cpu() - rsd[k]).abs().max()) / max(float(rsd[k].abs().max()), 1e-3)
         assert err < BF16_RTOL, k
+
+
+def test_large_batch_path_with_dropout_matches_the_fp32_path_on_the_same_masks():
+    """Inter-layer dropout on the large-batch family: bf16 dropout from the bf16 layer output, keep mask as bits applied
+    by the BPTT kernels while they read the gradient.  The Philox stream is a function of (seed, step, site, element),
+    so the fp32 path of the same module draws the SAME masks: two training steps of both must agree within 2e-2."""
+    import model as dropin
+    from helpers import BF16_RTOL
+    from slnlp_b200.rnn import FusedTrainStep
+    from slnlp_b200.vocab import Vocab
+    B, T, E, H, L, Vs, Vt = 512, 33, 256, 256, 3, 4098, 1026
+    mods = []
+    for prec in ("fp32", "bf16"):
+        torch.manual_seed(11)
+        m = dropin.EncoderDecoderLSTMAttn(src_vocab=Vocab(size=Vs), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E,
+                                          hidden_size=H, num_layers=L, dropout=0.3, device=torch.device("cuda"), precision=prec, seed=5)
+        mods.append(m.to(torch.device("cuda")).train())
+    X, lengths, y = _synthetic(B, T, Vs, Vt, True)
+    steps = [FusedTrainStep(m, B, T, lr=0.05) for m in mods]
+    assert any(steps[1].ws.masked) and any(steps[1].ws.skip_out32), "the bf16 module must take the masked-dropout kernels"
+    for it in range(2):
+        l32, l16 = (float(ts.step(X.cuda(), y.cuda(), lengths.cuda())[0]) for ts in steps)
+        assert abs(l16 - l32) < BF16_RTOL * abs(l32), (it, l16, l32)
+    sd32, sd16 = mods[0].state_dict(), mods[1].state_dict()
+    for k in sd32:
+        err = float((sd16[k] - sd32[k]).abs().max()) / max(float(sd32[k].abs().max()), 1e-3)
+        assert err < BF16_RTOL, k
