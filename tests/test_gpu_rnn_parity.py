@@ -331,7 +331,7 @@ def test_large_batch_path_with_dropout_matches_the_fp32_path_on_the_same_masks()
     from helpers import BF16_RTOL
     from slnlp_b200.rnn import FusedTrainStep
     from slnlp_b200.vocab import Vocab
-    B, T, E, H, L, Vs, Vt = 512, 33, 256, 256, 3, 4098, 1026
+    B, T, E, H, L, Vs, Vt = 512, 33, 1024, 512, 2, 4098, 1026      # every GEMM of the layer large enough for the pair kernel
     mods = []
     for prec in ("fp32", "bf16"):
         torch.manual_seed(11)
