@@ -301,6 +301,10 @@ int slnlp_ce_on_logp(const float* logp, const int64_t* y, int64_t ignore_index, 
 int slnlp_logsoftmax_ce_fused(const float* logits, const int64_t* y, int64_t ignore_index, int B, int V,
                               float* logp, float* loss_out, float* dlogits, int ld_dlogits, float* row_ws,
                               slnlp_stream_t stream);
+/* the mean-loss reduction of slnlp_logsoftmax_ce_fused as a call of its own: with loss_out = NULL there, the row
+ * losses stay in row_ws and this reduces them to loss_out = {mean loss over valid rows, n_valid} - nothing on the
+ * backward chain reads the loss, so the host runs it on a side stream. */
+int slnlp_ce_reduce(const float* row_ws, int B, float* loss_out, slnlp_stream_t stream);
 
 /* ---- K11/K12: GradientNormClipping -> clip_grad_norm_(max_norm, 2) (helper.py:227-229)
  * and torch.optim.SGD(momentum, nesterov=False) (config/*.yaml:39-42), over flat buffers.

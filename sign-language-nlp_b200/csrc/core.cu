@@ -787,13 +787,21 @@ int slnlp_ce_on_logp(const float* logp, const int64_t* y, int64_t ignore_index, 
 int slnlp_logsoftmax_ce_fused(const float* logits, const int64_t* y, int64_t ignore_index, int B, int V,
                               float* logp, float* loss_out, float* dlogits, int ld_dlogits, float* row_ws,
                               slnlp_stream_t stream) {
-  SLNLP_CHECK_ARG(logits && y && logp && loss_out && row_ws && B > 0 && V > 0, "logsoftmax_ce_fused: bad arguments");
+  SLNLP_CHECK_ARG(logits && y && logp && row_ws && B > 0 && V > 0, "logsoftmax_ce_fused: bad arguments");
   SLNLP_CHECK_ARG(!dlogits || ld_dlogits >= V, "logsoftmax_ce_fused: ld_dlogits < V");
   launch_pdl(logsoftmax_ce_fused_kernel, dim3(B), dim3(256), 0, as_stream(stream), logits, y, ignore_index, B, V, logp,
              row_ws, dlogits, ld_dlogits);
-  launch_pdl(ce_reduce_kernel, dim3(1), dim3(256), 0, as_stream(stream), row_ws, B, loss_out);
-  note_launches(1);
+  if (loss_out) {     // NULL: the caller reduces the row losses itself (slnlp_ce_reduce), off the backward chain
+    launch_pdl(ce_reduce_kernel, dim3(1), dim3(256), 0, as_stream(stream), row_ws, B, loss_out);
+    note_launches(1);
+  }
   SLNLP_LAUNCH_OK("logsoftmax_ce_fused");
+  return 0;
+}
+int slnlp_ce_reduce(const float* row_ws, int B, float* loss_out, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(row_ws && loss_out && B > 0, "ce_reduce: bad arguments");
+  launch_pdl(ce_reduce_kernel, dim3(1), dim3(256), 0, as_stream(stream), row_ws, B, loss_out);
+  SLNLP_LAUNCH_OK("ce_reduce");
   return 0;
 }
 

@@ -73,6 +73,7 @@ SIGNATURES = {
     "slnlp_log_softmax_bwd": [P, P, P, I, I, I, P],
     "slnlp_ce_on_logp": [P, P, L, I, I, P, P, I, P, P],
     "slnlp_logsoftmax_ce_fused": [P, P, L, I, I, P, P, P, I, P, P],
+    "slnlp_ce_reduce": [P, I, P, P],
     "slnlp_sumsq_partials": [],
     "slnlp_gradnorm": [P, L, P, P, P],
     "slnlp_sgd_momentum_clip": [P, P, P, L, P, P, F, P],

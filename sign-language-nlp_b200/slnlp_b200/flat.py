@@ -276,7 +276,7 @@ class FlatParamModule(nn.Module):
     # recurrent kernel.  Several lanes: the weight-gradient products of one layer are independent of each
     # other too, and each is a few CTAs of mostly fixed latency - side by side they cost one GEMM, in a
     # row (the last layer's, with nothing left to hide behind) they cost four
-    N_LANES = 4
+    N_LANES = 8
 
     def _side_stream(self, lane=0):
         with torch.cuda.device(self._flat.device):

@@ -467,7 +467,11 @@ class RnnEncDecB200(FlatParamModule):
         pre = "model.encoder.rnn."
         dg, st, out = ws.enc_gates[l].data_ptr(), ws.enc_stash[l].data_ptr(), ws.enc_out[l].data_ptr()
         xin = (ws.emb if l == 0 else ws.enc_xin[l]).data_ptr()
-        lane = (lambda i: self._side_branch(i)) if parallel else (lambda i: contextlib.nullcontext())
+        # consecutive layers alternate between two sets of four lanes: a lane is a FIFO, and layer l+1's weight-gradient
+        # GEMMs - still running, slowly, beside layer l's BPTT - would otherwise hold back layer l's (the LAST layer's
+        # then trail the step: measured 42 us after the final BPTT for three 10 us GEMMs)
+        base = 4 * (l % 2)
+        lane = (lambda i: self._side_branch(base + i)) if parallel else (lambda i: contextlib.nullcontext())
         pair = ws.pair[l]
         with lane(0):
             if pair and self._pair_ok(2 * GH, D, T * B):
@@ -798,9 +802,15 @@ class FusedTrainStep:
             if not getattr(m, "_joins_rng_lane", False):
                 m._join_lane(3)
         m._run_forward(ws, self.X, self.lengths, self.y)
+        # nothing in backward reads the mean loss (the gradient carries its own 1 / n_valid): under capture its reduction
+        # leaves the chain for a side lane; the data-parallel exchange weights by n_valid and keeps it in stream
+        loss_aside = self.grad_sync is None and torch.cuda.is_current_stream_capturing()
         check(lib.slnlp_logsoftmax_ce_fused(ws.logits.data_ptr(), self.y.data_ptr(), m.tgt_pad, self.B, m.V_tgt,
-                                            ws.logp.data_ptr(), ws.loss.data_ptr(), ws.dlogits.data_ptr(), ws.Vp,
-                                            ws.row_ws.data_ptr(), s), "logsoftmax_ce")
+                                            ws.logp.data_ptr(), None if loss_aside else ws.loss.data_ptr(),
+                                            ws.dlogits.data_ptr(), ws.Vp, ws.row_ws.data_ptr(), s), "logsoftmax_ce")
+        if loss_aside:
+            with m._side_branch(7):
+                check(lib.slnlp_ce_reduce(ws.row_ws.data_ptr(), self.B, ws.loss.data_ptr(), _stream()), "ce_reduce")
         bucketed = getattr(self.grad_sync, "bucketed", False)
         if bucketed:     # data parallel: gradient ranges are exchanged while the rest of backward runs (dp.py)
             self.grad_sync.begin(ws.loss)
@@ -813,6 +823,7 @@ class FusedTrainStep:
             self.grad_sync.finish(self.gflat, ws.loss)
         elif self.grad_sync is not None:
             self.grad_sync(self.gflat, ws.loss)
+        m._join_side()      # every side lane (weight gradients, the loss reduction) is back before the optimizer
         n = m._numel
         check(lib.slnlp_gradnorm(self.gflat.data_ptr(), n, self.partials.data_ptr(), self.norm.data_ptr(), s), "gradnorm")
         check(lib.slnlp_sgd_momentum_clip_zero(m._flat.data_ptr(), self.gflat.data_ptr(), self.buf.data_ptr(), n,
