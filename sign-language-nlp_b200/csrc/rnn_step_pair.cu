@@ -95,7 +95,7 @@ template <int HT, int SEQ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
     lstm_step_fwd_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapH, PairFwd p) {
   extern __shared__ uint8_t smem_dyn[];
-  constexpr int G = 4, NACC = 512 / (G * SEQ), BS = SEQ * 64;   // accumulator sets; bytes of a CTA's B tile (SEQ/2 rows)
+  constexpr int G = 4, NACC = (512 / (G * SEQ)) > 2 ? 2 : 512 / (G * SEQ), BS = SEQ * 64;   // accumulator sets (at most two); bytes of a CTA's B tile (SEQ/2 rows)
   constexpr int SPT = SEQ / RP_EG, NCH = SPT / 4;            // sequences per epilogue thread, chunks of four
   const int warp = warp_uniform(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
@@ -275,11 +275,12 @@ struct PairBwd {
 };
 
 // mapW: w_hhT_bf as [ndir][H][4H], box {64, 128, 1}; mapG: dg_bf as [T][B][ndir*4H], box {64, 64, 1}
-template <int HT>
+// SEQ = sequences per tile (128 / 64 / 32): the launcher takes the largest that still gives every cluster a tile
+template <int HT, int SEQ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
     lstm_step_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapG, PairBwd p) {
   extern __shared__ uint8_t smem_dyn[];
-  constexpr int G = 4, SEQ = 128;
+  constexpr int G = 4, BS = SEQ * 64, SPT = SEQ / RP_EG, NCH = SPT / 4;   // B tile bytes; sequences per thread; chunks of four
   const int warp = warp_uniform(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
@@ -287,7 +288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
   const bool has_next = p.step > 0;                 // the step processed just before this one exists
   const int nk = has_next ? GH / 64 : 0;
   const int per_dir = p.tiles_u * p.tiles_s;
-  PairRing r = pair_setup<RP_STAGES_B, RP_AB, RP_BS, 256>(smem_dyn, warp, &mapW, &mapG);
+  PairRing r = pair_setup<RP_STAGES_B, RP_AB, BS, (2 * SEQ < 32 ? 32 : 2 * SEQ)>(smem_dyn, warp, &mapW, &mapG);
   pdl_wait();
   pdl_launch_dependents();
 
@@ -298,14 +299,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
         const int d = tile / per_dir, rem = tile - d * per_dir;
         const int ub = rem / p.tiles_s, sb = rem - ub * p.tiles_s;
         const int t = d == 0 ? T - 1 - p.step : p.step, tn = d == 0 ? t + 1 : t - 1;
-        const int u0 = ub * 256 + (int)rank * 128, s0 = sb * SEQ + (int)rank * 64;
+        const int u0 = ub * 256 + (int)rank * 128, s0 = sb * SEQ + (int)rank * (SEQ / 2);
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const uint32_t s = it % RP_STAGES_B, round = it / RP_STAGES_B;
           if (round > 0) mbar_wait(&r.empty[s], (round - 1) & 1u);
-          if (rank == 0) mbar_expect_tx(&r.full[s], 2 * (RP_AB + RP_BS));
+          if (rank == 0) mbar_expect_tx(&r.full[s], 2 * (RP_AB + BS));
           const uint32_t bar = map_to_cta(smem_u32(&r.full[s]), 0);
           tma_load_3d_pair(r.sA + s * RP_AB, &mapW, bar, kb * 64, u0, d);
-          tma_load_3d_pair(r.sB + s * RP_BS, &mapG, bar, d * GH + kb * 64, s0, tn);
+          tma_load_3d_pair(r.sB + s * BS, &mapG, bar, d * GH + kb * 64, s0, tn);
         }
       }
     }
@@ -326,7 +327,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_bf16_pair(acc, dA + (uint64_t)((s * RP_AB + kk * 32) >> 4), dB + (uint64_t)((s * RP_BS + kk * 32) >> 4), idesc,
+              umma_bf16_pair(acc, dA + (uint64_t)((s * RP_AB + kk * 32) >> 4), dB + (uint64_t)((s * BS + kk * 32) >> 4), idesc,
                              (kb > 0 || kk > 0) ? 1u : 0u);
             umma_commit_pair(&r.empty[s]);
             if (kb == nk - 1) umma_commit_pair(&r.tfull[as]);
@@ -350,8 +351,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
       const bool has_prev = tp >= 0 && tp < T;
       const uint32_t as = tl & 1u, use = tl >> 1;
       const int unit = ub * 256 + (int)rank * 128 + q * 32 + lane;
-      const int b0 = sb * SEQ + e * 32;
-      const int nvalid = min(32, B - b0);
+      const int b0 = sb * SEQ + e * SPT;
+      const int nvalid = min(SPT, B - b0);
       const int64_t rb = ((int64_t)t * B + b0) * 2 + d;
       float* gp = p.gates + rb * GH + unit;
       __nv_bfloat16* gbp = p.dg_bf + rb * GH + unit;
@@ -393,17 +394,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
         tc_fence_after();
       }
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch = 0; ch < NCH; ++ch) {
         const int buf = ch & 1;
-        if (ch < 7) fetch(ch + 1, buf ^ 1);
+        if (ch < NCH - 1) fetch(ch + 1, buf ^ 1);
         float m[4];
         if (nk > 0) {
           uint32_t raw[4];
-          tmem_ld4_nowait(r.tmem + ((uint32_t)(q * 32) << 16) + as * SEQ + e * 32 + ch * 4, raw);
+          tmem_ld4_nowait(r.tmem + ((uint32_t)(q * 32) << 16) + as * SEQ + e * SPT + ch * 4, raw);
           tmem_wait_ld();
 #pragma unroll
           for (int x = 0; x < 4; ++x) m[x] = __uint_as_float(raw[x]);
-          if (ch == 7) {
+          if (ch == NCH - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader + as * 8);
@@ -451,7 +452,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 1) tmem_dealloc_pair(r.tmem, 256);
+  if (warp == 1) tmem_dealloc_pair(r.tmem, (2 * SEQ < 32 ? 32 : 2 * SEQ));
+}
+
+static int pair_seq_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SLNLP_PAIR_SEQ");
+    const int x = e ? atoi(e) : 0;
+    v = (x == 128 || x == 64 || x == 32) ? x : 0;
+  }
+  return v;
 }
 
 // hidden sizes with an instantiation (H is a template parameter of the epilogues); two directions only
@@ -465,17 +476,15 @@ int lstm_layer_fwd_pairstep(int T, int B, int H, int ndir, float* gates, const u
   if (((uintptr_t)w_hh_bf | (uintptr_t)out_bf) & 15) return -1;
   CUtensorMap mapW, mapH;
   if (!tensor_map3_bf16(w_hh_bf, H, (uint64_t)4 * H, ndir, H, (uint64_t)4 * H * H, 128, &mapW)) return -1;
-  // 64-sequence tiles (MMAs under the epilogue) unless $SLNLP_PAIR_SEQ=128
-  static int seq = 0;
-  if (!seq) {
-    const char* e = getenv("SLNLP_PAIR_SEQ");
-    seq = (e && atoi(e) == 128) ? 128 : 64;
-  }
+  // sequences per tile: 64 (two accumulator sets: MMAs under the epilogue), 32 when 64 would leave clusters without a
+  // tile (small per-rank batches of the data-parallel config); $SLNLP_PAIR_SEQ=128|64|32 forces one
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int seq = pair_seq_env();
+  if (!seq) seq = (ndir * (H / 256) * ceil_div(B, 64) >= sms / 2) ? 64 : 32;
   if (!tensor_map3_bf16(out_bf, (uint64_t)ndir * H, B, T, (uint64_t)ndir * H, (uint64_t)B * ndir * H, seq / 2, &mapH)) return -1;
   PairFwd p{T, B, H, ndir, 0, H / 256, ceil_div(B, seq), 0, gates, b_hh, lengths, out, reinterpret_cast<__nv_bfloat16*>(out_bf),
             stash, h_final};
   p.tiles = ndir * p.tiles_u * p.tiles_s;
-  const int sms = sm_count() > 0 ? sm_count() : 148;
   dim3 grid(2 * std::min(p.tiles, sms / 2));
   constexpr size_t sm = rp_smem(RP_STAGES_F, RP_AF + RP_BS);
   auto run = [&](auto kernel) {
@@ -485,15 +494,16 @@ int lstm_layer_fwd_pairstep(int T, int B, int H, int ndir, float* gates, const u
       launch_pdl(kernel, grid, dim3(RP_THREADS), sm, s, mapW, mapH, p);
     }
   };
-  if (seq == 64) {
-    if (H == 256) run(lstm_step_fwd_pair_kernel<256, 64>);
-    else if (H == 512) run(lstm_step_fwd_pair_kernel<512, 64>);
-    else run(lstm_step_fwd_pair_kernel<1024, 64>);
-  } else {
-    if (H == 256) run(lstm_step_fwd_pair_kernel<256, 128>);
-    else if (H == 512) run(lstm_step_fwd_pair_kernel<512, 128>);
-    else run(lstm_step_fwd_pair_kernel<1024, 128>);
-  }
+#define SLNLP_FWD(S)                                            \
+  do {                                                          \
+    if (H == 256) run(lstm_step_fwd_pair_kernel<256, S>);       \
+    else if (H == 512) run(lstm_step_fwd_pair_kernel<512, S>);  \
+    else run(lstm_step_fwd_pair_kernel<1024, S>);               \
+  } while (0)
+  if (seq == 128) SLNLP_FWD(128);
+  else if (seq == 64) SLNLP_FWD(64);
+  else SLNLP_FWD(32);
+#undef SLNLP_FWD
   note_launches(T);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("rnn_layer_fwd(pair step): launch failed: %s", cudaGetErrorString(e));
@@ -508,11 +518,20 @@ int lstm_layer_bwd_pairstep(int T, int B, int H, int ndir, float* gates, uint16_
   if (((uintptr_t)w_hhT_bf | (uintptr_t)dg_bf) & 15) return -1;
   CUtensorMap mapW, mapG;
   if (!tensor_map3_bf16(w_hhT_bf, (uint64_t)4 * H, H, ndir, (uint64_t)4 * H, (uint64_t)4 * H * H, 128, &mapW)) return -1;
-  if (!tensor_map3_bf16(dg_bf, (uint64_t)ndir * 4 * H, B, T, (uint64_t)ndir * 4 * H, (uint64_t)B * ndir * 4 * H, 64, &mapG)) return -1;
-  PairBwd p{T, B, H, ndir, 0, H / 256, ceil_div(B, 128), 0, write_f32, gates, reinterpret_cast<__nv_bfloat16*>(dg_bf), stash,
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int seq = pair_seq_env();
+  if (!seq) {
+    seq = 32;
+    for (int cand : {128, 64})
+      if (ndir * (H / 256) * ceil_div(B, cand) >= sms / 2) {
+        seq = cand;
+        break;
+      }
+  }
+  if (!tensor_map3_bf16(dg_bf, (uint64_t)ndir * 4 * H, B, T, (uint64_t)ndir * 4 * H, (uint64_t)B * ndir * 4 * H, seq / 2, &mapG)) return -1;
+  PairBwd p{T, B, H, ndir, 0, H / 256, ceil_div(B, seq), 0, write_f32, gates, reinterpret_cast<__nv_bfloat16*>(dg_bf), stash,
             lengths, dout, dh_final, dc_final, carry, dout_keep, dout_scale};
   p.tiles = ndir * p.tiles_u * p.tiles_s;
-  const int sms = sm_count() > 0 ? sm_count() : 148;
   dim3 grid(2 * std::min(p.tiles, sms / 2));
   constexpr size_t sm = rp_smem(RP_STAGES_B, RP_AB + RP_BS);
   auto run = [&](auto kernel) {
@@ -522,9 +541,16 @@ int lstm_layer_bwd_pairstep(int T, int B, int H, int ndir, float* gates, uint16_
       launch_pdl(kernel, grid, dim3(RP_THREADS), sm, s, mapW, mapG, p);
     }
   };
-  if (H == 256) run(lstm_step_bwd_pair_kernel<256>);
-  else if (H == 512) run(lstm_step_bwd_pair_kernel<512>);
-  else run(lstm_step_bwd_pair_kernel<1024>);
+#define SLNLP_BWD(S)                                            \
+  do {                                                          \
+    if (H == 256) run(lstm_step_bwd_pair_kernel<256, S>);       \
+    else if (H == 512) run(lstm_step_bwd_pair_kernel<512, S>);  \
+    else run(lstm_step_bwd_pair_kernel<1024, S>);               \
+  } while (0)
+  if (seq == 128) SLNLP_BWD(128);
+  else if (seq == 64) SLNLP_BWD(64);
+  else SLNLP_BWD(32);
+#undef SLNLP_BWD
   note_launches(T);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("rnn_layer_bwd(pair step): launch failed: %s", cudaGetErrorString(e));
