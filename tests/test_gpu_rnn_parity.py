@@ -283,8 +283,8 @@ def test_factored_six_field_embedding_variant(kind):
         m(X=X[..., :5].cuda(), y=y.cuda(), lengths=lengths.cuda())
 
 
-@pytest.mark.parametrize("B,T,E,H,L", [(512, 16, 256, 256, 3), (300, 40, 256, 384, 2)])
-def test_large_batch_bf16_operand_path_against_the_reference(B, T, E, H, L):
+@pytest.mark.parametrize("kind,B,T,E,H,L", [("lstm", 512, 16, 256, 256, 3), ("lstm", 300, 40, 256, 384, 2), ("gru", 512, 16, 256, 256, 2)])
+def test_large_batch_bf16_operand_path_against_the_reference(kind, B, T, E, H, L):
     """The family BASELINE.json configs[3] (data-parallel LSTM, batch 4096) runs on: CTA-pair bf16 GEMMs for the
     hoisted projections / dX / dW, bf16-operand per-step recurrent kernels writing bf16 copies of h_t and of
     d(pre-activations), bias sums over the bf16 copy, tensor-core decoder cell - against the torch.nn port of the
@@ -296,9 +296,10 @@ def test_large_batch_bf16_operand_path_against_the_reference(B, T, E, H, L):
     from slnlp_b200.vocab import Vocab
     Vs, Vt = 4098, 1026
     torch.manual_seed(7)
-    ref = port.build_port("lstm", Vs, Vt, E, H, L, dropout=0.0)
-    m = dropin.EncoderDecoderLSTMAttn(src_vocab=Vocab(size=Vs), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E,
-                                      hidden_size=H, num_layers=L, dropout=0.0, device=torch.device("cuda"), precision="bf16")
+    ref = port.build_port(kind, Vs, Vt, E, H, L, dropout=0.0)
+    cls = dropin.EncoderDecoderLSTMAttn if kind == "lstm" else dropin.EncoderDecoderGRUAttn
+    m = cls(src_vocab=Vocab(size=Vs), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E,
+            hidden_size=H, num_layers=L, dropout=0.0, device=torch.device("cuda"), precision="bf16")
     m.load_state_dict(ref.state_dict())
     m = m.to(torch.device("cuda"))
     X, lengths, y = _synthetic(B, T, Vs, Vt, True)
@@ -311,7 +312,8 @@ def test_large_batch_bf16_operand_path_against_the_reference(B, T, E, H, L):
     assert rel_err(got, want) < BF16_RTOL
     m.train()
     ts = FusedTrainStep(m, B, T, lr=0.01)
-    assert all(ts.ws.pair) and ts.ws.bf_step, "the shape must take the large-batch kernels this test is about"
+    # GRU: CTA-pair GEMMs around the tf32 per-step recurrent kernels (the bf16 step kernels' backward is LSTM-only)
+    assert all(ts.ws.pair) and ts.ws.bf_step == (kind == "lstm"), "the shape must take the large-batch kernels this test is about"
     opt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9)
     for step in range(2):
         want_loss = port.reference_train_step(ref, opt, X, y, lengths)
