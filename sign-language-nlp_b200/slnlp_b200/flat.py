@@ -260,14 +260,14 @@ class FlatParamModule(nn.Module):
         return self.f32_tensor_cores if env is None else env != "0"
 
     def _gemm_ws(self):
-        """Split-K scratch of the GEMMs of this module: one buffer per stream the module launches on
-        (the main stream and the weight-gradient side lanes never share partials)."""
-        key = torch.cuda.current_stream().cuda_stream
-        pool = self.__dict__.setdefault("_gemm_scratch", {})
-        if not isinstance(pool, dict):
-            pool = self.__dict__["_gemm_scratch"] = {}
+        """Split-K scratch of the GEMMs: one buffer per (thread, device, stream) - kernels on one stream are ordered, so
+        the modules a thread steps one after another share it (the main stream and the weight-gradient side lanes never
+        share partials).  Per MODULE it cost a grid-search fit ~9 fresh 10 MB allocations: 19 ms of a 71 ms fit at
+        emb 128 / hidden 128 / 2 layers, 130 of 254 ms at 512 / 256 / 4 (profiles/prof_grid_fit.py)."""
+        key = (self._flat.device, torch.cuda.current_stream().cuda_stream)
+        pool = _tls.__dict__.setdefault("gemm_scratch", {})
         ws = pool.get(key)
-        if ws is None or ws.device != self._flat.device:
+        if ws is None:
             ws = pool[key] = torch.empty(lib.slnlp_gemm_workspace_floats(), device=self._flat.device)
         return ws
 
