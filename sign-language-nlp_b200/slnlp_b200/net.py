@@ -164,6 +164,15 @@ class NeuralNetClassifier(ClassifierMixin, BaseEstimator):
         fit_seed = getattr(self, "_fit_seed", None)
         if fit_seed is None:
             self.module_ = mod_cls(**mkw).to(dev)
+        elif getattr(mod_cls, "accepts_init_generator", False):
+            # a seeded fit (grid farm) of a module that draws its initial weights from a generator it is GIVEN: a private
+            # one per fit - the same stream torch.manual_seed(fit_seed) would give, without touching (or queueing on) the
+            # process-global generator the other worker threads share.  (Under the lock below the seeded construction of
+            # every fit was one critical section: ~100 ms per fit on average over the LSTM grid, which capped the packed
+            # farm at the same fits/hour for 2, 4 or 6 fits per GPU.)
+            mkw.setdefault("seed", fit_seed)
+            mkw["init_generator"] = torch.Generator().manual_seed(fit_seed)
+            self.module_ = mod_cls(**mkw).to(dev)
         else:
             # a seeded fit (grid farm): the process-global torch generator is shared by every worker thread,
             # so the seeded construction is one critical section and leaves the generator as it found it

@@ -36,6 +36,7 @@ from .flat import CAPTURE_LOCK, FlatParamModule, _Box, _align4, _stream, capture
 
 class RnnEncDecB200(FlatParamModule):
     MAX_OUTPUT_LEN = 1  # bkp:332
+    accepts_init_generator = True     # __init__(init_generator=torch.Generator): see _build_parameters
     _joins_rng_lane = True   # _run_forward joins side lane 3 (rng advance + dropout factors) before the first RNN layer
     _dead = ("model.decoder.pre_output_layer.weight",)
 
@@ -77,29 +78,59 @@ class RnnEncDecB200(FlatParamModule):
         self.overlap_dw = (self.H == 128) if env is None else env != "0"
         # the small decoder / generator / attention / bridge weight gradients always leave the chain
         self.overlap_small = os.environ.get("SLNLP_OVERLAP_SMALL", "1") != "0"
-        self._build_parameters()
+        self._build_parameters(kwargs.get("init_generator", None))
         self.seed = int(kwargs.get("seed", torch.initial_seed() & 0x7FFFFFFF))
 
     # ------------------------------------------------------------------ parameters
-    def _build_parameters(self):
+    def _build_parameters(self, gen=None):
         E, H, L, G = self.E, self.H, self.L, self.G
-        rnn_cls = nn.LSTM if self.rnn_type == "lstm" else nn.GRU
-        # default initialisers drawn in the reference's construction order (bkp:362-381):
-        # Encoder.rnn, attention (key, query, energy), Decoder.rnn, bridge, pre_output,
-        # src Embedding, trg Embedding, Generator.  torch.nn is used for init only.
-        t_enc = rnn_cls(E, H, L, batch_first=True, bidirectional=True)
-        t_key = nn.Linear(2 * H, H, bias=False)
-        t_query = nn.Linear(H, H, bias=False)
-        t_energy = nn.Linear(H, 1, bias=False)
-        t_dec = rnn_cls(E + 2 * H, H, L, batch_first=True)
-        t_bridge = nn.Linear(2 * H, H, bias=True)
-        t_pre = nn.Linear(3 * H + E, H, bias=False)
+        # default initialisers drawn in the reference's construction order (bkp:362-381): Encoder.rnn, attention (key,
+        # query, energy), Decoder.rnn, bridge, pre_output, src Embedding, trg Embedding, Generator - the draws torch.nn's
+        # reset_parameters() make (RNNBase: uniform(+-1/sqrt(H)) over its parameters in registration order; Linear:
+        # kaiming_uniform(a = sqrt 5) then the bias; Embedding: normal, padding row zeroed), on plain tensors.  `gen` =
+        # None draws from the process-global CPU generator like torch.nn would (same torch.manual_seed -> the
+        # reference's initial weights, tests/test_host_logic.py); the grid farm passes a PRIVATE generator per fit, so
+        # that concurrent fits neither share nor serialise on the global one.
+        import math
+        from types import SimpleNamespace as NS
+        init = nn.init
+
+        def rnn(D_in, bidirectional):
+            ns, stdv = NS(), (1.0 / math.sqrt(H) if H > 0 else 0)
+            for l in range(L):
+                d_in = D_in if l == 0 else H * (2 if bidirectional else 1)
+                for suf in (("", "_reverse") if bidirectional else ("",)):
+                    for kind, shape in (("weight_ih", (G * H, d_in)), ("weight_hh", (G * H, H)), ("bias_ih", (G * H,)),
+                                        ("bias_hh", (G * H,))):
+                        setattr(ns, f"{kind}_l{l}{suf}", init.uniform_(torch.empty(*shape), -stdv, stdv, generator=gen))
+            return ns
+
+        def linear(d_in, d_out, bias):
+            ns = NS(weight=init.kaiming_uniform_(torch.empty(d_out, d_in), a=math.sqrt(5), generator=gen), bias=None)
+            if bias:
+                bound = 1 / math.sqrt(d_in) if d_in > 0 else 0
+                ns.bias = init.uniform_(torch.empty(d_out), -bound, bound, generator=gen)
+            return ns
+
+        def embedding(rows, width, padding_idx):
+            w = init.normal_(torch.empty(rows, width), generator=gen)
+            if padding_idx is not None:
+                w[padding_idx].fill_(0)
+            return NS(weight=w)
+
+        t_enc = rnn(E, True)
+        t_key = linear(2 * H, H, False)
+        t_query = linear(H, H, False)
+        t_energy = linear(H, 1, False)
+        t_dec = rnn(E + 2 * H, False)
+        t_bridge = linear(2 * H, H, True)
+        t_pre = linear(3 * H + E, H, False)
         if self.field_rows:
-            t_src_fields = [nn.Embedding(v, w, padding_idx=self.src_pad) for v, w in zip(self.field_rows, self.field_widths)]
+            t_src_fields = [embedding(v, w, self.src_pad) for v, w in zip(self.field_rows, self.field_widths)]
         else:
-            t_src = nn.Embedding(self.V_src, E, padding_idx=self.src_pad)
-        t_trg = nn.Embedding(self.V_tgt, E, padding_idx=self.tgt_pad)
-        t_gen = nn.Linear(H, self.V_tgt, bias=False)
+            t_src = embedding(self.V_src, E, self.src_pad)
+        t_trg = embedding(self.V_tgt, E, self.tgt_pad)
+        t_gen = linear(H, self.V_tgt, False)
 
         # flat layout: per layer the two directions of each tensor are adjacent
         segs: List = []  # (name, init tensor)
