@@ -70,6 +70,10 @@ class TransformerB200(FlatParamModule):
         self.tgt_pad = tgt_vocab.stoi[PAD_WORD]
         self.validate_inputs = True
         self.overlap_small = os.environ.get("SLNLP_OVERLAP_SMALL", "1") != "0"
+        # the encoder's [B*S]-row weight gradients + bias sums on the side lane too: a dW GEMM at 3,200 rows is a
+        # partial wave of mostly fixed latency, and beside the d(activation) chain it costs nothing (cfg3 2.312 -> 2.200
+        # ms/step; $SLNLP_TR_SIDE_BIG=0 puts them back in stream)
+        self.overlap_big = os.environ.get("SLNLP_TR_SIDE_BIG", "1") != "0"
         self.seed = int(kwargs.get("seed", torch.initial_seed() & 0x7FFFFFFF))
         self._build_parameters()
 
@@ -125,7 +129,7 @@ class TransformerB200(FlatParamModule):
         if dx is not None:
             self._gemm(0, 0, rows, n_in, n_out, dy, lddy, self._ptr(w) + 4 * w_off * n_in, n_in, dx, n_in, None,
                        beta_dx, big=big)
-        with (self._side_branch() if (self.overlap_small and not big) else contextlib.nullcontext()):
+        with (self._side_branch() if (self.overlap_small and (not big or self.overlap_big)) else contextlib.nullcontext()):
             self._gemm(1, 0, n_out, n_in, rows, dy, lddy, x, ldx or n_in, self._ptr(w, g) + 4 * w_off * n_in, n_in, None,
                        1.0, big=big)
             if b:
