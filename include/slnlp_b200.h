@@ -230,7 +230,14 @@ int slnlp_rnn_layer_fwd_bf16(int mode, int T, int B, int H, int ndir, float* gat
 int slnlp_rnn_layer_bwd_bf16(int mode, int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, float* stash,
                              const float* out, const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout,
                              const float* dh_final, const float* dc_final, float* carry, int write_f32,
-                             const uint32_t* dout_keep, float dout_scale, slnlp_stream_t stream);
+                             const uint32_t* dout_keep, float dout_scale, int gates_in_dg, slnlp_stream_t stream);
+/* slnlp_rnn_layer_fwd_bf16 with the BPTT stash of the activated gates as bf16: gates_act_bf [T][B][ndir*G*H] (CTA-pair
+ * kernels only; `gates` then keeps the hoisted projection).  Pass the SAME buffer as dg_bf with gates_in_dg = 1 to
+ * slnlp_rnn_layer_bwd_bf16: a step reads its activated gates there and overwrites them with d(pre-activations) -
+ * one bf16 buffer, two lives, 8 instead of 16 bytes per element in each direction. */
+int slnlp_rnn_layer_fwd_bf16_ex(int mode, int T, int B, int H, int ndir, float* gates, const uint16_t* w_hh_bf,
+                                const float* b_hh, const int64_t* lengths, float* out, uint16_t* out_bf, float* stash,
+                                float* h_final, uint16_t* gates_act_bf, slnlp_stream_t stream);
 /* 1 where the two calls above run the persistent CTA-pair step kernels (rnn_step_pair.cu: LSTM, two directions,
  * B > 256, H = 256 / 512 / 1024).  Only those accept out = NULL in the forward (nobody reads the fp32 copy of a
  * lower layer's output once its consumers take out_bf) and, in the backward, dout_keep: the keep mask of the

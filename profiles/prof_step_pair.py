@@ -30,7 +30,7 @@ def fwd():
 def bwd(wf):
     L.check(L.lib.slnlp_rnn_layer_bwd_bf16(0, T, B, H, 2, gates.data_ptr(), dg_bf.data_ptr(), stash.data_ptr(), out.data_ptr(),
                                            wT_bf.data_ptr(), lengths.data_ptr(), dout.data_ptr(), dfin.data_ptr(), None,
-                                           carry.data_ptr(), wf, None, 1.0, S()))
+                                           carry.data_ptr(), wf, None, 1.0, 0, S()))
 def timeit(fn):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); a.record(); fn(); b.record(); torch.cuda.synchronize()

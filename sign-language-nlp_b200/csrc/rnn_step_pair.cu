@@ -86,6 +86,7 @@ struct PairFwd {
   __nv_bfloat16* out_bf;
   float* stash;
   float* h_final;
+  __nv_bfloat16* gact_bf;   // optional: activated gates stashed as bf16 [T][B][ndir*4H] instead of in place in `gates`
 };
 
 // mapW: w_hh_bf as [ndir][4H][H], box {64, 128, 1}; mapH: out_bf as [T][B][ndir*H], box {64, 64, 1}
@@ -173,6 +174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
       const int nvalid = min(SPT, B - b0);
       const int64_t rb = ((int64_t)t * B + b0) * 2 + d;
       float* gp = p.gates + rb * GH + unit;
+      __nv_bfloat16* gab = p.gact_bf ? p.gact_bf + rb * GH + unit : nullptr;
       float* sp = p.stash + rb * HT + unit;
       const float* pp = sp + (int64_t)(tp - t) * B * SH;                // c_{t-1} of the same sequences
       float* op = p.out ? p.out + rb * HT + unit : nullptr;      // NULL: nobody reads the fp32 copy of this layer's output
@@ -247,7 +249,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
           const float go = sigmoid_fast(xg[buf][3][x] + acc[3][x] + bias[3]);
           const float cc = gf * pv[buf][x] + gi * gg;
           const float hv = go * tanh_fast(cc);
-          gp[j * SG] = gi; gp[j * SG + HT] = gf; gp[j * SG + 2 * HT] = gg; gp[j * SG + 3 * HT] = go;
+          if (gab) {     // the BPTT stash as bf16 (8 instead of 16 bytes per element, and again when it is read back)
+            gab[j * SG] = __float2bfloat16_rn(gi); gab[j * SG + HT] = __float2bfloat16_rn(gf);
+            gab[j * SG + 2 * HT] = __float2bfloat16_rn(gg); gab[j * SG + 3 * HT] = __float2bfloat16_rn(go);
+          } else {
+            gp[j * SG] = gi; gp[j * SG + HT] = gf; gp[j * SG + 2 * HT] = gg; gp[j * SG + 3 * HT] = go;
+          }
           sp[j * SH] = cc;
           if (op) op[j * SH] = hv;
           obp[j * SH] = __float2bfloat16_rn(hv);
@@ -272,6 +279,7 @@ struct PairBwd {
   float* carry;
   const uint32_t* dout_keep;   // optional keep mask of the dropout between this layer and the next (1 bit per element of dout)
   float dout_scale;            // 1 / (1 - p)
+  int gates_in_dg;             // the activated gates were stashed as bf16 IN dg_bf (forward's gact_bf): read them there
 };
 
 // mapW: w_hhT_bf as [ndir][H][4H], box {64, 128, 1}; mapG: dg_bf as [T][B][ndir*4H], box {64, 64, 1}
@@ -364,8 +372,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
       const int64_t ci0 = ((int64_t)d * B + b0) * HT + unit;
       float* cp = p.carry + ci0;
       const int64_t* lp = p.lengths ? p.lengths + b0 : nullptr;
-      float gv[2][G][4], sv[2][4], pv[2][4], dh[2][4], cr[2][4];
-      uint32_t kw[2][4];
+      float sv[2][4], pv[2][4], dh[2][4], cr[2][4];
+      uint32_t gv[2][G][4], kw[2][4];
       int len[2][4];
       const float dscale = kp ? p.dout_scale : 1.f;
       auto fetch = [&](int ch, int buf) {
@@ -379,7 +387,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
           const int j = ch * 4 + x;
           const bool live = t < len[buf][x];
 #pragma unroll
-          for (int g = 0; g < G; ++g) gv[buf][g][x] = live ? gp[j * SG + g * HT] : 0.f;
+          for (int g = 0; g < G; ++g) {      // raw bits (fp32, or bf16 zero-extended by the load): loads only (see kw)
+            if (p.gates_in_dg) gv[buf][g][x] = live ? (uint32_t)reinterpret_cast<const unsigned short*>(gbp)[j * SG + g * HT] : 0u;
+            else gv[buf][g][x] = live ? __float_as_uint(gp[j * SG + g * HT]) : 0u;
+          }
           sv[buf][x] = live ? sp[j * SH] : 0.f;
           pv[buf][x] = (live && has_prev) ? pp[j * SH] : 0.f;
           dh[buf][x] = (live && dop) ? dop[j * SH] : 0.f;
@@ -431,7 +442,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1)
             } else {
               dhx += m[x];
             }
-            const float gi = gv[buf][0][x], gf = gv[buf][1][x], gg = gv[buf][2][x], go = gv[buf][3][x];
+            const int sh = p.gates_in_dg ? 16 : 0;      // bf16 bits -> the fp32 with the same value
+            const float gi = __uint_as_float(gv[buf][0][x] << sh), gf = __uint_as_float(gv[buf][1][x] << sh);
+            const float gg = __uint_as_float(gv[buf][2][x] << sh), go = __uint_as_float(gv[buf][3][x] << sh);
             const float tc = tanh_fast(sv[buf][x]);
             const float dc = dhx * go * (1.f - tc * tc) + cin;
             og[0] = dc * gg * gi * (1.f - gi);
@@ -471,7 +484,8 @@ static bool pair_step_ok(int T, int B, int H, int ndir) {
 }
 
 int lstm_layer_fwd_pairstep(int T, int B, int H, int ndir, float* gates, const uint16_t* w_hh_bf, const float* b_hh,
-                            const int64_t* lengths, float* out, uint16_t* out_bf, float* stash, float* h_final, cudaStream_t s) {
+                            const int64_t* lengths, float* out, uint16_t* out_bf, float* stash, float* h_final, uint16_t* gact_bf,
+                            cudaStream_t s) {
   if (!pair_step_ok(T, B, H, ndir)) return -1;
   if (((uintptr_t)w_hh_bf | (uintptr_t)out_bf) & 15) return -1;
   CUtensorMap mapW, mapH;
@@ -483,7 +497,7 @@ int lstm_layer_fwd_pairstep(int T, int B, int H, int ndir, float* gates, const u
   if (!seq) seq = (ndir * (H / 256) * ceil_div(B, 64) >= sms / 2) ? 64 : 32;
   if (!tensor_map3_bf16(out_bf, (uint64_t)ndir * H, B, T, (uint64_t)ndir * H, (uint64_t)B * ndir * H, seq / 2, &mapH)) return -1;
   PairFwd p{T, B, H, ndir, 0, H / 256, ceil_div(B, seq), 0, gates, b_hh, lengths, out, reinterpret_cast<__nv_bfloat16*>(out_bf),
-            stash, h_final};
+            stash, h_final, reinterpret_cast<__nv_bfloat16*>(gact_bf)};
   p.tiles = ndir * p.tiles_u * p.tiles_s;
   dim3 grid(2 * std::min(p.tiles, sms / 2));
   constexpr size_t sm = rp_smem(RP_STAGES_F, RP_AF + RP_BS);
@@ -513,7 +527,7 @@ int lstm_layer_fwd_pairstep(int T, int B, int H, int ndir, float* gates, const u
 int lstm_layer_bwd_pairstep(int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, const float* stash,
                             const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout, const float* dh_final,
                             const float* dc_final, float* carry, int write_f32, const uint32_t* dout_keep, float dout_scale,
-                            cudaStream_t s) {
+                            int gates_in_dg, cudaStream_t s) {
   if (!pair_step_ok(T, B, H, ndir)) return -1;
   if (((uintptr_t)w_hhT_bf | (uintptr_t)dg_bf) & 15) return -1;
   CUtensorMap mapW, mapG;
@@ -530,7 +544,7 @@ int lstm_layer_bwd_pairstep(int T, int B, int H, int ndir, float* gates, uint16_
   }
   if (!tensor_map3_bf16(dg_bf, (uint64_t)ndir * 4 * H, B, T, (uint64_t)ndir * 4 * H, (uint64_t)B * ndir * 4 * H, seq / 2, &mapG)) return -1;
   PairBwd p{T, B, H, ndir, 0, H / 256, ceil_div(B, seq), 0, write_f32, gates, reinterpret_cast<__nv_bfloat16*>(dg_bf), stash,
-            lengths, dout, dh_final, dc_final, carry, dout_keep, dout_scale};
+            lengths, dout, dh_final, dc_final, carry, dout_keep, dout_scale, gates_in_dg};
   p.tiles = ndir * p.tiles_u * p.tiles_s;
   dim3 grid(2 * std::min(p.tiles, sms / 2));
   constexpr size_t sm = rp_smem(RP_STAGES_B, RP_AB + RP_BS);

@@ -655,11 +655,12 @@ int rnn_layer_bwd_bfstep(int mode, int T, int B, int H, int ndir, float* gates, 
 
 // persistent CTA-pair form of the same step (rnn_step_pair.cu; LSTM); -1 = unsupported
 int lstm_layer_fwd_pairstep(int T, int B, int H, int ndir, float* gates, const uint16_t* w_hh_bf, const float* b_hh,
-                            const int64_t* lengths, float* out, uint16_t* out_bf, float* stash, float* h_final, cudaStream_t s);
+                            const int64_t* lengths, float* out, uint16_t* out_bf, float* stash, float* h_final, uint16_t* gact_bf,
+                            cudaStream_t s);
 int lstm_layer_bwd_pairstep(int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, const float* stash,
                             const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout, const float* dh_final,
                             const float* dc_final, float* carry, int write_f32, const uint32_t* dout_keep, float dout_scale,
-                            cudaStream_t s);
+                            int gates_in_dg, cudaStream_t s);
 static bool pair_step_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -671,17 +672,27 @@ static bool pair_step_enabled() {
 
 }  // namespace slnlp
 
+extern "C" int slnlp_rnn_layer_fwd_bf16_ex(int mode, int T, int B, int H, int ndir, float* gates, const uint16_t* w_hh_bf,
+                                           const float* b_hh, const int64_t* lengths, float* out, uint16_t* out_bf, float* stash,
+                                           float* h_final, uint16_t* gates_act_bf, slnlp_stream_t stream);
 extern "C" int slnlp_rnn_layer_fwd_bf16(int mode, int T, int B, int H, int ndir, float* gates, const uint16_t* w_hh_bf,
                                         const float* b_hh, const int64_t* lengths, float* out, uint16_t* out_bf, float* stash,
                                         float* h_final, slnlp_stream_t stream) {
+  return slnlp_rnn_layer_fwd_bf16_ex(mode, T, B, H, ndir, gates, w_hh_bf, b_hh, lengths, out, out_bf, stash, h_final, nullptr, stream);
+}
+extern "C" int slnlp_rnn_layer_fwd_bf16_ex(int mode, int T, int B, int H, int ndir, float* gates, const uint16_t* w_hh_bf,
+                                           const float* b_hh, const int64_t* lengths, float* out, uint16_t* out_bf, float* stash,
+                                           float* h_final, uint16_t* gates_act_bf, slnlp_stream_t stream) {
   using namespace slnlp;
   SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM || mode == SLNLP_MODE_GRU, "rnn_layer_fwd_bf16: bad mode %d", mode);
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_fwd_bf16: bad shape");
   SLNLP_CHECK_ARG(gates && w_hh_bf && b_hh && out_bf && stash, "rnn_layer_fwd_bf16: null pointer");
   if (mode == SLNLP_MODE_LSTM && pair_step_enabled()) {
-    const int rp = lstm_layer_fwd_pairstep(T, B, H, ndir, gates, w_hh_bf, b_hh, lengths, out, out_bf, stash, h_final, as_stream(stream));
+    const int rp = lstm_layer_fwd_pairstep(T, B, H, ndir, gates, w_hh_bf, b_hh, lengths, out, out_bf, stash, h_final, gates_act_bf,
+                                           as_stream(stream));
     if (rp >= 0) return rp;
   }
+  SLNLP_CHECK_ARG(!gates_act_bf, "rnn_layer_fwd_bf16: a bf16 gate stash needs the CTA-pair kernels: ask slnlp_rnn_bf16_pair_supported");
   SLNLP_CHECK_ARG(out, "rnn_layer_fwd_bf16: out = NULL (bf16 copy only) needs the CTA-pair kernels: ask slnlp_rnn_bf16_pair_supported");
   const int rc = rnn_layer_fwd_bfstep(mode, T, B, H, ndir, gates, w_hh_bf, b_hh, lengths, out, out_bf, stash, h_final, as_stream(stream));
   SLNLP_CHECK_ARG(rc >= 0, "rnn_layer_fwd_bf16: needs H a multiple of 64 and 16-byte aligned operands");
@@ -691,17 +702,17 @@ extern "C" int slnlp_rnn_layer_fwd_bf16(int mode, int T, int B, int H, int ndir,
 extern "C" int slnlp_rnn_layer_bwd_bf16(int mode, int T, int B, int H, int ndir, float* gates, uint16_t* dg_bf, float* stash,
                                         const float* out, const uint16_t* w_hhT_bf, const int64_t* lengths, const float* dout,
                                         const float* dh_final, const float* dc_final, float* carry, int write_f32,
-                                        const uint32_t* dout_keep, float dout_scale, slnlp_stream_t stream) {
+                                        const uint32_t* dout_keep, float dout_scale, int gates_in_dg, slnlp_stream_t stream) {
   using namespace slnlp;
   SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM, "rnn_layer_bwd_bf16: LSTM only (mode %d)", mode);
   SLNLP_CHECK_ARG(T > 0 && B > 0 && H > 0 && (ndir == 1 || ndir == 2), "rnn_layer_bwd_bf16: bad shape");
   SLNLP_CHECK_ARG(gates && dg_bf && stash && out && w_hhT_bf && carry, "rnn_layer_bwd_bf16: null pointer");
   if (pair_step_enabled()) {
     const int rp = lstm_layer_bwd_pairstep(T, B, H, ndir, gates, dg_bf, stash, w_hhT_bf, lengths, dout, dh_final, dc_final, carry, write_f32,
-                                           dout_keep, dout_scale, as_stream(stream));
+                                           dout_keep, dout_scale, gates_in_dg, as_stream(stream));
     if (rp >= 0) return rp;
   }
-  SLNLP_CHECK_ARG(!dout_keep, "rnn_layer_bwd_bf16: a dropout keep mask needs the CTA-pair kernels: ask slnlp_rnn_bf16_pair_supported");
+  SLNLP_CHECK_ARG(!dout_keep && !gates_in_dg, "rnn_layer_bwd_bf16: a dropout keep mask needs the CTA-pair kernels: ask slnlp_rnn_bf16_pair_supported");
   const int rc = rnn_layer_bwd_bfstep(mode, T, B, H, ndir, gates, dg_bf, stash, out, w_hhT_bf, lengths, dout, dh_final, dc_final,
                                       carry, as_stream(stream));
   SLNLP_CHECK_ARG(rc >= 0, "rnn_layer_bwd_bf16: needs H a multiple of 128 and 16-byte aligned operands");

@@ -49,7 +49,8 @@ SIGNATURES = {
     "slnlp_rnn_extras_supported": [I, I, I, I, I],
     "slnlp_rnn_bf16_step_supported": [I, I, I, I, I],
     "slnlp_rnn_layer_fwd_bf16": [I, I, I, I, I, P, P, P, P, P, P, P, P, P],
-    "slnlp_rnn_layer_bwd_bf16": [I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P, F, P],
+    "slnlp_rnn_layer_bwd_bf16": [I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P, F, I, P],
+    "slnlp_rnn_layer_fwd_bf16_ex": [I, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
     "slnlp_rnn_bf16_pair_supported": [I, I, I, I, I],
     "slnlp_rnn_layer_fwd_ex": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "slnlp_rnn_layer_bwd_ex": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],

@@ -233,11 +233,13 @@ class RnnEncDecB200(FlatParamModule):
                 # large batch: the per-step kernels read bf16 operands (h_{t-1} from the bf16 copy of `out` they
                 # write themselves, W_hh from a bf16 copy) - the recurrence there is bound by operand bytes
                 self._cast_bf16(self._ptr(f"{pre}weight_hh_l{l}"), H, ws.w_hh_bf[l], 2 * G * H, H)
-                check(lib.slnlp_rnn_layer_fwd_bf16(mode, T, B, H, 2, ws.enc_gates[l].data_ptr(), ws.w_hh_bf[l].data_ptr(),
-                                                   self._ptr(f"{pre}bias_hh_l{l}"), lp,
-                                                   None if ws.skip_out32[l] else ws.enc_out[l].data_ptr(),
-                                                   ws.out_bf[l].data_ptr(), ws.enc_stash[l].data_ptr(),
-                                                   ws.enc_hfin[l].data_ptr(), s), "rnn_layer_fwd_bf16")
+                # (gates_bf: the activated gates are stashed as bf16 in the buffer BPTT later overwrites with dG)
+                check(lib.slnlp_rnn_layer_fwd_bf16_ex(mode, T, B, H, 2, ws.enc_gates[l].data_ptr(), ws.w_hh_bf[l].data_ptr(),
+                                                      self._ptr(f"{pre}bias_hh_l{l}"), lp,
+                                                      None if ws.skip_out32[l] else ws.enc_out[l].data_ptr(),
+                                                      ws.out_bf[l].data_ptr(), ws.enc_stash[l].data_ptr(),
+                                                      ws.enc_hfin[l].data_ptr(),
+                                                      ws.dg_bf[l].data_ptr() if ws.gates_bf[l] else None, s), "rnn_layer_fwd_bf16")
             else:
                 check(lib.slnlp_rnn_layer_fwd(mode, prec, T, B, H, 2, ws.enc_gates[l].data_ptr(),
                                               self._ptr(f"{pre}weight_hh_l{l}"), self._ptr(f"{pre}bias_hh_l{l}"),
@@ -438,7 +440,8 @@ class RnnEncDecB200(FlatParamModule):
                                                    ws.w_hhT_bf[l].data_ptr(), lp, ws.d_seq.data_ptr(), ws.d_hfin.data_ptr(),
                                                    None, ws.carry.data_ptr(), 0 if ws.dg_bf_only[l] else 1,
                                                    ws.keep_bits[l].data_ptr() if ws.masked[l] else None,
-                                                   1.0 / (1.0 - self.p_rnn) if ws.masked[l] else 1.0, s),
+                                                   1.0 / (1.0 - self.p_rnn) if ws.masked[l] else 1.0,
+                                                   1 if ws.gates_bf[l] else 0, s),
                       "rnn_layer_bwd_bf16")
             else:
                 check(lib.slnlp_concat_dirs(ws.d_enc_final[l].data_ptr(), ws.d_hfin.data_ptr(), B, H, 2, 1, s),
@@ -655,6 +658,8 @@ class _Workspace:
         self.masked = [pairk and drop and bwd and l < L - 1 and self.bf_in[l + 1] and (T * B * 2 * H) % 128 == 0 for l in range(L)]
         self.keep_bits = [torch.empty(T * B * 2 * H // 32, dtype=torch.int32, device=dev) if self.masked[l] else None
                           for l in range(L)]
+        self.gates_bf = [pairk and bwd and self.dg_bf[l] is not None and os.environ.get("SLNLP_GATES_BF16", "1") != "0"
+                         for l in range(L)]
         self.skip_out32 = [pairk and l < L - 1 and (self.dg_bf_only[l] or not bwd) and
                            (self.masked[l] if (drop and bwd) else (self.bf_in[l + 1] and not drop)) for l in range(L)]
         self.emb = f(T, B, E)

@@ -603,7 +603,7 @@ def test_rnn_layer_at_cfg4_shape_batch_4096_hidden_512(mode):
             assert torch.equal(out_bf, out.to(torch.bfloat16))        # the bf16 copy the GEMMs and the next step read
             L.check(L.lib.slnlp_rnn_layer_bwd_bf16(md, T, B, H, 2, gates.data_ptr(), dg_bf.data_ptr(), stash.data_ptr(),
                                                    out.data_ptr(), wT_bf.data_ptr(), len_d.data_ptr(), dout_tm.data_ptr(),
-                                                   dfin_d.data_ptr(), None, carry.data_ptr(), 1, None, 1.0, S()))
+                                                   dfin_d.data_ptr(), None, carry.data_ptr(), 1, None, 1.0, 0, S()))
             assert torch.equal(dg_bf, gates.to(torch.bfloat16))
             if L.lib.slnlp_rnn_bf16_pair_supported(md, T, B, H, 2):
                 # the CTA-pair kernels' extras: forward without the fp32 copy of `out`; backward applying an inter-layer
@@ -627,9 +627,24 @@ def test_rnn_layer_at_cfg4_shape_batch_4096_hidden_512(mode):
                     L.check(L.lib.slnlp_rnn_layer_bwd_bf16(md, T, B, H, 2, g2.data_ptr(), dgx.data_ptr(), stash2.data_ptr(),
                                                            out.data_ptr(), wT_bf.data_ptr(), len_d.data_ptr(), dsrc.data_ptr(),
                                                            dfin_d.data_ptr(), None, carry.data_ptr(), 0,
-                                                           kb.data_ptr() if kb is not None else None, sc, S()))
+                                                           kb.data_ptr() if kb is not None else None, sc, 0, S()))
                 assert torch.equal(dg_a, dg_b)
                 assert rel_err(dg_a.float(), gates) > 1e-3          # the mask did change the gradient
+                # the activated gates stashed as bf16 in the buffer BPTT overwrites with dG (one buffer, two lives)
+                g3, dg_c = torch.empty_like(gates), torch.empty_like(dg_bf)
+                L.check(L.lib.slnlp_gemm_f32(0, 1, T * B, 2 * G * H, D, x_tm.data_ptr(), D, w_ih.data_ptr(), D,
+                                             g3.data_ptr(), 2 * G * H, b_ih.data_ptr(), 0.0, None, 0, S()))
+                L.check(L.lib.slnlp_rnn_layer_fwd_bf16_ex(md, T, B, H, 2, g3.data_ptr(), w_bf.data_ptr(), b_hh.data_ptr(),
+                                                          len_d.data_ptr(), None, out_bf2.data_ptr(), stash2.data_ptr(),
+                                                          hfin2.data_ptr(), dg_c.data_ptr(), S()))
+                assert torch.equal(out_bf2, out_bf) and torch.equal(stash2, stash)
+                live = (torch.arange(T, device="cuda").view(T, 1) < len_d.view(1, B)).view(T, B, 1, 1, 1).expand_as(g2)
+                assert torch.equal(dg_c[live], g2.to(torch.bfloat16)[live])      # the same activations, rounded
+                carry.zero_()
+                L.check(L.lib.slnlp_rnn_layer_bwd_bf16(md, T, B, H, 2, g3.data_ptr(), dg_c.data_ptr(), stash2.data_ptr(),
+                                                       out.data_ptr(), wT_bf.data_ptr(), len_d.data_ptr(), dout_tm.data_ptr(),
+                                                       dfin_d.data_ptr(), None, carry.data_ptr(), 0, bits.data_ptr(), scale, 1, S()))
+                assert rel_err(dg_c.float(), dg_b.float()) < BF16_RTOL
         else:
             c0 = L.lib.slnlp_launch_count()
             L.check(L.lib.slnlp_rnn_layer_fwd(md, prec, T, B, H, 2, gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(),
