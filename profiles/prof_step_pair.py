@@ -24,13 +24,15 @@ for d in range(2):
     L.check(L.lib.slnlp_cast_bf16(w_hh[d].data_ptr(), H, wT_bf[d].data_ptr(), G * H, G * H, H, 1, S()))
 dout, dfin, carry = f(T, B, 2 * H), f(2, B, H), torch.zeros(4, B, H, device="cuda")
 gates = gates0.clone()
+GB = L.lib.slnlp_rnn_bf16_pair_supported(0, T, B, H, 2) and os.environ.get("GATES_BF16", "0") == "1"   # bf16 gate stash in dg_bf
 def fwd():
-    L.check(L.lib.slnlp_rnn_layer_fwd_bf16(0, T, B, H, 2, gates.data_ptr(), w_bf.data_ptr(), b_hh.data_ptr(), lengths.data_ptr(),
-                                           out.data_ptr(), out_bf.data_ptr(), stash.data_ptr(), hfin.data_ptr(), S()))
+    L.check(L.lib.slnlp_rnn_layer_fwd_bf16_ex(0, T, B, H, 2, gates.data_ptr(), w_bf.data_ptr(), b_hh.data_ptr(), lengths.data_ptr(),
+                                              out.data_ptr(), out_bf.data_ptr(), stash.data_ptr(), hfin.data_ptr(),
+                                              dg_bf.data_ptr() if GB else None, S()))
 def bwd(wf):
     L.check(L.lib.slnlp_rnn_layer_bwd_bf16(0, T, B, H, 2, gates.data_ptr(), dg_bf.data_ptr(), stash.data_ptr(), out.data_ptr(),
                                            wT_bf.data_ptr(), lengths.data_ptr(), dout.data_ptr(), dfin.data_ptr(), None,
-                                           carry.data_ptr(), wf, None, 1.0, 0, S()))
+                                           carry.data_ptr(), wf, None, 1.0, 1 if GB else 0, S()))
 def timeit(fn):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); a.record(); fn(); b.record(); torch.cuda.synchronize()
@@ -39,10 +41,10 @@ tf, tb, tb1 = [], [], []
 for i in range(reps):
     gates.copy_(gates0)
     tf.append(timeit(fwd))
-    keep = gates.clone()
+    keep, keepb = gates.clone(), dg_bf.clone()
     tb.append(timeit(lambda: bwd(0)))
-    gates.copy_(keep)
+    gates.copy_(keep); dg_bf.copy_(keepb)
     tb1.append(timeit(lambda: bwd(1)))
 el = B * H * 2
-print(f"T {T} B {B} H {H}: fwd {min(tf):.1f} us/step ({el * 46 / min(tf) / 1e3:.0f} GB/s of the 46 B/element), "
+print(("bf16 gate stash: " if GB else "") + f"T {T} B {B} H {H}: fwd {min(tf):.1f} us/step ({el * 46 / min(tf) / 1e3:.0f} GB/s of the 46 B/element), "
       f"bwd {min(tb):.1f} us/step bf16-only ({el * 44 / min(tb) / 1e3:.0f} GB/s of 44 B/element), bwd + fp32 dG {min(tb1):.1f} us/step")
