@@ -169,6 +169,19 @@ int slnlp_dec_cell_fwd(int mode, int B, int H, int D, const float* x, const floa
                        float* gates, float* stash, float* h, float* h_drop, float p_drop,
                        const uint64_t* rng, uint32_t site, slnlp_stream_t stream);
 
+/* Backward of slnlp_dec_cell_fwd as ONE launch (replaces slnlp_rnn_layer_bwd(T = 1) + axpy + the d(input) GEMM + its
+ * dropout; bkp:190,215-216,278-279).  In: the forward's gates / stash, h0 / c0 (LSTM: c0 aliases h0; GRU: c0 NULL),
+ * dh [B,H] = d(h_1).  Out: dgx [B,G,H] = d(x-side pre-activations) and, GRU only, dnh [B,H] = d(W_hn h0 + b_hn) - the
+ * operands of the dW_ih / dW_hh / bias products, written to buffers of their OWN (gates stays intact);
+ * dx [B,D] = dgx W_ih, multiplied by the keep / scale factor slnlp_dropout(site) draws when rng != NULL (the layer's
+ * input was dropout(h of the layer below)); dh0 [B,H] = d(h0) (LSTM: + d(c0)).  dx and dh0 must not alias dh.
+ * H and D multiples of 16 (slnlp_dec_cell_bwd_supported). */
+int slnlp_dec_cell_bwd_supported(int mode, int B, int H, int D);
+int slnlp_dec_cell_bwd(int mode, int B, int H, int D, const float* gates, const float* stash, const float* h0,
+                       const float* c0, const float* dh, const float* w_ih, const float* w_hh, float* dgx,
+                       float* dnh, float* dx, float* dh0, float p_drop, const uint64_t* rng, uint32_t site,
+                       slnlp_stream_t stream);
+
 /* BPTT of the same layer.  gates: in = activated gates, out = d(x-side pre-activations)
  * (zeros at frozen steps) ready for the hoisted dW_ih / dx GEMMs.  stash: GRU only,
  * out = d(W_hn h + b_hn).  dout [T,B,ndir*H] / dh_final / dc_final may be NULL.
@@ -290,6 +303,26 @@ int slnlp_attn_step_bwd(const float* dctx, const float* q, const float* pk, cons
                         const float* val, const float* alpha, int T, int B, int H, int W,
                         float* dval, float* dpk, float* dq, float* dv_part,
                         slnlp_stream_t stream);
+
+/* ---- K7b: the decoder head of the single decode step, one launch per direction of autograd, one CTA per sequence:
+ * bridge (bkp:268-280: hidden0[l] = tanh(W_b enc_final[l] + b_b), every layer) -> query (bkp:312) -> the attention of
+ * slnlp_attn_step_fwd -> decoder input [trg_embed[bos] || ctx] (bkp:202-216).  enc_final [L,B,2H], hidden0 [L,B,H],
+ * dec_xin [B,E+2H]; the other arguments as slnlp_attn_step_fwd (W = 2H).  w_bridge == NULL: hidden0 is an INPUT (the
+ * caller ran the bridge); w_query == NULL: q is an input.  A fused bridge needs the fused query.  ctx may be NULL. */
+int slnlp_dec_head_supported(int T, int B, int H, int L, int fuse_query, int fuse_bridge);
+int slnlp_dec_head_fwd(int T, int B, int H, int L, int E, const float* enc_final, const float* w_bridge,
+                       const float* b_bridge, const float* w_query, const float* pk, const float* v,
+                       const float* val, const int64_t* X, int64_t pad_idx, const float* bos_row,
+                       float* hidden0, float* q, float* alpha, float* ctx, float* dec_xin,
+                       slnlp_stream_t stream);
+/* Backward twin.  d_decx [B,E+2H] = d(decoder input) (its last 2H columns are d(ctx)); dval / dpk / dq / dv_part as
+ * slnlp_attn_step_bwd.  w_query != NULL: d_hidden0[L-1] += dq W_q (d_hidden0 [L,B,H] holds the decoder cells' d(h0) on
+ * entry).  w_bridge != NULL: d_hidden0 *= 1 - hidden0^2 (every layer, written back: the operand of the bridge's weight
+ * gradient) and d_enc_final [L,B,2H] = d_hidden0 W_b. */
+int slnlp_dec_head_bwd(int T, int B, int H, int L, int E, const float* d_decx, const float* q, const float* pk,
+                       const float* v, const float* val, const float* alpha, const float* hidden0,
+                       const float* w_query, const float* w_bridge, float* dval, float* dpk, float* dq,
+                       float* dv_part, float* d_hidden0, float* d_enc_final, slnlp_stream_t stream);
 
 /* ---- K10: generator log_softmax (bkp:75-76) + skorch CrossEntropyLoss(ignore_index)
  * applied on the log-probs (config/*.yaml:36, helper.py:67-70).

@@ -168,6 +168,227 @@ __global__ void __launch_bounds__(DJ * DB) dec_cell_fwd_kernel(DecCellFwd p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Backward of the same single step as ONE kernel per layer.  Replaces the chain
+//     gate-gradient step kernel -> final-state step kernel (d h0 = dG W_hh) -> axpy (LSTM: c0 = h0, bkp:278-279)
+//     -> d(input) GEMM (dG W_ih) -> split-K reduce -> dropout of the gradient
+// (five to six dependent launches of 3-6 us).  The output is the row-concatenation [dx | dh0] = dG [W_ih | W_hh]:
+// a CTA owns CB_NC of its D + H columns and CB_BB batch rows, RECOMPUTES the element-wise gate gradients of its
+// rows (7 loads and one tanhf per unit: cheaper than a grid-wide exchange) into shared memory next to its
+// column slice of the weights, and contracts over K = G*H in chunks of CB_KC.  256 threads = 4 slices of the
+// chunk x (8 row groups x 8 column pairs): 4 x 2 outputs per thread (rows rq, rq + 8, ..: conflict-free) from float4 shared-memory reads, slices met
+// in shared memory.  The CTAs of column block 0 also write dG (x side; GRU: and d(W_hn h0 + b_hn)) for the
+// weight-gradient GEMMs - to buffers of their own, the activated gates stay intact for the other CTAs.
+constexpr int CB_NC = 16;
+constexpr int CB_BB = 32;
+constexpr int CB_KC = 512;
+constexpr int CB_LD = CB_KC + 4;
+constexpr int CB_THREADS = 256;
+
+struct DecCellBwd {
+  int B, H, D;
+  const float* gates;    // [B,G,H] activated gates
+  const float* stash;    // [B,H]: LSTM c_1; GRU W_hn h0 + b_hn
+  const float* h0;       // [B,H]
+  const float* c0;       // [B,H] (LSTM) or null
+  const float* dh;       // [B,H] d(h_1)
+  const float* w_ih;     // [G*H,D]
+  const float* w_hh;     // [G*H,H]
+  float* dgx;            // [B,G,H] d(x-side pre-activations)
+  float* dnh;            // [B,H] GRU: d(W_hn h0 + b_hn); LSTM: null
+  float* dx;             // [B,D] d(input) (x dropout keep/scale of `site` when rng)
+  float* dh0;            // [B,H] d(h0) (LSTM: + d(c0))
+  float p_drop;
+  const uint64_t* rng;
+  uint32_t site;
+};
+
+// the forward's values of unit j of sequence b that its gate gradients need (loaded apart from the math: a thread
+// issues the loads of several units before it uses any of them)
+template <int G>
+struct CellIn {
+  float g[G];        // activated gates
+  float st, hp, dh;  // stash (LSTM c_1; GRU W_hn h0 + b_hn), c0 (LSTM) / h0 (GRU), d(h_1)
+};
+template <int G>
+__device__ __forceinline__ void dec_cell_load(const DecCellBwd& p, int b, int j, CellIn<G>& in) {
+  const int H = p.H;
+  const float* gt = p.gates + (int64_t)b * G * H;
+  const int64_t e = (int64_t)b * H + j;
+#pragma unroll
+  for (int g = 0; g < G; ++g) in.g[g] = gt[g * H + j];
+  in.st = p.stash[e];
+  in.dh = p.dh[e];
+  in.hp = G == 4 ? (p.c0 ? p.c0[e] : 0.f) : p.h0[e];
+}
+// gx: x-side d(pre-activations); nh: the h-side candidate gate (GRU; LSTM: = gx[2]); extra: the direct path into d(h0)
+// (LSTM: d c0 = dc f, c0 aliases h0; GRU: dh z).  All zero for dh = 0 (rows past the batch).
+template <int G>
+__device__ __forceinline__ void dec_cell_math(const CellIn<G>& in, float (&gx)[G], float& nh, float& extra) {
+  const float dh = in.dh;
+  if (G == 4) {
+    const float gi = in.g[0], gf = in.g[1], gg = in.g[2], go = in.g[G - 1];
+    const float tc = tanhf(in.st);
+    const float dc = dh * go * (1.f - tc * tc);
+    gx[0] = dc * gg * gi * (1.f - gi);
+    gx[1] = dc * in.hp * gf * (1.f - gf);
+    gx[2] = dc * gi * (1.f - gg * gg);
+    gx[G - 1] = dh * tc * go * (1.f - go);
+    nh = gx[2];
+    extra = dc * gf;
+  } else {
+    const float gr = in.g[0], gz = in.g[1], gn = in.g[2];
+    const float da_n = dh * (1.f - gz) * (1.f - gn * gn);
+    gx[0] = da_n * in.st * gr * (1.f - gr);
+    gx[1] = dh * (in.hp - gn) * gz * (1.f - gz);
+    gx[2] = da_n;
+    nh = da_n * gr;
+    extra = dh * gz;
+  }
+}
+constexpr int CB_PU = 8;    // units whose loads a thread keeps in flight
+
+template <int G>
+__global__ void __launch_bounds__(CB_THREADS) dec_cell_bwd_kernel(DecCellBwd p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) float smem[];
+  float* Dsm = smem;                          // [CB_BB][CB_LD] gate gradients of this CTA's rows, one K chunk
+  float* Wsm = Dsm + CB_BB * CB_LD;           // [CB_NC][CB_LD] this CTA's weight columns, K-major
+  float* red = Wsm + CB_NC * CB_LD;           // [4][CB_BB*CB_NC]
+  float* Esm = red + 4 * CB_BB * CB_NC;       // [CB_BB][CB_NC] the direct path into d(h0) of this CTA's columns
+  const int H = p.H, B = p.B, D = p.D, GH = G * p.H;
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * CB_NC, b0 = blockIdx.y * CB_BB;
+  const bool hside = n0 >= D;                 // columns of d(h0): contract with W_hh and the h-side candidate gate
+  const float* Wm = hside ? p.w_hh : p.w_ih;
+  const int ldw = hside ? H : D, nc0 = hside ? n0 - D : n0;
+  const bool writer = blockIdx.x == 0;
+  const bool wvec = (((uintptr_t)Wm) & 15) == 0;   // rows and column blocks are multiples of 16 floats by construction
+  const int ks = tid >> 6, rq = tid & 7, cp = (tid & 63) >> 3;
+
+  float acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+
+  for (int kc = 0; kc < GH; kc += CB_KC) {
+    const int kn = min(CB_KC, GH - kc);
+    if (kc) __syncthreads();
+    // this CTA's weight columns of the chunk: eight 16-byte loads per thread, all issued before the first is used
+    constexpr int NWV = CB_KC * CB_NC / 4 / CB_THREADS;
+    float4 wr[NWV];
+    if (wvec) {
+#pragma unroll
+      for (int i = 0; i < NWV; ++i) {
+        const int e4 = tid + i * CB_THREADS, c4 = e4 & 3, kk = e4 >> 2;
+        wr[i] = kk < kn ? __ldg(reinterpret_cast<const float4*>(Wm + (int64_t)(kc + kk) * ldw + nc0) + c4)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      for (int e = tid; e < CB_KC * CB_NC; e += CB_THREADS) {
+        const int c = e % CB_NC, kk = e / CB_NC;
+        Wsm[c * CB_LD + kk] = (kk < kn && nc0 + c < ldw) ? __ldg(Wm + (int64_t)(kc + kk) * ldw + nc0 + c) : 0.f;
+      }
+    }
+    bool w_pending = wvec;
+    auto store_w = [&]() {
+#pragma unroll
+      for (int i = 0; i < NWV; ++i) {
+        const int e4 = tid + i * CB_THREADS, c4 = e4 & 3, kk = e4 >> 2;
+        Wsm[(c4 * 4 + 0) * CB_LD + kk] = wr[i].x;
+        Wsm[(c4 * 4 + 1) * CB_LD + kk] = wr[i].y;
+        Wsm[(c4 * 4 + 2) * CB_LD + kk] = wr[i].z;
+        Wsm[(c4 * 4 + 3) * CB_LD + kk] = wr[i].w;
+      }
+      w_pending = false;
+    };
+    if (kn < CB_KC) {
+      const int nz = CB_KC - kn;
+      for (int e = tid; e < CB_BB * nz; e += CB_THREADS) Dsm[(e / nz) * CB_LD + kn + e % nz] = 0.f;
+    }
+    // gate gradients of this CTA's rows: the loads of CB_PU units in flight per thread
+    for (int pr0 = tid; pr0 < CB_BB * H; pr0 += CB_PU * CB_THREADS) {
+      CellIn<G> in[CB_PU];
+#pragma unroll
+      for (int u = 0; u < CB_PU; ++u) {
+        const int pr = pr0 + u * CB_THREADS, bb = pr / H, j = pr - bb * H, b = b0 + bb;
+        if (pr < CB_BB * H && b < B) {
+          dec_cell_load<G>(p, b, j, in[u]);
+        } else {
+#pragma unroll
+          for (int g = 0; g < G; ++g) in[u].g[g] = 0.f;
+          in[u].st = in[u].hp = in[u].dh = 0.f;
+        }
+      }
+      if (w_pending) store_w();
+#pragma unroll
+      for (int u = 0; u < CB_PU; ++u) {
+        const int pr = pr0 + u * CB_THREADS, bb = pr / H, j = pr - bb * H, b = b0 + bb;
+        if (pr >= CB_BB * H) continue;
+        float gx[G], nh, extra;
+        dec_cell_math<G>(in[u], gx, nh, extra);
+        if (writer && kc == 0 && b < B) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) p.dgx[((int64_t)b * G + g) * H + j] = gx[g];
+          if (G == 3 && p.dnh) p.dnh[(int64_t)b * H + j] = nh;
+        }
+        if (hside) {
+          gx[2] = nh;
+          if (j >= nc0 && j < nc0 + CB_NC) Esm[bb * CB_NC + j - nc0] = extra;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int k = g * H + j - kc;
+          if (k >= 0 && k < CB_KC) Dsm[bb * CB_LD + k] = gx[g];
+        }
+      }
+    }
+    if (w_pending) store_w();
+    __syncthreads();
+    const int kbeg = ks * (CB_KC / 4);
+#pragma unroll 4
+    for (int kk = kbeg; kk < kbeg + CB_KC / 4; kk += 4) {
+      float4 d[4], wv[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[i] = *reinterpret_cast<const float4*>(&Dsm[(i * 8 + rq) * CB_LD + kk]);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) wv[c] = *reinterpret_cast<const float4*>(&Wsm[(cp * 2 + c) * CB_LD + kk]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          acc[i][c] = fmaf(d[i].x, wv[c].x, acc[i][c]);
+          acc[i][c] = fmaf(d[i].y, wv[c].y, acc[i][c]);
+          acc[i][c] = fmaf(d[i].z, wv[c].z, acc[i][c]);
+          acc[i][c] = fmaf(d[i].w, wv[c].w, acc[i][c]);
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) red[ks * (CB_BB * CB_NC) + (i * 8 + rq) * CB_NC + cp * 2 + c] = acc[i][c];
+  __syncthreads();
+  for (int o = tid; o < CB_BB * CB_NC; o += CB_THREADS) {
+    const int bb = o / CB_NC, c = o % CB_NC, b = b0 + bb;
+    if (b >= B || nc0 + c >= ldw) continue;
+    float s = red[o] + red[CB_BB * CB_NC + o] + red[2 * CB_BB * CB_NC + o] + red[3 * CB_BB * CB_NC + o];
+    if (hside) {
+      p.dh0[(int64_t)b * H + nc0 + c] = s + Esm[bb * CB_NC + c];
+    } else {
+      const int64_t e = (int64_t)b * D + nc0 + c;
+      if (p.rng) {   // the input was dropout(h of the layer below): the keep / scale factor slnlp_dropout(site) drew for e
+        float u[4];
+        philox_uniform4(p.rng[0], p.rng[1], p.site, (uint64_t)(e >> 2), u);
+        const float uu = (e & 3) == 0 ? u[0] : (e & 3) == 1 ? u[1] : (e & 3) == 2 ? u[2] : u[3];
+        s = uu < 1.f - p.p_drop ? s * (1.f / (1.f - p.p_drop)) : 0.f;
+      }
+      p.dx[e] = s;
+    }
+  }
+}
+
 }  // namespace slnlp
 
 extern "C" int slnlp_dec_cell_fwd(int mode, int B, int H, int D, const float* x, const float* h0, const float* c0,
@@ -184,5 +405,35 @@ extern "C" int slnlp_dec_cell_fwd(int mode, int B, int H, int D, const float* x,
   if (mode == SLNLP_MODE_LSTM) launch_pdl(dec_cell_fwd_kernel<4>, grid, dim3(DJ * DB), 0, as_stream(stream), p);
   else launch_pdl(dec_cell_fwd_kernel<3>, grid, dim3(DJ * DB), 0, as_stream(stream), p);
   SLNLP_LAUNCH_OK("dec_cell_fwd");
+  return 0;
+}
+
+extern "C" int slnlp_dec_cell_bwd_supported(int mode, int B, int H, int D) {
+  (void)mode;
+  return (B > 0 && H > 0 && D > 0 && H % slnlp::CB_NC == 0 && D % slnlp::CB_NC == 0) ? 1 : 0;
+}
+
+extern "C" int slnlp_dec_cell_bwd(int mode, int B, int H, int D, const float* gates, const float* stash, const float* h0,
+                                  const float* c0, const float* dh, const float* w_ih, const float* w_hh, float* dgx,
+                                  float* dnh, float* dx, float* dh0, float p_drop, const uint64_t* rng, uint32_t site,
+                                  slnlp_stream_t stream) {
+  using namespace slnlp;
+  SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM || mode == SLNLP_MODE_GRU, "dec_cell_bwd: bad mode");
+  SLNLP_CHECK_ARG(B > 0 && H > 0 && D > 0 && gates && stash && h0 && dh && w_ih && w_hh && dgx && dx && dh0,
+                  "dec_cell_bwd: bad arguments");
+  SLNLP_CHECK_ARG(mode == SLNLP_MODE_LSTM || dnh, "dec_cell_bwd: the GRU needs dnh");
+  SLNLP_CHECK_ARG(H % CB_NC == 0 && D % CB_NC == 0, "dec_cell_bwd: H and D must be multiples of %d (ask slnlp_dec_cell_bwd_supported)", CB_NC);
+  SLNLP_CHECK_ARG(!rng || (p_drop >= 0.f && p_drop < 1.f), "dec_cell_bwd: dropout needs 0 <= p < 1");
+  DecCellBwd p{B, H, D, gates, stash, h0, c0, dh, w_ih, w_hh, dgx, dnh, dx, dh0, p_drop, rng, site};
+  const dim3 grid((D + H) / CB_NC, ceil_div(B, CB_BB));
+  const size_t sm = (size_t)((CB_BB + CB_NC) * CB_LD + 5 * CB_BB * CB_NC) * sizeof(float);
+  if (mode == SLNLP_MODE_LSTM) {
+    cudaFuncSetAttribute(dec_cell_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    launch_pdl(dec_cell_bwd_kernel<4>, grid, dim3(CB_THREADS), sm, as_stream(stream), p);
+  } else {
+    cudaFuncSetAttribute(dec_cell_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    launch_pdl(dec_cell_bwd_kernel<3>, grid, dim3(CB_THREADS), sm, as_stream(stream), p);
+  }
+  SLNLP_LAUNCH_OK("dec_cell_bwd");
   return 0;
 }

@@ -55,6 +55,11 @@ SIGNATURES = {
     "slnlp_rnn_layer_fwd_ex": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "slnlp_rnn_layer_bwd_ex": [I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "slnlp_dec_cell_fwd": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, F, P, U32, P],
+    "slnlp_dec_cell_bwd_supported": [I, I, I, I],
+    "slnlp_dec_cell_bwd": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, F, P, U32, P],
+    "slnlp_dec_head_supported": [I, I, I, I, I, I],
+    "slnlp_dec_head_fwd": [I, I, I, I, I, P, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P],
+    "slnlp_dec_head_bwd": [I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "slnlp_pad_fill": [P, P, I, I, I, F, P],
     "slnlp_pad_fill_copy": [P, P, P, I, I, I, F, P],
     "slnlp_concat_dirs": [P, P, I, I, I, I, P],

@@ -269,22 +269,36 @@ class RnnEncDecB200(FlatParamModule):
             self._gemm(0, 1, T * B, H, 2 * H, enc_out.data_ptr(), 2 * H,
                        self._ptr("model.decoder.attention.key_layer.weight"), 2 * H, ws.pk.data_ptr(), H, big=True)
         # bridge (bkp:268-280)
-        self._gemm(0, 1, L * B, H, 2 * H, ws.enc_final.data_ptr(), 2 * H, self._ptr("model.decoder.bridge.weight"),
-                   2 * H, ws.hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.bias"), act="tanh")
+        if not ws.fuse_bridge:
+            self._gemm(0, 1, L * B, H, 2 * H, ws.enc_final.data_ptr(), 2 * H, self._ptr("model.decoder.bridge.weight"),
+                       2 * H, ws.hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.bias"), act="tanh")
         # attention (bkp:304-327)
-        self._gemm(0, 1, B, H, H, ws.hidden0[L - 1].data_ptr(), H,
-                   self._ptr("model.decoder.attention.query_layer.weight"), H, ws.q.data_ptr(), H)
+        if not ws.fuse_query:
+            self._gemm(0, 1, B, H, H, ws.hidden0[L - 1].data_ptr(), H,
+                       self._ptr("model.decoder.attention.query_layer.weight"), H, ws.q.data_ptr(), H)
         self._join_lane(2)
-        check(lib.slnlp_attn_step_fwd(ws.q.data_ptr(), ws.pk.data_ptr(),
-                                      self._ptr("model.decoder.attention.energy_layer.weight"),
-                                      enc_out.data_ptr(), Xp, self.src_pad, T, B, H, 2 * H,
-                                      ws.alpha.data_ptr(), ws.ctx.data_ptr(), s), "attn_fwd")
+        bos_row = self._ptr("model.trg_embed.weight") + 4 * self.bos_idx * E
+        if ws.dec_head:
+            # bridge -> tanh -> query -> attention -> [bos embedding || context]: one launch, one CTA per sequence
+            check(lib.slnlp_dec_head_fwd(T, B, H, L, E, ws.enc_final.data_ptr(),
+                                         self._ptr("model.decoder.bridge.weight") if ws.fuse_bridge else None,
+                                         self._ptr("model.decoder.bridge.bias"),
+                                         self._ptr("model.decoder.attention.query_layer.weight") if ws.fuse_query else None,
+                                         ws.pk.data_ptr(), self._ptr("model.decoder.attention.energy_layer.weight"),
+                                         enc_out.data_ptr(), Xp, self.src_pad, bos_row, ws.hidden0.data_ptr(),
+                                         ws.q.data_ptr(), ws.alpha.data_ptr(), ws.ctx.data_ptr(), ws.dec_xin[0].data_ptr(),
+                                         s), "dec_head_fwd")
+        else:
+            check(lib.slnlp_attn_step_fwd(ws.q.data_ptr(), ws.pk.data_ptr(),
+                                          self._ptr("model.decoder.attention.energy_layer.weight"),
+                                          enc_out.data_ptr(), Xp, self.src_pad, T, B, H, 2 * H,
+                                          ws.alpha.data_ptr(), ws.ctx.data_ptr(), s), "attn_fwd")
         # one decoder step (bkp:215-216): at the reference's batch its cell stays on the fused fp32 kernel (a single
         # step of 50 sequences gains nothing from the tensor-core kernels, measured); batches > 256 (or
         # SLNLP_DEC_TC=1) take the tensor-core GEMM + step kernels (the skinny fp32 cell was 1.6 ms per layer at 4096)
         dec_prec = prec if (os.environ.get("SLNLP_DEC_TC", "0") == "1" or B > 256) else 0
-        check(lib.slnlp_dec_input_fwd(self._ptr("model.trg_embed.weight") + 4 * self.bos_idx * E,
-                                      ws.ctx.data_ptr(), ws.dec_xin[0].data_ptr(), B, E, 2 * H, s), "dec_input")
+        if not ws.dec_head:
+            check(lib.slnlp_dec_input_fwd(bos_row, ws.ctx.data_ptr(), ws.dec_xin[0].data_ptr(), B, E, 2 * H, s), "dec_input")
         fused_cell = os.environ.get("SLNLP_DEC_FUSED", "1") != "0" and dec_prec == 0
         for l in range(L):
             D = E + 2 * H if l == 0 else H
@@ -340,27 +354,39 @@ class RnnEncDecB200(FlatParamModule):
         with small():
             self._gemm(1, 0, V, H, B, ws.dlogits.data_ptr(), ws.Vp, ws.dec_h[L - 1].data_ptr(), H,
                        gp("model.generator.proj.weight"), H, None, 1.0)
+        cell_bwd = ws.dec_cell_bwd
         self._gemm(0, 0, B, H, V, ws.dlogits.data_ptr(), ws.Vp, self._ptr("model.generator.proj.weight"), H,
-                   ws.d_h.data_ptr(), H)
+                   (ws.d_hl[L - 1] if cell_bwd else ws.d_h).data_ptr(), H)
         # decoder cells, top down
         dec_prec = prec if (os.environ.get("SLNLP_DEC_TC", "0") == "1" or B > 256) else 0
         pre = "model.decoder.rnn."
         for l in range(L - 1, -1, -1):
             D = E + 2 * H if l == 0 else H
             h0 = ws.hidden0[l].data_ptr()
-            dg, dst = ws.dec_gates[l].data_ptr(), ws.dec_stash[l].data_ptr()
-            check(lib.slnlp_rnn_layer_bwd(mode, dec_prec, 1, B, H, 1, dg, dst, ws.dec_h[l].data_ptr(),
-                                          self._ptr(f"{pre}weight_hh_l{l}"), None, h0, h0 if mode == 0 else None,
-                                          ws.d_h.data_ptr(), None, None, ws.d_hidden0[l].data_ptr(),
-                                          ws.d_c0.data_ptr() if mode == 0 else None, ws.carry.data_ptr(), s),
-                  "rnn_layer_bwd(dec)")
-            if mode == 0:  # LSTM: c0 = h0 = hidden0 (bkp:278-279)
-                check(lib.slnlp_axpy(ws.d_hidden0[l].data_ptr(), ws.d_c0.data_ptr(), 1.0, B * H, s), "axpy")
             xin = ws.dec_xin[l].data_ptr()
-            dx = ws.d_decx if l == 0 else ws.d_h
             # d(input) of the cell; for l > 0 the input was dropout(h_{l-1}): the mask rides in the epilogue
             ddrop = (self.p_rnn, rng, 100 + l - 1) if (l > 0 and drop) else None
-            self._gemm(0, 0, B, D, GH, dg, GH, self._ptr(f"{pre}weight_ih_l{l}"), D, dx.data_ptr(), D, drop=ddrop)
+            if cell_bwd:
+                # gate gradients, d(h0) (+ d(c0): c0 = h0 = hidden0, bkp:278-279) and d(input) of the cell: one launch
+                dg = ws.dec_dg[l].data_ptr()
+                dst = ws.dec_dnh[l].data_ptr() if mode != 0 else None
+                dx = ws.d_decx if l == 0 else ws.d_hl[l - 1]
+                check(lib.slnlp_dec_cell_bwd(mode, B, H, D, ws.dec_gates[l].data_ptr(), ws.dec_stash[l].data_ptr(), h0,
+                                             h0 if mode == 0 else None, ws.d_hl[l].data_ptr(),
+                                             self._ptr(f"{pre}weight_ih_l{l}"), self._ptr(f"{pre}weight_hh_l{l}"), dg, dst,
+                                             dx.data_ptr(), ws.d_hidden0[l].data_ptr(), self.p_rnn if ddrop else 0.0,
+                                             rng if ddrop else None, 100 + l - 1 if ddrop else 0, s), "dec_cell_bwd")
+            else:
+                dg, dst = ws.dec_gates[l].data_ptr(), ws.dec_stash[l].data_ptr()
+                check(lib.slnlp_rnn_layer_bwd(mode, dec_prec, 1, B, H, 1, dg, dst, ws.dec_h[l].data_ptr(),
+                                              self._ptr(f"{pre}weight_hh_l{l}"), None, h0, h0 if mode == 0 else None,
+                                              ws.d_h.data_ptr(), None, None, ws.d_hidden0[l].data_ptr(),
+                                              ws.d_c0.data_ptr() if mode == 0 else None, ws.carry.data_ptr(), s),
+                      "rnn_layer_bwd(dec)")
+                if mode == 0:  # LSTM: c0 = h0 = hidden0 (bkp:278-279)
+                    check(lib.slnlp_axpy(ws.d_hidden0[l].data_ptr(), ws.d_c0.data_ptr(), 1.0, B * H, s), "axpy")
+                dx = ws.d_decx if l == 0 else ws.d_h
+                self._gemm(0, 0, B, D, GH, dg, GH, self._ptr(f"{pre}weight_ih_l{l}"), D, dx.data_ptr(), D, drop=ddrop)
             with small():
                 ss = _stream()
                 self._gemm(1, 0, GH, D, B, dg, GH, xin, D, gp(f"{pre}weight_ih_l{l}"), D, None, 1.0)
@@ -379,25 +405,41 @@ class RnnEncDecB200(FlatParamModule):
             drow = gp("model.trg_embed.weight") + 4 * self.bos_idx * E
         else:
             drow = ws.scratch_row.data_ptr()  # padding_idx row gets no gradient
-        check(lib.slnlp_dec_input_bwd(ws.d_decx.data_ptr(), drow, ws.d_ctx.data_ptr(), B, E, 2 * H, s), "dec_input_bwd")
-        # attention
         enc_out = ws.enc_filled
         att = "model.decoder.attention."
-        check(lib.slnlp_attn_step_bwd(ws.d_ctx.data_ptr(), ws.q.data_ptr(), ws.pk.data_ptr(),
-                                      self._ptr(att + "energy_layer.weight"), enc_out.data_ptr(),
-                                      ws.alpha.data_ptr(), T, B, H, 2 * H, ws.d_seq.data_ptr(), ws.d_pk.data_ptr(),
-                                      ws.d_q.data_ptr(), ws.dv_part.data_ptr(), s), "attn_bwd")
+        if ws.dec_head_bwd:
+            # the bos row's gradient is a leaf (side lane); attention -> query -> tanh' -> bridge backward read d(ctx)
+            # in place from d(decoder input): one launch, one CTA per sequence
+            with small():
+                check(lib.slnlp_dec_input_bwd(ws.d_decx.data_ptr(), drow, ws.d_ctx.data_ptr(), B, E, 2 * H, _stream()),
+                      "dec_input_bwd")
+            check(lib.slnlp_dec_head_bwd(T, B, H, L, E, ws.d_decx.data_ptr(), ws.q.data_ptr(), ws.pk.data_ptr(),
+                                         self._ptr(att + "energy_layer.weight"), enc_out.data_ptr(), ws.alpha.data_ptr(),
+                                         ws.hidden0.data_ptr(),
+                                         self._ptr(att + "query_layer.weight") if ws.fuse_query else None,
+                                         self._ptr("model.decoder.bridge.weight") if ws.fuse_bridge else None,
+                                         ws.d_seq.data_ptr(), ws.d_pk.data_ptr(), ws.d_q.data_ptr(), ws.dv_part.data_ptr(),
+                                         ws.d_hidden0.data_ptr(), ws.d_enc_final.data_ptr(), s), "dec_head_bwd")
+        else:
+            check(lib.slnlp_dec_input_bwd(ws.d_decx.data_ptr(), drow, ws.d_ctx.data_ptr(), B, E, 2 * H, s), "dec_input_bwd")
+            # attention
+            check(lib.slnlp_attn_step_bwd(ws.d_ctx.data_ptr(), ws.q.data_ptr(), ws.pk.data_ptr(),
+                                          self._ptr(att + "energy_layer.weight"), enc_out.data_ptr(),
+                                          ws.alpha.data_ptr(), T, B, H, 2 * H, ws.d_seq.data_ptr(), ws.d_pk.data_ptr(),
+                                          ws.d_q.data_ptr(), ws.dv_part.data_ptr(), s), "attn_bwd")
         # d(encoder output) through the key projection: only the encoder BPTT waits for it - a side lane under
         # capture, next to query -> tanh' -> bridge
         with self._side_branch(2):
             self._gemm(0, 0, T * B, 2 * H, H, ws.d_pk.data_ptr(), H, self._ptr(att + "key_layer.weight"), 2 * H,
                        ws.d_seq.data_ptr(), 2 * H, None, 1.0, big=True)
-        self._gemm(0, 0, B, H, H, ws.d_q.data_ptr(), H, self._ptr(att + "query_layer.weight"), H,
-                   ws.d_hidden0[L - 1].data_ptr(), H, None, 1.0)
+        if not ws.fuse_query:
+            self._gemm(0, 0, B, H, H, ws.d_q.data_ptr(), H, self._ptr(att + "query_layer.weight"), H,
+                       ws.d_hidden0[L - 1].data_ptr(), H, None, 1.0)
         # bridge
-        check(lib.slnlp_tanh_bwd(ws.d_hidden0.data_ptr(), ws.hidden0.data_ptr(), L * B * H, s), "tanh_bwd")
-        self._gemm(0, 0, L * B, 2 * H, H, ws.d_hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.weight"),
-                   2 * H, ws.d_enc_final.data_ptr(), 2 * H)
+        if not ws.fuse_bridge:
+            check(lib.slnlp_tanh_bwd(ws.d_hidden0.data_ptr(), ws.hidden0.data_ptr(), L * B * H, s), "tanh_bwd")
+            self._gemm(0, 0, L * B, 2 * H, H, ws.d_hidden0.data_ptr(), H, self._ptr("model.decoder.bridge.weight"),
+                       2 * H, ws.d_enc_final.data_ptr(), 2 * H)
         with small():
             ss = _stream()
             check(lib.slnlp_colsum_f32(ws.dv_part.data_ptr(), B, H, H, gp(att + "energy_layer.weight"), 1.0, ss), "colsum")
@@ -679,10 +721,37 @@ class _Workspace:
         self.dec_h = [f(1, B, H) for _ in range(L)]
         self.dec_xin = [f(B, E + 2 * H)] + [f(B, H) if drop else self.dec_h[l - 1] for l in range(1, L)]
         self.logits, self.logp = f(B, V), f(B, V)
+        # the decoder side at the reference's batch sizes as per-sequence fused kernels (dec_head.cu, dec_cell.cu):
+        # head = attention -> decoder input in one launch (backward: the attention reads d(ctx) in place from d(decoder
+        # input), the bos row's gradient is a leaf on a side lane); cell_bwd = one launch per decoder layer instead of
+        # step kernels + axpy + d(input) GEMM + split-K reduce + dropout.  $SLNLP_DEC_HEAD_FUSE=1 also folds the query
+        # (H <= 256) and bridge (H <= 128) products into the head kernels, one CTA per sequence: measured SLOWER at the
+        # reference's batch (cfg1 0.381 -> 0.398 ms/step: the head then waits for the key projection, which ran NEXT to
+        # bridge -> tanh -> query before, and 32 warps re-reading 192 KB of weights per sequence cost what the two
+        # 6 us GEMM launches did) - kept for the parity test and the record, off by default
+        mode = MODE[m.rnn_type]
+        small = B <= 256
+        self.fuse_query = (small and H <= 256 and os.environ.get("SLNLP_DEC_HEAD", "1") != "0" and
+                           os.environ.get("SLNLP_DEC_HEAD_FUSE", "0") == "1")
+        self.fuse_bridge = self.fuse_query and H <= 128
+        self.dec_head = (small and os.environ.get("SLNLP_DEC_HEAD", "1") != "0" and
+                         bool(lib.slnlp_dec_head_supported(T, B, H, L, int(self.fuse_query), int(self.fuse_bridge))))
+        if not self.dec_head:
+            self.fuse_query = self.fuse_bridge = False
+        # the backward twin without the two products is attn_step_bwd reading d(ctx) in place
+        self.dec_head_bwd = self.dec_head and (self.fuse_query or os.environ.get("SLNLP_DEC_HEAD_BWD", "0") == "1")
+        self.dec_cell_bwd = (small and os.environ.get("SLNLP_DEC_CELL_BWD", "1") != "0" and
+                             os.environ.get("SLNLP_DEC_TC", "0") != "1" and os.environ.get("SLNLP_DEC_FUSED", "1") != "0" and
+                             all(bool(lib.slnlp_dec_cell_bwd_supported(mode, B, H, E + 2 * H if l == 0 else H))
+                                 for l in range(L)))
         if bwd:
             self.Vp = (V + 3) & ~3                    # row stride of dlogits: 16-byte rows keep its GEMMs on TMA
             self.dlogits = torch.zeros(B, self.Vp, device=dev)
             self.d_h, self.d_c0 = f(B, H), f(B, H)
+            if self.dec_cell_bwd:     # d(h_1) per layer (a layer's d(input) must not overwrite what its own CTAs still read)
+                self.d_hl = [f(B, H) for _ in range(L)]
+                self.dec_dg = [f(B, G, H) for _ in range(L)]
+                self.dec_dnh = [f(B, H) if G == 3 else None for _ in range(L)]
             self.d_decx, self.d_ctx = f(B, E + 2 * H), f(B, 2 * H)
             self.d_seq = f(T, B, 2 * H)       # d enc_out / d layer outputs (reused down the stack)
             self.d_pk, self.d_q, self.dv_part = f(T, B, H), f(B, H), f(B, H)

@@ -350,3 +350,44 @@ def test_large_batch_path_with_dropout_matches_the_fp32_path_on_the_same_masks()
     for k in sd32:
         err = float((sd16[k] - sd32[k]).abs().max()) / max(float(sd32[k].abs().max()), 1e-3)
         assert err < BF16_RTOL, k
+
+
+@pytest.mark.parametrize("kind,E,H,L,B,T,dropout,precision", [
+    ("lstm", 128, 128, 2, 50, 64, 0.1, "fp32"),     # cfg1: bridge + query fused, both decoder cells
+    ("lstm", 128, 128, 2, 50, 64, 0.1, "bf16"),
+    ("gru", 64, 96, 3, 37, 20, 0.2, "fp32"),        # GRU gate gradients (x / h halves of the candidate gate), ragged rows
+    ("lstm", 256, 256, 2, 50, 33, 0.1, "bf16"),     # query fused, bridge on the GEMM; K = 1024: two chunks
+    ("gru", 48, 512, 1, 9, 12, 0.0, "fp32"),        # neither product fused; GH = 1536: a ragged last chunk
+    ("lstm", 24, 20, 3, 6, 7, 0.3, "fp32"),         # H % 16 != 0: cells stay on the step kernels, scalar weight rows
+])
+def test_decoder_fused_kernels_match_the_unfused_chain(monkeypatch, kind, E, H, L, B, T, dropout, precision):
+    """dec_head.cu (bridge -> tanh -> query -> attention -> decoder input, and its backward twin) and the one-launch
+    decoder-cell backward of dec_cell.cu against the chain of GEMM / element-wise / step kernels they replace: same
+    weights, same batch, same dropout masks (same seed and sites) - log-probs and every parameter gradient."""
+    import model as dropin
+    from slnlp_b200.vocab import Vocab
+    Vs, Vt = 300, 40
+    cls = dropin.EncoderDecoderLSTMAttn if kind == "lstm" else dropin.EncoderDecoderGRUAttn
+    X, lengths, y = _synthetic(B, T, Vs, Vt, ragged=True)
+    X, lengths, y = X.cuda(), lengths.cuda(), y.cuda()
+    out = {}
+    for fused in ("1", "2", "0"):       # 1: the default fused kernels; 2: + query / bridge products inside the head kernels
+        monkeypatch.setenv("SLNLP_DEC_HEAD", "0" if fused == "0" else "1")
+        monkeypatch.setenv("SLNLP_DEC_CELL_BWD", "0" if fused == "0" else "1")
+        monkeypatch.setenv("SLNLP_DEC_HEAD_FUSE", "1" if fused == "2" else "0")
+        torch.manual_seed(5)
+        m = cls(src_vocab=Vocab(size=Vs), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E, hidden_size=H,
+                num_layers=L, dropout=dropout, device=torch.device("cuda"), seed=11, precision=precision)
+        m = m.to(torch.device("cuda"))
+        m.train()
+        logp = m(X=X, y=y, lengths=lengths)
+        torch.nn.functional.cross_entropy(logp, y, ignore_index=1).backward()
+        out[fused] = (logp.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+    # the fused kernels are fp32 FMA; the chain runs tf32 MMAs on the tensor-core path
+    tol = 2e-5 if precision == "fp32" else 5e-3
+    scale = max(float(v.abs().max()) for v in out["0"][1].values())
+    for fused in ("1", "2"):
+        assert rel_err(out[fused][0], out["0"][0]) < tol
+        assert set(out[fused][1]) == set(out["0"][1])
+        for k, ref in out["0"][1].items():
+            assert grad_rel_err(out[fused][1][k], ref, scale) < (5e-5 if precision == "fp32" else 2e-2), (fused, k)
