@@ -427,13 +427,14 @@ extern "C" int slnlp_dec_cell_bwd(int mode, int B, int H, int D, const float* ga
   DecCellBwd p{B, H, D, gates, stash, h0, c0, dh, w_ih, w_hh, dgx, dnh, dx, dh0, p_drop, rng, site};
   const dim3 grid((D + H) / CB_NC, ceil_div(B, CB_BB));
   const size_t sm = (size_t)((CB_BB + CB_NC) * CB_LD + 5 * CB_BB * CB_NC) * sizeof(float);
-  if (mode == SLNLP_MODE_LSTM) {
+  static bool attr = false;
+  if (!attr) {
     cudaFuncSetAttribute(dec_cell_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    launch_pdl(dec_cell_bwd_kernel<4>, grid, dim3(CB_THREADS), sm, as_stream(stream), p);
-  } else {
     cudaFuncSetAttribute(dec_cell_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    launch_pdl(dec_cell_bwd_kernel<3>, grid, dim3(CB_THREADS), sm, as_stream(stream), p);
+    attr = true;
   }
+  if (mode == SLNLP_MODE_LSTM) launch_pdl(dec_cell_bwd_kernel<4>, grid, dim3(CB_THREADS), sm, as_stream(stream), p);
+  else launch_pdl(dec_cell_bwd_kernel<3>, grid, dim3(CB_THREADS), sm, as_stream(stream), p);
   SLNLP_LAUNCH_OK("dec_cell_bwd");
   return 0;
 }

@@ -281,6 +281,12 @@ static int gemm_tma_launch(bool x3, int transA, int transB, int M, int N, int K,
     if (splits > K / 128) splits = K / 128;
     while (splits > 1 && (int64_t)splits * M * N > workspace_floats) --splits;
     if (splits < 1) splits = 1;
+    // $SLNLP_SPLITK_MAX caps the K-slices of one product (tuning knob of profiles/bench_gemm_dw.py: the default
+    // 2 * SMs / tiles measured best - 7.5 us for dW_ih [1024 x 128, K 3200] against 22.6 unsplit)
+    if (const char* e = getenv("SLNLP_SPLITK_MAX")) {
+      const int cap = atoi(e);
+      if (cap >= 1 && splits > cap) splits = cap;
+    }
   }
   // fp32-accurate mode: at most 512 of K per accumulator (see below) - longer reductions are split even when the
   // tile grid is full: in place for gradient accumulations, through the workspace + one reduce launch otherwise
