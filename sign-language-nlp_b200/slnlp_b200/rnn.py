@@ -740,9 +740,14 @@ class _Workspace:
             self.fuse_query = self.fuse_bridge = False
         # the backward twin without the two products is attn_step_bwd reading d(ctx) in place
         self.dec_head_bwd = self.dec_head and (self.fuse_query or os.environ.get("SLNLP_DEC_HEAD_BWD", "0") == "1")
-        self.dec_cell_bwd = (small and os.environ.get("SLNLP_DEC_CELL_BWD", "1") != "0" and
+        # (the one-launch cell backward pays while a layer's contraction G*H x (D + H) stays within 2^18 weights: cfg1
+        # 0.379 -> 0.368 ms/step; at GRU 512 / 256 - 768 x 1280 and 768 x 512 - it measured 29.7 us per launch and the
+        # step 1.782 -> 1.827 ms: those shapes keep the step kernels + tensor-core GEMM.  $SLNLP_DEC_CELL_BWD=2 forces it)
+        env_cb = os.environ.get("SLNLP_DEC_CELL_BWD", "1")
+        self.dec_cell_bwd = (small and env_cb != "0" and
                              os.environ.get("SLNLP_DEC_TC", "0") != "1" and os.environ.get("SLNLP_DEC_FUSED", "1") != "0" and
-                             all(bool(lib.slnlp_dec_cell_bwd_supported(mode, B, H, E + 2 * H if l == 0 else H))
+                             all(bool(lib.slnlp_dec_cell_bwd_supported(mode, B, H, E + 2 * H if l == 0 else H)) and
+                                 (env_cb == "2" or G * H * ((E + 2 * H if l == 0 else H) + H) <= (1 << 18))
                                  for l in range(L)))
         if bwd:
             self.Vp = (V + 3) & ~3                    # row stride of dlogits: 16-byte rows keep its GEMMs on TMA

@@ -373,7 +373,7 @@ def test_decoder_fused_kernels_match_the_unfused_chain(monkeypatch, kind, E, H, 
     out = {}
     for fused in ("1", "2", "0"):       # 1: the default fused kernels; 2: + query / bridge products inside the head kernels
         monkeypatch.setenv("SLNLP_DEC_HEAD", "0" if fused == "0" else "1")
-        monkeypatch.setenv("SLNLP_DEC_CELL_BWD", "0" if fused == "0" else "1")
+        monkeypatch.setenv("SLNLP_DEC_CELL_BWD", "0" if fused == "0" else "2")      # 2: at every supported shape
         monkeypatch.setenv("SLNLP_DEC_HEAD_FUSE", "1" if fused == "2" else "0")
         torch.manual_seed(5)
         m = cls(src_vocab=Vocab(size=Vs), tgt_vocab=Vocab(size=Vt), batch_first=True, embedding_size=E, hidden_size=H,
