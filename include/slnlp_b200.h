@@ -418,6 +418,11 @@ int slnlp_layernorm_bwd(const float* dy, const float* x, const float* res, const
 int slnlp_relu_fwd(float* x, int64_t n, slnlp_stream_t stream);
 /* dx = dy * (y > 0) in place on dy */
 int slnlp_relu_bwd(float* dy, const float* y, int64_t n, slnlp_stream_t stream);
+/* x = dropout(relu(x), p) in place, one pass, with the mask slnlp_dropout(site) draws (nn.TransformerEncoderLayer /
+ * DecoderLayer: linear2(dropout(relu(linear1(x)))), model/transformer.py:40-45); and its backward
+ * dy = y > 0 ? dy / (1 - p) : 0 on the stored y (positive exactly where the unit was active and kept: no random numbers). */
+int slnlp_relu_dropout_fwd(float* x, int64_t n, float p, const uint64_t* rng, uint32_t site, slnlp_stream_t stream);
+int slnlp_relu_dropout_bwd(float* dy, const float* y, int64_t n, float p, slnlp_stream_t stream);
 
 #ifdef __cplusplus
 }

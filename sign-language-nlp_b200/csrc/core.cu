@@ -497,6 +497,32 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(float* dy, const float* _
        i += (int64_t)gridDim.x * blockDim.x)
     dy[i] = y[i] > 0.f ? dy[i] : 0.f;
 }
+// y = dropout(relu(x), p) in place with the mask slnlp_dropout(site) draws (Philox block = 4 consecutive elements): the
+// FFN's activation + dropout as ONE pass (nn.TransformerEncoderLayer: linear2(dropout(relu(linear1(x)))))
+__global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(float* __restrict__ x, int64_t n, float p,
+                                                               const uint64_t* __restrict__ rng, uint32_t site) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const uint64_t seed = rng[0], step = rng[1];
+  const float keep = 1.f - p, inv = 1.f / (1.f - p);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += (int64_t)gridDim.x * blockDim.x) {
+    float u[4];
+    philox_uniform4(seed, step, site, (uint64_t)q, u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = q * 4 + j;
+      if (i < n) x[i] = u[j] < keep ? fmaxf(x[i], 0.f) * inv : 0.f;
+    }
+  }
+}
+// d x of the same: y > 0 exactly where the unit was active AND kept, so the backward needs no random numbers
+__global__ void __launch_bounds__(256) relu_scaled_bwd_kernel(float* dy, const float* __restrict__ y, float scale, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dy[i] = y[i] > 0.f ? dy[i] * scale : 0.f;
+}
 __global__ void __launch_bounds__(256) axpy_kernel(float* y, const float* __restrict__ x, float a, int64_t n) {
   pdl_wait();
   pdl_launch_dependents();
@@ -713,6 +739,20 @@ int slnlp_relu_bwd(float* dy, const float* y, int64_t n, slnlp_stream_t stream) 
   if (n == 0) return 0;
   launch_pdl(relu_bwd_kernel, dim3(ew_grid(n)), dim3(256), 0, as_stream(stream), dy, y, n);
   SLNLP_LAUNCH_OK("relu_bwd");
+  return 0;
+}
+int slnlp_relu_dropout_fwd(float* x, int64_t n, float p, const uint64_t* rng, uint32_t site, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(x && rng && n >= 0 && p >= 0.f && p < 1.f, "relu_dropout_fwd: bad arguments");
+  if (n == 0) return 0;
+  launch_pdl(relu_dropout_fwd_kernel, dim3(ew_grid((n + 3) / 4)), dim3(256), 0, as_stream(stream), x, n, p, rng, site);
+  SLNLP_LAUNCH_OK("relu_dropout_fwd");
+  return 0;
+}
+int slnlp_relu_dropout_bwd(float* dy, const float* y, int64_t n, float p, slnlp_stream_t stream) {
+  SLNLP_CHECK_ARG(dy && y && n >= 0 && p >= 0.f && p < 1.f, "relu_dropout_bwd: bad arguments");
+  if (n == 0) return 0;
+  launch_pdl(relu_scaled_bwd_kernel, dim3(ew_grid(n)), dim3(256), 0, as_stream(stream), dy, y, 1.f / (1.f - p), n);
+  SLNLP_LAUNCH_OK("relu_dropout_bwd");
   return 0;
 }
 int slnlp_axpy(float* y, const float* x, float a, int64_t n, slnlp_stream_t stream) {

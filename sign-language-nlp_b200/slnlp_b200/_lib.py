@@ -67,6 +67,8 @@ SIGNATURES = {
     "slnlp_tanh_bwd": [P, P, L, P],
     "slnlp_relu_fwd": [P, L, P],
     "slnlp_relu_bwd": [P, P, L, P],
+    "slnlp_relu_dropout_fwd": [P, L, F, P, U32, P],
+    "slnlp_relu_dropout_bwd": [P, P, L, F, P],
     "slnlp_dropout": [P, P, L, F, P, U32, P],
     "slnlp_rng_advance": [P, P],
     "slnlp_dropout_mask": [P, L, F, P, U32, P],

@@ -169,8 +169,11 @@ class TransformerB200(FlatParamModule):
         """st.hdn = dropout(relu(x W1^T + b1)); st.f = dropout(hdn W2^T + b2)"""
         E, F = self.E, self.F
         self._lin_fwd(x, rows, pre + "linear1.weight", pre + "linear1.bias", st.hdn.data_ptr(), F, E, big=big)
-        check(lib.slnlp_relu_fwd(st.hdn.data_ptr(), rows * F, _stream()), "relu")
-        self._drop(ws, st.hdn.data_ptr(), rows * F, site)
+        if ws.train and self.p_drop > 0.0:     # activation + dropout: one pass
+            check(lib.slnlp_relu_dropout_fwd(st.hdn.data_ptr(), rows * F, self.p_drop, self._rng_state().data_ptr(), site,
+                                             _stream()), "relu_dropout")
+        else:
+            check(lib.slnlp_relu_fwd(st.hdn.data_ptr(), rows * F, _stream()), "relu")
         self._lin_fwd(st.hdn.data_ptr(), rows, pre + "linear2.weight", pre + "linear2.bias", st.f.data_ptr(), E, F, big=big)
         self._drop(ws, st.f.data_ptr(), rows * E, site + 1)
 
@@ -185,8 +188,10 @@ class TransformerB200(FlatParamModule):
         else:
             dfp = dsum
         self._lin_bwd(g, dfp, st.hdn.data_ptr(), rows, pre + "linear2.weight", pre + "linear2.bias", dhdn, E, F, 0.0, big=big)
-        self._drop(ws, dhdn, rows * F, site)
-        check(lib.slnlp_relu_bwd(dhdn, st.hdn.data_ptr(), rows * F, _stream()), "relu_bwd")
+        if ws.train and self.p_drop > 0.0:     # st.hdn > 0 exactly where the unit was active and kept
+            check(lib.slnlp_relu_dropout_bwd(dhdn, st.hdn.data_ptr(), rows * F, self.p_drop, _stream()), "relu_dropout_bwd")
+        else:
+            check(lib.slnlp_relu_bwd(dhdn, st.hdn.data_ptr(), rows * F, _stream()), "relu_bwd")
         self._lin_bwd(g, dhdn, x, rows, pre + "linear1.weight", pre + "linear1.bias", dsum, F, E, 1.0, big=big)
 
     # ------------------------------------------------------------------ forward
