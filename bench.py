@@ -724,7 +724,7 @@ def grid_search(env, args, w=None):
     y = ds.y().to_array()
     gs = GridSearchFarm(net, grid, cv=5, scoring=h.build_scoring("neg_log_loss", ds.labels(), allow_multiple=False),
                         refit=False, backend="torchrun" if world > 1 else "inline", per_fit_checkpoint_dirs=False,
-                        fits_per_gpu=args.fits_per_gpu)
+                        fits_per_gpu=args.fits_per_gpu, procs_per_gpu=args.procs_per_gpu if world == 1 else 1)
     l0 = _lib.lib.slnlp_launch_count()
     env.barrier()
     t0 = time.perf_counter()
@@ -743,9 +743,13 @@ def grid_search(env, args, w=None):
             "epochs_per_fit": args.grid_epochs, "sequences": args.grid_seqs, "batch": w["B"],
             "train_steps_per_fit": steps_per_fit, "seq_len": w["T"], "v_src": w["Vs"], "v_tgt": w["Vt"],
             "early_stopping": "off (fixed epochs)", "fits_per_gpu": args.fits_per_gpu,
-            "parallelism": f"{world} rank(s), one per GPU, x {args.fits_per_gpu} fit(s) at a time per GPU (threads, private streams, "
-                           "one captured step graph each), longest-first, fits claimed from a store counter, no collective",
-            "gpu_launches_rank0": int(_lib.lib.slnlp_launch_count() - l0),
+            "procs_per_gpu": args.procs_per_gpu if world == 1 else 1,
+            "parallelism": (f"{world} rank(s), one per GPU, x {args.fits_per_gpu} fit(s) at a time per GPU (threads, private streams, "
+                            "one captured step graph each), longest-first, fits claimed from a store counter, no collective"
+                            if (world > 1 or args.procs_per_gpu <= 1) else
+                            f"1 GPU shared by {args.procs_per_gpu} worker processes x {args.fits_per_gpu} fit(s) at a time each (threads, "
+                            "private streams, one captured step graph each), longest-first from one task queue, no collective"),
+            "gpu_launches_rank0": int(_lib.lib.slnlp_launch_count() - l0) + int(getattr(gs, "worker_launches_", 0)),
             "worker_busy_seconds": {str(k): round(v, 2) for k, v in sorted(busy.items())},
             "best_params": {k: v for k, v in gs.best_params_.items()}, "best_score": gs.best_score_,
             "mean_test_score": [float(v) for v in gs.cv_results_["mean_test_score"]]}
@@ -800,6 +804,8 @@ def main():
                                                                       "(default: the slice as a sub-record, the full grid for --workload cfg5)")
     ap.add_argument("--fits-per-gpu", type=int, default=int(os.environ.get("SLNLP_FITS_PER_GPU", "4")),
                     help="cfg5: fits packed on each GPU (worker threads, private streams)")
+    ap.add_argument("--procs-per-gpu", type=int, default=int(os.environ.get("SLNLP_PROCS_PER_GPU", "1")),
+                    help="cfg5, one GPU: worker processes sharing the GPU, each with --fits-per-gpu threads")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.batch:

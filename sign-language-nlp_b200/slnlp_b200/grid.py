@@ -117,19 +117,25 @@ def _worker_main(gpu, task_q, result_q, payload_bytes, fits_per_gpu=1):
     """One process per GPU; fits_per_gpu threads inside it (each ends on its own None sentinel)."""
     _pack_env(fits_per_gpu)
     if fits_per_gpu <= 1:
-        return _worker_loop(gpu, task_q, result_q, payload_bytes, False)
-    threads = [threading.Thread(target=_worker_loop, args=(gpu, task_q, result_q, payload_bytes, True), daemon=True)
-               for _ in range(fits_per_gpu)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+        _worker_loop(gpu, task_q, result_q, payload_bytes, False)
+    else:
+        threads = [threading.Thread(target=_worker_loop, args=(gpu, task_q, result_q, payload_bytes, True), daemon=True)
+                   for _ in range(fits_per_gpu)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    try:        # this process's kernel launches, for the parent's account (bench.py's gpu_launches claim)
+        from ._lib import lib
+        result_q.put((-2, {"launches": int(lib.slnlp_launch_count())}, None))
+    except Exception:
+        pass
 
 
 class GridSearchFarm:
     def __init__(self, estimator, param_grid, *, scoring=None, n_jobs=None, refit=True, cv=None, verbose=0,
                  pre_dispatch=None, error_score="raise", return_train_score=False, n_gpus=None, backend="auto",
-                 per_fit_checkpoint_dirs=True, resume_file=None, fits_per_gpu=None, random_state=1):
+                 per_fit_checkpoint_dirs=True, resume_file=None, fits_per_gpu=None, random_state=1, procs_per_gpu=None):
         self.estimator, self.param_grid, self.scoring, self.n_jobs = estimator, param_grid, scoring, n_jobs
         self.refit, self.cv, self.verbose, self.pre_dispatch = refit, cv, verbose, pre_dispatch
         self.error_score, self.return_train_score = error_score, return_train_score
@@ -139,6 +145,12 @@ class GridSearchFarm:
         # the whole grid on any failure, helper.py:162, and has no resume - SURVEY.md section 5)
         self.resume_file = resume_file
         self.fits_per_gpu = fits_per_gpu
+        # procs_per_gpu worker PROCESSES share each GPU, each with fits_per_gpu threads (spawn / inline backends; the torchrun
+        # backend keeps one process per rank).  The idea: a small fit is a few ms of GPU work inside ~50 ms of Python, and
+        # threads of one process queue for its interpreter lock.  MEASURED on one B200 without MPS, full 810-fit cfg5 grid
+        # (profiles/r02_grid_procs_*.json): 1 process x 4 threads 48.3 s; 3 x 4: 57.3 s; 4 x 2: 58.8 s; 6 x 1: 202.9 s - contexts
+        # of different processes time-slice the GPU instead of sharing it, which costs more than the lock.  Default 1.
+        self.procs_per_gpu = procs_per_gpu
         # every fit is seeded from (random_state, candidate, fold): the reference seeds the process once
         # (main.py:21, seed 1) and its fits then draw from whatever the worker's RNG holds; None restores that
         self.random_state = random_state
@@ -181,10 +193,15 @@ class GridSearchFarm:
             results = self._run_torchrun(cands, folds, tasks, order, X, y, scorer)
         else:
             n = self.n_gpus or (torch.cuda.device_count() if torch.cuda.is_available() else 0)
+            ppg = self._procs_per_gpu()
             if n <= 1 or backend == "inline":
-                results = self._run_inline(cands, folds, tasks, order, X, y, scorer)
+                if ppg > 1:      # one GPU (the current device) or none, several worker processes on it
+                    gpus = [torch.cuda.current_device()] if torch.cuda.is_available() else [None]
+                    results = self._run_spawn(gpus, cands, folds, tasks, order, X, y, scorer, ppg)
+                else:
+                    results = self._run_inline(cands, folds, tasks, order, X, y, scorer)
             else:
-                results = self._run_spawn(n, cands, folds, tasks, order, X, y, scorer)
+                results = self._run_spawn(list(range(n)), cands, folds, tasks, order, X, y, scorer, ppg)
         results.update(done)
         self.search_time_ = time.perf_counter() - t0
         self.n_fits_ = len(tasks)
@@ -253,6 +270,10 @@ class GridSearchFarm:
         k = self.fits_per_gpu if self.fits_per_gpu is not None else int(os.environ.get("SLNLP_FITS_PER_GPU", "1"))
         return max(1, int(k))
 
+    def _procs_per_gpu(self):
+        p = self.procs_per_gpu if self.procs_per_gpu is not None else int(os.environ.get("SLNLP_PROCS_PER_GPU", "1"))
+        return max(1, int(p))
+
     def _run_packed(self, k, cands, folds, tasks, order, X, y, scorer):
         """One GPU (or none), k fits at a time: worker threads of THIS process on private streams."""
         import torch
@@ -319,13 +340,16 @@ class GridSearchFarm:
                       f"fit {out[t]['fit_time']:.2f}s", flush=True)
         return out
 
-    def _run_spawn(self, n, cands, folds, tasks, order, X, y, scorer):
+    def _run_spawn(self, gpus, cands, folds, tasks, order, X, y, scorer, procs_per_gpu=1):
+        """Worker processes fed by one queue: ``procs_per_gpu`` per entry of ``gpus`` (device indices; None = CPU),
+        fits_per_gpu threads in each."""
         import torch.multiprocessing as mp
         ctx = mp.get_context("spawn")
         task_q, result_q = ctx.Queue(), ctx.Queue()
         payload = pickle.dumps((self.estimator, X, y, scorer))
         k = self._fits_per_gpu()
-        procs = [ctx.Process(target=_worker_main, args=(g, task_q, result_q, payload, k), daemon=True) for g in range(n)]
+        procs = [ctx.Process(target=_worker_main, args=(g, task_q, result_q, payload, k), daemon=True)
+                 for g in gpus for _ in range(max(1, procs_per_gpu))]
         for p in procs:
             p.start()
         for t in order:
@@ -334,11 +358,16 @@ class GridSearchFarm:
         for _ in range(len(procs) * k):      # one sentinel per worker thread
             task_q.put(None)
         out = {}
+        self.worker_launches_, reported = 0, 0
         try:
             while len(out) < len(order):
                 tid, res, err = self._next_result(result_q, procs)
                 if err is not None:
                     raise RuntimeError(f"grid-search fit failed (error_score='raise'):\n{err}")
+                if tid == -2:          # a worker process that ran out of tasks reports its launch count and leaves
+                    self.worker_launches_ += res["launches"]
+                    reported += 1
+                    continue
                 out[tid] = res
                 self._journal(tid, res)
                 if self.verbose:
@@ -351,6 +380,16 @@ class GridSearchFarm:
                     p.terminate()
             raise
         finally:
+            deadline = time.time() + 30
+            while reported < len(procs) and time.time() < deadline and len(out) >= len(order):
+                try:                    # the workers' last words (drained before the joins: a child flushes its queue at exit)
+                    tid, res, _ = result_q.get(timeout=0.5)
+                    if tid == -2:
+                        self.worker_launches_ += res["launches"]
+                        reported += 1
+                except queue.Empty:
+                    if not any(p.is_alive() for p in procs):
+                        break
             for p in procs:
                 p.join(timeout=30)
                 if p.is_alive():

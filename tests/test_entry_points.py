@@ -212,6 +212,21 @@ def test_grid_search_resumes_from_its_journal(tmp_path):
     assert c.n_resumed_ == 9 and c.best_params_ == a.best_params_
 
 
+def test_grid_search_over_several_worker_processes_matches_the_inline_search():
+    """procs_per_gpu = 2 (worker processes fed by one queue, here on the CPU with a scikit-learn estimator) returns the
+    same table as the search run one fit at a time in this process."""
+    from sklearn.linear_model import LogisticRegression
+    rng = np.random.RandomState(1)
+    X = rng.randn(120, 5)
+    y = (X[:, 0] + 0.3 * X[:, 1] > 0).astype(int)
+    grid = {"C": [0.01, 0.1, 1.0, 10.0]}
+    a = GridSearchFarm(LogisticRegression(max_iter=200), grid, cv=3, scoring="accuracy", refit=False, backend="inline").fit(X, y)
+    b = GridSearchFarm(LogisticRegression(max_iter=200), grid, cv=3, scoring="accuracy", refit=False, backend="inline",
+                       procs_per_gpu=2, fits_per_gpu=2).fit(X, y)
+    assert b.n_fits_ == 12 and np.allclose(a.cv_results_["mean_test_score"], b.cv_results_["mean_test_score"])
+    assert b.best_params_ == a.best_params_ and b.worker_launches_ == 0        # no kernels on a CPU-only host
+
+
 def test_product_package_never_imports_the_oracle():
     """The oracle is test infrastructure: nothing under the product package may import it."""
     import re
