@@ -1,13 +1,18 @@
-// K7b: the decoder "head" of the single decode step as ONE kernel per direction of autograd
-// (bkp:268-280 bridge, bkp:304-327 attention, bkp:202-216 decoder input).  At the reference's batch (50) the
-// chain  bridge GEMM -> tanh -> query GEMM -> attention -> [bos embedding || context]  was five dependent
-// launches of 4-8 us each, every one of them launch + round-trip latency (the math is < 1 MFLOP per
-// sequence); backward the same five in reverse.  Every stage is independent per sequence, so one CTA per
-// sequence walks the whole chain: the bridge and query rows are warp-per-output dot products against weights
-// it reads from L2 (W_bridge H x 2H and W_query H x H: 192 KB at H = 128), then the fused attention of
-// attention.cu.  The per-CTA weight reads stop paying when the matrices outgrow a few hundred KB, so both
-// products are optional: w_bridge == NULL -> hidden0 is an input (the caller ran GEMM + tanh),
-// w_query == NULL -> q is an input.  fp32 FMA with full-precision tanhf / expf: serves both precision paths.
+// K7b: the decoder "head" of the single decode step, one kernel per direction of autograd, one CTA per sequence
+// (bkp:304-327 attention, bkp:202-216 decoder input; optionally bkp:268-280 bridge and bkp:312 query).
+//   default form : attention (scores, masked softmax, context) + [bos embedding || context] in one launch; backward twin =
+//                  the attention backward reading d(ctx) in place from d(decoder input).
+//   optional     : the bridge rows (tanh(W_b enc_final + b_b), every layer) and the query row (W_q hidden0[L-1]) of the
+//                  sequence as warp-per-output dot products by the same CTA (w_bridge / w_query != NULL), and their
+//                  backward (d hidden0 += dq W_q, tanh', d enc_final = d hidden0 W_b).
+// Every stage is independent per sequence, which is what made the one-CTA-per-sequence form attractive: at the reference's
+// batch (50) bridge GEMM -> tanh -> query GEMM -> attention -> decoder input are five dependent launches of 2-8 us, all
+// launch and round-trip latency.  MEASURED (profiles/r02_dec_fused_ab.txt): folding the two products in is SLOWER than the
+// launches it removes (cfg1 0.381 -> 0.398 ms/step; 16.0 / 20.0 us per launch against 7.9 / 11.3 without them): the head then
+// waits for the key projection, which ran next to bridge -> tanh -> query before, and 32 warps re-reading 192 KB of weights
+// per sequence and replicating the scalar work cost what two 6 us GEMM launches did.  The callers therefore pass
+// w_bridge = w_query = NULL by default ($SLNLP_DEC_HEAD_FUSE=1 turns the products on; parity-tested either way).
+// fp32 FMA with full-precision tanhf / expf: serves both precision paths.
 #include "common.cuh"
 
 namespace slnlp {
