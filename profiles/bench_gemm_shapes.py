@@ -1,5 +1,5 @@
 """Time every distinct GEMM shape of one cfg1 / cfg2 / cfg3 train step in isolation (CUDA-graph
-replay of 20 calls, L2-warm), for the TMA-fed tf32, the register-staged bf16 and the fp32-FMA kernels:
+replay of 20 calls, L2-warm), for the TMA-fed tf32 and the fp32-FMA kernels:
     python profiles/bench_gemm_shapes.py [cfg1|cfg2|cfg3]
 Prints us per call, achieved TFLOP/s and GB/s of algorithmic bytes 4(MK+KN+MN)."""
 import os, sys
@@ -29,7 +29,7 @@ else:
               ("out dW", 1, 0, E, E, R), ("ffn1 dW", 1, 0, F, E, R), ("ffn2 dW", 1, 0, E, F, R), ("ffn2 dx", 0, 0, R, F, E)]
 ws = torch.empty(L.lib.slnlp_gemm_workspace_floats(), device="cuda")
 S = torch.cuda.current_stream().cuda_stream
-print(f"{'gemm':12s} tA tB {'M':>6} {'N':>6} {'K':>6} | {'tf32/TMA us':>11} {'TF/s':>7} {'GB/s':>7} | {'bf16 us':>8} | {'f32 us':>8}")
+print(f"{'gemm':12s} tA tB {'M':>6} {'N':>6} {'K':>6} | {'tf32/TMA us':>11} {'TF/s':>7} {'GB/s':>7} | {'f32 us':>8}")
 for name, tA, tB, M, N, K in shapes:
     A = torch.randn((K, M) if tA else (M, K), device="cuda")
     Bm = torch.randn((N, K) if tB else (K, N), device="cuda")
@@ -54,4 +54,4 @@ for name, tA, tB, M, N, K in shapes:
         torch.cuda.synchronize()
         res.append(a.elapsed_time(b) * 1e3 / 100)
     fl, by = 2.0 * M * N * K, 4.0 * (M * K + K * N + M * N)
-    print(f"{name:12s} {tA:2d} {tB:2d} {M:6d} {N:6d} {K:6d} | {res[0]:11.2f} {fl / res[0] / 1e6:7.1f} {by / res[0] / 1e3:7.0f} | {res[1]:8.2f} | {res[2]:8.2f}")
+    print(f"{name:12s} {tA:2d} {tB:2d} {M:6d} {N:6d} {K:6d} | {res[0]:11.2f} {fl / res[0] / 1e6:7.1f} {by / res[0] / 1e3:7.0f} | {res[1]:8.2f}")
