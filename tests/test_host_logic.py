@@ -158,3 +158,33 @@ def test_factored_embedding_variant_surface():
                                      hidden_size=16, num_layers=1, dropout=0.0, src_field_vocab_sizes=rows, src_field_widths=widths)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(X=torch.ones(2, 3, 6, dtype=torch.long), y=torch.ones(2, dtype=torch.long), lengths=torch.tensor([3, 3]))
+
+
+def test_decoder_side_kernel_selection(monkeypatch):
+    """Which decoder-side kernels a workspace takes (host logic only, no launch): the one-launch cell backward while every
+    layer's contraction G*H x (D + H) stays within 2^18 weights and H, D are multiples of 16; the head kernel at batches
+    <= 256; the query / bridge products inside it only on request and only up to H = 256 / 128."""
+    import model as dropin
+    from slnlp_b200.rnn import _Workspace
+    from slnlp_b200.vocab import Vocab
+    for k in ("SLNLP_DEC_HEAD", "SLNLP_DEC_HEAD_BWD", "SLNLP_DEC_HEAD_FUSE", "SLNLP_DEC_CELL_BWD", "SLNLP_DEC_TC", "SLNLP_DEC_FUSED"):
+        monkeypatch.delenv(k, raising=False)
+
+    def flags(kind, E, H, L, B=50, T=64):
+        cls = dropin.EncoderDecoderLSTMAttn if kind == "lstm" else dropin.EncoderDecoderGRUAttn
+        m = cls(src_vocab=Vocab(size=100), tgt_vocab=Vocab(size=20), batch_first=True, embedding_size=E, hidden_size=H,
+                num_layers=L, dropout=0.1, device=torch.device("cpu"))
+        ws = _Workspace(m, B, T, True)
+        return dict(head=ws.dec_head, head_bwd=ws.dec_head_bwd, query=ws.fuse_query, bridge=ws.fuse_bridge, cell_bwd=ws.dec_cell_bwd)
+
+    assert flags("lstm", 128, 128, 2) == dict(head=True, head_bwd=False, query=False, bridge=False, cell_bwd=True)     # cfg1
+    assert flags("gru", 512, 256, 4)["cell_bwd"] is False          # cfg2: 768 x 1280 weights per contraction
+    assert flags("lstm", 24, 20, 3)["cell_bwd"] is False           # H % 16 != 0
+    assert flags("lstm", 128, 128, 2, B=4096) == dict(head=False, head_bwd=False, query=False, bridge=False, cell_bwd=False)
+    monkeypatch.setenv("SLNLP_DEC_CELL_BWD", "2")
+    monkeypatch.setenv("SLNLP_DEC_HEAD_FUSE", "1")
+    assert flags("gru", 512, 256, 4) == dict(head=True, head_bwd=True, query=True, bridge=False, cell_bwd=True)
+    assert flags("lstm", 128, 128, 2)["bridge"] is True
+    monkeypatch.setenv("SLNLP_DEC_HEAD", "0")
+    monkeypatch.setenv("SLNLP_DEC_CELL_BWD", "0")
+    assert flags("lstm", 128, 128, 2) == dict(head=False, head_bwd=False, query=False, bridge=False, cell_bwd=False)
