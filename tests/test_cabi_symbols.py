@@ -48,6 +48,27 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc != 0 and "mode" in _lib.last_error()
 
 
+def test_fused_decoder_entry_points_validate_their_arguments_without_a_gpu():
+    from slnlp_b200 import _lib
+    L = _lib.lib
+    assert L.slnlp_dec_cell_bwd_supported(0, 50, 128, 384) == 1 and L.slnlp_dec_cell_bwd_supported(0, 50, 20, 64) == 0
+    assert L.slnlp_dec_head_supported(64, 50, 128, 2, 0, 0) == 1
+    assert L.slnlp_dec_head_supported(64, 50, 128, 2, 0, 1) == 0          # a fused bridge needs the fused query
+    assert L.slnlp_dec_head_supported(64, 50, 512, 6, 1, 1) == 1 and L.slnlp_dec_head_supported(20000, 50, 128, 2, 0, 0) == 0
+    one = 8      # any non-null address: the checks below fail before anything is dereferenced or launched
+    rc = L.slnlp_dec_cell_bwd(0, 50, 20, 64, one, one, one, one, one, one, one, one, None, one, one, 0.0, None, 0, None)
+    assert rc != 0 and "multiples of 16" in _lib.last_error()
+    rc = L.slnlp_dec_cell_bwd(1, 50, 32, 64, one, one, one, None, one, one, one, one, None, one, one, 0.0, None, 0, None)
+    assert rc != 0 and "GRU" in _lib.last_error()
+    rc = L.slnlp_dec_head_fwd(64, 50, 128, 2, 128, None, None, None, None, None, None, None, None, 1, None, None, None, None, None,
+                              None, None)
+    assert rc != 0 and "null" in _lib.last_error()
+    rc = L.slnlp_dec_head_bwd(64, 50, 128, 2, 128, one, one, one, one, one, one, None, None, one, one, one, one, one, None, None, None)
+    assert rc != 0 and "fused bridge" in _lib.last_error()
+    rc = L.slnlp_relu_dropout_fwd(one, 16, 1.5, one, 0, None)
+    assert rc != 0 and "relu_dropout_fwd" in _lib.last_error()
+
+
 def test_library_is_cuda_only_sm100a():
     """The .so carries sm_100a SASS (and nothing for another arch)."""
     import subprocess
